@@ -1,0 +1,159 @@
+"""Loader for ``libgalax_b200.so`` (the C ABI declared in ``include/galax_b200.h``).
+
+There is no CPU fallback: if the library is missing or CUDA is unavailable, every compute entry
+raises.  ``build()`` compiles the library in-tree with nvcc for sm_100a (it cross-compiles on a
+machine without a GPU).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+_SRC = _PKG / "csrc"
+LIB_PATH = _PKG / "libgalax_b200.so"
+HEADER = _PKG.parent / "include" / "galax_b200.h"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]  # fmt: skip
+
+GX_MAX_COMPONENTS = 14
+KIND_MN, KIND_HERNQUIST, KIND_NFW, KIND_PLC = 0, 1, 2, 3
+PHI, GRAD, ACC, HESS = 1, 2, 4, 8
+OK, MAX_STEPS_REACHED, NONFINITE = 0, 1, 2
+SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1
+LAYOUT_NT3, LAYOUT_T3N = 0, 1
+DF_FARDAL15, DF_CHEN24 = 0, 1
+
+
+class GxComponent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 4)]
+
+
+class GxPotential(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("G", C.c_double), ("c", GxComponent * GX_MAX_COMPONENTS)]
+
+
+class GxPid(C.Structure):
+    _fields_ = [
+        ("rtol", C.c_double), ("atol", C.c_double),
+        ("pcoeff", C.c_double), ("icoeff", C.c_double), ("dcoeff", C.c_double),
+        ("safety", C.c_double), ("factormin", C.c_double), ("factormax", C.c_double),
+        ("dtmin", C.c_double), ("dtmax", C.c_double),
+        ("force_dtmin", C.c_int32), ("reserved", C.c_int32),
+        ("dt0", C.c_double),
+    ]  # fmt: skip
+
+
+class GalaxB200Error(RuntimeError):
+    pass
+
+
+def sources() -> list[Path]:
+    return [_SRC / "gx_kernels.cu"]
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    m = LIB_PATH.stat().st_mtime
+    deps = list(_SRC.glob("*.cu")) + list(_SRC.glob("*.cuh")) + list(_SRC.glob("*.h")) + [HEADER]
+    return any(d.stat().st_mtime > m for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile ``libgalax_b200.so`` for sm_100a if it is missing or older than its sources."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        raise GalaxB200Error("nvcc not found: cannot build libgalax_b200.so")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(s) for s in sources()]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    env = dict(os.environ)
+    env.pop("CC", None)  # the image's $CC points at a gcc nvcc cannot drive
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise GalaxB200Error(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "gx_version": (C.c_int, []),
+    "gx_strerror": (C.c_char_p, [C.c_int]),
+    "gx_workspace_bytes": (C.c_int64, []),
+    "gx_potential_eval": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_double, C.c_int64, C.c_uint32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_integrate_fixed": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                     C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_integrate_dopri8": (C.c_int, [C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int64,
+                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_stream_release": (C.c_int, [C.POINTER(GxPotential), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "gx_energy_angmom": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "gx_host_potential_eval": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_double, C.c_int64, C.c_uint32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_host_integrate_fixed": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                          C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_host_integrate_dopri8": (C.c_int, [C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int32,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_bench_dfma": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "gx_debug_math": (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+}  # fmt: skip
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library (loaded once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise GalaxB200Error(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for this path)"
+            )
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().gx_strerror(rc).decode()
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise GalaxB200Error(f"{what}: {msg} (code {rc})")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise GalaxB200Error("galax_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch

@@ -1,0 +1,115 @@
+"""Generate ``gx_tables.h``: Dopri8 (Prince-Dormand RK8(7)13M + FSAL) tables in Nystrom form.
+
+The Hamiltonian field is (dq/dt, dp/dt) = (p, a(q)), so a stage's position only needs the stage
+accelerations a_l:   q_i = q0 + c_i h p0 + h^2 sum_l AA[i][l] a_l,   AA = A @ A.
+Likewise q1 / the q error / the q dense output use  b^T A,  e^T A  and  B(theta)^T A.
+All products are formed in exact rational arithmetic and rounded once.
+
+The tableau itself is typed in here independently of ``oracle/dopri8_tableau.py`` (the oracle is test
+infrastructure and is not imported by product code); ``tests/test_tables.py`` checks that the two agree
+and that this table satisfies the order conditions.
+
+Run:  python galax_b200/csrc/gen_tables.py
+"""
+from fractions import Fraction as F
+from pathlib import Path
+
+A = [
+    [],
+    [F(1, 18)],
+    [F(1, 48), F(1, 16)],
+    [F(1, 32), 0, F(3, 32)],
+    [F(5, 16), 0, F(-75, 64), F(75, 64)],
+    [F(3, 80), 0, 0, F(3, 16), F(3, 20)],
+    [F(29443841, 614563906), 0, 0, F(77736538, 692538347), F(-28693883, 1125000000), F(23124283, 1800000000)],
+    [F(16016141, 946692911), 0, 0, F(61564180, 158732637), F(22789713, 633445777), F(545815736, 2771057229),
+     F(-180193667, 1043307555)],
+    [F(39632708, 573591083), 0, 0, F(-433636366, 683701615), F(-421739975, 2616292301), F(100302831, 723423059),
+     F(790204164, 839813087), F(800635310, 3783071287)],
+    [F(246121993, 1340847787), 0, 0, F(-37695042795, 15268766246), F(-309121744, 1061227803),
+     F(-12992083, 490766935), F(6005943493, 2108947869), F(393006217, 1396673457), F(123872331, 1001029789)],
+    [F(-1028468189, 846180014), 0, 0, F(8478235783, 508512852), F(1311729495, 1432422823),
+     F(-10304129995, 1701304382), F(-48777925059, 3047939560), F(15336726248, 1032824649),
+     F(-45442868181, 3398467696), F(3065993473, 597172653)],
+    [F(185892177, 718116043), 0, 0, F(-3185094517, 667107341), F(-477755414, 1098053517),
+     F(-703635378, 230739211), F(5731566787, 1027545527), F(5232866602, 850066563), F(-4093664535, 808688257),
+     F(3962137247, 1805957418), F(65686358, 487910083)],
+    [F(403863854, 491063109), 0, 0, F(-5068492393, 434740067), F(-411421997, 543043805), F(652783627, 914296604),
+     F(11173962825, 925320556), F(-13158990841, 6184727034), F(3936647629, 1978049680), F(-160528059, 685178525),
+     F(248638103, 1413531060), 0],
+]
+B_SOL = [F(14005451, 335480064), 0, 0, 0, 0, F(-59238493, 1068277825), F(181606767, 758867731),
+         F(561292985, 797845732), F(-1041891430, 1371343529), F(760417239, 1151165299), F(118820643, 751138087),
+         F(-528747749, 2220607170), F(1, 4), 0]
+B_HAT = [F(13451932, 455176623), 0, 0, 0, 0, F(-808719846, 976000145), F(1757004468, 5645159321),
+         F(656045339, 265891186), F(-3867574721, 1518517206), F(465885868, 322736535), F(53011238, 667516719),
+         F(2, 45), 0, 0]
+A.append([B_SOL[j] for j in range(13)])  # FSAL stage
+C = [F(0), F(1, 18), F(1, 12), F(1, 8), F(5, 16), F(3, 8), F(59, 400), F(93, 200), F(5490023248, 9719169821),
+     F(13, 20), F(1201146811, 1299019798), F(1), F(1), F(1)]
+
+# degree-6 continuous extension, b_i(theta) = sum_m DENSE_B[i][m-1] theta^m (see DESIGN.md "Dense output")
+DENSE_B = [
+    [1.0, -6.691018173783315, 19.999006933368626, -30.061056828966635, 22.139650499809203, -6.344834939286462],
+    [0.0] * 6, [0.0] * 6, [0.0] * 6, [0.0] * 6,
+    [0.0, -7.614265804585636, 52.22735327929503, -121.49996277313414, 116.44221495503238, -39.61079198522323],
+    [0.0, 10.729828206995803, -46.89529333174393, 83.17378648512963, -67.14512895979595, 20.376120406616955],
+    [0.0, 0.5010105848592362, -0.08581287575176573, 9.520887022608708, -16.567313740971997, 7.334739678660368],
+    [0.0, 4.352779189231888, -35.97576607870187, 87.9744965874054, -89.99136937851385, 32.880100066764946],
+    [0.0, -0.7606570723149959, 6.469460633091836, -17.512977453034445, 22.62357948159191, -10.15884255841119],
+    [0.0, -1.2356641964061477, 10.26007488020532, -28.56236272873234, 32.23628249753497, -12.54014297009153],
+    [0.0, 4.68718979313984, -33.31834766465918, 80.9399770753902, -82.10232756187993, 29.555398819256105],
+    [0.0, -6.319348569127368, 46.32029783816455, -114.22497801652129, 116.2664567950579, -41.792428047573885],
+    [0.0, 2.3501460419902416, -19.000973613268876, 50.25219062985484, -53.90204458786452, 20.30068152928823],
+]
+
+N = 14
+
+
+def amat():
+    return [[F(A[i][j]) if j < len(A[i]) else F(0) for j in range(N)] for i in range(N)]
+
+
+def tables():
+    Am = amat()
+    AA = [[sum(Am[i][j] * Am[j][l] for j in range(N)) for l in range(N)] for i in range(N)]
+    e = [F(s) - F(h) for s, h in zip(B_SOL, B_HAT)]
+    eA = [sum(e[j] * Am[j][l] for j in range(N)) for l in range(N)]
+    DB = [[F(v) for v in row] for row in DENSE_B]
+    DQ = [[sum(DB[j][m] * Am[j][l] for j in range(N)) for m in range(6)] for l in range(N)]
+    return dict(A=Am, AA=AA, C=C, B=[F(b) for b in B_SOL], E=e, EA=eA, DB=DB, DQ=DQ)
+
+
+def fmt(v):
+    return repr(float(v))
+
+
+def emit():
+    t = tables()
+    out = ["// GENERATED by galax_b200/csrc/gen_tables.py -- do not edit.",
+           "// Dopri8 = Prince-Dormand RK8(7)13M + FSAL stage, Nystrom form for (dq,dp) = (p, a(q)).",
+           "#pragma once", "namespace gx { namespace dp8 {", "constexpr int NS = 14;"]
+
+    def mat(name, M, cols):
+        out.append(f"__device__ constexpr double {name}[{len(M)}][{cols}] = {{")
+        for row in M:
+            out.append("    {" + ", ".join(fmt(v) for v in row) + "},")
+        out.append("};")
+
+    def vec(name, v):
+        out.append(f"__device__ constexpr double {name}[{len(v)}] = {{" + ", ".join(fmt(x) for x in v) + "};")
+
+    mat("A", t["A"], N)      # p-stage weights (only the last row, b_sol, is used by the kernels)
+    mat("AA", t["AA"], N)    # q_i = q0 + CN[i] h p0 + h^2 sum_l AA[i][l] a_l
+    vec("CN", t["C"])
+    vec("B", t["B"])         # p1 = p0 + h sum_l B[l] a_l
+    vec("E", t["E"])         # err_p = h sum_l E[l] a_l
+    vec("EA", t["EA"])       # err_q = h^2 sum_l EA[l] a_l
+    mat("DB", t["DB"], 6)    # p(theta) = p0 + h sum_l (sum_m DB[l][m] theta^(m+1)) a_l
+    mat("DQ", t["DQ"], 6)    # q(theta) = q0 + theta h p0 + h^2 sum_l (sum_m DQ[l][m] theta^(m+1)) a_l
+    out.append("}}  // namespace gx::dp8")
+    Path(__file__).with_name("gx_tables.h").write_text("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    emit()

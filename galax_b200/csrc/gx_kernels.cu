@@ -1,0 +1,859 @@
+// gx_kernels.cu -- sm_100a kernels + C ABI of the galax hot path (see include/galax_b200.h).
+//
+//   K1  k_potential_eval     bulk Phi / grad / acc / Hessian                       (HBM-bound)
+//   K2  k_integrate_fixed    one thread per particle, state in registers,
+//                            SemiImplicitEuler / LeapfrogMidpoint + ConstantStepSize (FP64-pipe-bound)
+//   K3  k_integrate_dopri8   persistent warps, per-lane work queue, per-particle PID step control,
+//                            Dopri8 in Nystrom form with all 14 stage accelerations in registers
+//   K4  k_stream_release     Fardal+15 / Chen+24 release conditions (then K3 with per-particle t0)
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo (no fast-math).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/galax_b200.h"
+#include "gx_potential.cuh"
+#include "gx_tables.h"
+
+namespace gx {
+
+// ================================================================================================
+// host: gx_potential -> DevPot
+// ================================================================================================
+
+enum Model { MODEL_GENERIC = 0, MODEL_MW = 1, MODEL_MW2022 = 2, MODEL_BOVY = 3 };
+
+static int build_devpot(const gx_potential *pot, DevPot &D, Model &model) {
+    if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
+    memset(&D, 0, sizeof D);
+    const double G = pot->G;
+    for (int i = 0; i < pot->n; ++i) {
+        const gx_component &c = pot->c[i];
+        switch (c.kind) {
+        case GX_KIND_MIYAMOTO_NAGAI: {
+            if (D.n_mn >= MAX_MN) return GX_ERR_UNSUPPORTED;
+            DevMN &m = D.mn[D.n_mn++];
+            m.GM = G * c.p[0];
+            m.a = c.p[1];
+            m.b2 = c.p[2] * c.p[2];
+            m.ab2 = c.p[1] * m.b2;
+            break;
+        }
+        case GX_KIND_HERNQUIST: {
+            if (D.n_hern >= MAX_HERN) return GX_ERR_UNSUPPORTED;
+            DevHern &h = D.hern[D.n_hern++];
+            h.GM = G * c.p[0];
+            h.c = c.p[1];
+            break;
+        }
+        case GX_KIND_NFW: {
+            if (D.n_nfw >= MAX_NFW) return GX_ERR_UNSUPPORTED;
+            DevNFW &n = D.nfw[D.n_nfw++];
+            n.GM = G * c.p[0];
+            n.rs = c.p[1];
+            n.inv_rs = 1.0 / c.p[1];
+            n.GM_inv_rs = n.GM / c.p[1];
+            break;
+        }
+        case GX_KIND_POWERLAWCUTOFF: {
+            if (D.n_plc >= MAX_PLC) return GX_ERR_UNSUPPORTED;
+            double alpha = c.p[1], rc = c.p[2];
+            if (!(alpha >= 0.0 && alpha < 2.0)) return GX_ERR_UNSUPPORTED;  // Phi needs Gamma(1 - alpha/2)
+            DevPLC &p = D.plc[D.n_plc++];
+            p.GM = G * c.p[0];
+            p.a = 1.5 - alpha / 2;
+            p.lgam_a = lgamma(p.a);
+            p.inv_rc = 1.0 / rc;
+            p.a2 = 1.0 - alpha / 2;
+            p.lgam_a2 = lgamma(p.a2);
+            p.tail = tgamma(p.a2) / (rc * tgamma(p.a));
+            break;
+        }
+        default:
+            return GX_ERR_UNSUPPORTED;
+        }
+    }
+    model = MODEL_GENERIC;
+    if (D.n_mn == 1 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW;
+    if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW2022;
+    if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1) model = MODEL_BOVY;
+    return 0;
+}
+
+#define GX_DISPATCH_MODEL(model, CALL)                 \
+    switch (model) {                                   \
+    case MODEL_MW: { using C = CountsMW; CALL; } break;         \
+    case MODEL_MW2022: { using C = CountsMW2022; CALL; } break; \
+    case MODEL_BOVY: { using C = CountsBovy; CALL; } break;     \
+    default: { using C = CountsRuntime; CALL; } break;          \
+    }
+
+static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : GX_ERR_CUDA; }
+
+// ================================================================================================
+// K1 bulk evaluation
+// ================================================================================================
+
+struct EvalArgs {
+    const double *xyz;
+    double *phi, *grad, *acc, *hess;
+    long long N;
+    unsigned what;
+};
+
+template <class C>
+__global__ void __launch_bounds__(256) k_potential_eval(const __grid_constant__ DevPot P, const EvalArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += stride) {
+        const double x = __ldg(a.xyz + 3 * i), y = __ldg(a.xyz + 3 * i + 1), z = __ldg(a.xyz + 3 * i + 2);
+        if (a.what & GX_PHI) a.phi[i] = potential_value<C>(P, x, y, z);
+        if (a.what & (GX_GRAD | GX_ACC)) {
+            double g0, g1, g2;
+            gradient<C>(P, x, y, z, g0, g1, g2);
+            if (a.what & GX_GRAD) {
+                a.grad[3 * i] = g0; a.grad[3 * i + 1] = g1; a.grad[3 * i + 2] = g2;
+            }
+            if (a.what & GX_ACC) {
+                a.acc[3 * i] = -g0; a.acc[3 * i + 1] = -g1; a.acc[3 * i + 2] = -g2;
+            }
+        }
+        if (a.what & GX_HESS) {
+            double H[6];
+            hessian<C>(P, x, y, z, H);
+            double *h = a.hess + 9 * i;
+            h[0] = H[0]; h[1] = H[1]; h[2] = H[2];
+            h[3] = H[1]; h[4] = H[3]; h[5] = H[4];
+            h[6] = H[2]; h[7] = H[4]; h[8] = H[5];
+        }
+    }
+}
+
+// ================================================================================================
+// K2 fixed-step integrator
+// ================================================================================================
+
+struct FixedArgs {
+    const double *q0, *p0, *ts;
+    double *q, *p;
+    int *status;
+    long long N, max_steps;
+    long long sn, sk, sc;  // output strides (elements): particle, save, component
+    double t0, t1, dt0;
+    int T;
+};
+
+__device__ __forceinline__ double clip_to_end(double tprev, double tnext, double t1, bool keep) {
+    // diffrax _clip_to_end (fp64 tolerance 1e-10)
+    if (tnext > t1 - 1e-10) return keep ? t1 : tprev + 0.5 * (t1 - tprev);
+    return tnext;
+}
+
+__device__ __forceinline__ bool finite3(double a, double b, double c) {
+    return isfinite(a) && isfinite(b) && isfinite(c);
+}
+
+// State update arithmetic is deliberately un-fused (__dmul_rn + __dadd_rn): diffrax computes
+// y1 = y0 + f*dt as a multiply followed by an add, and XLA:CPU does not contract them.
+template <class C, int SCHEME>
+__global__ void __launch_bounds__(128) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const double dir = (a.t1 >= a.t0) ? 1.0 : -1.0;
+    const double T0 = a.t0 * dir, T1 = a.t1 * dir, h0 = a.dt0 * dir;
+    double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
+    double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
+    double mqx = qx, mqy = qy, mqz = qz, mpx = px, mpy = py, mpz = pz, tm = T0;  // LeapfrogMidpoint memory
+    double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    int k = 0;
+    double tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+    while (tsave <= T0) {  // save times equal to t0 return y0
+        qo[k * a.sk] = qx; qo[k * a.sk + a.sc] = qy; qo[k * a.sk + 2 * a.sc] = qz;
+        po[k * a.sk] = px; po[k * a.sk + a.sc] = py; po[k * a.sk + 2 * a.sc] = pz;
+        ++k;
+        tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+    }
+    double tprev = T0, tnext = clip_to_end(T0, T0 + h0, T1, true);
+    long long n = 0;
+    int st = GX_OK;
+    while (tprev < T1) {
+        if (a.max_steps >= 0 && n >= a.max_steps) { st = GX_MAX_STEPS_REACHED; break; }
+        const double hs = (tnext - tprev) * dir;  // signed step in physical time
+        double nqx, nqy, nqz, npx, npy, npz, gx_, gy_, gz_;
+        if (SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER) {
+            nqx = __dadd_rn(qx, __dmul_rn(px, hs));
+            nqy = __dadd_rn(qy, __dmul_rn(py, hs));
+            nqz = __dadd_rn(qz, __dmul_rn(pz, hs));
+            gradient<C>(P, nqx, nqy, nqz, gx_, gy_, gz_);
+            npx = __dadd_rn(px, __dmul_rn(-gx_, hs));
+            npy = __dadd_rn(py, __dmul_rn(-gy_, hs));
+            npz = __dadd_rn(pz, __dmul_rn(-gz_, hs));
+        } else {
+            const double hh = (tnext - tm) * dir;
+            gradient<C>(P, qx, qy, qz, gx_, gy_, gz_);
+            nqx = __dadd_rn(mqx, __dmul_rn(px, hh));
+            nqy = __dadd_rn(mqy, __dmul_rn(py, hh));
+            nqz = __dadd_rn(mqz, __dmul_rn(pz, hh));
+            npx = __dadd_rn(mpx, __dmul_rn(-gx_, hh));
+            npy = __dadd_rn(mpy, __dmul_rn(-gy_, hh));
+            npz = __dadd_rn(mpz, __dmul_rn(-gz_, hh));
+            mqx = qx; mqy = qy; mqz = qz; mpx = px; mpy = py; mpz = pz;
+            tm = tprev;
+        }
+        ++n;
+        while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
+            const double th = (tsave - tprev) / (tnext - tprev);
+            qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
+            qo[k * a.sk + a.sc] = __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy)));
+            qo[k * a.sk + 2 * a.sc] = __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz)));
+            po[k * a.sk] = __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px)));
+            po[k * a.sk + a.sc] = __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py)));
+            po[k * a.sk + 2 * a.sc] = __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz)));
+            ++k;
+            tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+        }
+        qx = nqx; qy = nqy; qz = nqz; px = npx; py = npy; pz = npz;
+        tprev = tnext;
+        tnext = clip_to_end(tprev, tprev + h0, T1, true);
+    }
+    if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
+    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+    for (; k < a.T; ++k) {
+        qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
+        po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
+    }
+    if (a.status) a.status[i] = st;
+}
+
+// ================================================================================================
+// K3 Dopri8 + PID, persistent warps with a per-lane work queue
+// ================================================================================================
+
+struct Dp8Args {
+    const double *q0, *p0, *t0v, *ts;
+    const int *order;
+    double *q, *p;
+    int *status, *n_acc, *n_tot;
+    unsigned long long *ticket;
+    long long N, max_steps;
+    long long sn, sk, sc;
+    double t0s, t1;
+    double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax, dtmin, dtmax, dt0;
+    int T;
+};
+
+__host__ __device__ constexpr bool row_nonzero(const double *row, int n) {
+    for (int i = 0; i < n; ++i)
+        if (row[i] != 0.0) return true;
+    return false;
+}
+
+__device__ __forceinline__ double rms6(double a, double b, double c, double d, double e, double f) {
+    double s = a * a;
+    s = fma(b, b, s); s = fma(c, c, s); s = fma(d, d, s); s = fma(e, e, s); s = fma(f, f, s);
+    return sqrt(s * (1.0 / 6.0));
+}
+
+template <class C>
+__device__ __forceinline__ void accel(const DevPot &P, double x, double y, double z, double &ax, double &ay,
+                                      double &az) {
+    double g0, g1, g2;
+    gradient<C>(P, x, y, z, g0, g1, g2);
+    ax = -g0; ay = -g1; az = -g2;
+}
+
+// Hairer-Norsett-Wanner initial step as restated by diffrax (_select_initial_step), error order 8.
+// Works in tau = dir*t: f = dir * (p, a).
+template <class C>
+__device__ double select_initial_step(const DevPot &P, double dir, const double y[6], const double a0[3],
+                                      double rtol, double atol) {
+    double f0[6] = {y[3] * dir, y[4] * dir, y[5] * dir, a0[0] * dir, a0[1] * dir, a0[2] * dir};
+    double sc[6], v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sc[i] = atol + fabs(y[i]) * rtol;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = y[i] / sc[i];
+    double d0 = rms6(v[0], v[1], v[2], v[3], v[4], v[5]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = f0[i] / sc[i];
+    double d1 = rms6(v[0], v[1], v[2], v[3], v[4], v[5]);
+    bool cond = (d0 < 1e-5) || (d1 < 1e-5);
+    double h0 = cond ? 1e-6 : 0.01 * (d0 / d1);
+    double y1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y1[i] = y[i] + h0 * f0[i];
+    double a1x, a1y, a1z;
+    accel<C>(P, y1[0], y1[1], y1[2], a1x, a1y, a1z);
+    double f1[6] = {y1[3] * dir, y1[4] * dir, y1[5] * dir, a1x * dir, a1y * dir, a1z * dir};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
+    double d2 = rms6(v[0], v[1], v[2], v[3], v[4], v[5]) / h0;
+    double maxd = fmax(d1, d2);
+    double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / maxd, 1.0 / 8.0);
+    return fmin(100.0 * h0, h1);
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
+    using namespace dp8;
+    const unsigned FULL = 0xffffffffu;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+
+    bool have = false, exhausted = false;
+    long long idx = 0;
+    double q0x = 0, q0y = 0, q0z = 0, p0x = 0, p0y = 0, p0z = 0;  // state at tprev
+    double ax[NS], ay[NS], az[NS];                                // stage accelerations; [0] is FSAL
+    double dir = 1.0, T1 = 0, tprev = 0, tnext = 0, tsave = INF;
+    double prev_inv = 1.0, prev_prev_inv = 1.0;
+    bool at_dtmin = false;
+    int k = 0, nacc = 0, ntot = 0, st = GX_OK;
+    ax[0] = ay[0] = az[0] = 0.0;
+
+    for (;;) {
+        // ---------------- refill idle lanes from the global ticket counter
+        if (!have && !exhausted) {
+            unsigned long long tk = atomicAdd(a.ticket, 1ULL);
+            if (tk >= (unsigned long long)a.N) {
+                exhausted = true;
+            } else {
+                idx = a.order ? (long long)a.order[tk] : (long long)tk;
+                const double t0 = a.t0v ? a.t0v[idx] : a.t0s;
+                dir = (a.t1 >= t0) ? 1.0 : -1.0;
+                const double T0 = t0 * dir;
+                T1 = a.t1 * dir;
+                q0x = a.q0[3 * idx]; q0y = a.q0[3 * idx + 1]; q0z = a.q0[3 * idx + 2];
+                p0x = a.p0[3 * idx]; p0y = a.p0[3 * idx + 1]; p0z = a.p0[3 * idx + 2];
+                k = 0; nacc = 0; ntot = 0; st = GX_OK;
+                prev_inv = prev_prev_inv = 1.0;
+                at_dtmin = false;
+                double *qo = a.q + idx * a.sn, *po = a.p + idx * a.sn;
+                tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+                while (tsave <= T0) {
+                    qo[k * a.sk] = q0x; qo[k * a.sk + a.sc] = q0y; qo[k * a.sk + 2 * a.sc] = q0z;
+                    po[k * a.sk] = p0x; po[k * a.sk + a.sc] = p0y; po[k * a.sk + 2 * a.sc] = p0z;
+                    ++k;
+                    tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+                }
+                accel<C>(P, q0x, q0y, q0z, ax[0], ay[0], az[0]);
+                double h;
+                if (a.dt0 > 0.0) {
+                    h = a.dt0;
+                } else {
+                    const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
+                    const double a0[3] = {ax[0], ay[0], az[0]};
+                    h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol);
+                }
+                tprev = T0;
+                tnext = clip_to_end(T0, T0 + h, T1, true);
+                have = true;
+            }
+        }
+        if (__all_sync(FULL, !have)) break;
+        if (!have) continue;
+
+        // ---------------- finished (or failed) particle: write remaining saves, counters, free the lane
+        if (!(tprev < T1) || st != GX_OK || (a.max_steps >= 0 && ntot >= a.max_steps && tprev < T1)) {
+            if (tprev < T1 && st == GX_OK) st = GX_MAX_STEPS_REACHED;
+            double *qo = a.q + idx * a.sn, *po = a.p + idx * a.sn;
+            for (; k < a.T; ++k) {
+                qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
+                po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
+            }
+            if (a.status) a.status[idx] = st;
+            if (a.n_acc) a.n_acc[idx] = nacc;
+            if (a.n_tot) a.n_tot[idx] = ntot;
+            have = false;
+            continue;
+        }
+
+        // ---------------- one attempted step of size h from (tprev, y0)
+        const double h = tnext - tprev;
+        const double hd = h * dir;  // signed step in physical time
+        const double hd2 = hd * hd;
+        double sx = 0, sy = 0, sz = 0;
+#pragma unroll
+        for (int i = 1; i < NS; ++i) {
+            // q_i = q0 + CN[i] hd p0 + hd^2 sum_{l<i} AA[i][l] a_l
+            sx = 0; sy = 0; sz = 0;
+#pragma unroll
+            for (int l = 0; l < i; ++l) {
+                if (AA[i][l] != 0.0) {
+                    sx = fma(AA[i][l], ax[l], sx);
+                    sy = fma(AA[i][l], ay[l], sy);
+                    sz = fma(AA[i][l], az[l], sz);
+                }
+            }
+            const double ch = CN[i] * hd;
+            const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
+            const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
+            const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
+            accel<C>(P, xi, yi, zi, ax[i], ay[i], az[i]);
+            if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: stage 14 sits at q1
+        }
+        const double q1x = sx, q1y = sy, q1z = sz;
+        double bx = 0, by = 0, bz = 0, epx = 0, epy = 0, epz = 0, eqx = 0, eqy = 0, eqz = 0;
+#pragma unroll
+        for (int l = 0; l < NS; ++l) {
+            if (B[l] != 0.0) { bx = fma(B[l], ax[l], bx); by = fma(B[l], ay[l], by); bz = fma(B[l], az[l], bz); }
+            if (E[l] != 0.0) { epx = fma(E[l], ax[l], epx); epy = fma(E[l], ay[l], epy); epz = fma(E[l], az[l], epz); }
+            if (EA[l] != 0.0) { eqx = fma(EA[l], ax[l], eqx); eqy = fma(EA[l], ay[l], eqy); eqz = fma(EA[l], az[l], eqz); }
+        }
+        const double p1x = fma(hd, bx, p0x), p1y = fma(hd, by, p0y), p1z = fma(hd, bz, p0z);
+        ++ntot;
+
+        // ---------------- PID controller (diffrax PIDController.adapt_step_size)
+        const bool nan1 = isnan(q1x) || isnan(q1y) || isnan(q1z) || isnan(p1x) || isnan(p1y) || isnan(p1z);
+        double e0 = hd2 * eqx, e1 = hd2 * eqy, e2 = hd2 * eqz, e3 = hd * epx, e4 = hd * epy, e5 = hd * epz;
+        e0 = e0 / (a.atol + fmax(fabs(q0x), fabs(nan1 ? q0x : q1x)) * a.rtol);
+        e1 = e1 / (a.atol + fmax(fabs(q0y), fabs(nan1 ? q0y : q1y)) * a.rtol);
+        e2 = e2 / (a.atol + fmax(fabs(q0z), fabs(nan1 ? q0z : q1z)) * a.rtol);
+        e3 = e3 / (a.atol + fmax(fabs(p0x), fabs(nan1 ? p0x : p1x)) * a.rtol);
+        e4 = e4 / (a.atol + fmax(fabs(p0y), fabs(nan1 ? p0y : p1y)) * a.rtol);
+        e5 = e5 / (a.atol + fmax(fabs(p0z), fabs(nan1 ? p0z : p1z)) * a.rtol);
+        double serr = rms6(e0, e1, e2, e3, e4, e5);
+        if (isnan(serr)) serr = INF;
+        bool keep = serr < 1.0;
+        if (a.dtmin > 0.0) keep = keep || at_dtmin;
+        double inv = 1.0 / serr;
+        const double c1 = (a.icoeff + a.pcoeff + a.dcoeff) * 0.125;
+        const double c2 = -(a.pcoeff + 2.0 * a.dcoeff) * 0.125;
+        const double c3 = a.dcoeff * 0.125;
+        double factor = a.safety;
+        if (c1 != 0.0) factor *= pow(inv, c1);
+        if (c2 != 0.0) factor *= pow(prev_inv, c2);
+        if (c3 != 0.0) factor *= pow(prev_prev_inv, c3);
+        const double fmin_ = keep ? 1.0 : a.factormin;
+        factor = fmin(fmax(factor, fmin_), a.factormax);
+        double dt = h * factor;
+        if (inv == 0.0 || isinf(inv)) { inv = 1.0; prev_inv = 1.0; }
+        if (a.dtmax > 0.0) dt = fmin(dt, a.dtmax);
+        if (a.dtmin > 0.0) { at_dtmin = dt <= a.dtmin; dt = fmax(dt, a.dtmin); }
+
+        if (keep) {
+            // ------------ SaveAt(ts): degree-6 continuous extension on the accepted step
+            if (tsave <= tnext) {
+                double *qo = a.q + idx * a.sn, *po = a.p + idx * a.sn;
+                while (tsave <= tnext) {
+                    const double th = (tsave - tprev) / (tnext - tprev);
+                    double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
+#pragma unroll
+                    for (int l = 0; l < NS; ++l) {
+                        if (row_nonzero(DQ[l], 6)) {
+                            double w = DQ[l][5];
+#pragma unroll
+                            for (int m = 4; m >= 0; --m) w = fma(w, th, DQ[l][m]);
+                            w *= th;
+                            wqx = fma(w, ax[l], wqx); wqy = fma(w, ay[l], wqy); wqz = fma(w, az[l], wqz);
+                        }
+                        if (row_nonzero(DB[l], 6)) {
+                            double w = DB[l][5];
+#pragma unroll
+                            for (int m = 4; m >= 0; --m) w = fma(w, th, DB[l][m]);
+                            w *= th;
+                            wpx = fma(w, ax[l], wpx); wpy = fma(w, ay[l], wpy); wpz = fma(w, az[l], wpz);
+                        }
+                    }
+                    const double thh = th * hd;
+                    qo[k * a.sk] = fma(hd2, wqx, fma(thh, p0x, q0x));
+                    qo[k * a.sk + a.sc] = fma(hd2, wqy, fma(thh, p0y, q0y));
+                    qo[k * a.sk + 2 * a.sc] = fma(hd2, wqz, fma(thh, p0z, q0z));
+                    po[k * a.sk] = fma(hd, wpx, p0x);
+                    po[k * a.sk + a.sc] = fma(hd, wpy, p0y);
+                    po[k * a.sk + 2 * a.sc] = fma(hd, wpz, p0z);
+                    ++k;
+                    tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+                }
+            }
+            q0x = q1x; q0y = q1y; q0z = q1z; p0x = p1x; p0y = p1y; p0z = p1z;
+            ax[0] = ax[NS - 1]; ay[0] = ay[NS - 1]; az[0] = az[NS - 1];
+            prev_prev_inv = prev_inv;
+            prev_inv = inv;
+            tprev = tnext;
+            ++nacc;
+            if (!(finite3(q0x, q0y, q0z) && finite3(p0x, p0y, p0z))) st = GX_NONFINITE;
+        }
+        if (tprev > T1) tprev = T1;
+        tnext = clip_to_end(tprev, tprev + dt, T1, keep);
+    }
+}
+
+// ================================================================================================
+// K4 stream release (Fardal+15 / Chen+24)
+// ================================================================================================
+
+struct ReleaseArgs {
+    const double *xq, *xp, *mass, *draws;
+    double *ql, *pl, *qt, *pt;
+    long long M;
+    double G;
+    int df;
+};
+
+template <class C>
+__global__ void __launch_bounds__(128) k_stream_release(const __grid_constant__ DevPot P, const ReleaseArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.M) return;
+    const double x[3] = {a.xq[3 * i], a.xq[3 * i + 1], a.xq[3 * i + 2]};
+    const double v[3] = {a.xp[3 * i], a.xp[3 * i + 1], a.xp[3 * i + 2]};
+    const double r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const double L[3] = {x[1] * v[2] - x[2] * v[1], x[2] * v[0] - x[0] * v[2], x[0] * v[1] - x[1] * v[0]};
+    // omega = |x cross v| / r^2     (register_api.py:77-88)
+    const double om[3] = {L[0] / (r * r), L[1] / (r * r), L[2] / (r * r)};
+    const double omega = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    // d2Phi/dr2 = rhat . H . rhat  (register_funcs.py:442-457); r_t = cbrt(G m / (omega^2 - d2Phi/dr2))
+    double H[6];
+    hessian<C>(P, x[0], x[1], x[2], H);
+    const double rh[3] = {x[0] / r, x[1] / r, x[2] / r};
+    const double d2 = rh[0] * (H[0] * rh[0] + H[1] * rh[1] + H[2] * rh[2]) +
+                      rh[1] * (H[1] * rh[0] + H[3] * rh[1] + H[4] * rh[2]) +
+                      rh[2] * (H[2] * rh[0] + H[4] * rh[1] + H[5] * rh[2]);
+    const double m = a.mass[i];
+    const double rt = cbrt(a.G * m / (omega * omega - d2));
+    const double Ln = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
+    const double zh[3] = {L[0] / Ln, L[1] / Ln, L[2] / Ln};
+    const double vr = v[0] * rh[0] + v[1] * rh[1] + v[2] * rh[2];
+    double ph[3] = {v[0] - vr * rh[0], v[1] - vr * rh[1], v[2] - vr * rh[2]};
+    const double pn = sqrt(ph[0] * ph[0] + ph[1] * ph[1] + ph[2] * ph[2]);
+    ph[0] /= pn; ph[1] /= pn; ph[2] /= pn;
+    if (a.df == GX_DF_FARDAL15) {
+        const double vc = omega * rt;
+        const double kr = 2.0 + a.draws[0 * a.M + i] * 0.5;
+        const double kvphi = kr * (0.3 + a.draws[1 * a.M + i] * 0.5);
+        const double kz = 0.0 + a.draws[2 * a.M + i] * 0.5;
+        const double kvz = 0.0 + a.draws[3 * a.M + i] * 0.5;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a.qt[3 * i + c] = x[c] + rt * (kr * rh[c] + kz * zh[c]);
+            a.pt[3 * i + c] = v[c] + vc * (kvphi * ph[c] + kvz * zh[c]);
+            a.ql[3 * i + c] = x[c] - rt * (kr * rh[c] - kz * zh[c]);
+            a.pl[3 * i + c] = v[c] - vc * (kvphi * ph[c] - kvz * zh[c]);
+        }
+    } else {
+        const double D2R = 0.017453292519943295;
+        const double *pv = a.draws + 6 * i;
+        const double Dr = pv[0] * rt;
+        const double vesc = sqrt(2.0 * a.G * m / Dr);
+        const double Dv = pv[3] * vesc;
+        double sp, cp, st_, ct, sa, ca, sb, cb;
+        sincos(pv[1] * D2R, &sp, &cp);
+        sincos(pv[2] * D2R, &st_, &ct);
+        sincos(pv[4] * D2R, &sa, &ca);
+        sincos(pv[5] * D2R, &sb, &cb);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double dx = (Dr * ct * cp) * rh[c], dy = (Dr * ct * sp) * ph[c], dz = (Dr * st_) * zh[c];
+            const double ex = (Dv * cb * ca) * rh[c], ey = (Dv * cb * sa) * ph[c], ez = (Dv * sb) * zh[c];
+            a.qt[3 * i + c] = x[c] + dx + dy + dz;
+            a.pt[3 * i + c] = v[c] + ex + ey + ez;
+            a.ql[3 * i + c] = x[c] - dx - dy + dz;
+            a.pl[3 * i + c] = v[c] - ex - ey + ez;
+        }
+    }
+}
+
+// ================================================================================================
+// diagnostics, probes, FP64 peak microbenchmark
+// ================================================================================================
+
+template <class C>
+__global__ void __launch_bounds__(256) k_energy_angmom(const __grid_constant__ DevPot P, const double *q,
+                                                       const double *p, long long N, double *E, double *L) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
+    const double vx = p[3 * i], vy = p[3 * i + 1], vz = p[3 * i + 2];
+    if (E) E[i] = 0.5 * (vx * vx + vy * vy + vz * vz) + potential_value<C>(P, x, y, z);
+    if (L) {
+        L[3 * i] = y * vz - z * vy;
+        L[3 * i + 1] = z * vx - x * vz;
+        L[3 * i + 2] = x * vy - y * vx;
+    }
+}
+
+__global__ void k_bench_dfma(long long iters, double *sink) {
+    // 8 independent chains per thread; x <- x*m + c keeps every value bounded.
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    const double m = 0.999999, c = 1e-6;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, m, c); x1 = fma(x1, m, c); x2 = fma(x2, m, c); x3 = fma(x3, m, c);
+            x4 = fma(x4, m, c); x5 = fma(x5, m, c); x6 = fma(x6, m, c); x7 = fma(x7, m, c);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+__global__ void k_debug_math(int op, double a, double lgam, const double *x, long long N, double *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double v = x[i];
+    double r;
+    switch (op) {
+    case 0: r = rcp_fast(v); break;
+    case 1: r = rsqrt_fast(v); break;
+    case 2: r = log1p_pos(v); break;
+    case 3: r = gammainc_P(a, lgam, v, nullptr); break;
+    case 4: { double inv = rcp_fast(1.0 + v); r = nfw_menc_shape(v, inv); } break;
+    default: r = 0.0;
+    }
+    out[i] = r;
+}
+
+}  // namespace gx
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace gx;
+
+extern "C" {
+
+int gx_version(void) { return GX_VERSION; }
+
+const char *gx_strerror(int code) {
+    switch (code) {
+    case 0: return "ok";
+    case GX_ERR_BADARG: return "bad argument";
+    case GX_ERR_UNSUPPORTED: return "unsupported potential component or parameter";
+    case GX_ERR_CUDA: return "CUDA error";
+    default: return "unknown error";
+    }
+}
+
+int64_t gx_workspace_bytes(void) { return 256; }
+
+static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+static void out_strides(int layout, long long N, int T, long long &sn, long long &sk, long long &sc) {
+    if (layout == GX_LAYOUT_T3N) { sn = 1; sk = 3 * N; sc = N; }
+    else { sn = 3LL * T; sk = 3; sc = 1; }
+}
+
+int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what, double *phi,
+                      double *grad, double *acc, double *hess, void *stream) {
+    (void)t;
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model);
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && !xyz)) return GX_ERR_BADARG;
+    if (((what & GX_PHI) && !phi) || ((what & GX_GRAD) && !grad) || ((what & GX_ACC) && !acc) ||
+        ((what & GX_HESS) && !hess))
+        return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    EvalArgs a{xyz, phi, grad, acc, hess, (long long)N, what};
+    const int block = 256;
+    long long want = (N + block - 1) / block;
+    int grid = (int)(want < 148LL * 32 ? want : 148LL * 32);  // grid-stride beyond 32 CTAs/SM worth of work
+    cudaStream_t s = (cudaStream_t)stream;
+    GX_DISPATCH_MODEL(model, (k_potential_eval<C><<<grid, block, 0, s>>>(D, a)));
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0, double t1,
+                       double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
+                       double *q, double *p, int32_t *status, void *stream) {
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model);
+    if (rc) return rc;
+    if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
+    if (scheme != GX_SCHEME_SEMI_IMPLICIT_EULER && scheme != GX_SCHEME_LEAPFROG_MIDPOINT) return GX_ERR_BADARG;
+    if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
+    const double dir = (t1 >= t0) ? 1.0 : -1.0;
+    if (t1 != t0 && !(dt0 * dir > 0.0)) return GX_ERR_BADARG;  // ConstantStepSize needs dt0 in the direction of t1
+    if (N == 0) return 0;
+    FixedArgs a;
+    a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p; a.status = status;
+    a.N = N; a.max_steps = max_steps; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
+    out_strides(layout, N, T, a.sn, a.sk, a.sc);
+    // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers
+    const int block = (N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32);
+    const int grid = grid_for(N, block);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
+        GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER><<<grid, block, 0, s>>>(D, a)));
+    } else {
+        GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT><<<grid, block, 0, s>>>(D, a)));
+    }
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,
+                        const double *t0, double t0_scalar, double t1, const double *ts, int32_t T, int64_t max_steps,
+                        const int32_t *order, int32_t layout, double *q, double *p, int32_t *status,
+                        int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model);
+    if (rc) return rc;
+    if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (T > 0 && (!ts || !q || !p)) || !workspace)
+        return GX_ERR_BADARG;
+    if (!(pid->rtol >= 0.0) || !(pid->atol >= 0.0) || (pid->rtol == 0.0 && pid->atol == 0.0)) return GX_ERR_BADARG;
+    if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
+    if (e != cudaSuccess) return GX_ERR_CUDA;
+    Dp8Args a;
+    a.q0 = q0; a.p0 = p0; a.t0v = t0; a.ts = ts; a.order = order; a.q = q; a.p = p;
+    a.status = status; a.n_acc = n_accepted; a.n_tot = n_attempted;
+    a.ticket = (unsigned long long *)workspace;
+    a.N = N; a.max_steps = max_steps; a.t0s = t0_scalar; a.t1 = t1;
+    a.rtol = pid->rtol; a.atol = pid->atol;
+    a.pcoeff = pid->pcoeff; a.icoeff = pid->icoeff; a.dcoeff = pid->dcoeff;
+    a.safety = pid->safety; a.factormin = pid->factormin; a.factormax = pid->factormax;
+    a.dtmin = pid->dtmin; a.dtmax = pid->dtmax;
+    a.dt0 = (pid->dt0 > 0.0) ? pid->dt0 : -1.0;
+    a.T = T;
+    out_strides(layout, N, T, a.sn, a.sk, a.sc);
+    // persistent launch: resident CTAs only (occupancy query), never more lanes than particles
+    const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define GX_OCC(C_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate_dopri8<C_>, block, 0)
+    switch (model) {
+    case MODEL_MW: GX_OCC(CountsMW); break;
+    case MODEL_MW2022: GX_OCC(CountsMW2022); break;
+    case MODEL_BOVY: GX_OCC(CountsBovy); break;
+    default: GX_OCC(CountsRuntime); break;
+    }
+#undef GX_OCC
+    if (per_sm < 1) per_sm = 1;
+    long long want = (N + block - 1) / block;
+    long long resident = (long long)per_sm * sms;
+    int grid = (int)(want < resident ? want : resident);
+    GX_DISPATCH_MODEL(model, (k_integrate_dopri8<C><<<grid, block, 0, s>>>(D, a)));
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_stream_release(const gx_potential *pot, int32_t df, const double *prog_q, const double *prog_p,
+                      const double *prog_mass, const double *draws, int64_t M, double *q_lead, double *p_lead,
+                      double *q_trail, double *p_trail, void *stream) {
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model);
+    if (rc) return rc;
+    if (df != GX_DF_FARDAL15 && df != GX_DF_CHEN24) return GX_ERR_BADARG;
+    if (M < 0 || (M > 0 && (!prog_q || !prog_p || !prog_mass || !draws || !q_lead || !p_lead || !q_trail || !p_trail)))
+        return GX_ERR_BADARG;
+    if (M == 0) return 0;
+    ReleaseArgs a{prog_q, prog_p, prog_mass, draws, q_lead, p_lead, q_trail, p_trail, (long long)M, pot->G, df};
+    cudaStream_t s = (cudaStream_t)stream;
+    GX_DISPATCH_MODEL(model, (k_stream_release<C><<<grid_for(M, 128), 128, 0, s>>>(D, a)));
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_energy_angmom(const gx_potential *pot, const double *q, const double *p, int64_t N, double *energy,
+                     double *angmom, void *stream) {
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model);
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && (!q || !p))) return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    GX_DISPATCH_MODEL(model, (k_energy_angmom<C><<<grid_for(N, 256), 256, 0, s>>>(D, q, p, (long long)N, energy, angmom)));
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, int64_t *fma_per_thread,
+                  void *stream) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink) return GX_ERR_BADARG;
+    k_bench_dfma<<<blocks, threads, 0, (cudaStream_t)stream>>>((long long)iters, sink);
+    if (fma_per_thread) *fma_per_thread = iters * 8 * 16;
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream) {
+    if (N < 0 || (N > 0 && (!x || !out))) return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    k_debug_math<<<grid_for(N, 256), 256, 0, (cudaStream_t)stream>>>(op, a, lgamma(a), x, (long long)N, out);
+    return cuda_rc(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entries
+// ------------------------------------------------------------------------------------------------
+
+struct DevBuf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t bytes) { return bytes ? cudaMalloc(&p, bytes) : cudaSuccess; }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+#define GX_CK(expr) do { if ((expr) != cudaSuccess) return GX_ERR_CUDA; } while (0)
+
+int gx_host_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what,
+                           double *phi, double *grad, double *acc, double *hess) {
+    if (N < 0) return GX_ERR_BADARG;
+    DevBuf dx, dphi, dg, da, dh;
+    const size_t n = (size_t)N;
+    GX_CK(dx.alloc(n * 24));
+    if (what & GX_PHI) GX_CK(dphi.alloc(n * 8));
+    if (what & GX_GRAD) GX_CK(dg.alloc(n * 24));
+    if (what & GX_ACC) GX_CK(da.alloc(n * 24));
+    if (what & GX_HESS) GX_CK(dh.alloc(n * 72));
+    if (n) GX_CK(cudaMemcpy(dx.p, xyz, n * 24, cudaMemcpyHostToDevice));
+    int rc = gx_potential_eval(pot, (const double *)dx.p, t, N, what, (double *)dphi.p, (double *)dg.p,
+                               (double *)da.p, (double *)dh.p, nullptr);
+    if (rc) return rc;
+    if (n && (what & GX_PHI)) GX_CK(cudaMemcpy(phi, dphi.p, n * 8, cudaMemcpyDeviceToHost));
+    if (n && (what & GX_GRAD)) GX_CK(cudaMemcpy(grad, dg.p, n * 24, cudaMemcpyDeviceToHost));
+    if (n && (what & GX_ACC)) GX_CK(cudaMemcpy(acc, da.p, n * 24, cudaMemcpyDeviceToHost));
+    if (n && (what & GX_HESS)) GX_CK(cudaMemcpy(hess, dh.p, n * 72, cudaMemcpyDeviceToHost));
+    GX_CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int gx_host_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
+                            double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
+                            double *q, double *p, int32_t *status) {
+    if (N < 0 || T < 0) return GX_ERR_BADARG;
+    const size_t n = (size_t)N, out = n * (size_t)T * 24;
+    DevBuf dq0, dp0, dts, dq, dp, dst;
+    GX_CK(dq0.alloc(n * 24)); GX_CK(dp0.alloc(n * 24)); GX_CK(dts.alloc((size_t)T * 8));
+    GX_CK(dq.alloc(out)); GX_CK(dp.alloc(out)); GX_CK(dst.alloc(n * 4));
+    if (n) { GX_CK(cudaMemcpy(dq0.p, q0, n * 24, cudaMemcpyHostToDevice)); GX_CK(cudaMemcpy(dp0.p, p0, n * 24, cudaMemcpyHostToDevice)); }
+    if (T) GX_CK(cudaMemcpy(dts.p, ts, (size_t)T * 8, cudaMemcpyHostToDevice));
+    int rc = gx_integrate_fixed(pot, (const double *)dq0.p, (const double *)dp0.p, N, t0, t1, dt0,
+                                (const double *)dts.p, T, scheme, max_steps, GX_LAYOUT_NT3, (double *)dq.p,
+                                (double *)dp.p, (int32_t *)dst.p, nullptr);
+    if (rc) return rc;
+    if (out) { GX_CK(cudaMemcpy(q, dq.p, out, cudaMemcpyDeviceToHost)); GX_CK(cudaMemcpy(p, dp.p, out, cudaMemcpyDeviceToHost)); }
+    if (n && status) GX_CK(cudaMemcpy(status, dst.p, n * 4, cudaMemcpyDeviceToHost));
+    GX_CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int gx_host_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0,
+                             int64_t N, const double *t0, double t0_scalar, double t1, const double *ts, int32_t T,
+                             int64_t max_steps, double *q, double *p, int32_t *status, int32_t *n_accepted,
+                             int32_t *n_attempted) {
+    if (N < 0 || T < 0) return GX_ERR_BADARG;
+    const size_t n = (size_t)N, out = n * (size_t)T * 24;
+    DevBuf dq0, dp0, dt0, dts, dq, dp, dst, dna, dnt, dws;
+    GX_CK(dq0.alloc(n * 24)); GX_CK(dp0.alloc(n * 24)); GX_CK(dts.alloc((size_t)T * 8));
+    if (t0) GX_CK(dt0.alloc(n * 8));
+    GX_CK(dq.alloc(out)); GX_CK(dp.alloc(out)); GX_CK(dst.alloc(n * 4)); GX_CK(dna.alloc(n * 4)); GX_CK(dnt.alloc(n * 4));
+    GX_CK(dws.alloc(256));
+    if (n) { GX_CK(cudaMemcpy(dq0.p, q0, n * 24, cudaMemcpyHostToDevice)); GX_CK(cudaMemcpy(dp0.p, p0, n * 24, cudaMemcpyHostToDevice)); }
+    if (n && t0) GX_CK(cudaMemcpy(dt0.p, t0, n * 8, cudaMemcpyHostToDevice));
+    if (T) GX_CK(cudaMemcpy(dts.p, ts, (size_t)T * 8, cudaMemcpyHostToDevice));
+    int rc = gx_integrate_dopri8(pot, pid, (const double *)dq0.p, (const double *)dp0.p, N,
+                                 t0 ? (const double *)dt0.p : nullptr, t0_scalar, t1, (const double *)dts.p, T,
+                                 max_steps, nullptr, GX_LAYOUT_NT3, (double *)dq.p, (double *)dp.p, (int32_t *)dst.p,
+                                 (int32_t *)dna.p, (int32_t *)dnt.p, dws.p, nullptr);
+    if (rc) return rc;
+    if (out) { GX_CK(cudaMemcpy(q, dq.p, out, cudaMemcpyDeviceToHost)); GX_CK(cudaMemcpy(p, dp.p, out, cudaMemcpyDeviceToHost)); }
+    if (n && status) GX_CK(cudaMemcpy(status, dst.p, n * 4, cudaMemcpyDeviceToHost));
+    if (n && n_accepted) GX_CK(cudaMemcpy(n_accepted, dna.p, n * 4, cudaMemcpyDeviceToHost));
+    if (n && n_attempted) GX_CK(cudaMemcpy(n_attempted, dnt.p, n * 4, cudaMemcpyDeviceToHost));
+    GX_CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+}  // extern "C"

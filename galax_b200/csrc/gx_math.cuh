@@ -1,0 +1,147 @@
+// gx_math.cuh -- fp64 building blocks for the sm_100a kernels.
+//
+// The B200 FP64 pipe issues one DFMA-class warp instruction every 2 cycles per SM sub-partition;
+// IEEE division / sqrt / log1p from libdevice cost 20-60 such instructions plus slow-path branches.
+// The integrators only need the acceleration to ~1e-15 relative (its rounding error enters the state
+// scaled by h*|a|/|p| ~ 1e-3), so the hot path uses MUFU-seeded reciprocal / rsqrt with one cubically
+// convergent correction (max error ~1 ulp, no branches) and a lean log1p.  Everything here is plain
+// IEEE arithmetic on normal inputs: no --use_fast_math, no flush-to-zero beyond the MUFU seed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gx {
+
+// ---- MUFU seeds (relative error ~2^-20; only the upper 32 bits of the operand are examined)
+__device__ __forceinline__ double rcp_seed(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// 1/x for normal x: seed e0 ~ 2^-20, one cubic step -> e0^3 ~ 2^-60, final rounding ~0.5-1 ulp.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double y = rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+// x^(-1/2) for normal x > 0: y1 = y0 (1 + h/2 + 3h^2/8), h = 1 - x y0^2.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y = rsqrt_seed(x);
+    double t = x * y;
+    double h = fma(-t, y, 1.0);
+    double u = y * h;
+    return fma(u, fma(0.375, h, 0.5), y);
+}
+
+// sqrt(x) with one Newton correction on top of x*rsqrt_fast(x) (~0.5 ulp); rs receives rsqrt_fast(x).
+__device__ __forceinline__ double sqrt_rs(double x, double &rs) {
+    rs = rsqrt_fast(x);
+    double g = x * rs;
+    double r = fma(-g, g, x);
+    return fma(r, 0.5 * rs, g);
+}
+
+// ---- log1p(s), s >= 0.  u = 1+s with the rounding error c folded back in (log1p = log u + c/u);
+// log u by the classic argument reduction u = 2^k m, m in [sqrt(1/2), sqrt(2)), f = m-1, w = f/(2+f),
+// log m = 2 atanh(w) with the degree-7 minimax polynomial in w^2 of fdlibm's e_log.c (public domain,
+// |error| < 2^-58.45).
+__device__ __forceinline__ double log1p_pos(double s) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    double u = 1.0 + s;
+    // exact rounding error of 1+s (s >= 0): for s < 1, c = s - (u-1); else c = 1 - (u-s)
+    double c = (s < 1.0) ? (s - (u - 1.0)) : (1.0 - (u - s));
+    int hi = __double2hiint(u), lo = __double2loint(u);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    // m in [sqrt(1/2), sqrt(2)): if mantissa >= sqrt(2) (0x6a09e), halve m and bump k
+    int i = (hi + 0x95f64) & 0x100000;
+    k += (i >> 20);
+    double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
+    double f = m - 1.0;
+    double w = f * rcp_fast(2.0 + f);
+    double z = w * w;
+    double z2 = z * z;
+    // even / odd split of the polynomial (two shorter dependency chains)
+    double t1 = z2 * fma(z2, fma(z2, Lg6, Lg4), Lg2);
+    double t2 = z * fma(z2, fma(z2, fma(z2, Lg7, Lg5), Lg3), Lg1);
+    double R = t1 + t2;
+    double hfsq = 0.5 * f * f;
+    double dk = (double)k;
+    // log m = f - hfsq + w (hfsq + R);  log1p = k ln2 + log m + c/u  (c/u only needs the seed's accuracy)
+    double corr = c * rcp_seed(u);
+    double lo_part = fma(w, hfsq + R, fma(dk, ln2_lo, corr));
+    return fma(dk, ln2_hi, f - (hfsq - lo_part));
+}
+
+// ln(1+s) - s/(1+s), the NFW enclosed-mass shape.  Below s = 0.02 the two terms cancel to O(s^2) and the
+// alternating series sum_{k>=2} (-1)^k (k-1)/k s^k is used instead (13 terms: 0.02^12 < 5e-21).
+__device__ __forceinline__ double nfw_menc_shape(double s, double inv_1ps) {
+    if (s < 0.02) {
+        double p = 12.0 / 13.0;  // k = 13 (odd -> negative sign applied below)
+        p = fma(-p, s, 11.0 / 12.0);
+        p = fma(-p, s, 10.0 / 11.0);
+        p = fma(-p, s, 9.0 / 10.0);
+        p = fma(-p, s, 8.0 / 9.0);
+        p = fma(-p, s, 7.0 / 8.0);
+        p = fma(-p, s, 6.0 / 7.0);
+        p = fma(-p, s, 5.0 / 6.0);
+        p = fma(-p, s, 4.0 / 5.0);
+        p = fma(-p, s, 3.0 / 4.0);
+        p = fma(-p, s, 2.0 / 3.0);
+        p = fma(-p, s, 1.0 / 2.0);
+        return p * s * s;
+    }
+    return fma(-s, inv_1ps, log1p_pos(s));
+}
+
+// ---- regularised lower incomplete gamma P(a, x), a > 0, x >= 0 (Bovy bulge: a = 0.6).
+// Series for x < a+1, modified-Lentz continued fraction for Q = 1-P otherwise.  lgam = lgamma(a).
+// On exit dP = x^(a-1) e^-x / Gamma(a) = dP/dx (needed by the Hessian).
+__device__ __noinline__ double gammainc_P(double a, double lgam, double x, double *dP) {
+    if (!(x > 0.0)) {
+        if (dP) *dP = (a == 1.0) ? 1.0 : ((a > 1.0) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL));
+        return 0.0;
+    }
+    double lx = log(x);
+    double pref = exp(fma(a, lx, -x) - lgam);  // x^a e^-x / Gamma(a)
+    if (dP) *dP = pref / x;
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 200; ++n) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (del < sum * 1e-17) break;
+        }
+        return sum * pref;
+    }
+    if (x > 745.0) return 1.0;
+    const double FPMIN = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / FPMIN, d = 1.0 / b, h = d;
+    for (int i = 1; i < 500; ++i) {
+        double an = -i * (i - a);
+        b += 2.0;
+        d = fma(an, d, b);
+        if (fabs(d) < FPMIN) d = FPMIN;
+        c = b + an / c;
+        if (fabs(c) < FPMIN) c = FPMIN;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return 1.0 - pref * h;
+}
+
+}  // namespace gx

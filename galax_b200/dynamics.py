@@ -1,0 +1,580 @@
+"""Host-side mirror of ``galax.dynamics`` for the hot path: orbit integration and mock streams.
+
+Names, argument order and defaults follow the reference:
+
+* ``evaluate_orbit(pot, w0, t, *, integrator=None, dense=False)``  legacy/funcs.py:42-213
+* ``compute_orbit(pot_or_field, w0, ts, *, solver=None, dense=False)``  orbit/compute.py:28-98
+* ``Integrator(dynamics_solver=..., diffeq_kw=...)``  legacy/integrator.py:42-245 (default Dopri8, rtol=atol=1e-7,
+  ``max_steps=None``)
+* ``OrbitSolver(solver, stepsize_controller, max_steps)``  orbit/solver.py:121-141 (default Dopri8, 1e-8, 2**16)
+* ``MockStreamGenerator(df, potential, progenitor_integrator=, stream_integrator=).run(...)``
+  legacy/mockstream/mockstream_generator.py:160-275, ``FardalStreamDF`` / ``ChenStreamDF`` df/*.py
+
+``SemiImplicitEuler``, ``LeapfrogMidpoint``, ``Dopri8``, ``ConstantStepSize`` and ``PIDController`` are
+parameter records standing in for the diffrax objects the reference passes around (diffrax is not a
+dependency here); their fields and defaults are diffrax 0.7.0's.
+
+All numerics run in the CUDA library (``include/galax_b200.h``); arrays are fp64 in the potential's unit
+system.  numpy in -> numpy out; CUDA torch tensors in -> CUDA tensors out with no host round trip.
+
+Semantic notes (also in DESIGN.md):
+* step control is always per particle (what the reference does on its ``vmap`` / vectorised paths); the
+  reference's scalar-time batch path instead solves the whole batch as one ODE with a shared step.
+* ``dense=True``, events, ``args`` and differentiating through the call are not supported and raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Any, Callable, Sequence
+
+import numpy as np
+
+from . import _lib
+from .potential import AbstractPotential, _to_device
+
+# ------------------------------------------------------------------------------------------------
+# diffrax stand-ins (plain records)
+
+
+@dataclasses.dataclass(frozen=True)
+class SemiImplicitEuler:
+    """diffrax.SemiImplicitEuler: q1 = q0 + p0 h ; p1 = p0 - grad Phi(q1) h.  The reference's "leapfrog"."""
+
+
+@dataclasses.dataclass(frozen=True)
+class LeapfrogMidpoint:
+    """diffrax.LeapfrogMidpoint: y_{n+1} = y_{n-1} + f(y_n) (t_{n+1} - t_{n-1})."""
+
+
+@dataclasses.dataclass(frozen=True)
+class Dopri8:
+    """diffrax.Dopri8 (Prince-Dormand 8(7)13M + FSAL); ``scan_kind`` has no numerical effect."""
+
+    scan_kind: str | None = None
+
+
+@dataclasses.dataclass(frozen=True)
+class ConstantStepSize:
+    """diffrax.ConstantStepSize: needs ``dt0``."""
+
+
+@dataclasses.dataclass(frozen=True)
+class PIDController:
+    """diffrax.PIDController with diffrax 0.7.0 defaults."""
+
+    rtol: float
+    atol: float
+    pcoeff: float = 0.0
+    icoeff: float = 1.0
+    dcoeff: float = 0.0
+    dtmin: float | None = None
+    dtmax: float | None = None
+    force_dtmin: bool = True
+    factormin: float = 0.2
+    factormax: float = 10.0
+    safety: float = 0.9
+
+    def c_struct(self, dt0: float | None) -> _lib.GxPid:
+        if self.dtmin is not None and not self.force_dtmin:
+            raise NotImplementedError("PIDController(force_dtmin=False) is not supported")
+        pid = _lib.GxPid()
+        pid.rtol, pid.atol = float(self.rtol), float(self.atol)
+        pid.pcoeff, pid.icoeff, pid.dcoeff = float(self.pcoeff), float(self.icoeff), float(self.dcoeff)
+        pid.safety, pid.factormin, pid.factormax = float(self.safety), float(self.factormin), float(self.factormax)
+        pid.dtmin = -1.0 if self.dtmin is None else float(self.dtmin)
+        pid.dtmax = -1.0 if self.dtmax is None else float(self.dtmax)
+        pid.force_dtmin = int(self.force_dtmin)
+        pid.dt0 = -1.0 if dt0 is None else float(dt0)
+        return pid
+
+
+# ------------------------------------------------------------------------------------------------
+# containers (coordinates/_src/pscs, dynamics/_src/orbit/orbit.py:18-75)
+
+
+@dataclasses.dataclass
+class PhaseSpacePosition:
+    q: Any
+    p: Any
+
+    def w(self):
+        return _cat(self.q, self.p)
+
+
+@dataclasses.dataclass
+class PhaseSpaceCoordinate:
+    q: Any
+    p: Any
+    t: Any = None
+
+    def w(self):
+        return _cat(self.q, self.p)
+
+
+@dataclasses.dataclass
+class Orbit:
+    """q, p: (*batch, T, 3); t: (T,).  Mirrors ``gd.Orbit`` (orbit/orbit.py:18-75)."""
+
+    q: Any
+    p: Any
+    t: Any
+    potential: AbstractPotential | None = None
+    status: Any = None
+    n_steps: Any = None
+
+    def w(self):
+        return _cat(self.q, self.p)
+
+    @property
+    def shape(self):
+        return tuple(self.q.shape[:-1])
+
+    def __getitem__(self, idx):
+        return PhaseSpaceCoordinate(self.q[..., idx, :], self.p[..., idx, :], self.t[idx])
+
+    def total_energy(self):
+        """E = |p|^2/2 + Phi(q) evaluated on the device."""
+        return _energy(self.potential, self.q, self.p)
+
+
+@dataclasses.dataclass
+class Solution:
+    """Shape-compatible stand-in for ``diffrax.Solution``: ys = (q, p) each (*batch, T, 3)."""
+
+    t0: Any
+    t1: Any
+    ts: Any
+    ys: tuple
+    stats: dict
+    result: Any
+
+
+def _cat(q, p):
+    if isinstance(q, np.ndarray):
+        return np.concatenate([q, p], axis=-1)
+    import torch
+
+    return torch.cat([q, p], dim=-1)
+
+
+class HamiltonianField:
+    """``gd.fields.HamiltonianField(pot)`` (orbit/field_hamiltonian.py:229-249): (dq, dp) = (p, -grad Phi)."""
+
+    def __init__(self, potential: AbstractPotential):
+        if not isinstance(potential, AbstractPotential):
+            raise TypeError("HamiltonianField needs a galax_b200 potential")
+        self.potential = potential
+
+    def __call__(self, t, q, p, args=None):
+        if args is not None:
+            raise NotImplementedError("field args are not supported")
+        return p, self.potential.acceleration(q, t)
+
+
+def _as_potential(obj) -> AbstractPotential:
+    if isinstance(obj, HamiltonianField):
+        return obj.potential
+    if isinstance(obj, AbstractPotential):
+        return obj
+    raise TypeError(f"expected a potential or HamiltonianField, got {type(obj).__name__}")
+
+
+# ------------------------------------------------------------------------------------------------
+# low-level launch wrapper
+
+
+def _split_w0(w0):
+    """-> q, p, t (t may be None).  Accepts what legacy/funcs.py:45 accepts."""
+    if isinstance(w0, (PhaseSpaceCoordinate, Orbit)):
+        return w0.q, w0.p, w0.t
+    if isinstance(w0, PhaseSpacePosition):
+        return w0.q, w0.p, None
+    if isinstance(w0, (tuple, list)) and len(w0) == 2:
+        return w0[0], w0[1], None
+    if hasattr(w0, "shape") and w0.shape[-1] == 6:
+        return w0[..., 0:3], w0[..., 3:6], None
+    raise TypeError("w0 must be a PhaseSpaceCoordinate/Position, a (q, p) tuple or a (*batch, 6) array")
+
+
+def _period_order(q, p, t0v, t1, torch):
+    """Processing order for the adaptive kernel: most expensive particles first, neighbours alike.
+
+    Cost proxy = (integration length) / (dynamical time r/|v|); cheap to compute, good enough to keep
+    the lanes of a warp in step (north_star: "period-sorted particle ordering")."""
+    r = q.norm(dim=-1)
+    v = p.norm(dim=-1).clamp_min(1e-300)
+    span = (t1 - t0v).abs() if t0v is not None else 1.0
+    cost = span * v / r.clamp_min(1e-300)
+    return torch.argsort(cost, descending=True).to(torch.int32).contiguous()
+
+
+def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",
+               throw=True):  # fmt: skip
+    """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,)."""
+    torch = _lib.require_cuda()
+    dq, restore = _to_device(q0)
+    dp, _ = _to_device(p0)
+    batch = tuple(dq.shape[:-1])
+    dq = dq.reshape(-1, 3).contiguous()
+    dp = dp.expand(*batch, 3).reshape(-1, 3).contiguous() if dp.shape != dq.shape else dp.reshape(-1, 3).contiguous()
+    N = dq.shape[0]
+    dev = dq.device
+    ts_np = np.atleast_1d(np.asarray(ts.detach().cpu() if isinstance(ts, torch.Tensor) else ts, dtype=np.float64))
+    T = int(ts_np.shape[0])
+    dts = torch.from_numpy(ts_np).to(dev)
+    t1 = float(t1)
+    t0_arr = None
+    t0_is_array = (isinstance(t0, (np.ndarray, torch.Tensor)) and np.ndim(t0) > 0) or isinstance(t0, (list, tuple))
+    if t0_is_array:
+        t0_arr, _ = _to_device(t0)
+        t0_arr = t0_arr.reshape(-1).contiguous()
+        if t0_arr.shape[0] != N:
+            raise ValueError("per-particle t0 must match the batch size")
+        t0s = 0.0
+    else:
+        t0s = float(t0)
+    if layout == "NT3":
+        q = torch.empty((N, T, 3), dtype=torch.float64, device=dev)
+        p = torch.empty((N, T, 3), dtype=torch.float64, device=dev)
+        lay = _lib.LAYOUT_NT3
+    elif layout == "T3N":
+        q = torch.empty((T, 3, N), dtype=torch.float64, device=dev)
+        p = torch.empty((T, 3, N), dtype=torch.float64, device=dev)
+        lay = _lib.LAYOUT_T3N
+    else:
+        raise ValueError("layout must be 'NT3' or 'T3N'")
+    status = torch.empty((N,), dtype=torch.int32, device=dev)
+    P = pot.c_struct()
+    ms = -1 if max_steps is None else int(max_steps)
+    stats: dict[str, Any] = {}
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        if isinstance(solver, (SemiImplicitEuler, LeapfrogMidpoint)):
+            if not isinstance(controller, ConstantStepSize):
+                raise NotImplementedError(f"{type(solver).__name__} requires ConstantStepSize()")
+            if dt0 is None:
+                raise ValueError("ConstantStepSize requires dt0")
+            if t0_arr is not None:
+                raise NotImplementedError("per-particle t0 is only supported by the adaptive solver")
+            scheme = _lib.SCHEME_SIE if isinstance(solver, SemiImplicitEuler) else _lib.SCHEME_LEAPFROG_MIDPOINT
+            rc = L.gx_integrate_fixed(C.byref(P), dq.data_ptr(), dp.data_ptr(), N, t0s, t1, float(dt0),
+                                      dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
+                                      status.data_ptr(), stream)  # fmt: skip
+            _lib.check(rc, "gx_integrate_fixed")
+        elif isinstance(solver, Dopri8):
+            if not isinstance(controller, PIDController):
+                raise NotImplementedError("Dopri8 requires a PIDController")
+            pid = controller.c_struct(dt0)
+            nacc = torch.empty((N,), dtype=torch.int32, device=dev)
+            ntot = torch.empty((N,), dtype=torch.int32, device=dev)
+            ws = torch.empty((int(L.gx_workspace_bytes()) // 8,), dtype=torch.int64, device=dev)
+            order = _period_order(dq, dp, t0_arr, t1, torch) if (sort and N > 64) else None
+            rc = L.gx_integrate_dopri8(C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
+                                       None if t0_arr is None else t0_arr.data_ptr(), t0s, t1, dts.data_ptr(), T, ms,
+                                       None if order is None else order.data_ptr(), lay, q.data_ptr(), p.data_ptr(),
+                                       status.data_ptr(), nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(),
+                                       stream)  # fmt: skip
+            _lib.check(rc, "gx_integrate_dopri8")
+            stats["num_accepted_steps"] = nacc.reshape(batch)
+            stats["num_steps"] = ntot.reshape(batch)
+        else:
+            raise NotImplementedError(
+                f"solver {type(solver).__name__} is not supported (SemiImplicitEuler, LeapfrogMidpoint, Dopri8)"
+            )
+    if throw:
+        bad = torch.nonzero(status != _lib.OK)
+        if bad.numel():
+            i = int(bad[0, 0])
+            code = int(status[i])
+            why = {1: "max_steps reached", 2: "non-finite state"}.get(code, f"status {code}")
+            raise RuntimeError(f"integration failed for particle {i} of {N}: {why} ({bad.shape[0]} failed in total)")
+    if layout == "NT3":
+        q = q.reshape(*batch, T, 3)
+        p = p.reshape(*batch, T, 3)
+    return restore(q), restore(p), status.reshape(batch), stats
+
+
+def _energy(pot, q, p):
+    torch = _lib.require_cuda()
+    dq, restore = _to_device(q)
+    dp, _ = _to_device(p)
+    batch = tuple(dq.shape[:-1])
+    dq = dq.reshape(-1, 3).contiguous()
+    dp = dp.reshape(-1, 3).contiguous()
+    E = torch.empty((dq.shape[0],), dtype=torch.float64, device=dq.device)
+    P = pot.c_struct()
+    with torch.cuda.device(dq.device):
+        rc = _lib.lib().gx_energy_angmom(C.byref(P), dq.data_ptr(), dp.data_ptr(), dq.shape[0], E.data_ptr(), None,
+                                         torch.cuda.current_stream().cuda_stream)  # fmt: skip
+    _lib.check(rc, "gx_energy_angmom")
+    return restore(E.reshape(batch))
+
+
+# ------------------------------------------------------------------------------------------------
+# OrbitSolver / Integrator
+
+
+@dataclasses.dataclass(frozen=True)
+class OrbitSolver:
+    """orbit/solver.py:121-141.  Defaults: Dopri8, PIDController(1e-8, 1e-8), max_steps=2**16."""
+
+    solver: Any = dataclasses.field(default_factory=Dopri8)
+    stepsize_controller: Any = dataclasses.field(default_factory=lambda: PIDController(rtol=1e-8, atol=1e-8))
+    max_steps: int | None = 2**16
+    event: Any = None
+
+    def solve(self, field, w0, t0, t1=None, /, *, saveat=None, dt0=None, max_steps="default", args=None,
+              dense=False, unbatch_time=False, throw=True, sort=True):  # fmt: skip
+        """``OrbitSolver.solve(field, (q0, p0), t0, t1, saveat=ts, dt0=..., max_steps=...)``.
+
+        Like orbit/solver.py:774-803; when ``w0`` carries a time, the 3-argument form
+        ``solve(field, w0, t1)`` is accepted (orbit/solver.py:431-442).
+        """
+        if args is not None or dense or self.event is not None:
+            raise NotImplementedError("args / dense=True / events are not supported by the CUDA path")
+        pot = _as_potential(field)
+        q0, p0, tw = _split_w0(w0)
+        if t1 is None:
+            if tw is None:
+                raise ValueError("solve(field, w0, t1) needs w0 to carry a time")
+            t0, t1 = tw, t0
+        t1f = float(np.asarray(t1))
+        ts = np.atleast_1d(np.asarray([t1f] if saveat is None else saveat, dtype=np.float64))
+        ms = self.max_steps if max_steps == "default" else max_steps
+        q, p, status, stats = _integrate(pot, q0, p0, t0, t1f, ts, solver=self.solver,
+                                         controller=self.stepsize_controller, dt0=dt0, max_steps=ms, throw=throw,
+                                         sort=sort)  # fmt: skip
+        if unbatch_time and ts.shape[0] == 1:
+            q, p = q[..., 0, :], p[..., 0, :]
+        return Solution(t0=t0, t1=t1f, ts=ts, ys=(q, p), stats=stats, result=status)
+
+
+def _default_integrator_solver() -> OrbitSolver:
+    # legacy/integrator.py:37-39,161-168: Dopri8, rtol = atol = 1e-7
+    return OrbitSolver(solver=Dopri8(), stepsize_controller=PIDController(rtol=1e-7, atol=1e-7))
+
+
+@dataclasses.dataclass(frozen=True)
+class Integrator:
+    """legacy/integrator.py:42-245.  ``diffeq_kw`` defaults to ``max_steps=None`` (:170-174)."""
+
+    dynamics_solver: OrbitSolver = dataclasses.field(default_factory=_default_integrator_solver)
+    diffeq_kw: dict = dataclasses.field(default_factory=lambda: {"max_steps": None})
+
+    def __call__(self, field, w0, t0, t1, /, *, saveat=None, dense=False, throw=True):
+        if dense:
+            raise NotImplementedError("dense=True (interpolated orbits) is not supported by the CUDA path")
+        kw = dict(self.diffeq_kw)
+        q0, p0, _ = _split_w0(w0)
+        sol = self.dynamics_solver.solve(field, (q0, p0), t0, t1, saveat=saveat, dt0=kw.get("dt0"),
+                                         max_steps=kw.get("max_steps", "default"), throw=throw)  # fmt: skip
+        q, p = sol.ys
+        if saveat is None:
+            return PhaseSpaceCoordinate(q[..., 0, :], p[..., 0, :], sol.t1)
+        return PhaseSpaceCoordinate(q, p, sol.ts)
+
+
+default_integrator = Integrator()
+
+
+def evaluate_orbit(pot, w0, t, /, *, integrator: Integrator | None = None, dense: bool = False, throw=True) -> Orbit:
+    """``gd.evaluate_orbit`` (legacy/funcs.py:42-213): integrate w0 to t[0], then t[0] -> t[-1] saving at t."""
+    if dense:
+        raise NotImplementedError("dense=True is not supported by the CUDA path")
+    pot = _as_potential(pot)
+    integrator = default_integrator if integrator is None else integrator
+    t_host = np.atleast_1d(np.asarray(t.detach().cpu() if hasattr(t, "detach") else t, dtype=np.float64))
+    q0, p0, tw0 = _split_w0(w0)
+    field = HamiltonianField(pot)
+    if tw0 is not None:
+        # integration A: w0.t -> t[0] (legacy/funcs.py:194-206); zero-length when equal
+        tw0f = np.asarray(tw0.detach().cpu() if hasattr(tw0, "detach") else tw0, dtype=np.float64)
+        if tw0f.ndim == 0 and float(tw0f) == float(t_host[0]):
+            pass
+        else:
+            w = integrator(field, (q0, p0), tw0 if tw0f.ndim else float(tw0f), float(t_host[0]), throw=throw)
+            q0, p0 = w.q, w.p
+    # integration B: t[0] -> t[-1], saveat = t (legacy/funcs.py:210)
+    w = integrator(field, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw)
+    return Orbit(q=w.q, p=w.p, t=t_host, potential=pot)
+
+
+def compute_orbit(pot_or_field, w0, ts, /, *, solver: OrbitSolver | None = None, dense: bool = False,
+                  throw=True) -> Orbit:  # fmt: skip
+    """``gd.compute_orbit`` (orbit/compute.py:28-98): same two-phase solve with an ``OrbitSolver``."""
+    if dense:
+        raise NotImplementedError("dense=True is not supported by the CUDA path")
+    pot = _as_potential(pot_or_field)
+    solver = OrbitSolver() if solver is None else solver
+    t_host = np.atleast_1d(np.asarray(ts.detach().cpu() if hasattr(ts, "detach") else ts, dtype=np.float64))
+    q0, p0, tw0 = _split_w0(w0)
+    if tw0 is not None and float(np.asarray(tw0)) != float(t_host[0]):
+        s0 = solver.solve(pot, (q0, p0), float(np.asarray(tw0)), float(t_host[0]), throw=throw)
+        q0, p0 = s0.ys[0][..., 0, :], s0.ys[1][..., 0, :]
+    sol = solver.solve(pot, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw)
+    return Orbit(q=sol.ys[0], p=sol.ys[1], t=t_host, potential=pot, status=sol.result, n_steps=sol.stats)
+
+
+# ------------------------------------------------------------------------------------------------
+# mock streams
+
+
+@dataclasses.dataclass
+class MockStreamArm:
+    """dynamics/_src/mockstream/arm.py:20-98."""
+
+    q: Any
+    p: Any
+    t: Any
+    release_time: Any
+
+    def w(self):
+        return _cat(self.q, self.p)
+
+
+class MockStream(dict):
+    """dynamics/_src/mockstream/core.py:20-84: {'lead', 'trail'}; concatenated views sorted by release time."""
+
+    def _joined(self, name):
+        arms = list(self.values())
+        import torch
+
+        parts = [getattr(a, name) for a in arms]
+        rel = [a.release_time for a in arms]
+        if isinstance(parts[0], np.ndarray):
+            order = np.argsort(np.concatenate(rel), kind="stable")
+            return np.concatenate(parts)[order]
+        order = torch.argsort(torch.cat(rel), stable=True)
+        return torch.cat(parts)[order]
+
+    @property
+    def q(self):
+        return self._joined("q")
+
+    @property
+    def p(self):
+        return self._joined("p")
+
+    @property
+    def release_time(self):
+        return self._joined("release_time")
+
+
+class AbstractStreamDF:
+    """legacy/mockstream/df/base.py:28-131.  ``rng`` supplies the random draws (see ``_draws``)."""
+
+    df_kind: int = -1
+
+    def _draws(self, rng, M: int) -> np.ndarray:
+        raise NotImplementedError
+
+    def sample(self, rng, pot, prog_orbit: Orbit, prog_mass):
+        """-> dict(lead=MockStreamArm, trail=MockStreamArm) of release conditions along ``prog_orbit``."""
+        torch = _lib.require_cuda()
+        pot = _as_potential(pot)
+        dq, restore = _to_device(prog_orbit.q)
+        dp, _ = _to_device(prog_orbit.p)
+        dq = dq.reshape(-1, 3).contiguous()
+        dp = dp.reshape(-1, 3).contiguous()
+        M = dq.shape[0]
+        ts = prog_orbit.t
+        if callable(prog_mass):  # ProgenitorMassCallable (df/progenitor.py:30-50)
+            mass = np.asarray(prog_mass(np.asarray(ts, dtype=np.float64)), dtype=np.float64)
+        else:
+            mass = np.full((M,), float(getattr(prog_mass, "value", prog_mass)))
+        dm = torch.from_numpy(np.ascontiguousarray(mass)).to(dq.device)
+        draws = rng if isinstance(rng, (np.ndarray, torch.Tensor)) else self._draws(rng, M)
+        dd, _ = _to_device(draws)
+        dd = dd.contiguous()
+        outs = [torch.empty((M, 3), dtype=torch.float64, device=dq.device) for _ in range(4)]
+        P = pot.c_struct()
+        with torch.cuda.device(dq.device):
+            rc = _lib.lib().gx_stream_release(C.byref(P), self.df_kind, dq.data_ptr(), dp.data_ptr(), dm.data_ptr(),
+                                              dd.data_ptr(), M, *[o.data_ptr() for o in outs],
+                                              torch.cuda.current_stream().cuda_stream)  # fmt: skip
+        _lib.check(rc, "gx_stream_release")
+        ql, pl, qt, pt = (restore(o) for o in outs)
+        return {"lead": MockStreamArm(ql, pl, ts, ts), "trail": MockStreamArm(qt, pt, ts, ts)}
+
+
+class FardalStreamDF(AbstractStreamDF):
+    """df/fardal15.py: k_r = 2 + 0.5 n1, k_vphi = k_r (0.3 + 0.5 n2), k_z = 0.5 n3, k_vz = 0.5 n4."""
+
+    df_kind = _lib.DF_FARDAL15
+
+    def _draws(self, rng, M):
+        return np.random.default_rng(rng).standard_normal((4, M))
+
+
+class ChenStreamDF(AbstractStreamDF):
+    """df/chen24.py: 6-D Gaussian in (Dr/r_t, phi, theta, Dv/v_esc, alpha, beta), 'no progenitor' version."""
+
+    df_kind = _lib.DF_CHEN24
+    mean = np.array([1.6, -30, 0, 1, 20, 0], dtype=np.float64)
+    cov = np.array(
+        [
+            [0.1225, 0, 0, 0, -4.9, 0],
+            [0, 529, 0, 0, 0, 0],
+            [0, 0, 144, 0, 0, 0],
+            [0, 0, 0, 0, 0, 0],
+            [-4.9, 0, 0, 0, 400, 0],
+            [0, 0, 0, 0, 0, 484],
+        ],
+        dtype=np.float64,
+    )
+
+    def _draws(self, rng, M):
+        return np.random.default_rng(rng).multivariate_normal(self.mean, self.cov, size=M, method="svd")
+
+
+@dataclasses.dataclass(frozen=True)
+class MockStreamGenerator:
+    """legacy/mockstream/mockstream_generator.py:33-275."""
+
+    df: AbstractStreamDF
+    potential: AbstractPotential
+    progenitor_integrator: Integrator = dataclasses.field(default_factory=Integrator)
+    stream_integrator: Integrator = dataclasses.field(default_factory=Integrator)
+
+    def run(self, rng, ts, prog_w0, prog_mass, *, vmapped: bool | None = None, throw=True):
+        """-> (MockStream, final progenitor PhaseSpaceCoordinate).
+
+        ``rng``: a seed / ``numpy.random.Generator`` (draws are made on the host with numpy), or the draws
+        themselves (Fardal: (4, M) standard normals; Chen: (M, 6) samples).  The reference's jax PRNG stream
+        is not reproduced.  ``vmapped`` is accepted for signature parity and ignored: every
+        particle is an independent lane of the work queue.
+        """
+        ts = np.asarray(ts.detach().cpu() if hasattr(ts, "detach") else ts, dtype=np.float64)
+        if ts.ndim != 1 or ts.shape[0] < 2:
+            raise ValueError("ts must be a 1-D array of at least two stripping times")
+        q0, p0, tw0 = _split_w0(prog_w0)
+        if np.ndim(q0) != 1:
+            raise ValueError("prog_w0 must be scalar")  # mockstream_generator.py:230
+        if ts[1] < ts[0]:  # cond_reverse (mockstream_generator.py:236)
+            ts = ts[::-1].copy()
+        w0 = PhaseSpaceCoordinate(q0, p0, ts[0] if tw0 is None else tw0)
+        # progenitor orbit saved at the stripping times (:239)
+        prog_o = evaluate_orbit(self.potential, w0, ts, integrator=self.progenitor_integrator, throw=throw)
+        mock0 = self.df.sample(rng, self.potential, prog_o, prog_mass)
+        # stream particles: release time -> t_f = ts[-1] + 1e-3, keep the final state (:88,139)
+        t_f = float(ts[-1]) + 1e-3
+        field = HamiltonianField(self.potential)
+        arms = {}
+        for name in ("lead", "trail"):
+            arm = mock0[name]
+            w = self.stream_integrator(field, (arm.q, arm.p), ts, t_f, throw=throw)
+            tt = np.ones_like(ts) * ts[-1]
+            arms[name] = MockStreamArm(w.q, w.p, tt, arm.release_time)
+        return MockStream(arms), prog_o[-1]
+
+
+__all__ = [
+    "SemiImplicitEuler", "LeapfrogMidpoint", "Dopri8", "ConstantStepSize", "PIDController",
+    "PhaseSpacePosition", "PhaseSpaceCoordinate", "Orbit", "Solution", "HamiltonianField",
+    "OrbitSolver", "Integrator", "default_integrator", "evaluate_orbit", "compute_orbit",
+    "MockStreamArm", "MockStream", "AbstractStreamDF", "FardalStreamDF", "ChenStreamDF", "MockStreamGenerator",
+]  # fmt: skip

@@ -1,0 +1,160 @@
+/* galax_b200.h -- C ABI of the B200-native galax hot path (libgalax_b200.so).
+ *
+ * The reference (GalacticDynamics/galax) is pure Python on JAX: it has no FFI for this path today.
+ * Each entry point below replaces one piece of the reference's Python/JAX stack; the comment above it
+ * cites the reference interface it stands in for (paths relative to /root/reference/src/galax/).
+ * INTEGRATION.md shows the ctypes / XLA-FFI binding a galax maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - `gx_*` entries take DEVICE pointers to contiguous row-major fp64 and only ENQUEUE work on
+ *     `stream` (no synchronisation, no allocation); `gx_host_*` entries take HOST pointers, copy
+ *     in/out and synchronise before returning;
+ *   - return value: 0 on success, <0 on an argument / CUDA error (gx_strerror); per-particle
+ *     outcomes (max_steps reached, non-finite state) are reported in the `status` array;
+ *   - units: whatever unit system the potential parameters are expressed in (galax: kpc, Myr, Msun);
+ *   - re-entrant: no global mutable state; the potential is passed by value into each launch
+ *     (kernel-parameter constant bank).
+ */
+#ifndef GALAX_B200_H
+#define GALAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GX_VERSION 100
+
+/* component kinds: potential/_src/builtin/{miyamotonagai,hernquist,nfw/base,powerlawcutoff}.py */
+#define GX_KIND_MIYAMOTO_NAGAI 0 /* p = (m_tot, a, b)       */
+#define GX_KIND_HERNQUIST 1      /* p = (m_tot, r_s)        (r_s = 0: Kepler) */
+#define GX_KIND_NFW 2            /* p = (m, r_s)            */
+#define GX_KIND_POWERLAWCUTOFF 3 /* p = (m_tot, alpha, r_c) */
+#define GX_MAX_COMPONENTS 14
+
+typedef struct {
+    int32_t kind;
+    int32_t reserved;
+    double p[4];
+} gx_component;
+
+/* A composite potential = sum of components (potential/_src/base_multi.py:39-82).  MN3 disks are passed as
+ * their three Miyamoto-Nagai components (builtin/mn3.py:90-119).  G = pot.constants["G"].value. */
+typedef struct {
+    int32_t n;
+    int32_t reserved;
+    double G;
+    gx_component c[GX_MAX_COMPONENTS];
+} gx_potential;
+
+/* `what` bit mask for gx_potential_eval */
+#define GX_PHI 1u  /* potential/_src/base.py:113-136  _potential            -> phi[N]      */
+#define GX_GRAD 2u /* potential/_src/base.py:170-179  _gradient             -> grad[N,3]   */
+#define GX_ACC 4u  /* potential/_src/register_funcs.py:327-340 acceleration -> acc[N,3]    */
+#define GX_HESS 8u /* potential/_src/base.py:230-239  _hessian              -> hess[N,3,3] */
+
+/* per-particle status */
+#define GX_OK 0
+#define GX_MAX_STEPS_REACHED 1 /* diffrax RESULTS.max_steps_reached */
+#define GX_NONFINITE 2         /* state became inf/nan              */
+
+/* error codes */
+#define GX_ERR_BADARG (-1)
+#define GX_ERR_UNSUPPORTED (-2)
+#define GX_ERR_CUDA (-3)
+
+/* fixed-step schemes */
+#define GX_SCHEME_SEMI_IMPLICIT_EULER 0 /* diffrax.SemiImplicitEuler (the reference's "leapfrog") */
+#define GX_SCHEME_LEAPFROG_MIDPOINT 1   /* diffrax.LeapfrogMidpoint                               */
+
+/* output layout of saved states, element (particle n, save k, component c) */
+#define GX_LAYOUT_NT3 0 /* [N,T,3]  the reference's (*batch, T, 3), orbit/register_dfx.py:80-82 */
+#define GX_LAYOUT_T3N 1 /* [T,3,N]  structure-of-arrays: fully coalesced stores                 */
+
+/* Step-size controller = diffrax.PIDController as galax constructs it
+ * (dynamics/_src/legacy/integrator.py:37-39,161-168; dynamics/_src/orbit/solver.py:121-141). */
+typedef struct {
+    double rtol, atol;
+    double pcoeff, icoeff, dcoeff;       /* defaults 0, 1, 0 */
+    double safety, factormin, factormax; /* defaults 0.9, 0.2, 10 */
+    double dtmin, dtmax;                 /* <= 0: unset */
+    int32_t force_dtmin;
+    int32_t reserved;
+    double dt0; /* <= 0 or NaN: Hairer initial-step heuristic (diffrax dt0=None) */
+} gx_pid;
+
+const char *gx_strerror(int code);
+int gx_version(void);
+
+/* Bulk evaluation.  Replaces pot.potential/gradient/acceleration/hessian on (N,3) arrays:
+ * potential/_src/register_funcs.py:33-98,276-288,327-340 -> AbstractCompositePotential._gradient/_hessian
+ * (base_multi.py:48-82).  Unrequested outputs may be NULL.  `t` is accepted for signature parity; the
+ * supported parameters are time-independent (ConstantParameter). */
+int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what, double *phi,
+                      double *grad, double *acc, double *hess, void *stream);
+
+/* Fixed-step integration.  Replaces
+ *   OrbitSolver(solver=dfx.SemiImplicitEuler(), stepsize_controller=dfx.ConstantStepSize())
+ *       .solve(HamiltonianField(pot), (q0, p0), t0, t1, dt0=dt0, max_steps=..., saveat=ts)
+ * (dynamics/_src/orbit/field_hamiltonian.py:256-301, dynamics/_src/orbit/solver.py:774-803 -> diffrax.diffeqsolve).
+ * q0,p0: [N,3]; ts: [T] device array of save times inside [t0,t1] (ascending in the direction of integration);
+ * q,p: saved states in `layout`; status: [N] int32 (may be NULL); max_steps < 0 = unbounded. */
+int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0, double t1,
+                       double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
+                       double *q, double *p, int32_t *status, void *stream);
+
+/* Adaptive integration, per-particle step control.  Replaces
+ *   OrbitSolver(dfx.Dopri8(), stepsize_controller=dfx.PIDController(rtol, atol)).solve(lstrat.VMap, field, ...)
+ * and the per-particle solves of Integrator/evaluate_orbit (dynamics/_src/legacy/integrator.py:179-245,449-527;
+ * dynamics/_src/legacy/funcs.py:186-213).
+ * t0: [N] device array of per-particle start times, or NULL to use the scalar t0_scalar.
+ * order: optional [N] int32 processing order (e.g. sorted by expected step count); NULL = identity.
+ * n_accepted / n_attempted: [N] int32 step counters (may be NULL).
+ * workspace: device buffer of gx_workspace_bytes() bytes (work-queue ticket), zeroed by the call. */
+int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,
+                        const double *t0, double t0_scalar, double t1, const double *ts, int32_t T, int64_t max_steps,
+                        const int32_t *order, int32_t layout, double *q, double *p, int32_t *status,
+                        int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream);
+int64_t gx_workspace_bytes(void);
+
+/* Stream release (distribution function).  Replaces FardalStreamDF._sample / ChenStreamDF._sample given the random
+ * draws (dynamics/_src/legacy/mockstream/df/fardal15.py:49-94, df/chen24.py:61-137; tidal radius
+ * dynamics/_src/cluster/radius.py:198-215; omega dynamics/_src/register_api.py:77-88).
+ * prog_q, prog_p: [M,3] progenitor orbit at the stripping times; prog_mass: [M];
+ * draws: Fardal [4,M] standard normals (kr, kvphi, kz, kvz); Chen [M,6] multivariate-normal samples.
+ * outputs: [M,3] each. */
+#define GX_DF_FARDAL15 0
+#define GX_DF_CHEN24 1
+int gx_stream_release(const gx_potential *pot, int32_t df, const double *prog_q, const double *prog_p,
+                      const double *prog_mass, const double *draws, int64_t M, double *q_lead, double *p_lead,
+                      double *q_trail, double *p_trail, void *stream);
+
+/* Derived diagnostics on device: E = |p|^2/2 + Phi(q) and L = q x p for [N,3] states (used for the energy-drift
+ * report; coordinates/_src/pscs/base.py total_energy / angular_momentum). */
+int gx_energy_angmom(const gx_potential *pot, const double *q, const double *p, int64_t N, double *energy,
+                     double *angmom, void *stream);
+
+/* ---- host-buffer convenience entries (allocate, copy in, run, copy out, synchronise) ---- */
+int gx_host_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what,
+                           double *phi, double *grad, double *acc, double *hess);
+int gx_host_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
+                            double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
+                            double *q, double *p, int32_t *status);
+int gx_host_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0,
+                             int64_t N, const double *t0, double t0_scalar, double t1, const double *ts, int32_t T,
+                             int64_t max_steps, double *q, double *p, int32_t *status, int32_t *n_accepted,
+                             int32_t *n_attempted);
+
+/* ---- measurement helpers ---- */
+/* FP64 FMA-pipe peak: every thread runs `iters` rounds of 8 independent DFMA chains.  Returns the number of
+ * DFMA instructions issued per thread (iters*8*unroll) via *fma_per_thread; time it with events on `stream`. */
+int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, int64_t *fma_per_thread, void *stream);
+/* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x) */
+int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GALAX_B200_H */

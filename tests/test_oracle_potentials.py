@@ -1,0 +1,153 @@
+"""CPU: the oracle (numpy + C) against the reference's own known-answer tests and invariants."""
+import json
+from pathlib import Path
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+from oracle import cref
+from oracle import potentials as op
+
+KATS = json.loads((Path(__file__).parent / "golden" / "potential_kats.json").read_text())
+
+
+def build(m):
+    kind = m["kind"]
+    if kind in op.MODELS:
+        return op.MODELS[kind]()
+    single = {"MN": op.KIND_MN, "Hernquist": op.KIND_HERNQUIST, "NFW": op.KIND_NFW, "PowerLawCutoff": op.KIND_PLC}
+    if kind in single:
+        return op.single(single[kind], *m["params"])
+    return op.mn3_potential(*m["params"], sech2=kind.endswith("Sech2"), positive_density=m["positive_density"])
+
+
+def evaluators():
+    def numpy_eval(p, x):
+        return dict(phi=op.potential(p, x), grad=op.gradient(p, x), hess=op.hessian(p, x))
+
+    def c_eval(p, x):
+        o = cref.potential_eval(p, x, ("phi", "grad", "hess"))
+        return dict(phi=o["phi"][0], grad=o["grad"][0], hess=o["hess"][0])
+
+    return {"numpy": numpy_eval, "c": c_eval}
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+@pytest.mark.parametrize("case", KATS["cases"], ids=lambda c: c["name"])
+def test_reference_kats(case, impl):
+    """Same tolerance as the reference's tests: atol=1e-8 + numpy's default rtol=1e-5."""
+    p = build(case["model"])
+    x = np.array(KATS["x"])
+    out = evaluators()[impl](p, x)
+    assert np.isclose(out["phi"], case["potential"], atol=1e-8)
+    assert np.allclose(out["grad"], case["gradient"], atol=1e-8)
+    assert np.allclose(out["hess"], case["hessian"], atol=1e-8)
+    tr = np.trace(out["hess"])
+    assert np.isclose(tr / (4 * np.pi * p.G), case["density"], atol=1e-8)
+    assert np.allclose(out["hess"] - np.eye(3) * tr / 3, case["tidal_tensor"], atol=1e-8)
+
+
+def test_full_precision_kats():
+    """The two KATs the reference prints to 12+ digits must match to ~1e-13 relative."""
+    x = np.array(KATS["x"])
+    for case in KATS["cases"]:
+        if case["name"] in ("MilkyWayPotential2022", "MN3Sech2", "MN3Exponential"):
+            g = op.gradient(build(case["model"]), x)
+            assert np.allclose(g, case["gradient"], rtol=5e-11, atol=0)  # printed to 12-13 digits
+
+
+def test_kepler_doctest():
+    e = KATS["extra"][0]
+    g = op.gradient(build(e["model"]), np.array(e["x"], float))
+    assert np.allclose(g, e["gradient"], atol=1e-8)
+
+
+@pytest.mark.parametrize("name", list(op.MODELS))
+def test_c_matches_numpy(name):
+    rng = np.random.default_rng(1)
+    r = 10 ** rng.uniform(-1, 2, 2000)
+    v = rng.normal(size=(2000, 3))
+    xyz = v / np.linalg.norm(v, axis=1, keepdims=True) * r[:, None]
+    pot = op.MODELS[name]()
+    o = cref.potential_eval(pot, xyz)
+    assert np.allclose(o["phi"], op.potential(pot, xyz), rtol=2e-15, atol=0)
+    assert np.allclose(o["grad"], op.gradient(pot, xyz), rtol=1e-13, atol=0)
+    assert np.allclose(o["hess"], op.hessian(pot, xyz), rtol=1e-11, atol=1e-22)
+    assert np.array_equal(o["acc"], -o["grad"])
+
+
+def test_invariants_like_reference():
+    """tests/unit/potential/test_base.py:120-165: batch == scalar, tr(H) = 4 pi G rho, acc = -grad."""
+    bx = np.array([[1.0, 2, 3], [4, 5, 6], [7, 8, 9]])
+    for f in op.MODELS.values():
+        pot = f()
+        g = op.gradient(pot, bx)
+        for i in range(3):
+            assert np.array_equal(op.gradient(pot, bx[i]), g[i])
+        assert np.allclose(op.laplacian(pot, bx), 4 * np.pi * pot.G * op.density(pot, bx))
+        assert np.array_equal(op.acceleration(pot, bx), -g)
+        H = op.hessian(pot, bx)
+        assert np.allclose(H, np.swapaxes(H, -1, -2))
+
+
+def _mp_potential(pot, x, y, z):
+    """The reference's *potential* in 40-digit arithmetic (for differentiating it independently)."""
+    G = mp.mpf(pot.G)
+    tiny = mp.mpf(op.TINY)
+    total = mp.mpf(0)
+    for c in pot.components:
+        p = [mp.mpf(v) for v in c.params]
+        r = mp.sqrt(x * x + y * y + z * z + tiny)
+        if c.kind == op.KIND_MN:
+            total += -G * p[0] / mp.sqrt(x * x + y * y + (mp.sqrt(z * z + p[2] ** 2) + p[1]) ** 2)
+        elif c.kind == op.KIND_HERNQUIST:
+            total += -G * p[0] / (r + p[1])
+        elif c.kind == op.KIND_NFW:
+            s = r / p[1]
+            total += -G * p[0] / p[1] * mp.log1p(s) / s
+        else:
+            ah = p[1] / 2
+            s2 = (r / p[2]) ** 2
+            ga = mp.mpf("1.5") - ah
+            t1 = G * p[0] * mp.gammainc(ga, 0, s2) * (ah - mp.mpf("1.5")) / (r * mp.gamma(mp.mpf("2.5") - ah))
+            t2 = G * p[0] * mp.gammainc(1 - ah, 0, s2) / (p[2] * mp.gamma(ga))
+            total += t1 + t2 - G * p[0] * mp.gamma(1 - ah) / (p[2] * mp.gamma(ga))
+    return total
+
+
+@pytest.mark.parametrize("name", list(op.MODELS))
+def test_hand_derivatives_vs_mpmath_differentiation(name):
+    """grad / Hessian closed forms == numerical derivatives of the reference's potential (what jax.grad gives)."""
+    mp.mp.dps = 40
+    pot = op.MODELS[name]()
+    for pt in ([1.0, 2.0, 3.0], [8.0, 0.3, -0.2], [0.05, -0.02, 0.01], [30.0, 40.0, -25.0]):
+        f = lambda x, y, z: _mp_potential(pot, x, y, z)  # noqa: E731
+        g = [mp.diff(f, pt, tuple(int(i == k) for i in range(3))) for k in range(3)]
+        gg = op.gradient(pot, np.array(pt))
+        assert np.allclose([float(v) for v in g], gg, rtol=5e-14, atol=0), (name, pt)
+        H = op.hessian(pot, np.array(pt))
+        for a in range(3):
+            for b in range(a, 3):
+                order = [0, 0, 0]
+                order[a] += 1
+                order[b] += 1
+                h = float(mp.diff(f, pt, tuple(order)))
+                assert np.isclose(H[a, b], h, rtol=1e-11, atol=1e-13 * np.abs(H).max()), (name, pt, a, b)
+        assert np.isclose(float(f(*[mp.mpf(v) for v in pt])), op.potential(pot, np.array(pt)), rtol=1e-14)
+
+
+def test_gammainc_c_vs_scipy():
+    from scipy import special as sps
+
+    for a in (0.6, 0.1, 1.05, 1.5):
+        for x in np.logspace(-8, 2.5, 120):
+            assert np.isclose(cref.gammainc(a, x), sps.gammainc(a, x), rtol=5e-15, atol=1e-300)
+
+
+def test_mn3_parameters_match_survey():
+    comps = op.milky_way_potential_2022().components
+    assert np.allclose([c.params[0] for c in comps[:3]], [7.872307e9, -2.75625222e11, 3.20618419e11], rtol=1e-7)
+    assert np.allclose([c.params[1] for c in comps[:3]], [1.5259432, 6.78276444, 5.89479962], rtol=1e-8)
+    assert comps[0].params[2] == pytest.approx(0.20663742603550295, rel=1e-15)
+    assert comps[5].params[1] == 68.8867 * 0.001

@@ -642,11 +642,12 @@ int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int6
     DevPot D; Model model;
     int rc = build_devpot(pot, D, model);
     if (rc) return rc;
-    if (N < 0 || (N > 0 && !xyz)) return GX_ERR_BADARG;
+    if (N < 0) return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    if (!xyz) return GX_ERR_BADARG;
     if (((what & GX_PHI) && !phi) || ((what & GX_GRAD) && !grad) || ((what & GX_ACC) && !acc) ||
         ((what & GX_HESS) && !hess))
         return GX_ERR_BADARG;
-    if (N == 0) return 0;
     EvalArgs a{xyz, phi, grad, acc, hess, (long long)N, what};
     const int block = 256;
     long long want = (N + block - 1) / block;
@@ -662,7 +663,7 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     DevPot D; Model model;
     int rc = build_devpot(pot, D, model);
     if (rc) return rc;
-    if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
+    if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
     if (scheme != GX_SCHEME_SEMI_IMPLICIT_EULER && scheme != GX_SCHEME_LEAPFROG_MIDPOINT) return GX_ERR_BADARG;
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
@@ -691,7 +692,7 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     DevPot D; Model model;
     int rc = build_devpot(pot, D, model);
     if (rc) return rc;
-    if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (T > 0 && (!ts || !q || !p)) || !workspace)
+    if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
         return GX_ERR_BADARG;
     if (!(pid->rtol >= 0.0) || !(pid->atol >= 0.0) || (pid->rtol == 0.0 && pid->atol == 0.0)) return GX_ERR_BADARG;
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;

@@ -92,14 +92,14 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             double u = r + c.c;
             fs = fma(c.GM * rinv, rcp_fast(u * u), fs);  // GM / ((r+c)^2 r)
         }
-        const double rinv3 = rinv * rinv * rinv;
+        const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
 #pragma unroll
         for (int i = 0; i < C::kNFW; ++i) {
             if (!C::is_static && i >= P.n_nfw) break;
             const DevNFW &c = P.nfw[i];
             double s = r * c.inv_rs;
             double m = nfw_menc_shape(s, rcp_fast(1.0 + s));
-            fs = fma(c.GM * m, rinv3, fs);  // GM m(s) / r^3
+            fs = fma((c.GM * m) * rinv, rinv2, fs);  // GM m(s) / r^3
         }
 #pragma unroll
         for (int i = 0; i < C::kPLC; ++i) {
@@ -107,7 +107,7 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             const DevPLC &c = P.plc[i];
             double s = r * c.inv_rc;
             double Pg = gammainc_P(c.a, c.lgam_a, s * s, nullptr);
-            fs = fma(c.GM * Pg, rinv3, fs);  // GM P(a, s^2) / r^3
+            fs = fma((c.GM * Pg) * rinv, rinv2, fs);  // GM P(a, s^2) / r^3
         }
     }
     gx_ = (fxy + fs) * x;

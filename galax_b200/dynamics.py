@@ -293,8 +293,8 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             why = {1: "max_steps reached", 2: "non-finite state"}.get(code, f"status {code}")
             raise RuntimeError(f"integration failed for particle {i} of {N}: {why} ({bad.shape[0]} failed in total)")
     if layout == "NT3":
-        q = q.reshape(*batch, T, 3)
-        p = p.reshape(*batch, T, 3)
+        q = q.reshape(batch + (T, 3))
+        p = p.reshape(batch + (T, 3))
     return restore(q), restore(p), status.reshape(batch), stats
 
 
@@ -311,7 +311,7 @@ def _energy(pot, q, p):
         rc = _lib.lib().gx_energy_angmom(C.byref(P), dq.data_ptr(), dp.data_ptr(), dq.shape[0], E.data_ptr(), None,
                                          torch.cuda.current_stream().cuda_stream)  # fmt: skip
     _lib.check(rc, "gx_energy_angmom")
-    return restore(E.reshape(batch))
+    return restore(E.reshape(tuple(batch)))
 
 
 # ------------------------------------------------------------------------------------------------

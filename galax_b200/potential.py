@@ -97,7 +97,7 @@ class AbstractPotential:
             )
         _lib.check(rc, "gx_potential_eval")
         shapes = {"phi": (), "grad": (3,), "acc": (3,), "hess": (3, 3)}
-        return {k: restore(v.reshape(*batch, *shapes[k])) for k, v in out.items()}
+        return {k: restore(v.reshape(tuple(batch) + shapes[k])) for k, v in out.items()}
 
     def potential(self, q, t=0.0):
         """``pot.potential(q, t)`` (api.py:27-110, register_funcs.py:33-80)."""

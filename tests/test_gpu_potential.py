@@ -1,0 +1,167 @@
+"""GPU: bulk potential / gradient / Hessian kernel (K1) against the oracle, through the C ABI."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import galax_b200.potential as gp
+from oracle import potentials as op
+
+pytestmark = pytest.mark.gpu
+
+KATS = json.loads((Path(__file__).parent / "golden" / "potential_kats.json").read_text())
+PAIRS = {
+    "MilkyWayPotential": (gp.MilkyWayPotential, op.milky_way_potential),
+    "MilkyWayPotential2022": (gp.MilkyWayPotential2022, op.milky_way_potential_2022),
+    "BovyMWPotential2014": (gp.BovyMWPotential2014, op.bovy_mw_potential_2014),
+}
+
+
+def build_gp(m):
+    kind = m["kind"]
+    if kind in PAIRS:
+        return PAIRS[kind][0]()
+    if kind == "MN":
+        return gp.MiyamotoNagaiPotential(*m["params"])
+    if kind == "Hernquist":
+        return gp.HernquistPotential(*m["params"])
+    if kind == "NFW":
+        return gp.NFWPotential(*m["params"])
+    if kind == "PowerLawCutoff":
+        return gp.PowerLawCutoffPotential(*m["params"])
+    cls = gp.MN3Sech2Potential if kind.endswith("Sech2") else gp.MN3ExponentialPotential
+    return cls(*m["params"], positive_density=m["positive_density"])
+
+
+def points(n, seed, lo=-1.0, hi=2.0):
+    rng = np.random.default_rng(seed)
+    r = 10 ** rng.uniform(lo, hi, n)
+    v = rng.normal(size=(n, 3))
+    return v / np.linalg.norm(v, axis=1, keepdims=True) * r[:, None]
+
+
+@pytest.mark.parametrize("case", KATS["cases"], ids=lambda c: c["name"])
+def test_reference_kats_on_gpu(case):
+    pot = build_gp(case["model"])
+    x = np.array(KATS["x"])
+    assert np.isclose(pot.potential(x), case["potential"], atol=1e-8)
+    assert np.allclose(pot.gradient(x), case["gradient"], atol=1e-8)
+    assert np.allclose(pot.acceleration(x), -np.array(case["gradient"]), atol=1e-8)
+    assert np.allclose(pot.hessian(x), case["hessian"], atol=1e-8)
+    assert np.isclose(pot.density(x), case["density"], atol=1e-8)
+    assert np.allclose(pot.tidal_tensor(x), case["tidal_tensor"], atol=1e-8)
+
+
+@pytest.mark.parametrize("name", list(PAIRS))
+def test_bulk_eval_matches_oracle(name):
+    """r log-uniform in [0.1, 100] kpc (C5's distribution).  fp64: few-ulp agreement."""
+    cls, ofun = PAIRS[name]
+    pot, opot = cls(), ofun()
+    xyz = points(20000, seed=5)
+    g, go = pot.gradient(xyz), op.gradient(opot, xyz)
+    gscale = np.linalg.norm(go, axis=1, keepdims=True)
+    assert (np.abs(g - go) / gscale).max() < 3e-15
+    assert np.array_equal(pot.acceleration(xyz), -g)
+    phi, phio = pot.potential(xyz), op.potential(opot, xyz)
+    assert np.abs(phi / phio - 1).max() < 3e-15
+    H, Ho = pot.hessian(xyz), op.hessian(opot, xyz)
+    hscale = np.abs(Ho).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(H - Ho) / hscale).max() < 2e-13
+    assert np.array_equal(H, np.swapaxes(H, 1, 2))
+    # reference invariants (tests/unit/potential/test_base.py:120-165)
+    assert np.allclose(pot.laplacian(xyz), 4 * np.pi * pot.G * pot.density(xyz), rtol=1e-14)
+    assert np.allclose(pot.d2potential_dr2(xyz), op.d2potential_dr2(opot, xyz), rtol=1e-11, atol=1e-18)
+    assert np.allclose(pot.dpotential_dr(xyz), op.dpotential_dr(opot, xyz), rtol=1e-13)
+
+
+def test_generic_composite_path():
+    """A composite that matches none of the three specialised models takes the runtime-count kernel."""
+    pot = gp.CompositePotential(
+        disk=gp.MiyamotoNagaiPotential(5e10, 3.0, 0.3), disk2=gp.MiyamotoNagaiPotential(1e10, 6.0, 0.5),
+        bulge=gp.HernquistPotential(4e9, 0.8), halo=gp.NFWPotential(6e11, 18.0), halo2=gp.NFWPotential(1e11, 40.0),
+        bar=gp.PowerLawCutoffPotential(3e9, 1.2, 2.5),
+    )
+    opot = op.Potential(
+        (op.Component(op.KIND_MN, (5e10, 3.0, 0.3)), op.Component(op.KIND_MN, (1e10, 6.0, 0.5)),
+         op.Component(op.KIND_HERNQUIST, (4e9, 0.8)), op.Component(op.KIND_NFW, (6e11, 18.0)),
+         op.Component(op.KIND_NFW, (1e11, 40.0)), op.Component(op.KIND_PLC, (3e9, 1.2, 2.5)))
+    )
+    xyz = points(5000, seed=6)
+    go = op.gradient(opot, xyz)
+    assert (np.abs(pot.gradient(xyz) - go) / np.linalg.norm(go, axis=1, keepdims=True)).max() < 6e-15
+    assert np.abs(pot.potential(xyz) / op.potential(opot, xyz) - 1).max() < 6e-15
+    Ho = op.hessian(opot, xyz)
+    assert (np.abs(pot.hessian(xyz) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 2e-13
+
+
+def test_edge_cases():
+    pot = gp.MilkyWayPotential()
+    assert pot.gradient(np.zeros((0, 3))).shape == (0, 3)
+    # origin: finite (safe_sqrt semantics), and zero by symmetry
+    g0 = pot.gradient(np.zeros((1, 3)))
+    assert np.isfinite(g0).all() and np.all(g0 == 0.0)
+    assert np.isfinite(pot.hessian(np.array([[1e-3, 0, 0]]))).all()
+    # batch shapes and scalar == batch
+    x = np.arange(24.0).reshape(2, 4, 3) + 1
+    g = pot.gradient(x)
+    assert g.shape == (2, 4, 3) and np.array_equal(pot.gradient(x[1, 2]), g[1, 2])
+    assert pot.hessian(x).shape == (2, 4, 3, 3) and pot.potential(x).shape == (2, 4)
+    # huge radii stay finite
+    assert np.isfinite(pot.gradient(np.array([[1e6, -2e6, 3e5]]))).all()
+    # small-s NFW series branch is continuous with the log1p branch
+    halo = gp.NFWPotential(5.4e11, 15.62)
+    ohalo = op.single(op.KIND_NFW, 5.4e11, 15.62)
+    xs = np.array([[r, 0.0, 0.0] for r in (1e-6, 1e-3, 0.3, 0.3124, 0.3125, 1.0)])
+    assert np.allclose(halo.gradient(xs)[:, 0], op.gradient(ohalo, xs)[:, 0], rtol=1e-14)
+
+
+def test_torch_cuda_tensors_stay_on_device():
+    import torch
+
+    pot = gp.MilkyWayPotential2022()
+    x = torch.tensor(points(1000, seed=7), device="cuda")
+    a = pot.acceleration(x)
+    assert isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64
+    assert np.array_equal(a.cpu().numpy(), pot.acceleration(x.cpu().numpy()))
+
+
+def test_fast_math_primitives(built_lib):
+    """MUFU-seeded rcp / rsqrt / log1p / incomplete gamma: max relative error in ulp-ish units."""
+    import torch
+    from scipy import special as sps
+
+    from galax_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10 ** rng.uniform(-300, 300, 20000), 10 ** rng.uniform(-3, 3, 20000), [2.2250738585072014e-308, 1.0, 4.0]])
+    dx = torch.tensor(x, device="cuda")
+    out = torch.empty_like(dx)
+
+    def run(op_, a=1.0, src=dx):
+        o = torch.empty_like(src)
+        rc = built_lib.gx_debug_math(op_, a, src.data_ptr(), src.numel(), o.data_ptr(), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        return o.cpu().numpy()
+
+    assert np.abs(run(0) * x - 1).max() < 3e-16
+    assert np.abs(run(1) * np.sqrt(x) - 1).max() < 4e-16
+    s = np.concatenate([10 ** rng.uniform(-12, 6, 40000), [0.0, 1.0, 0.02, 0.4142135623730951]])
+    ds = torch.tensor(s, device="cuda")
+    l = run(2, src=ds)
+    ref = np.log1p(s)
+    assert np.abs(l[ref > 0] / ref[ref > 0] - 1).max() < 5e-16 and l[ref == 0].max() == 0.0
+    m = run(4, src=ds)
+    import mpmath as mp
+
+    mp.mp.dps = 30
+    idx = rng.choice(len(s), 400, replace=False)
+    for i in idx:
+        if s[i] > 0:
+            t = float(mp.log1p(mp.mpf(s[i])) - mp.mpf(s[i]) / (1 + mp.mpf(s[i])))
+            assert abs(m[i] / t - 1) < max(5e-16, 8e-16 / min(s[i], 1.0)), (s[i], m[i], t)  # cancellation ~eps/s above the series cut
+    for a in (0.6, 0.1, 1.05):
+        xs = 10 ** rng.uniform(-8, 2.7, 20000)
+        g = run(3, a=a, src=torch.tensor(xs, device="cuda"))
+        assert np.abs(g / sps.gammainc(a, xs) - 1).max() < 2e-14

@@ -15,7 +15,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 _SRC = _PKG / "csrc"
-LIB_PATH = _PKG / "libgalax_b200.so"
+LIB_PATH = Path(os.environ.get("GALAX_B200_LIB", _PKG / "libgalax_b200.so"))  # override: A/B builds only
 HEADER = _PKG.parent / "include" / "galax_b200.h"
 
 NVCC_FLAGS = [

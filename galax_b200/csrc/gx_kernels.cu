@@ -139,11 +139,15 @@ struct FixedArgs {
     const double *q0, *p0, *ts;
     double *q, *p;
     int *status;
-    long long N, max_steps;
+    long long N, n_steps;  // n_steps: trip count of the shared time grid (host-computed)
     long long sn, sk, sc;  // output strides (elements): particle, save, component
     double t0, t1, dt0;
-    int T;
+    int T, hit_max_steps;
 };
+
+static inline double clip_to_end_host(double tprev, double tnext, double t1) {
+    return (tnext > t1 - 1e-10) ? t1 : tnext;
+}
 
 __device__ __forceinline__ double clip_to_end(double tprev, double tnext, double t1, bool keep) {
     // diffrax _clip_to_end (fp64 tolerance 1e-10)
@@ -157,31 +161,32 @@ __device__ __forceinline__ bool finite3(double a, double b, double c) {
 
 // State update arithmetic is deliberately un-fused (__dmul_rn + __dadd_rn): diffrax computes
 // y1 = y0 + f*dt as a multiply followed by an add, and XLA:CPU does not contract them.
-template <class C, int SCHEME>
+// The time grid (tnext = tprev + dt0 accumulated in fp64, last step clipped to t1) is identical for every
+// particle; the host walks it once to get the trip count, so the device loop is a counted loop.
+template <class C, int SCHEME, bool FWD>
 __global__ void __launch_bounds__(128) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
-    const double dir = (a.t1 >= a.t0) ? 1.0 : -1.0;
-    const double T0 = a.t0 * dir, T1 = a.t1 * dir, h0 = a.dt0 * dir;
+    // integrate in tau = dir * t (diffrax flips the sign of time the same way for t1 < t0)
+    const double T0 = FWD ? a.t0 : -a.t0, T1 = FWD ? a.t1 : -a.t1, h0 = FWD ? a.dt0 : -a.dt0;
     double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
     double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
     double mqx = qx, mqy = qy, mqz = qz, mpx = px, mpy = py, mpz = pz, tm = T0;  // LeapfrogMidpoint memory
     double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int k = 0;
-    double tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+    auto load_ts = [&](int kk) { return (kk < a.T) ? (FWD ? __ldg(a.ts + kk) : -__ldg(a.ts + kk)) : INF; };
+    double tsave = load_ts(k);
     while (tsave <= T0) {  // save times equal to t0 return y0
         qo[k * a.sk] = qx; qo[k * a.sk + a.sc] = qy; qo[k * a.sk + 2 * a.sc] = qz;
         po[k * a.sk] = px; po[k * a.sk + a.sc] = py; po[k * a.sk + 2 * a.sc] = pz;
         ++k;
-        tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+        tsave = load_ts(k);
     }
     double tprev = T0, tnext = clip_to_end(T0, T0 + h0, T1, true);
-    long long n = 0;
-    int st = GX_OK;
-    while (tprev < T1) {
-        if (a.max_steps >= 0 && n >= a.max_steps) { st = GX_MAX_STEPS_REACHED; break; }
-        const double hs = (tnext - tprev) * dir;  // signed step in physical time
+    for (long long n = 0; n < a.n_steps; ++n) {
+        const double h = tnext - tprev;
+        const double hs = FWD ? h : -h;  // signed step in physical time
         double nqx, nqy, nqz, npx, npy, npz, gx_, gy_, gz_;
         if (SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER) {
             nqx = __dadd_rn(qx, __dmul_rn(px, hs));
@@ -192,7 +197,8 @@ __global__ void __launch_bounds__(128) k_integrate_fixed(const __grid_constant__
             npy = __dadd_rn(py, __dmul_rn(-gy_, hs));
             npz = __dadd_rn(pz, __dmul_rn(-gz_, hs));
         } else {
-            const double hh = (tnext - tm) * dir;
+            const double hm = tnext - tm;
+            const double hh = FWD ? hm : -hm;
             gradient<C>(P, qx, qy, qz, gx_, gy_, gz_);
             nqx = __dadd_rn(mqx, __dmul_rn(px, hh));
             nqy = __dadd_rn(mqy, __dmul_rn(py, hh));
@@ -203,22 +209,24 @@ __global__ void __launch_bounds__(128) k_integrate_fixed(const __grid_constant__
             mqx = qx; mqy = qy; mqz = qz; mpx = px; mpy = py; mpz = pz;
             tm = tprev;
         }
-        ++n;
-        while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
-            const double th = (tsave - tprev) / (tnext - tprev);
-            qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
-            qo[k * a.sk + a.sc] = __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy)));
-            qo[k * a.sk + 2 * a.sc] = __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz)));
-            po[k * a.sk] = __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px)));
-            po[k * a.sk + a.sc] = __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py)));
-            po[k * a.sk + 2 * a.sc] = __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz)));
-            ++k;
-            tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+        if (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
+            do {
+                const double th = (tsave - tprev) / (tnext - tprev);
+                qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
+                qo[k * a.sk + a.sc] = __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy)));
+                qo[k * a.sk + 2 * a.sc] = __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz)));
+                po[k * a.sk] = __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px)));
+                po[k * a.sk + a.sc] = __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py)));
+                po[k * a.sk + 2 * a.sc] = __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz)));
+                ++k;
+                tsave = load_ts(k);
+            } while (tsave <= tnext);
         }
         qx = nqx; qy = nqy; qz = nqz; px = npx; py = npy; pz = npz;
         tprev = tnext;
         tnext = clip_to_end(tprev, tprev + h0, T1, true);
     }
+    int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
     if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
     const double NANV = __longlong_as_double(0x7ff8000000000000LL);
     for (; k < a.T; ++k) {
@@ -296,8 +304,11 @@ __device__ double select_initial_step(const DevPot &P, double dir, const double 
     return fmin(100.0 * h0, h1);
 }
 
+#ifndef GX_DP8_MIN_BLOCKS
+#define GX_DP8_MIN_BLOCKS 1
+#endif
 template <class C>
-__global__ void __launch_bounds__(128) k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
+__global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     using namespace dp8;
     const unsigned FULL = 0xffffffffu;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -600,7 +611,7 @@ __global__ void k_debug_math(int op, double a, double lgam, const double *x, lon
     case 1: r = rsqrt_fast(v); break;
     case 2: r = log1p_pos(v); break;
     case 3: r = gammainc_P(a, lgam, v, nullptr); break;
-    case 4: { double inv = rcp_fast(1.0 + v); r = nfw_menc_shape(v, inv); } break;
+    case 4: r = nfw_menc_shape(v); break;
     default: r = 0.0;
     }
     out[i] = r;
@@ -671,16 +682,33 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     if (N == 0) return 0;
     FixedArgs a;
     a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p; a.status = status;
-    a.N = N; a.max_steps = max_steps; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
+    a.N = N; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
+    {   // walk the time grid exactly as the device does (same fp64 operations) to get the trip count
+        const double T0 = t0 * dir, T1 = t1 * dir, h0 = dt0 * dir;
+        double tprev = T0, tnext = clip_to_end_host(T0, T0 + h0, T1);
+        long long n = 0;
+        int hit = 0;
+        while (tprev < T1) {
+            if (max_steps >= 0 && n >= max_steps) { hit = 1; break; }
+            ++n;
+            tprev = tnext;
+            tnext = clip_to_end_host(tprev, tprev + h0, T1);
+        }
+        a.n_steps = n;
+        a.hit_max_steps = hit;
+    }
     // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers
     const int block = (N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32);
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
+    const bool fwd = dir > 0;
     if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
-        GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER><<<grid, block, 0, s>>>(D, a)));
+        if (fwd) { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, true><<<grid, block, 0, s>>>(D, a))); }
+        else { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, false><<<grid, block, 0, s>>>(D, a))); }
     } else {
-        GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT><<<grid, block, 0, s>>>(D, a)));
+        if (fwd) { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, true><<<grid, block, 0, s>>>(D, a))); }
+        else { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, false><<<grid, block, 0, s>>>(D, a))); }
     }
     return cuda_rc(cudaGetLastError());
 }

@@ -49,22 +49,22 @@ __device__ __forceinline__ double sqrt_rs(double x, double &rs) {
     return fma(r, 0.5 * rs, g);
 }
 
-// ---- log1p(s), s >= 0.  u = 1+s with the rounding error c folded back in (log1p = log u + c/u);
+// ---- log1p(s), s >= 0, given u = fl(1+s) and inv_u ~ 1/u (any accuracy >= the MUFU seed's).
+// The rounding error of the sum, c = s - (u - 1), is exact for 0 <= s < 2^52 (u - 1 is exact because 1 is a
+// multiple of ulp(u); the second difference is exact by Sterbenz) and is folded back in: log1p = log u + c/u.
 // log u by the classic argument reduction u = 2^k m, m in [sqrt(1/2), sqrt(2)), f = m-1, w = f/(2+f),
 // log m = 2 atanh(w) with the degree-7 minimax polynomial in w^2 of fdlibm's e_log.c (public domain,
 // |error| < 2^-58.45).
-__device__ __forceinline__ double log1p_pos(double s) {
+__device__ __forceinline__ double log1p_pos(double s, double u, double inv_u) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
                  Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
                  Lg7 = 1.479819860511658591e-01;
-    double u = 1.0 + s;
-    // exact rounding error of 1+s (s >= 0): for s < 1, c = s - (u-1); else c = 1 - (u-s)
-    double c = (s < 1.0) ? (s - (u - 1.0)) : (1.0 - (u - s));
+    const double c = s - (u - 1.0);
     int hi = __double2hiint(u), lo = __double2loint(u);
     int k = (hi >> 20) - 1023;
     hi &= 0x000fffff;
-    // m in [sqrt(1/2), sqrt(2)): if mantissa >= sqrt(2) (0x6a09e), halve m and bump k
+    // m in [sqrt(1/2), sqrt(2)): if the mantissa is >= sqrt(2), halve m and bump k
     int i = (hi + 0x95f64) & 0x100000;
     k += (i >> 20);
     double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
@@ -75,18 +75,22 @@ __device__ __forceinline__ double log1p_pos(double s) {
     // even / odd split of the polynomial (two shorter dependency chains)
     double t1 = z2 * fma(z2, fma(z2, Lg6, Lg4), Lg2);
     double t2 = z * fma(z2, fma(z2, fma(z2, Lg7, Lg5), Lg3), Lg1);
-    double R = t1 + t2;
-    double hfsq = 0.5 * f * f;
+    double hf = 0.5 * f;
+    double hfsq = hf * f;
     double dk = (double)k;
-    // log m = f - hfsq + w (hfsq + R);  log1p = k ln2 + log m + c/u  (c/u only needs the seed's accuracy)
-    double corr = c * rcp_seed(u);
-    double lo_part = fma(w, hfsq + R, fma(dk, ln2_lo, corr));
+    // log m = f - hfsq + w (hfsq + R);  log1p = k ln2 + log m + c/u
+    double lo_part = fma(w, hfsq + (t1 + t2), fma(dk, ln2_lo, c * inv_u));
     return fma(dk, ln2_hi, f - (hfsq - lo_part));
+}
+
+__device__ __forceinline__ double log1p_pos(double s) {
+    double u = 1.0 + s;
+    return log1p_pos(s, u, rcp_seed(u));
 }
 
 // ln(1+s) - s/(1+s), the NFW enclosed-mass shape.  Below s = 0.02 the two terms cancel to O(s^2) and the
 // alternating series sum_{k>=2} (-1)^k (k-1)/k s^k is used instead (13 terms: 0.02^12 < 5e-21).
-__device__ __forceinline__ double nfw_menc_shape(double s, double inv_1ps) {
+__device__ __forceinline__ double nfw_menc_shape(double s) {
     if (s < 0.02) {
         double p = 12.0 / 13.0;  // k = 13 (odd -> negative sign applied below)
         p = fma(-p, s, 11.0 / 12.0);
@@ -102,7 +106,9 @@ __device__ __forceinline__ double nfw_menc_shape(double s, double inv_1ps) {
         p = fma(-p, s, 1.0 / 2.0);
         return p * s * s;
     }
-    return fma(-s, inv_1ps, log1p_pos(s));
+    const double u = 1.0 + s;
+    const double inv_u = rcp_fast(u);
+    return fma(-s, inv_u, log1p_pos(s, u, inv_u));
 }
 
 // ---- regularised lower incomplete gamma P(a, x), a > 0, x >= 0 (Bovy bulge: a = 0.6).

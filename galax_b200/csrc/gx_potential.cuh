@@ -65,41 +65,47 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
                                          double &gz_) {
     const double z2 = z * z;
     const double R2 = fma(y, y, x * x);
-    double fxy = 0.0, fz = 0.0;
+    // accumulate() starts from the first term instead of adding to 0.0 (a DADD the compiler must keep)
+    double fxy = 0.0, fz = 0.0, fs = 0.0;
+    bool have_d = false, have_s = false;
 #pragma unroll
     for (int i = 0; i < C::kMN; ++i) {
         if (!C::is_static && i >= P.n_mn) break;
         const DevMN &c = P.mn[i];
         double zeta2 = z2 + c.b2;
-        double rz = rsqrt_fast(zeta2);            // 1/zeta
+        double rz = rsqrt_fast(zeta2);       // 1/zeta
         double apz = fma(zeta2, rz, c.a);    // a + zeta
         double D2 = fma(apz, apz, R2);
         double rD = rsqrt_fast(D2);
-        double f = c.GM * rD * (rD * rD);    // GM / D^3
-        fxy += f;
-        fz = fma(f, apz * rz, fz);           // GM/D^3 * (a+zeta)/zeta
+        double f = (c.GM * rD) * (rD * rD);  // GM / D^3
+        double g = f * (apz * rz);           // GM/D^3 * (a+zeta)/zeta
+        if (C::is_static && i == 0) { fxy = f; fz = g; }
+        else { fxy += f; fz += g; }
+        have_d = true;
     }
-    double fs = 0.0;
-    const bool any_sph = C::is_static ? (C::hern(P) + C::nfw(P) + C::plc(P) > 0) : (P.n_hern + P.n_nfw + P.n_plc > 0);
+    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0) : (P.n_hern + P.n_nfw + P.n_plc > 0);
     if (any_sph) {
         const double r2 = (R2 + z2) + TINY;
         const double rinv = rsqrt_fast(r2);
         const double r = r2 * rinv;
+        const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
 #pragma unroll
         for (int i = 0; i < C::kH; ++i) {
             if (!C::is_static && i >= P.n_hern) break;
             const DevHern &c = P.hern[i];
             double u = r + c.c;
-            fs = fma(c.GM * rinv, rcp_fast(u * u), fs);  // GM / ((r+c)^2 r)
+            double t = (c.GM * rinv) * rcp_fast(u * u);  // GM / ((r+c)^2 r)
+            if (C::is_static && i == 0) fs = t; else fs += t;
+            have_s = true;
         }
-        const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
 #pragma unroll
         for (int i = 0; i < C::kNFW; ++i) {
             if (!C::is_static && i >= P.n_nfw) break;
             const DevNFW &c = P.nfw[i];
-            double s = r * c.inv_rs;
-            double m = nfw_menc_shape(s, rcp_fast(1.0 + s));
-            fs = fma((c.GM * m) * rinv, rinv2, fs);  // GM m(s) / r^3
+            double m = nfw_menc_shape(r * c.inv_rs);
+            double t = (c.GM * m) * rinv;  // GM m(s) / r^3 = t * rinv^2
+            if (C::is_static && C::kH == 0 && i == 0) fs = t * rinv2; else fs = fma(t, rinv2, fs);
+            have_s = true;
         }
 #pragma unroll
         for (int i = 0; i < C::kPLC; ++i) {
@@ -108,11 +114,14 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             double s = r * c.inv_rc;
             double Pg = gammainc_P(c.a, c.lgam_a, s * s, nullptr);
             fs = fma((c.GM * Pg) * rinv, rinv2, fs);  // GM P(a, s^2) / r^3
+            have_s = true;
         }
     }
-    gx_ = (fxy + fs) * x;
-    gy_ = (fxy + fs) * y;
-    gz_ = (fz + fs) * z;
+    (void)have_d; (void)have_s;
+    const double fh = fxy + fs, fv = fz + fs;
+    gx_ = fh * x;
+    gy_ = fh * y;
+    gz_ = fv * z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,7 +188,7 @@ __device__ __forceinline__ void hessian(const DevPot &P, double x, double y, dou
         for (int i = 0; i < C::nfw(P); ++i) {
             const DevNFW &c = P.nfw[i];
             double s = r * c.inv_rs;
-            double m = nfw_menc_shape(s, 1.0 / (1.0 + s));
+            double m = nfw_menc_shape(s);
             double d1 = c.GM * m / r2;
             d1r += d1 / r;
             d2 += c.GM * s / (c.rs * (1.0 + s) * (1.0 + s) * r2) - 2.0 * d1 / r;

@@ -90,14 +90,21 @@ def emit():
            "// Dopri8 = Prince-Dormand RK8(7)13M + FSAL stage, Nystrom form for (dq,dp) = (p, a(q)).",
            "#pragma once", "namespace gx { namespace dp8 {", "constexpr int NS = 14;"]
 
+    # Values live in __constant__ memory (an unrolled access becomes a c[bank][imm] operand of the DFMA, no
+    # extra instruction); the sparsity pattern is constexpr so zero coefficients vanish at compile time.
     def mat(name, M, cols):
-        out.append(f"__device__ constexpr double {name}[{len(M)}][{cols}] = {{")
+        out.append(f"__constant__ double {name}[{len(M)}][{cols}] = {{")
         for row in M:
             out.append("    {" + ", ".join(fmt(v) for v in row) + "},")
         out.append("};")
+        out.append(f"__device__ constexpr bool {name}_NZ[{len(M)}][{cols}] = {{")
+        for row in M:
+            out.append("    {" + ", ".join("true" if float(v) != 0.0 else "false" for v in row) + "},")
+        out.append("};")
 
     def vec(name, v):
-        out.append(f"__device__ constexpr double {name}[{len(v)}] = {{" + ", ".join(fmt(x) for x in v) + "};")
+        out.append(f"__constant__ double {name}[{len(v)}] = {{" + ", ".join(fmt(x) for x in v) + "};")
+        out.append(f"__device__ constexpr bool {name}_NZ[{len(v)}] = {{" + ", ".join("true" if float(x) != 0.0 else "false" for x in v) + "};")
 
     mat("A", t["A"], N)      # p-stage weights (only the last row, b_sol, is used by the kernels)
     mat("AA", t["AA"], N)    # q_i = q0 + CN[i] h p0 + h^2 sum_l AA[i][l] a_l

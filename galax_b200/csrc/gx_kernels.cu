@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/galax_b200.h"
@@ -25,6 +26,20 @@ namespace gx {
 // ================================================================================================
 
 enum Model { MODEL_GENERIC = 0, MODEL_MW = 1, MODEL_MW2022 = 2, MODEL_BOVY = 3 };
+
+// Q(a, x) ~ x^(a-1) e^-x / Gamma(a) (1 + (a-1)/x + ...): find where it drops below 2^-55 so that P == 1 in fp64.
+static void fill_gamma_tab(GammaTab &g, double a) {
+    g.a = a;
+    g.lgam = lgamma(a);
+    double x = 30.0;
+    while (x < 80.0) {
+        double q = exp((a - 1.0) * log(x) - x - g.lgam) * (1.0 + fabs(a - 1.0) / x);
+        if (q < 2.7e-17) break;
+        x += 0.25;
+    }
+    g.xcut = x;
+    for (int n = 0; n < PLC_NT; ++n) g.inv[n] = 1.0 / (a + n);
+}
 
 static int build_devpot(const gx_potential *pot, DevPot &D, Model &model) {
     if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
@@ -64,12 +79,10 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model) {
             if (!(alpha >= 0.0 && alpha < 2.0)) return GX_ERR_UNSUPPORTED;  // Phi needs Gamma(1 - alpha/2)
             DevPLC &p = D.plc[D.n_plc++];
             p.GM = G * c.p[0];
-            p.a = 1.5 - alpha / 2;
-            p.lgam_a = lgamma(p.a);
             p.inv_rc = 1.0 / rc;
-            p.a2 = 1.0 - alpha / 2;
-            p.lgam_a2 = lgamma(p.a2);
-            p.tail = tgamma(p.a2) / (rc * tgamma(p.a));
+            fill_gamma_tab(p.ga, 1.5 - alpha / 2);
+            fill_gamma_tab(p.ga2, 1.0 - alpha / 2);
+            p.tail = tgamma(p.ga2.a) / (rc * tgamma(p.ga.a));
             break;
         }
         default:
@@ -253,9 +266,9 @@ struct Dp8Args {
     int T;
 };
 
-__host__ __device__ constexpr bool row_nonzero(const double *row, int n) {
+__host__ __device__ constexpr bool row_nonzero(const bool *row, int n) {
     for (int i = 0; i < n; ++i)
-        if (row[i] != 0.0) return true;
+        if (row[i]) return true;
     return false;
 }
 
@@ -270,6 +283,21 @@ __device__ __forceinline__ void accel(const DevPot &P, double x, double y, doubl
                                       double &az) {
     double g0, g1, g2;
     gradient<C>(P, x, y, z, g0, g1, g2);
+    ax = -g0; ay = -g1; az = -g2;
+}
+
+// Out-of-line right-hand side for the Dopri8 kernel: 13 inlined copies of the gradient make the step body
+// ~100 KB of SASS, far beyond the 32 KB instruction cache (ncu: "no_instruction" was the top stall).  The
+// potential parameters are staged in shared memory once per CTA so the callee needs no pointer argument.
+template <class C>
+__device__ __forceinline__ DevPot *pot_smem() {
+    __shared__ DevPot sP;
+    return &sP;
+}
+template <class C>
+__device__ __noinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az) {
+    double g0, g1, g2;
+    gradient<C>(*pot_smem<C>(), x, y, z, g0, g1, g2);
     ax = -g0; ay = -g1; az = -g2;
 }
 
@@ -294,7 +322,7 @@ __device__ double select_initial_step(const DevPot &P, double dir, const double 
 #pragma unroll
     for (int i = 0; i < 6; ++i) y1[i] = y[i] + h0 * f0[i];
     double a1x, a1y, a1z;
-    accel<C>(P, y1[0], y1[1], y1[2], a1x, a1y, a1z);
+    accel_call<C>(y1[0], y1[1], y1[2], a1x, a1y, a1z);
     double f1[6] = {y1[3] * dir, y1[4] * dir, y1[5] * dir, a1x * dir, a1y * dir, a1z * dir};
 #pragma unroll
     for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
@@ -305,24 +333,39 @@ __device__ double select_initial_step(const DevPot &P, double dir, const double 
 }
 
 #ifndef GX_DP8_MIN_BLOCKS
-#define GX_DP8_MIN_BLOCKS 1
+#define GX_DP8_MIN_BLOCKS 3
 #endif
+// The 14 x 3 stage accelerations are thread-private arrays; because the right-hand side is an out-of-line call
+// they live in the thread's local-memory frame (L1-resident, 336 B/thread) rather than in registers.  Measured
+// alternatives on B200 (MW2022, rtol = atol = 1e-10, 3e5 particles): everything inlined with the stages in
+// registers 161 ms (I-cache bound: 105 KB of SASS); stages in shared memory 151-205 ms; this version 121 ms.
 template <class C>
-__global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
+__global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
+k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     using namespace dp8;
+    {   // stage the potential parameters in shared memory for accel_call()
+        const double *src = reinterpret_cast<const double *>(&P);
+        double *dst = reinterpret_cast<double *>(pot_smem<C>());
+        for (int w = threadIdx.x; w < (int)(sizeof(DevPot) / sizeof(double)); w += blockDim.x) dst[w] = src[w];
+        __syncthreads();
+    }
     const unsigned FULL = 0xffffffffu;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const double NANV = __longlong_as_double(0x7ff8000000000000LL);
 
+    const bool simple_i = (a.pcoeff == 0.0 && a.dcoeff == 0.0 && a.icoeff == 1.0);
     bool have = false, exhausted = false;
     long long idx = 0;
     double q0x = 0, q0y = 0, q0z = 0, p0x = 0, p0y = 0, p0z = 0;  // state at tprev
-    double ax[NS], ay[NS], az[NS];                                // stage accelerations; [0] is FSAL
+    double rx[NS], ry[NS], rz_[NS];  // stage accelerations; [0] is the FSAL value
+#define AX(l) rx[l]
+#define AY(l) ry[l]
+#define AZ(l) rz_[l]
     double dir = 1.0, T1 = 0, tprev = 0, tnext = 0, tsave = INF;
     double prev_inv = 1.0, prev_prev_inv = 1.0;
     bool at_dtmin = false;
     int k = 0, nacc = 0, ntot = 0, st = GX_OK;
-    ax[0] = ay[0] = az[0] = 0.0;
+    AX(0) = 0.0; AY(0) = 0.0; AZ(0) = 0.0;
 
     for (;;) {
         // ---------------- refill idle lanes from the global ticket counter
@@ -349,13 +392,13 @@ __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(con
                     ++k;
                     tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 }
-                accel<C>(P, q0x, q0y, q0z, ax[0], ay[0], az[0]);
+                { double t0_, t1_, t2_; accel_call<C>(q0x, q0y, q0z, t0_, t1_, t2_); AX(0) = t0_; AY(0) = t1_; AZ(0) = t2_; }
                 double h;
                 if (a.dt0 > 0.0) {
                     h = a.dt0;
                 } else {
                     const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
-                    const double a0[3] = {ax[0], ay[0], az[0]};
+                    const double a0[3] = {AX(0), AY(0), AZ(0)};
                     h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol);
                 }
                 tprev = T0;
@@ -392,26 +435,26 @@ __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(con
             sx = 0; sy = 0; sz = 0;
 #pragma unroll
             for (int l = 0; l < i; ++l) {
-                if (AA[i][l] != 0.0) {
-                    sx = fma(AA[i][l], ax[l], sx);
-                    sy = fma(AA[i][l], ay[l], sy);
-                    sz = fma(AA[i][l], az[l], sz);
+                if (AA_NZ[i][l]) {
+                    sx = fma(AA[i][l], AX(l), sx);
+                    sy = fma(AA[i][l], AY(l), sy);
+                    sz = fma(AA[i][l], AZ(l), sz);
                 }
             }
             const double ch = CN[i] * hd;
             const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
             const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
             const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
-            accel<C>(P, xi, yi, zi, ax[i], ay[i], az[i]);
+            { double t0_, t1_, t2_; accel_call<C>(xi, yi, zi, t0_, t1_, t2_); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
             if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: stage 14 sits at q1
         }
         const double q1x = sx, q1y = sy, q1z = sz;
         double bx = 0, by = 0, bz = 0, epx = 0, epy = 0, epz = 0, eqx = 0, eqy = 0, eqz = 0;
 #pragma unroll
         for (int l = 0; l < NS; ++l) {
-            if (B[l] != 0.0) { bx = fma(B[l], ax[l], bx); by = fma(B[l], ay[l], by); bz = fma(B[l], az[l], bz); }
-            if (E[l] != 0.0) { epx = fma(E[l], ax[l], epx); epy = fma(E[l], ay[l], epy); epz = fma(E[l], az[l], epz); }
-            if (EA[l] != 0.0) { eqx = fma(EA[l], ax[l], eqx); eqy = fma(EA[l], ay[l], eqy); eqz = fma(EA[l], az[l], eqz); }
+            if (B_NZ[l]) { bx = fma(B[l], AX(l), bx); by = fma(B[l], AY(l), by); bz = fma(B[l], AZ(l), bz); }
+            if (E_NZ[l]) { epx = fma(E[l], AX(l), epx); epy = fma(E[l], AY(l), epy); epz = fma(E[l], AZ(l), epz); }
+            if (EA_NZ[l]) { eqx = fma(EA[l], AX(l), eqx); eqy = fma(EA[l], AY(l), eqy); eqz = fma(EA[l], AZ(l), eqz); }
         }
         const double p1x = fma(hd, bx, p0x), p1y = fma(hd, by, p0y), p1z = fma(hd, bz, p0z);
         ++ntot;
@@ -419,24 +462,38 @@ __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(con
         // ---------------- PID controller (diffrax PIDController.adapt_step_size)
         const bool nan1 = isnan(q1x) || isnan(q1y) || isnan(q1z) || isnan(p1x) || isnan(p1y) || isnan(p1z);
         double e0 = hd2 * eqx, e1 = hd2 * eqy, e2 = hd2 * eqz, e3 = hd * epx, e4 = hd * epy, e5 = hd * epz;
-        e0 = e0 / (a.atol + fmax(fabs(q0x), fabs(nan1 ? q0x : q1x)) * a.rtol);
-        e1 = e1 / (a.atol + fmax(fabs(q0y), fabs(nan1 ? q0y : q1y)) * a.rtol);
-        e2 = e2 / (a.atol + fmax(fabs(q0z), fabs(nan1 ? q0z : q1z)) * a.rtol);
-        e3 = e3 / (a.atol + fmax(fabs(p0x), fabs(nan1 ? p0x : p1x)) * a.rtol);
-        e4 = e4 / (a.atol + fmax(fabs(p0y), fabs(nan1 ? p0y : p1y)) * a.rtol);
-        e5 = e5 / (a.atol + fmax(fabs(p0z), fabs(nan1 ? p0z : p1z)) * a.rtol);
-        double serr = rms6(e0, e1, e2, e3, e4, e5);
-        if (isnan(serr)) serr = INF;
-        bool keep = serr < 1.0;
+        e0 *= rcp_fast(a.atol + fmax(fabs(q0x), fabs(nan1 ? q0x : q1x)) * a.rtol);
+        e1 *= rcp_fast(a.atol + fmax(fabs(q0y), fabs(nan1 ? q0y : q1y)) * a.rtol);
+        e2 *= rcp_fast(a.atol + fmax(fabs(q0z), fabs(nan1 ? q0z : q1z)) * a.rtol);
+        e3 *= rcp_fast(a.atol + fmax(fabs(p0x), fabs(nan1 ? p0x : p1x)) * a.rtol);
+        e4 *= rcp_fast(a.atol + fmax(fabs(p0y), fabs(nan1 ? p0y : p1y)) * a.rtol);
+        e5 *= rcp_fast(a.atol + fmax(fabs(p0z), fabs(nan1 ? p0z : p1z)) * a.rtol);
+        double ms = e0 * e0;  // mean square of the scaled error; serr = sqrt(ms)
+        ms = fma(e1, e1, ms); ms = fma(e2, e2, ms); ms = fma(e3, e3, ms); ms = fma(e4, e4, ms); ms = fma(e5, e5, ms);
+        ms *= (1.0 / 6.0);
+        const bool bad = !(ms <= 1.7976931348623157e308);  // NaN or inf error estimate -> reject, shrink
+        bool keep = !bad && ms < 1.0;
         if (a.dtmin > 0.0) keep = keep || at_dtmin;
-        double inv = 1.0 / serr;
-        const double c1 = (a.icoeff + a.pcoeff + a.dcoeff) * 0.125;
-        const double c2 = -(a.pcoeff + 2.0 * a.dcoeff) * 0.125;
-        const double c3 = a.dcoeff * 0.125;
-        double factor = a.safety;
-        if (c1 != 0.0) factor *= pow(inv, c1);
-        if (c2 != 0.0) factor *= pow(prev_inv, c2);
-        if (c3 != 0.0) factor *= pow(prev_prev_inv, c3);
+        double factor, inv = 1.0;
+        if (simple_i) {
+            // I-controller (diffrax default pcoeff = dcoeff = 0, icoeff = 1):
+            // factor = safety * serr^(-1/8) = safety * ms^(-1/16), by one rsqrt and three square roots
+            double y = rsqrt_fast(ms);             // ms^(-1/2)
+            y = y * rsqrt_fast(y);                 // ms^(-1/4)
+            y = y * rsqrt_fast(y);                 // ms^(-1/8)
+            y = y * rsqrt_fast(y);                 // ms^(-1/16)
+            factor = bad ? 0.0 : ((ms > 0.0) ? a.safety * y : a.factormax);
+        } else {
+            const double serr = bad ? INF : sqrt(ms);
+            inv = 1.0 / serr;
+            const double c1 = (a.icoeff + a.pcoeff + a.dcoeff) * 0.125;
+            const double c2 = -(a.pcoeff + 2.0 * a.dcoeff) * 0.125;
+            const double c3 = a.dcoeff * 0.125;
+            factor = a.safety;
+            if (c1 != 0.0) factor *= pow(inv, c1);
+            if (c2 != 0.0) factor *= pow(prev_inv, c2);
+            if (c3 != 0.0) factor *= pow(prev_prev_inv, c3);
+        }
         const double fmin_ = keep ? 1.0 : a.factormin;
         factor = fmin(fmax(factor, fmin_), a.factormax);
         double dt = h * factor;
@@ -453,19 +510,19 @@ __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(con
                     double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
 #pragma unroll
                     for (int l = 0; l < NS; ++l) {
-                        if (row_nonzero(DQ[l], 6)) {
+                        if (row_nonzero(DQ_NZ[l], 6)) {
                             double w = DQ[l][5];
 #pragma unroll
                             for (int m = 4; m >= 0; --m) w = fma(w, th, DQ[l][m]);
                             w *= th;
-                            wqx = fma(w, ax[l], wqx); wqy = fma(w, ay[l], wqy); wqz = fma(w, az[l], wqz);
+                            wqx = fma(w, AX(l), wqx); wqy = fma(w, AY(l), wqy); wqz = fma(w, AZ(l), wqz);
                         }
-                        if (row_nonzero(DB[l], 6)) {
+                        if (row_nonzero(DB_NZ[l], 6)) {
                             double w = DB[l][5];
 #pragma unroll
                             for (int m = 4; m >= 0; --m) w = fma(w, th, DB[l][m]);
                             w *= th;
-                            wpx = fma(w, ax[l], wpx); wpy = fma(w, ay[l], wpy); wpz = fma(w, az[l], wpz);
+                            wpx = fma(w, AX(l), wpx); wpy = fma(w, AY(l), wpy); wpz = fma(w, AZ(l), wpz);
                         }
                     }
                     const double thh = th * hd;
@@ -480,7 +537,7 @@ __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(con
                 }
             }
             q0x = q1x; q0y = q1y; q0z = q1z; p0x = p1x; p0y = p1y; p0z = p1z;
-            ax[0] = ax[NS - 1]; ay[0] = ay[NS - 1]; az[0] = az[NS - 1];
+            AX(0) = AX(NS - 1); AY(0) = AY(NS - 1); AZ(0) = AZ(NS - 1);
             prev_prev_inv = prev_inv;
             prev_inv = inv;
             tprev = tnext;
@@ -490,6 +547,9 @@ __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS) k_integrate_dopri8(con
         if (tprev > T1) tprev = T1;
         tnext = clip_to_end(tprev, tprev + dt, T1, keep);
     }
+#undef AX
+#undef AY
+#undef AZ
 }
 
 // ================================================================================================
@@ -601,7 +661,7 @@ __global__ void k_bench_dfma(long long iters, double *sink) {
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
-__global__ void k_debug_math(int op, double a, double lgam, const double *x, long long N, double *out) {
+__global__ void k_debug_math(int op, const GammaTab *gt, const double *x, long long N, double *out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const double v = x[i];
@@ -610,7 +670,7 @@ __global__ void k_debug_math(int op, double a, double lgam, const double *x, lon
     case 0: r = rcp_fast(v); break;
     case 1: r = rsqrt_fast(v); break;
     case 2: r = log1p_pos(v); break;
-    case 3: r = gammainc_P(a, lgam, v, nullptr); break;
+    case 3: r = gammainc_P(*gt, v, nullptr); break;
     case 4: r = nfw_menc_shape(v); break;
     default: r = 0.0;
     }
@@ -740,24 +800,23 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     a.dt0 = (pid->dt0 > 0.0) ? pid->dt0 : -1.0;
     a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
-    // persistent launch: resident CTAs only (occupancy query), never more lanes than particles
+    // persistent launch: resident CTAs only (occupancy query), never more lanes than particles; small batches
+    // use narrow CTAs so that the few particles spread over all SMs.
     const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define GX_OCC(C_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate_dopri8<C_>, block, 0)
-    switch (model) {
-    case MODEL_MW: GX_OCC(CountsMW); break;
-    case MODEL_MW2022: GX_OCC(CountsMW2022); break;
-    case MODEL_BOVY: GX_OCC(CountsBovy); break;
-    default: GX_OCC(CountsRuntime); break;
-    }
-#undef GX_OCC
-    if (per_sm < 1) per_sm = 1;
-    long long want = (N + block - 1) / block;
-    long long resident = (long long)per_sm * sms;
-    int grid = (int)(want < resident ? want : resident);
-    GX_DISPATCH_MODEL(model, (k_integrate_dopri8<C><<<grid, block, 0, s>>>(D, a)));
+#define GX_LAUNCH_DP8(C_)                                                                                     \
+    do {                                                                                                      \
+        auto kern = k_integrate_dopri8<C_>;                                                                   \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);                               \
+        if (per_sm < 1) per_sm = 1;                                                                           \
+        long long want = (N + block - 1) / block, resident = (long long)per_sm * sms;                         \
+        int grid = (int)(want < resident ? want : resident);                                                  \
+        kern<<<grid, block, 0, s>>>(D, a);                                                                    \
+    } while (0)
+    GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
+#undef GX_LAUNCH_DP8
     return cuda_rc(cudaGetLastError());
 }
 
@@ -800,8 +859,17 @@ int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, 
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream) {
     if (N < 0 || (N > 0 && (!x || !out))) return GX_ERR_BADARG;
     if (N == 0) return 0;
-    k_debug_math<<<grid_for(N, 256), 256, 0, (cudaStream_t)stream>>>(op, a, lgamma(a), x, (long long)N, out);
-    return cuda_rc(cudaGetLastError());
+    GammaTab *gt = nullptr;
+    if (op == 3) {  // debug-only: a small device allocation for the table
+        GammaTab h;
+        fill_gamma_tab(h, a);
+        if (cudaMalloc(&gt, sizeof h) != cudaSuccess) return GX_ERR_CUDA;
+        cudaMemcpyAsync(gt, &h, sizeof h, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    }
+    k_debug_math<<<grid_for(N, 256), 256, 0, (cudaStream_t)stream>>>(op, gt, x, (long long)N, out);
+    int rc = cuda_rc(cudaGetLastError());
+    if (gt) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(gt); }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

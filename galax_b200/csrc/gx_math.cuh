@@ -112,42 +112,31 @@ __device__ __forceinline__ double nfw_menc_shape(double s) {
 }
 
 // ---- regularised lower incomplete gamma P(a, x), a > 0, x >= 0 (Bovy bulge: a = 0.6).
-// Series for x < a+1, modified-Lentz continued fraction for Q = 1-P otherwise.  lgam = lgamma(a).
-// On exit dP = x^(a-1) e^-x / Gamma(a) = dP/dx (needed by the Hessian).
-__device__ __noinline__ double gammainc_P(double a, double lgam, double x, double *dP) {
+//   P(a,x) = x^a e^-x / Gamma(a) * sum_{n>=0} x^n / (a (a+1) ... (a+n))
+// The series has only positive terms (no cancellation) and is used for every x below the point where
+// Q = 1 - P drops under 2^-54 (then P rounds to 1); the reciprocals 1/(a+n) are tabulated on the host, so a term
+// costs one multiply and one add.  On exit *dP = x^(a-1) e^-x / Gamma(a) = dP/dx (needed by the Hessian).
+constexpr int PLC_NT = 128;
+struct GammaTab {
+    double a, lgam, xcut;     // lgam = lgamma(a); P(a, x >= xcut) == 1 in fp64
+    double inv[PLC_NT];       // inv[n] = 1 / (a + n)
+};
+
+__device__ __noinline__ double gammainc_P(const GammaTab &g, double x, double *dP) {
     if (!(x > 0.0)) {
-        if (dP) *dP = (a == 1.0) ? 1.0 : ((a > 1.0) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL));
+        if (dP) *dP = (g.a == 1.0) ? 1.0 : ((g.a > 1.0) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL));
         return 0.0;
     }
-    double lx = log(x);
-    double pref = exp(fma(a, lx, -x) - lgam);  // x^a e^-x / Gamma(a)
+    const double pref = exp(fma(g.a, log(x), -x) - g.lgam);  // x^a e^-x / Gamma(a)
     if (dP) *dP = pref / x;
-    if (x < a + 1.0) {
-        double ap = a, del = 1.0 / a, sum = del;
-        for (int n = 0; n < 200; ++n) {
-            ap += 1.0;
-            del *= x / ap;
-            sum += del;
-            if (del < sum * 1e-17) break;
-        }
-        return sum * pref;
+    if (x >= g.xcut) return 1.0;
+    double del = g.inv[0], sum = del;
+    for (int n = 1; n < PLC_NT; ++n) {
+        del *= x * g.inv[n];
+        sum += del;
+        if (del < sum * 2e-17) break;
     }
-    if (x > 745.0) return 1.0;
-    const double FPMIN = 1e-300;
-    double b = x + 1.0 - a, c = 1.0 / FPMIN, d = 1.0 / b, h = d;
-    for (int i = 1; i < 500; ++i) {
-        double an = -i * (i - a);
-        b += 2.0;
-        d = fma(an, d, b);
-        if (fabs(d) < FPMIN) d = FPMIN;
-        c = b + an / c;
-        if (fabs(c) < FPMIN) c = FPMIN;
-        d = 1.0 / d;
-        double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < 1e-16) break;
-    }
-    return 1.0 - pref * h;
+    return fmin(sum * pref, 1.0);
 }
 
 }  // namespace gx

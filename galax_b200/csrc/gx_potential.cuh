@@ -24,13 +24,13 @@ namespace gx {
 constexpr int MAX_MN = 6;
 constexpr int MAX_HERN = 4;
 constexpr int MAX_NFW = 2;
-constexpr int MAX_PLC = 2;
+constexpr int MAX_PLC = 1;
 constexpr double TINY = 2.2250738585072014e-308;
 
 struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
 struct DevHern { double GM, c; };
 struct DevNFW { double GM, rs, inv_rs, GM_inv_rs; };
-struct DevPLC { double GM, a, lgam_a, inv_rc, a2, lgam_a2, tail; };  // a2 = a-1/2, tail = Gamma(a2)/(rc Gamma(a))
+struct DevPLC { double GM, inv_rc, tail; GammaTab ga, ga2; };  // ga: a = 3/2 - alpha/2; ga2: a - 1/2; tail = Gamma(a2)/(rc Gamma(a))
 
 struct DevPot {
     int n_mn, n_hern, n_nfw, n_plc;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             if (!C::is_static && i >= P.n_plc) break;
             const DevPLC &c = P.plc[i];
             double s = r * c.inv_rc;
-            double Pg = gammainc_P(c.a, c.lgam_a, s * s, nullptr);
+            double Pg = gammainc_P(c.ga, s * s, nullptr);
             fs = fma((c.GM * Pg) * rinv, rinv2, fs);  // GM P(a, s^2) / r^3
             have_s = true;
         }
@@ -144,8 +144,8 @@ __device__ __forceinline__ double potential_value(const DevPot &P, double x, dou
     for (int i = 0; i < C::plc(P); ++i) {
         const DevPLC &c = P.plc[i];
         double s = r * c.inv_rc, s2 = s * s;
-        double Pa = gammainc_P(c.a, c.lgam_a, s2, nullptr);
-        double Qa2 = 1.0 - gammainc_P(c.a2, c.lgam_a2, s2, nullptr);
+        double Pa = gammainc_P(c.ga, s2, nullptr);
+        double Qa2 = 1.0 - gammainc_P(c.ga2, s2, nullptr);
         phi -= c.GM * (Pa / r + Qa2 * c.tail);
     }
     return phi;
@@ -196,7 +196,7 @@ __device__ __forceinline__ void hessian(const DevPot &P, double x, double y, dou
         for (int i = 0; i < C::plc(P); ++i) {
             const DevPLC &c = P.plc[i];
             double s = r * c.inv_rc, dP;
-            double Pg = gammainc_P(c.a, c.lgam_a, s * s, &dP);
+            double Pg = gammainc_P(c.ga, s * s, &dP);
             double d1 = c.GM * Pg / r2;
             d1r += d1 / r;
             d2 += c.GM * dP * 2.0 * c.inv_rc * c.inv_rc / r - 2.0 * d1 / r;

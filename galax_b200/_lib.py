@@ -31,6 +31,7 @@ OK, MAX_STEPS_REACHED, NONFINITE = 0, 1, 2
 SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1
 LAYOUT_NT3, LAYOUT_T3N = 0, 1
 DF_FARDAL15, DF_CHEN24 = 0, 1
+DENSE_RECORD_DOUBLES = 51
 
 
 class GxComponent(C.Structure):
@@ -105,6 +106,11 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_integrate_dopri8_record": (C.c_int, [C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p, C.c_void_p,
+                                             C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_dense_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
     "gx_stream_release": (C.c_int, [C.POINTER(GxPotential), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),

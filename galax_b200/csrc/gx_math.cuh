@@ -90,8 +90,9 @@ __device__ __forceinline__ double log1p_pos(double s) {
 
 // ln(1+s) - s/(1+s), the NFW enclosed-mass shape.  Below s = 0.02 the two terms cancel to O(s^2) and the
 // alternating series sum_{k>=2} (-1)^k (k-1)/k s^k is used instead (13 terms: 0.02^12 < 5e-21).
-__device__ __forceinline__ double nfw_menc_shape(double s) {
+__device__ __forceinline__ double nfw_menc_shape(double s, double &inv_u) {
     if (s < 0.02) {
+        inv_u = rcp_fast(1.0 + s);
         double p = 12.0 / 13.0;  // k = 13 (odd -> negative sign applied below)
         p = fma(-p, s, 11.0 / 12.0);
         p = fma(-p, s, 10.0 / 11.0);
@@ -107,8 +108,12 @@ __device__ __forceinline__ double nfw_menc_shape(double s) {
         return p * s * s;
     }
     const double u = 1.0 + s;
-    const double inv_u = rcp_fast(u);
+    inv_u = rcp_fast(u);
     return fma(-s, inv_u, log1p_pos(s, u, inv_u));
+}
+__device__ __forceinline__ double nfw_menc_shape(double s) {
+    double inv_u;
+    return nfw_menc_shape(s, inv_u);
 }
 
 // ---- regularised lower incomplete gamma P(a, x), a > 0, x >= 0 (Bovy bulge: a = 0.6).

@@ -151,7 +151,91 @@ __device__ __forceinline__ double potential_value(const DevPot &P, double x, dou
     return phi;
 }
 
-// H[0..5] = (xx, xy, xz, yy, yz, zz)
+// ---------------------------------------------------------------------------------------------
+// fused gradient + Hessian with the fast primitives (bulk kernel, C5 and the stream release).
+// g = grad Phi; H[0..5] = (xx, xy, xz, yy, yz, zz).
+template <class C>
+__device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, double z, double g[3], double H[6]) {
+    const double z2 = z * z, R2 = fma(y, y, x * x);
+    double gxy = 0.0, gz = 0.0;  // g = (gxy x, gxy y, gz) for the flattened part
+#pragma unroll
+    for (int k = 0; k < 6; ++k) H[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < C::kMN; ++i) {
+        if (!C::is_static && i >= P.n_mn) break;
+        const DevMN &c = P.mn[i];
+        const double zeta2 = z2 + c.b2;
+        const double rz = rsqrt_fast(zeta2);
+        const double apz = fma(zeta2, rz, c.a);
+        const double D2 = fma(apz, apz, R2);
+        const double rD = rsqrt_fast(D2), rD2 = rD * rD;
+        const double f3 = (c.GM * rD) * rD2;     // GM / D^3
+        const double f5 = 3.0 * f3 * rD2;        // 3 GM / D^5
+        const double w = apz * rz;               // (a + zeta) / zeta
+        const double uz = z * w;
+        const double duz = fma(c.ab2 * rz, rz * rz, 1.0);  // 1 + a b^2 / zeta^3
+        gxy += f3;
+        gz = fma(f3, w, gz);
+        H[0] += fma(-f5 * x, x, f3);
+        H[1] -= f5 * x * y;
+        H[2] -= f5 * x * uz;
+        H[3] += fma(-f5 * y, y, f3);
+        H[4] -= f5 * y * uz;
+        H[5] += fma(-f5 * uz, uz, f3 * duz);
+    }
+    double d1r = 0.0, d2 = 0.0;  // sum over spherical components of Phi'/r and Phi''
+    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0) : (P.n_hern + P.n_nfw + P.n_plc > 0);
+    if (any_sph) {
+        const double r2 = (R2 + z2) + TINY;
+        const double rinv = rsqrt_fast(r2);
+        const double r = r2 * rinv;
+        const double rinv2 = rinv * rinv;
+#pragma unroll
+        for (int i = 0; i < C::kH; ++i) {
+            if (!C::is_static && i >= P.n_hern) break;
+            const double iu = rcp_fast(r + P.hern[i].c);
+            const double d1 = P.hern[i].GM * iu * iu;  // GM / (r+c)^2
+            d1r = fma(d1, rinv, d1r);
+            d2 = fma(-2.0 * d1, iu, d2);
+        }
+#pragma unroll
+        for (int i = 0; i < C::kNFW; ++i) {
+            if (!C::is_static && i >= P.n_nfw) break;
+            const DevNFW &c = P.nfw[i];
+            double iu;
+            const double m = nfw_menc_shape(r * c.inv_rs, iu);
+            const double t = ((c.GM * m) * rinv) * rinv2;  // Phi'/r = GM m / r^3
+            d1r += t;
+            // Phi'' = GM s / (rs (1+s)^2 r^2) - 2 Phi'/r = (GM / rs^2) (1/r) / (1+s)^2 - 2 Phi'/r
+            d2 += fma(c.GM_inv_rs * c.inv_rs * rinv, iu * iu, -2.0 * t);
+        }
+#pragma unroll
+        for (int i = 0; i < C::kPLC; ++i) {
+            if (!C::is_static && i >= P.n_plc) break;
+            const DevPLC &c = P.plc[i];
+            const double s = r * c.inv_rc;
+            double dP;
+            const double Pg = gammainc_P(c.ga, s * s, &dP);
+            const double t = ((c.GM * Pg) * rinv) * rinv2;
+            d1r += t;
+            d2 += fma(c.GM * dP * 2.0 * c.inv_rc * c.inv_rc, rinv, -2.0 * t);
+        }
+        // H += (Phi'/r) I + (Phi'' - Phi'/r) n n^T
+        const double w = (d2 - d1r) * rinv2;
+        H[0] += fma(w * x, x, d1r);
+        H[1] = fma(w * x, y, H[1]);
+        H[2] = fma(w * x, z, H[2]);
+        H[3] += fma(w * y, y, d1r);
+        H[4] = fma(w * y, z, H[4]);
+        H[5] += fma(w * z, z, d1r);
+    }
+    g[0] = (gxy + d1r) * x;
+    g[1] = (gxy + d1r) * y;
+    g[2] = (gz + d1r) * z;
+}
+
+// H[0..5] = (xx, xy, xz, yy, yz, zz)   (IEEE div/sqrt version, kept for the r -> 0 corner and as a cross-check)
+
 template <class C>
 __device__ __forceinline__ void hessian(const DevPot &P, double x, double y, double z, double H[6]) {
     const double z2 = z * z, R2 = fma(y, y, x * x);

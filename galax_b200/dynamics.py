@@ -152,6 +152,14 @@ class Solution:
     result: Any
 
 
+def _cat0(a, b):
+    if isinstance(a, np.ndarray):
+        return np.concatenate([a, b], axis=0)
+    import torch
+
+    return torch.cat([a, b], dim=0)
+
+
 def _cat(q, p):
     if isinstance(q, np.ndarray):
         return np.concatenate([q, p], axis=-1)
@@ -273,12 +281,26 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             ntot = torch.empty((N,), dtype=torch.int32, device=dev)
             ws = torch.empty((int(L.gx_workspace_bytes()) // 8,), dtype=torch.int64, device=dev)
             order = _period_order(dq, dp, t0_arr, t1, torch) if (sort and N > 64) else None
-            rc = L.gx_integrate_dopri8(C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
+            if N == 1 and T >= 64 and t0_arr is None and t0s != t1 and layout == "NT3":
+                # single orbit, many saves (mock-stream progenitor): record the steps, evaluate the dense output
+                # for all save times in parallel (gx_integrate_dopri8_record + gx_dense_eval)
+                cap = int(min(ms, 1 << 16)) if ms > 0 else (1 << 16)
+                rec = torch.empty((cap, _lib.DENSE_RECORD_DOUBLES), dtype=torch.float64, device=dev)
+                n_rec = torch.zeros((1,), dtype=torch.int32, device=dev)
+                rc = L.gx_integrate_dopri8_record(C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), t0s, t1, ms,
+                                                  rec.data_ptr(), cap, n_rec.data_ptr(), status.data_ptr(),
+                                                  nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(), stream)  # fmt: skip
+                _lib.check(rc, "gx_integrate_dopri8_record")
+                rc = L.gx_dense_eval(rec.data_ptr(), n_rec.data_ptr(), t0s, t1, dts.data_ptr(), T, q.data_ptr(),
+                                     p.data_ptr(), stream)  # fmt: skip
+                _lib.check(rc, "gx_dense_eval")
+            else:
+              rc = L.gx_integrate_dopri8(C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
                                        None if t0_arr is None else t0_arr.data_ptr(), t0s, t1, dts.data_ptr(), T, ms,
                                        None if order is None else order.data_ptr(), lay, q.data_ptr(), p.data_ptr(),
                                        status.data_ptr(), nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(),
                                        stream)  # fmt: skip
-            _lib.check(rc, "gx_integrate_dopri8")
+              _lib.check(rc, "gx_integrate_dopri8")
             stats["num_accepted_steps"] = nacc.reshape(batch)
             stats["num_steps"] = ntot.reshape(batch)
         else:
@@ -563,12 +585,14 @@ class MockStreamGenerator:
         # stream particles: release time -> t_f = ts[-1] + 1e-3, keep the final state (:88,139)
         t_f = float(ts[-1]) + 1e-3
         field = HamiltonianField(self.potential)
-        arms = {}
-        for name in ("lead", "trail"):
-            arm = mock0[name]
-            w = self.stream_integrator(field, (arm.q, arm.p), ts, t_f, throw=throw)
-            tt = np.ones_like(ts) * ts[-1]
-            arms[name] = MockStreamArm(w.q, w.p, tt, arm.release_time)
+        # both arms in ONE launch: 2M independent particles with per-particle start times on the work queue
+        M = ts.shape[0]
+        lead, trail = mock0["lead"], mock0["trail"]
+        q_all, p_all = _cat0(lead.q, trail.q), _cat0(lead.p, trail.p)
+        w = self.stream_integrator(field, (q_all, p_all), np.concatenate([ts, ts]), t_f, throw=throw)
+        tt = np.ones_like(ts) * ts[-1]
+        arms = {"lead": MockStreamArm(w.q[:M], w.p[:M], tt, lead.release_time),
+                "trail": MockStreamArm(w.q[M:], w.p[M:], tt, trail.release_time)}  # fmt: skip
         return MockStream(arms), prog_o[-1]
 
 

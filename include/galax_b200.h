@@ -119,6 +119,20 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
                         int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream);
 int64_t gx_workspace_bytes(void);
 
+/* Single orbit with many save times (the progenitor orbit of MockStreamGenerator.run, mockstream_generator.py:239:
+ * one adaptive solve saved at all M stripping times).  gx_integrate_dopri8_record integrates ONE particle and
+ * records every accepted step (GX_DENSE_RECORD_DOUBLES doubles each) instead of saving; gx_dense_eval then evaluates
+ * the solver's dense output at M times in parallel.  Numerically identical to gx_integrate_dopri8 with saveat = ts.
+ * rec: device buffer of rec_capacity * GX_DENSE_RECORD_DOUBLES doubles; n_rec: device int32 (records written);
+ * status is GX_MAX_STEPS_REACHED when the buffer was too small. */
+#define GX_DENSE_RECORD_DOUBLES 51
+int gx_integrate_dopri8_record(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0,
+                               double t0, double t1, int64_t max_steps, double *rec, int32_t rec_capacity,
+                               int32_t *n_rec, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
+                               void *workspace, void *stream);
+int gx_dense_eval(const double *rec, const int32_t *n_rec, double t0, double t1, const double *ts, int64_t M,
+                  double *q, double *p, void *stream);
+
 /* Stream release (distribution function).  Replaces FardalStreamDF._sample / ChenStreamDF._sample given the random
  * draws (dynamics/_src/legacy/mockstream/df/fardal15.py:49-94, df/chen24.py:61-137; tidal radius
  * dynamics/_src/cluster/radius.py:198-215; omega dynamics/_src/register_api.py:77-88).

@@ -299,3 +299,27 @@ def test_mockstream_generator_matches_oracle_and_reference_test_shape():
     assert np.abs(stream["lead"].q - ref["lead_q"]).max() < 5e-3
     assert np.abs(stream["trail"].q - ref["trail_q"]).max() < 5e-3
     assert np.median(np.abs(stream["lead"].q - ref["lead_q"])) < 2e-4
+
+
+def test_single_orbit_record_and_parallel_dense_output_matches_in_kernel_saves():
+    """N = 1 with many saves takes gx_integrate_dopri8_record + gx_dense_eval; it must reproduce the in-kernel
+    SaveAt path (same steps, same continuous extension)."""
+    pot = gp.MilkyWayPotential()
+    q0 = np.array([[30.0, 10.0, 20.0]])
+    p0 = np.array([[10.0, -150.0, -20.0]]) * KMS
+    ts = np.linspace(0.0, 3000.0, 777)
+    kw = dict(solver=gd.Dopri8(), controller=gd.PIDController(1e-7, 1e-7), dt0=None, max_steps=None)
+    q1, p1, st1, s1 = gd._integrate(pot, q0, p0, 0.0, 3000.0, ts, **kw)  # N = 1, T >= 64: record path
+    q2, p2, st2, s2 = gd._integrate(pot, np.repeat(q0, 2, 0), np.repeat(p0, 2, 0), 0.0, 3000.0, ts, **kw)
+    assert q1.shape == (1, 777, 3)
+    assert int(s1["num_accepted_steps"][0]) == int(s2["num_accepted_steps"][0])
+    assert np.allclose(q1[0], q2[0], rtol=1e-13, atol=1e-13) and np.allclose(p1[0], p2[0], rtol=1e-13, atol=1e-15)
+    assert np.array_equal(q1[0, 0], q0[0])
+    # backward in time and a record buffer that is too small
+    tb = np.linspace(0.0, -1000.0, 100)
+    qb1, _, _, _ = gd._integrate(pot, q0, p0, 0.0, -1000.0, tb, **kw)
+    qb2, _, _, _ = gd._integrate(pot, np.repeat(q0, 2, 0), np.repeat(p0, 2, 0), 0.0, -1000.0, tb, **kw)
+    assert np.allclose(qb1[0], qb2[0], rtol=1e-13, atol=1e-13)
+    with pytest.raises(RuntimeError, match="max_steps"):
+        gd._integrate(pot, q0, p0, 0.0, 3000.0, ts, solver=gd.Dopri8(), controller=gd.PIDController(1e-7, 1e-7),
+                      dt0=None, max_steps=20)

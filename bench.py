@@ -82,7 +82,7 @@ def run_reference(args) -> None:
     n = CPU_SAMPLE_PARTICLES
     q, r, vdir, f = host_ics(n, seed=1)
     p = vdir * (op.circular_velocity(opot, r) * f)[:, None]
-    cores = cref.num_threads()
+    cores = cref.use_all_cores()
 
     def step():
         cref.integrate_fixed(opot, q, p, 0.0, T1, DT0, [T1])
@@ -318,6 +318,7 @@ def run_gpu(args) -> None:
         from oracle import potentials as op
 
         cref.build()
+        cref.use_all_cores()
         opot = op.milky_way_potential()
         ns = CPU_SAMPLE_PARTICLES
         cref.integrate_fixed(opot, q_h[:256], p_h[:256], 0.0, 10.0, DT0, [10.0])  # warm

@@ -115,6 +115,13 @@ def num_threads() -> int:
     return int(lib().oc_num_threads())
 
 
+def use_all_cores() -> int:
+    """Override OMP_NUM_THREADS (torchrun sets it to 1): use every core this process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oc_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def gammainc(a: float, x: float) -> float:
     return float(lib().oc_gammainc(a, x))
 

@@ -623,6 +623,14 @@ void oc_release_chen(const oc_potential *P, int64_t M, const double *xq, const d
     }
 }
 
+void oc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oc_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

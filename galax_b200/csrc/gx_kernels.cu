@@ -18,6 +18,7 @@
 #include "../../include/galax_b200.h"
 #include "gx_potential.cuh"
 #include "gx_tables.h"
+#include "plc_table.h"
 
 namespace gx {
 
@@ -41,7 +42,7 @@ static void fill_gamma_tab(GammaTab &g, double a) {
     for (int n = 0; n < PLC_NT; ++n) g.inv[n] = 1.0 / (a + n);
 }
 
-static int build_devpot(const gx_potential *pot, DevPot &D, Model &model) {
+static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool use_device = true) {
     if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
     memset(&D, 0, sizeof D);
     const double G = pot->G;
@@ -80,6 +81,8 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model) {
             DevPLC &p = D.plc[D.n_plc++];
             p.GM = G * c.p[0];
             p.inv_rc = 1.0 / rc;
+            p.GM_rc3 = p.GM / (rc * rc * rc);
+            p.tab = use_device ? plc_table_for(1.5 - alpha / 2) : nullptr;
             fill_gamma_tab(p.ga, 1.5 - alpha / 2);
             fill_gamma_tab(p.ga2, 1.0 - alpha / 2);
             p.tail = tgamma(p.ga2.a) / (rc * tgamma(p.ga.a));

@@ -30,7 +30,36 @@ constexpr double TINY = 2.2250738585072014e-308;
 struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
 struct DevHern { double GM, c; };
 struct DevNFW { double GM, rs, inv_rs, GM_inv_rs; };
-struct DevPLC { double GM, inv_rc, tail; GammaTab ga, ga2; };  // ga: a = 3/2 - alpha/2; ga2: a - 1/2; tail = Gamma(a2)/(rc Gamma(a))
+// ga: a = 3/2 - alpha/2; ga2: a - 1/2; tail = Gamma(a2)/(rc Gamma(a)).
+// tab: optional device table of G(s) = P(a, s^2) / s^3, s = r/r_c, as degree-(PLC_DEG) polynomials on 8 intervals
+// per octave of s in [2^PLC_E_LO, 2^PLC_E_HI) (built on the host in long double, see plc_table.h); GM_rc3 = GM/rc^3.
+constexpr int PLC_DEG = 13, PLC_E_LO = -11, PLC_E_HI = 3, PLC_SUB = 8;
+constexpr int PLC_NINT = (PLC_E_HI - PLC_E_LO) * PLC_SUB;
+constexpr double PLC_S_ONE = 8.0;  // = 2^PLC_E_HI: s^2 = 64 > xcut (<= 41 for every 0 < a <= 3/2), so P == 1
+struct DevPLC { double GM, inv_rc, tail, GM_rc3; const double *tab; GammaTab ga, ga2; };
+
+// G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
+__device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double &G, double *dG) {
+    if (c.tab == nullptr) return false;
+    const int hi = __double2hiint(s);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    if (e < PLC_E_LO || e >= PLC_E_HI) return false;
+    const int sub = (hi >> 17) & (PLC_SUB - 1);
+    const int j = (e - PLC_E_LO) * PLC_SUB + sub;
+    // interval [2^e (1 + sub/8), 2^e (1 + (sub+1)/8)): t in [-1, 1)
+    const double scale = __hiloint2double((1023 - e + 4) << 20, 0);              // 2^(4-e) = 16 / 2^e
+    const double t = fma(s, scale, -(double)(2 * PLC_SUB + 2 * sub + 1));      // 16 s/2^e - 16 - 2 sub - 1
+    const double *p = c.tab + (long long)j * (PLC_DEG + 1);
+    double v = __ldg(p + PLC_DEG), d = 0.0;
+#pragma unroll
+    for (int k = PLC_DEG - 1; k >= 0; --k) {
+        if (dG) d = fma(d, t, v);
+        v = fma(v, t, __ldg(p + k));
+    }
+    G = v;
+    if (dG) *dG = d * scale;  // dt/ds = scale
+    return true;
+}
 
 struct DevPot {
     int n_mn, n_hern, n_nfw, n_plc;
@@ -111,9 +140,16 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
         for (int i = 0; i < C::kPLC; ++i) {
             if (!C::is_static && i >= P.n_plc) break;
             const DevPLC &c = P.plc[i];
-            double s = r * c.inv_rc;
-            double Pg = gammainc_P(c.ga, s * s, nullptr);
-            fs = fma((c.GM * Pg) * rinv, rinv2, fs);  // GM P(a, s^2) / r^3
+            const double s = r * c.inv_rc;
+            double Gs;
+            if (s >= PLC_S_ONE) {
+                fs = fma(c.GM * rinv, rinv2, fs);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
+            } else if (plc_table_eval(c, s, Gs, nullptr)) {
+                fs = fma(c.GM_rc3, Gs, fs);  // GM P(a, s^2) / r^3 = (GM / rc^3) G(s)
+            } else {
+                const double Pg = gammainc_P(c.ga, s * s, nullptr);
+                fs = fma((c.GM * Pg) * rinv, rinv2, fs);
+            }
             have_s = true;
         }
     }
@@ -214,11 +250,23 @@ __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, d
             if (!C::is_static && i >= P.n_plc) break;
             const DevPLC &c = P.plc[i];
             const double s = r * c.inv_rc;
-            double dP;
-            const double Pg = gammainc_P(c.ga, s * s, &dP);
-            const double t = ((c.GM * Pg) * rinv) * rinv2;
-            d1r += t;
-            d2 += fma(c.GM * dP * 2.0 * c.inv_rc * c.inv_rc, rinv, -2.0 * t);
+            double Gs, dGs;
+            if (s >= PLC_S_ONE) {
+                const double t = (c.GM * rinv) * rinv2;  // P == 1, dP/dx == 0 in fp64
+                d1r += t;
+                d2 -= 2.0 * t;
+            } else if (plc_table_eval(c, s, Gs, &dGs)) {
+                // Phi'/r = K G(s), K = GM/rc^3;  Phi'' = d(r K G)/dr = K (G + s G')
+                const double t = c.GM_rc3 * Gs;
+                d1r += t;
+                d2 += fma(c.GM_rc3 * s, dGs, t);
+            } else {
+                double dP;
+                const double Pg = gammainc_P(c.ga, s * s, &dP);
+                const double t = ((c.GM * Pg) * rinv) * rinv2;
+                d1r += t;
+                d2 += fma(c.GM * dP * 2.0 * c.inv_rc * c.inv_rc, rinv, -2.0 * t);
+            }
         }
         // H += (Phi'/r) I + (Phi'' - Phi'/r) n n^T
         const double w = (d2 - d1r) * rinv2;

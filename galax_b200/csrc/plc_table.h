@@ -1,0 +1,116 @@
+// plc_table.h -- host-side construction and per-device cache of the PowerLawCutoff force table.
+//
+// G(s) = P(a, s^2) / s^3 (s = r / r_c, P the regularised lower incomplete gamma function) is what the
+// PowerLawCutoff force needs: Phi'(r)/r = (G M / r_c^3) G(s)  (reference: builtin/powerlawcutoff.py:88-117, whose
+// gradient collapses to G M P(a, s^2) / r^2).  The direct evaluation (log, exp, a ~60-term series) made
+// BovyMWPotential2014 ten times slower than MilkyWayPotential, so G is tabulated once per exponent a: 8 intervals
+// per octave of s over [2^-11, 2^3), a degree-13 polynomial each (relative error < 3e-16, checked at build time
+// against the long-double series on a finer grid).  Outside the range the kernels fall back to the series.
+//
+// The table depends only on a; it is built in long double on the host, uploaded once per (device, a) and kept for
+// the life of the process (immutable after creation, so sharing it between streams and threads is safe).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <mutex>
+#include <vector>
+
+#include "gx_potential.cuh"
+
+namespace gx {
+
+// P(a, x) in long double: positive-term series (x < a + 40) -- enough for x = s^2 < 64.
+static long double plc_P_ld(long double a, long double x) {
+    if (x <= 0.0L) return 0.0L;
+    long double ap = a, del = 1.0L / a, sum = del;
+    for (int n = 0; n < 4000; ++n) {
+        ap += 1.0L;
+        del *= x / ap;
+        sum += del;
+        if (del < sum * 1e-22L) break;
+    }
+    long double v = sum * expl(-x + a * logl(x) - lgammal(a));
+    return v > 1.0L ? 1.0L : v;
+}
+
+static long double plc_G_ld(long double a, long double s) { return plc_P_ld(a, s * s) / (s * s * s); }
+
+// Chebyshev interpolation on [-1, 1] at PLC_DEG+1 nodes, converted to monomial coefficients in long double.
+static void plc_fit_interval(long double a, long double s0, long double s1, double *coef, double *max_rel_err) {
+    constexpr int n = PLC_DEG + 1;
+    const long double PI = 3.141592653589793238462643383279502884L;
+    long double f[n], c[n];
+    for (int k = 0; k < n; ++k) {
+        long double tk = cosl(PI * (k + 0.5L) / n);
+        f[k] = plc_G_ld(a, 0.5L * (s0 + s1) + 0.5L * (s1 - s0) * tk);
+    }
+    for (int j = 0; j < n; ++j) {  // Chebyshev coefficients
+        long double sum = 0.0L;
+        for (int k = 0; k < n; ++k) sum += f[k] * cosl(PI * j * (k + 0.5L) / n);
+        c[j] = 2.0L * sum / n;
+    }
+    c[0] *= 0.5L;
+    // Chebyshev -> monomial: accumulate T_j(t) by the three-term recurrence on coefficient vectors
+    long double mono[n] = {0}, Tm1[n] = {0}, Tm0[n] = {0}, Tn[n];
+    Tm1[0] = 1.0L;  // T_0
+    Tm0[1] = 1.0L;  // T_1
+    for (int i = 0; i < n; ++i) mono[i] += c[0] * Tm1[i];
+    if (n > 1)
+        for (int i = 0; i < n; ++i) mono[i] += c[1] * Tm0[i];
+    for (int j = 2; j < n; ++j) {
+        for (int i = 0; i < n; ++i) Tn[i] = -Tm1[i];
+        for (int i = 0; i + 1 < n; ++i) Tn[i + 1] += 2.0L * Tm0[i];
+        for (int i = 0; i < n; ++i) { mono[i] += c[j] * Tn[i]; Tm1[i] = Tm0[i]; Tm0[i] = Tn[i]; }
+    }
+    for (int i = 0; i < n; ++i) coef[i] = (double)mono[i];
+    // verify in double Horner (what the device does) on a fine grid
+    double worst = 0.0;
+    for (int k = 0; k <= 40; ++k) {
+        double t = -1.0 + 2.0 * k / 40.0;
+        double v = coef[n - 1];
+        for (int i = n - 2; i >= 0; --i) v = fma(v, t, coef[i]);
+        long double s = 0.5L * (s0 + s1) + 0.5L * (s1 - s0) * (long double)t;
+        long double ref = plc_G_ld(a, s);
+        double rel = (double)fabsl(((long double)v - ref) / ref);
+        if (rel > worst) worst = rel;
+    }
+    if (max_rel_err && worst > *max_rel_err) *max_rel_err = worst;
+}
+
+struct PlcTableEntry { int device; double a; double *dev_ptr; double max_rel_err; };
+
+// Returns the device table for exponent a on the current device (building and uploading it on first use), or
+// nullptr if it cannot be built to 1e-14 (then the kernels use the series).
+static const double *plc_table_for(double a, double *max_rel_err_out = nullptr) {
+    static std::mutex mu;
+    static std::vector<PlcTableEntry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &e : cache)
+        if (e.device == dev && e.a == a) {
+            if (max_rel_err_out) *max_rel_err_out = e.max_rel_err;
+            return e.dev_ptr;
+        }
+    std::vector<double> host((size_t)PLC_NINT * (PLC_DEG + 1));
+    double worst = 0.0;
+    for (int j = 0; j < PLC_NINT; ++j) {
+        const int e = PLC_E_LO + j / PLC_SUB, sub = j % PLC_SUB;
+        const long double base = ldexpl(1.0L, e);
+        plc_fit_interval(a, base * (1.0L + sub / (long double)PLC_SUB), base * (1.0L + (sub + 1) / (long double)PLC_SUB),
+                         host.data() + (size_t)j * (PLC_DEG + 1), &worst);
+    }
+    double *d = nullptr;
+    if (worst < 1e-14 && cudaMalloc(&d, host.size() * sizeof(double)) == cudaSuccess) {
+        if (cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(d);
+            d = nullptr;
+        }
+    }
+    cache.push_back({dev, a, d, worst});
+    if (max_rel_err_out) *max_rel_err_out = worst;
+    return d;
+}
+
+}  // namespace gx

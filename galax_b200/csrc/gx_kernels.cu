@@ -137,52 +137,120 @@ __global__ void __launch_bounds__(256) k_potential_eval_direct(const __grid_cons
     }
 }
 
-// With the Hessian (72 B/point out) tiles of 256 points are staged through shared memory so that every global access is a fully coalesced
-// 8-byte-per-lane stream (the natural [N,3] / [N,3,3] layouts would otherwise make each store instruction
-// touch 32 different sectors).  Persistent grid-stride over tiles.
+// ---- TMA (bulk async copy) + mbarrier helpers: 1-D cp.async.bulk global <-> shared, sm_90+ ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GX_DONE;\n"
+        "bra GX_WAIT;\n"
+        "GX_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// With the Hessian (72 B/point out) the natural [N,3] / [N,3,3] layouts would make every store instruction
+// touch 32 different sectors, so tiles of 256 points are staged through shared memory and moved by the TMA engine:
+// one elected thread issues a 6 KB cp.async.bulk load per tile (completion on an mbarrier, the next tile's load
+// is in flight while the current one is computed) and 6/6/18 KB cp.async.bulk stores of the results.
+// Persistent CTAs, grid-stride over tiles; a ragged last tile takes the plain load/store path.
 constexpr int EVAL_TILE = 256;
 
 template <class C>
 __global__ void __launch_bounds__(EVAL_TILE) k_potential_eval(const __grid_constant__ DevPot P, const EvalArgs a) {
-    __shared__ double s_in[EVAL_TILE * 3];
-    __shared__ double s_g[EVAL_TILE * 3];
-    __shared__ double s_h[EVAL_TILE * 9];
+    __shared__ alignas(128) double s_in[2][EVAL_TILE * 3];
+    __shared__ alignas(128) double s_g[EVAL_TILE * 3];
+    __shared__ alignas(128) double s_a[EVAL_TILE * 3];
+    __shared__ alignas(128) double s_h[EVAL_TILE * 9];
+    __shared__ alignas(8) unsigned long long bar[2];
     const int tid = threadIdx.x;
     const long long n_tiles = (a.N + EVAL_TILE - 1) / EVAL_TILE;
     const bool want_g = (a.what & (GX_GRAD | GX_ACC)) != 0, want_h = (a.what & GX_HESS) != 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto tile_cnt = [&](long long t) { long long r = a.N - t * EVAL_TILE; return (int)(r < EVAL_TILE ? r : EVAL_TILE); };
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles && tile_cnt(tile) == EVAL_TILE) {
+        mbar_expect_tx(&bar[0], EVAL_TILE * 24);
+        tma_load_1d(s_in[0], a.xyz + tile * EVAL_TILE * 3, EVAL_TILE * 24, &bar[0]);
+    }
+    unsigned it = 0;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
         const long long base = tile * EVAL_TILE;
-        const int cnt = (int)((a.N - base) < EVAL_TILE ? (a.N - base) : EVAL_TILE);
-        for (int k = tid; k < cnt * 3; k += EVAL_TILE) s_in[k] = __ldg(a.xyz + base * 3 + k);
-        __syncthreads();
+        const int cnt = tile_cnt(tile);
+        const bool full = (cnt == EVAL_TILE);
+        const long long next = tile + gridDim.x;
+        if (tid == 0 && next < n_tiles && tile_cnt(next) == EVAL_TILE) {  // prefetch the next tile
+            mbar_expect_tx(&bar[stage ^ 1], EVAL_TILE * 24);
+            tma_load_1d(s_in[stage ^ 1], a.xyz + next * EVAL_TILE * 3, EVAL_TILE * 24, &bar[stage ^ 1]);
+        }
+        if (full) {
+            mbar_wait(&bar[stage], (it >> 1) & 1);
+        } else {
+            for (int k = tid; k < cnt * 3; k += EVAL_TILE) s_in[stage][k] = __ldg(a.xyz + base * 3 + k);
+            __syncthreads();
+        }
         if (tid < cnt) {
-            const double x = s_in[3 * tid], y = s_in[3 * tid + 1], z = s_in[3 * tid + 2];
+            const double x = s_in[stage][3 * tid], y = s_in[stage][3 * tid + 1], z = s_in[stage][3 * tid + 2];
             if (a.what & GX_PHI) a.phi[base + tid] = potential_value<C>(P, x, y, z);  // already coalesced
+            double g[3] = {0, 0, 0};
             if (want_h) {
-                double g[3], H[6];
+                double H[6];
                 grad_hess<C>(P, x, y, z, g, H);
-                s_g[3 * tid] = g[0]; s_g[3 * tid + 1] = g[1]; s_g[3 * tid + 2] = g[2];
                 double *h = s_h + 9 * tid;
                 h[0] = H[0]; h[1] = H[1]; h[2] = H[2];
                 h[3] = H[1]; h[4] = H[3]; h[5] = H[4];
                 h[6] = H[2]; h[7] = H[4]; h[8] = H[5];
             } else if (want_g) {
-                double g0, g1, g2;
-                gradient<C>(P, x, y, z, g0, g1, g2);
-                s_g[3 * tid] = g0; s_g[3 * tid + 1] = g1; s_g[3 * tid + 2] = g2;
+                gradient<C>(P, x, y, z, g[0], g[1], g[2]);
             }
+            if (a.what & GX_GRAD) { s_g[3 * tid] = g[0]; s_g[3 * tid + 1] = g[1]; s_g[3 * tid + 2] = g[2]; }
+            if (a.what & GX_ACC) { s_a[3 * tid] = -g[0]; s_a[3 * tid + 1] = -g[1]; s_a[3 * tid + 2] = -g[2]; }
+        }
+        if (full) {
+            fence_async_smem();  // make the generic-proxy writes above visible to the async (TMA) proxy
+            __syncthreads();
+            if (tid == 0) {
+                if (a.what & GX_GRAD) tma_store_1d(a.grad + base * 3, s_g, EVAL_TILE * 24);
+                if (a.what & GX_ACC) tma_store_1d(a.acc + base * 3, s_a, EVAL_TILE * 24);
+                if (want_h) tma_store_1d(a.hess + base * 9, s_h, EVAL_TILE * 72);
+                tma_commit();
+                tma_wait_read0();  // the staging buffers may be rewritten once the engine has read them
+            }
+        } else {
+            __syncthreads();
+            if (a.what & GX_GRAD) for (int k = tid; k < cnt * 3; k += EVAL_TILE) a.grad[base * 3 + k] = s_g[k];
+            if (a.what & GX_ACC) for (int k = tid; k < cnt * 3; k += EVAL_TILE) a.acc[base * 3 + k] = s_a[k];
+            if (want_h) for (int k = tid; k < cnt * 9; k += EVAL_TILE) a.hess[base * 9 + k] = s_h[k];
         }
         __syncthreads();
-        if (a.what & GX_GRAD)
-            for (int k = tid; k < cnt * 3; k += EVAL_TILE) a.grad[base * 3 + k] = s_g[k];
-        if (a.what & GX_ACC)
-            for (int k = tid; k < cnt * 3; k += EVAL_TILE) a.acc[base * 3 + k] = -s_g[k];
-        if (want_h)
-            for (int k = tid; k < cnt * 9; k += EVAL_TILE) a.hess[base * 9 + k] = s_h[k];
-        // the next iteration's loads into s_in are ordered after this iteration's reads by the barrier above;
-        // s_g / s_h are rewritten only after the next barrier
-        __syncthreads();
     }
+    if (tid == 0) tma_wait_all();
 }
 
 // ================================================================================================
@@ -846,7 +914,7 @@ int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int6
     long long want = (N + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
     if (what & GX_HESS) {
-        int grid = (int)(want < 148LL * 6 ? want : 148LL * 6);  // persistent: 6 CTAs of 256 threads per SM
+        int grid = (int)(want < 148LL * 5 ? want : 148LL * 5);  // persistent: 5 CTAs (43 KB smem each) per SM
         GX_DISPATCH_MODEL(model, (k_potential_eval<C><<<grid, block, 0, s>>>(D, a)));
     } else {
         int grid = (int)(want < 148LL * 32 ? want : 148LL * 32);

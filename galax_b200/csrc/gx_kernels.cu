@@ -285,8 +285,11 @@ __device__ __forceinline__ bool finite3(double a, double b, double c) {
 // y1 = y0 + f*dt as a multiply followed by an add, and XLA:CPU does not contract them.
 // The time grid (tnext = tprev + dt0 accumulated in fp64, last step clipped to t1) is identical for every
 // particle; the host walks it once to get the trip count, so the device loop is a counted loop.
+#ifndef GX_FIXED_MIN_BLOCKS
+#define GX_FIXED_MIN_BLOCKS 1
+#endif
 template <class C, int SCHEME, bool FWD>
-__global__ void __launch_bounds__(128) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
+__global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     // integrate in tau = dir * t (diffrax flips the sign of time the same way for t1 < t0)
@@ -851,6 +854,26 @@ __global__ void k_bench_dfma(long long iters, double *sink) {
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// Same, but every DFMA reads three different registers (x <- x*y + z with y, z loop-carried), the operand pattern
+// of real code: measures what the register file can feed the FP64 pipe.
+__global__ void k_bench_dfma3(long long iters, double *sink) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    double y0 = 0.999999 + x0 * 1e-9, y1 = y0 - 1e-9, y2 = y0 - 2e-9, y3 = y0 - 3e-9;
+    double z0 = 1e-6 + x0 * 1e-12, z1 = z0 * 1.1, z2 = z0 * 1.2, z3 = z0 * 1.3;
+    for (long long it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, y0, z0); x1 = fma(x1, y1, z1); x2 = fma(x2, y2, z2); x3 = fma(x3, y3, z3);
+            x4 = fma(x4, y1, z0); x5 = fma(x5, y2, z1); x6 = fma(x6, y3, z2); x7 = fma(x7, y0, z3);
+        }
+        // keep y, z loop-carried so they stay in registers and are not folded
+        y0 = fma(y0, 1.0, 0.0 * x0); z0 = fma(z0, 1.0, 0.0 * x1);
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) sink[0] = s + y0 + y1 + y2 + y3 + z0 + z1 + z2 + z3;
+}
+
 __global__ void k_debug_math(int op, const GammaTab *gt, const double *x, long long N, double *out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -1073,8 +1096,11 @@ int gx_energy_angmom(const gx_potential *pot, const double *q, const double *p, 
 
 int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, int64_t *fma_per_thread,
                   void *stream) {
-    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink) return GX_ERR_BADARG;
-    k_bench_dfma<<<blocks, threads, 0, (cudaStream_t)stream>>>((long long)iters, sink);
+    if (blocks == 0 || threads <= 0 || threads > 1024 || !sink) return GX_ERR_BADARG;
+    if (iters < 0) return GX_ERR_BADARG;
+    // blocks < 0 selects the three-register-operand variant (same instruction count)
+    if (blocks < 0) k_bench_dfma3<<<-blocks, threads, 0, (cudaStream_t)stream>>>((long long)iters, sink);
+    else k_bench_dfma<<<blocks, threads, 0, (cudaStream_t)stream>>>((long long)iters, sink);
     if (fma_per_thread) *fma_per_thread = iters * 8 * 16;
     return cuda_rc(cudaGetLastError());
 }

@@ -163,7 +163,9 @@ int gx_host_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const d
 
 /* ---- measurement helpers ---- */
 /* FP64 FMA-pipe peak: every thread runs `iters` rounds of 8 independent DFMA chains.  Returns the number of
- * DFMA instructions issued per thread (iters*8*unroll) via *fma_per_thread; time it with events on `stream`. */
+ * DFMA instructions issued per thread (iters*8*unroll) via *fma_per_thread; time it with events on `stream`.
+ * blocks > 0: x <- x*m + c with m, c constants (one register operand; the textbook peak);
+ * blocks < 0: |blocks| CTAs of x <- x*y + z with three distinct register operands (what real code looks like). */
 int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, int64_t *fma_per_thread, void *stream);
 /* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x) */
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream);

@@ -323,3 +323,22 @@ def test_single_orbit_record_and_parallel_dense_output_matches_in_kernel_saves()
     with pytest.raises(RuntimeError, match="max_steps"):
         gd._integrate(pot, q0, p0, 0.0, 3000.0, ts, solver=gd.Dopri8(), controller=gd.PIDController(1e-7, 1e-7),
                       dt0=None, max_steps=20)
+
+
+def test_host_arrays_round_trip_through_pinned_memory():
+    """numpy in -> numpy out, CPU torch in -> CPU torch out (pinned staging), identical to the CUDA-tensor path."""
+    import torch
+
+    pot, opot = gp.MilkyWayPotential(), op.milky_way_potential()
+    q0, p0 = synthetic_ics(opot, 5003, seed=21)
+    kw = dict(solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(), dt0=0.1, max_steps=None)
+    ts = np.array([0.0, 12.5, 50.0])
+    ref = gd._integrate(pot, torch.from_numpy(q0).cuda(), torch.from_numpy(p0).cuda(), 0.0, 50.0, ts, **kw)
+    assert ref[0].is_cuda
+    got = gd._integrate(pot, q0, p0, 0.0, 50.0, ts, **kw)
+    assert isinstance(got[0], np.ndarray) and np.array_equal(got[0], ref[0].cpu().numpy())
+    got_t = gd._integrate(pot, torch.from_numpy(q0).pin_memory(), torch.from_numpy(p0).pin_memory(), 0.0, 50.0, ts, **kw)
+    assert not got_t[0].is_cuda and np.array_equal(got_t[1].numpy(), ref[1].cpu().numpy())
+    keep = got[0].copy()
+    gd._integrate(pot, q0 * 1.01, p0, 0.0, 50.0, ts, **kw)  # a later call must not overwrite an earlier result
+    assert np.array_equal(got[0], keep)

@@ -299,7 +299,9 @@ def run_gpu(args) -> None:
     achieved = per_gpu_rate * FLOP_PER_STEP / 1e12
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved / dfma_peak,
-        "traffic": None,
+        "traffic": 80.5e6 if n == N_PER_GPU else None,
+        "traffic_source": "ncu --set full, profiles/ncu_k_integrate_fixed_r1.txt: dram read 59.9 MB + write 20.7 MB per "
+                          "launch (algorithmic: 58.2 MB in + 58.2 MB out + 4.8 MB status; L2 absorbs part of the writes)",
         "kernel": "k_integrate_fixed<MW,SIE>", "kernel_ms": k_ms,
         "algorithmic_flop_per_particle_step": FLOP_PER_STEP,
         "peak_three_register_operands": dfma_peak_3reg,
@@ -308,6 +310,33 @@ def run_gpu(args) -> None:
         "note": "canonical weighted flop (div/sqrt=18, log1p=56) per SURVEY.md 8d; the kernel issues fewer real "
                 "instructions than that (MUFU-seeded rcp/rsqrt), see profiles/ for ncu-counted FP64 instructions",
     }  # fmt: skip
+
+    # The HBM-bound leg of the path (C5): acceleration + Hessian on 2e7 points, against the measured copy peak
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        hbm_peak, hbm_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+    else:
+        hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    npts = 20_000_000
+    xs = torch.randn(npts, 3, dtype=torch.float64, device=dev) * 10
+    acc_o = torch.empty((npts, 3), dtype=torch.float64, device=dev)
+    hes_o = torch.empty((npts, 9), dtype=torch.float64, device=dev)
+    k1 = []
+    for i in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        L.gx_potential_eval(C.byref(P), xs.data_ptr(), 0.0, npts, _lib.ACC | _lib.HESS, None, None, acc_o.data_ptr(),
+                            hes_o.data_ptr(), stream)
+        b.record()
+        torch.cuda.synchronize()
+        if i:
+            k1.append(a.elapsed_time(b) * 1e-3)
+    k1_gbs = npts * 120 / float(np.mean(k1)) / 1e9
+    roofline_k1 = {"bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak,
+                   "traffic": None, "kernel": "k_potential_eval<MW> (acc + Hessian, TMA-staged tiles)",
+                   "algorithmic_bytes_per_point": 120, "points": npts, "peak_source": hbm_src}  # fmt: skip
+    del xs, acc_o, hes_o
 
     # C1 exactly as stated: 10^4 particles
     qc, pc = q_d[:10_000].contiguous(), p_d[:10_000].contiguous()
@@ -356,7 +385,7 @@ def run_gpu(args) -> None:
                 "d2h_bytes_per_step": (2 * n * 24 + n * 4) * world,
                 "api": "galax_b200.dynamics.OrbitSolver(SemiImplicitEuler, ConstantStepSize).solve(pot, (q, p), 0, 1000, dt0=0.1) "
                        "with pinned host tensors"},
-        "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": gpu_launches, "roofline": roofline, "roofline_hbm_leg": roofline_k1, "cpu_baseline": cpu,
         "c1_exact": {"particles": 10_000, "value": c1_rate, "unit": UNIT, "ms": min(c1) * 1e3},
         "energy_drift": energy, "fp64_peak_tflops_measured": dfma_peak,
         "fp64_peak_tflops_measured_3reg_operands": dfma_peak_3reg,

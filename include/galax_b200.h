@@ -13,8 +13,9 @@
  *   - return value: 0 on success, <0 on an argument / CUDA error (gx_strerror); per-particle
  *     outcomes (max_steps reached, non-finite state) are reported in the `status` array;
  *   - units: whatever unit system the potential parameters are expressed in (galax: kpc, Myr, Msun);
- *   - re-entrant: no global mutable state; the potential is passed by value into each launch
- *     (kernel-parameter constant bank).
+ *   - re-entrant: the potential is passed by value into each launch (kernel-parameter constant bank); the only
+ *     process-wide state is an append-only, mutex-guarded cache of immutable PowerLawCutoff force tables
+ *     (12.5 KB of device memory per device and exponent, allocated on first use).
  */
 #ifndef GALAX_B200_H
 #define GALAX_B200_H

@@ -9,8 +9,8 @@ C ABI in ``include/galax_b200.h``); there is no CPU fallback.
     import galax_b200.dynamics as gd
 """
 
-from . import _lib, dynamics, potential
+from . import _lib, dynamics, experimental, potential
 from ._lib import GalaxB200Error, build
 
-__all__ = ["potential", "dynamics", "build", "GalaxB200Error"]
+__all__ = ["potential", "dynamics", "experimental", "build", "GalaxB200Error"]
 __version__ = "0.1.0"

@@ -32,6 +32,7 @@ SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1
 LAYOUT_NT3, LAYOUT_T3N = 0, 1
 DF_FARDAL15, DF_CHEN24 = 0, 1
 DENSE_RECORD_DOUBLES = 51
+SOLVER_DOPRI8, SOLVER_DOPRI5 = 8, 5
 
 
 class GxComponent(C.Structure):
@@ -111,6 +112,15 @@ _SIGNATURES = {
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gx_dense_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    "gx_integrate_adaptive": (C.c_int, [C.c_int32, C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int64,
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_integrate_adaptive_record": (C.c_int, [C.c_int32, C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p,
+                                               C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_void_p, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_dense_eval_solver": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gx_stream_release": (C.c_int, [C.POINTER(GxPotential), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),

@@ -65,30 +65,62 @@ DENSE_B = [
 
 N = 14
 
+# ---- Dormand-Prince 5(4), 7 stages FSAL (diffrax.Dopri5; the reference's experimental StreamSimulator default,
+# dynamics/_src/experimental/stream.py:32-41).  Dense output = diffrax's FourthOrderPolynomialInterpolation with
+# Shampine's mid-point weights, rewritten as stage weights b_i(theta) (see oracle/dopri5_tableau.py).
+A5 = [
+    [],
+    [F(1, 5)],
+    [F(3, 40), F(9, 40)],
+    [F(44, 45), F(-56, 15), F(32, 9)],
+    [F(19372, 6561), F(-25360, 2187), F(64448, 6561), F(-212, 729)],
+    [F(9017, 3168), F(-355, 33), F(46732, 5247), F(49, 176), F(-5103, 18656)],
+    [F(35, 384), F(0), F(500, 1113), F(125, 192), F(-2187, 6784), F(11, 84)],
+]
+B5_SOL = [F(35, 384), F(0), F(500, 1113), F(125, 192), F(-2187, 6784), F(11, 84), F(0)]
+B5_HAT = [F(5179, 57600), F(0), F(7571, 16695), F(393, 640), F(-92097, 339200), F(187, 2100), F(1, 40)]
+C5 = [F(0), F(1, 5), F(3, 10), F(4, 5), F(8, 9), F(1), F(1)]
+C5_MID = [F(6025192743, 30085553152) / 2, F(0), F(51252292925, 65400821598) / 2, F(-2691868925, 45128329728) / 2,
+          F(187940372067, 1594534317056) / 2, F(-1776094331, 19743644256) / 2, F(11237099, 235043384) / 2]
 
-def amat():
-    return [[F(A[i][j]) if j < len(A[i]) else F(0) for j in range(N)] for i in range(N)]
+
+def dense5():
+    out = []
+    for i in range(7):
+        d0, d6 = F(int(i == 0)), F(int(i == 6))
+        b, cm = B5_SOL[i], C5_MID[i]
+        out.append([d0, d6 - 4 * d0 - 5 * b + 16 * cm, 5 * d0 - 3 * d6 + 14 * b - 32 * cm,
+                    2 * d6 - 2 * d0 - 8 * b + 16 * cm, F(0), F(0)])
+    return out
 
 
-def tables():
-    Am = amat()
-    AA = [[sum(Am[i][j] * Am[j][l] for j in range(N)) for l in range(N)] for i in range(N)]
-    e = [F(s) - F(h) for s, h in zip(B_SOL, B_HAT)]
-    eA = [sum(e[j] * Am[j][l] for j in range(N)) for l in range(N)]
-    DB = [[F(v) for v in row] for row in DENSE_B]
-    DQ = [[sum(DB[j][m] * Am[j][l] for j in range(N)) for m in range(6)] for l in range(N)]
-    return dict(A=Am, AA=AA, C=C, B=[F(b) for b in B_SOL], E=e, EA=eA, DB=DB, DQ=DQ)
+def amat(Arows=None, n=N):
+    Arows = A if Arows is None else Arows
+    return [[F(Arows[i][j]) if j < len(Arows[i]) else F(0) for j in range(n)] for i in range(n)]
+
+
+def tables(which="dp8"):
+    if which == "dp8":
+        n, Am, bs, bh, cs = N, amat(), B_SOL, B_HAT, C
+        DB = [[F(v) for v in row] for row in DENSE_B]
+    else:
+        n, Am, bs, bh, cs = 7, amat(A5, 7), B5_SOL, B5_HAT, C5
+        DB = dense5()
+    AA = [[sum(Am[i][j] * Am[j][l] for j in range(n)) for l in range(n)] for i in range(n)]
+    e = [F(s) - F(h) for s, h in zip(bs, bh)]
+    eA = [sum(e[j] * Am[j][l] for j in range(n)) for l in range(n)]
+    DQ = [[sum(DB[j][m] * Am[j][l] for j in range(n)) for m in range(6)] for l in range(n)]
+    return dict(A=Am, AA=AA, C=cs, B=[F(b) for b in bs], E=e, EA=eA, DB=DB, DQ=DQ)
 
 
 def fmt(v):
     return repr(float(v))
 
 
-def emit():
-    t = tables()
-    out = ["// GENERATED by galax_b200/csrc/gen_tables.py -- do not edit.",
-           "// Dopri8 = Prince-Dormand RK8(7)13M + FSAL stage, Nystrom form for (dq,dp) = (p, a(q)).",
-           "#pragma once", "namespace gx { namespace dp8 {", "constexpr int NS = 14;"]
+def emit_namespace(out, ns, order, t):
+    n = len(t["B"])
+    out.append(f"namespace {ns} {{")
+    out.append(f"constexpr int NS = {n};")
 
     # Values live in __constant__ memory (an unrolled access becomes a c[bank][imm] operand of the DFMA, no
     # extra instruction); the sparsity pattern is constexpr so zero coefficients vanish at compile time.
@@ -106,15 +138,36 @@ def emit():
         out.append(f"__constant__ double {name}[{len(v)}] = {{" + ", ".join(fmt(x) for x in v) + "};")
         out.append(f"__device__ constexpr bool {name}_NZ[{len(v)}] = {{" + ", ".join("true" if float(x) != 0.0 else "false" for x in v) + "};")
 
-    mat("A", t["A"], N)      # p-stage weights (only the last row, b_sol, is used by the kernels)
-    mat("AA", t["AA"], N)    # q_i = q0 + CN[i] h p0 + h^2 sum_l AA[i][l] a_l
+    mat("A", t["A"], n)      # p-stage weights (only the last row, b_sol, is used by the kernels)
+    mat("AA", t["AA"], n)    # q_i = q0 + CN[i] h p0 + h^2 sum_l AA[i][l] a_l
     vec("CN", t["C"])
     vec("B", t["B"])         # p1 = p0 + h sum_l B[l] a_l
     vec("E", t["E"])         # err_p = h sum_l E[l] a_l
     vec("EA", t["EA"])       # err_q = h^2 sum_l EA[l] a_l
     mat("DB", t["DB"], 6)    # p(theta) = p0 + h sum_l (sum_m DB[l][m] theta^(m+1)) a_l
     mat("DQ", t["DQ"], 6)    # q(theta) = q0 + theta h p0 + h^2 sum_l (sum_m DQ[l][m] theta^(m+1)) a_l
-    out.append("}}  // namespace gx::dp8")
+    out.append(f"}}  // namespace {ns}")
+    # compile-time view used by the solver-templated kernels
+    out.append(f"struct Tab{ns.capitalize()} {{")
+    out.append(f"    static constexpr int NS = {n};")
+    out.append(f"    static constexpr int ORDER = {order};  // diffrax error_order")
+    for name in ("AA", "DB", "DQ"):
+        out.append(f"    __device__ __forceinline__ static double {name}(int i, int j) {{ return {ns}::{name}[i][j]; }}")
+        out.append(f"    __host__ __device__ static constexpr bool {name}_NZ(int i, int j) {{ return {ns}::{name}_NZ[i][j]; }}")
+    for name in ("CN", "B", "E", "EA"):
+        out.append(f"    __device__ __forceinline__ static double {name}(int i) {{ return {ns}::{name}[i]; }}")
+        out.append(f"    __host__ __device__ static constexpr bool {name}_NZ(int i) {{ return {ns}::{name}_NZ[i]; }}")
+    out.append("};")
+
+
+def emit():
+    out = ["// GENERATED by galax_b200/csrc/gen_tables.py -- do not edit.",
+           "// Dopri8 = Prince-Dormand RK8(7)13M + FSAL stage; Dopri5 = Dormand-Prince 5(4) + FSAL stage;",
+           "// both in Nystrom form for (dq, dp) = (p, a(q)).",
+           "#pragma once", "namespace gx {"]
+    emit_namespace(out, "dp8", 8, tables("dp8"))
+    emit_namespace(out, "dp5", 5, tables("dp5"))
+    out.append("}  // namespace gx")
     Path(__file__).with_name("gx_tables.h").write_text("\n".join(out) + "\n")
 
 

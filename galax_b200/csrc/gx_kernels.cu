@@ -381,9 +381,16 @@ struct Dp8Args {
     int T;
 };
 
-__host__ __device__ constexpr bool row_nonzero(const bool *row, int n) {
-    for (int i = 0; i < n; ++i)
-        if (row[i]) return true;
+template <class TB>
+__host__ __device__ constexpr bool dq_row_nz(int l) {
+    for (int m = 0; m < 6; ++m)
+        if (TB::DQ_NZ(l, m)) return true;
+    return false;
+}
+template <class TB>
+__host__ __device__ constexpr bool db_row_nz(int l) {
+    for (int m = 0; m < 6; ++m)
+        if (TB::DB_NZ(l, m)) return true;
     return false;
 }
 
@@ -416,11 +423,11 @@ __device__ __noinline__ void accel_call(double x, double y, double z, double &ax
     ax = -g0; ay = -g1; az = -g2;
 }
 
-// Hairer-Norsett-Wanner initial step as restated by diffrax (_select_initial_step), error order 8.
+// Hairer-Norsett-Wanner initial step as restated by diffrax (_select_initial_step); inv_order = 1 / error order.
 // Works in tau = dir*t: f = dir * (p, a).
 template <class C>
 __device__ double select_initial_step(const DevPot &P, double dir, const double y[6], const double a0[3],
-                                      double rtol, double atol) {
+                                      double rtol, double atol, double inv_order) {
     double f0[6] = {y[3] * dir, y[4] * dir, y[5] * dir, a0[0] * dir, a0[1] * dir, a0[2] * dir};
     double sc[6], v[6];
 #pragma unroll
@@ -443,7 +450,7 @@ __device__ double select_initial_step(const DevPot &P, double dir, const double 
     for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
     double d2 = rms6(v[0], v[1], v[2], v[3], v[4], v[5]) / h0;
     double maxd = fmax(d1, d2);
-    double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / maxd, 1.0 / 8.0);
+    double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / maxd, inv_order);
     return fmin(100.0 * h0, h1);
 }
 
@@ -456,10 +463,11 @@ constexpr int REC_DOUBLES = GX_DENSE_RECORD_DOUBLES;  // tprev, tnext, hd, q0[3]
 // they live in the thread's local-memory frame (L1-resident, 336 B/thread) rather than in registers.  Measured
 // alternatives on B200 (MW2022, rtol = atol = 1e-10, 3e5 particles): everything inlined with the stages in
 // registers 161 ms (I-cache bound: 105 KB of SASS); stages in shared memory 151-205 ms; this version 121 ms.
-template <class C>
+// TB = TabDp8 (diffrax.Dopri8) or TabDp5 (diffrax.Dopri5): same kernel, tableau resolved at compile time.
+template <class C, class TB>
 __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
 k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
-    using namespace dp8;
+    constexpr int NS = TB::NS;
     {   // stage the potential parameters in shared memory for accel_call()
         const double *src = reinterpret_cast<const double *>(&P);
         double *dst = reinterpret_cast<double *>(pot_smem<C>());
@@ -470,7 +478,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const double NANV = __longlong_as_double(0x7ff8000000000000LL);
 
-    const bool simple_i = (a.pcoeff == 0.0 && a.dcoeff == 0.0 && a.icoeff == 1.0);
+    const bool simple_i = (TB::ORDER == 8) && (a.pcoeff == 0.0 && a.dcoeff == 0.0 && a.icoeff == 1.0);
     bool have = false, exhausted = false;
     long long idx = 0;
     double q0x = 0, q0y = 0, q0z = 0, p0x = 0, p0y = 0, p0z = 0;  // state at tprev
@@ -516,7 +524,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                 } else {
                     const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
                     const double a0[3] = {AX(0), AY(0), AZ(0)};
-                    h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol);
+                    h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol, 1.0 / TB::ORDER);
                 }
                 tprev = T0;
                 tnext = clip_to_end(T0, T0 + h, T1, true);
@@ -549,30 +557,30 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         double sx = 0, sy = 0, sz = 0;
 #pragma unroll
         for (int i = 1; i < NS; ++i) {
-            // q_i = q0 + CN[i] hd p0 + hd^2 sum_{l<i} AA[i][l] a_l
+            // q_i = q0 + CN[i] hd p0 + hd^2 sum_{l<i} TB::AA(i, l) a_l
             sx = 0; sy = 0; sz = 0;
 #pragma unroll
             for (int l = 0; l < i; ++l) {
-                if (AA_NZ[i][l]) {
-                    sx = fma(AA[i][l], AX(l), sx);
-                    sy = fma(AA[i][l], AY(l), sy);
-                    sz = fma(AA[i][l], AZ(l), sz);
+                if (TB::AA_NZ(i, l)) {
+                    sx = fma(TB::AA(i, l), AX(l), sx);
+                    sy = fma(TB::AA(i, l), AY(l), sy);
+                    sz = fma(TB::AA(i, l), AZ(l), sz);
                 }
             }
-            const double ch = CN[i] * hd;
+            const double ch = TB::CN(i) * hd;
             const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
             const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
             const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
             { double t0_, t1_, t2_; accel_call<C>(xi, yi, zi, t0_, t1_, t2_); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
-            if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: stage 14 sits at q1
+            if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1
         }
         const double q1x = sx, q1y = sy, q1z = sz;
         double bx = 0, by = 0, bz = 0, epx = 0, epy = 0, epz = 0, eqx = 0, eqy = 0, eqz = 0;
 #pragma unroll
         for (int l = 0; l < NS; ++l) {
-            if (B_NZ[l]) { bx = fma(B[l], AX(l), bx); by = fma(B[l], AY(l), by); bz = fma(B[l], AZ(l), bz); }
-            if (E_NZ[l]) { epx = fma(E[l], AX(l), epx); epy = fma(E[l], AY(l), epy); epz = fma(E[l], AZ(l), epz); }
-            if (EA_NZ[l]) { eqx = fma(EA[l], AX(l), eqx); eqy = fma(EA[l], AY(l), eqy); eqz = fma(EA[l], AZ(l), eqz); }
+            if (TB::B_NZ(l)) { bx = fma(TB::B(l), AX(l), bx); by = fma(TB::B(l), AY(l), by); bz = fma(TB::B(l), AZ(l), bz); }
+            if (TB::E_NZ(l)) { epx = fma(TB::E(l), AX(l), epx); epy = fma(TB::E(l), AY(l), epy); epz = fma(TB::E(l), AZ(l), epz); }
+            if (TB::EA_NZ(l)) { eqx = fma(TB::EA(l), AX(l), eqx); eqy = fma(TB::EA(l), AY(l), eqy); eqz = fma(TB::EA(l), AZ(l), eqz); }
         }
         const double p1x = fma(hd, bx, p0x), p1y = fma(hd, by, p0y), p1z = fma(hd, bz, p0z);
         ++ntot;
@@ -604,9 +612,9 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         } else {
             const double serr = bad ? INF : sqrt(ms);
             inv = 1.0 / serr;
-            const double c1 = (a.icoeff + a.pcoeff + a.dcoeff) * 0.125;
-            const double c2 = -(a.pcoeff + 2.0 * a.dcoeff) * 0.125;
-            const double c3 = a.dcoeff * 0.125;
+            const double c1 = (a.icoeff + a.pcoeff + a.dcoeff) * (1.0 / TB::ORDER);
+            const double c2 = -(a.pcoeff + 2.0 * a.dcoeff) * (1.0 / TB::ORDER);
+            const double c3 = a.dcoeff * (1.0 / TB::ORDER);
             factor = a.safety;
             if (c1 != 0.0) factor *= pow(inv, c1);
             if (c2 != 0.0) factor *= pow(prev_inv, c2);
@@ -639,17 +647,17 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
 #pragma unroll
                     for (int l = 0; l < NS; ++l) {
-                        if (row_nonzero(DQ_NZ[l], 6)) {
-                            double w = DQ[l][5];
+                        if (dq_row_nz<TB>(l)) {
+                            double w = TB::DQ(l, 5);
 #pragma unroll
-                            for (int m = 4; m >= 0; --m) w = fma(w, th, DQ[l][m]);
+                            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DQ(l, m));
                             w *= th;
                             wqx = fma(w, AX(l), wqx); wqy = fma(w, AY(l), wqy); wqz = fma(w, AZ(l), wqz);
                         }
-                        if (row_nonzero(DB_NZ[l], 6)) {
-                            double w = DB[l][5];
+                        if (db_row_nz<TB>(l)) {
+                            double w = TB::DB(l, 5);
 #pragma unroll
-                            for (int m = 4; m >= 0; --m) w = fma(w, th, DB[l][m]);
+                            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DB(l, m));
                             w *= th;
                             wpx = fma(w, AX(l), wpx); wpy = fma(w, AY(l), wpy); wpz = fma(w, AZ(l), wpz);
                         }
@@ -684,10 +692,11 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
 // Dense output in parallel: one thread per save time, binary search over the recorded accepted steps, then the
 // same degree-6 continuous extension as the in-kernel SaveAt path.  Used for single orbits with many saves (the
 // progenitor orbit of a mock stream: 5e5 saves on ~10^3 steps), where a serial in-kernel evaluation would dominate.
+template <class TB>
 __global__ void __launch_bounds__(256) k_dense_eval(const double *__restrict__ rec, const int *__restrict__ n_rec_p,
                                                     double t0, double t1, const double *__restrict__ ts, long long M,
                                                     double *__restrict__ q, double *__restrict__ p) {
-    using namespace dp8;
+    constexpr int NS = TB::NS;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     const int n_rec = *n_rec_p;
@@ -721,17 +730,17 @@ __global__ void __launch_bounds__(256) k_dense_eval(const double *__restrict__ r
 #pragma unroll
     for (int l = 0; l < NS; ++l) {
         const double ax = r[9 + 3 * l], ay = r[10 + 3 * l], az = r[11 + 3 * l];
-        if (row_nonzero(DQ_NZ[l], 6)) {
-            double w = DQ[l][5];
+        if (dq_row_nz<TB>(l)) {
+            double w = TB::DQ(l, 5);
 #pragma unroll
-            for (int m = 4; m >= 0; --m) w = fma(w, th, DQ[l][m]);
+            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DQ(l, m));
             w *= th;
             wqx = fma(w, ax, wqx); wqy = fma(w, ay, wqy); wqz = fma(w, az, wqz);
         }
-        if (row_nonzero(DB_NZ[l], 6)) {
-            double w = DB[l][5];
+        if (db_row_nz<TB>(l)) {
+            double w = TB::DB(l, 5);
 #pragma unroll
-            for (int m = 4; m >= 0; --m) w = fma(w, th, DB[l][m]);
+            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DB(l, m));
             w *= th;
             wpx = fma(w, ax, wpx); wpy = fma(w, ay, wpy); wpz = fma(w, az, wpz);
         }
@@ -993,7 +1002,7 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
 
 // gx_integrate_dopri8_record() passes its record buffer to the launch code through a thread-local (the two entry
 // points share everything else); it is reset before returning, so plain gx_integrate_dopri8 calls never see it.
-struct RecTls { double *rec = nullptr; int *n_rec = nullptr; int cap = 0; };
+struct RecTls { double *rec = nullptr; int *n_rec = nullptr; int cap = 0; int solver = GX_SOLVER_DOPRI8; };
 static thread_local RecTls g_rec_tls;
 
 int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,
@@ -1032,7 +1041,8 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define GX_LAUNCH_DP8(C_)                                                                                     \
     do {                                                                                                      \
-        auto kern = k_integrate_dopri8<C_>;                                                                   \
+        auto kern = (g_rec_tls.solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5>                   \
+                                                           : k_integrate_dopri8<C_, TabDp8>;                  \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);                               \
         if (per_sm < 1) per_sm = 1;                                                                           \
         long long want = (N + block - 1) / block, resident = (long long)per_sm * sms;                         \
@@ -1044,26 +1054,57 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     return cuda_rc(cudaGetLastError());
 }
 
-int gx_integrate_dopri8_record(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0,
-                               double t0, double t1, int64_t max_steps, double *rec, int32_t rec_capacity,
-                               int32_t *n_rec, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
-                               void *workspace, void *stream) {
+int gx_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                          const double *p0, int64_t N, const double *t0, double t0_scalar, double t1, const double *ts,
+                          int32_t T, int64_t max_steps, const int32_t *order, int32_t layout, double *q, double *p,
+                          int32_t *status, int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
+    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
+    const int saved = g_rec_tls.solver;
+    g_rec_tls.solver = solver;
+    int rc = gx_integrate_dopri8(pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, order, layout, q, p, status,
+                                 n_accepted, n_attempted, workspace, stream);
+    g_rec_tls.solver = saved;
+    return rc;
+}
+
+int gx_integrate_adaptive_record(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                 const double *p0, double t0, double t1, int64_t max_steps, double *rec,
+                                 int32_t rec_capacity, int32_t *n_rec, int32_t *status, int32_t *n_accepted,
+                                 int32_t *n_attempted, void *workspace, void *stream) {
+    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     if (!rec || !n_rec || rec_capacity <= 0) return GX_ERR_BADARG;
     cudaError_t e = cudaMemsetAsync(n_rec, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return GX_ERR_CUDA;
-    g_rec_tls.rec = rec; g_rec_tls.n_rec = n_rec; g_rec_tls.cap = rec_capacity;
+    g_rec_tls.rec = rec; g_rec_tls.n_rec = n_rec; g_rec_tls.cap = rec_capacity; g_rec_tls.solver = solver;
     int rc = gx_integrate_dopri8(pot, pid, q0, p0, 1, nullptr, t0, t1, nullptr, 0, max_steps, nullptr, GX_LAYOUT_NT3,
                                  nullptr, nullptr, status, n_accepted, n_attempted, workspace, stream);
     g_rec_tls = RecTls();
     return rc;
 }
 
-int gx_dense_eval(const double *rec, const int32_t *n_rec, double t0, double t1, const double *ts, int64_t M,
-                  double *q, double *p, void *stream) {
+int gx_integrate_dopri8_record(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0,
+                               double t0, double t1, int64_t max_steps, double *rec, int32_t rec_capacity,
+                               int32_t *n_rec, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
+                               void *workspace, void *stream) {
+    return gx_integrate_adaptive_record(GX_SOLVER_DOPRI8, pot, pid, q0, p0, t0, t1, max_steps, rec, rec_capacity, n_rec,
+                                        status, n_accepted, n_attempted, workspace, stream);
+}
+
+int gx_dense_eval_solver(int32_t solver, const double *rec, const int32_t *n_rec, double t0, double t1,
+                         const double *ts, int64_t M, double *q, double *p, void *stream) {
+    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     if (M < 0 || (M > 0 && (!rec || !n_rec || !ts || !q || !p))) return GX_ERR_BADARG;
     if (M == 0) return 0;
-    k_dense_eval<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(rec, n_rec, t0, t1, ts, (long long)M, q, p);
+    if (solver == GX_SOLVER_DOPRI5)
+        k_dense_eval<TabDp5><<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(rec, n_rec, t0, t1, ts, (long long)M, q, p);
+    else
+        k_dense_eval<TabDp8><<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(rec, n_rec, t0, t1, ts, (long long)M, q, p);
     return cuda_rc(cudaGetLastError());
+}
+
+int gx_dense_eval(const double *rec, const int32_t *n_rec, double t0, double t1, const double *ts, int64_t M,
+                  double *q, double *p, void *stream) {
+    return gx_dense_eval_solver(GX_SOLVER_DOPRI8, rec, n_rec, t0, t1, ts, M, q, p, stream);
 }
 
 int gx_stream_release(const gx_potential *pot, int32_t df, const double *prog_q, const double *prog_p,

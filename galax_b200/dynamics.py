@@ -57,6 +57,13 @@ class Dopri8:
 
 
 @dataclasses.dataclass(frozen=True)
+class Dopri5:
+    """diffrax.Dopri5 (Dormand-Prince 5(4) + FSAL): default of the reference's experimental StreamSimulator."""
+
+    scan_kind: str | None = None
+
+
+@dataclasses.dataclass(frozen=True)
 class ConstantStepSize:
     """diffrax.ConstantStepSize: needs ``dt0``."""
 
@@ -273,9 +280,10 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
                                       dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
                                       status.data_ptr(), stream)  # fmt: skip
             _lib.check(rc, "gx_integrate_fixed")
-        elif isinstance(solver, Dopri8):
+        elif isinstance(solver, (Dopri8, Dopri5)):
             if not isinstance(controller, PIDController):
-                raise NotImplementedError("Dopri8 requires a PIDController")
+                raise NotImplementedError("Dopri8 / Dopri5 require a PIDController")
+            code = _lib.SOLVER_DOPRI8 if isinstance(solver, Dopri8) else _lib.SOLVER_DOPRI5
             pid = controller.c_struct(dt0)
             nacc = torch.empty((N,), dtype=torch.int32, device=dev)
             ntot = torch.empty((N,), dtype=torch.int32, device=dev)
@@ -287,25 +295,25 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
                 cap = int(min(ms, 1 << 16)) if ms > 0 else (1 << 16)
                 rec = torch.empty((cap, _lib.DENSE_RECORD_DOUBLES), dtype=torch.float64, device=dev)
                 n_rec = torch.zeros((1,), dtype=torch.int32, device=dev)
-                rc = L.gx_integrate_dopri8_record(C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), t0s, t1, ms,
-                                                  rec.data_ptr(), cap, n_rec.data_ptr(), status.data_ptr(),
-                                                  nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(), stream)  # fmt: skip
-                _lib.check(rc, "gx_integrate_dopri8_record")
-                rc = L.gx_dense_eval(rec.data_ptr(), n_rec.data_ptr(), t0s, t1, dts.data_ptr(), T, q.data_ptr(),
-                                     p.data_ptr(), stream)  # fmt: skip
-                _lib.check(rc, "gx_dense_eval")
+                rc = L.gx_integrate_adaptive_record(code, C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), t0s,
+                                                    t1, ms, rec.data_ptr(), cap, n_rec.data_ptr(), status.data_ptr(),
+                                                    nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(), stream)  # fmt: skip
+                _lib.check(rc, "gx_integrate_adaptive_record")
+                rc = L.gx_dense_eval_solver(code, rec.data_ptr(), n_rec.data_ptr(), t0s, t1, dts.data_ptr(), T,
+                                            q.data_ptr(), p.data_ptr(), stream)  # fmt: skip
+                _lib.check(rc, "gx_dense_eval_solver")
             else:
-              rc = L.gx_integrate_dopri8(C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
+              rc = L.gx_integrate_adaptive(code, C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
                                        None if t0_arr is None else t0_arr.data_ptr(), t0s, t1, dts.data_ptr(), T, ms,
                                        None if order is None else order.data_ptr(), lay, q.data_ptr(), p.data_ptr(),
                                        status.data_ptr(), nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(),
                                        stream)  # fmt: skip
-              _lib.check(rc, "gx_integrate_dopri8")
+              _lib.check(rc, "gx_integrate_adaptive")
             stats["num_accepted_steps"] = nacc.reshape(batch)
             stats["num_steps"] = ntot.reshape(batch)
         else:
             raise NotImplementedError(
-                f"solver {type(solver).__name__} is not supported (SemiImplicitEuler, LeapfrogMidpoint, Dopri8)"
+                f"solver {type(solver).__name__} is not supported (SemiImplicitEuler, LeapfrogMidpoint, Dopri8, Dopri5)"
             )
     if throw:
         bad = torch.nonzero(status != _lib.OK)
@@ -597,7 +605,7 @@ class MockStreamGenerator:
 
 
 __all__ = [
-    "SemiImplicitEuler", "LeapfrogMidpoint", "Dopri8", "ConstantStepSize", "PIDController",
+    "SemiImplicitEuler", "LeapfrogMidpoint", "Dopri8", "Dopri5", "ConstantStepSize", "PIDController",
     "PhaseSpacePosition", "PhaseSpaceCoordinate", "Orbit", "Solution", "HamiltonianField",
     "OrbitSolver", "Integrator", "default_integrator", "evaluate_orbit", "compute_orbit",
     "MockStreamArm", "MockStream", "AbstractStreamDF", "FardalStreamDF", "ChenStreamDF", "MockStreamGenerator",

@@ -134,6 +134,22 @@ int gx_integrate_dopri8_record(const gx_potential *pot, const gx_pid *pid, const
 int gx_dense_eval(const double *rec, const int32_t *n_rec, double t0, double t1, const double *ts, int64_t M,
                   double *q, double *p, void *stream);
 
+/* The same three entries with the explicit Runge-Kutta pair selectable: GX_SOLVER_DOPRI8 = diffrax.Dopri8 (galax's
+ * default everywhere except) GX_SOLVER_DOPRI5 = diffrax.Dopri5, the default of the experimental StreamSimulator
+ * (dynamics/_src/experimental/stream.py:32-41).  gx_integrate_dopri8* are these with solver = GX_SOLVER_DOPRI8. */
+#define GX_SOLVER_DOPRI8 8
+#define GX_SOLVER_DOPRI5 5
+int gx_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                          const double *p0, int64_t N, const double *t0, double t0_scalar, double t1, const double *ts,
+                          int32_t T, int64_t max_steps, const int32_t *order, int32_t layout, double *q, double *p,
+                          int32_t *status, int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream);
+int gx_integrate_adaptive_record(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                 const double *p0, double t0, double t1, int64_t max_steps, double *rec,
+                                 int32_t rec_capacity, int32_t *n_rec, int32_t *status, int32_t *n_accepted,
+                                 int32_t *n_attempted, void *workspace, void *stream);
+int gx_dense_eval_solver(int32_t solver, const double *rec, const int32_t *n_rec, double t0, double t1,
+                         const double *ts, int64_t M, double *q, double *p, void *stream);
+
 /* Stream release (distribution function).  Replaces FardalStreamDF._sample / ChenStreamDF._sample given the random
  * draws (dynamics/_src/legacy/mockstream/df/fardal15.py:49-94, df/chen24.py:61-137; tidal radius
  * dynamics/_src/cluster/radius.py:198-215; omega dynamics/_src/register_api.py:77-88).

@@ -28,6 +28,8 @@ class _Potential(C.Structure):
 
 class _Tableau(C.Structure):
     _fields_ = [
+        ("ns", C.c_int),
+        ("order", C.c_double),
         ("a", (C.c_double * 14) * 14),
         ("b_sol", C.c_double * 14),
         ("b_err", C.c_double * 14),
@@ -94,18 +96,22 @@ def c_potential(pot: op.Potential) -> _Potential:
     return P
 
 
-def c_tableau() -> _Tableau:
+def c_tableau(solver: str = "dopri8") -> _Tableau:
+    from . import dopri5_tableau as tab5
+
+    mod, ns, order = (tabmod, 14, 8.0) if solver == "dopri8" else (tab5, 7, 5.0)
     t = _Tableau()
-    A = tabmod.a_matrix()
-    for i in range(14):
-        for j in range(14):
+    t.ns, t.order = ns, order
+    A = mod.a_matrix()
+    for i in range(ns):
+        for j in range(ns):
             t.a[i][j] = A[i, j]
-    for name, vec in (("b_sol", tabmod.b_sol()), ("b_err", tabmod.b_err()), ("c", tabmod.c_vec())):
+    for name, vec in (("b_sol", mod.b_sol()), ("b_err", mod.b_err()), ("c", mod.c_vec())):
         arr = getattr(t, name)
-        for i in range(14):
+        for i in range(ns):
             arr[i] = vec[i]
-    Bd = tabmod.dense_b()
-    for i in range(14):
+    Bd = mod.dense_b()
+    for i in range(ns):
         for m in range(6):
             t.dense[i][m] = Bd[i, m]
     return t
@@ -175,8 +181,9 @@ def make_pid(rtol, atol, *, pcoeff=0.0, icoeff=1.0, dcoeff=0.0, safety=0.9, fact
     return pid
 
 
-def integrate_dopri8(pot, q0, p0, t0, t1, ts, *, rtol=1e-8, atol=1e-8, max_steps=-1, **pid_kw):
-    """Per-particle Dopri8 + PID.  ``t0`` scalar or array[N].  Returns q, p, status, n_accepted, n_attempted."""
+def integrate_dopri8(pot, q0, p0, t0, t1, ts, *, rtol=1e-8, atol=1e-8, max_steps=-1, solver="dopri8", **pid_kw):
+    """Per-particle Dopri8 (or ``solver="dopri5"``) + PID.  ``t0`` scalar or array[N].
+    Returns q, p, status, n_accepted, n_attempted."""
     q0, p0, ts = _f64(q0).reshape(-1, 3), _f64(p0).reshape(-1, 3), _f64(ts).reshape(-1)
     N, T = q0.shape[0], ts.shape[0]
     t0a = _f64(t0).reshape(-1)
@@ -188,7 +195,7 @@ def integrate_dopri8(pot, q0, p0, t0, t1, ts, *, rtol=1e-8, atol=1e-8, max_steps
     status = np.zeros(N, dtype=np.int32)
     nacc = np.zeros(N, dtype=np.int32)
     ntot = np.zeros(N, dtype=np.int32)
-    P, tab, pid = c_potential(pot), c_tableau(), make_pid(rtol, atol, **pid_kw)
+    P, tab, pid = c_potential(pot), c_tableau(solver), make_pid(rtol, atol, **pid_kw)
     lib().oc_integrate_dopri8(
         C.byref(P), C.byref(tab), C.byref(pid), C.c_int64(N), _dp(q0), _dp(p0), _dp(t0a), C.c_int(stride),
         C.c_double(t1), C.c_int(T), _dp(ts), C.c_int64(-1 if max_steps is None else max_steps),

@@ -366,7 +366,10 @@ int oc_integrate_fixed(const oc_potential *P, int64_t N, const double *q0, const
 
 /* ---------------------------------------------------------------- Dopri8 + PID, per particle */
 
+/* explicit FSAL Runge-Kutta pair: Dopri8 (ns = 14, order 8) or Dopri5 (ns = 7, order 5); the last stage sits at y1 */
 typedef struct {
+    int ns;
+    double order; /* diffrax error_order: exponent 1/order in the step-size rule and the initial-step heuristic */
     double a[14][14];
     double b_sol[14];
     double b_err[14];
@@ -421,7 +424,8 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
                         const double *q0, const double *p0, const double *t0v, int t0_stride, double t1,
                         int T, const double *ts, int64_t max_steps, double *q_out, double *p_out,
                         int32_t *status, int32_t *n_acc, int32_t *n_tot) {
-    const double order = 8.0;
+    const double order = tab->order;
+    const int ns = tab->ns;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t i = 0; i < N; ++i) {
         double t0 = t0v[(int64_t)t0_stride * i];
@@ -450,7 +454,7 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
             double h = tnext - tprev;
             for (int c = 0; c < 6; ++c) K[0][c] = f0[c] * h;
             double ys[6];
-            for (int s = 1; s < 14; ++s) {
+            for (int s = 1; s < ns; ++s) {
                 for (int c = 0; c < 6; ++c) {
                     double inc = 0.0;
                     for (int j = 0; j < s; ++j) inc += tab->a[s][j] * K[j][c];
@@ -459,12 +463,12 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
                 field_dir(P, dir, ys, flast);
                 for (int c = 0; c < 6; ++c) K[s][c] = flast[c] * h;
             }
-            /* a[13][:] == b_sol, so ys is y1 and K[13] = f(y1) h (FSAL) */
+            /* a[ns-1][:] == b_sol, so ys is y1 and K[ns-1] = f(y1) h (FSAL) */
             double y1[6], err[6], sc[6];
             for (int c = 0; c < 6; ++c) {
                 y1[c] = ys[c];
                 double e = 0.0;
-                for (int j = 0; j < 14; ++j) e += tab->b_err[j] * K[j][c];
+                for (int j = 0; j < ns; ++j) e += tab->b_err[j] * K[j][c];
                 err[c] = e;
             }
             ++ntot;
@@ -501,14 +505,14 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
                 while (k < T && ts[k] * dir <= tnext) {
                     double th = (ts[k] * dir - tprev) / (tnext - tprev);
                     double bw[14];
-                    for (int j = 0; j < 14; ++j) {
+                    for (int j = 0; j < ns; ++j) {
                         double pv = tab->dense[j][5];
                         for (int m = 4; m >= 0; --m) pv = pv * th + tab->dense[j][m];
                         bw[j] = pv * th;
                     }
                     for (int c = 0; c < 6; ++c) {
                         double inc = 0.0;
-                        for (int j = 0; j < 14; ++j) inc += bw[j] * K[j][c];
+                        for (int j = 0; j < ns; ++j) inc += bw[j] * K[j][c];
                         double v = y[c] + inc;
                         if (c < 3) qo[3 * k + c] = v; else po[3 * k + c - 3] = v;
                     }

@@ -1,0 +1,107 @@
+"""GPU: the ``galax.dynamics.experimental`` mirror (integrate_orbit, Fardal2015DF, StreamSimulator) and Dopri5."""
+import numpy as np
+import pytest
+
+import galax_b200.dynamics as gd
+import galax_b200.experimental as ge
+import galax_b200.potential as gp
+from oracle import cref
+from oracle import potentials as op
+
+from conftest import synthetic_ics
+
+pytestmark = pytest.mark.gpu
+KMS = gp.KMS
+
+
+def test_dopri5_matches_oracle_and_truth():
+    pot, opot = gp.MilkyWayPotential(), op.milky_way_potential()
+    q0, p0 = synthetic_ics(opot, 128, seed=31)
+    ts = np.linspace(0.0, 300.0, 13)
+    kw = dict(solver=gd.Dopri5(), controller=gd.PIDController(1e-8, 1e-8), dt0=None, max_steps=None)
+    q, p, st, stats = gd._integrate(pot, q0, p0, 0.0, 300.0, ts, **kw)
+    qr, pr, sr, na, nt = cref.integrate_dopri8(opot, q0, p0, 0.0, 300.0, ts, rtol=1e-8, atol=1e-8, solver="dopri5")
+    qt, *_ = cref.integrate_dopri8(opot, q0, p0, 0.0, 300.0, ts, rtol=1e-13, atol=1e-13)
+    d = (np.abs(q - qr) / (1e-8 + 1e-8 * np.abs(qr))).max(axis=(1, 2))
+    assert np.median(d) <= 10.0 and np.mean(d <= 10.0) >= 0.6
+    eg, eo = np.abs(q - qt).max(axis=(1, 2)), np.abs(qr - qt).max(axis=(1, 2))
+    assert 0.5 <= np.median(eg) / np.median(eo) <= 2.0
+    assert abs(int(stats["num_steps"].sum()) / int(nt.sum()) - 1) < 0.02
+    # Dopri5 needs several times more steps than Dopri8 at the same tolerance
+    _, _, _, s8 = gd._integrate(pot, q0, p0, 0.0, 300.0, ts, solver=gd.Dopri8(), controller=gd.PIDController(1e-8, 1e-8),
+                                dt0=None, max_steps=None)
+    assert int(stats["num_steps"].sum()) > 1.5 * int(s8["num_steps"].sum())
+
+
+def test_dopri5_short_horizon_step_end_parity_and_single_orbit_record_path():
+    pot, opot = gp.MilkyWayPotential2022(), op.milky_way_potential_2022()
+    q0, p0 = synthetic_ics(opot, 64, seed=32)
+    kw = dict(solver=gd.Dopri5(), controller=gd.PIDController(1e-9, 1e-9), dt0=0.5, max_steps=None)
+    q, p, st, stats = gd._integrate(pot, q0, p0, 0.0, 20.0, [20.0], **kw)
+    qr, pr, sr, na, nt = cref.integrate_dopri8(opot, q0, p0, 0.0, 20.0, [20.0], rtol=1e-9, atol=1e-9, dt0=0.5, solver="dopri5")
+    assert np.mean(stats["num_steps"].cpu().numpy() == nt) > 0.8
+    assert np.median(np.abs(q - qr).max(axis=(1, 2))) < 1e-10
+    ts = np.linspace(0.0, 500.0, 200)
+    a = gd._integrate(pot, q0[:1], p0[:1], 0.0, 500.0, ts, solver=gd.Dopri5(), controller=gd.PIDController(1e-8, 1e-8),
+                      dt0=None, max_steps=None)
+    b = gd._integrate(pot, q0[:2], p0[:2], 0.0, 500.0, ts, solver=gd.Dopri5(), controller=gd.PIDController(1e-8, 1e-8),
+                      dt0=None, max_steps=None)
+    assert np.allclose(a[0][0], b[0][0], rtol=1e-13, atol=1e-13)
+
+
+def test_integrate_orbit_reference_benchmark_shapes():
+    """tests/benchmark/test_experimental.py:80-96: Hernquist, one orbit, 1000 saves over 100 Myr; scalar / batched."""
+    pot = gp.HernquistPotential(1e12, 10.0)
+    opot = op.single(op.KIND_HERNQUIST, 1e12, 10.0)
+    qp0 = (np.array([15.0, 0.0, 0.0]), np.array([0.0, 0.225, 0.0]))
+    saveat = np.linspace(0.0, 100.0, 1000)
+    sol = ge.integrate_orbit(pot, qp0, saveat=saveat)
+    assert sol.ys[0].shape == (1000, 3) and sol.t0 == 0.0 and sol.t1 == 100.0
+    qr, pr, *_ = cref.integrate_dopri8(opot, [qp0[0]], [qp0[1]], 0.0, 100.0, saveat, rtol=1e-7, atol=1e-7, dtmin=0.3,
+                                       max_steps=10_000)
+    assert np.abs(sol.ys[0] - qr[0]).max() < 1e-5
+    end = ge.integrate_orbit(ge.VMap, pot, qp0, 0.0, 100.0)
+    assert end.ys[0].shape == (3,) and np.abs(end.ys[0] - qr[0, -1]).max() < 1e-5
+    one = ge.integrate_orbit(pot, qp0, 0.0, saveat=50.0)
+    assert one.ys[0].shape == (3,)
+    B = 64
+    q0 = np.repeat(qp0[0][None], B, 0) * np.linspace(0.8, 1.2, B)[:, None]
+    p0 = np.repeat(qp0[1][None], B, 0)
+    for strat in (ge.Scan, ge.VMap, ge.NoLoop):
+        sb = ge.integrate_orbit(strat, pot, (q0, p0), 0.0, 100.0, saveat=saveat)
+        assert sb.ys[0].shape == (B, 1000, 3)
+    t0s = np.linspace(-50.0, 0.0, B)
+    sb = ge.integrate_orbit(ge.VMap, pot, (q0, p0), t0s, 100.0)
+    assert sb.ys[0].shape == (B, 3) and np.isfinite(sb.ys[0]).all()
+    with pytest.raises(ValueError):
+        ge.integrate_orbit(pot, qp0, None, 1.0)
+
+
+def test_fardal2015df_parameters_and_stream_simulator():
+    """experimental/stream.py doctest setup: Hernquist(1e12, 10), 2000 release times over [-4000, -150] Myr."""
+    pot = gp.HernquistPotential(1e12, 10.0)
+    opot = op.single(op.KIND_HERNQUIST, 1e12, 10.0)
+    rng = np.random.default_rng(0)
+    x = np.array([15.0, 0.0, 0.0])
+    v = np.array([0.0, 220.0 * KMS, 0.0])
+    n = rng.standard_normal((4, 1))
+    xl, vl, xt, vt = ge.Fardal2015DF().sample(n, pot, 0.0, x, v, 1e5)
+    ref = cref.release_fardal(opot, x[None], v[None], 1e5, n)
+    assert xl.shape == (3,) and np.allclose(xl, ref[0][0], rtol=1e-13) and np.allclose(vt, ref[3][0], rtol=1e-12)
+    df = ge.Fardal2015DF(kr_bar=1.5, sigma_kr=0.25, kvphi_bar=0.4, sigma_kz=0.1)
+    xl2, _, xt2, _ = df.sample(n, pot, 0.0, x, v, 1e5)
+    # radial offset scales with k_r = 1.5 + 0.25 n instead of 2 + 0.5 n
+    rt = np.linalg.norm(ref[2][0] - x) / np.hypot(2 + 0.5 * n[0, 0], 0.5 * n[2, 0])
+    assert np.isclose(np.linalg.norm(xt2 - x), rt * np.hypot(1.5 + 0.25 * n[0, 0], 0.1 * n[2, 0]), rtol=1e-10)
+
+    M = 2000
+    release = np.linspace(-4000.0, -150.0, M)
+    sim = ge.StreamSimulator()
+    ics = sim.init(pot, (x, np.array([0.0, 0.225, 0.0])), 0.0, release_times=release, Msat=1e5, key=0)
+    assert ics.qp_lead[0].shape == (M, 3) and np.isfinite(ics.qp_trail[1]).all() and ics.prog_mass.shape == (M,)
+    lead, trail = sim.run(pot, ics, t1=0.0)
+    assert lead[0].shape == (M, 3) and trail[1].shape == (M, 3) and np.isfinite(lead[0]).all()
+    # oracle: same ICs through the Dopri5 oracle with dtmin = 0.3
+    qr, pr, st, na, nt = cref.integrate_dopri8(opot, ics.qp_lead[0][:200], ics.qp_lead[1][:200], release[:200], 0.0, [0.0],
+                                               rtol=1e-7, atol=1e-7, dtmin=0.3, max_steps=10_000, solver="dopri5")
+    assert np.median(np.abs(lead[0][:200] - qr[:, 0]).max(axis=1)) < 1e-3

@@ -184,3 +184,26 @@ def test_mockstream_shapes_and_finiteness_like_reference():
     for k in ("lead_q", "lead_p", "trail_q", "trail_p"):
         assert out[k].shape == (10, 3) and np.isfinite(out[k]).all()
     assert out["prog_q"].shape == (10, 3)
+
+
+def test_dopri5_tableau_and_oracle():
+    """Dormand-Prince 5(4): order conditions, Shampine mid-point, and the oracle against a DOP853 truth."""
+    from oracle import dopri5_tableau as t5
+
+    r = t5.verify()
+    assert r["order5_sol"] < 5e-15 and r["order4_hat"] < 5e-15
+    pot = op.milky_way_potential()
+    q0, p0 = synthetic_ics(pot, 4, seed=9)
+    ts = np.linspace(0, 300, 7)
+    for tol, bound in ((1e-7, 2e-3), (1e-10, 2e-6)):
+        q, p, st, na, nt = cref.integrate_dopri8(pot, q0, p0, 0.0, 300.0, ts, rtol=tol, atol=tol, solver="dopri5")
+        assert (st == 0).all()
+        for i in range(4):
+            def f(t, y):
+                return np.concatenate([y[3:], -op.gradient(pot, y[:3])])
+            s = solve_ivp(f, (0, 300), np.concatenate([q0[i], p0[i]]), method="DOP853", rtol=1e-13, atol=1e-13, t_eval=ts)
+            assert np.abs(q[i] - s.y[:3].T).max() < bound
+    # dtmin with force_dtmin (the experimental API's controller): never steps below dtmin, always finishes
+    q, p, st, na, nt = cref.integrate_dopri8(pot, q0, p0, 0.0, 300.0, [300.0], rtol=1e-12, atol=1e-12, dtmin=0.3,
+                                             solver="dopri5")
+    assert (st == 0).all() and (nt <= 1001).all()

@@ -35,3 +35,17 @@ def test_header_is_current():
     t = g.tables()
     for v in (t["AA"][13][0], t["EA"][5], t["DQ"][0][2]):
         assert repr(float(v)) in hdr
+
+
+def test_dopri5_tables_match_oracle_tableau():
+    import gen_tables as g
+
+    from oracle import dopri5_tableau as t5
+
+    t = g.tables("dp5")
+    A = np.array([[float(v) for v in row] for row in t["A"]])
+    assert np.array_equal(A, t5.a_matrix())
+    assert np.array_equal(np.array([float(v) for v in t["B"]]), t5.b_sol())
+    assert np.array_equal(np.array([float(v) for v in t["E"]]), t5.b_err())
+    assert np.array_equal(np.array([[float(v) for v in r] for r in t["DB"]]), t5.dense_b())
+    assert np.allclose(np.array([[float(v) for v in r] for r in t["AA"]]), A @ A, rtol=1e-13, atol=1e-15)

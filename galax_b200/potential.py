@@ -241,6 +241,30 @@ class KeplerPotential(AbstractPotential):
 
 
 @dataclasses.dataclass(frozen=True)
+class PlummerPotential(AbstractPotential):
+    """builtin/plummer.py: Phi = -G m / sqrt(r^2 + r_s^2)  (a Miyamoto-Nagai model with a = 0)."""
+
+    m_tot: float
+    r_s: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_MN, (_const("m_tot", self.m_tot), 0.0, _const("r_s", self.r_s)))]
+
+
+@dataclasses.dataclass(frozen=True)
+class KuzminPotential(AbstractPotential):
+    """builtin/kuzmin.py: Phi = -G m / sqrt(R^2 + (r_s + |z|)^2)  (a Miyamoto-Nagai model with b = 0)."""
+
+    m_tot: float
+    r_s: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_MN, (_const("m_tot", self.m_tot), _const("r_s", self.r_s), 0.0))]
+
+
+@dataclasses.dataclass(frozen=True)
 class NFWPotential(AbstractPotential):
     """builtin/nfw/base.py: Phi = -(G m / r_s) log(1 + r/r_s) / (r/r_s)."""
 
@@ -420,7 +444,8 @@ class BovyMWPotential2014(MilkyWayPotential):
 
 
 __all__ = [
-    "AbstractPotential", "MiyamotoNagaiPotential", "HernquistPotential", "KeplerPotential", "NFWPotential",
+    "AbstractPotential", "MiyamotoNagaiPotential", "HernquistPotential", "KeplerPotential", "PlummerPotential",
+    "KuzminPotential", "NFWPotential",
     "PowerLawCutoffPotential", "MN3ExponentialPotential", "MN3Sech2Potential", "CompositePotential",
     "MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014", "G_GALACTIC", "KMS",
 ]  # fmt: skip

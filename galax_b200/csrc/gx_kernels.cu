@@ -946,8 +946,22 @@ int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int6
     long long want = (N + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
     if (what & GX_HESS) {
-        int grid = (int)(want < 148LL * 5 ? want : 148LL * 5);  // persistent: 5 CTAs (43 KB smem each) per SM
-        GX_DISPATCH_MODEL(model, (k_potential_eval<C><<<grid, block, 0, s>>>(D, a)));
+        // persistent CTAs: exactly the resident set (43 KB static shared memory each; ask for the full carveout)
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define GX_LAUNCH_EVAL(C_)                                                                                    \
+    do {                                                                                                      \
+        auto kern = k_potential_eval<C_>;                                                                     \
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);                      \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);                               \
+        if (per_sm < 1) per_sm = 1;                                                                           \
+        long long resident = (long long)per_sm * sms;                                                         \
+        int grid = (int)(want < resident ? want : resident);                                                  \
+        kern<<<grid, block, 0, s>>>(D, a);                                                                    \
+    } while (0)
+        GX_DISPATCH_MODEL(model, GX_LAUNCH_EVAL(C));
+#undef GX_LAUNCH_EVAL
     } else {
         int grid = (int)(want < 148LL * 32 ? want : 148LL * 32);
         GX_DISPATCH_MODEL(model, (k_potential_eval_direct<C><<<grid, block, 0, s>>>(D, a)));

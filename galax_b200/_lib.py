@@ -26,6 +26,7 @@ NVCC_FLAGS = [
 
 GX_MAX_COMPONENTS = 14
 KIND_MN, KIND_HERNQUIST, KIND_NFW, KIND_PLC = 0, 1, 2, 3
+KIND_LOG, KIND_ISOCHRONE, KIND_SATOH = 4, 5, 6
 PHI, GRAD, ACC, HESS = 1, 2, 4, 8
 OK, MAX_STEPS_REACHED, NONFINITE = 0, 1, 2
 SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1
@@ -36,7 +37,7 @@ SOLVER_DOPRI8, SOLVER_DOPRI5 = 8, 5
 
 
 class GxComponent(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 4)]
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 8)]
 
 
 class GxPotential(C.Structure):

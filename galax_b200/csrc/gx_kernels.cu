@@ -88,14 +88,47 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool u
             p.tail = tgamma(p.ga2.a) / (rc * tgamma(p.ga.a));
             break;
         }
+        case GX_KIND_LOGARITHMIC: {
+            if (D.n_log >= MAX_LOG) return GX_ERR_UNSUPPORTED;
+            const double vc = c.p[0], rs = c.p[1], q1 = c.p[2], q2 = c.p[3], q3 = c.p[4], phi = c.p[5];
+            if (!(q1 > 0.0 && q2 > 0.0 && q3 > 0.0)) return GX_ERR_BADARG;
+            const double sp = sin(phi), cp = cos(phi);
+            DevLog &l = D.lg[D.n_log++];
+            l.vc2 = vc * vc;
+            l.rs2 = rs * rs;
+            l.c11 = cp * cp / (q1 * q1) + sp * sp / (q2 * q2);
+            l.c22 = sp * sp / (q1 * q1) + cp * cp / (q2 * q2);
+            l.c12 = cp * sp * (1.0 / (q1 * q1) - 1.0 / (q2 * q2));
+            l.c33 = 1.0 / (q3 * q3);
+            break;
+        }
+        case GX_KIND_ISOCHRONE: {
+            if (D.n_iso >= MAX_ISO) return GX_ERR_UNSUPPORTED;
+            DevIso &s = D.iso[D.n_iso++];
+            s.GM = G * c.p[0];
+            s.b = c.p[1];
+            s.b2 = c.p[1] * c.p[1];
+            break;
+        }
+        case GX_KIND_SATOH: {
+            if (D.n_satoh >= MAX_SATOH) return GX_ERR_UNSUPPORTED;
+            DevSatoh &m = D.satoh[D.n_satoh++];
+            m.GM = G * c.p[0];
+            m.a = c.p[1];
+            m.b2 = c.p[2] * c.p[2];
+            m.ab2 = c.p[1] * m.b2;
+            break;
+        }
         default:
             return GX_ERR_UNSUPPORTED;
         }
     }
     model = MODEL_GENERIC;
-    if (D.n_mn == 1 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW;
-    if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW2022;
-    if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1) model = MODEL_BOVY;
+    if (D.n_log + D.n_iso + D.n_satoh == 0) {
+        if (D.n_mn == 1 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW;
+        if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW2022;
+        if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1) model = MODEL_BOVY;
+    }
     return 0;
 }
 
@@ -779,7 +812,8 @@ __global__ void __launch_bounds__(128) k_stream_release(const __grid_constant__ 
     const double omega = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
     // d2Phi/dr2 = rhat . H . rhat  (register_funcs.py:442-457); r_t = cbrt(G m / (omega^2 - d2Phi/dr2))
     double H[6];
-    hessian<C>(P, x[0], x[1], x[2], H);
+    double gdummy[3];
+    grad_hess<C>(P, x[0], x[1], x[2], gdummy, H);
     const double rh[3] = {x[0] / r, x[1] / r, x[2] / r};
     const double d2 = rh[0] * (H[0] * rh[0] + H[1] * rh[1] + H[2] * rh[2]) +
                       rh[1] * (H[1] * rh[0] + H[3] * rh[1] + H[4] * rh[2]) +
@@ -1014,15 +1048,16 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     return cuda_rc(cudaGetLastError());
 }
 
-// gx_integrate_dopri8_record() passes its record buffer to the launch code through a thread-local (the two entry
-// points share everything else); it is reset before returning, so plain gx_integrate_dopri8 calls never see it.
-struct RecTls { double *rec = nullptr; int *n_rec = nullptr; int cap = 0; int solver = GX_SOLVER_DOPRI8; };
-static thread_local RecTls g_rec_tls;
+}  // extern "C"
 
-int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,
-                        const double *t0, double t0_scalar, double t1, const double *ts, int32_t T, int64_t max_steps,
-                        const int32_t *order, int32_t layout, double *q, double *p, int32_t *status,
-                        int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
+// Shared implementation of every adaptive entry point: `solver` picks the tableau, `rec` (optional) switches the
+// kernel from saving to recording accepted steps.
+static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const gx_potential *pot, const gx_pid *pid,
+                         const double *q0, const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
+                         const double *ts, int32_t T, int64_t max_steps, const int32_t *order, int32_t layout,
+                         double *q, double *p, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
+                         void *workspace, void *stream) {
+    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     DevPot D; Model model;
     int rc = build_devpot(pot, D, model);
     if (rc) return rc;
@@ -1038,7 +1073,7 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     a.q0 = q0; a.p0 = p0; a.t0v = t0; a.ts = ts; a.order = order; a.q = q; a.p = p;
     a.status = status; a.n_acc = n_accepted; a.n_tot = n_attempted;
     a.ticket = (unsigned long long *)workspace;
-    a.rec = g_rec_tls.rec; a.n_rec = g_rec_tls.n_rec; a.rec_cap = g_rec_tls.cap;
+    a.rec = rec; a.n_rec = n_rec; a.rec_cap = rec_cap;
     a.N = N; a.max_steps = max_steps; a.t0s = t0_scalar; a.t1 = t1;
     a.rtol = pid->rtol; a.atol = pid->atol;
     a.pcoeff = pid->pcoeff; a.icoeff = pid->icoeff; a.dcoeff = pid->dcoeff;
@@ -1055,8 +1090,8 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define GX_LAUNCH_DP8(C_)                                                                                     \
     do {                                                                                                      \
-        auto kern = (g_rec_tls.solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5>                   \
-                                                           : k_integrate_dopri8<C_, TabDp8>;                  \
+        auto kern = (solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5>                             \
+                                                 : k_integrate_dopri8<C_, TabDp8>;                            \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);                               \
         if (per_sm < 1) per_sm = 1;                                                                           \
         long long want = (N + block - 1) / block, resident = (long long)per_sm * sms;                         \
@@ -1068,17 +1103,22 @@ int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double
     return cuda_rc(cudaGetLastError());
 }
 
+extern "C" {
+
 int gx_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
                           const double *p0, int64_t N, const double *t0, double t0_scalar, double t1, const double *ts,
                           int32_t T, int64_t max_steps, const int32_t *order, int32_t layout, double *q, double *p,
                           int32_t *status, int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
-    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
-    const int saved = g_rec_tls.solver;
-    g_rec_tls.solver = solver;
-    int rc = gx_integrate_dopri8(pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, order, layout, q, p, status,
-                                 n_accepted, n_attempted, workspace, stream);
-    g_rec_tls.solver = saved;
-    return rc;
+    return adaptive_impl(solver, nullptr, nullptr, 0, pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, order,
+                         layout, q, p, status, n_accepted, n_attempted, workspace, stream);
+}
+
+int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,
+                        const double *t0, double t0_scalar, double t1, const double *ts, int32_t T, int64_t max_steps,
+                        const int32_t *order, int32_t layout, double *q, double *p, int32_t *status,
+                        int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
+    return adaptive_impl(GX_SOLVER_DOPRI8, nullptr, nullptr, 0, pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T,
+                         max_steps, order, layout, q, p, status, n_accepted, n_attempted, workspace, stream);
 }
 
 int gx_integrate_adaptive_record(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
@@ -1087,13 +1127,9 @@ int gx_integrate_adaptive_record(int32_t solver, const gx_potential *pot, const 
                                  int32_t *n_attempted, void *workspace, void *stream) {
     if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     if (!rec || !n_rec || rec_capacity <= 0) return GX_ERR_BADARG;
-    cudaError_t e = cudaMemsetAsync(n_rec, 0, sizeof(int32_t), (cudaStream_t)stream);
-    if (e != cudaSuccess) return GX_ERR_CUDA;
-    g_rec_tls.rec = rec; g_rec_tls.n_rec = n_rec; g_rec_tls.cap = rec_capacity; g_rec_tls.solver = solver;
-    int rc = gx_integrate_dopri8(pot, pid, q0, p0, 1, nullptr, t0, t1, nullptr, 0, max_steps, nullptr, GX_LAYOUT_NT3,
-                                 nullptr, nullptr, status, n_accepted, n_attempted, workspace, stream);
-    g_rec_tls = RecTls();
-    return rc;
+    if (cudaMemsetAsync(n_rec, 0, sizeof(int32_t), (cudaStream_t)stream) != cudaSuccess) return GX_ERR_CUDA;
+    return adaptive_impl(solver, rec, n_rec, rec_capacity, pot, pid, q0, p0, 1, nullptr, t0, t1, nullptr, 0, max_steps,
+                         nullptr, GX_LAYOUT_NT3, nullptr, nullptr, status, n_accepted, n_attempted, workspace, stream);
 }
 
 int gx_integrate_dopri8_record(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0,

@@ -25,6 +25,9 @@ constexpr int MAX_MN = 6;
 constexpr int MAX_HERN = 4;
 constexpr int MAX_NFW = 2;
 constexpr int MAX_PLC = 1;
+constexpr int MAX_LOG = 2;
+constexpr int MAX_ISO = 2;
+constexpr int MAX_SATOH = 2;
 constexpr double TINY = 2.2250738585072014e-308;
 
 struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
@@ -61,12 +64,24 @@ __device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double
     return true;
 }
 
+// (LMJ09)LogarithmicPotential, builtin/logarithmic.py:45-108: Phi = vc^2/2 ln(rs^2 + x^T M x), M symmetric with
+// M = R(phi)^T diag(1/q1^2, 1/q2^2, 1/q3^2) R(phi) (rotation about z): c11, c12, c22, c33.
+struct DevLog { double vc2, rs2, c11, c12, c22, c33; };
+// IsochronePotential, builtin/isochrone.py:80-90: Phi = -GM / (b + sqrt(r^2 + b^2)).
+struct DevIso { double GM, b, b2; };
+// SatohPotential, builtin/satoh.py:63-70: Phi = -GM / sqrt(R^2 + z^2 + a (a + 2 sqrt(z^2 + b^2))) -- a
+// Miyamoto-Nagai form whose D^2 is smaller by b^2.
+struct DevSatoh { double GM, a, b2, ab2; };
+
 struct DevPot {
-    int n_mn, n_hern, n_nfw, n_plc;
+    int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, pad_;
     DevMN mn[MAX_MN];
     DevHern hern[MAX_HERN];
     DevNFW nfw[MAX_NFW];
     DevPLC plc[MAX_PLC];
+    DevLog lg[MAX_LOG];
+    DevIso iso[MAX_ISO];
+    DevSatoh satoh[MAX_SATOH];
 };
 
 // Static component counts let the compiler unroll and schedule the whole evaluation as one block of
@@ -76,6 +91,8 @@ struct Counts {
     static constexpr bool is_static = (NMN >= 0);
     static constexpr int kMN = is_static ? NMN : MAX_MN, kH = is_static ? NH : MAX_HERN,
                          kNFW = is_static ? NNFW : MAX_NFW, kPLC = is_static ? NPLC : MAX_PLC;
+    // the three specialised Milky-Way models contain none of the further kinds; the runtime path loops over them
+    static constexpr int kLOG = is_static ? 0 : MAX_LOG, kISO = is_static ? 0 : MAX_ISO, kSAT = is_static ? 0 : MAX_SATOH;
     __device__ __forceinline__ static int mn(const DevPot &P) { return is_static ? NMN : P.n_mn; }
     __device__ __forceinline__ static int hern(const DevPot &P) { return is_static ? NH : P.n_hern; }
     __device__ __forceinline__ static int nfw(const DevPot &P) { return is_static ? NNFW : P.n_nfw; }
@@ -112,7 +129,20 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
         else { fxy += f; fz += g; }
         have_d = true;
     }
-    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0) : (P.n_hern + P.n_nfw + P.n_plc > 0);
+#pragma unroll
+    for (int i = 0; i < C::kSAT; ++i) {
+        if (i >= P.n_satoh) break;
+        const DevSatoh &c = P.satoh[i];
+        double zeta2 = z2 + c.b2;
+        double rz = rsqrt_fast(zeta2);
+        double apz = fma(zeta2, rz, c.a);
+        double rD = rsqrt_fast(fma(apz, apz, R2 - c.b2));
+        double f = (c.GM * rD) * (rD * rD);
+        fxy += f;
+        fz = fma(f, apz * rz, fz);
+    }
+    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0)
+                                      : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
     if (any_sph) {
         const double r2 = (R2 + z2) + TINY;
         const double rinv = rsqrt_fast(r2);
@@ -126,6 +156,14 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             double t = (c.GM * rinv) * rcp_fast(u * u);  // GM / ((r+c)^2 r)
             if (C::is_static && i == 0) fs = t; else fs += t;
             have_s = true;
+        }
+#pragma unroll
+        for (int i = 0; i < C::kISO; ++i) {
+            if (i >= P.n_iso) break;
+            const DevIso &c = P.iso[i];
+            double ia = rsqrt_fast(r2 + c.b2);            // 1/a, a = sqrt(r^2 + b^2)
+            double ibpa = rcp_fast(fma(r2 + c.b2, ia, c.b));  // 1/(b + a)
+            fs = fma(c.GM * ia, ibpa * ibpa, fs);         // Phi'/r = GM / (a (b+a)^2)
         }
 #pragma unroll
         for (int i = 0; i < C::kNFW; ++i) {
@@ -158,6 +196,16 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
     gx_ = fh * x;
     gy_ = fh * y;
     gz_ = fv * z;
+#pragma unroll
+    for (int i = 0; i < C::kLOG; ++i) {
+        if (i >= P.n_log) break;
+        const DevLog &c = P.lg[i];
+        const double mx = fma(c.c11, x, c.c12 * y), my = fma(c.c12, x, c.c22 * y), mz = c.c33 * z;  // M x
+        const double f = c.vc2 * rcp_fast(c.rs2 + fma(x, mx, fma(y, my, z * mz)));
+        gx_ = fma(f, mx, gx_);
+        gy_ = fma(f, my, gy_);
+        gz_ = fma(f, mz, gz_);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -183,6 +231,21 @@ __device__ __forceinline__ double potential_value(const DevPot &P, double x, dou
         double Pa = gammainc_P(c.ga, s2, nullptr);
         double Qa2 = 1.0 - gammainc_P(c.ga2, s2, nullptr);
         phi -= c.GM * (Pa / r + Qa2 * c.tail);
+    }
+    for (int i = 0; i < C::kSAT; ++i) {
+        if (i >= P.n_satoh) break;
+        const DevSatoh &c = P.satoh[i];
+        phi -= c.GM / sqrt(R2 + z2 + c.a * (c.a + 2.0 * sqrt(z2 + c.b2)));
+    }
+    for (int i = 0; i < C::kISO; ++i) {
+        if (i >= P.n_iso) break;
+        phi -= P.iso[i].GM / (P.iso[i].b + sqrt(r * r + P.iso[i].b2));
+    }
+    for (int i = 0; i < C::kLOG; ++i) {
+        if (i >= P.n_log) break;
+        const DevLog &c = P.lg[i];
+        const double q = fma(x, fma(c.c11, x, c.c12 * y), fma(y, fma(c.c12, x, c.c22 * y), c.c33 * z2));
+        phi += 0.5 * c.vc2 * log(c.rs2 + q);
     }
     return phi;
 }
@@ -219,8 +282,31 @@ __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, d
         H[4] -= f5 * y * uz;
         H[5] += fma(-f5 * uz, uz, f3 * duz);
     }
+#pragma unroll
+    for (int i = 0; i < C::kSAT; ++i) {
+        if (i >= P.n_satoh) break;
+        const DevSatoh &c = P.satoh[i];
+        const double zeta2 = z2 + c.b2;
+        const double rz = rsqrt_fast(zeta2);
+        const double apz = fma(zeta2, rz, c.a);
+        const double rD = rsqrt_fast(fma(apz, apz, R2 - c.b2)), rD2 = rD * rD;
+        const double f3 = (c.GM * rD) * rD2;
+        const double f5 = 3.0 * f3 * rD2;
+        const double w = apz * rz;
+        const double uz = z * w;
+        const double duz = fma(c.ab2 * rz, rz * rz, 1.0);
+        gxy += f3;
+        gz = fma(f3, w, gz);
+        H[0] += fma(-f5 * x, x, f3);
+        H[1] -= f5 * x * y;
+        H[2] -= f5 * x * uz;
+        H[3] += fma(-f5 * y, y, f3);
+        H[4] -= f5 * y * uz;
+        H[5] += fma(-f5 * uz, uz, f3 * duz);
+    }
     double d1r = 0.0, d2 = 0.0;  // sum over spherical components of Phi'/r and Phi''
-    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0) : (P.n_hern + P.n_nfw + P.n_plc > 0);
+    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0)
+                                      : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
     if (any_sph) {
         const double r2 = (R2 + z2) + TINY;
         const double rinv = rsqrt_fast(r2);
@@ -268,6 +354,17 @@ __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, d
                 d2 += fma(c.GM * dP * 2.0 * c.inv_rc * c.inv_rc, rinv, -2.0 * t);
             }
         }
+#pragma unroll
+        for (int i = 0; i < C::kISO; ++i) {
+            if (i >= P.n_iso) break;
+            const DevIso &c = P.iso[i];
+            const double ia = rsqrt_fast(r2 + c.b2);
+            const double ibpa = rcp_fast(fma(r2 + c.b2, ia, c.b));
+            const double t = (c.GM * ia) * (ibpa * ibpa);  // Phi'/r
+            d1r += t;
+            // Phi' = r t  =>  Phi'' = t - r^2 t (1/a^2 + 2/(a (b+a)))
+            d2 += t - r2 * t * fma(2.0 * ia, ibpa, ia * ia);
+        }
         // H += (Phi'/r) I + (Phi'' - Phi'/r) n n^T
         const double w = (d2 - d1r) * rinv2;
         H[0] += fma(w * x, x, d1r);
@@ -280,67 +377,21 @@ __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, d
     g[0] = (gxy + d1r) * x;
     g[1] = (gxy + d1r) * y;
     g[2] = (gz + d1r) * z;
-}
-
-// H[0..5] = (xx, xy, xz, yy, yz, zz)   (IEEE div/sqrt version, kept for the r -> 0 corner and as a cross-check)
-
-template <class C>
-__device__ __forceinline__ void hessian(const DevPot &P, double x, double y, double z, double H[6]) {
-    const double z2 = z * z, R2 = fma(y, y, x * x);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) H[k] = 0.0;
-    for (int i = 0; i < C::mn(P); ++i) {
-        const DevMN &c = P.mn[i];
-        double zeta2 = z2 + c.b2;
-        double zeta = sqrt(zeta2);
-        double apz = c.a + zeta;
-        double D2 = fma(apz, apz, R2);
-        double D = sqrt(D2);
-        double f3 = c.GM / (D2 * D);
-        double f5 = 3.0 * f3 / D2;
-        double uz = z * apz / zeta;
-        double duz = 1.0 + c.ab2 / (zeta2 * zeta);
-        H[0] += f3 - f5 * x * x;
-        H[1] -= f5 * x * y;
-        H[2] -= f5 * x * uz;
-        H[3] += f3 - f5 * y * y;
-        H[4] -= f5 * y * uz;
-        H[5] += f3 * duz - f5 * uz * uz;
-    }
-    if (C::hern(P) + C::nfw(P) + C::plc(P) > 0) {
-        const double r2 = (R2 + z2) + TINY;
-        const double r = sqrt(r2);
-        double d1r = 0.0, d2 = 0.0;  // sum of Phi'/r and Phi''
-        for (int i = 0; i < C::hern(P); ++i) {
-            double u = r + P.hern[i].c;
-            double d1 = P.hern[i].GM / (u * u);
-            d1r += d1 / r;
-            d2 -= 2.0 * d1 / u;
-        }
-        for (int i = 0; i < C::nfw(P); ++i) {
-            const DevNFW &c = P.nfw[i];
-            double s = r * c.inv_rs;
-            double m = nfw_menc_shape(s);
-            double d1 = c.GM * m / r2;
-            d1r += d1 / r;
-            d2 += c.GM * s / (c.rs * (1.0 + s) * (1.0 + s) * r2) - 2.0 * d1 / r;
-        }
-        for (int i = 0; i < C::plc(P); ++i) {
-            const DevPLC &c = P.plc[i];
-            double s = r * c.inv_rc, dP;
-            double Pg = gammainc_P(c.ga, s * s, &dP);
-            double d1 = c.GM * Pg / r2;
-            d1r += d1 / r;
-            d2 += c.GM * dP * 2.0 * c.inv_rc * c.inv_rc / r - 2.0 * d1 / r;
-        }
-        // H = (Phi'/r) I + (Phi'' - Phi'/r) n n^T
-        double w = (d2 - d1r) / r2;
-        H[0] += d1r + w * x * x;
-        H[1] += w * x * y;
-        H[2] += w * x * z;
-        H[3] += d1r + w * y * y;
-        H[4] += w * y * z;
-        H[5] += d1r + w * z * z;
+    for (int i = 0; i < C::kLOG; ++i) {
+        if (i >= P.n_log) break;
+        const DevLog &c = P.lg[i];
+        const double mx = fma(c.c11, x, c.c12 * y), my = fma(c.c12, x, c.c22 * y), mz = c.c33 * z;
+        const double iD = rcp_fast(c.rs2 + fma(x, mx, fma(y, my, z * mz)));
+        const double f = c.vc2 * iD, f2 = 2.0 * f * iD;
+        g[0] = fma(f, mx, g[0]); g[1] = fma(f, my, g[1]); g[2] = fma(f, mz, g[2]);
+        // H = vc^2 (M / D - 2 (M x)(M x)^T / D^2)
+        H[0] += fma(f, c.c11, -f2 * mx * mx);
+        H[1] += fma(f, c.c12, -f2 * mx * my);
+        H[2] -= f2 * mx * mz;
+        H[3] += fma(f, c.c22, -f2 * my * my);
+        H[4] -= f2 * my * mz;
+        H[5] += fma(f, c.c33, -f2 * mz * mz);
     }
 }
 

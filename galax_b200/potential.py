@@ -265,6 +265,60 @@ class KuzminPotential(AbstractPotential):
 
 
 @dataclasses.dataclass(frozen=True)
+class IsochronePotential(AbstractPotential):
+    """builtin/isochrone.py: Phi = -G m / (r_s + sqrt(r^2 + r_s^2))."""
+
+    m_tot: float
+    r_s: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_ISOCHRONE, (_const("m_tot", self.m_tot), _const("r_s", self.r_s)))]
+
+
+@dataclasses.dataclass(frozen=True)
+class SatohPotential(AbstractPotential):
+    """builtin/satoh.py: Phi = -G m / sqrt(R^2 + z^2 + a (a + 2 sqrt(z^2 + b^2)))."""
+
+    m_tot: float
+    a: float
+    b: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_SATOH, (_const("m_tot", self.m_tot), _const("a", self.a), _const("b", self.b)))]
+
+
+@dataclasses.dataclass(frozen=True)
+class LMJ09LogarithmicPotential(AbstractPotential):
+    """builtin/logarithmic.py:57-108: Phi = v_c^2/2 ln(r_s^2 + (x'/q1)^2 + (y'/q2)^2 + (z/q3)^2), (x', y') rotated by
+    ``phi`` about z.  ``v_c`` in the potential's speed unit (kpc/Myr: multiply km/s by ``KMS``), ``phi`` in radians."""
+
+    v_c: float
+    r_s: float
+    q1: float = 1.0
+    q2: float = 1.0
+    q3: float = 1.0
+    phi: float = 0.0
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_LOG, tuple(_const(n, getattr(self, n)) for n in ("v_c", "r_s", "q1", "q2", "q3", "phi")))]
+
+
+@dataclasses.dataclass(frozen=True)
+class LogarithmicPotential(AbstractPotential):
+    """builtin/logarithmic.py:27-53: the spherical case, Phi = v_c^2/2 ln(r_s^2 + r^2)."""
+
+    v_c: float
+    r_s: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_LOG, (_const("v_c", self.v_c), _const("r_s", self.r_s), 1.0, 1.0, 1.0, 0.0))]
+
+
+@dataclasses.dataclass(frozen=True)
 class NFWPotential(AbstractPotential):
     """builtin/nfw/base.py: Phi = -(G m / r_s) log(1 + r/r_s) / (r/r_s)."""
 
@@ -419,6 +473,17 @@ class MilkyWayPotential(CompositePotential):
         super().__init__(comps, G=G)
 
 
+class LM10Potential(MilkyWayPotential):
+    """builtin/milkyway.py:101-169 (Law & Majewski 2010): MN disk, Hernquist bulge, triaxial logarithmic halo."""
+
+    _defaults = {
+        "disk": dict(m_tot=1e11, a=6.5, b=0.26),
+        "bulge": dict(m_tot=3.4e10, r_s=0.7),
+        "halo": dict(v_c=math.sqrt(2.0) * 121.858 * KMS, r_s=12.0, q1=1.38, q2=1.0, q3=1.36, phi=math.radians(97.0)),
+    }
+    _classes = {"disk": MiyamotoNagaiPotential, "bulge": HernquistPotential, "halo": LMJ09LogarithmicPotential}
+
+
 class MilkyWayPotential2022(MilkyWayPotential):
     """builtin/milkyway.py:240-313: MN3Sech2 disk (positive density), NFW halo, two Hernquist spheres."""
 
@@ -445,7 +510,8 @@ class BovyMWPotential2014(MilkyWayPotential):
 
 __all__ = [
     "AbstractPotential", "MiyamotoNagaiPotential", "HernquistPotential", "KeplerPotential", "PlummerPotential",
-    "KuzminPotential", "NFWPotential",
+    "KuzminPotential", "IsochronePotential", "SatohPotential", "LogarithmicPotential", "LMJ09LogarithmicPotential",
+    "LM10Potential", "NFWPotential",
     "PowerLawCutoffPotential", "MN3ExponentialPotential", "MN3Sech2Potential", "CompositePotential",
     "MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014", "G_GALACTIC", "KMS",
 ]  # fmt: skip

@@ -33,12 +33,16 @@ extern "C" {
 #define GX_KIND_HERNQUIST 1      /* p = (m_tot, r_s)        (r_s = 0: Kepler) */
 #define GX_KIND_NFW 2            /* p = (m, r_s)            */
 #define GX_KIND_POWERLAWCUTOFF 3 /* p = (m_tot, alpha, r_c) */
+/* beyond the three named Milky-Way models; served by the runtime-count kernels */
+#define GX_KIND_LOGARITHMIC 4 /* builtin/logarithmic.py: p = (v_c, r_s, q1, q2, q3, phi[rad]); q = 1, phi = 0: spherical */
+#define GX_KIND_ISOCHRONE 5   /* builtin/isochrone.py:  p = (m_tot, r_s) */
+#define GX_KIND_SATOH 6       /* builtin/satoh.py:      p = (m_tot, a, b) */
 #define GX_MAX_COMPONENTS 14
 
 typedef struct {
     int32_t kind;
     int32_t reserved;
-    double p[4];
+    double p[8];
 } gx_component;
 
 /* A composite potential = sum of components (potential/_src/base_multi.py:39-82).  MN3 disks are passed as

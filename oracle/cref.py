@@ -19,7 +19,7 @@ OK, MAX_STEPS, NONFINITE = 0, 1, 2
 
 
 class _Component(C.Structure):
-    _fields_ = [("kind", C.c_int), ("group", C.c_int), ("p", C.c_double * 4)]
+    _fields_ = [("kind", C.c_int), ("group", C.c_int), ("p", C.c_double * 8)]
 
 
 class _Potential(C.Structure):

@@ -34,6 +34,9 @@
 #define OC_KIND_HERNQUIST 1
 #define OC_KIND_NFW 2
 #define OC_KIND_PLC 3
+#define OC_KIND_LOG 4
+#define OC_KIND_ISOCHRONE 5
+#define OC_KIND_SATOH 6
 #define OC_MAX_COMP 16
 
 #define OC_TINY 2.2250738585072014e-308
@@ -41,7 +44,7 @@
 typedef struct {
     int kind;
     int group; /* components with equal group id are summed first (MN3 disk) */
-    double p[4];
+    double p[8];
 } oc_component;
 
 typedef struct {
@@ -131,8 +134,30 @@ static double comp_potential(double G, const oc_component *c, const double q[3])
         double pinf = ga > 0 ? GM * tgamma(1 - ah) / (rc * tgamma(ga)) : 0.0;
         return t1 + t2 - pinf;
     }
+    case OC_KIND_LOG: {
+        double sp = sin(p[5]), cp = cos(p[5]);
+        double xr = x * cp + y * sp, yr = -x * sp + y * cp;
+        double r2 = (xr / p[2]) * (xr / p[2]) + (yr / p[3]) * (yr / p[3]) + (z / p[4]) * (z / p[4]);
+        return 0.5 * p[0] * p[0] * log(p[1] * p[1] + r2);
+    }
+    case OC_KIND_ISOCHRONE: {
+        double r = sqrt(x * x + y * y + z * z + OC_TINY);
+        return -G * p[0] / (p[1] + sqrt(r * r + p[1] * p[1]));
+    }
+    case OC_KIND_SATOH:
+        return -G * p[0] / sqrt(x * x + y * y + z * z + p[1] * (p[1] + 2.0 * sqrt(z * z + p[2] * p[2])));
     }
     return NAN;
+}
+
+static void log_matrix(const double *p, double M[3][3]) {
+    double sp = sin(p[5]), cp = cos(p[5]);
+    double i1 = 1.0 / (p[2] * p[2]), i2 = 1.0 / (p[3] * p[3]), i3 = 1.0 / (p[4] * p[4]);
+    M[0][0] = cp * cp * i1 + sp * sp * i2;
+    M[1][1] = sp * sp * i1 + cp * cp * i2;
+    M[0][1] = M[1][0] = cp * sp * (i1 - i2);
+    M[2][2] = i3;
+    M[0][2] = M[2][0] = M[1][2] = M[2][1] = 0.0;
 }
 
 /* radial derivatives of a spherical component: d1 = dPhi/dr, d2 = d2Phi/dr2 */
@@ -161,12 +186,37 @@ static void comp_radial(double G, const oc_component *c, double r, double *d1, d
         *d2 = GM * (dP * 2.0 * r / (rc * rc) / (r * r) - 2.0 * P / (r * r * r));
         return;
     }
+    case OC_KIND_ISOCHRONE: {
+        double b = p[1], a = sqrt(r * r + b * b);
+        *d1 = GM * r / (a * (b + a) * (b + a));
+        *d2 = GM * (1.0 / (a * (b + a) * (b + a)) - r * r / (a * a * a * (b + a) * (b + a)) -
+                    2.0 * r * r / (a * a * (b + a) * (b + a) * (b + a)));
+        return;
+    }
     }
     *d1 = *d2 = NAN;
 }
 
 static void comp_gradient(double G, const oc_component *c, const double q[3], double g[3]) {
     const double x = q[0], y = q[1], z = q[2];
+    if (c->kind == OC_KIND_LOG) {
+        double M[3][3], Mx[3];
+        log_matrix(c->p, M);
+        for (int i = 0; i < 3; ++i) Mx[i] = M[i][0] * x + M[i][1] * y + M[i][2] * z;
+        double D = c->p[1] * c->p[1] + x * Mx[0] + y * Mx[1] + z * Mx[2];
+        for (int i = 0; i < 3; ++i) g[i] = c->p[0] * c->p[0] * Mx[i] / D;
+        return;
+    }
+    if (c->kind == OC_KIND_SATOH) {
+        const double *p = c->p;
+        double zeta = sqrt(z * z + p[2] * p[2]);
+        double S = x * x + y * y + z * z + p[1] * (p[1] + 2.0 * zeta);
+        double f = G * p[0] / (S * sqrt(S));
+        g[0] = f * x;
+        g[1] = f * y;
+        g[2] = f * z * (1.0 + p[1] / zeta);
+        return;
+    }
     if (c->kind == OC_KIND_MN) {
         const double *p = c->p;
         double zeta = sqrt(z * z + p[2] * p[2]);
@@ -187,6 +237,30 @@ static void comp_gradient(double G, const oc_component *c, const double q[3], do
 
 static void comp_hessian(double G, const oc_component *c, const double q[3], double H[9]) {
     const double x = q[0], y = q[1], z = q[2];
+    if (c->kind == OC_KIND_LOG) {
+        double M[3][3], Mx[3];
+        log_matrix(c->p, M);
+        for (int i = 0; i < 3; ++i) Mx[i] = M[i][0] * x + M[i][1] * y + M[i][2] * z;
+        double D = c->p[1] * c->p[1] + x * Mx[0] + y * Mx[1] + z * Mx[2], vc2 = c->p[0] * c->p[0];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) H[3 * i + j] = vc2 * (M[i][j] / D - 2.0 * Mx[i] * Mx[j] / (D * D));
+        return;
+    }
+    if (c->kind == OC_KIND_SATOH) {
+        const double *p = c->p;
+        double a = p[1], b = p[2];
+        double zeta = sqrt(z * z + b * b);
+        double S = x * x + y * y + z * z + a * (a + 2.0 * zeta);
+        double f3 = G * p[0] / (S * sqrt(S)), f5 = 3.0 * f3 / S;
+        double u[3] = {x, y, z * (1.0 + a / zeta)};
+        double duz = 1.0 + a * b * b / (zeta * zeta * zeta);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) H[3 * i + j] = -f5 * (u[i] * u[j]);
+        H[0] += f3;
+        H[4] += f3;
+        H[8] += f3 * duz;
+        return;
+    }
     if (c->kind == OC_KIND_MN) {
         const double *p = c->p;
         double a = p[1], b = p[2];

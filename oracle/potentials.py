@@ -29,7 +29,11 @@ KIND_MN = 0  # MiyamotoNagaiPotential      p = (m_tot, a, b)
 KIND_HERNQUIST = 1  # HernquistPotential    p = (m_tot, r_s)
 KIND_NFW = 2  # NFWPotential                p = (m, r_s)
 KIND_PLC = 3  # PowerLawCutoffPotential     p = (m_tot, alpha, r_c)
-KIND_NAMES = {KIND_MN: "MN", KIND_HERNQUIST: "Hernquist", KIND_NFW: "NFW", KIND_PLC: "PowerLawCutoff"}
+KIND_LOG = 4  # (LMJ09)LogarithmicPotential p = (v_c, r_s, q1, q2, q3, phi)
+KIND_ISOCHRONE = 5  # IsochronePotential     p = (m_tot, r_s)
+KIND_SATOH = 6  # SatohPotential             p = (m_tot, a, b)
+KIND_NAMES = {KIND_MN: "MN", KIND_HERNQUIST: "Hernquist", KIND_NFW: "NFW", KIND_PLC: "PowerLawCutoff",
+              KIND_LOG: "Logarithmic", KIND_ISOCHRONE: "Isochrone", KIND_SATOH: "Satoh"}
 
 
 @dataclasses.dataclass(frozen=True)
@@ -215,9 +219,94 @@ def hessian_plc(G, m, alpha, r_c, xyz):
     return _spherical_hess(xyz, r, d1, d2)
 
 
-_POT = {KIND_MN: potential_mn, KIND_HERNQUIST: potential_hernquist, KIND_NFW: potential_nfw, KIND_PLC: potential_plc}
-_GRAD = {KIND_MN: gradient_mn, KIND_HERNQUIST: gradient_hernquist, KIND_NFW: gradient_nfw, KIND_PLC: gradient_plc}
-_HESS = {KIND_MN: hessian_mn, KIND_HERNQUIST: hessian_hernquist, KIND_NFW: hessian_nfw, KIND_PLC: hessian_plc}
+# ----------------------------------------------------------------------------------------
+# (LMJ09) Logarithmic (builtin/logarithmic.py:45-108); G is unused (the depth is set by v_c)
+
+
+def _log_matrix(q1, q2, q3, phi):
+    sp, cp = np.sin(phi), np.cos(phi)
+    R = np.array([[cp, sp, 0.0], [-sp, cp, 0.0], [0.0, 0.0, 1.0]])
+    return R.T @ np.diag([1 / q1**2, 1 / q2**2, 1 / q3**2]) @ R
+
+
+def potential_log(G, vc, rs, q1, q2, q3, phi, xyz):
+    sp, cp = np.sin(phi), np.cos(phi)
+    x = xyz[..., 0] * cp + xyz[..., 1] * sp
+    y = -xyz[..., 0] * sp + xyz[..., 1] * cp
+    r2 = (x / q1) ** 2 + (y / q2) ** 2 + (xyz[..., 2] / q3) ** 2
+    return 0.5 * vc**2 * np.log(rs**2 + r2)
+
+
+def gradient_log(G, vc, rs, q1, q2, q3, phi, xyz):
+    M = _log_matrix(q1, q2, q3, phi)
+    Mx = xyz @ M
+    D = rs**2 + np.sum(xyz * Mx, axis=-1)
+    return vc**2 * Mx / D[..., None]
+
+
+def hessian_log(G, vc, rs, q1, q2, q3, phi, xyz):
+    M = _log_matrix(q1, q2, q3, phi)
+    Mx = xyz @ M
+    D = rs**2 + np.sum(xyz * Mx, axis=-1)
+    return vc**2 * (M / D[..., None, None] - 2.0 * Mx[..., :, None] * Mx[..., None, :] / (D**2)[..., None, None])
+
+
+# Isochrone (builtin/isochrone.py:80-90)
+
+
+def potential_iso(G, m, b, xyz):
+    r = _r_safe(xyz)
+    return -G * m / (b + np.sqrt(r**2 + b**2))
+
+
+def gradient_iso(G, m, b, xyz):
+    r = _r_safe(xyz)
+    a = np.sqrt(r**2 + b**2)
+    return _spherical_grad(xyz, r, G * m * r / (a * (b + a) ** 2))
+
+
+def hessian_iso(G, m, b, xyz):
+    r = _r_safe(xyz)
+    a = np.sqrt(r**2 + b**2)
+    d1 = G * m * r / (a * (b + a) ** 2)
+    d2 = G * m * (1 / (a * (b + a) ** 2) - r**2 / (a**3 * (b + a) ** 2) - 2 * r**2 / (a**2 * (b + a) ** 3))
+    return _spherical_hess(xyz, r, d1, d2)
+
+
+# Satoh (builtin/satoh.py:63-70)
+
+
+def potential_satoh(G, m, a, b, xyz):
+    x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
+    return -G * m / np.sqrt(x**2 + y**2 + z**2 + a * (a + 2 * np.sqrt(z**2 + b**2)))
+
+
+def gradient_satoh(G, m, a, b, xyz):
+    x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
+    zeta = np.sqrt(z**2 + b**2)
+    S = x**2 + y**2 + z**2 + a * (a + 2 * zeta)
+    f = G * m / (S * np.sqrt(S))
+    return np.stack([f * x, f * y, f * z * (1 + a / zeta)], axis=-1)
+
+
+def hessian_satoh(G, m, a, b, xyz):
+    x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
+    zeta = np.sqrt(z**2 + b**2)
+    S = x**2 + y**2 + z**2 + a * (a + 2 * zeta)
+    f3 = G * m / (S * np.sqrt(S))
+    f5 = 3.0 * f3 / S
+    u = np.stack([x, y, z * (1 + a / zeta)], axis=-1)
+    duz = 1.0 + a * b**2 / zeta**3
+    H = -f5[..., None, None] * (u[..., :, None] * u[..., None, :])
+    H[..., 0, 0] += f3
+    H[..., 1, 1] += f3
+    H[..., 2, 2] += f3 * duz
+    return H
+
+
+_POT = {KIND_LOG: potential_log, KIND_ISOCHRONE: potential_iso, KIND_SATOH: potential_satoh, KIND_MN: potential_mn, KIND_HERNQUIST: potential_hernquist, KIND_NFW: potential_nfw, KIND_PLC: potential_plc}
+_GRAD = {KIND_LOG: gradient_log, KIND_ISOCHRONE: gradient_iso, KIND_SATOH: gradient_satoh, KIND_MN: gradient_mn, KIND_HERNQUIST: gradient_hernquist, KIND_NFW: gradient_nfw, KIND_PLC: gradient_plc}
+_HESS = {KIND_LOG: hessian_log, KIND_ISOCHRONE: hessian_iso, KIND_SATOH: hessian_satoh, KIND_MN: hessian_mn, KIND_HERNQUIST: hessian_hernquist, KIND_NFW: hessian_nfw, KIND_PLC: hessian_plc}
 
 
 # ----------------------------------------------------------------------------------------
@@ -358,6 +447,19 @@ def bovy_mw_potential_2014(G=G_GALACTIC) -> Potential:
         Component(KIND_NFW, (4.3683325e11, 16.0), "halo"),
     )
     return Potential(comps, G, name="BovyMWPotential2014")
+
+
+KMS = 0.001022712165045695  # 1 km/s in kpc/Myr
+
+
+def lm10_potential(G=G_GALACTIC) -> Potential:
+    """builtin/milkyway.py:101-169 (Law & Majewski 2010)."""
+    comps = (
+        Component(KIND_MN, (1e11, 6.5, 0.26), "disk"),
+        Component(KIND_HERNQUIST, (3.4e10, 0.7), "bulge"),
+        Component(KIND_LOG, (np.sqrt(2.0) * 121.858 * KMS, 12.0, 1.38, 1.0, 1.36, np.deg2rad(97.0)), "halo"),
+    )
+    return Potential(comps, G, name="LM10Potential")
 
 
 def single(kind: int, *params: float, G=G_GALACTIC) -> Potential:

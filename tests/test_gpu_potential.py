@@ -36,6 +36,17 @@ def build_gp(m):
         return gp.PlummerPotential(*m["params"])
     if kind == "Kuzmin":
         return gp.KuzminPotential(*m["params"])
+    if kind == "Isochrone":
+        return gp.IsochronePotential(*m["params"])
+    if kind == "Satoh":
+        return gp.SatohPotential(*m["params"])
+    if kind == "Logarithmic":
+        return gp.LogarithmicPotential(m["params_kms"][0] * gp.KMS, m["params_kms"][1])
+    if kind == "LMJ09Logarithmic":
+        v, rs, q1, q2, q3, ph = m["params_kms"]
+        return gp.LMJ09LogarithmicPotential(v * gp.KMS, rs, q1, q2, q3, np.deg2rad(ph))
+    if kind == "LM10Potential":
+        return gp.LM10Potential()
     cls = gp.MN3Sech2Potential if kind.endswith("Sech2") else gp.MN3ExponentialPotential
     return cls(*m["params"], positive_density=m["positive_density"])
 
@@ -102,6 +113,40 @@ def test_generic_composite_path():
     assert np.abs(pot.potential(xyz) / op.potential(opot, xyz) - 1).max() < 6e-15
     Ho = op.hessian(opot, xyz)
     assert (np.abs(pot.hessian(xyz) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 2e-13
+
+
+def test_lm10_and_further_kinds_bulk_and_orbits():
+    """logarithmic (triaxial, rotated), isochrone and Satoh components through every kernel."""
+    import galax_b200.dynamics as gd
+    from oracle import cref
+
+    pot, opot = gp.LM10Potential(), op.lm10_potential()
+    xyz = points(5000, seed=8)
+    go = op.gradient(opot, xyz)
+    assert (np.abs(pot.gradient(xyz) - go) / np.linalg.norm(go, axis=1, keepdims=True)).max() < 4e-15
+    assert np.allclose(pot.potential(xyz), op.potential(opot, xyz), rtol=1e-13, atol=1e-18)
+    Ho = op.hessian(opot, xyz)
+    assert (np.abs(pot.hessian(xyz) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 2e-13
+    mix = gp.CompositePotential(iso=gp.IsochronePotential(3e10, 2.0), sat=gp.SatohPotential(5e10, 3.0, 0.4),
+                                halo=gp.LogarithmicPotential(180 * gp.KMS, 10.0), bulge=gp.PlummerPotential(1e10, 0.5))
+    omix = op.Potential((op.Component(op.KIND_ISOCHRONE, (3e10, 2.0)), op.Component(op.KIND_SATOH, (5e10, 3.0, 0.4)),
+                         op.Component(op.KIND_LOG, (180 * op.KMS, 10.0, 1.0, 1.0, 1.0, 0.0)),
+                         op.Component(op.KIND_MN, (1e10, 0.0, 0.5))))
+    go = op.gradient(omix, xyz)
+    assert (np.abs(mix.gradient(xyz) - go) / np.linalg.norm(go, axis=1, keepdims=True)).max() < 4e-15
+    Ho = op.hessian(omix, xyz)
+    assert (np.abs(mix.hessian(xyz) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 2e-13
+    # orbits in LM10 (Sagittarius-like ICs), fixed step and adaptive
+    rng = np.random.default_rng(5)
+    q0 = np.array([19.0, 2.7, -6.9]) + rng.normal(size=(64, 3))
+    p0 = (np.array([230.0, -35.0, 195.0]) + rng.normal(size=(64, 3)) * 10) * gp.KMS
+    sie = gd.OrbitSolver(solver=gd.SemiImplicitEuler(), stepsize_controller=gd.ConstantStepSize(), max_steps=None)
+    sol = sie.solve(pot, (q0, p0), 0.0, 500.0, dt0=0.1)
+    qr, pr, st, n = cref.integrate_fixed(opot, q0, p0, 0.0, 500.0, 0.1, [500.0])
+    assert (np.linalg.norm(sol.ys[0] - qr, axis=-1) / np.linalg.norm(qr, axis=-1)).max() < 1e-12
+    orb = gd.evaluate_orbit(pot, (q0, p0), np.linspace(0.0, 500.0, 11))
+    qd, pd, *_ = cref.integrate_dopri8(opot, q0, p0, 0.0, 500.0, np.linspace(0.0, 500.0, 11), rtol=1e-7, atol=1e-7)
+    assert np.median(np.abs(orb.q - qd).max(axis=(1, 2))) < 1e-5
 
 
 def test_edge_cases():

@@ -25,6 +25,17 @@ def build(m):
         return op.single(op.KIND_MN, m["params"][0], 0.0, m["params"][1])
     if kind == "Kuzmin":
         return op.single(op.KIND_MN, m["params"][0], m["params"][1], 0.0)
+    if kind == "Isochrone":
+        return op.single(op.KIND_ISOCHRONE, *m["params"])
+    if kind == "Satoh":
+        return op.single(op.KIND_SATOH, *m["params"])
+    if kind == "Logarithmic":
+        return op.single(op.KIND_LOG, m["params_kms"][0] * op.KMS, m["params_kms"][1], 1.0, 1.0, 1.0, 0.0)
+    if kind == "LMJ09Logarithmic":
+        v, rs, q1, q2, q3, ph = m["params_kms"]
+        return op.single(op.KIND_LOG, v * op.KMS, rs, q1, q2, q3, np.deg2rad(ph))
+    if kind == "LM10Potential":
+        return op.lm10_potential()
     return op.mn3_potential(*m["params"], sech2=kind.endswith("Sech2"), positive_density=m["positive_density"])
 
 
@@ -115,6 +126,14 @@ def _mp_potential(pot, x, y, z):
         elif c.kind == op.KIND_NFW:
             s = r / p[1]
             total += -G * p[0] / p[1] * mp.log1p(s) / s
+        elif c.kind == op.KIND_LOG:
+            sp, cp = mp.sin(p[5]), mp.cos(p[5])
+            xr, yr = x * cp + y * sp, -x * sp + y * cp
+            total += mp.mpf("0.5") * p[0] ** 2 * mp.log(p[1] ** 2 + (xr / p[2]) ** 2 + (yr / p[3]) ** 2 + (z / p[4]) ** 2)
+        elif c.kind == op.KIND_ISOCHRONE:
+            total += -G * p[0] / (p[1] + mp.sqrt(r * r + p[1] ** 2))
+        elif c.kind == op.KIND_SATOH:
+            total += -G * p[0] / mp.sqrt(x * x + y * y + z * z + p[1] * (p[1] + 2 * mp.sqrt(z * z + p[2] ** 2)))
         else:
             ah = p[1] / 2
             s2 = (r / p[2]) ** 2
@@ -125,11 +144,18 @@ def _mp_potential(pot, x, y, z):
     return total
 
 
-@pytest.mark.parametrize("name", list(op.MODELS))
+EXTRA_MODELS = {
+    "LM10Potential": op.lm10_potential,
+    "Isochrone+Satoh": lambda: op.Potential((op.Component(op.KIND_ISOCHRONE, (3e10, 2.0)),
+                                             op.Component(op.KIND_SATOH, (5e10, 3.0, 0.4)))),
+}
+
+
+@pytest.mark.parametrize("name", list(op.MODELS) + list(EXTRA_MODELS))
 def test_hand_derivatives_vs_mpmath_differentiation(name):
     """grad / Hessian closed forms == numerical derivatives of the reference's potential (what jax.grad gives)."""
     mp.mp.dps = 40
-    pot = op.MODELS[name]()
+    pot = (op.MODELS.get(name) or EXTRA_MODELS[name])()
     for pt in ([1.0, 2.0, 3.0], [8.0, 0.3, -0.2], [0.05, -0.02, 0.01], [30.0, 40.0, -25.0]):
         f = lambda x, y, z: _mp_potential(pot, x, y, z)  # noqa: E731
         g = [mp.diff(f, pt, tuple(int(i == k) for i in range(3))) for k in range(3)]

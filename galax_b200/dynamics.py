@@ -537,7 +537,14 @@ class FardalStreamDF(AbstractStreamDF):
     df_kind = _lib.DF_FARDAL15
 
     def _draws(self, rng, M):
-        return np.random.default_rng(rng).standard_normal((4, M))
+        """An integer seed (or raw uint32[2] key data) reproduces ``jr.key(seed)`` -> ``jr.split(key, 4)`` ->
+        ``jr.normal(key_i, (M, 1))`` of df/fardal15.py:61,81-84 (see galax_b200/jaxrandom.py); a
+        ``numpy.random.Generator`` draws from numpy's stream instead."""
+        if isinstance(rng, np.random.Generator):
+            return rng.standard_normal((4, M))
+        from . import jaxrandom
+
+        return jaxrandom.fardal_draws(rng, M)
 
 
 class ChenStreamDF(AbstractStreamDF):
@@ -573,10 +580,11 @@ class MockStreamGenerator:
     def run(self, rng, ts, prog_w0, prog_mass, *, vmapped: bool | None = None, throw=True):
         """-> (MockStream, final progenitor PhaseSpaceCoordinate).
 
-        ``rng``: a seed / ``numpy.random.Generator`` (draws are made on the host with numpy), or the draws
-        themselves (Fardal: (4, M) standard normals; Chen: (M, 6) samples).  The reference's jax PRNG stream
-        is not reproduced.  ``vmapped`` is accepted for signature parity and ignored: every
-        particle is an independent lane of the work queue.
+        ``rng``: an integer seed (Fardal: reproduces the reference's ``jr.key(seed)`` draws through the threefry
+        restatement in ``galax_b200/jaxrandom.py``; Chen: numpy's stream, jax's SVD-based multivariate normal is not
+        reproduced), a ``numpy.random.Generator``, or the draws themselves (Fardal: (4, M) standard normals; Chen:
+        (M, 6) samples).  ``vmapped`` is accepted for signature parity and ignored: every particle is an independent
+        lane of the work queue.
         """
         ts = np.asarray(ts.detach().cpu() if hasattr(ts, "detach") else ts, dtype=np.float64)
         if ts.ndim != 1 or ts.shape[0] < 2:

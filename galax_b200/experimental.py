@@ -133,6 +133,25 @@ def integrate_orbit(*args, t0=None, t1=None, saveat=None, solver: DiffEqSolver =
 # ------------------------------------------------------------------------------------------------
 
 
+def _is_key_data(key) -> bool:
+    return isinstance(key, np.ndarray) and key.dtype == np.uint32 and key.shape == (2,)
+
+
+def _fardal_normals(key, M: int) -> np.ndarray:
+    """(4, M) standard normals: an int seed / uint32[2] key reproduces jax's stream (``jaxrandom``), a
+    ``numpy.random.Generator`` uses numpy's, a float array is taken as the draws themselves."""
+    import torch
+
+    from . import jaxrandom
+
+    if isinstance(key, np.random.Generator):
+        return key.standard_normal((4, M))
+    if isinstance(key, (int, np.integer)) or _is_key_data(key):
+        return jaxrandom.fardal_draws(key, M)
+    arr = key.detach().cpu().numpy() if isinstance(key, torch.Tensor) else np.asarray(key)
+    return np.asarray(arr, dtype=np.float64).reshape(4, M)
+
+
 @dataclasses.dataclass(frozen=True)
 class Fardal2015DF:
     """experimental/df.py:87-175: Fardal+15 release with adjustable means and dispersions."""
@@ -152,7 +171,9 @@ class Fardal2015DF:
     def sample(self, key, pot, /, t, x, v, Msat):
         """-> (x_lead, v_lead, x_trail, v_trail) for positions ``x`` / velocities ``v`` of shape ``(3,)`` or ``(M, 3)``.
 
-        ``key``: seed / Generator, or the standard-normal draws ``(4, M)``.  The release kernel hard-wires the
+        ``key``: an int seed or raw ``uint32[2]`` key data (reproduces ``jr.key(seed)``: pinned on the reference's
+        doctest, experimental/df.py:110-123), a ``numpy.random.Generator``, or the standard-normal draws ``(4, M)``.
+        The release kernel hard-wires the
         reference's legacy constants (kr = 2 + 0.5 n1, ...); other means/sigmas are mapped onto it exactly by an
         affine change of the draws (k = mean + sigma n = 2 + 0.5 n'  with  n' = (mean - 2 + sigma n) / 0.5, etc.).
         """
@@ -163,10 +184,7 @@ class Fardal2015DF:
         scalar = dq.ndim == 1
         dq, dp = dq.reshape(-1, 3).contiguous(), dp.reshape(-1, 3).contiguous()
         M = dq.shape[0]
-        if isinstance(key, (np.ndarray, torch.Tensor)):
-            n = np.asarray(key.detach().cpu() if isinstance(key, torch.Tensor) else key, dtype=np.float64).reshape(4, M)
-        else:
-            n = np.random.default_rng(key).standard_normal((4, M))
+        n = _fardal_normals(key, M)
         # affine map of the draws onto the kernel's fixed constants (2, 0.3, 0, 0; all sigmas 0.5)
         n_eff = np.empty_like(n)
         n_eff[0] = (self.kr_bar - 2.0 + self.sigma_kr * n[0]) / 0.5
@@ -204,30 +222,30 @@ class StreamSimulator:
 
     def init(self, pot, prog_w0, prog_t0, /, release_times, Msat, kinematic_df: Fardal2015DF | None = None, *, key,
              solver: DiffEqSolver = default_stream_solver, solver_kwargs: Mapping[str, Any] | None = None) -> StreamICs:  # fmt: skip
-        """Progenitor orbit from ``prog_t0`` to every release time (one solve, saved at the sorted release times;
-        backward in time when they precede ``prog_t0``), then the DF at those points (stream.py:122-237)."""
+        """stream.py:122-237: sort the release times; integrate the progenitor from ``prog_t0`` to the first one; then
+        integrate over the release times saving at each; then one DF sample per release time with the key chain
+        ``key, subkey = jr.split(key)`` of the reference's ``lax.scan``."""
+        from . import jaxrandom
+
         df = Fardal2015DF() if kinematic_df is None else kinematic_df
-        rel = np.asarray(release_times, dtype=np.float64)
-        order = np.argsort(rel)
-        q0, p0 = prog_w0
-        t0 = float(prog_t0)
+        rel = np.sort(np.asarray(release_times, dtype=np.float64))
+        M = rel.shape[0]
         kw = dict(solver_kwargs or {})
         ctrl = kw.get("stepsize_controller", solver.stepsize_controller)
         ms = kw.get("max_steps", solver.max_steps)
-        xq = np.empty((rel.shape[0], 3))
-        xp = np.empty((rel.shape[0], 3))
-        q0n, p0n = np.asarray(_host(q0), dtype=np.float64), np.asarray(_host(p0), dtype=np.float64)
-        before = order[rel[order] < t0][::-1]  # met going backward from prog_t0 (decreasing time)
-        after = order[rel[order] >= t0]        # met going forward
-        for idx in (before, after):
-            if idx.size == 0:
-                continue
-            ts = rel[idx]
-            q, p, _, _ = _integrate(pot, q0n[None], p0n[None], t0, float(ts[-1]), ts, solver=solver.solver,
-                                    controller=ctrl, dt0=kw.get("dt0"), max_steps=ms)  # fmt: skip
-            xq[idx], xp[idx] = q[0], p[0]
+        q0n = np.asarray(_host(prog_w0[0]), dtype=np.float64)[None]
+        p0n = np.asarray(_host(prog_w0[1]), dtype=np.float64)[None]
+        common = dict(solver=solver.solver, controller=ctrl, dt0=kw.get("dt0"), max_steps=ms)
+        qa, pa, _, _ = _integrate(pot, q0n, p0n, float(prog_t0), float(rel[0]), [float(rel[0])], **common)
+        xq, xp, _, _ = _integrate(pot, qa[:, 0], pa[:, 0], float(rel[0]), float(rel[-1]), rel, **common)
+        xq, xp = xq[0], xp[0]
         mass = np.broadcast_to(np.asarray(Msat, dtype=np.float64), rel.shape).copy()
-        ql, pl, qt, pt = df.sample(key, pot, rel, xq, xp, mass)
+        if isinstance(key, (int, np.integer)) or _is_key_data(key):
+            k = jaxrandom.key(key) if isinstance(key, (int, np.integer)) else key
+            draws = jaxrandom.fardal_draws_per_key(jaxrandom.split_chain(k, M))
+        else:
+            draws = _fardal_normals(key, M)
+        ql, pl, qt, pt = df.sample(draws, pot, rel, xq, xp, mass)
         return StreamICs(release_times=rel, prog_mass=mass, qp_lead=(ql, pl), qp_trail=(qt, pt))
 
     def run(self, pot, stream_ics: StreamICs, /, t1, *, solver: DiffEqSolver = default_stream_solver,

@@ -94,11 +94,22 @@ def test_fardal2015df_parameters_and_stream_simulator():
     rt = np.linalg.norm(ref[2][0] - x) / np.hypot(2 + 0.5 * n[0, 0], 0.5 * n[2, 0])
     assert np.isclose(np.linalg.norm(xt2 - x), rt * np.hypot(1.5 + 0.25 * n[0, 0], 0.1 * n[2, 0]), rtol=1e-10)
 
+    # the reference's doctest of Fardal2015DF.sample(jr.key(0), NFW(1e12, 15), ...) (experimental/df.py:110-123)
+    nfw = gp.NFWPotential(1e12, 15.0)
+    xl3, vl3, xt3, vt3 = ge.Fardal2015DF().sample(0, nfw, 0.0, np.array([15.0, 0, 0]), np.array([0, 220.0, 0]), 1e5)
+    assert np.allclose(xl3, [1.49962403e01, 0.0, 2.49694925e-04], rtol=2e-9, atol=1e-12)
+    assert np.allclose(vt3, [0.0, 2.19977919e02, 6.34205795e-03], rtol=2e-9, atol=1e-12)
+
     M = 2000
     release = np.linspace(-4000.0, -150.0, M)
     sim = ge.StreamSimulator()
     ics = sim.init(pot, (x, np.array([0.0, 0.225, 0.0])), 0.0, release_times=release, Msat=1e5, key=0)
     assert ics.qp_lead[0].shape == (M, 3) and np.isfinite(ics.qp_trail[1]).all() and ics.prog_mass.shape == (M,)
+    # the reference's doctest of StreamSimulator.init(..., key=jr.key(0)) (experimental/stream.py:79-106); the Dopri5
+    # progenitor orbit with forced dtmin = 0.3 is only good to ~1e-3, the PRNG-driven z-offsets to 3e-4
+    assert np.allclose(ics.qp_lead[0][0], [-10.76187104, -7.35400639, 0.0674116], atol=8e-3)
+    assert np.allclose(ics.qp_lead[0][-1], [-4.72896837, 14.03657666, -0.09171104], atol=8e-3)
+    assert np.isclose(ics.qp_lead[0][0, 2], 0.0674116, rtol=5e-4)
     lead, trail = sim.run(pot, ics, t1=0.0)
     assert lead[0].shape == (M, 3) and trail[1].shape == (M, 3) and np.isfinite(lead[0]).all()
     # oracle: same ICs through the Dopri5 oracle with dtmin = 0.3

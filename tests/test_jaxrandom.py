@@ -1,0 +1,64 @@
+"""CPU: the jax.random restatement (threefry2x32, split, normal) against published vectors and the reference's
+own doctests (the only places where the reference prints values that depend on its PRNG stream)."""
+import numpy as np
+
+from galax_b200 import jaxrandom as jr
+from oracle import cref
+from oracle import potentials as op
+
+
+def test_threefry_known_answers():
+    """Random123 known-answer vectors (Salmon et al. 2011), also used by jax's own test-suite."""
+    kat = [((0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]  # fmt: skip
+    for (k0, k1), (c0, c1), (e0, e1) in kat:
+        r0, r1 = jr.threefry2x32(k0, k1, [c0], [c1])
+        assert (int(r0[0]), int(r1[0])) == (e0, e1)
+        assert jr._threefry_int(k0, k1, c0, c1) == (e0, e1)
+
+
+def test_reference_doctest_fardal2015df_sample_key0():
+    """experimental/df.py:110-123: Fardal2015DF().sample(jr.key(0), NFW(1e12, 15), t=0, x=[15,0,0], v=[0,220,0],
+    Msat=1e5) -- pins key(), split(), normal() AND the release algebra / tidal radius on a reference-made value."""
+    pot = op.single(op.KIND_NFW, 1e12, 15.0)
+    n = jr.fardal_draws(0, 1)
+    ql, pl, qt, pt = cref.release_fardal(pot, [[15.0, 0, 0]], [[0, 220.0, 0]], 1e5, n)
+    assert np.allclose(ql[0], [1.49962403e01, 0.0, 2.49694925e-04], rtol=2e-9, atol=1e-12)
+    assert np.allclose(pl[0], [0.0, 2.20022081e02, 6.34205795e-03], rtol=2e-9, atol=1e-12)
+    assert np.allclose(qt[0], [1.50037597e01, 0.0, 2.49694925e-04], rtol=2e-9, atol=1e-12)
+    assert np.allclose(pt[0], [0.0, 2.19977919e02, 6.34205795e-03], rtol=2e-9, atol=1e-12)
+
+
+def test_reference_doctest_stream_simulator_init_key0():
+    """experimental/stream.py:79-106: StreamSimulator().init(Hernquist(1e12, 10), qp0, 0, release_times=
+    linspace(-4000, -150, 2000), Msat=1e5, key=jr.key(0)).  The progenitor orbit uses Dopri5 with dtmin = 0.3
+    (forced steps: global error ~1e-3 and sensitive to the step sequence), so positions agree to that level; the
+    z-offsets, which come from the PRNG chain times the tidal radius, agree to 2e-4."""
+    pot = op.single(op.KIND_HERNQUIST, 1e12, 10.0)
+    rel = np.linspace(-4000.0, -150.0, 2000)
+    kw = dict(rtol=1e-7, atol=1e-7, dtmin=0.3, max_steps=10_000, solver="dopri5")
+    q, p, st, _, _ = cref.integrate_dopri8(pot, [[15.0, 0, 0]], [[0, 0.225, 0]], 0.0, rel[0], [rel[0]], **kw)
+    Q, P, st2, _, _ = cref.integrate_dopri8(pot, q[0], p[0], rel[0], rel[-1], rel, **kw)
+    assert st[0] == 0 and st2[0] == 0
+    draws = jr.fardal_draws_per_key(jr.split_chain(jr.key(0), 2000))
+    ql, pl, qt, pt = cref.release_fardal(pot, Q[0], P[0], 1e5, draws)
+    assert np.allclose(ql[0], [-10.76187104, -7.35400639, 0.0674116], atol=6e-3)
+    assert np.allclose(ql[-1], [-4.72896837, 14.03657666, -0.09171104], atol=6e-3)
+    assert np.allclose(qt[0], [-11.00416221, -7.5195734, 0.0674116], atol=6e-3)
+    assert np.isclose(ql[0, 2], 0.0674116, rtol=3e-4) and np.isclose(ql[-1, 2], -0.09171104, rtol=3e-4)
+    assert np.allclose(pl[0], [4.77386246e-02, -2.74264308e-01, -4.68601912e-04], atol=3e-4)
+
+
+def test_split_chain_and_vectorised_draws_are_consistent():
+    k = jr.key(12)
+    sub = jr.split_chain(k, 5)
+    a, b = k, None
+    for i in range(5):
+        both = jr.split(a, 2)
+        a, b = both[0], both[1]
+        assert np.array_equal(sub[i], b)
+    one = jr.fardal_draws_per_key(sub[:1])
+    assert np.allclose(one[:, 0], jr.fardal_draws(sub[0], 1)[:, 0])
+    d = jr.fardal_draws(7, 100_000)
+    assert abs(d.mean()) < 0.01 and abs(d.std() - 1) < 0.01 and np.isfinite(d).all()

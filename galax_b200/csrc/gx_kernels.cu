@@ -551,14 +551,18 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 }
                 { double t0_, t1_, t2_; accel_call<C>(q0x, q0y, q0z, t0_, t1_, t2_); AX(0) = t0_; AY(0) = t1_; AZ(0) = t2_; }
+                // PIDController.init: heuristic when dt0 is None (exponent 1/(error_order + 1), Hairer II.4 -- the
+                // choice that reproduces the reference's 8-digit OrbitSolver doctests), then clamp to [dtmin, dtmax]
                 double h;
                 if (a.dt0 > 0.0) {
                     h = a.dt0;
                 } else {
                     const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
                     const double a0[3] = {AX(0), AY(0), AZ(0)};
-                    h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol, 1.0 / TB::ORDER);
+                    h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol, 1.0 / (TB::ORDER + 1));
                 }
+                if (a.dtmax > 0.0) h = fmin(h, a.dtmax);
+                if (a.dtmin > 0.0) { at_dtmin = h <= a.dtmin; h = fmax(h, a.dtmin); }
                 tprev = T0;
                 tnext = clip_to_end(T0, T0 + h, T1, true);
                 have = true;

@@ -516,12 +516,18 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
         double f0[6];
         field_dir(P, dir, y, f0);
         double tprev = T0, tnext;
-        {
-            double h = (pid->dt0 > 0.0) ? pid->dt0 : select_initial_step(P, dir, y, f0, pid->rtol, pid->atol, order);
-            tnext = clip_to_end(T0, T0 + h, T1, 1);
-        }
         double prev_inv = 1.0, prev_prev_inv = 1.0;
         int at_dtmin = 0;
+        {
+            /* PIDController.init: heuristic when dt0 is None, then clamp to [dtmin, dtmax].  The heuristic's exponent
+             * is 1/(error_order + 1) (Hairer II.4 with p = order): inferred from the reference's 8-digit OrbitSolver
+             * doctests, which this reproduces to 4e-9 (1/error_order: 6e-8, i.e. a different first step). */
+            double h = (pid->dt0 > 0.0) ? pid->dt0
+                                        : select_initial_step(P, dir, y, f0, pid->rtol, pid->atol, order + 1.0);
+            if (pid->dtmax > 0.0 && isfinite(pid->dtmax)) h = fmin(h, pid->dtmax);
+            if (pid->dtmin > 0.0) { at_dtmin = h <= pid->dtmin; h = fmax(h, pid->dtmin); }
+            tnext = clip_to_end(T0, T0 + h, T1, 1);
+        }
         double K[14][6], flast[6];
         while (tprev < T1) {
             if (max_steps >= 0 && ntot >= max_steps) { st = OC_MAX_STEPS; break; }

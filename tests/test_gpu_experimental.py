@@ -116,3 +116,18 @@ def test_fardal2015df_parameters_and_stream_simulator():
     qr, pr, st, na, nt = cref.integrate_dopri8(opot, ics.qp_lead[0][:200], ics.qp_lead[1][:200], release[:200], 0.0, [0.0],
                                                rtol=1e-7, atol=1e-7, dtmin=0.3, max_steps=10_000, solver="dopri5")
     assert np.median(np.abs(lead[0][:200] - qr[:, 0]).max(axis=1)) < 1e-3
+
+
+def test_reference_experimental_integrate_orbit_doctest_on_gpu():
+    """experimental/integrate.py:159-247 through the GPU path: 8 decimals, incl. a dense-output value."""
+    import json
+    from pathlib import Path
+
+    kats = json.loads((Path(__file__).parent / "golden" / "orbit_kats.json").read_text())
+    for case in kats["experimental"]:
+        pot = gp.NFWPotential(*case["model"]["params"])
+        ts = np.linspace(case["t0"], case["t1"], case["n_saves"])
+        sol = ge.integrate_orbit(pot, (np.array(case["q0"]), np.array(case["p0"])), t0=case["t0"], t1=case["t1"], saveat=ts)
+        for row, ref in case["rows"].items():
+            assert np.allclose(sol.ys[0][:, int(row)], ref["q"], atol=case["atol"], rtol=0)
+            assert np.allclose(sol.ys[1][:, int(row)], ref["p"], atol=case["atol"], rtol=0)

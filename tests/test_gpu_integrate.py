@@ -136,6 +136,20 @@ def test_reference_dopri8_doctests(case):
     assert np.allclose(sol.ys[1], case["p"], atol=case["atol"], rtol=0)
 
 
+@pytest.mark.parametrize("case", KATS["integrate_field"], ids=lambda c: c["name"][:40])
+def test_reference_integrate_field_doctest_given_its_first_step(case):
+    """dynamics/_src/solver.py:341-365 (Kepler, dtmin = 0.05); see the note in orbit_kats.json."""
+    pot = gp.KeplerPotential(*case["model"]["params"])
+    solver = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=case["rtol"], atol=case["atol_solver"],
+                                                                 dtmin=case["dtmin"]), max_steps=case["max_steps"])
+    ts = np.linspace(case["t0"], case["t1"], case["n_saves"])
+    sol = solver.solve(pot, (np.array(case["q0"]), np.array(case["p0"])), case["t0"], case["t1"], saveat=ts,
+                       dt0=case["dt0_observed"])
+    for row, ref in case["rows"].items():
+        assert np.allclose(sol.ys[0][int(row)], ref["q"], atol=ref["atol"], rtol=0)
+        assert np.allclose(sol.ys[1][int(row)], ref["p"], atol=ref["atol"], rtol=0)
+
+
 @pytest.mark.parametrize("name,tol", [("MilkyWayPotential2022", 1e-10), ("MilkyWayPotential", 1e-7),
                                       ("BovyMWPotential2014", 1e-8)])
 def test_dopri8_parity_with_oracle(name, tol):

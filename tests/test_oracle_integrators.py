@@ -207,3 +207,29 @@ def test_dopri5_tableau_and_oracle():
     q, p, st, na, nt = cref.integrate_dopri8(pot, q0, p0, 0.0, 300.0, [300.0], rtol=1e-12, atol=1e-12, dtmin=0.3,
                                              solver="dopri5")
     assert (st == 0).all() and (nt <= 1001).all()
+
+
+def test_reference_experimental_integrate_orbit_doctest():
+    """experimental/integrate.py:159-247: 8-decimal values incl. a save inside the first step (dense output)."""
+    for case in KATS["experimental"]:
+        pot = op.single(op.KIND_NFW, *case["model"]["params"])
+        ts = np.linspace(case["t0"], case["t1"], case["n_saves"])
+        q, p, st, na, nt = cref.integrate_dopri8(pot, case["q0"], case["p0"], case["t0"], case["t1"], ts, rtol=case["rtol"],
+                                                 atol=case["atol"] if False else case["rtol"], dtmin=case["dtmin"],
+                                                 max_steps=case["max_steps"])
+        for row, ref in case["rows"].items():
+            assert np.allclose(q[:, int(row)], ref["q"], atol=case["atol"], rtol=0)
+            assert np.allclose(p[:, int(row)], ref["p"], atol=case["atol"], rtol=0)
+
+
+def test_reference_integrate_field_doctest_given_its_first_step():
+    """dynamics/_src/solver.py:341-365 (Kepler, dtmin = 0.05): see the note in orbit_kats.json."""
+    for case in KATS["integrate_field"]:
+        pot = op.single(op.KIND_HERNQUIST, case["model"]["params"][0], 0.0)
+        ts = np.linspace(case["t0"], case["t1"], case["n_saves"])
+        q, p, st, na, nt = cref.integrate_dopri8(pot, [case["q0"]], [case["p0"]], case["t0"], case["t1"], ts,
+                                                 rtol=case["rtol"], atol=case["atol_solver"], dtmin=case["dtmin"],
+                                                 max_steps=case["max_steps"], dt0=case["dt0_observed"])
+        for row, ref in case["rows"].items():
+            assert np.allclose(q[0, int(row)], ref["q"], atol=ref["atol"], rtol=0)
+            assert np.allclose(p[0, int(row)], ref["p"], atol=ref["atol"], rtol=0)

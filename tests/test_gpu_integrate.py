@@ -136,6 +136,18 @@ def test_reference_dopri8_doctests(case):
     assert np.allclose(sol.ys[1], case["p"], atol=case["atol"], rtol=0)
 
 
+def test_reference_single_dopri8_step_doctest():
+    """`OrbitSolver.step` (orbit/solver.py:290-321): ONE Dopri8 step of 10 Myr, printed to 8 digits -- pins the
+    kernel's tableau arithmetic independently of step control (loose tolerance + dt0 = t1 - t0 => one step)."""
+    case = KATS["joint"][0]
+    pot = gp.HernquistPotential(*case["model"]["params"])
+    solver = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=1e-2, atol=1e-2))
+    sol = solver.solve(pot, (np.array(case["q0"]), np.array(case["p0_kms"]) * KMS), case["t0"], case["t1"], dt0=10.0)
+    assert int(sol.stats["num_steps"].max()) == 1
+    assert np.allclose(np.asarray(sol.ys[0])[:, 0], case["q"], atol=case["atol"], rtol=0)
+    assert np.allclose(np.asarray(sol.ys[1])[:, 0], case["p"], atol=case["atol"], rtol=0)
+
+
 @pytest.mark.parametrize("case", KATS["integrate_field"], ids=lambda c: c["name"][:40])
 def test_reference_integrate_field_doctest_given_its_first_step(case):
     """dynamics/_src/solver.py:341-365 (Kepler, dtmin = 0.05); see the note in orbit_kats.json."""

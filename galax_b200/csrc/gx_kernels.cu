@@ -126,7 +126,9 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool u
     model = MODEL_GENERIC;
     if (D.n_log + D.n_iso + D.n_satoh == 0) {
         if (D.n_mn == 1 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW;
-        if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW2022;
+        if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0 && D.mn[0].b2 == D.mn[1].b2 &&
+            D.mn[0].b2 == D.mn[2].b2)
+            model = MODEL_MW2022;  // CountsMW2022 evaluates sqrt(z^2 + b^2) once: needs one b (an MN3 disk)
         if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1) model = MODEL_BOVY;
     }
     return 0;

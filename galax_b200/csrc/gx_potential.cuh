@@ -86,9 +86,12 @@ struct DevPot {
 
 // Static component counts let the compiler unroll and schedule the whole evaluation as one block of
 // straight-line code; Runtime (-1) is the generic fallback for arbitrary composites of the four kinds.
-template <int NMN, int NH, int NNFW, int NPLC>
+template <int NMN, int NH, int NNFW, int NPLC, bool MN_SHARED_B = false>
 struct Counts {
     static constexpr bool is_static = (NMN >= 0);
+    // all Miyamoto-Nagai terms have the same b (the three disks of an MN3 model, mn3.py:121-130): sqrt(z^2 + b^2)
+    // is evaluated once.  Same bits as evaluating it per term; the host checks the equality before dispatching.
+    static constexpr bool mn_shared_b = MN_SHARED_B;
     static constexpr int kMN = is_static ? NMN : MAX_MN, kH = is_static ? NH : MAX_HERN,
                          kNFW = is_static ? NNFW : MAX_NFW, kPLC = is_static ? NPLC : MAX_PLC;
     // the three specialised Milky-Way models contain none of the further kinds; the runtime path loops over them
@@ -100,7 +103,7 @@ struct Counts {
 };
 using CountsRuntime = Counts<-1, -1, -1, -1>;
 using CountsMW = Counts<1, 2, 1, 0>;      // MilkyWayPotential:      MN disk, NFW halo, 2 Hernquist
-using CountsMW2022 = Counts<3, 2, 1, 0>;  // MilkyWayPotential2022:  MN3 disk, NFW halo, 2 Hernquist
+using CountsMW2022 = Counts<3, 2, 1, 0, true>;  // MilkyWayPotential2022:  MN3 disk (one b), NFW halo, 2 Hernquist
 using CountsBovy = Counts<1, 0, 1, 1>;    // BovyMWPotential2014:    MN disk, PLC bulge, NFW halo
 
 // ---------------------------------------------------------------------------------------------
@@ -114,12 +117,15 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
     // accumulate() starts from the first term instead of adding to 0.0 (a DADD the compiler must keep)
     double fxy = 0.0, fz = 0.0, fs = 0.0;
     bool have_d = false, have_s = false;
+    double zeta2 = 0.0, rz = 0.0;
 #pragma unroll
     for (int i = 0; i < C::kMN; ++i) {
         if (!C::is_static && i >= P.n_mn) break;
         const DevMN &c = P.mn[i];
-        double zeta2 = z2 + c.b2;
-        double rz = rsqrt_fast(zeta2);       // 1/zeta
+        if (!C::mn_shared_b || i == 0) {
+            zeta2 = z2 + c.b2;
+            rz = rsqrt_fast(zeta2);          // 1/zeta
+        }
         double apz = fma(zeta2, rz, c.a);    // a + zeta
         double D2 = fma(apz, apz, R2);
         double rD = rsqrt_fast(D2);
@@ -257,14 +263,17 @@ template <class C>
 __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, double z, double g[3], double H[6]) {
     const double z2 = z * z, R2 = fma(y, y, x * x);
     double gxy = 0.0, gz = 0.0;  // g = (gxy x, gxy y, gz) for the flattened part
+    double zeta2 = 0.0, rz = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) H[k] = 0.0;
 #pragma unroll
     for (int i = 0; i < C::kMN; ++i) {
         if (!C::is_static && i >= P.n_mn) break;
         const DevMN &c = P.mn[i];
-        const double zeta2 = z2 + c.b2;
-        const double rz = rsqrt_fast(zeta2);
+        if (!C::mn_shared_b || i == 0) {
+            zeta2 = z2 + c.b2;
+            rz = rsqrt_fast(zeta2);
+        }
         const double apz = fma(zeta2, rz, c.a);
         const double D2 = fma(apz, apz, R2);
         const double rD = rsqrt_fast(D2), rD2 = rD * rD;

@@ -27,6 +27,7 @@ NVCC_FLAGS = [
 GX_MAX_COMPONENTS = 14
 KIND_MN, KIND_HERNQUIST, KIND_NFW, KIND_PLC = 0, 1, 2, 3
 KIND_LOG, KIND_ISOCHRONE, KIND_SATOH = 4, 5, 6
+KIND_TRIAXIAL_HERNQUIST, KIND_JAFFE, KIND_BURKERT, KIND_STONE, KIND_HARMONIC, KIND_HENON_HEILES = 7, 8, 9, 10, 11, 12
 PHI, GRAD, ACC, HESS = 1, 2, 4, 8
 OK, MAX_STEPS_REACHED, NONFINITE = 0, 1, 2
 SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1

@@ -119,12 +119,47 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool u
             m.ab2 = c.p[1] * m.b2;
             break;
         }
+        case GX_KIND_TRIAXIAL_HERNQUIST:
+        case GX_KIND_JAFFE:
+        case GX_KIND_BURKERT:
+        case GX_KIND_STONE: {
+            if (D.n_rad >= MAX_RAD) return GX_ERR_UNSUPPORTED;
+            DevRad &r = D.rad[D.n_rad++];
+            r.pad_ = 0;
+            r.i1 = r.i2 = 1.0;
+            r.b = 0.0;
+            if (c.kind == GX_KIND_TRIAXIAL_HERNQUIST) {
+                if (!(c.p[2] > 0.0 && c.p[3] > 0.0)) return GX_ERR_BADARG;
+                r.profile = RAD_HERNQUIST; r.K = G * c.p[0]; r.a = c.p[1];
+                r.i1 = 1.0 / (c.p[2] * c.p[2]); r.i2 = 1.0 / (c.p[3] * c.p[3]);
+            } else if (c.kind == GX_KIND_JAFFE) {
+                r.profile = RAD_JAFFE; r.K = G * c.p[0]; r.a = c.p[1];
+            } else if (c.kind == GX_KIND_BURKERT) {
+                r.profile = RAD_BURKERT; r.K = G * c.p[0] / (3.0 * log(2.0) - M_PI / 2); r.a = c.p[1]; r.b = 1.0 / c.p[1];
+            } else {
+                if (!(c.p[1] > 0.0 && c.p[2] > 0.0) || c.p[1] == c.p[2]) return GX_ERR_BADARG;
+                r.profile = RAD_STONE; r.K = 2.0 * G * c.p[0] / (M_PI * (c.p[2] - c.p[1])); r.a = c.p[1]; r.b = c.p[2];
+            }
+            break;
+        }
+        case GX_KIND_HARMONIC: {
+            if (D.n_harm >= MAX_HARM) return GX_ERR_UNSUPPORTED;
+            DevHarm &h = D.harm[D.n_harm++];
+            h.w2x = c.p[0] * c.p[0]; h.w2y = c.p[1] * c.p[1]; h.w2z = c.p[2] * c.p[2];
+            break;
+        }
+        case GX_KIND_HENON_HEILES: {
+            if (D.n_henon >= MAX_HENON) return GX_ERR_UNSUPPORTED;
+            DevHenon &h = D.henon[D.n_henon++];
+            h.k = c.p[0]; h.it2 = 1.0 / (c.p[1] * c.p[1]);
+            break;
+        }
         default:
             return GX_ERR_UNSUPPORTED;
         }
     }
     model = MODEL_GENERIC;
-    if (D.n_log + D.n_iso + D.n_satoh == 0) {
+    if (D.n_log + D.n_iso + D.n_satoh + D.n_rad + D.n_harm + D.n_henon == 0) {
         if (D.n_mn == 1 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW;
         if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0 && D.mn[0].b2 == D.mn[1].b2 &&
             D.mn[0].b2 == D.mn[2].b2)

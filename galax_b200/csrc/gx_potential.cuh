@@ -28,6 +28,9 @@ constexpr int MAX_PLC = 1;
 constexpr int MAX_LOG = 2;
 constexpr int MAX_ISO = 2;
 constexpr int MAX_SATOH = 2;
+constexpr int MAX_RAD = 4;
+constexpr int MAX_HARM = 1;
+constexpr int MAX_HENON = 1;
 constexpr double TINY = 2.2250738585072014e-308;
 
 struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
@@ -73,8 +76,19 @@ struct DevIso { double GM, b, b2; };
 // Miyamoto-Nagai form whose D^2 is smaller by b^2.
 struct DevSatoh { double GM, a, b2, ab2; };
 
+// Profiles in an ellipsoidal radius m^2 = x^2 + y^2/q1^2 + z^2/q2^2 (i1 = 1/q1^2, i2 = 1/q2^2; spherical: 1, 1):
+//   RAD_HERNQUIST  TriaxialHernquistPotential, hernquist.py:160-176   K = GM,                    a = r_s
+//   RAD_JAFFE      JaffePotential,             jaffe.py:50-60         K = GM,                    a = r_s
+//   RAD_BURKERT    BurkertPotential,           burkert.py:197-227     K = GM/(3 ln2 - pi/2),     a = r_s, b = 1/r_s
+//   RAD_STONE      StoneOstriker15Potential,   stoneostriker15.py     K = 2GM/(pi (r_h - r_c)),  a = r_c, b = r_h
+enum { RAD_HERNQUIST = 0, RAD_JAFFE = 1, RAD_BURKERT = 2, RAD_STONE = 3 };
+struct DevRad { int profile, pad_; double K, a, b, i1, i2; };
+// HarmonicOscillatorPotential (example.py:75-85), HenonHeilesPotential (example.py:159-176): polynomials.
+struct DevHarm { double w2x, w2y, w2z; };
+struct DevHenon { double k, it2; };
+
 struct DevPot {
-    int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, pad_;
+    int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, n_rad, n_harm, n_henon;
     DevMN mn[MAX_MN];
     DevHern hern[MAX_HERN];
     DevNFW nfw[MAX_NFW];
@@ -82,7 +96,81 @@ struct DevPot {
     DevLog lg[MAX_LOG];
     DevIso iso[MAX_ISO];
     DevSatoh satoh[MAX_SATOH];
+    DevRad rad[MAX_RAD];
+    DevHarm harm[MAX_HARM];
+    DevHenon henon[MAX_HENON];
 };
+
+// Burkert: B(s) = 2 ln(1+s) + ln(1+s^2) - 2 atan(s) = M(<r) C/m.  Below s = 0.3 the three terms cancel to
+// O(s^3): B' = 4 s^2 / ((1+s)(1+s^2)) = 4 s^2 (1-s)/(1-s^4) integrates to 4 s^3 sum_n s^4n (1/(4n+3) - s/(4n+4)).
+__device__ __forceinline__ double burkert_B(double s) {
+    if (s < 0.3) {
+        const double s4 = (s * s) * (s * s);
+        double e = 0.0;
+#pragma unroll
+        for (int n = 8; n >= 0; --n) e = fma(e, s4, 1.0 / (double)(4 * n + 3) - s / (double)(4 * n + 4));
+        return 4.0 * (s * s * s) * e;
+    }
+    return 2.0 * log1p(s) + log1p(s * s) - 2.0 * atan(s);
+}
+// Stone-Ostriker: T(m) = r_h atan(m/r_h) - r_c atan(m/r_c) = M(<r) pi (r_h - r_c)/(2 M); series below 0.3 r_c.
+__device__ __forceinline__ double stone_T(double m, double rc, double rh) {
+    if (m < 0.3 * rc) {
+        const double uc = (m / rc) * (m / rc), uh = (m / rh) * (m / rh);
+        double acc = 0.0, pc = 1.0, ph = 1.0;
+#pragma unroll
+        for (int k = 1; k <= 16; ++k) {
+            pc *= uc; ph *= uh;
+            const double term = (ph - pc) / (double)(2 * k + 1);
+            acc += (k & 1) ? -term : term;
+        }
+        return m * acc;
+    }
+    return rh * atan2(m, rh) - rc * atan2(m, rc);
+}
+
+// f = F'(m)/m and (optionally) d2 = F''(m), phi = F(m) of a DevRad profile; m2 = m^2 (> 0).
+__device__ __forceinline__ void rad_profile(const DevRad &c, double m2, double &f, double *d2, double *phi) {
+    const double minv = rsqrt_fast(m2), m = m2 * minv;
+    switch (c.profile) {
+    case RAD_HERNQUIST: {
+        const double iu = rcp_fast(m + c.a);
+        const double d1 = c.K * iu * iu;
+        f = d1 * minv;
+        if (d2) *d2 = -2.0 * d1 * iu;
+        if (phi) *phi = -c.K * iu;
+        break;
+    }
+    case RAD_JAFFE: {
+        const double iu = rcp_fast(m + c.a);
+        const double d1 = c.K * minv * iu;  // GM / (m (m + a))
+        f = d1 * minv;
+        if (d2) *d2 = -d1 * (2.0 * m + c.a) * (minv * iu);
+        if (phi) *phi = -c.K / c.a * log(1.0 + c.a * minv);
+        break;
+    }
+    case RAD_BURKERT: {
+        const double s = m * c.b;
+        const double d1 = c.K * burkert_B(s) * (minv * minv);
+        f = d1 * minv;
+        if (d2) *d2 = fma(c.K * 4.0 * c.b * c.b * c.b, 1.0 / ((1.0 + s) * fma(s, s, 1.0)), -2.0 * f);
+        if (phi) {
+            const double si = 1.0 / s;
+            *phi = -c.K * c.b * (3.14159265358979323846 - 2.0 * (1.0 + si) * atan(s) + 2.0 * (1.0 + si) * log1p(s) -
+                                 (1.0 - si) * log1p(s * s));
+        }
+        break;
+    }
+    default: {  // RAD_STONE
+        const double rc = c.a, rh = c.b;
+        const double T = stone_T(m, rc, rh);
+        f = c.K * T * (minv * minv) * minv;
+        if (d2) *d2 = fma(c.K * (rh * rh - rc * rc), 1.0 / ((m2 + rh * rh) * (m2 + rc * rc)), -2.0 * f);
+        if (phi) *phi = -c.K * (T * minv + 0.5 * log((m2 + rh * rh) / (m2 + rc * rc)));
+        break;
+    }
+    }
+}
 
 // Static component counts let the compiler unroll and schedule the whole evaluation as one block of
 // straight-line code; Runtime (-1) is the generic fallback for arbitrary composites of the four kinds.
@@ -96,6 +184,7 @@ struct Counts {
                          kNFW = is_static ? NNFW : MAX_NFW, kPLC = is_static ? NPLC : MAX_PLC;
     // the three specialised Milky-Way models contain none of the further kinds; the runtime path loops over them
     static constexpr int kLOG = is_static ? 0 : MAX_LOG, kISO = is_static ? 0 : MAX_ISO, kSAT = is_static ? 0 : MAX_SATOH;
+    static constexpr int kRAD = is_static ? 0 : MAX_RAD, kHARM = is_static ? 0 : MAX_HARM, kHENON = is_static ? 0 : MAX_HENON;
     __device__ __forceinline__ static int mn(const DevPot &P) { return is_static ? NMN : P.n_mn; }
     __device__ __forceinline__ static int hern(const DevPot &P) { return is_static ? NH : P.n_hern; }
     __device__ __forceinline__ static int nfw(const DevPot &P) { return is_static ? NNFW : P.n_nfw; }
@@ -212,6 +301,29 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
         gy_ = fma(f, my, gy_);
         gz_ = fma(f, mz, gz_);
     }
+#pragma unroll 1
+    for (int i = 0; i < C::kRAD; ++i) {
+        if (i >= P.n_rad) break;
+        const DevRad &c = P.rad[i];
+        const double wy = y * c.i1, wz = z * c.i2;
+        double f;
+        rad_profile(c, fma(x, x, fma(y, wy, fma(z, wz, TINY))), f, nullptr, nullptr);
+        gx_ = fma(f, x, gx_);
+        gy_ = fma(f, wy, gy_);
+        gz_ = fma(f, wz, gz_);
+    }
+    for (int i = 0; i < C::kHARM; ++i) {
+        if (i >= P.n_harm) break;
+        gx_ = fma(P.harm[i].w2x, x, gx_);
+        gy_ = fma(P.harm[i].w2y, y, gy_);
+        gz_ = fma(P.harm[i].w2z, z, gz_);
+    }
+    for (int i = 0; i < C::kHENON; ++i) {
+        if (i >= P.n_henon) break;
+        const double k = P.henon[i].k, it2 = P.henon[i].it2;
+        gx_ = fma(fma(2.0 * k * x, y, x), it2, gx_);
+        gy_ = fma(fma(k, x * x - y * y, y), it2, gy_);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -252,6 +364,21 @@ __device__ __forceinline__ double potential_value(const DevPot &P, double x, dou
         const DevLog &c = P.lg[i];
         const double q = fma(x, fma(c.c11, x, c.c12 * y), fma(y, fma(c.c12, x, c.c22 * y), c.c33 * z2));
         phi += 0.5 * c.vc2 * log(c.rs2 + q);
+    }
+    for (int i = 0; i < C::kRAD; ++i) {
+        if (i >= P.n_rad) break;
+        const DevRad &c = P.rad[i];
+        double f, v;
+        rad_profile(c, fma(x, x, fma(y, y * c.i1, fma(z, z * c.i2, TINY))), f, nullptr, &v);
+        phi += v;
+    }
+    for (int i = 0; i < C::kHARM; ++i) {
+        if (i >= P.n_harm) break;
+        phi += 0.5 * fma(P.harm[i].w2x * x, x, fma(P.harm[i].w2y * y, y, P.harm[i].w2z * z2));
+    }
+    for (int i = 0; i < C::kHENON; ++i) {
+        if (i >= P.n_henon) break;
+        phi += (0.5 * R2 + P.henon[i].k * (x * x * y - y * y * y / 3.0)) * P.henon[i].it2;
     }
     return phi;
 }
@@ -401,6 +528,38 @@ __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, d
         H[3] += fma(f, c.c22, -f2 * my * my);
         H[4] -= f2 * my * mz;
         H[5] += fma(f, c.c33, -f2 * mz * mz);
+    }
+#pragma unroll 1
+    for (int i = 0; i < C::kRAD; ++i) {
+        if (i >= P.n_rad) break;
+        const DevRad &c = P.rad[i];
+        const double wy = y * c.i1, wz = z * c.i2;
+        const double m2 = fma(x, x, fma(y, wy, fma(z, wz, TINY)));
+        double f, d2;
+        rad_profile(c, m2, f, &d2, nullptr);
+        g[0] = fma(f, x, g[0]); g[1] = fma(f, wy, g[1]); g[2] = fma(f, wz, g[2]);
+        // H += (F'/m) diag(1, i1, i2) + (F'' - F'/m)/m^2 w w^T
+        const double w = (d2 - f) / m2;
+        H[0] += fma(w * x, x, f);
+        H[1] = fma(w * x, wy, H[1]);
+        H[2] = fma(w * x, wz, H[2]);
+        H[3] += fma(w * wy, wy, f * c.i1);
+        H[4] = fma(w * wy, wz, H[4]);
+        H[5] += fma(w * wz, wz, f * c.i2);
+    }
+    for (int i = 0; i < C::kHARM; ++i) {
+        if (i >= P.n_harm) break;
+        g[0] = fma(P.harm[i].w2x, x, g[0]); g[1] = fma(P.harm[i].w2y, y, g[1]); g[2] = fma(P.harm[i].w2z, z, g[2]);
+        H[0] += P.harm[i].w2x; H[3] += P.harm[i].w2y; H[5] += P.harm[i].w2z;
+    }
+    for (int i = 0; i < C::kHENON; ++i) {
+        if (i >= P.n_henon) break;
+        const double k = P.henon[i].k, it2 = P.henon[i].it2;
+        g[0] = fma(fma(2.0 * k * x, y, x), it2, g[0]);
+        g[1] = fma(fma(k, x * x - y * y, y), it2, g[1]);
+        H[0] += fma(2.0 * k, y, 1.0) * it2;
+        H[1] += 2.0 * k * x * it2;
+        H[3] += fma(-2.0 * k, y, 1.0) * it2;
     }
 }
 

@@ -65,6 +65,27 @@ def convert_potential(pot) -> bp.AbstractPotential:
         cls = bp.MN3Sech2Potential if isinstance(pot, gp.MN3Sech2Potential) else bp.MN3ExponentialPotential
         return cls(_value(pot.m_tot, um), _value(pot.h_R, ul), _value(pot.h_z, ul),
                    positive_density=bool(pot.positive_density), G=G)  # fmt: skip
+    # further single components: (galax class name, galax_b200 class, ((field, unit key), ...)) -- positional order of
+    # the galax_b200 constructors; units as the reference's ``_potential`` methods strip them
+    ua, ud, us = pot.units["angle"], pot.units["dimensionless"], pot.units["speed"]
+    simple = (
+        ("PlummerPotential", bp.PlummerPotential, (("m_tot", um), ("r_s", ul))),
+        ("KuzminPotential", bp.KuzminPotential, (("m_tot", um), ("r_s", ul))),
+        ("IsochronePotential", bp.IsochronePotential, (("m_tot", um), ("r_s", ul))),
+        ("SatohPotential", bp.SatohPotential, (("m_tot", um), ("a", ul), ("b", ul))),
+        ("JaffePotential", bp.JaffePotential, (("m_tot", um), ("r_s", ul))),
+        ("BurkertPotential", bp.BurkertPotential, (("m", um), ("r_s", ul))),
+        ("StoneOstriker15Potential", bp.StoneOstriker15Potential, (("m_tot", um), ("r_c", ul), ("r_h", ul))),
+        ("TriaxialHernquistPotential", bp.TriaxialHernquistPotential, (("m_tot", um), ("r_s", ul), ("q1", ud), ("q2", ud))),
+        ("LMJ09LogarithmicPotential", bp.LMJ09LogarithmicPotential,
+         (("v_c", us), ("r_s", ul), ("q1", ud), ("q2", ud), ("q3", ud), ("phi", ua))),
+        ("LogarithmicPotential", bp.LogarithmicPotential, (("v_c", us), ("r_s", ul))),
+    )  # fmt: skip
+    for name, cls, fields in simple:
+        if type(pot).__name__ == name:
+            return cls(*[_value(getattr(pot, f), unit) for f, unit in fields], G=G)
+    if type(pot).__name__ == "NullPotential":
+        return bp.NullPotential(G=G)
     if isinstance(pot, gp.AbstractCompositePotential):  # CompositePotential and the pre-composited MW models
         return bp.CompositePotential({k: convert_potential(v) for k, v in pot.items()}, G=G)
     raise NotImplementedError(f"{type(pot).__name__} has no galax_b200 kernel")
@@ -81,7 +102,10 @@ def register() -> None:
     Supported = (
         gp.MilkyWayPotential | gp.MilkyWayPotential2022 | gp.BovyMWPotential2014 | gp.MiyamotoNagaiPotential
         | gp.HernquistPotential | gp.NFWPotential | gp.PowerLawCutoffPotential | gp.MN3Sech2Potential
-        | gp.MN3ExponentialPotential
+        | gp.MN3ExponentialPotential | gp.LM10Potential | gp.KeplerPotential | gp.PlummerPotential | gp.KuzminPotential
+        | gp.IsochronePotential | gp.SatohPotential | gp.JaffePotential | gp.BurkertPotential
+        | gp.StoneOstriker15Potential | gp.TriaxialHernquistPotential | gp.LMJ09LogarithmicPotential
+        | gp.LogarithmicPotential
     )  # fmt: skip
 
     def _np(x):

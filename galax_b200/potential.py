@@ -290,6 +290,107 @@ class SatohPotential(AbstractPotential):
 
 
 @dataclasses.dataclass(frozen=True)
+class TriaxialHernquistPotential(AbstractPotential):
+    """builtin/hernquist.py:89-176: the Hernquist profile at m^2 = x^2 + (y/q1)^2 + (z/q2)^2."""
+
+    m_tot: float
+    r_s: float
+    q1: float = 1.0
+    q2: float = 1.0
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_TRIAXIAL_HERNQUIST, tuple(_const(n, getattr(self, n)) for n in ("m_tot", "r_s", "q1", "q2")))]
+
+
+@dataclasses.dataclass(frozen=True)
+class JaffePotential(AbstractPotential):
+    """builtin/jaffe.py: Phi = -G m / r_s ln(1 + r_s / r)."""
+
+    m_tot: float
+    r_s: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_JAFFE, (_const("m_tot", self.m_tot), _const("r_s", self.r_s)))]
+
+
+@dataclasses.dataclass(frozen=True)
+class BurkertPotential(AbstractPotential):
+    """builtin/burkert.py:37-227: cored halo; ``m`` is the characteristic mass pi rho_0 r_s^3 (3 ln 2 - pi/2)."""
+
+    m: float
+    r_s: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_BURKERT, (_const("m", self.m), _const("r_s", self.r_s)))]
+
+    @classmethod
+    def from_central_density(cls, rho_0: float, r_s: float, **kw) -> "BurkertPotential":
+        """builtin/burkert.py:114-150."""
+        return cls(m=math.pi * rho_0 * r_s**3 * (3 * math.log(2.0) - math.pi / 2), r_s=r_s, **kw)
+
+    def rho0(self) -> float:
+        """Central density (builtin/burkert.py:103-109)."""
+        return self.m / ((3 * math.log(2.0) - math.pi / 2) * math.pi * self.r_s**3)
+
+
+@dataclasses.dataclass(frozen=True)
+class StoneOstriker15Potential(AbstractPotential):
+    """builtin/stoneostriker15.py:19-160: rho ~ 1 / ((1 + r^2/r_c^2)(1 + r^2/r_h^2))."""
+
+    m_tot: float
+    r_c: float
+    r_h: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_STONE, (_const("m_tot", self.m_tot), _const("r_c", self.r_c), _const("r_h", self.r_h)))]
+
+
+@dataclasses.dataclass(frozen=True)
+class HarmonicOscillatorPotential(AbstractPotential):
+    """builtin/example.py:23-100: Phi = 1/2 sum (omega_i x_i)^2; ``omega`` a scalar or three values [1/Myr]."""
+
+    omega: Any
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        w = np.broadcast_to(np.asarray(self.omega, dtype=np.float64), (3,))
+        return [(_lib.KIND_HARMONIC, tuple(float(v) for v in w))]
+
+    def density(self, q, t=0.0):
+        """The reference's own ``_density`` (example.py:86-98): sum over ``atleast_1d(omega)``^2 / (4 pi G) -- for a
+        scalar omega that is a third of laplacian / (4 pi G); mirrored as is."""
+        rho = float(np.sum(np.atleast_1d(np.asarray(self.omega, dtype=np.float64)) ** 2)) / (4 * math.pi * self.G)
+        lap = self.laplacian(q, t)
+        return lap * 0 + rho
+
+
+@dataclasses.dataclass(frozen=True)
+class HenonHeilesPotential(AbstractPotential):
+    """builtin/example.py:107-176: Phi = (R^2/2 + coeff (x^2 y - y^3/3)) / timescale^2."""
+
+    coeff: float
+    timescale: float
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return [(_lib.KIND_HENON_HEILES, (_const("coeff", self.coeff), _const("timescale", self.timescale)))]
+
+
+@dataclasses.dataclass(frozen=True)
+class NullPotential(AbstractPotential):
+    """builtin/null.py: Phi = 0 (no components reach the device; every output is zero)."""
+
+    G: float = G_GALACTIC
+
+    def _flat_components(self):
+        return []
+
+
+@dataclasses.dataclass(frozen=True)
 class LMJ09LogarithmicPotential(AbstractPotential):
     """builtin/logarithmic.py:57-108: Phi = v_c^2/2 ln(r_s^2 + (x'/q1)^2 + (y'/q2)^2 + (z/q3)^2), (x', y') rotated by
     ``phi`` about z.  ``v_c`` in the potential's speed unit (kpc/Myr: multiply km/s by ``KMS``), ``phi`` in radians."""
@@ -511,7 +612,8 @@ class BovyMWPotential2014(MilkyWayPotential):
 __all__ = [
     "AbstractPotential", "MiyamotoNagaiPotential", "HernquistPotential", "KeplerPotential", "PlummerPotential",
     "KuzminPotential", "IsochronePotential", "SatohPotential", "LogarithmicPotential", "LMJ09LogarithmicPotential",
-    "LM10Potential", "NFWPotential",
+    "LM10Potential", "NFWPotential", "TriaxialHernquistPotential", "JaffePotential", "BurkertPotential",
+    "StoneOstriker15Potential", "HarmonicOscillatorPotential", "HenonHeilesPotential", "NullPotential",
     "PowerLawCutoffPotential", "MN3ExponentialPotential", "MN3Sech2Potential", "CompositePotential",
     "MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014", "G_GALACTIC", "KMS",
 ]  # fmt: skip

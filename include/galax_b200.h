@@ -37,6 +37,12 @@ extern "C" {
 #define GX_KIND_LOGARITHMIC 4 /* builtin/logarithmic.py: p = (v_c, r_s, q1, q2, q3, phi[rad]); q = 1, phi = 0: spherical */
 #define GX_KIND_ISOCHRONE 5   /* builtin/isochrone.py:  p = (m_tot, r_s) */
 #define GX_KIND_SATOH 6       /* builtin/satoh.py:      p = (m_tot, a, b) */
+#define GX_KIND_TRIAXIAL_HERNQUIST 7 /* builtin/hernquist.py:89-176: p = (m_tot, r_s, q1, q2) */
+#define GX_KIND_JAFFE 8       /* builtin/jaffe.py:      p = (m_tot, r_s) */
+#define GX_KIND_BURKERT 9     /* builtin/burkert.py:    p = (m, r_s) */
+#define GX_KIND_STONE 10      /* builtin/stoneostriker15.py: p = (m_tot, r_c, r_h), r_c != r_h */
+#define GX_KIND_HARMONIC 11   /* builtin/example.py:23-100  HarmonicOscillatorPotential: p = (omega_x, omega_y, omega_z) */
+#define GX_KIND_HENON_HEILES 12 /* builtin/example.py:107-176 HenonHeilesPotential: p = (coeff, timescale) */
 #define GX_MAX_COMPONENTS 14
 
 typedef struct {

@@ -37,6 +37,14 @@
 #define OC_KIND_LOG 4
 #define OC_KIND_ISOCHRONE 5
 #define OC_KIND_SATOH 6
+#define OC_KIND_TRIAXIAL_HERNQUIST 7 /* p = (m_tot, r_s, q1, q2)      builtin/hernquist.py:160-176 */
+#define OC_KIND_JAFFE 8              /* p = (m_tot, r_s)              builtin/jaffe.py:50-60 */
+#define OC_KIND_BURKERT 9            /* p = (m, r_s)                  builtin/burkert.py:197-227 */
+#define OC_KIND_STONE 10             /* p = (m_tot, r_c, r_h)         builtin/stoneostriker15.py:150-160 */
+#define OC_KIND_HARMONIC 11          /* p = (omega_x, omega_y, omega_z) builtin/example.py:75-85 */
+#define OC_KIND_HENON_HEILES 12      /* p = (coeff, timescale)        builtin/example.py:159-176 */
+#define OC_PI 3.14159265358979323846
+#define OC_BURKERT_C (3.0 * 0.69314718055994530942 - OC_PI / 2.0)
 #define OC_MAX_COMP 16
 
 #define OC_TINY 2.2250738585072014e-308
@@ -146,6 +154,29 @@ static double comp_potential(double G, const oc_component *c, const double q[3])
     }
     case OC_KIND_SATOH:
         return -G * p[0] / sqrt(x * x + y * y + z * z + p[1] * (p[1] + 2.0 * sqrt(z * z + p[2] * p[2])));
+    case OC_KIND_TRIAXIAL_HERNQUIST: {
+        double m = sqrt(x * x + (y / p[2]) * (y / p[2]) + (z / p[3]) * (z / p[3]) + OC_TINY);
+        return -G * p[0] / (m + p[1]);
+    }
+    case OC_KIND_JAFFE: {
+        double r = sqrt(x * x + y * y + z * z + OC_TINY);
+        return -G * p[0] / p[1] * log(1.0 + p[1] / r);
+    }
+    case OC_KIND_BURKERT: {
+        double r = sqrt(x * x + y * y + z * z + OC_TINY);
+        double s = r / p[1], si = 1.0 / s;
+        return -G * p[0] / (p[1] * OC_BURKERT_C) *
+               (OC_PI - 2.0 * (1.0 + si) * atan(s) + 2.0 * (1.0 + si) * log1p(s) - (1.0 - si) * log1p(s * s));
+    }
+    case OC_KIND_STONE: {
+        double r = sqrt(x * x + y * y + z * z + OC_TINY), rc = p[1], rh = p[2];
+        double A = -2.0 * G * p[0] / (OC_PI * (rh - rc));
+        return A * ((rh * atan2(r, rh) - rc * atan2(r, rc)) / r + 0.5 * log((r * r + rh * rh) / (r * r + rc * rc)));
+    }
+    case OC_KIND_HARMONIC:
+        return 0.5 * ((p[0] * x) * (p[0] * x) + (p[1] * y) * (p[1] * y) + (p[2] * z) * (p[2] * z));
+    case OC_KIND_HENON_HEILES:
+        return ((x * x + y * y) / 2.0 + p[0] * (x * x * y - y * y * y / 3.0)) / (p[1] * p[1]);
     }
     return NAN;
 }
@@ -158,6 +189,31 @@ static void log_matrix(const double *p, double M[3][3]) {
     M[0][1] = M[1][0] = cp * sp * (i1 - i2);
     M[2][2] = i3;
     M[0][2] = M[2][0] = M[1][2] = M[2][1] = 0.0;
+}
+
+/* Burkert: 2 ln(1+s) + ln(1+s^2) - 2 atan(s), series below s = 0.3 (see oracle/potentials.py:_burkert_B) */
+static double burkert_B(double s) {
+    if (s < 0.3) {
+        double s4 = (s * s) * (s * s), e = 0.0;
+        for (int n = 8; n >= 0; --n) e = e * s4 + (1.0 / (double)(4 * n + 3) - s / (double)(4 * n + 4));
+        return 4.0 * (s * s * s) * e;
+    }
+    return 2.0 * log1p(s) + log1p(s * s) - 2.0 * atan(s);
+}
+
+/* Stone-Ostriker: r_h atan(r/r_h) - r_c atan(r/r_c), Taylor series (16 terms) below r = 0.3 r_c */
+static double stone_T(double r, double rc, double rh) {
+    if (r < 0.3 * rc) {
+        double uc = (r / rc) * (r / rc), uh = (r / rh) * (r / rh), acc = 0.0, pc = 1.0, ph = 1.0;
+        for (int k = 1; k <= 16; ++k) {
+            pc *= uc;
+            ph *= uh;
+            double term = (ph - pc) / (double)(2 * k + 1);
+            acc += (k & 1) ? -term : term;
+        }
+        return r * acc;
+    }
+    return rh * atan2(r, rh) - rc * atan2(r, rc);
 }
 
 /* radial derivatives of a spherical component: d1 = dPhi/dr, d2 = d2Phi/dr2 */
@@ -184,6 +240,30 @@ static void comp_radial(double G, const oc_component *c, double r, double *d1, d
         double dP = pow(s2, a - 1.0) * exp(-s2) / tgamma(a);
         *d1 = GM * P / (r * r);
         *d2 = GM * (dP * 2.0 * r / (rc * rc) / (r * r) - 2.0 * P / (r * r * r));
+        return;
+    }
+    case OC_KIND_TRIAXIAL_HERNQUIST: { /* r is the ellipsoidal radius here */
+        double u = r + p[1];
+        *d1 = GM / (u * u);
+        *d2 = -2.0 * GM / (u * u * u);
+        return;
+    }
+    case OC_KIND_JAFFE: {
+        double a = p[1], ra = r * (r + a);
+        *d1 = GM / ra;
+        *d2 = -GM * (2.0 * r + a) / (ra * ra);
+        return;
+    }
+    case OC_KIND_BURKERT: {
+        double rs = p[1], s = r / rs, k = GM / OC_BURKERT_C;
+        *d1 = k * burkert_B(s) / (r * r);
+        *d2 = k * 4.0 * s * s / ((1.0 + s) * (1.0 + s * s) * rs * r * r) - 2.0 * (*d1) / r;
+        return;
+    }
+    case OC_KIND_STONE: {
+        double rc = p[1], rh = p[2], A = 2.0 * GM / (OC_PI * (rh - rc));
+        *d1 = A * stone_T(r, rc, rh) / (r * r);
+        *d2 = A * (rh * rh - rc * rc) / ((r * r + rh * rh) * (r * r + rc * rc)) - 2.0 * (*d1) / r;
         return;
     }
     case OC_KIND_ISOCHRONE: {
@@ -227,12 +307,31 @@ static void comp_gradient(double G, const oc_component *c, const double q[3], do
         g[2] = f * z * (p[1] + zeta) / zeta;
         return;
     }
-    double r = sqrt(x * x + y * y + z * z + OC_TINY), d1, d2;
+    if (c->kind == OC_KIND_HARMONIC) {
+        g[0] = c->p[0] * c->p[0] * x;
+        g[1] = c->p[1] * c->p[1] * y;
+        g[2] = c->p[2] * c->p[2] * z;
+        return;
+    }
+    if (c->kind == OC_KIND_HENON_HEILES) {
+        double k = c->p[0], it2 = 1.0 / (c->p[1] * c->p[1]);
+        g[0] = (x + 2.0 * k * x * y) * it2;
+        g[1] = (y + k * (x * x - y * y)) * it2;
+        g[2] = 0.0;
+        return;
+    }
+    /* profiles in the (ellipsoidal) radius: grad = (F'/m) (x, y/q1^2, z/q2^2) */
+    double i1 = 1.0, i2 = 1.0;
+    if (c->kind == OC_KIND_TRIAXIAL_HERNQUIST) {
+        i1 = 1.0 / (c->p[2] * c->p[2]);
+        i2 = 1.0 / (c->p[3] * c->p[3]);
+    }
+    double r = sqrt(x * x + y * y * i1 + z * z * i2 + OC_TINY), d1, d2;
     comp_radial(G, c, r, &d1, &d2);
     double f = d1 / r;
     g[0] = f * x;
-    g[1] = f * y;
-    g[2] = f * z;
+    g[1] = f * (y * i1);
+    g[2] = f * (z * i2);
 }
 
 static void comp_hessian(double G, const oc_component *c, const double q[3], double H[9]) {
@@ -278,14 +377,34 @@ static void comp_hessian(double G, const oc_component *c, const double q[3], dou
         H[8] += f3 * duz;
         return;
     }
-    double r = sqrt(x * x + y * y + z * z + OC_TINY), d1, d2;
+    if (c->kind == OC_KIND_HARMONIC) {
+        for (int i = 0; i < 9; ++i) H[i] = 0.0;
+        H[0] = c->p[0] * c->p[0];
+        H[4] = c->p[1] * c->p[1];
+        H[8] = c->p[2] * c->p[2];
+        return;
+    }
+    if (c->kind == OC_KIND_HENON_HEILES) {
+        double k = c->p[0], it2 = 1.0 / (c->p[1] * c->p[1]);
+        for (int i = 0; i < 9; ++i) H[i] = 0.0;
+        H[0] = (1.0 + 2.0 * k * y) * it2;
+        H[1] = H[3] = 2.0 * k * x * it2;
+        H[4] = (1.0 - 2.0 * k * y) * it2;
+        return;
+    }
+    double dg[3] = {1.0, 1.0, 1.0};
+    if (c->kind == OC_KIND_TRIAXIAL_HERNQUIST) {
+        dg[1] = 1.0 / (c->p[2] * c->p[2]);
+        dg[2] = 1.0 / (c->p[3] * c->p[3]);
+    }
+    double r = sqrt(x * x + y * y * dg[1] + z * z * dg[2] + OC_TINY), d1, d2;
     comp_radial(G, c, r, &d1, &d2);
-    double n[3] = {x / r, y / r, z / r};
+    double n[3] = {x / r, y * dg[1] / r, z * dg[2] / r}; /* w / m */
     double f = d1 / r;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
             double nn = n[i] * n[j];
-            H[3 * i + j] = d2 * nn + f * ((i == j ? 1.0 : 0.0) - nn);
+            H[3 * i + j] = (d2 - f) * nn + (i == j ? f * dg[i] : 0.0);
         }
 }
 

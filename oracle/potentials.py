@@ -32,7 +32,15 @@ KIND_PLC = 3  # PowerLawCutoffPotential     p = (m_tot, alpha, r_c)
 KIND_LOG = 4  # (LMJ09)LogarithmicPotential p = (v_c, r_s, q1, q2, q3, phi)
 KIND_ISOCHRONE = 5  # IsochronePotential     p = (m_tot, r_s)
 KIND_SATOH = 6  # SatohPotential             p = (m_tot, a, b)
-KIND_NAMES = {KIND_MN: "MN", KIND_HERNQUIST: "Hernquist", KIND_NFW: "NFW", KIND_PLC: "PowerLawCutoff",
+KIND_TRIAXIAL_HERNQUIST = 7  # TriaxialHernquistPotential p = (m_tot, r_s, q1, q2)
+KIND_JAFFE = 8  # JaffePotential             p = (m_tot, r_s)
+KIND_BURKERT = 9  # BurkertPotential         p = (m, r_s)
+KIND_STONE = 10  # StoneOstriker15Potential  p = (m_tot, r_c, r_h)
+KIND_HARMONIC = 11  # HarmonicOscillatorPotential p = (omega_x, omega_y, omega_z)
+KIND_HENON_HEILES = 12  # HenonHeilesPotential p = (coeff, timescale)
+KIND_NAMES = {KIND_TRIAXIAL_HERNQUIST: "TriaxialHernquist", KIND_JAFFE: "Jaffe", KIND_BURKERT: "Burkert", KIND_STONE: "StoneOstriker15",
+              KIND_HARMONIC: "HarmonicOscillator", KIND_HENON_HEILES: "HenonHeiles",
+              KIND_MN: "MN", KIND_HERNQUIST: "Hernquist", KIND_NFW: "NFW", KIND_PLC: "PowerLawCutoff",
               KIND_LOG: "Logarithmic", KIND_ISOCHRONE: "Isochrone", KIND_SATOH: "Satoh"}
 
 
@@ -304,10 +312,202 @@ def hessian_satoh(G, m, a, b, xyz):
     return H
 
 
+# ----------------------------------------------------------------------------------------
+# Profiles in an (ellipsoidal) radius m: Phi = F(m), m^2 = x^2 + (y/q1)^2 + (z/q2)^2.
+#   grad = (F'/m) w,  H = (F'/m) diag(1, 1/q1^2, 1/q2^2) + (F'' - F'/m)/m^2 w w^T,  w = (x, y/q1^2, z/q2^2)
+
+
+def _ellipsoidal(xyz, q1, q2):
+    x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
+    m = np.sqrt(x**2 + (y / q1) ** 2 + (z / q2) ** 2 + TINY)
+    w = np.stack([x, y / q1**2, z / q2**2], axis=-1)
+    return m, w
+
+
+def _ellipsoidal_grad(xyz, q1, q2, d1_of_m):
+    m, w = _ellipsoidal(xyz, q1, q2)
+    return (d1_of_m(m) / m)[..., None] * w
+
+
+def _ellipsoidal_hess(xyz, q1, q2, d1_of_m, d2_of_m):
+    m, w = _ellipsoidal(xyz, q1, q2)
+    d1m = d1_of_m(m) / m
+    H = ((d2_of_m(m) - d1m) / m**2)[..., None, None] * (w[..., :, None] * w[..., None, :])
+    for k, s in enumerate((1.0, 1.0 / q1**2, 1.0 / q2**2)):
+        H[..., k, k] += d1m * s
+    return H
+
+
+# TriaxialHernquist (builtin/hernquist.py:160-176): the spherical Hernquist profile at the ellipsoidal radius
+
+
+def potential_thern(G, m_tot, c, q1, q2, xyz):
+    m, _ = _ellipsoidal(xyz, q1, q2)
+    return -G * m_tot / (m + c)
+
+
+def gradient_thern(G, m_tot, c, q1, q2, xyz):
+    return _ellipsoidal_grad(xyz, q1, q2, lambda m: G * m_tot / (m + c) ** 2)
+
+
+def hessian_thern(G, m_tot, c, q1, q2, xyz):
+    return _ellipsoidal_hess(xyz, q1, q2, lambda m: G * m_tot / (m + c) ** 2, lambda m: -2 * G * m_tot / (m + c) ** 3)
+
+
+# Jaffe (builtin/jaffe.py:50-60): Phi = -GM/r_s ln(1 + r_s/r)
+
+
+def potential_jaffe(G, m_tot, a, xyz):
+    r = _r_safe(xyz)
+    return -G * m_tot / a * np.log(1 + a / r)
+
+
+def gradient_jaffe(G, m_tot, a, xyz):
+    return _ellipsoidal_grad(xyz, 1.0, 1.0, lambda r: G * m_tot / (r * (r + a)))
+
+
+def hessian_jaffe(G, m_tot, a, xyz):
+    return _ellipsoidal_hess(xyz, 1.0, 1.0, lambda r: G * m_tot / (r * (r + a)),
+                             lambda r: -G * m_tot * (2 * r + a) / (r * (r + a)) ** 2)
+
+
+# Burkert (builtin/burkert.py:197-227): Phi' = G M(<r)/r^2, M(<r) = m/C [2 ln(1+x) + ln(1+x^2) - 2 atan x]
+BURKERT_C = 3 * np.log(2.0) - np.pi / 2
+
+
+def potential_burkert(G, m, rs, xyz):
+    x = _r_safe(xyz) / rs
+    xi = 1 / x
+    return -G * m / (rs * BURKERT_C) * (np.pi - 2 * (1 + xi) * np.arctan(x) + 2 * (1 + xi) * np.log1p(x)
+                                        - (1 - xi) * np.log1p(x**2))
+
+
+def _burkert_B(s):
+    """2 ln(1+s) + ln(1+s^2) - 2 atan(s); the terms cancel to O(s^3), so below s = 0.3 integrate the series of
+    B' = 4 s^2 (1 - s)/(1 - s^4) instead: B = 4 s^3 sum_n s^(4n) (1/(4n+3) - s/(4n+4)), n = 0..8
+    (an accuracy device shared by the C oracle and the kernels)."""
+    s = np.asarray(s, dtype=np.float64)
+    s4 = s**4
+    e = np.zeros_like(s)
+    for n in range(8, -1, -1):
+        e = e * s4 + (1.0 / (4 * n + 3) - s / (4 * n + 4))
+    return np.where(s < 0.3, 4.0 * s**3 * e, 2 * np.log1p(s) + np.log1p(s**2) - 2 * np.arctan(s))
+
+
+def _burkert_d1(G, m, rs):
+    return lambda r: G * m / BURKERT_C * _burkert_B(r / rs) / r**2
+
+
+def _burkert_d2(G, m, rs):
+    def f(r):
+        x = r / rs
+        return G * m / BURKERT_C * 4 * x**2 / ((1 + x) * (1 + x**2) * rs * r**2) - 2 * _burkert_d1(G, m, rs)(r) / r
+    return f
+
+
+def gradient_burkert(G, m, rs, xyz):
+    return _ellipsoidal_grad(xyz, 1.0, 1.0, _burkert_d1(G, m, rs))
+
+
+def hessian_burkert(G, m, rs, xyz):
+    return _ellipsoidal_hess(xyz, 1.0, 1.0, _burkert_d1(G, m, rs), _burkert_d2(G, m, rs))
+
+
+# StoneOstriker15 (builtin/stoneostriker15.py:150-160): Phi' = G M(<r)/r^2,
+# M(<r) = 2 M/(pi (r_h - r_c)) (r_h atan(r/r_h) - r_c atan(r/r_c))
+
+
+def potential_stone(G, m_tot, rc, rh, xyz):
+    r = _r_safe(xyz)
+    A = -2 * G * m_tot / (np.pi * (rh - rc))
+    return A * ((rh * np.arctan2(r, rh) - rc * np.arctan2(r, rc)) / r + 0.5 * np.log((r**2 + rh**2) / (r**2 + rc**2)))
+
+
+def _stone_T(r, rc, rh):
+    """r_h atan(r/r_h) - r_c atan(r/r_c); Taylor series (16 terms) below r = 0.3 r_c where the two terms cancel
+    to O(r^3).  Needs r_c < r_h (the reference's convention) for the series' convergence."""
+    r = np.asarray(r, dtype=np.float64)
+    uc, uh = (r / rc) ** 2, (r / rh) ** 2
+    acc = np.zeros_like(r)
+    pc, ph = np.ones_like(r), np.ones_like(r)
+    for k in range(1, 17):
+        pc, ph = pc * uc, ph * uh
+        term = (ph - pc) / (2 * k + 1)
+        acc = acc - term if k % 2 else acc + term
+    return np.where(r < 0.3 * rc, r * acc, rh * np.arctan2(r, rh) - rc * np.arctan2(r, rc))
+
+
+def _stone_d1(G, m_tot, rc, rh):
+    A = 2 * G * m_tot / (np.pi * (rh - rc))
+    return lambda r: A * _stone_T(r, rc, rh) / r**2
+
+
+def _stone_d2(G, m_tot, rc, rh):
+    A = 2 * G * m_tot / (np.pi * (rh - rc))
+    # r_h^2/(r^2+r_h^2) - r_c^2/(r^2+r_c^2) = r^2 (r_h^2 - r_c^2)/((r^2+r_h^2)(r^2+r_c^2)): no cancellation
+    return lambda r: A * (rh**2 - rc**2) / ((r**2 + rh**2) * (r**2 + rc**2)) - 2 * _stone_d1(G, m_tot, rc, rh)(r) / r
+
+
+def gradient_stone(G, m_tot, rc, rh, xyz):
+    return _ellipsoidal_grad(xyz, 1.0, 1.0, _stone_d1(G, m_tot, rc, rh))
+
+
+def hessian_stone(G, m_tot, rc, rh, xyz):
+    return _ellipsoidal_hess(xyz, 1.0, 1.0, _stone_d1(G, m_tot, rc, rh), _stone_d2(G, m_tot, rc, rh))
+
+
+# HarmonicOscillator (builtin/example.py:75-85): Phi = 1/2 sum (omega_i x_i)^2
+
+
+def potential_harmonic(G, wx, wy, wz, xyz):
+    w = np.array([wx, wy, wz])
+    return 0.5 * np.sum((w * xyz) ** 2, axis=-1)
+
+
+def gradient_harmonic(G, wx, wy, wz, xyz):
+    return np.array([wx, wy, wz]) ** 2 * xyz
+
+
+def hessian_harmonic(G, wx, wy, wz, xyz):
+    return np.broadcast_to(np.diag(np.array([wx, wy, wz]) ** 2), xyz.shape[:-1] + (3, 3)).copy()
+
+
+# HenonHeiles (builtin/example.py:159-176): Phi = (R^2/2 + coeff (x^2 y - y^3/3)) / timescale^2
+
+
+def potential_henon(G, coeff, ts, xyz):
+    x, y = xyz[..., 0], xyz[..., 1]
+    return ((x**2 + y**2) / 2 + coeff * (x**2 * y - y**3 / 3.0)) / ts**2
+
+
+def gradient_henon(G, coeff, ts, xyz):
+    x, y = xyz[..., 0], xyz[..., 1]
+    return np.stack([x + 2 * coeff * x * y, y + coeff * (x**2 - y**2), np.zeros_like(x)], axis=-1) / ts**2
+
+
+def hessian_henon(G, coeff, ts, xyz):
+    x, y = xyz[..., 0], xyz[..., 1]
+    H = np.zeros(xyz.shape[:-1] + (3, 3))
+    H[..., 0, 0] = 1 + 2 * coeff * y
+    H[..., 0, 1] = H[..., 1, 0] = 2 * coeff * x
+    H[..., 1, 1] = 1 - 2 * coeff * y
+    return H / ts**2
+
+
+_NEW = {KIND_TRIAXIAL_HERNQUIST: (potential_thern, gradient_thern, hessian_thern),
+        KIND_JAFFE: (potential_jaffe, gradient_jaffe, hessian_jaffe),
+        KIND_BURKERT: (potential_burkert, gradient_burkert, hessian_burkert),
+        KIND_STONE: (potential_stone, gradient_stone, hessian_stone),
+        KIND_HARMONIC: (potential_harmonic, gradient_harmonic, hessian_harmonic),
+        KIND_HENON_HEILES: (potential_henon, gradient_henon, hessian_henon)}
+
 _POT = {KIND_LOG: potential_log, KIND_ISOCHRONE: potential_iso, KIND_SATOH: potential_satoh, KIND_MN: potential_mn, KIND_HERNQUIST: potential_hernquist, KIND_NFW: potential_nfw, KIND_PLC: potential_plc}
 _GRAD = {KIND_LOG: gradient_log, KIND_ISOCHRONE: gradient_iso, KIND_SATOH: gradient_satoh, KIND_MN: gradient_mn, KIND_HERNQUIST: gradient_hernquist, KIND_NFW: gradient_nfw, KIND_PLC: gradient_plc}
 _HESS = {KIND_LOG: hessian_log, KIND_ISOCHRONE: hessian_iso, KIND_SATOH: hessian_satoh, KIND_MN: hessian_mn, KIND_HERNQUIST: hessian_hernquist, KIND_NFW: hessian_nfw, KIND_PLC: hessian_plc}
 
+
+for _k, (_p, _g, _h) in _NEW.items():
+    _POT[_k], _GRAD[_k], _HESS[_k] = _p, _g, _h
 
 # ----------------------------------------------------------------------------------------
 # composite evaluation, summed in component order (base_multi.py:39-82)

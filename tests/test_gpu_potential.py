@@ -47,6 +47,10 @@ def build_gp(m):
         return gp.LMJ09LogarithmicPotential(v * gp.KMS, rs, q1, q2, q3, np.deg2rad(ph))
     if kind == "LM10Potential":
         return gp.LM10Potential()
+    more = {"TriaxialHernquist": gp.TriaxialHernquistPotential, "Jaffe": gp.JaffePotential, "Burkert": gp.BurkertPotential,
+            "StoneOstriker15": gp.StoneOstriker15Potential, "HenonHeiles": gp.HenonHeilesPotential}
+    if kind in more:
+        return more[kind](*m["params"])
     cls = gp.MN3Sech2Potential if kind.endswith("Sech2") else gp.MN3ExponentialPotential
     return cls(*m["params"], positive_density=m["positive_density"])
 
@@ -66,7 +70,9 @@ def test_reference_kats_on_gpu(case):
     assert np.allclose(pot.gradient(x), case["gradient"], atol=1e-8)
     assert np.allclose(pot.acceleration(x), -np.array(case["gradient"]), atol=1e-8)
     assert np.allclose(pot.hessian(x), case["hessian"], atol=1e-8)
-    if case["density"] > 1.0:
+    if case["density"] is None:  # xfail in the reference (TriaxialHernquist)
+        pass
+    elif case["density"] > 1.0:
         assert np.isclose(pot.density(x), case["density"], atol=1e-8)
     else:  # vacuum / razor-thin disk: 4 pi G rho is the rounding noise of a cancelling trace
         assert abs(pot.laplacian(x)) < 1e-15
@@ -147,6 +153,57 @@ def test_lm10_and_further_kinds_bulk_and_orbits():
     assert (np.linalg.norm(sol.ys[0] - qr, axis=-1) / np.linalg.norm(qr, axis=-1)).max() < 1e-12
     orb = gd.evaluate_orbit(pot, (q0, p0), np.linspace(0.0, 500.0, 11))
     qd, pd, *_ = cref.integrate_dopri8(opot, q0, p0, 0.0, 500.0, np.linspace(0.0, 500.0, 11), rtol=1e-7, atol=1e-7)
+    assert np.median(np.abs(orb.q - qd).max(axis=(1, 2))) < 1e-5
+
+
+def test_radial_profile_kinds_bulk_and_orbits():
+    """TriaxialHernquist, Jaffe, Burkert, StoneOstriker15 (+ harmonic, Henon-Heiles, Null) through K1-K3, incl. the
+    small-radius series of Burkert / Stone-Ostriker (points down to r = 1e-4 r_s)."""
+    import galax_b200.dynamics as gd
+    from oracle import cref
+
+    xyz = points(6000, seed=12, lo=-4.0, hi=2.0)
+    singles = [
+        (gp.TriaxialHernquistPotential(1e12, 1.0, 1.1, 0.5), op.single(op.KIND_TRIAXIAL_HERNQUIST, 1e12, 1.0, 1.1, 0.5)),
+        (gp.JaffePotential(1e12, 1.0), op.single(op.KIND_JAFFE, 1e12, 1.0)),
+        (gp.BurkertPotential(1e12, 1.0), op.single(op.KIND_BURKERT, 1e12, 1.0)),
+        (gp.StoneOstriker15Potential(1e12, 1.0, 10.0), op.single(op.KIND_STONE, 1e12, 1.0, 10.0)),
+        (gp.HenonHeilesPotential(0.3, 2.0), op.single(op.KIND_HENON_HEILES, 0.3, 2.0)),
+        (gp.HarmonicOscillatorPotential([0.1, 0.2, 0.3]), op.single(op.KIND_HARMONIC, 0.1, 0.2, 0.3)),
+    ]
+    for pot, opot in singles:
+        go, Ho, phio = op.gradient(opot, xyz), op.hessian(opot, xyz), op.potential(opot, xyz)
+        gn = np.linalg.norm(go, axis=1, keepdims=True) + 1e-300
+        assert (np.abs(pot.gradient(xyz) - go) / gn).max() < 2e-14, type(pot).__name__
+        assert (np.abs(pot.hessian(xyz) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 5e-13, type(pot).__name__
+        # (Henon-Heiles changes sign: an absolute term covers the zero crossings)
+        assert np.all(np.abs(pot.potential(xyz) - phio) <= 1e-13 * np.abs(phio) + 1e-16 * np.abs(phio).max()), type(pot).__name__
+    null = gp.NullPotential()
+    assert np.all(null.gradient(xyz[:10]) == 0) and np.all(null.potential(xyz[:10]) == 0) and np.all(null.hessian(xyz[:10]) == 0)
+    ho = gp.HarmonicOscillatorPotential(2.0)
+    assert np.isclose(ho.density(xyz[:3]), 4.0 / (4 * np.pi * ho.G)).all()  # the reference's own _density (example.py:86-98)
+    e = KATS["extra"][-1]
+    ho = gp.HarmonicOscillatorPotential(e["omega_per_myr"])
+    assert np.allclose(ho.gradient(np.array(KATS["x"])), e["gradient"], rtol=1e-8)
+    assert np.isclose(ho.potential(np.array(KATS["x"])), e["potential"], rtol=1e-8)
+    assert np.isclose(ho.density(np.array(KATS["x"])), e["density_reference_quirk"], rtol=1e-8)
+    # a dwarf-galaxy-like composite: Burkert halo + Jaffe nucleus + triaxial Hernquist bulge, orbits through K2 / K3
+    mix = gp.CompositePotential(halo=gp.BurkertPotential(5e10, 3.0), nuc=gp.JaffePotential(1e9, 0.3),
+                                bulge=gp.TriaxialHernquistPotential(5e9, 0.8, 0.9, 0.7), so=gp.StoneOstriker15Potential(1e10, 0.5, 20.0))
+    omix = op.Potential((op.Component(op.KIND_BURKERT, (5e10, 3.0)), op.Component(op.KIND_JAFFE, (1e9, 0.3)),
+                         op.Component(op.KIND_TRIAXIAL_HERNQUIST, (5e9, 0.8, 0.9, 0.7)), op.Component(op.KIND_STONE, (1e10, 0.5, 20.0))))
+    rng = np.random.default_rng(6)
+    q0 = rng.normal(size=(128, 3)) * 3.0
+    vc = np.sqrt(np.linalg.norm(op.gradient(omix, q0), axis=1) * np.linalg.norm(q0, axis=1))
+    d = rng.normal(size=(128, 3)); d -= (d * q0).sum(1, keepdims=True) * q0 / (q0 * q0).sum(1, keepdims=True)
+    p0 = d / np.linalg.norm(d, axis=1, keepdims=True) * (vc * rng.uniform(0.7, 1.0, 128))[:, None]
+    sie = gd.OrbitSolver(solver=gd.SemiImplicitEuler(), stepsize_controller=gd.ConstantStepSize(), max_steps=None)
+    sol = sie.solve(mix, (q0, p0), 0.0, 300.0, dt0=0.05)
+    qr, pr, st, n = cref.integrate_fixed(omix, q0, p0, 0.0, 300.0, 0.05, [300.0])
+    rel = np.linalg.norm(sol.ys[0] - qr, axis=-1) / np.linalg.norm(qr, axis=-1)
+    assert np.median(rel) < 1e-13 and np.mean(rel < 1e-11) > 0.95
+    orb = gd.evaluate_orbit(mix, (q0, p0), np.linspace(0.0, 300.0, 7))
+    qd, pd, *_ = cref.integrate_dopri8(omix, q0, p0, 0.0, 300.0, np.linspace(0.0, 300.0, 7), rtol=1e-7, atol=1e-7)
     assert np.median(np.abs(orb.q - qd).max(axis=(1, 2))) < 1e-5
 
 

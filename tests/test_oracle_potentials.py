@@ -36,6 +36,10 @@ def build(m):
         return op.single(op.KIND_LOG, v * op.KMS, rs, q1, q2, q3, np.deg2rad(ph))
     if kind == "LM10Potential":
         return op.lm10_potential()
+    more = {"TriaxialHernquist": op.KIND_TRIAXIAL_HERNQUIST, "Jaffe": op.KIND_JAFFE, "Burkert": op.KIND_BURKERT,
+            "StoneOstriker15": op.KIND_STONE, "HenonHeiles": op.KIND_HENON_HEILES}
+    if kind in more:
+        return op.single(more[kind], *m["params"])
     return op.mn3_potential(*m["params"], sech2=kind.endswith("Sech2"), positive_density=m["positive_density"])
 
 
@@ -61,7 +65,9 @@ def test_reference_kats(case, impl):
     assert np.allclose(out["grad"], case["gradient"], atol=1e-8)
     assert np.allclose(out["hess"], case["hessian"], atol=1e-8)
     tr = np.trace(out["hess"])
-    if case["density"] > 1.0:
+    if case["density"] is None:  # the reference marks this density test xfail (TriaxialHernquist)
+        pass
+    elif case["density"] > 1.0:
         assert np.isclose(tr / (4 * np.pi * p.G), case["density"], atol=1e-8)
     else:  # vacuum (Kepler) / razor-thin disk (Kuzmin): the trace cancels to rounding noise
         assert abs(tr) < 1e-15 * np.abs(out["hess"]).max() * 50
@@ -186,3 +192,51 @@ def test_mn3_parameters_match_survey():
     assert np.allclose([c.params[1] for c in comps[:3]], [1.5259432, 6.78276444, 5.89479962], rtol=1e-8)
     assert comps[0].params[2] == pytest.approx(0.20663742603550295, rel=1e-15)
     assert comps[5].params[1] == 68.8867 * 0.001
+
+
+def _mp_radial_kinds():
+    import mpmath as mp
+
+    G = op.G_GALACTIC
+
+    def burkert(x, y, z, m=1e12, rs=1.0):
+        s = mp.sqrt(x * x + y * y + z * z) / rs
+        C = 3 * mp.log(2) - mp.pi / 2
+        return -G * m / (rs * C) * (mp.pi - 2 * (1 + 1 / s) * mp.atan(s) + 2 * (1 + 1 / s) * mp.log1p(s)
+                                    - (1 - 1 / s) * mp.log1p(s * s))
+
+    def stone(x, y, z, m=1e12, rc=1.0, rh=10.0):
+        r = mp.sqrt(x * x + y * y + z * z)
+        A = -2 * G * m / (mp.pi * (rh - rc))
+        return A * ((rh * mp.atan2(r, rh) - rc * mp.atan2(r, rc)) / r + mp.log((r * r + rh * rh) / (r * r + rc * rc)) / 2)
+
+    def jaffe(x, y, z, m=1e12, a=1.0):
+        return -G * m / a * mp.log(1 + a / mp.sqrt(x * x + y * y + z * z))
+
+    def thern(x, y, z, m=1e12, c=1.0, q1=1.1, q2=0.5):
+        return -G * m / (mp.sqrt(x * x + (y / q1) ** 2 + (z / q2) ** 2) + c)
+
+    return [(burkert, op.single(op.KIND_BURKERT, 1e12, 1.0)), (stone, op.single(op.KIND_STONE, 1e12, 1.0, 10.0)),
+            (jaffe, op.single(op.KIND_JAFFE, 1e12, 1.0)), (thern, op.single(op.KIND_TRIAXIAL_HERNQUIST, 1e12, 1.0, 1.1, 0.5))]
+
+
+def test_radial_profile_kinds_vs_mpmath_differentiation():
+    """Hand-derived F'/m and F'' of the further kinds (incl. the small-radius series of Burkert and Stone-Ostriker)
+    against 40-digit differentiation of the reference's *potential* formulas (burkert.py:197-227,
+    stoneostriker15.py:150-160, jaffe.py:50-60, hernquist.py:160-176)."""
+    import mpmath as mp
+
+    mp.mp.dps = 40
+    pts = [(1.0, 2.0, 3.0), (0.01, 0.02, -0.005), (0.05, -0.03, 0.02), (30.0, -10.0, 5.0), (1e-3, 2e-4, -5e-4)]
+    for f, pot in _mp_radial_kinds():
+        for pt in pts:
+            g = np.array([float(mp.diff(f, pt, n)) for n in [(1, 0, 0), (0, 1, 0), (0, 0, 1)]])
+            H = np.array([[float(mp.diff(f, pt, tuple(int(i == a) + int(i == b) for i in range(3)))) for b in range(3)]
+                          for a in range(3)])
+            x = np.array([pt])
+            c = cref.potential_eval(pot, x, ("phi", "grad", "hess"))
+            for got_g, got_H, got_phi in ((op.gradient(pot, x)[0], op.hessian(pot, x)[0], op.potential(pot, x)[0]),
+                                          (c["grad"][0], c["hess"][0], c["phi"][0])):
+                assert np.abs(got_g - g).max() < 5e-15 * np.abs(g).max()
+                assert np.abs(got_H - H).max() < 5e-15 * np.abs(H).max()
+                assert abs(got_phi - float(f(*pt))) < 1e-14 * abs(got_phi)

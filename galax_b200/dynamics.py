@@ -565,7 +565,14 @@ class ChenStreamDF(AbstractStreamDF):
     )
 
     def _draws(self, rng, M):
-        return np.random.default_rng(rng).multivariate_normal(self.mean, self.cov, size=M, method="svd")
+        """An integer seed (or raw key data) follows ``jr.multivariate_normal(jr.key(seed), mean, cov, (M,),
+        method="svd")`` of df/chen24.py:89-91 (threefry normals + LAPACK SVD, see jaxrandom.multivariate_normal_svd);
+        a ``numpy.random.Generator`` draws from numpy's stream."""
+        if isinstance(rng, np.random.Generator):
+            return rng.multivariate_normal(self.mean, self.cov, size=M, method="svd")
+        from . import jaxrandom
+
+        return jaxrandom.chen_draws(rng, M)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -581,8 +588,8 @@ class MockStreamGenerator:
         """-> (MockStream, final progenitor PhaseSpaceCoordinate).
 
         ``rng``: an integer seed (Fardal: reproduces the reference's ``jr.key(seed)`` draws through the threefry
-        restatement in ``galax_b200/jaxrandom.py``; Chen: numpy's stream, jax's SVD-based multivariate normal is not
-        reproduced), a ``numpy.random.Generator``, or the draws themselves (Fardal: (4, M) standard normals; Chen:
+        restatement in ``galax_b200/jaxrandom.py``; Chen: the same threefry normals through numpy's LAPACK SVD), a
+        ``numpy.random.Generator``, or the draws themselves (Fardal: (4, M) standard normals; Chen:
         (M, 6) samples).  ``vmapped`` is accepted for signature parity and ignored: every particle is an independent
         lane of the work queue.
         """

@@ -132,3 +132,26 @@ def fardal_draws(seed_or_key, M: int) -> np.ndarray:
     k = key(seed_or_key) if np.ndim(seed_or_key) == 0 else np.asarray(seed_or_key, dtype=np.uint32)
     ks = split(k, 4)
     return np.stack([normal(ks[i], (M,)) for i in range(4)])
+
+
+def multivariate_normal_svd(seed_or_key, mean, cov, shape) -> np.ndarray:
+    """``jax.random.multivariate_normal(key, mean, cov, shape, method="svd")``: ``(u, s, _) = svd(cov)``,
+    ``factor = u * sqrt(s)``, ``mean + factor @ normal(key, shape + (d,))``.
+
+    The singular vectors' signs and order are the SVD routine's choice: XLA:CPU and numpy both call LAPACK's
+    ``gesdd``, so this reproduces the reference on CPU as far as the two LAPACK builds agree (XLA:GPU uses a Jacobi
+    solver with its own conventions -- the reference's own draws differ between its backends).  Unverified offline.
+    """
+    k = key(seed_or_key) if np.ndim(seed_or_key) == 0 else np.asarray(seed_or_key, dtype=np.uint32)
+    mean = np.asarray(mean, dtype=np.float64)
+    u, s, _ = np.linalg.svd(np.asarray(cov, dtype=np.float64))
+    factor = u * np.sqrt(s)[None, :]
+    z = normal(k, tuple(shape) + mean.shape[-1:])
+    return mean + np.einsum("ij,...j->...i", factor, z)
+
+
+def chen_draws(seed_or_key, M: int) -> np.ndarray:
+    """The ``(M, 6)`` samples of ``ChenStreamDF._sample`` (df/chen24.py:89-91) for ``jr.key(seed)``."""
+    from .dynamics import ChenStreamDF
+
+    return multivariate_normal_svd(seed_or_key, ChenStreamDF.mean, ChenStreamDF.cov, (M,))

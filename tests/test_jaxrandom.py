@@ -62,3 +62,22 @@ def test_split_chain_and_vectorised_draws_are_consistent():
     assert np.allclose(one[:, 0], jr.fardal_draws(sub[0], 1)[:, 0])
     d = jr.fardal_draws(7, 100_000)
     assert abs(d.mean()) < 0.01 and abs(d.std() - 1) < 0.01 and np.isfinite(d).all()
+
+
+def test_chen_multivariate_normal_svd_draws():
+    """df/chen24.py:89-91: mean + (u sqrt(s)) z with threefry normals; the zero-variance row (Dv/v_esc == 1) must come
+    out exactly, and the sample moments must reproduce the 6-D Gaussian (incl. the Dr-alpha covariance -4.9)."""
+    from galax_b200 import jaxrandom as jr
+    from galax_b200.dynamics import ChenStreamDF
+
+    x = jr.chen_draws(7, 200_000)
+    assert x.shape == (200_000, 6)
+    assert np.allclose(x[:, 3], 1.0, atol=1e-12)
+    assert np.allclose(x.mean(0), ChenStreamDF.mean, atol=5 * np.sqrt(np.diag(ChenStreamDF.cov) / 200_000) + 1e-12)
+    C = np.cov(x.T)
+    assert np.allclose(C, ChenStreamDF.cov, atol=0.02 * np.sqrt(np.outer(np.diag(ChenStreamDF.cov), np.diag(ChenStreamDF.cov))) + 1e-9)
+    assert np.array_equal(x, jr.chen_draws(7, 200_000)) and not np.array_equal(x[:10], jr.chen_draws(8, 10))
+    # the underlying normals are jax's: the first row is factor @ normal(key(7), (M, 6))[0]
+    u, s, _ = np.linalg.svd(ChenStreamDF.cov)
+    z = jr.normal(jr.key(7), (200_000, 6))
+    assert np.allclose(x[0], ChenStreamDF.mean + (u * np.sqrt(s)) @ z[0], atol=1e-12)

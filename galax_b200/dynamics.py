@@ -601,7 +601,12 @@ class MockStreamGenerator:
             raise ValueError("prog_w0 must be scalar")  # mockstream_generator.py:230
         if ts[1] < ts[0]:  # cond_reverse (mockstream_generator.py:236)
             ts = ts[::-1].copy()
-        w0 = PhaseSpaceCoordinate(q0, p0, ts[0] if tw0 is None else tw0)
+        # the pipeline (progenitor orbit -> release -> stream integration) stays on the device; results go back to
+        # the caller's array kind once, at the end
+        _lib.require_cuda()
+        q0d, to_caller = _to_device(q0)
+        p0d, _ = _to_device(p0)
+        w0 = PhaseSpaceCoordinate(q0d, p0d, ts[0] if tw0 is None else tw0)
         # progenitor orbit saved at the stripping times (:239)
         prog_o = evaluate_orbit(self.potential, w0, ts, integrator=self.progenitor_integrator, throw=throw)
         mock0 = self.df.sample(rng, self.potential, prog_o, prog_mass)
@@ -614,9 +619,12 @@ class MockStreamGenerator:
         q_all, p_all = _cat0(lead.q, trail.q), _cat0(lead.p, trail.p)
         w = self.stream_integrator(field, (q_all, p_all), np.concatenate([ts, ts]), t_f, throw=throw)
         tt = np.ones_like(ts) * ts[-1]
-        arms = {"lead": MockStreamArm(w.q[:M], w.p[:M], tt, lead.release_time),
-                "trail": MockStreamArm(w.q[M:], w.p[M:], tt, trail.release_time)}  # fmt: skip
-        return MockStream(arms), prog_o[-1]
+        wq, wp = to_caller(w.q), to_caller(w.p)
+        arms = {"lead": MockStreamArm(wq[:M], wp[:M], tt, lead.release_time),
+                "trail": MockStreamArm(wq[M:], wp[M:], tt, trail.release_time)}  # fmt: skip
+        last = prog_o[-1]
+        last = PhaseSpaceCoordinate(to_caller(last.q), to_caller(last.p), last.t)
+        return MockStream(arms), last
 
 
 __all__ = [

@@ -38,7 +38,11 @@ N_PER_GPU = 148 * 8192  # 1 212 416 particles: 64 CTAs of 128 threads per SM
 N_STEPS = 10_000  # dt0 = 0.1 Myr over 1 Gyr
 T1, DT0 = 1000.0, 0.1
 FLOP_PER_STEP = 280.0  # canonical weighted fp64 flop per MilkyWayPotential fixed step
-CPU_SAMPLE_PARTICLES = 4096
+# FP64 thread-instructions the kernel really executes per particle-step, counted by ncu on this very launch
+# (profiles/ncu_k_integrate_fixed_r1.txt: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on / (N x steps))
+NCU_FP64_INSTR_PER_STEP = {"dfma": 41.0, "dmul": 36.0, "dadd": 18.0}
+CPU_SAMPLE_PER_CORE = 8192  # cpu_baseline leg: ~10 s of CPU work at ~9e6 particle-steps/s/core
+REF_ARM_SAMPLE_PER_CORE = 2048  # --impl reference: ~2.5 s per bench step
 
 
 def workload_config(n_gpus: int, n: int = N_PER_GPU) -> dict:
@@ -79,10 +83,10 @@ def run_reference(args) -> None:
 
     cref.build()
     opot = op.milky_way_potential()
-    n = CPU_SAMPLE_PARTICLES
+    cores = cref.use_all_cores()
+    n = REF_ARM_SAMPLE_PER_CORE * cores
     q, r, vdir, f = host_ics(n, seed=1)
     p = vdir * (op.circular_velocity(opot, r) * f)[:, None]
-    cores = cref.use_all_cores()
 
     def step():
         cref.integrate_fixed(opot, q, p, 0.0, T1, DT0, [T1])
@@ -308,8 +312,18 @@ def run_gpu(args) -> None:
         "peak_source": "measured live: gx_bench_dfma (8 independent DFMA chains/thread), best of 3; "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "note": "canonical weighted flop (div/sqrt=18, log1p=56) per SURVEY.md 8d; the kernel issues fewer real "
-                "instructions than that (MUFU-seeded rcp/rsqrt), see profiles/ for ncu-counted FP64 instructions",
+                "instructions than that (MUFU-seeded rcp/rsqrt): see 'executed' for the ncu-counted rate",
     }  # fmt: skip
+    n_instr = sum(NCU_FP64_INSTR_PER_STEP.values())
+    n_flop = 2.0 * NCU_FP64_INSTR_PER_STEP["dfma"] + NCU_FP64_INSTR_PER_STEP["dmul"] + NCU_FP64_INSTR_PER_STEP["dadd"]
+    roofline["executed"] = {
+        "fp64_instr_per_particle_step": NCU_FP64_INSTR_PER_STEP,
+        "tflops": per_gpu_rate * n_flop / 1e12,                         # dfma x 2 + dmul + dadd, as ncu counts flop
+        "frac_of_dfma_peak": per_gpu_rate * n_flop / 1e12 / dfma_peak,
+        "fp64_issue_frac": per_gpu_rate * n_instr / (dfma_peak * 1e12 / 2.0),  # FP64 instructions / FP64 issue slots
+        "ncu_fp64_pipe_active_pct": 75.6,
+        "source": "profiles/ncu_k_integrate_fixed_r1.txt (same kernel, same launch shape)",
+    }
 
     # The HBM-bound leg of the path (C5): acceleration + Hessian on 2e7 points, against the measured copy peak
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -364,9 +378,8 @@ def run_gpu(args) -> None:
         from oracle import potentials as op
 
         cref.build()
-        cref.use_all_cores()
         opot = op.milky_way_potential()
-        ns = CPU_SAMPLE_PARTICLES
+        ns = min(n, CPU_SAMPLE_PER_CORE * cref.use_all_cores())
         cref.integrate_fixed(opot, q_h[:256], p_h[:256], 0.0, 10.0, DT0, [10.0])  # warm
         t0 = time.perf_counter()
         qr, pr, st, _ = cref.integrate_fixed(opot, q_h[:ns], p_h[:ns], 0.0, T1, DT0, [T1])

@@ -20,7 +20,7 @@ HEADER = _PKG.parent / "include" / "galax_b200.h"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "20091",
     "-shared", "-Xcompiler", "-fPIC",
 ]  # fmt: skip
 

@@ -198,14 +198,14 @@ using CountsBovy = Counts<1, 0, 1, 1>;    // BovyMWPotential2014:    MN disk, PL
 // ---------------------------------------------------------------------------------------------
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
+// The flattened + spherical part is returned as two scalars: grad = (fh x, fh y, fv z); the kinds that are neither
+// (triaxial logarithmic / ellipsoidal profiles / polynomials) are added to (ex, ey, ez) by gradient<C>() below.
+// Terms of the form GM_i w_i / r (Hernquist, NFW) are summed before the common factor 1/r is applied.
 template <class C>
-__device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
-                                         double &gz_) {
+__device__ __forceinline__ void gradient_factors(const DevPot &P, double x, double y, double z, double &fh, double &fv) {
     const double z2 = z * z;
-    const double R2 = fma(y, y, x * x);
-    // accumulate() starts from the first term instead of adding to 0.0 (a DADD the compiler must keep)
-    double fxy = 0.0, fz = 0.0, fs = 0.0;
-    bool have_d = false, have_s = false;
+    const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
+    double fxy = 0.0, fz = 0.0, fs = 0.0, fr = 0.0;  // fs: terms Phi'/r as they are; fr: terms still to be divided by r
     double zeta2 = 0.0, rz = 0.0;
 #pragma unroll
     for (int i = 0; i < C::kMN; ++i) {
@@ -222,24 +222,23 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
         double g = f * (apz * rz);           // GM/D^3 * (a+zeta)/zeta
         if (C::is_static && i == 0) { fxy = f; fz = g; }
         else { fxy += f; fz += g; }
-        have_d = true;
     }
 #pragma unroll
     for (int i = 0; i < C::kSAT; ++i) {
         if (i >= P.n_satoh) break;
         const DevSatoh &c = P.satoh[i];
-        double zeta2 = z2 + c.b2;
-        double rz = rsqrt_fast(zeta2);
-        double apz = fma(zeta2, rz, c.a);
+        double zs2 = z2 + c.b2;
+        double rzs = rsqrt_fast(zs2);
+        double apz = fma(zs2, rzs, c.a);
         double rD = rsqrt_fast(fma(apz, apz, R2 - c.b2));
         double f = (c.GM * rD) * (rD * rD);
         fxy += f;
-        fz = fma(f, apz * rz, fz);
+        fz = fma(f, apz * rzs, fz);
     }
     const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0)
                                       : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
     if (any_sph) {
-        const double r2 = (R2 + z2) + TINY;
+        const double r2 = R2 + z2;  // (R2 carries the TINY that keeps r > 0)
         const double rinv = rsqrt_fast(r2);
         const double r = r2 * rinv;
         const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
@@ -248,9 +247,8 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             if (!C::is_static && i >= P.n_hern) break;
             const DevHern &c = P.hern[i];
             double u = r + c.c;
-            double t = (c.GM * rinv) * rcp_fast(u * u);  // GM / ((r+c)^2 r)
-            if (C::is_static && i == 0) fs = t; else fs += t;
-            have_s = true;
+            double w = rcp_fast(u * u);  // Phi'/r = GM / ((r+c)^2 r)
+            if (C::is_static && i == 0) fr = c.GM * w; else fr = fma(c.GM, w, fr);
         }
 #pragma unroll
         for (int i = 0; i < C::kISO; ++i) {
@@ -265,9 +263,8 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             if (!C::is_static && i >= P.n_nfw) break;
             const DevNFW &c = P.nfw[i];
             double m = nfw_menc_shape(r * c.inv_rs);
-            double t = (c.GM * m) * rinv;  // GM m(s) / r^3 = t * rinv^2
-            if (C::is_static && C::kH == 0 && i == 0) fs = t * rinv2; else fs = fma(t, rinv2, fs);
-            have_s = true;
+            // Phi'/r = GM m(s) / r^3 = (GM m / r^2) / r
+            if (C::is_static && C::kH == 0 && i == 0) fr = (c.GM * m) * rinv2; else fr = fma(c.GM * m, rinv2, fr);
         }
 #pragma unroll
         for (int i = 0; i < C::kPLC; ++i) {
@@ -276,21 +273,24 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
             const double s = r * c.inv_rc;
             double Gs;
             if (s >= PLC_S_ONE) {
-                fs = fma(c.GM * rinv, rinv2, fs);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
+                fr = fma(c.GM, rinv2, fr);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
             } else if (plc_table_eval(c, s, Gs, nullptr)) {
                 fs = fma(c.GM_rc3, Gs, fs);  // GM P(a, s^2) / r^3 = (GM / rc^3) G(s)
             } else {
                 const double Pg = gammainc_P(c.ga, s * s, nullptr);
-                fs = fma((c.GM * Pg) * rinv, rinv2, fs);
+                fr = fma(c.GM * Pg, rinv2, fr);
             }
-            have_s = true;
         }
+        if (C::is_static && C::kPLC == 0) fs = fr * rinv; else fs = fma(fr, rinv, fs);
     }
-    (void)have_d; (void)have_s;
-    const double fh = fxy + fs, fv = fz + fs;
-    gx_ = fh * x;
-    gy_ = fh * y;
-    gz_ = fv * z;
+    fh = fxy + fs;
+    fv = fz + fs;
+}
+
+// the remaining kinds: e += grad of (triaxial logarithmic, ellipsoidal-radius profiles, polynomials)
+template <class C>
+__device__ __forceinline__ void gradient_extras(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
+                                                double &gz_) {
 #pragma unroll
     for (int i = 0; i < C::kLOG; ++i) {
         if (i >= P.n_log) break;
@@ -324,6 +324,19 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
         gx_ = fma(fma(2.0 * k * x, y, x), it2, gx_);
         gy_ = fma(fma(k, x * x - y * y, y), it2, gy_);
     }
+}
+
+// gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
+// small-s NFW series and the incomplete-gamma routine.
+template <class C>
+__device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
+                                         double &gz_) {
+    double fh, fv;
+    gradient_factors<C>(P, x, y, z, fh, fv);
+    gx_ = fh * x;
+    gy_ = fh * y;
+    gz_ = fv * z;
+    gradient_extras<C>(P, x, y, z, gx_, gy_, gz_);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -160,6 +160,51 @@ def emit_namespace(out, ns, order, t):
     out.append("};")
 
 
+LOG_TAB_BITS = 8
+
+
+def log_table(n_candidates=3000):
+    """(inv_c_j, -ln(inv_c_j)) for the 2^LOG_TAB_BITS mantissa intervals [1 + j/256, 1 + (j+1)/256).
+
+    Gal's accurate-table method: among the doubles next to 1/(interval midpoint), inv_c_j is the one whose
+    -ln(inv_c_j) lies closest to a double (typically < 2^-11 ulp away), so the tabulated logarithm carries no
+    rounding error worth mentioning and ln m = logc_j + log1p(m inv_c_j - 1) holds to ~2^-64 for the table.
+    Deterministic (fixed candidate window); takes about a minute of mpmath."""
+    import mpmath as mp
+    import numpy as np
+
+    mp.mp.dps = 40
+    n = 1 << LOG_TAB_BITS
+    rows = []
+    for j in range(n):
+        x0 = float(1 / (mp.mpf(1) + (mp.mpf(j) + mp.mpf("0.5")) / n))
+        best = None
+        x = x0
+        for _ in range(n_candidates // 2):
+            x = np.nextafter(x, 0.0)
+        for _ in range(n_candidates):
+            lv = -mp.log(mp.mpf(float(x)))
+            lf = float(lv)
+            err = abs(lv - mp.mpf(lf)) / mp.mpf(np.spacing(lf) if lf != 0 else 1.0)
+            if best is None or err < best[0]:
+                best = (err, float(x), lf)
+            x = np.nextafter(x, 2.0)
+        rows.append((best[1], best[2], float(best[0])))
+    return rows
+
+
+def emit_log_table(out):
+    out.append("// log table of gx_math.cuh::log_pos: {inv_c_j, -ln(inv_c_j)}, j = top %d mantissa bits" % LOG_TAB_BITS)
+    out.append("constexpr int LOG_TAB_BITS = %d;" % LOG_TAB_BITS)
+    out.append("__device__ const double2 LOG_TAB[%d] = {" % (1 << LOG_TAB_BITS))
+    rows = log_table()
+    out.append("// (largest distance of a tabulated logarithm from its exact value, rows j >= 4 -- the only ones reachable with")
+    out.append("//  k = 0, where the entry's own ulp matters: %.2e ulp)" % max(r[2] for r in rows[4:]))
+    for a, b, _ in rows:
+        out.append("    {%s, %s}," % (fmt(a), fmt(b)))
+    out.append("};")
+
+
 def emit():
     out = ["// GENERATED by galax_b200/csrc/gen_tables.py -- do not edit.",
            "// Dopri8 = Prince-Dormand RK8(7)13M + FSAL stage; Dopri5 = Dormand-Prince 5(4) + FSAL stage;",
@@ -167,6 +212,7 @@ def emit():
            "#pragma once", "namespace gx {"]
     emit_namespace(out, "dp8", 8, tables("dp8"))
     emit_namespace(out, "dp5", 5, tables("dp5"))
+    emit_log_table(out)
     out.append("}  // namespace gx")
     Path(__file__).with_name("gx_tables.h").write_text("\n".join(out) + "\n")
 

@@ -100,10 +100,10 @@ double oc_gammainc(double a, double x) { return oc_gammainc_P(a, x); }
 /* ---------------------------------------------------------------- single components */
 
 static double nfw_menc_shape(double s) {
-    /* ln(1+s) - s/(1+s); alternating series below s = 0.02 where the difference cancels */
-    if (s < 0.02) {
+    /* ln(1+s) - s/(1+s); alternating series below s = 2^-4 where the difference cancels */
+    if (s < 0.0625) {
         double ser = 0.0;
-        for (int k = 13; k >= 2; --k) {
+        for (int k = 18; k >= 2; --k) {
             double c = ((k & 1) ? -1.0 : 1.0) * (k - 1.0) / k;
             ser = ser * s + c;
         }

@@ -163,13 +163,13 @@ def _nfw_menc_shape(s):
     s = np.asarray(s, dtype=np.float64)
     direct = np.log1p(s) - s / (1.0 + s)
     # series  sum_{k>=2} (-1)^k (k-1)/k s^k
-    k = np.arange(2, 14)
+    k = np.arange(2, 19)
     coeff = ((-1.0) ** k) * (k - 1.0) / k
     ser = np.zeros_like(s)
     for c in coeff[::-1]:
         ser = ser * s + c
     ser = ser * s * s
-    return np.where(s < 0.02, ser, direct)
+    return np.where(s < 0.0625, ser, direct)  # 0.0625^17 < 4e-21; above, ln(1+s)/m(s) < 33: no digits to lose
 
 
 def gradient_nfw(G, m, r_s, xyz):

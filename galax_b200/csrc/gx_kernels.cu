@@ -164,7 +164,8 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool u
         if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0 && D.mn[0].b2 == D.mn[1].b2 &&
             D.mn[0].b2 == D.mn[2].b2)
             model = MODEL_MW2022;  // CountsMW2022 evaluates sqrt(z^2 + b^2) once: needs one b (an MN3 disk)
-        if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1) model = MODEL_BOVY;
+        if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1 && D.plc[0].tab != nullptr)
+            model = MODEL_BOVY;  // (the integrators stage the bulge's force table in shared memory)
     }
     return 0;
 }
@@ -366,6 +367,8 @@ __device__ __forceinline__ bool finite3(double a, double b, double c) {
 #endif
 template <class C, int SCHEME, bool FWD>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
+    constexpr bool STAGED = C::is_static && C::kPLC > 0;  // PowerLawCutoff table in shared memory (Bovy)
+    plc_stage<C>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     // integrate in tau = dir * t (diffrax flips the sign of time the same way for t1 < t0)
@@ -396,14 +399,14 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                gradient_factors<C>(P, nqx, nqy, nqz, fh, fv);
+                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
                 npy = fma(fhh, nqy, py);
                 npz = fma(fvh, nqz, pz);
                 gx_ = gy_ = gz_ = 0.0;
             } else {
-                gradient<C>(P, nqx, nqy, nqz, gx_, gy_, gz_);
+                gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_);
                 npx = fma(-gx_, hs, px);
                 npy = fma(-gy_, hs, py);
                 npz = fma(-gz_, hs, pz);
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqx = __dadd_rn(qx, __dmul_rn(px, hs));
             nqy = __dadd_rn(qy, __dmul_rn(py, hs));
             nqz = __dadd_rn(qz, __dmul_rn(pz, hs));
-            gradient<C>(P, nqx, nqy, nqz, gx_, gy_, gz_);
+            gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_);
             npx = __dadd_rn(px, __dmul_rn(-gx_, hs));
             npy = __dadd_rn(py, __dmul_rn(-gy_, hs));
             npz = __dadd_rn(pz, __dmul_rn(-gz_, hs));
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         } else {
             const double hm = tnext - tm;
             const double hh = FWD ? hm : -hm;
-            gradient<C>(P, qx, qy, qz, gx_, gy_, gz_);
+            gradient<C, STAGED>(P, qx, qy, qz, gx_, gy_, gz_);
             nqx = __dadd_rn(mqx, __dmul_rn(px, hh));
             nqy = __dadd_rn(mqy, __dmul_rn(py, hh));
             nqz = __dadd_rn(mqz, __dmul_rn(pz, hh));
@@ -515,7 +518,7 @@ __device__ __forceinline__ DevPot *pot_smem() {
 template <class C>
 __device__ __noinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az) {
     double g0, g1, g2;
-    gradient<C>(*pot_smem<C>(), x, y, z, g0, g1, g2);
+    gradient<C, (C::is_static && C::kPLC > 0)>(*pot_smem<C>(), x, y, z, g0, g1, g2);
     ax = -g0; ay = -g1; az = -g2;
 }
 
@@ -570,6 +573,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         for (int w = threadIdx.x; w < (int)(sizeof(DevPot) / sizeof(double)); w += blockDim.x) dst[w] = src[w];
         __syncthreads();
     }
+    plc_stage<C>(P);  // (Bovy) the PowerLawCutoff table, read by accel_call()
     const unsigned FULL = 0xffffffffu;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const double NANV = __longlong_as_double(0x7ff8000000000000LL);

@@ -45,8 +45,11 @@ constexpr double PLC_S_ONE = 8.0;  // = 2^PLC_E_HI: s^2 = 64 > xcut (<= 41 for e
 struct DevPLC { double GM, inv_rc, tail, GM_rc3; const double *tab; GammaTab ga, ga2; };
 
 // G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
-__device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double &G, double *dG) {
-    if (c.tab == nullptr) return false;
+// SMEM: the table was staged into shared memory with PLC_STRIDE doubles per interval (plc_stage below).
+constexpr int PLC_STRIDE = PLC_DEG + 2;  // 15: odd, so the intervals of neighbouring lanes fall into different banks
+template <bool SMEM>
+__device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, double &G, double *dG) {
+    if (tab == nullptr) return false;
     const int hi = __double2hiint(s);
     const int e = ((hi >> 20) & 0x7ff) - 1023;
     if (e < PLC_E_LO || e >= PLC_E_HI) return false;
@@ -55,16 +58,19 @@ __device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double
     // interval [2^e (1 + sub/8), 2^e (1 + (sub+1)/8)): t in [-1, 1)
     const double scale = __hiloint2double((1023 - e + 4) << 20, 0);              // 2^(4-e) = 16 / 2^e
     const double t = fma(s, scale, -(double)(2 * PLC_SUB + 2 * sub + 1));      // 16 s/2^e - 16 - 2 sub - 1
-    const double *p = c.tab + (long long)j * (PLC_DEG + 1);
-    double v = __ldg(p + PLC_DEG), d = 0.0;
+    const double *p = tab + (long long)j * (SMEM ? PLC_STRIDE : PLC_DEG + 1);
+    double v = SMEM ? p[PLC_DEG] : __ldg(p + PLC_DEG), d = 0.0;
 #pragma unroll
     for (int k = PLC_DEG - 1; k >= 0; --k) {
         if (dG) d = fma(d, t, v);
-        v = fma(v, t, __ldg(p + k));
+        v = fma(v, t, SMEM ? p[k] : __ldg(p + k));
     }
     G = v;
     if (dG) *dG = d * scale;  // dt/ds = scale
     return true;
+}
+__device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double &G, double *dG) {
+    return plc_table_eval_at<false>(c.tab, s, G, dG);
 }
 
 // (LMJ09)LogarithmicPotential, builtin/logarithmic.py:45-108: Phi = vc^2/2 ln(rs^2 + x^T M x), M symmetric with
@@ -195,13 +201,33 @@ using CountsMW = Counts<1, 2, 1, 0>;      // MilkyWayPotential:      MN disk, NF
 using CountsMW2022 = Counts<3, 2, 1, 0, true>;  // MilkyWayPotential2022:  MN3 disk (one b), NFW halo, 2 Hernquist
 using CountsBovy = Counts<1, 0, 1, 1>;    // BovyMWPotential2014:    MN disk, PLC bulge, NFW halo
 
+// Shared-memory copy of the (single) PowerLawCutoff table of a static model.  Every lane reads a different interval, so
+// from global memory each of the 14 coefficient loads of a step costs up to 32 L1 wavefronts per warp (the Bovy
+// fixed-step kernel was load-bound, not FP64-bound); from shared memory with an odd stride it is 2-4.
+template <class C>
+__device__ __forceinline__ double *plc_smem() {
+    __shared__ double t[PLC_NINT * PLC_STRIDE];
+    return t;
+}
+// Call once per CTA, by all threads, before the first gradient<C, true>().
+template <class C>
+__device__ __forceinline__ void plc_stage(const DevPot &P) {
+    if constexpr (C::is_static && C::kPLC > 0) {
+        double *t = plc_smem<C>();
+        const double *src = P.plc[0].tab;
+        for (int idx = threadIdx.x; idx < PLC_NINT * (PLC_DEG + 1); idx += blockDim.x)
+            t[(idx / (PLC_DEG + 1)) * PLC_STRIDE + idx % (PLC_DEG + 1)] = __ldg(src + idx);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
 // The flattened + spherical part is returned as two scalars: grad = (fh x, fh y, fv z); the kinds that are neither
 // (triaxial logarithmic / ellipsoidal profiles / polynomials) are added to (ex, ey, ez) by gradient<C>() below.
 // Terms of the form GM_i w_i / r (Hernquist, NFW) are summed before the common factor 1/r is applied.
-template <class C>
+template <class C, bool PLC_SMEM = false>
 __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, double y, double z, double &fh, double &fv) {
     const double z2 = z * z;
     const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
@@ -274,7 +300,8 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
             double Gs;
             if (s >= PLC_S_ONE) {
                 fr = fma(c.GM, rinv2, fr);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
-            } else if (plc_table_eval(c, s, Gs, nullptr)) {
+            } else if (PLC_SMEM ? plc_table_eval_at<true>(plc_smem<C>(), s, Gs, nullptr)
+                                : plc_table_eval(c, s, Gs, nullptr)) {
                 fs = fma(c.GM_rc3, Gs, fs);  // GM P(a, s^2) / r^3 = (GM / rc^3) G(s)
             } else {
                 const double Pg = gammainc_P(c.ga, s * s, nullptr);
@@ -328,11 +355,11 @@ __device__ __forceinline__ void gradient_extras(const DevPot &P, double x, doubl
 
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
-template <class C>
+template <class C, bool PLC_SMEM = false>
 __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
                                          double &gz_) {
     double fh, fv;
-    gradient_factors<C>(P, x, y, z, fh, fv);
+    gradient_factors<C, PLC_SMEM>(P, x, y, z, fh, fv);
     gx_ = fh * x;
     gy_ = fh * y;
     gz_ = fv * z;

@@ -327,6 +327,34 @@ def test_mockstream_generator_matches_oracle_and_reference_test_shape():
     assert np.median(np.abs(stream["lead"].q - ref["lead_q"])) < 2e-4
 
 
+def test_mockstream_generator_seeded_draws_chen_and_device_inputs():
+    """Integer seeds follow jax's key chain (Fardal: split + normal; Chen: multivariate_normal(method="svd")); the same
+    draws passed explicitly give the same stream bit for bit; CUDA-tensor progenitors keep the result on the device."""
+    import torch
+
+    from galax_b200 import jaxrandom
+
+    pot = gp.MilkyWayPotential()
+    M = 300
+    ts = np.linspace(0.0, 2000.0, M)
+    w0 = gd.PhaseSpaceCoordinate(np.array([30.0, 10, 20]), np.array([10.0, -150, -20]) * KMS, 0.0)
+    for df, draws in ((gd.FardalStreamDF(), jaxrandom.fardal_draws(5, M)), (gd.ChenStreamDF(), jaxrandom.chen_draws(5, M))):
+        gen = gd.MockStreamGenerator(df, pot)
+        s1, p1 = gen.run(5, ts, w0, 1e4)
+        s2, p2 = gen.run(draws, ts, w0, 1e4)
+        assert np.array_equal(s1.q, s2.q) and np.array_equal(s1.p, s2.p) and np.isfinite(s1.q).all()
+        s3, _ = gen.run(6, ts, w0, 1e4)
+        assert not np.array_equal(s1.q, s3.q)
+        # lead and trail sit on opposite sides of the progenitor's final position, a few tidal radii away
+        d_lead = np.linalg.norm(s1["lead"].q[-1] - p1.q), np.linalg.norm(s1["trail"].q[-1] - p1.q)
+        assert 0.0 < min(d_lead) and max(d_lead) < 2.0
+    wd = gd.PhaseSpaceCoordinate(torch.tensor(w0.q, device="cuda"), torch.tensor(w0.p, device="cuda"), 0.0)
+    sd, pd = gd.MockStreamGenerator(gd.FardalStreamDF(), pot).run(5, ts, wd, 1e4)
+    assert sd["lead"].q.is_cuda and pd.q.is_cuda
+    s1, _ = gd.MockStreamGenerator(gd.FardalStreamDF(), pot).run(5, ts, w0, 1e4)
+    assert np.array_equal(sd["lead"].q.cpu().numpy(), s1["lead"].q)
+
+
 def test_single_orbit_record_and_parallel_dense_output_matches_in_kernel_saves():
     """N = 1 with many saves takes gx_integrate_dopri8_record + gx_dense_eval; it must reproduce the in-kernel
     SaveAt path (same steps, same continuous extension)."""

@@ -1267,6 +1267,40 @@ int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, 
     return cuda_rc(cudaGetLastError());
 }
 
+// jax.random.normal (threefry2x32, partitionable, float64); see include/galax_b200.h and galax_b200/jaxrandom.py.
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+__global__ void __launch_bounds__(256) k_jax_normal(uint32_t k0, uint32_t k1, long long n, double *out) {
+    const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t x0 = (uint32_t)((unsigned long long)i >> 32) + ks[0], x1 = (uint32_t)i + ks[1];
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+            const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                x0 += x1;
+                x1 = rotl32(x1, R[g & 1][j]) ^ x0;
+            }
+            x0 += ks[(g + 1) % 3];
+            x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+        }
+        const unsigned long long bits = ((unsigned long long)x0 << 32) | x1;
+        const double fl = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)) - 1.0;
+        const double lo = -0.99999999999999988898;  // nextafter(-1, 0)
+        const double u = fmax(lo, __dadd_rn(__dmul_rn(fl, 1.0 - lo), lo));  // uniform(minval=lo, maxval=1)
+        out[i] = 1.41421356237309514547 * erfinv(u);
+    }
+}
+
+int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void *stream) {
+    if (n < 0 || (n > 0 && !out)) return GX_ERR_BADARG;
+    if (n == 0) return 0;
+    const long long want = (n + 255) / 256;
+    k_jax_normal<<<(int)(want < 148LL * 64 ? want : 148LL * 64), 256, 0, (cudaStream_t)stream>>>(key_hi, key_lo, (long long)n, out);
+    return cuda_rc(cudaGetLastError());
+}
+
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream) {
     if (N < 0 || (N > 0 && (!x || !out))) return GX_ERR_BADARG;
     if (N == 0) return 0;

@@ -531,6 +531,16 @@ class AbstractStreamDF:
         return {"lead": MockStreamArm(ql, pl, ts, ts), "trail": MockStreamArm(qt, pt, ts, ts)}
 
 
+def _device_jax_normal(key_data, n: int):
+    """``jax.random.normal(key, (n,))`` on the device (``gx_jax_normal``; threefry2x32, partitionable) -> CUDA tensor."""
+    torch = _lib.require_cuda()
+    out = torch.empty((n,), dtype=torch.float64, device="cuda")
+    rc = _lib.lib().gx_jax_normal(int(key_data[0]), int(key_data[1]), n, out.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "gx_jax_normal")
+    return out
+
+
 class FardalStreamDF(AbstractStreamDF):
     """df/fardal15.py: k_r = 2 + 0.5 n1, k_vphi = k_r (0.3 + 0.5 n2), k_z = 0.5 n3, k_vz = 0.5 n4."""
 
@@ -544,7 +554,10 @@ class FardalStreamDF(AbstractStreamDF):
             return rng.standard_normal((4, M))
         from . import jaxrandom
 
-        return jaxrandom.fardal_draws(rng, M)
+        torch = _lib.require_cuda()
+        k = jaxrandom.key(rng) if np.ndim(rng) == 0 else np.asarray(rng, dtype=np.uint32)
+        ks = jaxrandom.split(k, 4)  # four threefry evaluations on the host; the 4 M draws are made on the device
+        return torch.stack([_device_jax_normal(ks[i], M) for i in range(4)])
 
 
 class ChenStreamDF(AbstractStreamDF):
@@ -572,7 +585,12 @@ class ChenStreamDF(AbstractStreamDF):
             return rng.multivariate_normal(self.mean, self.cov, size=M, method="svd")
         from . import jaxrandom
 
-        return jaxrandom.chen_draws(rng, M)
+        torch = _lib.require_cuda()
+        k = jaxrandom.key(rng) if np.ndim(rng) == 0 else np.asarray(rng, dtype=np.uint32)
+        u, s, _ = np.linalg.svd(self.cov)
+        factor = torch.from_numpy(u * np.sqrt(s)[None, :]).to("cuda")
+        z = _device_jax_normal(k, 6 * M).reshape(M, 6)  # normal(key, (M, 6)), row-major counters
+        return torch.from_numpy(self.mean).to("cuda") + z @ factor.T
 
 
 @dataclasses.dataclass(frozen=True)

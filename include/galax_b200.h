@@ -194,6 +194,13 @@ int gx_host_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const d
  * blocks > 0: x <- x*m + c with m, c constants (one register operand; the textbook peak);
  * blocks < 0: |blocks| CTAs of x <- x*y + z with three distinct register operands (what real code looks like). */
 int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, int64_t *fma_per_thread, void *stream);
+/* jax.random.normal(key, (n,), float64) with jax's default threefry2x32 generator in partitionable mode (jax >= 0.5;
+ * the reference pins jax 0.8.0): element i = sqrt(2) erfinv(u_i), u_i from the 64 random bits threefry2x32(key, i).
+ * key = raw key data (hi, lo) as returned by jax.random.key_data.  Replaces the draws of
+ * legacy/mockstream/df/fardal15.py:61,81-84 (four such calls on jr.split(key, 4)) and df/chen24.py:89-91 (one call of
+ * shape (M, 6), then the SVD factor) so that a seeded stream needs no host-side random numbers.  Integer part exact;
+ * erfinv is CUDA's (XLA's differs at the 1e-16 level). */
+int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void *stream);
 /* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x) */
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream);
 

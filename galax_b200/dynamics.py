@@ -102,27 +102,47 @@ class PIDController:
 # containers (coordinates/_src/pscs, dynamics/_src/orbit/orbit.py:18-75)
 
 
-@dataclasses.dataclass
-class PhaseSpacePosition:
-    q: Any
-    p: Any
+class _PhaseSpaceDiagnostics:
+    """coordinates/_src/pscs/base.py:182-330: dynamical quantities of (q, p), evaluated on the device in one pass
+    (``gx_energy_angmom``) for any leading shape."""
+
+    def kinetic_energy(self):
+        """|p|^2 / 2 (pscs/base.py, ``kinetic_energy``)."""
+        return _energy(None, self.q, self.p)
+
+    def potential_energy(self, potential=None):
+        """Phi(q) (pscs/base.py:182-229)."""
+        pot = _as_potential(potential if potential is not None else getattr(self, "potential", None))
+        return pot.potential(self.q, 0.0)
+
+    def total_energy(self, potential=None):
+        """|p|^2/2 + Phi(q) (pscs/base.py:231-283)."""
+        pot = _as_potential(potential if potential is not None else getattr(self, "potential", None))
+        return _energy(pot, self.q, self.p)
+
+    def angular_momentum(self):
+        """q x p (pscs/base.py:285-322, ``specific_angular_momentum``)."""
+        return _energy(None, self.q, self.p, want="L")
 
     def w(self):
         return _cat(self.q, self.p)
 
 
 @dataclasses.dataclass
-class PhaseSpaceCoordinate:
+class PhaseSpacePosition(_PhaseSpaceDiagnostics):
+    q: Any
+    p: Any
+
+
+@dataclasses.dataclass
+class PhaseSpaceCoordinate(_PhaseSpaceDiagnostics):
     q: Any
     p: Any
     t: Any = None
 
-    def w(self):
-        return _cat(self.q, self.p)
-
 
 @dataclasses.dataclass
-class Orbit:
+class Orbit(_PhaseSpaceDiagnostics):
     """q, p: (*batch, T, 3); t: (T,).  Mirrors ``gd.Orbit`` (orbit/orbit.py:18-75)."""
 
     q: Any
@@ -132,19 +152,12 @@ class Orbit:
     status: Any = None
     n_steps: Any = None
 
-    def w(self):
-        return _cat(self.q, self.p)
-
     @property
     def shape(self):
         return tuple(self.q.shape[:-1])
 
     def __getitem__(self, idx):
         return PhaseSpaceCoordinate(self.q[..., idx, :], self.p[..., idx, :], self.t[idx])
-
-    def total_energy(self):
-        """E = |p|^2/2 + Phi(q) evaluated on the device."""
-        return _energy(self.potential, self.q, self.p)
 
 
 @dataclasses.dataclass
@@ -328,20 +341,32 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
     return restore(q), restore(p), status.reshape(batch), stats
 
 
-def _energy(pot, q, p):
+def _energy(pot, q, p, want="E"):
+    """E = |p|^2/2 + Phi(q) (``pot`` None: kinetic energy only) or L = q x p, on the device."""
     torch = _lib.require_cuda()
     dq, restore = _to_device(q)
     dp, _ = _to_device(p)
     batch = tuple(dq.shape[:-1])
     dq = dq.reshape(-1, 3).contiguous()
     dp = dp.reshape(-1, 3).contiguous()
-    E = torch.empty((dq.shape[0],), dtype=torch.float64, device=dq.device)
-    P = pot.c_struct()
+    n = dq.shape[0]
+    E = torch.empty((n,), dtype=torch.float64, device=dq.device) if want == "E" else None
+    L = torch.empty((n, 3), dtype=torch.float64, device=dq.device) if want == "L" else None
+    P = pot.c_struct() if pot is not None else NullPotentialStruct()
     with torch.cuda.device(dq.device):
-        rc = _lib.lib().gx_energy_angmom(C.byref(P), dq.data_ptr(), dp.data_ptr(), dq.shape[0], E.data_ptr(), None,
+        rc = _lib.lib().gx_energy_angmom(C.byref(P), dq.data_ptr(), dp.data_ptr(), n,
+                                         None if E is None else E.data_ptr(), None if L is None else L.data_ptr(),
                                          torch.cuda.current_stream().cuda_stream)  # fmt: skip
     _lib.check(rc, "gx_energy_angmom")
-    return restore(E.reshape(tuple(batch)))
+    return restore(E.reshape(batch)) if want == "E" else restore(L.reshape(batch + (3,)))
+
+
+def NullPotentialStruct() -> _lib.GxPotential:
+    """A potential with no components (Phi = 0)."""
+    P = _lib.GxPotential()
+    P.n = 0
+    P.G = 1.0
+    return P
 
 
 # ------------------------------------------------------------------------------------------------

@@ -282,6 +282,23 @@ def test_evaluate_orbit_and_compute_orbit_api():
 
 # ------------------------------------------------------------------ mock stream
 
+def test_phase_space_diagnostics_on_device():
+    """kinetic / potential / total energy and angular momentum of PhaseSpaceCoordinate and Orbit
+    (coordinates/_src/pscs/base.py:182-330; doctest :304-317: q = [1,0,0], p = [0,2,0] -> L = [0,0,2])."""
+    w = gd.PhaseSpaceCoordinate(np.array([1.0, 0, 0]), np.array([0, 2.0, 0]), 0.0)
+    assert np.array_equal(w.angular_momentum(), [0.0, 0.0, 2.0]) and w.kinetic_energy() == 2.0
+    pot, opot = gp.MilkyWayPotential(), op.milky_way_potential()
+    q0, p0 = synthetic_ics(opot, 64, seed=21)
+    orb = gd.evaluate_orbit(pot, (q0, p0), np.linspace(0.0, 200.0, 9))
+    assert orb.q.shape == (64, 9, 3)
+    K, U, E, L = orb.kinetic_energy(), orb.potential_energy(), orb.total_energy(), orb.angular_momentum()
+    assert K.shape == (64, 9) and L.shape == (64, 9, 3)
+    assert np.allclose(K, 0.5 * (orb.p**2).sum(-1), rtol=1e-15) and np.allclose(U, op.potential(opot, orb.q), rtol=1e-13)
+    assert np.allclose(E, K + U, rtol=1e-14) and np.allclose(L, np.cross(orb.q, orb.p), rtol=1e-14, atol=1e-16)
+    assert np.abs(E / E[:, :1] - 1).max() < 1e-5 and np.abs(L[..., 2] - L[:, :1, 2]).max() < 1e-6  # axisymmetric: E, L_z
+    assert np.allclose(gd.PhaseSpacePosition(q0, p0).total_energy(pot), E[:, 0], rtol=1e-14)
+
+
 @pytest.mark.parametrize("dfname", ["fardal", "chen"])
 def test_stream_release_matches_oracle(dfname):
     pot, opot = gp.MilkyWayPotential(), op.milky_way_potential()

@@ -282,6 +282,30 @@ def test_evaluate_orbit_and_compute_orbit_api():
 
 # ------------------------------------------------------------------ mock stream
 
+def test_adaptive_launches_with_different_potentials_on_two_streams():
+    """The Dopri8 RHS reads its parameters from one __constant__ image per device (stage_const_pot): interleaved
+    launches with different potentials on different streams must each see their own parameters."""
+    import torch
+
+    potA, potB = gp.MilkyWayPotential(), gp.HernquistPotential(1e12, 5.0)
+    q0, p0 = synthetic_ics(op.milky_way_potential(), 4096, seed=31)
+    dq, dp = torch.tensor(q0, device="cuda"), torch.tensor(p0, device="cuda")
+    solver = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=1e-8, atol=1e-8))
+    refA = solver.solve(potA, (dq, dp), 0.0, 300.0).ys[0].clone()
+    refB = solver.solve(potB, (dq, dp), 0.0, 300.0).ys[0].clone()
+    torch.cuda.synchronize()
+    sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(4):
+        with torch.cuda.stream(sA):
+            outs.append(("A", solver.solve(potA, (dq, dp), 0.0, 300.0, throw=False).ys[0]))
+        with torch.cuda.stream(sB):
+            outs.append(("B", solver.solve(potB, (dq, dp), 0.0, 300.0, throw=False).ys[0]))
+    torch.cuda.synchronize()
+    for tag, o in outs:
+        assert torch.equal(o, refA if tag == "A" else refB), tag
+
+
 def test_phase_space_diagnostics_on_device():
     """kinetic / potential / total energy and angular momentum of PhaseSpaceCoordinate and Orbit
     (coordinates/_src/pscs/base.py:182-330; doctest :304-317: q = [1,0,0], p = [0,2,0] -> L = [0,0,2])."""

@@ -370,18 +370,27 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
 // potential value and Hessian (bulk-evaluation kernel only; HBM-bound, so IEEE div/sqrt/log1p).
 template <class C>
 __device__ __forceinline__ double potential_value(const DevPot &P, double x, double y, double z) {
+    // the same MUFU-seeded primitives as the gradient (each within ~1 ulp); the PowerLawCutoff term keeps the series
     const double z2 = z * z, R2 = fma(y, y, x * x);
     double phi = 0.0;
+    double zeta2 = 0.0, rz = 0.0;
     for (int i = 0; i < C::mn(P); ++i) {
         const DevMN &c = P.mn[i];
-        double apz = sqrt(z2 + c.b2) + c.a;
-        phi -= c.GM / sqrt(fma(apz, apz, R2));
+        if (!C::mn_shared_b || i == 0) {
+            zeta2 = z2 + c.b2;
+            rz = rsqrt_fast(zeta2);
+        }
+        const double apz = fma(zeta2, rz, c.a);
+        phi = fma(-c.GM, rsqrt_fast(fma(apz, apz, R2)), phi);
     }
-    const double r = sqrt((R2 + z2) + TINY);
-    for (int i = 0; i < C::hern(P); ++i) phi -= P.hern[i].GM / (r + P.hern[i].c);
+    const double r2 = (R2 + z2) + TINY;
+    const double rinv = rsqrt_fast(r2);
+    const double r = r2 * rinv;
+    for (int i = 0; i < C::hern(P); ++i) phi = fma(-P.hern[i].GM, rcp_fast(r + P.hern[i].c), phi);
     for (int i = 0; i < C::nfw(P); ++i) {
-        double s = r * P.nfw[i].inv_rs;
-        phi -= P.nfw[i].GM_inv_rs * (log1p(s) / s);
+        const double s = r * P.nfw[i].inv_rs;
+        // ln(1+s)/s: s > 0 always (TINY); rinv * rs = 1/s without another reciprocal
+        phi = fma(-P.nfw[i].GM_inv_rs * log1p_pos(s), rinv * P.nfw[i].rs, phi);
     }
     for (int i = 0; i < C::plc(P); ++i) {
         const DevPLC &c = P.plc[i];

@@ -38,7 +38,7 @@ SOLVER_DOPRI8, SOLVER_DOPRI5 = 8, 5
 
 
 class GxComponent(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 8)]
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double * 8), ("dp", C.c_double * 8)]
 
 
 class GxPotential(C.Structure):

@@ -43,9 +43,38 @@ static void fill_gamma_tab(GammaTab &g, double a) {
     for (int n = 0; n < PLC_NT; ++n) g.inv[n] = 1.0 / (a + n);
 }
 
-static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool use_device = true) {
-    if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
+// How an entry treats LinearParameter rates (gx_component.dp): freeze the parameters at one time (bulk evaluation),
+// carry the raw parameters to the device for per-stage evaluation (integrators), or refuse.
+enum TdMode { TD_REJECT = 0, TD_FREEZE = 1, TD_INTEGRATE = 2 };
+
+static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, bool use_device = true,
+                        TdMode td_mode = TD_REJECT, double t_freeze = 0.0) {
+    if (!pot_in || pot_in->n < 0 || pot_in->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
     memset(&D, 0, sizeof D);
+    gx_potential frozen = *pot_in;
+    bool td = false;
+    for (int i = 0; i < frozen.n; ++i)
+        for (int k = 0; k < 8; ++k) {
+            if (frozen.c[i].dp[k] != 0.0) td = true;
+            frozen.c[i].p[k] += frozen.c[i].dp[k] * (td_mode == TD_FREEZE ? t_freeze : 0.0);
+        }
+    if (td && td_mode == TD_REJECT) return GX_ERR_UNSUPPORTED;
+    if (td && td_mode == TD_INTEGRATE) {
+        D.td.n = frozen.n;
+        D.td.G = frozen.G;
+        for (int i = 0; i < frozen.n; ++i) {
+            const int kind = pot_in->c[i].kind;
+            if (kind != GX_KIND_MIYAMOTO_NAGAI && kind != GX_KIND_HERNQUIST && kind != GX_KIND_NFW &&
+                kind != GX_KIND_ISOCHRONE && kind != GX_KIND_SATOH && kind != GX_KIND_TRIAXIAL_HERNQUIST &&
+                kind != GX_KIND_JAFFE)
+                return GX_ERR_UNSUPPORTED;
+            D.td.kind[i] = kind;
+            for (int k = 0; k < TD_NP; ++k) { D.td.p[i][k] = pot_in->c[i].p[k]; D.td.dp[i][k] = pot_in->c[i].dp[k]; }
+            for (int k = TD_NP; k < 8; ++k)
+                if (pot_in->c[i].dp[k] != 0.0) return GX_ERR_UNSUPPORTED;
+        }
+    }
+    const gx_potential *pot = &frozen;
     const double G = pot->G;
     for (int i = 0; i < pot->n; ++i) {
         const gx_component &c = pot->c[i];
@@ -160,7 +189,7 @@ static int build_devpot(const gx_potential *pot, DevPot &D, Model &model, bool u
         }
     }
     model = MODEL_GENERIC;
-    if (D.n_log + D.n_iso + D.n_satoh + D.n_rad + D.n_harm + D.n_henon == 0) {
+    if (D.td.n == 0 && D.n_log + D.n_iso + D.n_satoh + D.n_rad + D.n_harm + D.n_henon == 0) {
         if (D.n_mn == 1 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0) model = MODEL_MW;
         if (D.n_mn == 3 && D.n_hern == 2 && D.n_nfw == 1 && D.n_plc == 0 && D.mn[0].b2 == D.mn[1].b2 &&
             D.mn[0].b2 == D.mn[2].b2)
@@ -407,7 +436,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
                 npz = fma(fvh, nqz, pz);
                 gx_ = gy_ = gz_ = 0.0;
             } else {
-                gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_);
+                gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev);
                 npx = fma(-gx_, hs, px);
                 npy = fma(-gy_, hs, py);
                 npz = fma(-gz_, hs, pz);
@@ -416,7 +445,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqx = __dadd_rn(qx, __dmul_rn(px, hs));
             nqy = __dadd_rn(qy, __dmul_rn(py, hs));
             nqz = __dadd_rn(qz, __dmul_rn(pz, hs));
-            gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_);
+            gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev);
             npx = __dadd_rn(px, __dmul_rn(-gx_, hs));
             npy = __dadd_rn(py, __dmul_rn(-gy_, hs));
             npz = __dadd_rn(pz, __dmul_rn(-gz_, hs));
@@ -424,7 +453,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         } else {
             const double hm = tnext - tm;
             const double hh = FWD ? hm : -hm;
-            gradient<C, STAGED>(P, qx, qy, qz, gx_, gy_, gz_);
+            gradient<C, STAGED>(P, qx, qy, qz, gx_, gy_, gz_, FWD ? tprev : -tprev);
             nqx = __dadd_rn(mqx, __dmul_rn(px, hh));
             nqy = __dadd_rn(mqy, __dmul_rn(py, hh));
             nqz = __dadd_rn(mqz, __dmul_rn(pz, hh));
@@ -527,20 +556,36 @@ __device__ __forceinline__ DevPot *pot_smem() {
     return &sP;
 }
 template <class C>
-__device__ __noinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az) {
-    double g0, g1, g2;
+__device__ __forceinline__ const DevPot &rhs_pot() {
 #if GX_DP8_CONST_POT
-    gradient<C, (C::is_static && C::kPLC > 0)>(c_pot_dp8, x, y, z, g0, g1, g2);
+    return c_pot_dp8;
 #else
-    gradient<C, (C::is_static && C::kPLC > 0)>(*pot_smem<C>(), x, y, z, g0, g1, g2);
+    return *pot_smem<C>();
 #endif
+}
+template <class C>
+__device__ __noinline__ void accel_call_static(double x, double y, double z, double &ax, double &ay, double &az) {
+    double g0, g1, g2;
+    gradient<C, (C::is_static && C::kPLC > 0)>(rhs_pot<C>(), x, y, z, g0, g1, g2);
     ax = -g0; ay = -g1; az = -g2;
+}
+// runtime composites may be time dependent (LinearParameter): the callee also receives the physical time
+template <class C>
+__device__ __noinline__ void accel_call_timed(double t, double x, double y, double z, double &ax, double &ay, double &az) {
+    double g0, g1, g2;
+    gradient<C, false>(rhs_pot<C>(), x, y, z, g0, g1, g2, t);
+    ax = -g0; ay = -g1; az = -g2;
+}
+template <class C>
+__device__ __forceinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az, double t) {
+    if constexpr (C::is_static) accel_call_static<C>(x, y, z, ax, ay, az);
+    else accel_call_timed<C>(t, x, y, z, ax, ay, az);
 }
 
 // Hairer-Norsett-Wanner initial step as restated by diffrax (_select_initial_step); inv_order = 1 / error order.
 // Works in tau = dir*t: f = dir * (p, a).
 template <class C>
-__device__ double select_initial_step(const DevPot &P, double dir, const double y[6], const double a0[3],
+__device__ double select_initial_step(const DevPot &P, double dir, double tau0, const double y[6], const double a0[3],
                                       double rtol, double atol, double inv_order) {
     double f0[6] = {y[3] * dir, y[4] * dir, y[5] * dir, a0[0] * dir, a0[1] * dir, a0[2] * dir};
     double sc[6], v[6];
@@ -558,7 +603,7 @@ __device__ double select_initial_step(const DevPot &P, double dir, const double 
 #pragma unroll
     for (int i = 0; i < 6; ++i) y1[i] = y[i] + h0 * f0[i];
     double a1x, a1y, a1z;
-    accel_call<C>(y1[0], y1[1], y1[2], a1x, a1y, a1z);
+    accel_call<C>(y1[0], y1[1], y1[2], a1x, a1y, a1z, dir * (tau0 + h0));
     double f1[6] = {y1[3] * dir, y1[4] * dir, y1[5] * dir, a1x * dir, a1y * dir, a1z * dir};
 #pragma unroll
     for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
@@ -634,7 +679,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     ++k;
                     tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 }
-                { double t0_, t1_, t2_; accel_call<C>(q0x, q0y, q0z, t0_, t1_, t2_); AX(0) = t0_; AY(0) = t1_; AZ(0) = t2_; }
+                { double t0_, t1_, t2_; accel_call<C>(q0x, q0y, q0z, t0_, t1_, t2_, dir * T0); AX(0) = t0_; AY(0) = t1_; AZ(0) = t2_; }
                 // PIDController.init: heuristic when dt0 is None (exponent 1/(error_order + 1), Hairer II.4 -- the
                 // choice that reproduces the reference's 8-digit OrbitSolver doctests), then clamp to [dtmin, dtmax]
                 double h;
@@ -643,7 +688,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                 } else {
                     const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
                     const double a0[3] = {AX(0), AY(0), AZ(0)};
-                    h = select_initial_step<C>(P, dir, y, a0, a.rtol, a.atol, 1.0 / (TB::ORDER + 1));
+                    h = select_initial_step<C>(P, dir, T0, y, a0, a.rtol, a.atol, 1.0 / (TB::ORDER + 1));
                 }
                 if (a.dtmax > 0.0) h = fmin(h, a.dtmax);
                 if (a.dtmin > 0.0) { at_dtmin = h <= a.dtmin; h = fmax(h, a.dtmin); }
@@ -692,7 +737,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
             const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
             const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
             const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
-            { double t0_, t1_, t2_; accel_call<C>(xi, yi, zi, t0_, t1_, t2_); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
+            { double t0_, t1_, t2_; accel_call<C>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
             if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1
         }
         const double q1x = sx, q1y = sy, q1z = sz;
@@ -1053,9 +1098,8 @@ static void out_strides(int layout, long long N, int T, long long &sn, long long
 
 int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what, double *phi,
                       double *grad, double *acc, double *hess, void *stream) {
-    (void)t;
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model);
+    int rc = build_devpot(pot, D, model, true, TD_FREEZE, t);  // LinearParameter: the potential at time t
     if (rc) return rc;
     if (N < 0) return GX_ERR_BADARG;
     if (N == 0) return 0;
@@ -1095,7 +1139,7 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
                        double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
                        double *q, double *p, int32_t *status, void *stream) {
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model);
+    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE);
     if (rc) return rc;
     if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
     if (scheme != GX_SCHEME_SEMI_IMPLICIT_EULER && scheme != GX_SCHEME_LEAPFROG_MIDPOINT) return GX_ERR_BADARG;
@@ -1176,7 +1220,7 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
                          void *workspace, void *stream) {
     if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model);
+    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE);
     if (rc) return rc;
     if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
         return GX_ERR_BADARG;

@@ -93,6 +93,16 @@ struct DevRad { int profile, pad_; double K, a, b, i1, i2; };
 struct DevHarm { double w2x, w2y, w2z; };
 struct DevHenon { double k, it2; };
 
+// Time-dependent composites (LinearParameter, params/core.py:25-110): raw parameters and their rates; the integrators
+// evaluate every right-hand side with the parameters of its own time (gradient_td below).  n == 0: static potential.
+constexpr int TD_MAX = 14, TD_NP = 4;
+struct DevTD {
+    int n, pad_;
+    double G;
+    int kind[TD_MAX];
+    double p[TD_MAX][TD_NP], dp[TD_MAX][TD_NP];
+};
+
 struct DevPot {
     int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, n_rad, n_harm, n_henon;
     DevMN mn[MAX_MN];
@@ -105,6 +115,7 @@ struct DevPot {
     DevRad rad[MAX_RAD];
     DevHarm harm[MAX_HARM];
     DevHenon henon[MAX_HENON];
+    DevTD td;
 };
 
 // Burkert: B(s) = 2 ln(1+s) + ln(1+s^2) - 2 atan(s) = M(<r) C/m.  Below s = 0.3 the three terms cancel to
@@ -353,11 +364,74 @@ __device__ __forceinline__ void gradient_extras(const DevPot &P, double x, doubl
     }
 }
 
+// Gradient of a time-dependent composite at time t: the closed forms of gradient_factors() evaluated from the raw
+// parameters p_k(t) = p[k] + dp[k] t (kinds as in include/galax_b200.h; the host admits only these seven here).
+__device__ __noinline__ void gradient_td(const DevTD &R, double t, double x, double y, double z, double &gx_, double &gy_,
+                                         double &gz_) {
+    const double z2 = z * z, R2 = fma(y, y, fma(x, x, TINY));
+    const double r2 = R2 + z2, rinv = rsqrt_fast(r2), r = r2 * rinv, rinv2 = rinv * rinv;
+    double fxy = 0.0, fz = 0.0, fs = 0.0, ex = 0.0, ey = 0.0, ez = 0.0;
+    for (int i = 0; i < R.n; ++i) {
+        const double p0 = fma(R.dp[i][0], t, R.p[i][0]), p1 = fma(R.dp[i][1], t, R.p[i][1]);
+        const double p2 = fma(R.dp[i][2], t, R.p[i][2]), p3 = fma(R.dp[i][3], t, R.p[i][3]);
+        const double GM = R.G * p0;
+        switch (R.kind[i]) {
+        case 0: {  // Miyamoto-Nagai (m, a, b)
+            const double zeta2 = fma(p2, p2, z2), rz = rsqrt_fast(zeta2), apz = fma(zeta2, rz, p1);
+            const double rD = rsqrt_fast(fma(apz, apz, R2)), f = (GM * rD) * (rD * rD);
+            fxy += f;
+            fz = fma(f, apz * rz, fz);
+            break;
+        }
+        case 1: {  // Hernquist (m, r_s)
+            const double u = r + p1;
+            fs = fma(GM * rinv, rcp_fast(u * u), fs);
+            break;
+        }
+        case 2: {  // NFW (m, r_s)
+            const double m = nfw_menc_shape(r * rcp_fast(p1));
+            fs = fma((GM * m) * rinv, rinv2, fs);
+            break;
+        }
+        case 5: {  // Isochrone (m, b)
+            const double a2 = fma(p1, p1, r2), ia = rsqrt_fast(a2), ibpa = rcp_fast(fma(a2, ia, p1));
+            fs = fma(GM * ia, ibpa * ibpa, fs);
+            break;
+        }
+        case 6: {  // Satoh (m, a, b)
+            const double b2 = p2 * p2, zs2 = z2 + b2, rzs = rsqrt_fast(zs2), apz = fma(zs2, rzs, p1);
+            const double rD = rsqrt_fast(fma(apz, apz, R2 - b2)), f = (GM * rD) * (rD * rD);
+            fxy += f;
+            fz = fma(f, apz * rzs, fz);
+            break;
+        }
+        case 7: {  // triaxial Hernquist (m, r_s, q1, q2)
+            const double i1 = rcp_fast(p2 * p2), i2 = rcp_fast(p3 * p3), wy = y * i1, wz = z * i2;
+            const double m2 = fma(x, x, fma(y, wy, fma(z, wz, TINY))), minv = rsqrt_fast(m2), u = fma(m2, minv, p1);
+            const double f = GM * minv * rcp_fast(u * u);
+            ex = fma(f, x, ex); ey = fma(f, wy, ey); ez = fma(f, wz, ez);
+            break;
+        }
+        default: {  // 8: Jaffe (m, r_s): Phi'/r = GM / (r^2 (r + a))
+            fs = fma(GM * rinv2, rcp_fast(r + p1), fs);
+            break;
+        }
+        }
+    }
+    gx_ = fma(fxy + fs, x, ex);
+    gy_ = fma(fxy + fs, y, ey);
+    gz_ = fma(fz + fs, z, ez);
+}
+
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
 template <class C, bool PLC_SMEM = false>
 __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
-                                         double &gz_) {
+                                         double &gz_, double t = 0.0) {
+    if (!C::is_static && P.td.n > 0) {  // time-dependent composite (runtime path only)
+        gradient_td(P.td, t, x, y, z, gx_, gy_, gz_);
+        return;
+    }
     double fh, fv;
     gradient_factors<C, PLC_SMEM>(P, x, y, z, fh, fv);
     gx_ = fh * x;

@@ -25,17 +25,24 @@ from .. import dynamics as bd
 from .. import potential as bp
 
 
-def _value(param, unit) -> float:
-    """``ConstantParameter`` -> float in ``unit``; anything else is time-dependent and unsupported.
+def _value(param, unit, time_unit=None):
+    """``ConstantParameter`` -> float in ``unit``; ``LinearParameter`` -> ``galax_b200.potential.LinearParameter`` with
+    slope in ``unit``/``time_unit`` (the integrators evaluate it per stage).  Anything else (``UserParameter``, ...) is a
+    general function of time and unsupported.
 
-    galax: ``potential/_src/params/constant.py`` (``ConstantParameter.value``), ``params/field.py:206-223``.
+    galax: ``potential/_src/params/constant.py`` (``ConstantParameter.value``), ``params/core.py:25-110``
+    (``LinearParameter.slope / point_time / point_value``), ``params/field.py:206-223``.
     """
-    name = type(param).__name__
-    if name != "ConstantParameter":
-        raise NotImplementedError(f"galax_b200 supports ConstantParameter only, got {name}")
     import unxt as u
 
-    return float(u.ustrip(unit, param.value))
+    name = type(param).__name__
+    if name == "ConstantParameter":
+        return float(u.ustrip(unit, param.value))
+    if name == "LinearParameter" and time_unit is not None:
+        return bp.LinearParameter(slope=float(u.ustrip(unit / time_unit, param.slope)),
+                                  point_time=float(u.ustrip(time_unit, param.point_time)),
+                                  point_value=float(u.ustrip(unit, param.point_value)))
+    raise NotImplementedError(f"galax_b200 supports ConstantParameter and LinearParameter only, got {name}")
 
 
 def convert_potential(pot) -> bp.AbstractPotential:
@@ -48,15 +55,15 @@ def convert_potential(pot) -> bp.AbstractPotential:
     import galax.potential as gp
 
     G = float(pot.constants["G"].value)
-    ul, um = pot.units["length"], pot.units["mass"]
+    ul, um, ut = pot.units["length"], pot.units["mass"], pot.units["time"]
     if isinstance(pot, gp.MiyamotoNagaiPotential):
-        return bp.MiyamotoNagaiPotential(_value(pot.m_tot, um), _value(pot.a, ul), _value(pot.b, ul), G=G)
+        return bp.MiyamotoNagaiPotential(_value(pot.m_tot, um, ut), _value(pot.a, ul, ut), _value(pot.b, ul, ut), G=G)
     if isinstance(pot, gp.HernquistPotential):
-        return bp.HernquistPotential(_value(pot.m_tot, um), _value(pot.r_s, ul), G=G)
+        return bp.HernquistPotential(_value(pot.m_tot, um, ut), _value(pot.r_s, ul, ut), G=G)
     if isinstance(pot, gp.KeplerPotential):
-        return bp.KeplerPotential(_value(pot.m_tot, um), G=G)
+        return bp.KeplerPotential(_value(pot.m_tot, um, ut), G=G)
     if isinstance(pot, gp.NFWPotential):
-        return bp.NFWPotential(_value(pot.m, um), _value(pot.r_s, ul), G=G)
+        return bp.NFWPotential(_value(pot.m, um, ut), _value(pot.r_s, ul, ut), G=G)
     if isinstance(pot, gp.PowerLawCutoffPotential):
         return bp.PowerLawCutoffPotential(
             _value(pot.m_tot, um), _value(pot.alpha, pot.units["dimensionless"]), _value(pot.r_c, ul), G=G
@@ -83,7 +90,7 @@ def convert_potential(pot) -> bp.AbstractPotential:
     )  # fmt: skip
     for name, cls, fields in simple:
         if type(pot).__name__ == name:
-            return cls(*[_value(getattr(pot, f), unit) for f, unit in fields], G=G)
+            return cls(*[_value(getattr(pot, f), unit, ut) for f, unit in fields], G=G)
     if type(pot).__name__ == "NullPotential":
         return bp.NullPotential(G=G)
     if isinstance(pot, gp.AbstractCompositePotential):  # CompositePotential and the pre-composited MW models

@@ -31,15 +31,62 @@ G_GALACTIC = 4.498502151469553e-12
 KMS = 0.001022712165045695  # 1 km/s in kpc/Myr
 
 
+@dataclasses.dataclass(frozen=True)
+class LinearParameter:
+    """``gp.params.LinearParameter`` (potential/_src/params/core.py:25-110): p(t) = slope (t - point_time) + point_value,
+    all three in the potential's units (galactic: Msun, kpc, Myr)."""
+
+    slope: float
+    point_time: float
+    point_value: float
+
+    def __call__(self, t: float) -> float:
+        return self.slope * (t - self.point_time) + self.point_value
+
+
+@dataclasses.dataclass(frozen=True)
+class ConstantParameter:
+    """``gp.params.ConstantParameter`` (potential/_src/params/constant.py)."""
+
+    value: float
+
+    def __call__(self, t: float = 0.0) -> float:
+        return self.value
+
+
+class _Param(float):
+    """A parameter value at t = 0 that remembers its time derivative (0 for constants)."""
+
+    rate: float = 0.0
+
+    def __new__(cls, value: float, rate: float = 0.0):
+        obj = super().__new__(cls, value)
+        obj.rate = float(rate)
+        return obj
+
+
 def _const(name: str, v: Any) -> float:
-    """ConstantParameter only (potential/_src/params/constant.py); anything callable is time-dependent."""
+    """ConstantParameter or LinearParameter; any other callable (``UserParameter``) is rejected."""
+    if isinstance(v, LinearParameter):
+        return _Param(v.point_value - v.slope * v.point_time, v.slope)
+    if isinstance(v, ConstantParameter):
+        return _Param(v.value)
     if callable(v):
         raise NotImplementedError(
-            f"parameter {name!r} is time-dependent; galax_b200 kernels support ConstantParameter only"
+            f"parameter {name!r} is a general function of time; galax_b200 kernels support ConstantParameter and "
+            "LinearParameter only"
         )
     if hasattr(v, "value"):  # unxt.Quantity-like: caller must already be in the potential's units
         v = v.value
-    return float(v)
+    return _Param(float(v), getattr(v, "rate", 0.0))
+
+
+def _static(name: str, v: Any) -> float:
+    """For parameters that enter host-side preprocessing (MN3 fits, rotation matrices, gamma functions)."""
+    out = _const(name, v)
+    if getattr(out, "rate", 0.0) != 0.0:
+        raise NotImplementedError(f"parameter {name!r} of this potential cannot be time-dependent")
+    return float(out)
 
 
 class AbstractPotential:
@@ -64,7 +111,12 @@ class AbstractPotential:
             P.c[i].kind = kind
             for j, v in enumerate(params):
                 P.c[i].p[j] = float(v)
+                P.c[i].dp[j] = float(getattr(v, "rate", 0.0))
         return P
+
+    @property
+    def is_time_dependent(self) -> bool:
+        return any(getattr(v, "rate", 0.0) != 0.0 for _, params in self._flat_components() for v in params)
 
     # ---------------------------------------------------------------- evaluation
     def _eval(self, q, t, what: int):
@@ -481,7 +533,7 @@ class _AbstractMN3Potential(AbstractPotential):
 
     def _get_mn_components(self) -> list[MiyamotoNagaiPotential]:
         # builtin/mn3.py:90-119 (host-side algebra, same operation order)
-        m_tot, hR, hz = _const("m_tot", self.m_tot), _const("h_R", self.h_R), _const("h_z", self.h_z)
+        m_tot, hR, hz = _static("m_tot", self.m_tot), _static("h_R", self.h_R), _static("h_z", self.h_z)
         hzR = hz / hR
         K = _MN3_K_POS if self.positive_density else _MN3_K_NEG
         b_hR = np.asarray(self._b_coeffs) @ np.array([hzR**3, hzR**2, hzR])
@@ -610,7 +662,7 @@ class BovyMWPotential2014(MilkyWayPotential):
 
 
 __all__ = [
-    "AbstractPotential", "MiyamotoNagaiPotential", "HernquistPotential", "KeplerPotential", "PlummerPotential",
+    "AbstractPotential", "LinearParameter", "ConstantParameter", "MiyamotoNagaiPotential", "HernquistPotential", "KeplerPotential", "PlummerPotential",
     "KuzminPotential", "IsochronePotential", "SatohPotential", "LogarithmicPotential", "LMJ09LogarithmicPotential",
     "LM10Potential", "NFWPotential", "TriaxialHernquistPotential", "JaffePotential", "BurkertPotential",
     "StoneOstriker15Potential", "HarmonicOscillatorPotential", "HenonHeilesPotential", "NullPotential",

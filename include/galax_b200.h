@@ -45,10 +45,17 @@ extern "C" {
 #define GX_KIND_HENON_HEILES 12 /* builtin/example.py:107-176 HenonHeilesPotential: p = (coeff, timescale) */
 #define GX_MAX_COMPONENTS 14
 
+/* Parameters may depend linearly on time, p_k(t) = p[k] + dp[k] * t: galax's LinearParameter
+ * (potential/_src/params/core.py:25-110, slope * (t - point_time) + point_value with the offset folded into p[k]).
+ * dp == 0 everywhere: a static potential.  Time-dependent composites are supported by gx_potential_eval (frozen at
+ * its t) and by the integrators for the kinds MIYAMOTO_NAGAI, HERNQUIST, NFW, ISOCHRONE, SATOH, TRIAXIAL_HERNQUIST
+ * and JAFFE (each right-hand side is evaluated with the parameters of its own stage time); gx_stream_release and
+ * gx_energy_angmom return GX_ERR_UNSUPPORTED for them. */
 typedef struct {
     int32_t kind;
     int32_t reserved;
     double p[8];
+    double dp[8];
 } gx_component;
 
 /* A composite potential = sum of components (potential/_src/base_multi.py:39-82).  MN3 disks are passed as

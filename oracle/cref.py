@@ -19,7 +19,7 @@ OK, MAX_STEPS, NONFINITE = 0, 1, 2
 
 
 class _Component(C.Structure):
-    _fields_ = [("kind", C.c_int), ("group", C.c_int), ("p", C.c_double * 8)]
+    _fields_ = [("kind", C.c_int), ("group", C.c_int), ("p", C.c_double * 8), ("dp", C.c_double * 8)]
 
 
 class _Potential(C.Structure):
@@ -93,6 +93,8 @@ def c_potential(pot: op.Potential) -> _Potential:
         P.c[i].group = gid[i]
         for j, v in enumerate(comp.params):
             P.c[i].p[j] = v
+        for j, v in enumerate(comp.rates):
+            P.c[i].dp[j] = v
     return P
 
 
@@ -132,7 +134,7 @@ def gammainc(a: float, x: float) -> float:
     return float(lib().oc_gammainc(a, x))
 
 
-def potential_eval(pot: op.Potential, xyz, what=("phi", "grad", "acc", "hess")):
+def potential_eval(pot: op.Potential, xyz, what=("phi", "grad", "acc", "hess"), t: float = 0.0):
     xyz = _f64(xyz).reshape(-1, 3)
     N = xyz.shape[0]
     P = c_potential(pot)
@@ -141,7 +143,8 @@ def potential_eval(pot: op.Potential, xyz, what=("phi", "grad", "acc", "hess")):
     grad = np.empty((N, 3))
     acc = np.empty((N, 3))
     hess = np.empty((N, 3, 3))
-    lib().oc_potential_eval(C.byref(P), C.c_int64(N), _dp(xyz), C.c_uint(mask), _dp(phi), _dp(grad), _dp(acc), _dp(hess))
+    lib().oc_potential_eval_t(C.byref(P), C.c_double(t), C.c_int64(N), _dp(xyz), C.c_uint(mask), _dp(phi), _dp(grad),
+                              _dp(acc), _dp(hess))
     out = {"phi": phi, "grad": grad, "acc": acc, "hess": hess}
     return {k: out[k] for k in what}
 

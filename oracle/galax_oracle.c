@@ -53,6 +53,7 @@ typedef struct {
     int kind;
     int group; /* components with equal group id are summed first (MN3 disk) */
     double p[8];
+    double dp[8]; /* LinearParameter (potential/_src/params/core.py:25-110): p_k(t) = p[k] + dp[k] t */
 } oc_component;
 
 typedef struct {
@@ -408,6 +409,25 @@ static void comp_hessian(double G, const oc_component *c, const double q[3], dou
         }
 }
 
+/* ---------------------------------------------------------------- time dependence */
+
+static int is_time_dependent(const oc_potential *P) {
+    for (int i = 0; i < P->n; ++i)
+        for (int k = 0; k < 8; ++k)
+            if (P->c[i].dp[k] != 0.0) return 1;
+    return 0;
+}
+
+/* the potential frozen at time t (the reference evaluates every parameter as param(t) inside _potential) */
+static void potential_at(const oc_potential *P, double t, oc_potential *out) {
+    *out = *P;
+    for (int i = 0; i < P->n; ++i)
+        for (int k = 0; k < 8; ++k) {
+            out->c[i].p[k] = P->c[i].p[k] + P->c[i].dp[k] * t;
+            out->c[i].dp[k] = 0.0;
+        }
+}
+
 /* ---------------------------------------------------------------- composite (sum in order) */
 
 double oc_potential_value(const oc_potential *P, const double q[3]) {
@@ -447,8 +467,11 @@ void oc_gradient(const oc_potential *P, const double q[3], double g[3]) { sum_ve
 void oc_hessian(const oc_potential *P, const double q[3], double H[9]) { sum_vec(P, q, 9, H, comp_hessian); }
 
 /* bulk evaluation: what bit 0 = Phi, 1 = grad, 2 = acceleration(-grad), 3 = Hessian */
-void oc_potential_eval(const oc_potential *P, int64_t N, const double *xyz, unsigned what, double *phi,
-                       double *grad, double *acc, double *hess) {
+void oc_potential_eval_t(const oc_potential *P0, double t, int64_t N, const double *xyz, unsigned what, double *phi,
+                         double *grad, double *acc, double *hess) {
+    oc_potential Pt;
+    potential_at(P0, t, &Pt);
+    const oc_potential *P = &Pt;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i) {
         const double *q = xyz + 3 * i;
@@ -463,11 +486,23 @@ void oc_potential_eval(const oc_potential *P, int64_t N, const double *xyz, unsi
     }
 }
 
+void oc_potential_eval(const oc_potential *P, int64_t N, const double *xyz, unsigned what, double *phi,
+                       double *grad, double *acc, double *hess) {
+    oc_potential_eval_t(P, 0.0, N, xyz, what, phi, grad, acc, hess);
+}
+
 /* ---------------------------------------------------------------- field */
 
-static inline void accel(const oc_potential *P, const double q[3], double a[3]) {
+/* acceleration at physical time t */
+static inline void accel(const oc_potential *P, int td, double t, const double q[3], double a[3]) {
     double g[3];
-    oc_gradient(P, q, g);
+    if (td) {
+        oc_potential Pt;
+        potential_at(P, t, &Pt);
+        oc_gradient(&Pt, q, g);
+    } else {
+        oc_gradient(P, q, g);
+    }
     a[0] = -g[0];
     a[1] = -g[1];
     a[2] = -g[2];
@@ -498,6 +533,7 @@ int oc_integrate_fixed(const oc_potential *P, int64_t N, const double *q0, const
     double T0 = t0 * dir, T1 = t1 * dir;
     double h0 = dt0 * dir;
     if (!(h0 > 0.0) && T1 > T0) return -1;
+    const int td = is_time_dependent(P);
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t i = 0; i < N; ++i) {
         double q[3] = {q0[3 * i], q0[3 * i + 1], q0[3 * i + 2]};
@@ -520,11 +556,11 @@ int oc_integrate_fixed(const oc_potential *P, int64_t N, const double *q0, const
             double qn[3], pn[3], a[3];
             if (scheme == 0) {
                 for (int c = 0; c < 3; ++c) qn[c] = q[c] + (p[c] * dir) * h;
-                accel(P, qn, a);
+                accel(P, td, tprev * dir, qn, a); /* diffrax SemiImplicitEuler: both terms are evaluated at t0 of the step */
                 for (int c = 0; c < 3; ++c) pn[c] = p[c] + (a[c] * dir) * h;
             } else {
                 double hh = tnext - tm;
-                accel(P, q, a);
+                accel(P, td, tprev * dir, q, a);
                 for (int c = 0; c < 3; ++c) {
                     qn[c] = qm[c] + (p[c] * dir) * hh;
                     pn[c] = pm[c] + (a[c] * dir) * hh;
@@ -585,14 +621,14 @@ static inline double rms6(const double v[6]) {
     return sqrt(s / 6.0);
 }
 
-static void field_dir(const oc_potential *P, double dir, const double y[6], double f[6]) {
+static void field_dir(const oc_potential *P, int td, double dir, double tau, const double y[6], double f[6]) {
     double a[3];
-    accel(P, y, a);
+    accel(P, td, tau * dir, y, a);
     for (int c = 0; c < 3; ++c) { f[c] = y[3 + c] * dir; f[3 + c] = a[c] * dir; }
 }
 
-static double select_initial_step(const oc_potential *P, double dir, const double y0[6], const double f0[6],
-                                  double rtol, double atol, double order) {
+static double select_initial_step(const oc_potential *P, int td, double dir, double tau0, const double y0[6],
+                                  const double f0[6], double rtol, double atol, double order) {
     double sc[6], v[6];
     for (int i = 0; i < 6; ++i) sc[i] = atol + fabs(y0[i]) * rtol;
     for (int i = 0; i < 6; ++i) v[i] = y0[i] / sc[i];
@@ -603,7 +639,7 @@ static double select_initial_step(const oc_potential *P, double dir, const doubl
     double h0 = cond ? 1e-6 : 0.01 * (d0 / d1);
     double y1[6], f1[6];
     for (int i = 0; i < 6; ++i) y1[i] = y0[i] + h0 * f0[i];
-    field_dir(P, dir, y1, f1);
+    field_dir(P, td, dir, tau0 + h0, y1, f1);
     for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
     double d2 = rms6(v) / h0;
     double maxd = fmax(d1, d2);
@@ -619,6 +655,7 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
                         int32_t *status, int32_t *n_acc, int32_t *n_tot) {
     const double order = tab->order;
     const int ns = tab->ns;
+    const int td = is_time_dependent(P);
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t i = 0; i < N; ++i) {
         double t0 = t0v[(int64_t)t0_stride * i];
@@ -633,7 +670,7 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
             ++k;
         }
         double f0[6];
-        field_dir(P, dir, y, f0);
+        field_dir(P, td, dir, T0, y, f0);
         double tprev = T0, tnext;
         double prev_inv = 1.0, prev_prev_inv = 1.0;
         int at_dtmin = 0;
@@ -642,7 +679,7 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
              * is 1/(error_order + 1) (Hairer II.4 with p = order): inferred from the reference's 8-digit OrbitSolver
              * doctests, which this reproduces to 4e-9 (1/error_order: 6e-8, i.e. a different first step). */
             double h = (pid->dt0 > 0.0) ? pid->dt0
-                                        : select_initial_step(P, dir, y, f0, pid->rtol, pid->atol, order + 1.0);
+                                        : select_initial_step(P, td, dir, T0, y, f0, pid->rtol, pid->atol, order + 1.0);
             if (pid->dtmax > 0.0 && isfinite(pid->dtmax)) h = fmin(h, pid->dtmax);
             if (pid->dtmin > 0.0) { at_dtmin = h <= pid->dtmin; h = fmax(h, pid->dtmin); }
             tnext = clip_to_end(T0, T0 + h, T1, 1);
@@ -659,7 +696,7 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
                     for (int j = 0; j < s; ++j) inc += tab->a[s][j] * K[j][c];
                     ys[c] = y[c] + inc;
                 }
-                field_dir(P, dir, ys, flast);
+                field_dir(P, td, dir, tprev + tab->c[s] * h, ys, flast);
                 for (int c = 0; c < 6; ++c) K[s][c] = flast[c] * h;
             }
             /* a[ns-1][:] == b_sol, so ys is y1 and K[ns-1] = f(y1) h (FSAL) */

@@ -49,6 +49,13 @@ class Component:
     kind: int
     params: tuple[float, ...]
     name: str = ""
+    rates: tuple[float, ...] = ()  # LinearParameter (params/core.py:25-110): p_k(t) = params[k] + rates[k] * t
+
+    def params_at(self, t: float) -> tuple[float, ...]:
+        if not self.rates:
+            return self.params
+        r = tuple(self.rates) + (0.0,) * (len(self.params) - len(self.rates))
+        return tuple(p + dp * t for p, dp in zip(self.params, r))
 
 
 @dataclasses.dataclass(frozen=True)
@@ -513,25 +520,25 @@ for _k, (_p, _g, _h) in _NEW.items():
 # composite evaluation, summed in component order (base_multi.py:39-82)
 
 
-def _sum_components(table, pot: Potential, xyz):
+def _sum_components(table, pot: Potential, xyz, t=0.0):
     xyz = np.asarray(xyz, dtype=np.float64)
     total = None
     for grp in pot.group_list():
         sub = None
         for i in grp:
             c = pot.components[i]
-            v = table[c.kind](pot.G, *c.params, xyz)
+            v = table[c.kind](pot.G, *c.params_at(float(t)), xyz)
             sub = v if sub is None else sub + v
         total = sub if total is None else total + sub
     return total
 
 
 def potential(pot: Potential, xyz, t=0.0):
-    return _sum_components(_POT, pot, xyz)
+    return _sum_components(_POT, pot, xyz, t)
 
 
 def gradient(pot: Potential, xyz, t=0.0):
-    return _sum_components(_GRAD, pot, xyz)
+    return _sum_components(_GRAD, pot, xyz, t)
 
 
 def acceleration(pot: Potential, xyz, t=0.0):
@@ -540,7 +547,7 @@ def acceleration(pot: Potential, xyz, t=0.0):
 
 
 def hessian(pot: Potential, xyz, t=0.0):
-    return _sum_components(_HESS, pot, xyz)
+    return _sum_components(_HESS, pot, xyz, t)
 
 
 def laplacian(pot: Potential, xyz, t=0.0):

@@ -41,8 +41,8 @@ def test_library_is_sm100a_native(built_lib):
 def test_struct_layout_matches_header():
     from galax_b200 import _lib
 
-    assert C.sizeof(_lib.GxComponent) == 72
-    assert C.sizeof(_lib.GxPotential) == 16 + 72 * _lib.GX_MAX_COMPONENTS
+    assert C.sizeof(_lib.GxComponent) == 8 + 64 + 64  # kind, reserved, p[8], dp[8]
+    assert C.sizeof(_lib.GxPotential) == 16 + 136 * _lib.GX_MAX_COMPONENTS
     assert C.sizeof(_lib.GxPid) == 8 * 10 + 8 + 8
 
 

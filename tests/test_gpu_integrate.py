@@ -306,6 +306,59 @@ def test_adaptive_launches_with_different_potentials_on_two_streams():
         assert torch.equal(o, refA if tag == "A" else refB), tag
 
 
+def test_time_dependent_linear_parameters():
+    """LinearParameter (potential/_src/params/core.py:25-110): the reference's own doctest (Kepler losing mass, rho at 10
+    saves to 3 decimals) through compute_orbit; frozen-time bulk evaluation; fixed-step and Dopri8 orbits of a
+    composite with growing disk and halo against the oracle; unsupported combinations fail loudly."""
+    case = KATS["time_dependent"][0]
+    lp = gp.LinearParameter(slope=case["slope_msun_per_myr"], point_time=case["point_time"], point_value=case["point_value"])
+    pot = gp.KeplerPotential(m_tot=lp)
+    assert pot.is_time_dependent and not gp.KeplerPotential(1e12).is_time_dependent
+    w0 = gd.PhaseSpaceCoordinate(np.array(case["q0"]), np.array(case["p0_kms"]) * KMS, case["t0"])
+    orbit = gd.compute_orbit(pot, w0, np.linspace(case["t0"], case["t1"], case["n_saves"]))
+    assert np.allclose(np.hypot(orbit.q[:, 0], orbit.q[:, 1]), case["rho"], atol=case["atol"], rtol=0)
+
+    mix = gp.CompositePotential(
+        disk=gp.MiyamotoNagaiPotential(gp.LinearParameter(1e7, 0.0, 6.8e10), gp.LinearParameter(1e-4, 100.0, 3.01), 0.28),
+        halo=gp.NFWPotential(gp.LinearParameter(2e8, 0.0, 5.4e11), gp.LinearParameter(1e-3, 0.0, 15.62)),
+        bulge=gp.HernquistPotential(5e9, 1.0), nuc=gp.JaffePotential(gp.LinearParameter(-1e5, 0.0, 1e9), 0.3),
+        iso=gp.IsochronePotential(3e9, gp.LinearParameter(1e-4, 0.0, 2.0)), sat=gp.SatohPotential(2e9, 3.0, gp.LinearParameter(1e-5, 0.0, 0.4)),
+        tri=gp.TriaxialHernquistPotential(gp.LinearParameter(1e6, 0.0, 4e9), 0.8, 0.9, gp.LinearParameter(1e-5, 0.0, 0.7)))
+    omix = op.Potential((
+        op.Component(op.KIND_MN, (6.8e10, 3.0, 0.28), rates=(1e7, 1e-4, 0.0)), op.Component(op.KIND_NFW, (5.4e11, 15.62), rates=(2e8, 1e-3)),
+        op.Component(op.KIND_HERNQUIST, (5e9, 1.0)), op.Component(op.KIND_JAFFE, (1e9, 0.3), rates=(-1e5, 0.0)),
+        op.Component(op.KIND_ISOCHRONE, (3e9, 2.0), rates=(0.0, 1e-4)), op.Component(op.KIND_SATOH, (2e9, 3.0, 0.4), rates=(0.0, 0.0, 1e-5)),
+        op.Component(op.KIND_TRIAXIAL_HERNQUIST, (4e9, 0.8, 0.9, 0.7), rates=(1e6, 0.0, 0.0, 1e-5))))
+    xyz = np.random.default_rng(4).normal(size=(2000, 3)) * 8
+    for t in (0.0, 730.0):
+        go = op.gradient(omix, xyz, t)
+        assert (np.abs(mix.gradient(xyz, t) - go) / np.linalg.norm(go, axis=1, keepdims=True)).max() < 5e-15
+        Ho = op.hessian(omix, xyz, t)
+        assert (np.abs(mix.hessian(xyz, t) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 5e-13
+    q0, p0 = synthetic_ics(op.milky_way_potential(), 256, seed=41)
+    sie = gd.OrbitSolver(solver=gd.SemiImplicitEuler(), stepsize_controller=gd.ConstantStepSize(), max_steps=None)
+    sol = sie.solve(mix, (q0, p0), 0.0, 500.0, dt0=0.1)
+    qr, pr, st, n = cref.integrate_fixed(omix, q0, p0, 0.0, 500.0, 0.1, [500.0])
+    rel = np.linalg.norm(sol.ys[0][:, 0] - qr[:, 0], axis=-1) / np.linalg.norm(qr[:, 0], axis=-1)
+    assert np.median(rel) < 1e-13 and np.mean(rel < 1e-11) > 0.95
+    frozen = sie.solve(gp.CompositePotential(disk=gp.MiyamotoNagaiPotential(6.8e10, 3.0, 0.28), halo=gp.NFWPotential(5.4e11, 15.62)),
+                       (q0, p0), 0.0, 500.0, dt0=0.1)
+    assert np.abs(frozen.ys[0] - sol.ys[0]).max() > 1e-2  # the time dependence matters
+    ts = np.linspace(0.0, 500.0, 6)
+    for t0, t1, tsv in ((0.0, 500.0, ts), (500.0, 0.0, ts[::-1].copy())):  # forward and backward in time
+        so = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=1e-9, atol=1e-9)).solve(mix, (q0, p0), t0, t1, saveat=tsv)
+        qd, pd, *_ = cref.integrate_dopri8(omix, q0, p0, t0, t1, tsv, rtol=1e-9, atol=1e-9)
+        d = np.abs(so.ys[0] - qd).max(axis=(1, 2))
+        assert np.median(d) < 1e-7 and np.quantile(d, 0.9) < 1e-5, (t0, np.median(d), np.quantile(d, 0.9))
+    # not supported: time-dependent kinds outside the integrators' set, stream release, energies
+    bad = gp.CompositePotential(b=gp.PowerLawCutoffPotential(gp.LinearParameter(1e5, 0.0, 5e9), 1.8, 1.9))
+    assert np.isfinite(bad.gradient(xyz[:4], 100.0)).all()  # frozen-time evaluation works for every kind
+    with pytest.raises(Exception):
+        sie.solve(bad, (q0[:4], p0[:4]), 0.0, 10.0, dt0=0.1)
+    with pytest.raises(NotImplementedError):
+        gp.MN3Sech2Potential(gp.LinearParameter(1.0, 0.0, 4.7e10), 2.6, 0.3)._flat_components()
+
+
 def test_phase_space_diagnostics_on_device():
     """kinetic / potential / total energy and angular momentum of PhaseSpaceCoordinate and Orbit
     (coordinates/_src/pscs/base.py:182-330; doctest :304-317: q = [1,0,0], p = [0,2,0] -> L = [0,0,2])."""

@@ -233,3 +233,35 @@ def test_reference_integrate_field_doctest_given_its_first_step():
         for row, ref in case["rows"].items():
             assert np.allclose(q[0, int(row)], ref["q"], atol=ref["atol"], rtol=0)
             assert np.allclose(p[0, int(row)], ref["p"], atol=ref["atol"], rtol=0)
+
+
+def test_reference_linear_parameter_doctest_and_time_dependent_oracles_agree():
+    """potential/_src/params/core.py:52-74: a Kepler potential losing mass linearly; cylindrical radius at 10 saves
+    printed to 3 decimals.  Also: numpy and C oracles agree on time-dependent composites, frozen-time evaluation and
+    a fixed-step run with a growing halo."""
+    case = KATS["time_dependent"][0]
+    pot = op.Potential((op.Component(op.KIND_HERNQUIST, (case["point_value"] - case["slope_msun_per_myr"] * case["point_time"], 0.0),
+                                     rates=(case["slope_msun_per_myr"], 0.0)),))
+    ts = np.linspace(case["t0"], case["t1"], case["n_saves"])
+    q, p, st, na, nt = cref.integrate_dopri8(pot, [case["q0"]], [np.array(case["p0_kms"]) * KATS["kms"]], case["t0"], case["t1"], ts,
+                                             rtol=case["rtol"], atol=case["atol_solver"])
+    assert st[0] == 0 and np.allclose(np.hypot(q[0, :, 0], q[0, :, 1]), case["rho"], atol=case["atol"], rtol=0)
+    # frozen-time evaluation: numpy == C, and equals the static potential with the parameters of that time
+    mix = op.Potential((op.Component(op.KIND_MN, (6.8e10, 3.0, 0.28), rates=(1e7, 1e-4, 0.0)),
+                        op.Component(op.KIND_NFW, (5.4e11, 15.62), rates=(2e8, 1e-3)),
+                        op.Component(op.KIND_HERNQUIST, (5e9, 1.0))))
+    x = np.random.default_rng(0).normal(size=(50, 3)) * 8
+    t = 730.0
+    static = op.Potential((op.Component(op.KIND_MN, (6.8e10 + 1e7 * t, 3.0 + 1e-4 * t, 0.28)),
+                           op.Component(op.KIND_NFW, (5.4e11 + 2e8 * t, 15.62 + 1e-3 * t)), op.Component(op.KIND_HERNQUIST, (5e9, 1.0))))
+    c = cref.potential_eval(mix, x, ("phi", "grad", "hess"), t=t)
+    assert np.allclose(c["grad"], op.gradient(mix, x, t), rtol=1e-14) and np.allclose(c["grad"], op.gradient(static, x), rtol=1e-14)
+    assert np.allclose(c["hess"], op.hessian(static, x), rtol=1e-12, atol=1e-18) and np.allclose(c["phi"], op.potential(static, x), rtol=1e-14)
+    # a growing halo changes the orbit; zero rates reproduce the static run bit for bit
+    q0, p0 = np.array([[8.0, 0.0, 1.0]]), np.array([[0.0, 0.2, 0.02]])
+    qa, pa, *_ = cref.integrate_fixed(mix, q0, p0, 0.0, 500.0, 0.1, [500.0])
+    frozen0 = op.Potential(tuple(op.Component(cc.kind, cc.params) for cc in mix.components))
+    qb, pb, *_ = cref.integrate_fixed(frozen0, q0, p0, 0.0, 500.0, 0.1, [500.0])
+    zero = op.Potential(tuple(op.Component(cc.kind, cc.params, rates=(0.0,) * len(cc.params)) for cc in mix.components))
+    qc, pc, *_ = cref.integrate_fixed(zero, q0, p0, 0.0, 500.0, 0.1, [500.0])
+    assert np.array_equal(qb, qc) and np.abs(qa - qb).max() > 1e-3

@@ -105,13 +105,18 @@ def test_fardal2015df_parameters_and_stream_simulator():
     sim = ge.StreamSimulator()
     ics = sim.init(pot, (x, np.array([0.0, 0.225, 0.0])), 0.0, release_times=release, Msat=1e5, key=0)
     assert ics.qp_lead[0].shape == (M, 3) and np.isfinite(ics.qp_trail[1]).all() and ics.prog_mass.shape == (M,)
-    # the reference's doctest of StreamSimulator.init(..., key=jr.key(0)) (experimental/stream.py:79-106); the Dopri5
-    # progenitor orbit with forced dtmin = 0.3 is only good to ~1e-3, the PRNG-driven z-offsets to 3e-4
-    assert np.allclose(ics.qp_lead[0][0], [-10.76187104, -7.35400639, 0.0674116], atol=8e-3)
-    assert np.allclose(ics.qp_lead[0][-1], [-4.72896837, 14.03657666, -0.09171104], atol=8e-3)
-    assert np.isclose(ics.qp_lead[0][0, 2], 0.0674116, rtol=5e-4)
+    # the reference's doctest of StreamSimulator.init(..., key=jr.key(0)) and .run (experimental/stream.py:79-118): all
+    # printed digits (the GPU's step sequence can differ from the reference's in the last bits: 1e-6 margin)
+    assert np.allclose(ics.qp_lead[0][0], [-10.76187104, -7.35400639, 0.0674116], rtol=0, atol=1e-6)
+    assert np.allclose(ics.qp_lead[0][-1], [-4.72896837, 14.03657666, -0.09171104], rtol=0, atol=1e-6)
+    assert np.allclose(ics.qp_trail[0][0], [-11.00416221, -7.5195734, 0.0674116], rtol=0, atol=1e-6)
+    assert np.allclose(ics.qp_lead[1][0], [4.77386246e-02, -2.74264308e-01, -4.68601912e-04], rtol=0, atol=1e-7)
+    assert np.allclose(ics.qp_trail[1][-1], [-2.10223491e-01, -8.18272245e-02, -1.58559419e-04], rtol=0, atol=1e-7)
     lead, trail = sim.run(pot, ics, t1=0.0)
     assert lead[0].shape == (M, 3) and trail[1].shape == (M, 3) and np.isfinite(lead[0]).all()
+    assert np.allclose(lead[0][0], [-4.99685677e00, 5.65910858e00, 3.63136282e-02], rtol=0, atol=2e-5)
+    assert np.allclose(lead[0][-1], [1.48125263e01, 3.73149460e-01, 4.11255117e-02], rtol=0, atol=2e-6)
+    assert np.allclose(lead[1][-1], [-1.39058722e-02, 2.24719748e-01, -1.28802309e-03], rtol=0, atol=2e-7)
     # oracle: same ICs through the Dopri5 oracle with dtmin = 0.3
     qr, pr, st, na, nt = cref.integrate_dopri8(opot, ics.qp_lead[0][:200], ics.qp_lead[1][:200], release[:200], 0.0, [0.0],
                                                rtol=1e-7, atol=1e-7, dtmin=0.3, max_steps=10_000, solver="dopri5")

@@ -30,11 +30,13 @@ def test_reference_doctest_fardal2015df_sample_key0():
     assert np.allclose(pt[0], [0.0, 2.19977919e02, 6.34205795e-03], rtol=2e-9, atol=1e-12)
 
 
-def test_reference_doctest_stream_simulator_init_key0():
-    """experimental/stream.py:79-106: StreamSimulator().init(Hernquist(1e12, 10), qp0, 0, release_times=
-    linspace(-4000, -150, 2000), Msat=1e5, key=jr.key(0)).  The progenitor orbit uses Dopri5 with dtmin = 0.3
-    (forced steps: global error ~1e-3 and sensitive to the step sequence), so positions agree to that level; the
-    z-offsets, which come from the PRNG chain times the tidal radius, agree to 2e-4."""
+def test_reference_doctest_stream_simulator_init_and_run_key0():
+    """experimental/stream.py:79-118: StreamSimulator().init(Hernquist(1e12, 10), qp0, 0, release_times=
+    linspace(-4000, -150, 2000), Msat=1e5, key=jr.key(0)) and .run(pot, ics, t1=0): every printed number (positions,
+    velocities, both arms, first and last particle) to the last digit.  One chain pins Dopri5 (diffrax's embedded
+    weights: error = 2/3 of the textbook Dormand-Prince estimate), PIDController with forced dtmin = 0.3, the Dopri5
+    dense output at the 2000 release times, the backward first leg, the jax PRNG key chain, Fardal2015DF and the tidal
+    radius, and the per-particle start times of the final integration."""
     pot = op.single(op.KIND_HERNQUIST, 1e12, 10.0)
     rel = np.linspace(-4000.0, -150.0, 2000)
     kw = dict(rtol=1e-7, atol=1e-7, dtmin=0.3, max_steps=10_000, solver="dopri5")
@@ -43,11 +45,23 @@ def test_reference_doctest_stream_simulator_init_key0():
     assert st[0] == 0 and st2[0] == 0
     draws = jr.fardal_draws_per_key(jr.split_chain(jr.key(0), 2000))
     ql, pl, qt, pt = cref.release_fardal(pot, Q[0], P[0], 1e5, draws)
-    assert np.allclose(ql[0], [-10.76187104, -7.35400639, 0.0674116], atol=6e-3)
-    assert np.allclose(ql[-1], [-4.72896837, 14.03657666, -0.09171104], atol=6e-3)
-    assert np.allclose(qt[0], [-11.00416221, -7.5195734, 0.0674116], atol=6e-3)
-    assert np.isclose(ql[0, 2], 0.0674116, rtol=3e-4) and np.isclose(ql[-1, 2], -0.09171104, rtol=3e-4)
-    assert np.allclose(pl[0], [4.77386246e-02, -2.74264308e-01, -4.68601912e-04], atol=3e-4)
+    A = dict(rtol=0, atol=6e-9)
+    assert np.allclose(ql[0], [-10.76187104, -7.35400639, 0.0674116], **A)
+    assert np.allclose(ql[-1], [-4.72896837, 14.03657666, -0.09171104], **A)
+    assert np.allclose(qt[0], [-11.00416221, -7.5195734, 0.0674116], **A)
+    assert np.allclose(qt[-1], [-4.83974586, 14.36538765, -0.09171104], **A)
+    V = dict(rtol=0, atol=6e-10)
+    assert np.allclose(pl[0], [4.77386246e-02, -2.74264308e-01, -4.68601912e-04], **V)
+    assert np.allclose(pl[-1], [-2.09972781e-01, -8.17427593e-02, -1.58559419e-04], **V)
+    assert np.allclose(pt[0], [5.07429914e-02, -2.78660906e-01, -4.68601912e-04], **V)
+    assert np.allclose(pt[-1], [-2.10223491e-01, -8.18272245e-02, -1.58559419e-04], **V)
+    # .run: every particle from its release time to t1 = 0 (the oldest one over 4 Gyr: 5e-8)
+    qr, pr, st3, _, _ = cref.integrate_dopri8(pot, ql, pl, rel, 0.0, [0.0], **kw)
+    assert (st3 == 0).all()
+    assert np.allclose(qr[0, 0], [-4.99685677e00, 5.65910858e00, 3.63136282e-02], rtol=0, atol=1e-7)
+    assert np.allclose(qr[-1, 0], [1.48125263e01, 3.73149460e-01, 4.11255117e-02], rtol=0, atol=1e-7)
+    assert np.allclose(pr[0, 0], [-3.87842191e-01, -2.21692094e-01, 2.45336141e-03], rtol=0, atol=1e-8)
+    assert np.allclose(pr[-1, 0], [-1.39058722e-02, 2.24719748e-01, -1.28802309e-03], rtol=0, atol=1e-8)
 
 
 def test_split_chain_and_vectorised_draws_are_consistent():

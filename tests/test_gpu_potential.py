@@ -277,3 +277,63 @@ def test_fast_math_primitives(built_lib):
         xs = 10 ** rng.uniform(-8, 2.7, 20000)
         g = run(3, a=a, src=torch.tensor(xs, device="cuda"))
         assert np.abs(g / sps.gammainc(a, xs) - 1).max() < 2e-14
+
+
+def _random_composite(rng):
+    """A random composite of 2-6 components drawn from all 13 kinds (parameters in plausible galactic ranges)."""
+    makers = [
+        lambda: (gp.MiyamotoNagaiPotential, op.KIND_MN, (10 ** rng.uniform(9, 11), rng.uniform(1, 6), rng.uniform(0.1, 1))),
+        lambda: (gp.HernquistPotential, op.KIND_HERNQUIST, (10 ** rng.uniform(9, 12), rng.uniform(0.05, 10))),
+        lambda: (gp.NFWPotential, op.KIND_NFW, (10 ** rng.uniform(10, 12), rng.uniform(5, 30))),
+        lambda: (gp.PowerLawCutoffPotential, op.KIND_PLC, (10 ** rng.uniform(9, 10.5), 1.8, rng.uniform(1, 3))),
+        lambda: (gp.LMJ09LogarithmicPotential, op.KIND_LOG, (rng.uniform(100, 250) * gp.KMS, rng.uniform(1, 15), rng.uniform(0.8, 1.4),
+                                                            rng.uniform(0.8, 1.2), rng.uniform(0.7, 1.4), rng.uniform(0, 3))),
+        lambda: (gp.IsochronePotential, op.KIND_ISOCHRONE, (10 ** rng.uniform(9, 11), rng.uniform(0.5, 5))),
+        lambda: (gp.SatohPotential, op.KIND_SATOH, (10 ** rng.uniform(9, 11), rng.uniform(1, 6), rng.uniform(0.1, 1))),
+        lambda: (gp.TriaxialHernquistPotential, op.KIND_TRIAXIAL_HERNQUIST, (10 ** rng.uniform(9, 11), rng.uniform(0.3, 5),
+                                                                             rng.uniform(0.7, 1.3), rng.uniform(0.4, 1.2))),
+        lambda: (gp.JaffePotential, op.KIND_JAFFE, (10 ** rng.uniform(8, 10), rng.uniform(0.1, 2))),
+        lambda: (gp.BurkertPotential, op.KIND_BURKERT, (10 ** rng.uniform(9, 11), rng.uniform(1, 10))),
+        lambda: (gp.StoneOstriker15Potential, op.KIND_STONE, (10 ** rng.uniform(9, 11), rng.uniform(0.2, 2), rng.uniform(5, 40))),
+        lambda: (gp.HenonHeilesPotential, op.KIND_HENON_HEILES, (rng.uniform(0.001, 0.01), rng.uniform(50, 200))),
+    ]
+    picks, used = [], {}
+    for _ in range(int(rng.integers(2, 7))):
+        k = int(rng.integers(0, len(makers)))
+        # device-side capacity per kind (gx_potential.cuh MAX_*): 1 PowerLawCutoff / Henon-Heiles, 2 of most others
+        cap = {0: 6, 1: 4, 3: 1, 11: 1}.get(k, 2)
+        group = k if k not in (7, 8, 9, 10) else 7  # the four ellipsoidal-radius profiles share MAX_RAD = 4
+        cap = 4 if group == 7 else cap
+        if used.get(group, 0) >= cap:
+            continue
+        used[group] = used.get(group, 0) + 1
+        picks.append(makers[k]())
+    comps = {f"c{i}": cls(*params) for i, (cls, _, params) in enumerate(picks)}
+    return gp.CompositePotential(comps), op.Potential(tuple(op.Component(kind, tuple(params)) for _, kind, params in picks))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_composites_all_kinds_against_oracle(seed):
+    """Differential test: random composites of every kind through K1 (Phi, grad, Hessian) and a short K2 run."""
+    import galax_b200.dynamics as gd
+    from oracle import cref
+
+    rng = np.random.default_rng(1000 + seed)
+    pot, opot = _random_composite(rng)
+    xyz = points(3000, seed=seed, lo=-1.5, hi=2.0)
+    go = op.gradient(opot, xyz)
+    gsc = np.linalg.norm(go, axis=1, keepdims=True)
+    assert (np.abs(pot.gradient(xyz) - go) / gsc).max() < 3e-14
+    Ho = op.hessian(opot, xyz)
+    assert (np.abs(pot.hessian(xyz) - Ho) / np.abs(Ho).max(axis=(1, 2), keepdims=True)).max() < 2e-12
+    phio = op.potential(opot, xyz)
+    assert np.all(np.abs(pot.potential(xyz) - phio) <= 2e-13 * np.abs(phio) + 1e-15 * np.abs(phio).max())
+    q0 = points(64, seed=100 + seed, lo=0.5, hi=1.3)
+    vc = np.sqrt(np.linalg.norm(op.gradient(opot, q0), axis=1) * np.linalg.norm(q0, axis=1))
+    d = rng.normal(size=(64, 3))
+    p0 = d / np.linalg.norm(d, axis=1, keepdims=True) * (0.7 * vc)[:, None]
+    sie = gd.OrbitSolver(solver=gd.SemiImplicitEuler(), stepsize_controller=gd.ConstantStepSize(), max_steps=None)
+    sol = sie.solve(pot, (q0, p0), 0.0, 100.0, dt0=0.05)
+    qr, pr, st, n = cref.integrate_fixed(opot, q0, p0, 0.0, 100.0, 0.05, [100.0])
+    rel = np.linalg.norm(sol.ys[0][:, 0] - qr[:, 0], axis=-1) / np.linalg.norm(qr[:, 0], axis=-1)
+    assert np.median(rel) < 1e-13 and np.quantile(rel, 0.9) < 1e-10

@@ -1409,6 +1409,69 @@ int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void
     return cuda_rc(cudaGetLastError());
 }
 
+__host__ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t &o0,
+                                                      uint32_t &o1) {
+    const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+    uint32_t x0 = c0 + ks[0], x1 = c1 + ks[1];
+    const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+    for (int g = 0; g < 5; ++g) {
+        for (int j = 0; j < 4; ++j) {
+            x0 += x1;
+            x1 = ((x1 << R[g & 1][j]) | (x1 >> (32 - R[g & 1][j]))) ^ x0;
+        }
+        x0 += ks[(g + 1) % 3];
+        x1 += ks[(g + 2) % 3] + (uint32_t)(g + 1);
+    }
+    o0 = x0;
+    o1 = x1;
+}
+
+// draws[j][i] = normal(split(subkey_i, 4)[j], ()): key_j = threefry(subkey, counter j), bits = threefry(key_j, counter 0)
+__global__ void __launch_bounds__(256) k_jax_fardal_per_key(const uint2 *subkeys, long long M, double *draws) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const uint2 sk = subkeys[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t kj0, kj1, b0, b1;
+        threefry2x32(sk.x, sk.y, 0u, (uint32_t)j, kj0, kj1);
+        threefry2x32(kj0, kj1, 0u, 0u, b0, b1);
+        const unsigned long long bits = ((unsigned long long)b0 << 32) | b1;
+        const double fl = __longlong_as_double((long long)((bits >> 12) | 0x3FF0000000000000ULL)) - 1.0;
+        const double lo = -0.99999999999999988898;
+        const double u = fmax(lo, __dadd_rn(__dmul_rn(fl, 1.0 - lo), lo));
+        draws[(long long)j * M + i] = 1.41421356237309514547 * erfinv(u);
+    }
+}
+
+int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *stream) {
+    if (M < 0 || (M > 0 && !draws)) return GX_ERR_BADARG;
+    if (M == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint2 *h = (uint2 *)malloc((size_t)M * sizeof(uint2));
+    if (!h) return GX_ERR_CUDA;
+    uint32_t a = key_hi, b = key_lo;
+    for (int64_t i = 0; i < M; ++i) {  // key, subkey = split(key): split(key)[c] = threefry(key, counter c)
+        uint32_t n0, n1;
+        threefry2x32(a, b, 0u, 1u, h[i].x, h[i].y);
+        threefry2x32(a, b, 0u, 0u, n0, n1);
+        a = n0;
+        b = n1;
+    }
+    uint2 *d = nullptr;
+    int rc = 0;
+    if (cudaMallocAsync((void **)&d, (size_t)M * sizeof(uint2), s) != cudaSuccess) { free(h); return GX_ERR_CUDA; }
+    if (cudaMemcpyAsync(d, h, (size_t)M * sizeof(uint2), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = GX_ERR_CUDA;
+    if (!rc) {
+        k_jax_fardal_per_key<<<grid_for(M, 256), 256, 0, s>>>(d, (long long)M, draws);
+        rc = cuda_rc(cudaGetLastError());
+    }
+    cudaStreamSynchronize(s);  // the pageable staging buffer must outlive the copy
+    cudaFreeAsync(d, s);
+    free(h);
+    return rc;
+}
+
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream) {
     if (N < 0 || (N > 0 && (!x || !out))) return GX_ERR_BADARG;
     if (N == 0) return 0;

@@ -137,19 +137,35 @@ def _is_key_data(key) -> bool:
     return isinstance(key, np.ndarray) and key.dtype == np.uint32 and key.shape == (2,)
 
 
-def _fardal_normals(key, M: int) -> np.ndarray:
-    """(4, M) standard normals: an int seed / uint32[2] key reproduces jax's stream (``jaxrandom``), a
-    ``numpy.random.Generator`` uses numpy's, a float array is taken as the draws themselves."""
+def _fardal_normals(key, M: int):
+    """(4, M) standard normals on the device: an int seed / uint32[2] key reproduces jax's stream (``jr.split(key, 4)``,
+    each ``jr.normal(k_i, (M,))``, generated by ``gx_jax_normal``), a ``numpy.random.Generator`` uses numpy's, a float
+    array / tensor is taken as the draws themselves."""
     import torch
 
     from . import jaxrandom
+    from .dynamics import _device_jax_normal
 
     if isinstance(key, np.random.Generator):
-        return key.standard_normal((4, M))
+        return torch.from_numpy(key.standard_normal((4, M))).to("cuda")
     if isinstance(key, (int, np.integer)) or _is_key_data(key):
-        return jaxrandom.fardal_draws(key, M)
-    arr = key.detach().cpu().numpy() if isinstance(key, torch.Tensor) else np.asarray(key)
-    return np.asarray(arr, dtype=np.float64).reshape(4, M)
+        k = jaxrandom.key(key) if isinstance(key, (int, np.integer)) else np.asarray(key, dtype=np.uint32)
+        ks = jaxrandom.split(k, 4)
+        return torch.stack([_device_jax_normal(ks[i], M) for i in range(4)])
+    if isinstance(key, torch.Tensor):
+        return key.to(device="cuda", dtype=torch.float64).reshape(4, M)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(key, dtype=np.float64).reshape(4, M))).to("cuda")
+
+
+def _fardal_chain_normals(key_data, M: int):
+    """(4, M) normals of the ``StreamSimulator.init`` scan (``key, subkey = jr.split(key)`` per release time, then four
+    scalar normals on ``jr.split(subkey, 4)``): ``gx_jax_fardal_chain`` -- key chain on the host, draws on the device."""
+    torch = _lib.require_cuda()
+    out = torch.empty((4, M), dtype=torch.float64, device="cuda")
+    rc = _lib.lib().gx_jax_fardal_chain(int(key_data[0]), int(key_data[1]), M, out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "gx_jax_fardal_chain")
+    return out
 
 
 @dataclasses.dataclass(frozen=True)
@@ -184,16 +200,14 @@ class Fardal2015DF:
         scalar = dq.ndim == 1
         dq, dp = dq.reshape(-1, 3).contiguous(), dp.reshape(-1, 3).contiguous()
         M = dq.shape[0]
-        n = _fardal_normals(key, M)
+        n = _fardal_normals(key, M).to(dq.device)
         # affine map of the draws onto the kernel's fixed constants (2, 0.3, 0, 0; all sigmas 0.5)
-        n_eff = np.empty_like(n)
-        n_eff[0] = (self.kr_bar - 2.0 + self.sigma_kr * n[0]) / 0.5
-        n_eff[1] = (self.kvphi_bar - 0.3 + self.sigma_kvphi * n[1]) / 0.5
-        n_eff[2] = (self.kz_bar + self.sigma_kz * n[2]) / 0.5
-        n_eff[3] = (self.kvz_bar + self.sigma_kvz * n[3]) / 0.5
+        dd = torch.stack([(self.kr_bar - 2.0 + self.sigma_kr * n[0]) / 0.5,
+                          (self.kvphi_bar - 0.3 + self.sigma_kvphi * n[1]) / 0.5,
+                          (self.kz_bar + self.sigma_kz * n[2]) / 0.5,
+                          (self.kvz_bar + self.sigma_kvz * n[3]) / 0.5]).contiguous()
         mass = np.broadcast_to(np.asarray(Msat, dtype=np.float64), (M,)).copy()
         dm = torch.from_numpy(mass).to(dq.device)
-        dd = torch.from_numpy(np.ascontiguousarray(n_eff)).to(dq.device)
         outs = [torch.empty((M, 3), dtype=torch.float64, device=dq.device) for _ in range(4)]
         import ctypes as C
 
@@ -242,7 +256,7 @@ class StreamSimulator:
         mass = np.broadcast_to(np.asarray(Msat, dtype=np.float64), rel.shape).copy()
         if isinstance(key, (int, np.integer)) or _is_key_data(key):
             k = jaxrandom.key(key) if isinstance(key, (int, np.integer)) else key
-            draws = jaxrandom.fardal_draws_per_key(jaxrandom.split_chain(k, M))
+            draws = _fardal_chain_normals(k, M)
         else:
             draws = _fardal_normals(key, M)
         ql, pl, qt, pt = df.sample(draws, pot, rel, xq, xp, mass)

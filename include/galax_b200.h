@@ -208,6 +208,11 @@ int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, 
  * shape (M, 6), then the SVD factor) so that a seeded stream needs no host-side random numbers.  Integer part exact;
  * erfinv is CUDA's (XLA's differs at the 1e-16 level). */
 int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void *stream);
+/* The draws of the experimental StreamSimulator.init scan (experimental/stream.py:212-226, experimental/df.py:146-163):
+ * `for i in range(M): key, subkey = jr.split(key); Fardal2015DF.sample(subkey, ...)`, each sample being four scalar
+ * normals `jr.normal(k_j, ())` on `jr.split(subkey, 4)`.  The key chain is inherently sequential and runs on the host
+ * (integer arithmetic, ~50 ns per link); the 4 M normals are computed on the device.  draws: device [4][M]. */
+int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *stream);
 /* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x) */
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream);
 

@@ -123,6 +123,24 @@ def test_fardal2015df_parameters_and_stream_simulator():
     assert np.median(np.abs(lead[0][:200] - qr[:, 0]).max(axis=1)) < 1e-3
 
 
+def test_stream_simulator_key_chain_draws_on_device():
+    """gx_jax_fardal_chain (host key chain + device normals) against the numpy restatement, and a 2e5-release init."""
+    import time
+
+    from galax_b200 import jaxrandom as jr
+
+    k = jr.key(3)
+    d = ge._fardal_chain_normals(k, 3000).cpu().numpy()
+    ref = jr.fardal_draws_per_key(jr.split_chain(k, 3000))
+    assert np.abs(d - ref).max() < 1e-14 * np.abs(ref).max()
+    pot = gp.HernquistPotential(1e12, 10.0)
+    M = 200_000
+    t0 = time.perf_counter()
+    ics = ge.StreamSimulator().init(pot, (np.array([15.0, 0.0, 0.0]), np.array([0.0, 0.225, 0.0])), 0.0,
+                                    release_times=np.linspace(-4000.0, -150.0, M), Msat=1e5, key=0)
+    assert time.perf_counter() - t0 < 5.0 and np.isfinite(ics.qp_lead[0]).all() and ics.qp_lead[0].shape == (M, 3)
+
+
 def test_reference_experimental_integrate_orbit_doctest_on_gpu():
     """experimental/integrate.py:159-247 through the GPU path: 8 decimals, incl. a dense-output value."""
     import json

@@ -359,6 +359,18 @@ def test_time_dependent_linear_parameters():
         gp.MN3Sech2Potential(gp.LinearParameter(1.0, 0.0, 4.7e10), 2.6, 0.3)._flat_components()
 
 
+def test_reference_tidal_radius_doctests_through_release_kernel():
+    """cluster/api.py:54-64,70-76,180-198 (lagrange_points / tidal_radius doctests): with all Fardal draws zero the
+    release kernel places the leading particle at x - 2 r_t r_hat, so r_t is read off K4 directly."""
+    from test_oracle_integrators import TIDAL_KATS
+
+    for name, x, v, mass, rt in TIDAL_KATS:
+        pot = gp.MilkyWayPotential() if name == "MilkyWayPotential" else gp.NFWPotential(1e12, 20.0)
+        orbit = gd.Orbit(np.array([x]), np.array([v]), np.array([0.0]))
+        out = gd.FardalStreamDF().sample(np.zeros((4, 1)), pot, orbit, mass)
+        assert abs((x[0] - out["lead"].q[0, 0]) / 2 - rt) < 6e-9 and abs((out["trail"].q[0, 0] - x[0]) / 2 - rt) < 6e-9, name
+
+
 def test_phase_space_diagnostics_on_device():
     """kinetic / potential / total energy and angular momentum of PhaseSpaceCoordinate and Orbit
     (coordinates/_src/pscs/base.py:182-330; doctest :304-317: q = [1,0,0], p = [0,2,0] -> L = [0,0,2])."""

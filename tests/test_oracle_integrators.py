@@ -265,3 +265,20 @@ def test_reference_linear_parameter_doctest_and_time_dependent_oracles_agree():
     zero = op.Potential(tuple(op.Component(cc.kind, cc.params, rates=(0.0,) * len(cc.params)) for cc in mix.components))
     qc, pc, *_ = cref.integrate_fixed(zero, q0, p0, 0.0, 500.0, 0.1, [500.0])
     assert np.array_equal(qb, qc) and np.abs(qa - qb).max() > 1e-3
+
+
+TIDAL_KATS = [  # (potential, x [kpc], v [kpc/Myr], mass, r_t [kpc]) -- dynamics/_src/cluster/api.py:54-64,70-76,180-198
+    ("MilkyWayPotential", [8.0, 0.0, 0.0], [0.0, 220.0 * 0.001022712165045695, 0.0], 1e4, 0.02929074),
+    ("MilkyWayPotential", [8.0, 0.0, 0.0], [0.0, 220.0, 0.0], 1e4, 0.00039036),
+    ("NFW(1e12, 20)", [8.0, 0.0, 0.0], [8.0, 1e-7, 0.0], 1e4, 0.06362008),  # radial orbit; a 1e-7 tangential part fixes the plane
+]
+
+
+def test_reference_tidal_radius_and_lagrange_point_doctests():
+    """King (1962) tidal radius r_t = cbrt(G m / (Omega^2 - d2Phi/dr2)) (cluster/radius.py:198-215), read off the release
+    kernel with all Fardal draws zero (k_r = 2: x_lead = x - 2 r_t r_hat): the reference's lagrange_points / tidal_radius
+    doctest values to all printed digits."""
+    for name, x, v, mass, rt in TIDAL_KATS:
+        pot = op.milky_way_potential() if name == "MilkyWayPotential" else op.single(op.KIND_NFW, 1e12, 20.0)
+        ql, pl, qt, pt = cref.release_fardal(pot, np.array([x]), np.array([v]), mass, np.zeros((4, 1)))
+        assert abs((x[0] - ql[0, 0]) / 2 - rt) < 6e-9 and abs((qt[0, 0] - x[0]) / 2 - rt) < 6e-9, name

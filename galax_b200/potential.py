@@ -197,6 +197,17 @@ class AbstractPotential:
         rhat = qq / ((qq * qq).sum(-1, keepdims=True) ** 0.5)
         return (g * rhat).sum(-1)
 
+    def local_circular_velocity(self, q, t=0.0):
+        """sqrt(r |dPhi/dr|) (register_funcs.py:384-400)."""
+        qq = q if not isinstance(q, (list, tuple)) else np.asarray(q, dtype=np.float64)
+        r = (qq * qq).sum(-1) ** 0.5
+        return (r * abs(self.dpotential_dr(qq, t))) ** 0.5
+
+    def spherical_mass_enclosed(self, q, t=0.0):
+        """r^2 |dPhi/dr| / G (register_funcs.py:470-490)."""
+        qq = q if not isinstance(q, (list, tuple)) else np.asarray(q, dtype=np.float64)
+        return (qq * qq).sum(-1) * abs(self.dpotential_dr(qq, t)) / self.G
+
     # ---------------------------------------------------------------- orbits (base.py:384-456)
     def evaluate_orbit(self, w0, t, **kw):
         from .dynamics import evaluate_orbit

@@ -207,6 +207,18 @@ def test_radial_profile_kinds_bulk_and_orbits():
     assert np.median(np.abs(orb.q - qd).max(axis=(1, 2))) < 1e-5
 
 
+def test_reference_derived_quantity_doctests():
+    """potential/_src/api.py: dpotential_dr (:1060-1075), d2potential_dr2 (:1105-1125) of Kepler(1e12) at [1,2,3] and
+    [4,5,6] kpc; local_circular_velocity of NFW(1e12, 20) at 8 kpc (:1013-1035); spherical_mass_enclosed of
+    MilkyWayPotential at 8 kpc (:1177-1200) -- all printed digits."""
+    kep = gp.KeplerPotential(1e12)
+    x = np.array([[1.0, 2, 3], [4, 5, 6]])
+    assert np.allclose(kep.dpotential_dr(x), [0.32132158, 0.05842211], rtol=0, atol=6e-9)
+    assert np.allclose(kep.d2potential_dr2(x), [-0.17175361, -0.01331563], rtol=0, atol=6e-9)
+    assert abs(gp.NFWPotential(1e12, 20.0).local_circular_velocity(np.array([8.0, 0, 0])) - 0.16894332) < 6e-9
+    assert abs(gp.MilkyWayPotential().spherical_mass_enclosed(np.array([8.0, 0, 0])) / 9.99105233e10 - 1) < 6e-9
+
+
 def test_edge_cases():
     pot = gp.MilkyWayPotential()
     assert pot.gradient(np.zeros((0, 3))).shape == (0, 3)

@@ -240,3 +240,17 @@ def test_radial_profile_kinds_vs_mpmath_differentiation():
                 assert np.abs(got_g - g).max() < 5e-15 * np.abs(g).max()
                 assert np.abs(got_H - H).max() < 5e-15 * np.abs(H).max()
                 assert abs(got_phi - float(f(*pt))) < 1e-14 * abs(got_phi)
+
+
+def test_reference_derived_quantity_doctests_oracle():
+    """potential/_src/api.py doctests: dpotential_dr / d2potential_dr2 (Kepler 1e12), local_circular_velocity
+    (NFW 1e12, 20 at 8 kpc), spherical_mass_enclosed (MilkyWayPotential at 8 kpc)."""
+    x = np.array([[1.0, 2, 3], [4, 5, 6]])
+    kep = op.single(op.KIND_HERNQUIST, 1e12, 0.0)
+    r = np.linalg.norm(x, axis=1, keepdims=True)
+    assert np.allclose((op.gradient(kep, x) * x / r).sum(1), [0.32132158, 0.05842211], rtol=0, atol=6e-9)
+    assert np.allclose(np.einsum("ni,nij,nj->n", x / r, op.hessian(kep, x), x / r), [-0.17175361, -0.01331563], rtol=0, atol=6e-9)
+    q = np.array([[8.0, 0, 0]])
+    assert abs(np.sqrt(8 * abs(op.gradient(op.single(op.KIND_NFW, 1e12, 20.0), q)[0, 0])) - 0.16894332) < 6e-9
+    mw = op.milky_way_potential()
+    assert abs(64 * abs(op.gradient(mw, q)[0, 0]) / mw.G / 9.99105233e10 - 1) < 6e-9

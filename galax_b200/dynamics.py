@@ -338,6 +338,9 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
     if layout == "NT3":
         q = q.reshape(batch + (T, 3))
         p = p.reshape(batch + (T, 3))
+    if not (hasattr(q0, "is_cuda") and q0.is_cuda):  # host callers get host bookkeeping too (int32 torch tensors on the CPU:
+        status = status.cpu()                        # np.asarray(...) / .numpy() work, no device round trip later)
+        stats = {k: v.cpu() for k, v in stats.items()}
     return restore(q), restore(p), status.reshape(batch), stats
 
 

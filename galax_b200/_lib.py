@@ -31,6 +31,7 @@ KIND_TRIAXIAL_HERNQUIST, KIND_JAFFE, KIND_BURKERT, KIND_STONE, KIND_HARMONIC, KI
 PHI, GRAD, ACC, HESS = 1, 2, 4, 8
 OK, MAX_STEPS_REACHED, NONFINITE = 0, 1, 2
 SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1
+SCHEME_GENERAL_KERNEL = 0x100
 LAYOUT_NT3, LAYOUT_T3N = 0, 1
 DF_FARDAL15, DF_CHEN24 = 0, 1
 DENSE_RECORD_DOUBLES = 51

@@ -380,6 +380,17 @@ struct FixedArgs {
     int T, hit_max_steps;
 };
 
+// Run-length form of the shared time grid (k_integrate_fixed_seg).  diffrax's grid t_{n+1} = fl(t_n + dt0) has a step
+// h_n = t_{n+1} - t_n that is exactly representable and piecewise constant: while t stays inside one binade the sum
+// rounds the same way every time, so h only changes where t crosses a power of two (and at the clipped last step).
+// C1's 10^4 steps are ~30 runs.  The host, which walks the grid anyway for the trip count, passes the runs by value.
+constexpr int FIXED_MAX_SEG = 120;
+struct FixedSeg {
+    int n_seg;
+    long long cnt[FIXED_MAX_SEG];  // steps in the run
+    double h[FIXED_MAX_SEG];       // their common step (in tau = dir * t)
+};
+
 static inline double clip_to_end_host(double tprev, double tnext, double t1) {
     return (tnext > t1 - 1e-10) ? t1 : tnext;
 }
@@ -406,6 +417,9 @@ __device__ __forceinline__ bool finite3(double a, double b, double c) {
 #endif
 #ifndef GX_FUSED_UPDATE
 #define GX_FUSED_UPDATE 1
+#endif
+#ifndef GX_FIXED_SEG
+#define GX_FIXED_SEG 1
 #endif
 template <class C, int SCHEME, bool FWD>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
@@ -491,6 +505,96 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         qx = nqx; qy = nqy; qz = nqz; px = npx; py = npy; pz = npz;
         tprev = tnext;
         tnext = clip_to_end(tprev, tprev + h0, T1, true);
+    }
+    int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
+    if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
+    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+    for (; k < a.T; ++k) {
+        qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
+        po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
+    }
+    if (a.status) a.status[i] = st;
+}
+
+// K2, run-length variant (static models, SemiImplicitEuler): the same arithmetic on the state as k_integrate_fixed,
+// but no time arithmetic inside the hot loop.  Within a run the grid times are t_s + j h exactly (every sum is
+// representable), so "which step contains the next save time" is decided once per save by an exact comparison
+// (fma(j, h, t_s) is the grid time itself) instead of a DADD + 2 DSETP + FSEL per step, the step is a uniform
+// constant-bank operand, and the state is updated in place.  Saves are interpolated exactly as in k_integrate_fixed
+// (same theta, same operations): results are bit-identical to it.
+template <class C, bool FWD>
+__global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS)
+k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
+    static_assert(C::is_static, "run-length variant: static models only");
+    constexpr bool STAGED = C::kPLC > 0;
+    plc_stage<C>(P);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const double T0 = FWD ? a.t0 : -a.t0;
+    double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
+    double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
+    double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    int k = 0;
+    auto load_ts = [&](int kk) { return (kk < a.T) ? (FWD ? __ldg(a.ts + kk) : -__ldg(a.ts + kk)) : INF; };
+    double tsave = load_ts(k);
+    while (tsave <= T0) {  // save times equal to t0 return y0
+        qo[k * a.sk] = qx; qo[k * a.sk + a.sc] = qy; qo[k * a.sk + 2 * a.sc] = qz;
+        po[k * a.sk] = px; po[k * a.sk + a.sc] = py; po[k * a.sk + 2 * a.sc] = pz;
+        ++k;
+        tsave = load_ts(k);
+    }
+    double tprev = T0;
+    for (int s = 0; s < sg.n_seg; ++s) {
+        const double h = sg.h[s];
+        const double hs = FWD ? h : -h;  // signed step in physical time
+        long long cnt = sg.cnt[s];
+        while (cnt > 0) {
+            // m = number of leading steps of this run that end before the next save time
+            long long m = cnt;
+            if (tsave < INF) {
+                const double x = (tsave - tprev) / h;
+                long long j = (x >= (double)cnt) ? cnt : ((x > 0.0) ? (long long)x : 0);
+                while (j < cnt && fma((double)(j + 1), h, tprev) < tsave) ++j;
+                while (j > 0 && !(fma((double)j, h, tprev) < tsave)) --j;
+                m = j;
+            }
+            for (long long n = 0; n < m; ++n) {
+                qx = fma(px, hs, qx);
+                qy = fma(py, hs, qy);
+                qz = fma(pz, hs, qz);
+                double fh, fv;
+                gradient_factors<C, STAGED>(P, qx, qy, qz, fh, fv);
+                const double fhh = -fh * hs, fvh = -fv * hs;
+                px = fma(fhh, qx, px);
+                py = fma(fhh, qy, py);
+                pz = fma(fvh, qz, pz);
+            }
+            tprev = fma((double)m, h, tprev);
+            cnt -= m;
+            if (cnt > 0) {  // the step that contains (at least) one save time
+                const double tnext = tprev + h;
+                const double nqx = fma(px, hs, qx), nqy = fma(py, hs, qy), nqz = fma(pz, hs, qz);
+                double fh, fv;
+                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv);
+                const double fhh = -fh * hs, fvh = -fv * hs;
+                const double npx = fma(fhh, nqx, px), npy = fma(fhh, nqy, py), npz = fma(fvh, nqz, pz);
+                while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
+                    const double th = (tsave - tprev) / (tnext - tprev);
+                    qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
+                    qo[k * a.sk + a.sc] = __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy)));
+                    qo[k * a.sk + 2 * a.sc] = __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz)));
+                    po[k * a.sk] = __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px)));
+                    po[k * a.sk + a.sc] = __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py)));
+                    po[k * a.sk + 2 * a.sc] = __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz)));
+                    ++k;
+                    tsave = load_ts(k);
+                }
+                qx = nqx; qy = nqy; qz = nqz; px = npx; py = npy; pz = npz;
+                tprev = tnext;
+                --cnt;
+            }
+        }
     }
     int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
     if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
@@ -1157,12 +1261,17 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     int rc = build_devpot(pot, D, model, true, TD_INTEGRATE);
     if (rc) return rc;
     if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
+    const bool general_kernel = (scheme & GX_SCHEME_GENERAL_KERNEL) != 0;
+    scheme &= ~GX_SCHEME_GENERAL_KERNEL;
     if (scheme != GX_SCHEME_SEMI_IMPLICIT_EULER && scheme != GX_SCHEME_LEAPFROG_MIDPOINT) return GX_ERR_BADARG;
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
     if (t1 != t0 && !(dt0 * dir > 0.0)) return GX_ERR_BADARG;  // ConstantStepSize needs dt0 in the direction of t1
     if (N == 0) return 0;
     FixedArgs a;
+    FixedSeg sg;
+    double seg_t0 = 0.0;
+    bool seg_ok = GX_FIXED_SEG && GX_FUSED_UPDATE && !general_kernel && scheme == GX_SCHEME_SEMI_IMPLICIT_EULER && model != MODEL_GENERIC;
     a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p; a.status = status;
     a.N = N; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
@@ -1171,9 +1280,21 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
         double tprev = T0, tnext = clip_to_end_host(T0, T0 + h0, T1);
         long long n = 0;
         int hit = 0;
+        sg.n_seg = 0;
         while (tprev < T1) {
             if (max_steps >= 0 && n >= max_steps) { hit = 1; break; }
             ++n;
+            if (seg_ok) {  // run-length encode h_n = tnext - tprev (exact); a run must also satisfy t_s + j h == t_j
+                const double h = tnext - tprev;
+                if (sg.n_seg > 0 && sg.h[sg.n_seg - 1] == h &&
+                    fma((double)(sg.cnt[sg.n_seg - 1] + 1), h, seg_t0) == tnext) {
+                    ++sg.cnt[sg.n_seg - 1];
+                } else if (sg.n_seg < FIXED_MAX_SEG && tprev + h == tnext) {
+                    sg.h[sg.n_seg] = h; sg.cnt[sg.n_seg] = 1; seg_t0 = tprev; ++sg.n_seg;
+                } else {
+                    seg_ok = false;  // too many runs (or an inexact difference): the general kernel handles it
+                }
+            }
             tprev = tnext;
             tnext = clip_to_end_host(tprev, tprev + h0, T1);
         }
@@ -1185,7 +1306,22 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
     const bool fwd = dir > 0;
-    if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
+    if (seg_ok) {
+        switch (model) {
+        case MODEL_MW:
+            if (fwd) k_integrate_fixed_seg<CountsMW, true><<<grid, block, 0, s>>>(D, a, sg);
+            else k_integrate_fixed_seg<CountsMW, false><<<grid, block, 0, s>>>(D, a, sg);
+            break;
+        case MODEL_MW2022:
+            if (fwd) k_integrate_fixed_seg<CountsMW2022, true><<<grid, block, 0, s>>>(D, a, sg);
+            else k_integrate_fixed_seg<CountsMW2022, false><<<grid, block, 0, s>>>(D, a, sg);
+            break;
+        default:
+            if (fwd) k_integrate_fixed_seg<CountsBovy, true><<<grid, block, 0, s>>>(D, a, sg);
+            else k_integrate_fixed_seg<CountsBovy, false><<<grid, block, 0, s>>>(D, a, sg);
+            break;
+        }
+    } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
         if (fwd) { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, true><<<grid, block, 0, s>>>(D, a))); }
         else { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, false><<<grid, block, 0, s>>>(D, a))); }
     } else {

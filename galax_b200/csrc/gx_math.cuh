@@ -115,7 +115,7 @@ __device__ __forceinline__ double log1p_pos(double s) {
 // ln(1+s) - s/(1+s), the NFW enclosed-mass shape.  Below s = 2^-4 the two terms cancel to O(s^2) and the
 // alternating series sum_{k>=2} (-1)^k (k-1)/k s^k is used instead (17 terms: 0.0625^16 < 6e-20).
 __device__ __forceinline__ double nfw_menc_shape(double s, double &inv_u) {
-    if (s < 0.0625) {
+    if (__double2hiint(s) < 0x3fb00000) {  // s < 2^-4 for s >= 0, decided on the integer pipe (no FP64 DSETP)
         inv_u = rcp_fast(1.0 + s);
         double p = 17.0 / 18.0;  // k = 18
 #pragma unroll

@@ -240,7 +240,7 @@ def _period_order(q, p, t0v, t1, torch):
 
 
 def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",
-               throw=True):  # fmt: skip
+               throw=True, general_kernel=False):  # fmt: skip
     """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,)."""
     torch = _lib.require_cuda()
     dq, restore = _to_device(q0)
@@ -289,6 +289,8 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             if t0_arr is not None:
                 raise NotImplementedError("per-particle t0 is only supported by the adaptive solver")
             scheme = _lib.SCHEME_SIE if isinstance(solver, SemiImplicitEuler) else _lib.SCHEME_LEAPFROG_MIDPOINT
+            if general_kernel:  # testing aid: the per-step time arithmetic kernel instead of the run-length one
+                scheme |= _lib.SCHEME_GENERAL_KERNEL
             rc = L.gx_integrate_fixed(C.byref(P), dq.data_ptr(), dp.data_ptr(), N, t0s, t1, float(dt0),
                                       dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
                                       status.data_ptr(), stream)  # fmt: skip

@@ -86,6 +86,9 @@ typedef struct {
 /* fixed-step schemes */
 #define GX_SCHEME_SEMI_IMPLICIT_EULER 0 /* diffrax.SemiImplicitEuler (the reference's "leapfrog") */
 #define GX_SCHEME_LEAPFROG_MIDPOINT 1   /* diffrax.LeapfrogMidpoint                               */
+/* or-ed into `scheme`: use the general fixed-step kernel (time arithmetic every step) where the run-length kernel
+ * would be chosen.  Results are bit-identical; for tests and A/B timing. */
+#define GX_SCHEME_GENERAL_KERNEL 0x100
 
 /* output layout of saved states, element (particle n, save k, component c) */
 #define GX_LAYOUT_NT3 0 /* [N,T,3]  the reference's (*batch, T, 3), orbit/register_dfx.py:80-82 */

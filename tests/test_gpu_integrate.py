@@ -107,6 +107,39 @@ def test_leapfrog_midpoint_and_max_steps():
     assert (s.result == 1).all() and np.isnan(s.ys[0]).all()
 
 
+@pytest.mark.parametrize("name", list(PAIRS))
+def test_run_length_kernel_is_bit_identical_to_the_general_kernel(name):
+    """k_integrate_fixed_seg (run-length time grid, no time arithmetic in the hot loop) against k_integrate_fixed:
+    same bits for every grid shape -- saves on and between step boundaries, several saves inside one step, a save
+    at t0, backward runs, grids that cross t = 0, a clipped last step, max_steps, both layouts."""
+    pot_cls, opot_f = PAIRS[name]
+    pot, opot = pot_cls(), opot_f()
+    q0, p0 = synthetic_ics(opot, 257, seed=11)
+    rng = np.random.default_rng(5)
+    kw = dict(solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(), throw=False)
+    cases = [
+        (0.0, 100.0, 0.1, np.array([100.0]), None),
+        (0.0, 100.0, 0.1, np.linspace(0.0, 100.0, 1001), None),                       # every step boundary
+        (0.0, 37.3, 0.25, np.sort(rng.uniform(0, 37.3, 500)), None),                  # several saves per step
+        (-40.0, 55.5, 0.07, np.concatenate([[-40.0], np.sort(rng.uniform(-40, 55.5, 40)), [55.5]]), None),
+        (30.0, -20.0, -0.13, np.sort(rng.uniform(-20, 30, 25))[::-1].copy(), None),   # backward through zero
+        (1000.0, 1003.0, 1e-3, np.array([1001.5, 1003.0]), None),                     # large t: coarse ulp of the grid
+        (0.0, 10.0, 3.0, np.array([2.9, 3.0, 3.1, 9.99, 10.0]), None),                # clipped last step
+        (0.0, 100.0, 0.1, np.array([50.0, 100.0]), 600),                              # max_steps reached
+        (5.0, 5.0, 0.1, np.array([5.0]), None),                                       # zero length
+    ]
+    for t0, t1, dt0, ts, ms in cases:
+        for layout in ("NT3", "T3N"):
+            a = gd._integrate(pot, q0, p0, t0, t1, ts, dt0=dt0, max_steps=ms, layout=layout, **kw)
+            b = gd._integrate(pot, q0, p0, t0, t1, ts, dt0=dt0, max_steps=ms, layout=layout, general_kernel=True, **kw)
+            assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True), (t0, t1, dt0)
+            assert np.array_equal(a[2], b[2])
+        if ms is None and t0 != t1:  # and both agree with the oracle
+            qr, pr, _, _ = cref.integrate_fixed(opot, q0, p0, t0, t1, dt0, ts)
+            a = gd._integrate(pot, q0, p0, t0, t1, ts, dt0=dt0, max_steps=ms, **kw)
+            assert relerr_vec(a[0], qr) <= 1e-11 and relerr_vec(a[1], pr) <= 1e-11
+
+
 def test_conserved_quantities_full_size():
     """Size-independent properties at a large N: bounded energy error of the symplectic map and exact (to
     rounding) conservation of L_z in the axisymmetric potential."""

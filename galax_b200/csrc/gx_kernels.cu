@@ -425,6 +425,7 @@ template <class C, int SCHEME, bool FWD>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     constexpr bool STAGED = C::is_static && C::kPLC > 0;  // PowerLawCutoff table in shared memory (Bovy)
     plc_stage<C>(P);
+    const unsigned plc_base = plc_smem_base<C>();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     // integrate in tau = dir * t (diffrax flips the sign of time the same way for t1 < t0)
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv);
+                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv, plc_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
                 npy = fma(fhh, nqy, py);
@@ -528,6 +529,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     static_assert(C::is_static, "run-length variant: static models only");
     constexpr bool STAGED = C::kPLC > 0;
     plc_stage<C>(P);
+    const unsigned plc_base = plc_smem_base<C>();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     const double T0 = FWD ? a.t0 : -a.t0;
@@ -564,7 +566,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 qy = fma(py, hs, qy);
                 qz = fma(pz, hs, qz);
                 double fh, fv;
-                gradient_factors<C, STAGED>(P, qx, qy, qz, fh, fv);
+                gradient_factors<C, STAGED>(P, qx, qy, qz, fh, fv, plc_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 px = fma(fhh, qx, px);
                 py = fma(fhh, qy, py);
@@ -576,7 +578,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 const double tnext = tprev + h;
                 const double nqx = fma(px, hs, qx), nqy = fma(py, hs, qy), nqz = fma(pz, hs, qz);
                 double fh, fv;
-                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv);
+                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv, plc_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 const double npx = fma(fhh, nqx, px), npy = fma(fhh, nqy, py), npz = fma(fvh, nqz, pz);
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)

@@ -90,8 +90,21 @@ __device__ __forceinline__ double log1p_pos(double s, double u, double inv_u) {
 // (truncation r^7/7 < 2^-65).  {inv_c_j, logc_j = -ln(inv_c_j)} come from gx_tables.h (256 x 16 B, L1-resident).
 // 12 FP64 instructions instead of the 33 of the atanh form above; error <= ~1.5 ulp of the result.  Not for s
 // near 0: logc_j + log1p(r) cancels there (the NFW shape uses its series below s = 2^-4 anyway).
+// The constants that are not 32-bit-immediate doubles sit in the constant bank (GX_LOG_CONST_BANK=1): as literals the
+// compiler re-materialises each with two UMOV/IMAD.MOV per use, and on this pipe mix every instruction costs an
+// issue slot (FP64 two): -7 instructions per NFW evaluation.
+#ifndef GX_LOG_CONST_BANK
+#define GX_LOG_CONST_BANK 1
+#endif
+#if GX_LOG_CONST_BANK
+__constant__ double LOG_C[4] = {6.93147180559945286227e-01, -1.0 / 6.0, 0.2, 1.0 / 3.0};
+#endif
 __device__ __forceinline__ double log1p_tab(double s, double u, double inv_u) {
-    const double LN2 = 6.93147180559945286227e-01;
+#if GX_LOG_CONST_BANK
+    const double LN2 = LOG_C[0], C6 = LOG_C[1], C5 = LOG_C[2], C3 = LOG_C[3];
+#else
+    const double LN2 = 6.93147180559945286227e-01, C6 = -1.0 / 6.0, C5 = 0.2, C3 = 1.0 / 3.0;
+#endif
     const double c = s - (u - 1.0);
     const int hi = __double2hiint(u);
     const int k = (hi >> 20) - 1023;
@@ -99,9 +112,9 @@ __device__ __forceinline__ double log1p_tab(double s, double u, double inv_u) {
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
     const double2 t = __ldg(&LOG_TAB[j]);
     const double r = fma(m, t.x, -1.0);
-    double p = fma(r, -1.0 / 6.0, 0.2);
+    double p = fma(r, C6, C5);
     p = fma(p, r, -0.25);
-    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, C3);
     p = fma(p, r, -0.5);
     const double lo = fma(r * r, p, fma(c, inv_u, r));  // log1p(r) + c/u
     return fma((double)k, LN2, t.y) + lo;

@@ -47,26 +47,50 @@ struct DevPLC { double GM, inv_rc, tail, GM_rc3; const double *tab; GammaTab ga,
 // G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
 // SMEM: the table was staged into shared memory with PLC_STRIDE doubles per interval (plc_stage below).
 constexpr int PLC_STRIDE = PLC_DEG + 2;  // 15: odd, so the intervals of neighbouring lanes fall into different banks
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 template <bool SMEM>
-__device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, double &G, double *dG) {
+__device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, double &G, double *dG,
+                                                  unsigned smem_base = 0) {
     if (tab == nullptr) return false;
     const int hi = __double2hiint(s);
-    const int e = ((hi >> 20) & 0x7ff) - 1023;
-    if (e < PLC_E_LO || e >= PLC_E_HI) return false;
-    const int sub = (hi >> 17) & (PLC_SUB - 1);
-    const int j = (e - PLC_E_LO) * PLC_SUB + sub;
-    // interval [2^e (1 + sub/8), 2^e (1 + (sub+1)/8)): t in [-1, 1)
-    const double scale = __hiloint2double((1023 - e + 4) << 20, 0);              // 2^(4-e) = 16 / 2^e
-    const double t = fma(s, scale, -(double)(2 * PLC_SUB + 2 * sub + 1));      // 16 s/2^e - 16 - 2 sub - 1
-    const double *p = tab + (long long)j * (SMEM ? PLC_STRIDE : PLC_DEG + 1);
-    double v = SMEM ? p[PLC_DEG] : __ldg(p + PLC_DEG), d = 0.0;
+    // interval index from the bits of s > 0: (hi >> 17) = exponent field * 8 + top three mantissa bits
+    const unsigned j = (unsigned)(hi >> 17) - (unsigned)((1023 + PLC_E_LO) * PLC_SUB);
+    if (j >= (unsigned)PLC_NINT) return false;  // s outside [2^PLC_E_LO, 2^PLC_E_HI) (also NaN / negative)
+    // interval [2^e (1 + sub/8), 2^e (1 + (sub+1)/8)), t in [-1, 1):  t = 16 m - (17 + 2 sub) with m = s / 2^e in [1, 2).
+    // Both operands come straight from the bits of s (exact; identical to fma(s, 2^(4-e), -(17 + 2 sub))).
+    static_assert(PLC_SUB == 8, "bit tricks below assume 8 intervals per octave");
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
+    const double c16 = __hiloint2double((hi & 0x000e0000) | 0x40310000, 0);  // 16 (1 + sub/8 + 1/16)
+    const double t = fma(m, 16.0, -c16);
+    double v, d = 0.0;
+    if (SMEM) {
+        // 32-bit shared-window address; the fixed-step kernels pass the table's base (plc_smem_base) so that the window
+        // base (S2R SR_CgaCtaId + LEA) is not re-derived in every step
+        const unsigned a0 = (smem_base ? smem_base : (unsigned)__cvta_generic_to_shared(tab)) + j * (unsigned)(PLC_STRIDE * 8);
+        v = lds_f64(a0 + PLC_DEG * 8);
 #pragma unroll
-    for (int k = PLC_DEG - 1; k >= 0; --k) {
-        if (dG) d = fma(d, t, v);
-        v = fma(v, t, SMEM ? p[k] : __ldg(p + k));
+        for (int k = PLC_DEG - 1; k >= 0; --k) {
+            if (dG) d = fma(d, t, v);
+            v = fma(v, t, lds_f64(a0 + k * 8));
+        }
+    } else {
+        const double *p = tab + (long long)j * (PLC_DEG + 1);
+        v = __ldg(p + PLC_DEG);
+#pragma unroll
+        for (int k = PLC_DEG - 1; k >= 0; --k) {
+            if (dG) d = fma(d, t, v);
+            v = fma(v, t, __ldg(p + k));
+        }
     }
     G = v;
-    if (dG) *dG = d * scale;  // dt/ds = scale
+    if (dG) {
+        const int e = ((hi >> 20) & 0x7ff) - 1023;
+        *dG = d * __hiloint2double((1023 - e + 4) << 20, 0);  // dt/ds = 2^(4-e)
+    }
     return true;
 }
 __device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double &G, double *dG) {
@@ -220,6 +244,16 @@ __device__ __forceinline__ double *plc_smem() {
     __shared__ double t[PLC_NINT * PLC_STRIDE];
     return t;
 }
+// Shared-window address of the staged table, made opaque so that it stays in a register across the step loop.
+template <class C>
+__device__ __forceinline__ unsigned plc_smem_base() {
+    unsigned b = 0;
+    if constexpr (C::is_static && C::kPLC > 0) {
+        b = (unsigned)__cvta_generic_to_shared(plc_smem<C>());
+        asm volatile("" : "+r"(b));
+    }
+    return b;
+}
 // Call once per CTA, by all threads, before the first gradient<C, true>().
 template <class C>
 __device__ __forceinline__ void plc_stage(const DevPot &P) {
@@ -239,7 +273,8 @@ __device__ __forceinline__ void plc_stage(const DevPot &P) {
 // (triaxial logarithmic / ellipsoidal profiles / polynomials) are added to (ex, ey, ez) by gradient<C>() below.
 // Terms of the form GM_i w_i / r (Hernquist, NFW) are summed before the common factor 1/r is applied.
 template <class C, bool PLC_SMEM = false>
-__device__ __forceinline__ void gradient_factors(const DevPot &P, double x, double y, double z, double &fh, double &fv) {
+__device__ __forceinline__ void gradient_factors(const DevPot &P, double x, double y, double z, double &fh, double &fv,
+                                                 unsigned plc_base = 0) {
     const double z2 = z * z;
     const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
     double fxy = 0.0, fz = 0.0, fs = 0.0, fr = 0.0;  // fs: terms Phi'/r as they are; fr: terms still to be divided by r
@@ -311,7 +346,7 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
             double Gs;
             if (s >= PLC_S_ONE) {
                 fr = fma(c.GM, rinv2, fr);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
-            } else if (PLC_SMEM ? plc_table_eval_at<true>(plc_smem<C>(), s, Gs, nullptr)
+            } else if (PLC_SMEM ? plc_table_eval_at<true>(plc_smem<C>(), s, Gs, nullptr, plc_base)
                                 : plc_table_eval(c, s, Gs, nullptr)) {
                 fs = fma(c.GM_rc3, Gs, fs);  // GM P(a, s^2) / r^3 = (GM / rc^3) G(s)
             } else {

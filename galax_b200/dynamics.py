@@ -33,7 +33,7 @@ from typing import Any, Callable, Sequence
 import numpy as np
 
 from . import _lib
-from .potential import AbstractPotential, _to_device
+from .potential import AbstractPotential, _to_device, _to_host_many
 
 # ------------------------------------------------------------------------------------------------
 # diffrax stand-ins (plain records)
@@ -239,10 +239,101 @@ def _period_order(q, p, t0v, t1, torch):
     return torch.argsort(cost, descending=True).to(torch.int32).contiguous()
 
 
+# Large batches that arrive in pinned host memory are processed in PIPELINE_CHUNKS slices on two side streams, so that
+# the host->device copy of slice k+1 and the device->host copy of slice k-1 overlap the kernel of slice k (particles
+# are independent; the kernels of neighbouring slices also fill each other's tail waves).  Same numbers as one launch.
+PIPELINE_MIN_PARTICLES = 1 << 19
+PIPELINE_CHUNKS = 4
+PIPELINE_MAX_OUTPUT_BYTES = 8 << 30
+
+
+def _pipeline_ok(torch, q0, p0, t0, ts, layout) -> bool:
+    if layout != "NT3" or not (isinstance(q0, torch.Tensor) and isinstance(p0, torch.Tensor)):
+        return False
+    if q0.is_cuda or p0.is_cuda or not (q0.is_pinned() and p0.is_pinned()):
+        return False
+    if q0.dtype != torch.float64 or p0.dtype != torch.float64 or q0.shape != p0.shape or q0.shape[-1] != 3:
+        return False
+    if isinstance(t0, torch.Tensor) and t0.is_cuda:
+        return False
+    n = q0.numel() // 3
+    if n * max(int(np.size(ts)), 1) * 48 > PIPELINE_MAX_OUTPUT_BYTES:  # (pinned host buffers for the whole result)
+        return False
+    return n >= PIPELINE_MIN_PARTICLES and q0.is_contiguous() and p0.is_contiguous()
+
+
+_PIPELINE_STREAMS: dict[int, list] = {}
+
+
+def _pipeline_streams(torch, dev):
+    """Two side streams per device, created once: the caching allocators keep their blocks per stream, so fresh
+    streams on every call would turn each call's buffers into new cudaMalloc / cudaHostAlloc calls."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _PIPELINE_STREAMS:
+        _PIPELINE_STREAMS[key] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    return _PIPELINE_STREAMS[key]
+
+
+def _integrate_pipelined(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort, throw, general_kernel):
+    import torch
+
+    batch = tuple(q0.shape[:-1])
+    qh, ph = q0.reshape(-1, 3), p0.reshape(-1, 3)
+    N = qh.shape[0]
+    t0_is_array = (isinstance(t0, (np.ndarray, torch.Tensor)) and np.ndim(t0) > 0) or isinstance(t0, (list, tuple))
+    t0h = None
+    if t0_is_array:
+        t0h = torch.as_tensor(np.asarray(t0, dtype=np.float64) if not isinstance(t0, torch.Tensor) else t0).reshape(-1)
+        if t0h.shape[0] != N:
+            raise ValueError("per-particle t0 must match the batch size")
+    ts_np = np.atleast_1d(np.asarray(ts.detach().cpu() if isinstance(ts, torch.Tensor) else ts, dtype=np.float64))
+    T = int(ts_np.shape[0])
+    q_out = torch.empty((N, T, 3), dtype=torch.float64, pin_memory=True)
+    p_out = torch.empty((N, T, 3), dtype=torch.float64, pin_memory=True)
+    status = torch.empty((N,), dtype=torch.int32, pin_memory=True)
+    stat_out: dict[str, Any] = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cur = torch.cuda.current_stream(dev)
+    streams = _pipeline_streams(torch, dev)
+    bounds = [(N * k) // PIPELINE_CHUNKS for k in range(PIPELINE_CHUNKS + 1)]
+    for k in range(PIPELINE_CHUNKS):
+        a, b = bounds[k], bounds[k + 1]
+        s = streams[k % 2]
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            dq = qh[a:b].to(dev, non_blocking=True)
+            dp = ph[a:b].to(dev, non_blocking=True)
+            t0k = t0 if t0h is None else t0h[a:b].to(dev)
+            qd, pd, st, stats = _integrate(pot, dq, dp, t0k, t1, ts_np, solver=solver, controller=controller, dt0=dt0,
+                                           max_steps=max_steps, sort=sort, layout="NT3", throw=False,
+                                           general_kernel=general_kernel)
+            q_out[a:b].copy_(qd, non_blocking=True)
+            p_out[a:b].copy_(pd, non_blocking=True)
+            status[a:b].copy_(st, non_blocking=True)
+            for name, v in stats.items():
+                if name not in stat_out:
+                    stat_out[name] = torch.empty((N,), dtype=v.dtype, pin_memory=True)
+                stat_out[name][a:b].copy_(v, non_blocking=True)
+    for s in streams:
+        s.synchronize()
+    if throw:
+        bad = torch.nonzero(status != _lib.OK)
+        if bad.numel():
+            i = int(bad[0, 0])
+            code = int(status[i])
+            why = {1: "max_steps reached", 2: "non-finite state"}.get(code, f"status {code}")
+            raise RuntimeError(f"integration failed for particle {i} of {N}: {why} ({bad.shape[0]} failed in total)")
+    return (q_out.reshape(batch + (T, 3)), p_out.reshape(batch + (T, 3)), status.reshape(batch),
+            {k: v.reshape(batch) for k, v in stat_out.items()})
+
+
 def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",
                throw=True, general_kernel=False):  # fmt: skip
     """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,)."""
     torch = _lib.require_cuda()
+    if _pipeline_ok(torch, q0, p0, t0, ts, layout):
+        return _integrate_pipelined(pot, q0, p0, t0, t1, ts, solver=solver, controller=controller, dt0=dt0,
+                                    max_steps=max_steps, sort=sort, throw=throw, general_kernel=general_kernel)
     dq, restore = _to_device(q0)
     dp, _ = _to_device(p0)
     batch = tuple(dq.shape[:-1])
@@ -330,6 +421,18 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             raise NotImplementedError(
                 f"solver {type(solver).__name__} is not supported (SemiImplicitEuler, LeapfrogMidpoint, Dopri8, Dopri5)"
             )
+    if layout == "NT3":
+        q = q.reshape(batch + (T, 3))
+        p = p.reshape(batch + (T, 3))
+    host_caller = not (hasattr(q0, "is_cuda") and q0.is_cuda)
+    if host_caller:
+        # Host callers get host results and host bookkeeping (int32 torch tensors on the CPU: np.asarray(...) /
+        # .numpy() work, no device round trip later).  Everything goes back through pinned memory in one batch of
+        # asynchronous copies with a single synchronisation; the status check below then reads host memory.
+        q, p, status, *rest = _to_host_many([q, p, status, *stats.values()])
+        stats = dict(zip(stats.keys(), rest))
+        if isinstance(q0, np.ndarray) or not isinstance(q0, torch.Tensor):
+            q, p = q.numpy(), p.numpy()
     if throw:
         bad = torch.nonzero(status != _lib.OK)
         if bad.numel():
@@ -337,13 +440,7 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             code = int(status[i])
             why = {1: "max_steps reached", 2: "non-finite state"}.get(code, f"status {code}")
             raise RuntimeError(f"integration failed for particle {i} of {N}: {why} ({bad.shape[0]} failed in total)")
-    if layout == "NT3":
-        q = q.reshape(batch + (T, 3))
-        p = p.reshape(batch + (T, 3))
-    if not (hasattr(q0, "is_cuda") and q0.is_cuda):  # host callers get host bookkeeping too (int32 torch tensors on the CPU:
-        status = status.cpu()                        # np.asarray(...) / .numpy() work, no device round trip later)
-        stats = {k: v.cpu() for k, v in stats.items()}
-    return restore(q), restore(p), status.reshape(batch), stats
+    return q, p, status.reshape(batch), stats
 
 
 def _energy(pot, q, p, want="E"):

@@ -250,6 +250,18 @@ def _to_host(r):
     return out
 
 
+def _to_host_many(tensors):
+    """Several device results -> pinned host tensors: all copies queued, one synchronisation."""
+    import torch
+
+    outs = [torch.empty(r.shape, dtype=r.dtype, pin_memory=True) for r in tensors]
+    for o, r in zip(outs, tensors):
+        o.copy_(r, non_blocking=True)
+    if tensors:
+        torch.cuda.current_stream(tensors[0].device).synchronize()
+    return outs
+
+
 def _to_device(x):
     """-> (float64 CUDA tensor, function mapping a CUDA result back to the caller's array kind)."""
     import torch

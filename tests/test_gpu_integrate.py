@@ -542,3 +542,34 @@ def test_host_arrays_round_trip_through_pinned_memory():
     keep = got[0].copy()
     gd._integrate(pot, q0 * 1.01, p0, 0.0, 50.0, ts, **kw)  # a later call must not overwrite an earlier result
     assert np.array_equal(got[0], keep)
+
+
+def test_pipelined_host_path_equals_single_launch():
+    """Pinned host tensors above PIPELINE_MIN_PARTICLES go through the chunked copy/compute pipeline: same bits as
+    one launch on device-resident inputs, for the fixed-step and the adaptive kernels, statuses included."""
+    import torch
+
+    pot, opot = gp.MilkyWayPotential(), op.milky_way_potential()
+    N = gd.PIPELINE_MIN_PARTICLES + 1237  # ragged chunk bounds
+    q0, p0 = synthetic_ics(opot, 4096, seed=21)
+    reps = -(-N // 4096)
+    scale = 1.0 + 1e-3 * np.arange(reps)[:, None, None]
+    q0 = (q0[None] * scale).reshape(-1, 3)[:N].copy()
+    p0 = np.tile(p0, (reps, 1))[:N].copy()
+    qp, pp = torch.from_numpy(q0).pin_memory(), torch.from_numpy(p0).pin_memory()
+    qd, pd = qp.cuda(), pp.cuda()
+    ts = np.array([10.0, 20.0])
+    kw = dict(solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(), dt0=0.1, max_steps=None)
+    a = gd._integrate(pot, qp, pp, 0.0, 20.0, ts, **kw)
+    b = gd._integrate(pot, qd, pd, 0.0, 20.0, ts, **kw)
+    assert not a[0].is_cuda and a[0].shape == (N, 2, 3)
+    assert torch.equal(a[0], b[0].cpu()) and torch.equal(a[1], b[1].cpu()) and torch.equal(a[2], b[2].cpu())
+    kw = dict(solver=gd.Dopri8(), controller=gd.PIDController(1e-8, 1e-8), dt0=None, max_steps=4096)
+    t0 = np.linspace(0.0, 5.0, N)  # per-particle start times are sliced with the particles
+    a = gd._integrate(pot, qp, pp, t0, 20.0, ts, **kw)
+    b = gd._integrate(pot, qd, pd, torch.from_numpy(t0).cuda(), 20.0, ts, **kw)
+    assert torch.equal(a[0], b[0].cpu()) and torch.equal(a[1], b[1].cpu()) and torch.equal(a[2], b[2].cpu())
+    assert torch.equal(a[3]["num_steps"], b[3]["num_steps"].cpu())
+    with pytest.raises(RuntimeError, match="max_steps"):
+        gd._integrate(pot, qp, pp, 0.0, 20.0, ts, solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(),
+                      dt0=0.1, max_steps=5)

@@ -46,6 +46,9 @@ struct DevPLC { double GM, inv_rc, tail, GM_rc3; const double *tab; GammaTab ga,
 
 // G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
 // SMEM: the table was staged into shared memory with PLC_STRIDE doubles per interval (plc_stage below).
+#ifndef GX_HERN_PAIR
+#define GX_HERN_PAIR 1
+#endif
 constexpr int PLC_STRIDE = PLC_DEG + 2;  // 15: odd, so the intervals of neighbouring lanes fall into different banks
 __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
@@ -314,13 +317,25 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
         const double rinv = rsqrt_fast(r2);
         const double r = r2 * rinv;
         const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
+#if GX_HERN_PAIR
+        if constexpr (C::is_static && C::kH == 2) {
+            // bulge + nucleus over one reciprocal: GM1/u1^2 + GM2/u2^2 = (GM1 u2^2 + GM2 u1^2) / (u1 u2)^2
+            // (one MUFU seed + refinement instead of two: -1 FP64 and -3 other instructions per evaluation)
+            const double u1 = r + P.hern[0].c, u2 = r + P.hern[1].c;
+            const double w1 = u1 * u1, w2 = u2 * u2;
+            const double num = fma(P.hern[1].GM, w1, P.hern[0].GM * w2);
+            fr = num * rcp_fast(w1 * w2);
+        } else
+#endif
+        {
 #pragma unroll
-        for (int i = 0; i < C::kH; ++i) {
-            if (!C::is_static && i >= P.n_hern) break;
-            const DevHern &c = P.hern[i];
-            double u = r + c.c;
-            double w = rcp_fast(u * u);  // Phi'/r = GM / ((r+c)^2 r)
-            if (C::is_static && i == 0) fr = c.GM * w; else fr = fma(c.GM, w, fr);
+            for (int i = 0; i < C::kH; ++i) {
+                if (!C::is_static && i >= P.n_hern) break;
+                const DevHern &c = P.hern[i];
+                double u = r + c.c;
+                double w = rcp_fast(u * u);  // Phi'/r = GM / ((r+c)^2 r)
+                if (C::is_static && i == 0) fr = c.GM * w; else fr = fma(c.GM, w, fr);
+            }
         }
 #pragma unroll
         for (int i = 0; i < C::kISO; ++i) {

@@ -39,9 +39,9 @@ N_STEPS = 10_000  # dt0 = 0.1 Myr over 1 Gyr
 T1, DT0 = 1000.0, 0.1
 FLOP_PER_STEP = 280.0  # canonical weighted fp64 flop per MilkyWayPotential fixed step
 # FP64 thread-instructions the kernel really executes per particle-step, counted by ncu on this very launch
-# (profiles/ncu_k_integrate_fixed_r1e.txt: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on / (N x steps))
-NCU_FP64_INSTR_PER_STEP = {"dfma": 42.04, "dmul": 21.01, "dadd": 7.00}
-NCU_FP64_PIPE_ACTIVE_PCT = 81.0
+# (profiles/ncu_k_integrate_fixed_r1f.txt: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on / (N x steps))
+NCU_FP64_INSTR_PER_STEP = {"dfma": 39.07, "dmul": 23.03, "dadd": 7.01}
+NCU_FP64_PIPE_ACTIVE_PCT = 82.9
 CPU_SAMPLE_PER_CORE = 8192  # cpu_baseline leg: ~10 s of CPU work at ~9e6 particle-steps/s/core
 REF_ARM_SAMPLE_PER_CORE = 2048  # --impl reference: ~2.5 s per bench step
 
@@ -304,8 +304,8 @@ def run_gpu(args) -> None:
     achieved = per_gpu_rate * FLOP_PER_STEP / 1e12
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved / dfma_peak,
-        "traffic": 76.6e6 if n == N_PER_GPU else None,
-        "traffic_source": "ncu --set full, profiles/ncu_k_integrate_fixed_r1e.txt: dram read 59.3 MB + write 17.2 MB per "
+        "traffic": 78.8e6 if n == N_PER_GPU else None,
+        "traffic_source": "ncu --set full, profiles/ncu_k_integrate_fixed_r1f.txt: dram read 59.8 MB + write 19.0 MB per "
                           "launch (algorithmic: 58.2 MB in + 58.2 MB out + 4.8 MB status; L2 absorbs part of the writes)",
         "kernel": "k_integrate_fixed_seg<MW> (SemiImplicitEuler, run-length time grid)", "kernel_ms": k_ms,
         "algorithmic_flop_per_particle_step": FLOP_PER_STEP,
@@ -323,7 +323,7 @@ def run_gpu(args) -> None:
         "frac_of_dfma_peak": per_gpu_rate * n_flop / 1e12 / dfma_peak,
         "fp64_issue_frac": per_gpu_rate * n_instr / (dfma_peak * 1e12 / 2.0),  # FP64 instructions / FP64 issue slots
         "ncu_fp64_pipe_active_pct": NCU_FP64_PIPE_ACTIVE_PCT,
-        "source": "profiles/ncu_k_integrate_fixed_r1e.txt (same kernel, same launch shape)",
+        "source": "profiles/ncu_k_integrate_fixed_r1f.txt (same kernel, same launch shape)",
     }
 
     # The HBM-bound leg of the path (C5): acceleration + Hessian on 2e7 points, against the measured copy peak

@@ -173,6 +173,9 @@ def run_gpu(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set
+        # in the environment) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()  # fails loudly if libgalax_b200.so is missing
     pot = gp.MilkyWayPotential()

@@ -37,62 +37,79 @@ struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
 struct DevHern { double GM, c; };
 struct DevNFW { double GM, rs, inv_rs, GM_inv_rs; };
 // ga: a = 3/2 - alpha/2; ga2: a - 1/2; tail = Gamma(a2)/(rc Gamma(a)).
-// tab: optional device table of G(s) = P(a, s^2) / s^3, s = r/r_c, as degree-(PLC_DEG) polynomials on 8 intervals
-// per octave of s in [2^PLC_E_LO, 2^PLC_E_HI) (built on the host in long double, see plc_table.h); GM_rc3 = GM/rc^3.
-constexpr int PLC_DEG = 13, PLC_E_LO = -11, PLC_E_HI = 3, PLC_SUB = 8;
+// tab: optional device table of G(s) = P(a, s^2) / s^3, s = r/r_c, as degree-(PLC_DEG) polynomials on 2^PLC_SUB_BITS
+// intervals per octave of s in [2^PLC_E_LO, 2^PLC_E_HI) (built on the host in long double, see plc_table.h);
+// GM_rc3 = GM/rc^3.  Degree 9 on 32 intervals per octave is at the rounding floor for the value (2.1e-16; 5e-15 for the
+// derivative the Hessian needs) -- the first table (degree 13 on 8 intervals) spent 4 more FMAs and, with 8-byte loads,
+// 9 more load instructions per evaluation.  A row is PLC_DEG + 1 = 10 doubles (80 B, 16-byte aligned): five 16-byte loads.
+constexpr int PLC_DEG = 9, PLC_E_LO = -11, PLC_E_HI = 3, PLC_SUB_BITS = 5, PLC_SUB = 1 << PLC_SUB_BITS;
 constexpr int PLC_NINT = (PLC_E_HI - PLC_E_LO) * PLC_SUB;
 constexpr double PLC_S_ONE = 8.0;  // = 2^PLC_E_HI: s^2 = 64 > xcut (<= 41 for every 0 < a <= 3/2), so P == 1
 struct DevPLC { double GM, inv_rc, tail, GM_rc3; const double *tab; GammaTab ga, ga2; };
 
-// G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
-// SMEM: the table was staged into shared memory with PLC_STRIDE doubles per interval (plc_stage below).
 #ifndef GX_HERN_PAIR
 #define GX_HERN_PAIR 1
 #endif
-constexpr int PLC_STRIDE = PLC_DEG + 2;  // 15: odd, so the intervals of neighbouring lanes fall into different banks
-__device__ __forceinline__ double lds_f64(unsigned addr) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+// SMEM: the table was staged into shared memory (plc_stage below), rows of PLC_STRIDE doubles.
+constexpr int PLC_STRIDE = PLC_DEG + 1;
+static_assert(PLC_DEG % 2 == 1 && PLC_STRIDE % 2 == 0, "rows are read as pairs of doubles (16-byte loads)");
+__device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
+// G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
 template <bool SMEM>
 __device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, double &G, double *dG,
                                                   unsigned smem_base = 0) {
     if (tab == nullptr) return false;
     const int hi = __double2hiint(s);
-    // interval index from the bits of s > 0: (hi >> 17) = exponent field * 8 + top three mantissa bits
-    const unsigned j = (unsigned)(hi >> 17) - (unsigned)((1023 + PLC_E_LO) * PLC_SUB);
+    // interval index from the bits of s > 0: (hi >> (20 - B)) = exponent field * 2^B + top B mantissa bits
+    constexpr int B = PLC_SUB_BITS;
+    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + PLC_E_LO) * PLC_SUB);
     if (j >= (unsigned)PLC_NINT) return false;  // s outside [2^PLC_E_LO, 2^PLC_E_HI) (also NaN / negative)
-    // interval [2^e (1 + sub/8), 2^e (1 + (sub+1)/8)), t in [-1, 1):  t = 16 m - (17 + 2 sub) with m = s / 2^e in [1, 2).
-    // Both operands come straight from the bits of s (exact; identical to fma(s, 2^(4-e), -(17 + 2 sub))).
-    static_assert(PLC_SUB == 8, "bit tricks below assume 8 intervals per octave");
+    // interval [2^e (1 + sub/2^B), 2^e (1 + (sub+1)/2^B)), t in [-1, 1):  t = 2^(B+1) m - (2^(B+1) + 2 sub + 1) with
+    // m = s / 2^e in [1, 2).  Both operands come straight from the bits of s (exact).
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
-    const double c16 = __hiloint2double((hi & 0x000e0000) | 0x40310000, 0);  // 16 (1 + sub/8 + 1/16)
-    const double t = fma(m, 16.0, -c16);
+    constexpr int TOP = ((1 << B) - 1) << (20 - B), HALF = 1 << (19 - B), EXPC = (1023 + B + 1) << 20;
+    const double cB = __hiloint2double((hi & TOP) | HALF | EXPC, 0);  // 2^(B+1) (1 + sub/2^B + 2^-(B+1))
+    const double t = fma(m, (double)(2 << B), -cB);
     double v, d = 0.0;
     if (SMEM) {
         // 32-bit shared-window address; the fixed-step kernels pass the table's base (plc_smem_base) so that the window
         // base (S2R SR_CgaCtaId + LEA) is not re-derived in every step
         const unsigned a0 = (smem_base ? smem_base : (unsigned)__cvta_generic_to_shared(tab)) + j * (unsigned)(PLC_STRIDE * 8);
-        v = lds_f64(a0 + PLC_DEG * 8);
+        double2 c = lds_v2f64(a0 + (PLC_DEG - 1) * 8);
+        v = c.y;
+        if (dG) d = v;
+        v = fma(v, t, c.x);
 #pragma unroll
-        for (int k = PLC_DEG - 1; k >= 0; --k) {
+        for (int k = PLC_DEG - 3; k >= 0; k -= 2) {
+            c = lds_v2f64(a0 + k * 8);
             if (dG) d = fma(d, t, v);
-            v = fma(v, t, lds_f64(a0 + k * 8));
+            v = fma(v, t, c.y);
+            if (dG) d = fma(d, t, v);
+            v = fma(v, t, c.x);
         }
     } else {
-        const double *p = tab + (long long)j * (PLC_DEG + 1);
-        v = __ldg(p + PLC_DEG);
+        const double2 *p = reinterpret_cast<const double2 *>(tab + (long long)j * (PLC_DEG + 1));
+        double2 c = __ldg(p + (PLC_DEG - 1) / 2);
+        v = c.y;
+        if (dG) d = v;
+        v = fma(v, t, c.x);
 #pragma unroll
-        for (int k = PLC_DEG - 1; k >= 0; --k) {
+        for (int k = (PLC_DEG - 3) / 2; k >= 0; --k) {
+            c = __ldg(p + k);
             if (dG) d = fma(d, t, v);
-            v = fma(v, t, __ldg(p + k));
+            v = fma(v, t, c.y);
+            if (dG) d = fma(d, t, v);
+            v = fma(v, t, c.x);
         }
     }
     G = v;
     if (dG) {
         const int e = ((hi >> 20) & 0x7ff) - 1023;
-        *dG = d * __hiloint2double((1023 - e + 4) << 20, 0);  // dt/ds = 2^(4-e)
+        *dG = d * __hiloint2double((1023 - e + B + 1) << 20, 0);  // dt/ds = 2^(B+1-e)
     }
     return true;
 }
@@ -239,12 +256,12 @@ using CountsMW = Counts<1, 2, 1, 0>;      // MilkyWayPotential:      MN disk, NF
 using CountsMW2022 = Counts<3, 2, 1, 0, true>;  // MilkyWayPotential2022:  MN3 disk (one b), NFW halo, 2 Hernquist
 using CountsBovy = Counts<1, 0, 1, 1>;    // BovyMWPotential2014:    MN disk, PLC bulge, NFW halo
 
-// Shared-memory copy of the (single) PowerLawCutoff table of a static model.  Every lane reads a different interval, so
-// from global memory each of the 14 coefficient loads of a step costs up to 32 L1 wavefronts per warp (the Bovy
-// fixed-step kernel was load-bound, not FP64-bound); from shared memory with an odd stride it is 2-4.
+// Shared-memory copy of the (single) PowerLawCutoff table of a static model (35 KB).  Every lane reads a different
+// interval, so from global memory each coefficient load of a step costs up to 32 L1 wavefronts per warp (the Bovy
+// fixed-step kernel was load-bound, not FP64-bound); from shared memory it is a few.
 template <class C>
 __device__ __forceinline__ double *plc_smem() {
-    __shared__ double t[PLC_NINT * PLC_STRIDE];
+    __shared__ __align__(16) double t[PLC_NINT * PLC_STRIDE];
     return t;
 }
 // Shared-window address of the staged table, made opaque so that it stays in a register across the step loop.
@@ -263,8 +280,10 @@ __device__ __forceinline__ void plc_stage(const DevPot &P) {
     if constexpr (C::is_static && C::kPLC > 0) {
         double *t = plc_smem<C>();
         const double *src = P.plc[0].tab;
-        for (int idx = threadIdx.x; idx < PLC_NINT * (PLC_DEG + 1); idx += blockDim.x)
-            t[(idx / (PLC_DEG + 1)) * PLC_STRIDE + idx % (PLC_DEG + 1)] = __ldg(src + idx);
+        static_assert(PLC_STRIDE == PLC_DEG + 1, "rows are copied as they are");
+        const double2 *src2 = reinterpret_cast<const double2 *>(src);
+        double2 *t2 = reinterpret_cast<double2 *>(t);
+        for (int idx = threadIdx.x; idx < PLC_NINT * PLC_STRIDE / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
         __syncthreads();
     }
 }

@@ -102,6 +102,9 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
             n.rs = c.p[1];
             n.inv_rs = 1.0 / c.p[1];
             n.GM_inv_rs = n.GM / c.p[1];
+            n.GM_rs3 = n.GM / (c.p[1] * c.p[1] * c.p[1]);
+            n.pad_ = 0.0;
+            if (use_device && D.nfw_tab == nullptr) D.nfw_tab = nfw_table();
             break;
         }
         case GX_KIND_POWERLAWCUTOFF: {
@@ -429,6 +432,8 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
     constexpr bool STAGED = C::is_static && C::kPLC > 0;  // PowerLawCutoff table in shared memory (Bovy)
     plc_stage<C>(P);
     const unsigned plc_base = plc_smem_base<C>();
+    constexpr bool NFWT = nfw_tab_fixed_ok<C>();
+    const unsigned nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     // integrate in tau = dir * t (diffrax flips the sign of time the same way for t1 < t0)
@@ -459,14 +464,14 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv, plc_base);
+                gradient_factors<C, STAGED, NFWT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
                 npy = fma(fhh, nqy, py);
                 npz = fma(fvh, nqz, pz);
                 gx_ = gy_ = gz_ = 0.0;
             } else {
-                gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev);
+                gradient<C, STAGED, NFWT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
                 npx = fma(-gx_, hs, px);
                 npy = fma(-gy_, hs, py);
                 npz = fma(-gz_, hs, pz);
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqx = __dadd_rn(qx, __dmul_rn(px, hs));
             nqy = __dadd_rn(qy, __dmul_rn(py, hs));
             nqz = __dadd_rn(qz, __dmul_rn(pz, hs));
-            gradient<C, STAGED>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev);
+            gradient<C, STAGED, NFWT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
             npx = __dadd_rn(px, __dmul_rn(-gx_, hs));
             npy = __dadd_rn(py, __dmul_rn(-gy_, hs));
             npz = __dadd_rn(pz, __dmul_rn(-gz_, hs));
@@ -483,7 +488,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         } else {
             const double hm = tnext - tm;
             const double hh = FWD ? hm : -hm;
-            gradient<C, STAGED>(P, qx, qy, qz, gx_, gy_, gz_, FWD ? tprev : -tprev);
+            gradient<C, STAGED, NFWT>(P, qx, qy, qz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
             nqx = __dadd_rn(mqx, __dmul_rn(px, hh));
             nqy = __dadd_rn(mqy, __dmul_rn(py, hh));
             nqz = __dadd_rn(mqz, __dmul_rn(pz, hh));
@@ -533,6 +538,8 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     constexpr bool STAGED = C::kPLC > 0;
     plc_stage<C>(P);
     const unsigned plc_base = plc_smem_base<C>();
+    constexpr bool NFWT = nfw_tab_fixed_ok<C>();
+    const unsigned nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     const double T0 = FWD ? a.t0 : -a.t0;
@@ -578,7 +585,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qy = fma(py, hs, qy);
                     qz = fma(pz, hs, qz);
                     double fh, fv;
-                    gradient_factors<C, STAGED>(P, qx, qy, qz, fh, fv, plc_base);
+                    gradient_factors<C, STAGED, NFWT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
                     const double fhh = -fh * hs, fvh = -fv * hs;
                     px = fma(fhh, qx, px);
                     py = fma(fhh, qy, py);
@@ -591,7 +598,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 const double tnext = tprev + h;
                 const double nqx = fma(px, hs, qx), nqy = fma(py, hs, qy), nqz = fma(pz, hs, qz);
                 double fh, fv;
-                gradient_factors<C, STAGED>(P, nqx, nqy, nqz, fh, fv, plc_base);
+                gradient_factors<C, STAGED, NFWT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 const double npx = fma(fhh, nqx, px), npy = fma(fhh, nqy, py), npz = fma(fvh, nqz, pz);
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
@@ -697,7 +704,11 @@ __device__ __forceinline__ const DevPot &rhs_pot() {
 template <class C>
 __device__ __noinline__ void accel_call_static(double x, double y, double z, double &ax, double &ay, double &az) {
     double g0, g1, g2;
-    gradient<C, (C::is_static && C::kPLC > 0)>(rhs_pot<C>(), x, y, z, g0, g1, g2);
+    unsigned nfw_base = 0;  // the kernel prologue staged the NFW force table (nfw_stage) iff the potential carries it
+    if constexpr (nfw_tab_ok<C>()) {
+        if (rhs_pot<C>().nfw_tab != nullptr) nfw_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
+    }
+    gradient<C, (C::is_static && C::kPLC > 0), nfw_tab_ok<C>()>(rhs_pot<C>(), x, y, z, g0, g1, g2, 0.0, nfw_base);
     ax = -g0; ay = -g1; az = -g2;
 }
 // runtime composites may be time dependent (LinearParameter): the callee also receives the physical time
@@ -767,6 +778,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     }
 #endif
     plc_stage<C>(P);  // (Bovy) the PowerLawCutoff table, read by accel_call()
+    (void)nfw_stage<C, nfw_tab_ok<C>()>(P);  // (MW, MW2022) the NFW force table, likewise
     const unsigned FULL = 0xffffffffu;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const double NANV = __longlong_as_double(0x7ff8000000000000LL);
@@ -1181,7 +1193,7 @@ __global__ void k_bench_dfma3(long long iters, double *sink) {
     if (s == 123.456) sink[0] = s + y0 + y1 + y2 + y3 + z0 + z1 + z2 + z3;
 }
 
-__global__ void k_debug_math(int op, const GammaTab *gt, const double *x, long long N, double *out) {
+__global__ void k_debug_math(int op, const GammaTab *gt, const double *tab, const double *x, long long N, double *out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const double v = x[i];
@@ -1192,6 +1204,17 @@ __global__ void k_debug_math(int op, const GammaTab *gt, const double *x, long l
     case 2: r = log1p_pos(v); break;
     case 3: r = gammainc_P(*gt, v, nullptr); break;
     case 4: r = nfw_menc_shape(v); break;
+    case 5:  // NFW force table F(s); NaN outside the tabulated range
+        if (!poly_table_eval<false, NFW_E_LO, NFW_NINT>(tab, v, r, nullptr)) r = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+    case 6:  // PowerLawCutoff table G(s) for exponent a; NaN outside the tabulated range
+        if (!plc_table_eval_at<false>(tab, v, r, nullptr)) r = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+    case 7: {  // ... and its derivative dG/ds
+        double g;
+        if (!plc_table_eval_at<false>(tab, v, g, &r)) r = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+    }
     default: r = 0.0;
     }
     out[i] = r;
@@ -1633,7 +1656,11 @@ int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out,
         if (cudaMalloc(&gt, sizeof h) != cudaSuccess) return GX_ERR_CUDA;
         cudaMemcpyAsync(gt, &h, sizeof h, cudaMemcpyHostToDevice, (cudaStream_t)stream);
     }
-    k_debug_math<<<grid_for(N, 256), 256, 0, (cudaStream_t)stream>>>(op, gt, x, (long long)N, out);
+    const double *tab = nullptr;
+    if (op == 5) tab = nfw_table();
+    if (op == 6 || op == 7) tab = plc_table_for(a);
+    if (op >= 5 && op <= 7 && tab == nullptr) return GX_ERR_UNSUPPORTED;  // the table could not be built to 1e-14
+    k_debug_math<<<grid_for(N, 256), 256, 0, (cudaStream_t)stream>>>(op, gt, tab, x, (long long)N, out);
     int rc = cuda_rc(cudaGetLastError());
     if (gt) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(gt); }
     return rc;

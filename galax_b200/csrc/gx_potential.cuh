@@ -35,7 +35,7 @@ constexpr double TINY = 2.2250738585072014e-308;
 
 struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
 struct DevHern { double GM, c; };
-struct DevNFW { double GM, rs, inv_rs, GM_inv_rs; };
+struct DevNFW { double GM, rs, inv_rs, GM_inv_rs, GM_rs3, pad_; };  // GM_rs3 = GM / rs^3 (force table)
 // ga: a = 3/2 - alpha/2; ga2: a - 1/2; tail = Gamma(a2)/(rc Gamma(a)).
 // tab: optional device table of G(s) = P(a, s^2) / s^3, s = r/r_c, as degree-(PLC_DEG) polynomials on 2^PLC_SUB_BITS
 // intervals per octave of s in [2^PLC_E_LO, 2^PLC_E_HI) (built on the host in long double, see plc_table.h);
@@ -58,16 +58,18 @@ __device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
-// G(s) and (optionally) dG/ds from the table; returns false when s is outside the tabulated range.
-template <bool SMEM>
-__device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, double &G, double *dG,
-                                                  unsigned smem_base = 0) {
-    if (tab == nullptr) return false;
+// Piecewise-polynomial table lookup: value and (optionally) derivative with respect to s of a function tabulated on
+// 2^PLC_SUB_BITS intervals per octave of s in [2^E_LO, 2^E_LO + NINT / 2^PLC_SUB_BITS octaves); returns false when s is
+// outside the tabulated range.  Shared by the PowerLawCutoff and the NFW force tables.
+template <bool SMEM, int E_LO, int NINT>
+__device__ __forceinline__ bool poly_table_eval(const double *tab, double s, double &G, double *dG,
+                                                unsigned smem_base = 0) {
+    if (!SMEM && tab == nullptr) return false;
     const int hi = __double2hiint(s);
     // interval index from the bits of s > 0: (hi >> (20 - B)) = exponent field * 2^B + top B mantissa bits
     constexpr int B = PLC_SUB_BITS;
-    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + PLC_E_LO) * PLC_SUB);
-    if (j >= (unsigned)PLC_NINT) return false;  // s outside [2^PLC_E_LO, 2^PLC_E_HI) (also NaN / negative)
+    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + E_LO) * PLC_SUB);
+    if (j >= (unsigned)NINT) return false;  // s outside the table (also NaN / negative)
     // interval [2^e (1 + sub/2^B), 2^e (1 + (sub+1)/2^B)), t in [-1, 1):  t = 2^(B+1) m - (2^(B+1) + 2 sub + 1) with
     // m = s / 2^e in [1, 2).  Both operands come straight from the bits of s (exact).
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
@@ -113,6 +115,23 @@ __device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, d
     }
     return true;
 }
+template <bool SMEM>
+__device__ __forceinline__ bool plc_table_eval_at(const double *tab, double s, double &G, double *dG,
+                                                  unsigned smem_base = 0) {
+    if (tab == nullptr) return false;
+    return poly_table_eval<SMEM, PLC_E_LO, PLC_NINT>(tab, s, G, dG, smem_base);
+}
+// NFW force table: F(s) = (ln(1+s) - s/(1+s)) / s^3, so that Phi'/r = G m M(s) / r^3 = (G m / r_s^3) F(s), s = r/r_s.
+// One universal function (no parameter): 12 octaves [2^-7, 2^5) x 32 intervals x degree 9 = 30 KB, staged in shared
+// memory by the fixed-step and Dopri kernels of the static models without a PowerLawCutoff component.  Replaces, per
+// evaluation, the reciprocal of 1+s, the table logarithm and the small-s series switch (21 FP64 + 12 other
+// instructions) by 12 FP64 + five 16-byte loads + 5 integer instructions, and is accurate to 2e-16 everywhere (the
+// closed form loses digits to cancellation around s ~ 2^-4).  Outside the range the closed form is used.
+constexpr int NFW_E_LO = -7, NFW_E_HI = 5;
+constexpr int NFW_NINT = (NFW_E_HI - NFW_E_LO) * PLC_SUB;
+#ifndef GX_NFW_TABLE
+#define GX_NFW_TABLE 1
+#endif
 __device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double &G, double *dG) {
     return plc_table_eval_at<false>(c.tab, s, G, dG);
 }
@@ -159,6 +178,7 @@ struct DevPot {
     DevRad rad[MAX_RAD];
     DevHarm harm[MAX_HARM];
     DevHenon henon[MAX_HENON];
+    const double *nfw_tab;  // universal NFW force table (nfw_table(), plc_table.h) or nullptr
     DevTD td;
 };
 
@@ -288,15 +308,52 @@ __device__ __forceinline__ void plc_stage(const DevPot &P) {
     }
 }
 
+// The same for the NFW force table (static models with one NFW halo and no PowerLawCutoff table: both do not fit
+// beside 5-6 resident CTAs).
+template <class C>
+__host__ __device__ constexpr bool nfw_tab_ok() { return GX_NFW_TABLE && C::is_static && C::kNFW == 1 && C::kPLC == 0; }
+// The lookup moves 80 B per evaluation from randomly scattered rows through the SM's single shared-memory port (bank
+// conflicts included: ~60 port cycles per warp evaluation).  The Dopri kernels (3 warps per scheduler) gain 2.5-4.5 %;
+// of the fixed-step kernels MilkyWayPotential2022's heavier step (three disks) gains 6 %, but MilkyWayPotential's step
+// (166 issue cycles per warp-step on each of four schedulers) saturates that port and runs 14 % SLOWER with the table.
+// So the fixed-step kernels use it from GX_NFW_TABLE_FIXED_MIN_MN Miyamoto-Nagai terms up.
+#ifndef GX_NFW_TABLE_FIXED_MIN_MN
+#define GX_NFW_TABLE_FIXED_MIN_MN 3
+#endif
+template <class C>
+__host__ __device__ constexpr bool nfw_tab_fixed_ok() { return nfw_tab_ok<C>() && C::kMN >= GX_NFW_TABLE_FIXED_MIN_MN; }
+template <class C>
+__device__ __forceinline__ double *nfw_smem() {
+    __shared__ __align__(16) double t[NFW_NINT * PLC_STRIDE];
+    return t;
+}
+// Call once per CTA, by all threads; returns the shared-window address of the table (0 = no table: closed form).
+template <class C, bool ON>
+__device__ __forceinline__ unsigned nfw_stage(const DevPot &P) {
+    unsigned b = 0;
+    if constexpr (ON) {
+        if (P.nfw_tab != nullptr) {  // (uniform)
+            double *t = nfw_smem<C>();
+            const double2 *src2 = reinterpret_cast<const double2 *>(P.nfw_tab);
+            double2 *t2 = reinterpret_cast<double2 *>(t);
+            for (int idx = threadIdx.x; idx < NFW_NINT * PLC_STRIDE / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
+            __syncthreads();
+            b = (unsigned)__cvta_generic_to_shared(t);
+            asm volatile("" : "+r"(b));
+        }
+    }
+    return b;
+}
+
 // ---------------------------------------------------------------------------------------------
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
 // The flattened + spherical part is returned as two scalars: grad = (fh x, fh y, fv z); the kinds that are neither
 // (triaxial logarithmic / ellipsoidal profiles / polynomials) are added to (ex, ey, ez) by gradient<C>() below.
 // Terms of the form GM_i w_i / r (Hernquist, NFW) are summed before the common factor 1/r is applied.
-template <class C, bool PLC_SMEM = false>
+template <class C, bool PLC_SMEM = false, bool NFW_TAB = false>
 __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, double y, double z, double &fh, double &fv,
-                                                 unsigned plc_base = 0) {
+                                                 unsigned plc_base = 0, unsigned nfw_base = 0) {
     const double z2 = z * z;
     const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
     double fxy = 0.0, fz = 0.0, fs = 0.0, fr = 0.0;  // fs: terms Phi'/r as they are; fr: terms still to be divided by r
@@ -368,7 +425,15 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
         for (int i = 0; i < C::kNFW; ++i) {
             if (!C::is_static && i >= P.n_nfw) break;
             const DevNFW &c = P.nfw[i];
-            double m = nfw_menc_shape(r * c.inv_rs);
+            const double s = r * c.inv_rs;
+            if constexpr (NFW_TAB) {
+                double F;
+                if (nfw_base != 0 && poly_table_eval<true, NFW_E_LO, NFW_NINT>(nullptr, s, F, nullptr, nfw_base)) {
+                    fs = fma(c.GM_rs3, F, fs);  // Phi'/r = (GM / rs^3) F(s)
+                    continue;
+                }
+            }
+            double m = nfw_menc_shape(s);
             // Phi'/r = GM m(s) / r^3 = (GM m / r^2) / r
             if (C::is_static && C::kH == 0 && i == 0) fr = (c.GM * m) * rinv2; else fr = fma(c.GM * m, rinv2, fr);
         }
@@ -388,7 +453,7 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
                 fr = fma(c.GM * Pg, rinv2, fr);
             }
         }
-        if (C::is_static && C::kPLC == 0) fs = fr * rinv; else fs = fma(fr, rinv, fs);
+        if (C::is_static && C::kPLC == 0 && !NFW_TAB) fs = fr * rinv; else fs = fma(fr, rinv, fs);
     }
     fh = fxy + fs;
     fv = fz + fs;
@@ -494,15 +559,15 @@ __device__ __noinline__ void gradient_td(const DevTD &R, double t, double x, dou
 
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
-template <class C, bool PLC_SMEM = false>
+template <class C, bool PLC_SMEM = false, bool NFW_TAB = false>
 __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
-                                         double &gz_, double t = 0.0) {
+                                         double &gz_, double t = 0.0, unsigned nfw_base = 0) {
     if (!C::is_static && P.td.n > 0) {  // time-dependent composite (runtime path only)
         gradient_td(P.td, t, x, y, z, gx_, gy_, gz_);
         return;
     }
     double fh, fv;
-    gradient_factors<C, PLC_SMEM>(P, x, y, z, fh, fv);
+    gradient_factors<C, PLC_SMEM, NFW_TAB>(P, x, y, z, fh, fv, 0, nfw_base);
     gx_ = fh * x;
     gy_ = fh * y;
     gz_ = fv * z;

@@ -39,13 +39,14 @@ static long double plc_P_ld(long double a, long double x) {
 static long double plc_G_ld(long double a, long double s) { return plc_P_ld(a, s * s) / (s * s * s); }
 
 // Chebyshev interpolation on [-1, 1] at PLC_DEG+1 nodes, converted to monomial coefficients in long double.
-static void plc_fit_interval(long double a, long double s0, long double s1, double *coef, double *max_rel_err) {
+template <class F>
+static void fit_interval(const F &fun, long double s0, long double s1, double *coef, double *max_rel_err) {
     constexpr int n = PLC_DEG + 1;
     const long double PI = 3.141592653589793238462643383279502884L;
     long double f[n], c[n];
     for (int k = 0; k < n; ++k) {
         long double tk = cosl(PI * (k + 0.5L) / n);
-        f[k] = plc_G_ld(a, 0.5L * (s0 + s1) + 0.5L * (s1 - s0) * tk);
+        f[k] = fun(0.5L * (s0 + s1) + 0.5L * (s1 - s0) * tk);
     }
     for (int j = 0; j < n; ++j) {  // Chebyshev coefficients
         long double sum = 0.0L;
@@ -73,11 +74,66 @@ static void plc_fit_interval(long double a, long double s0, long double s1, doub
         double v = coef[n - 1];
         for (int i = n - 2; i >= 0; --i) v = fma(v, t, coef[i]);
         long double s = 0.5L * (s0 + s1) + 0.5L * (s1 - s0) * (long double)t;
-        long double ref = plc_G_ld(a, s);
+        long double ref = fun(s);
         double rel = (double)fabsl(((long double)v - ref) / ref);
         if (rel > worst) worst = rel;
     }
     if (max_rel_err && worst > *max_rel_err) *max_rel_err = worst;
+}
+
+static void plc_fit_interval(long double a, long double s0, long double s1, double *coef, double *max_rel_err) {
+    fit_interval([a](long double s) { return plc_G_ld(a, s); }, s0, s1, coef, max_rel_err);
+}
+
+// NFW force shape F(s) = (ln(1+s) - s/(1+s)) / s^3 in long double; below s = 0.1 the alternating series
+// sum_{k>=2} (-1)^k (k-1)/k s^(k-3) (the two closed-form terms cancel to O(s^2)).
+static long double nfw_F_ld(long double s) {
+    if (s < 0.1L) {
+        long double sum = 0.0L, pw = 1.0L / s;  // s^(k-3) for k = 2
+        for (int k = 2; k < 80; ++k) {
+            sum += ((k & 1) ? -1.0L : 1.0L) * (long double)(k - 1) / (long double)k * pw;
+            pw *= s;
+        }
+        return sum;
+    }
+    return (log1pl(s) - s / (1.0L + s)) / (s * s * s);
+}
+
+// The universal NFW force table on the current device (built and uploaded on first use, immutable afterwards), or
+// nullptr if it cannot be built to 1e-14 (then the kernels keep the closed form).
+static const double *nfw_table(double *max_rel_err_out = nullptr) {
+    struct Entry { int device; double *dev_ptr; double max_rel_err; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &e : cache)
+        if (e.device == dev) {
+            if (max_rel_err_out) *max_rel_err_out = e.max_rel_err;
+            return e.dev_ptr;
+        }
+    static std::vector<double> host;  // the fit does not depend on the device: done once per process
+    static double worst = 0.0;
+    if (host.empty()) {
+        host.resize((size_t)NFW_NINT * (PLC_DEG + 1));
+        for (int j = 0; j < NFW_NINT; ++j) {
+            const int e = NFW_E_LO + j / PLC_SUB, sub = j % PLC_SUB;
+            const long double base = ldexpl(1.0L, e);
+            fit_interval(nfw_F_ld, base * (1.0L + sub / (long double)PLC_SUB),
+                         base * (1.0L + (sub + 1) / (long double)PLC_SUB), host.data() + (size_t)j * (PLC_DEG + 1), &worst);
+        }
+    }
+    double *d = nullptr;
+    if (worst < 1e-14 && cudaMalloc(&d, host.size() * sizeof(double)) == cudaSuccess) {
+        if (cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(d);
+            d = nullptr;
+        }
+    }
+    cache.push_back({dev, d, worst});
+    if (max_rel_err_out) *max_rel_err_out = worst;
+    return d;
 }
 
 struct PlcTableEntry { int device; double a; double *dev_ptr; double max_rel_err; };

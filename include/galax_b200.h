@@ -216,7 +216,9 @@ int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void
  * normals `jr.normal(k_j, ())` on `jr.split(subkey, 4)`.  The key chain is inherently sequential and runs on the host
  * (integer arithmetic, ~50 ns per link); the 4 M normals are computed on the device.  draws: device [4][M]. */
 int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *stream);
-/* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x) */
+/* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x), 4 NFW shape ln(1+s) - s/(1+s),
+ * 5 NFW force table F(s) = shape / s^3, 6 / 7 PowerLawCutoff table G(s) = P(a, s^2) / s^3 and dG/ds (NaN outside the
+ * tabulated range) */
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream);
 
 #ifdef __cplusplus

@@ -6,7 +6,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 import galax_b200.dynamics as gd, galax_b200.potential as gp
 from quick_perf import ev_time, ics
-pot = gp.MilkyWayPotential2022()
+pot = getattr(gp, os.environ.get("POT", "MilkyWayPotential2022"))()
 N = int(os.environ.get("N", 148 * 2048)); T = int(os.environ.get("T", 10))
 q, p = ics(pot, N, seed=2)
 ts = np.linspace(0, 5000.0, T)

@@ -285,6 +285,27 @@ def test_fast_math_primitives(built_lib):
         if s[i] > 0:
             t = float(mp.log1p(mp.mpf(s[i])) - mp.mpf(s[i]) / (1 + mp.mpf(s[i])))
             assert abs(m[i] / t - 1) < max(5e-16, 8e-16 / min(s[i], 1.0)), (s[i], m[i], t)  # cancellation ~eps/s above the series cut
+    # force tables (piecewise degree-9 polynomials, 32 intervals per octave): value at the rounding floor everywhere,
+    # interval boundaries included
+    edges = np.ldexp(1.0 + np.arange(32) / 32.0, rng.integers(-7, 5, 32))
+    below = np.nextafter(edges, 0)
+    st = np.concatenate([2.0 ** rng.uniform(-7, 5, 30000), edges, below[below >= 2.0 ** -7], [2.0 ** -7, np.nextafter(32.0, 0)]])
+    F = run(5, src=torch.tensor(st, device="cuda"))
+    assert np.isfinite(F).all()
+    for i in np.concatenate([rng.choice(30000, 300, replace=False), np.arange(30000, len(st))]):
+        sv = mp.mpf(float(st[i]))
+        t = float((mp.log1p(sv) - sv / (1 + sv)) / sv**3)
+        assert abs(F[i] / t - 1) < 5e-16, (st[i], F[i], t)
+    assert np.isnan(run(5, src=torch.tensor([2.0 ** -7.001, 32.0, 1e3, 0.0], dtype=torch.float64, device="cuda"))).all()
+    sp = 2.0 ** rng.uniform(-11, 3, 400)
+    for a in (0.6, 1.05):
+        G, dG = run(6, a=a, src=torch.tensor(sp, device="cuda")), run(7, a=a, src=torch.tensor(sp, device="cuda"))
+        for i in range(0, 400, 4):
+            sv = mp.mpf(float(sp[i]))
+            Pv = mp.gammainc(a, 0, sv * sv, regularized=True)
+            t = Pv / sv**3
+            dt = 2 * sv * (sv * sv) ** (a - 1) * mp.e ** (-sv * sv) / mp.gamma(a) / sv**3 - 3 * Pv / sv**4
+            assert abs(G[i] / float(t) - 1) < 6e-16 and abs(dG[i] / float(dt) - 1) < 5e-14, (a, sp[i])
     for a in (0.6, 0.1, 1.05):
         xs = 10 ** rng.uniform(-8, 2.7, 20000)
         g = run(3, a=a, src=torch.tensor(xs, device="cuda"))

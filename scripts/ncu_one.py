@@ -8,7 +8,8 @@ import galax_b200.dynamics as gd, galax_b200.potential as gp
 from galax_b200 import _lib
 from quick_perf import ics
 which = sys.argv[1]
-N = 148 * 8192
+import os
+N = int(os.environ.get("N", 148 * 8192))
 if which in ("fixed", "fixed_bovy"):
     pot = gp.MilkyWayPotential() if which == "fixed" else gp.BovyMWPotential2014()
     q, p = ics(pot, N, seed=1)

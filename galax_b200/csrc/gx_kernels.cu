@@ -398,6 +398,38 @@ static inline double clip_to_end_host(double tprev, double tnext, double t1) {
     return (tnext > t1 - 1e-10) ? t1 : tnext;
 }
 
+// Walk diffrax's ConstantStepSize grid exactly as the device does (same fp64 operations): trip count, whether
+// max_steps cut it short, and (while `seg_ok`) its run-length form for k_integrate_fixed_seg.  seg_ok turns false when
+// the grid needs more than FIXED_MAX_SEG runs or a step is not exactly representable (the general kernel handles both).
+static void walk_time_grid(double t0, double t1, double dt0, long long max_steps, FixedSeg &sg, bool &seg_ok,
+                           long long &n_steps, int &hit_max_steps) {
+    const double dir = (t1 >= t0) ? 1.0 : -1.0;
+    const double T0 = t0 * dir, T1 = t1 * dir, h0 = dt0 * dir;
+    double tprev = T0, tnext = clip_to_end_host(T0, T0 + h0, T1), seg_t0 = 0.0;
+    long long n = 0;
+    int hit = 0;
+    sg.n_seg = 0;
+    while (tprev < T1) {
+        if (max_steps >= 0 && n >= max_steps) { hit = 1; break; }
+        ++n;
+        if (seg_ok) {  // run-length encode h_n = tnext - tprev (exact); a run must also satisfy t_s + j h == t_j
+            const double h = tnext - tprev;
+            if (sg.n_seg > 0 && sg.h[sg.n_seg - 1] == h &&
+                fma((double)(sg.cnt[sg.n_seg - 1] + 1), h, seg_t0) == tnext) {
+                ++sg.cnt[sg.n_seg - 1];
+            } else if (sg.n_seg < FIXED_MAX_SEG && tprev + h == tnext) {
+                sg.h[sg.n_seg] = h; sg.cnt[sg.n_seg] = 1; seg_t0 = tprev; ++sg.n_seg;
+            } else {
+                seg_ok = false;
+            }
+        }
+        tprev = tnext;
+        tnext = clip_to_end_host(tprev, tprev + h0, T1);
+    }
+    n_steps = n;
+    hit_max_steps = hit;
+}
+
 __device__ __forceinline__ double clip_to_end(double tprev, double tnext, double t1, bool keep) {
     // diffrax _clip_to_end (fp64 tolerance 1e-10)
     if (tnext > t1 - 1e-10) return keep ? t1 : tprev + 0.5 * (t1 - tprev);
@@ -1308,37 +1340,11 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     if (N == 0) return 0;
     FixedArgs a;
     FixedSeg sg;
-    double seg_t0 = 0.0;
     bool seg_ok = GX_FIXED_SEG && GX_FUSED_UPDATE && !general_kernel && scheme == GX_SCHEME_SEMI_IMPLICIT_EULER && model != MODEL_GENERIC;
     a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p; a.status = status;
     a.N = N; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
-    {   // walk the time grid exactly as the device does (same fp64 operations) to get the trip count
-        const double T0 = t0 * dir, T1 = t1 * dir, h0 = dt0 * dir;
-        double tprev = T0, tnext = clip_to_end_host(T0, T0 + h0, T1);
-        long long n = 0;
-        int hit = 0;
-        sg.n_seg = 0;
-        while (tprev < T1) {
-            if (max_steps >= 0 && n >= max_steps) { hit = 1; break; }
-            ++n;
-            if (seg_ok) {  // run-length encode h_n = tnext - tprev (exact); a run must also satisfy t_s + j h == t_j
-                const double h = tnext - tprev;
-                if (sg.n_seg > 0 && sg.h[sg.n_seg - 1] == h &&
-                    fma((double)(sg.cnt[sg.n_seg - 1] + 1), h, seg_t0) == tnext) {
-                    ++sg.cnt[sg.n_seg - 1];
-                } else if (sg.n_seg < FIXED_MAX_SEG && tprev + h == tnext) {
-                    sg.h[sg.n_seg] = h; sg.cnt[sg.n_seg] = 1; seg_t0 = tprev; ++sg.n_seg;
-                } else {
-                    seg_ok = false;  // too many runs (or an inexact difference): the general kernel handles it
-                }
-            }
-            tprev = tnext;
-            tnext = clip_to_end_host(tprev, tprev + h0, T1);
-        }
-        a.n_steps = n;
-        a.hit_max_steps = hit;
-    }
+    walk_time_grid(t0, t1, dt0, max_steps, sg, seg_ok, a.n_steps, a.hit_max_steps);
     // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers
     const int block = (N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32);
     const int grid = grid_for(N, block);
@@ -1644,6 +1650,25 @@ int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *dra
     cudaFreeAsync(d, s);
     free(h);
     return rc;
+}
+
+int gx_fixed_time_grid(double t0, double t1, double dt0, int64_t max_steps, int64_t *n_steps, int32_t *hit_max_steps,
+                       int32_t *n_runs, int64_t *run_count, double *run_step, int32_t run_capacity) {
+    const double dir = (t1 >= t0) ? 1.0 : -1.0;
+    if (t1 != t0 && !(dt0 * dir > 0.0)) return GX_ERR_BADARG;
+    FixedSeg sg;
+    bool seg_ok = true;
+    long long n = 0;
+    int hit = 0;
+    walk_time_grid(t0, t1, dt0, max_steps, sg, seg_ok, n, hit);
+    if (n_steps) *n_steps = n;
+    if (hit_max_steps) *hit_max_steps = hit;
+    if (n_runs) *n_runs = seg_ok ? sg.n_seg : -1;
+    if (seg_ok && run_count && run_step) {
+        if (run_capacity < sg.n_seg) return GX_ERR_BADARG;
+        for (int k = 0; k < sg.n_seg; ++k) { run_count[k] = sg.cnt[k]; run_step[k] = sg.h[k]; }
+    }
+    return 0;
 }
 
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream) {

@@ -126,6 +126,16 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
                        double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
                        double *q, double *p, int32_t *status, void *stream);
 
+/* Host only (no CUDA call): the time grid gx_integrate_fixed walks for (t0, t1, dt0, max_steps) -- diffrax's
+ * ConstantStepSize grid t_{n+1} = fl(t_n + dt0) with the last step clipped to t1 (_clip_to_end, 1e-10) -- as a trip
+ * count and in run-length form: run k is run_count[k] steps of the exactly representable size run_step[k] (in the
+ * direction of integration; t_s + j * run_step[k] reproduces the grid times exactly inside a run).  This is what the
+ * fixed-step kernel for MilkyWayPotential / MilkyWayPotential2022 / BovyMWPotential2014 consumes; n_runs = -1 means the
+ * grid has more than 120 runs (or a step that is not exactly representable) and the general kernel is used.
+ * Any output pointer may be NULL. */
+int gx_fixed_time_grid(double t0, double t1, double dt0, int64_t max_steps, int64_t *n_steps, int32_t *hit_max_steps,
+                       int32_t *n_runs, int64_t *run_count, double *run_step, int32_t run_capacity);
+
 /* Adaptive integration, per-particle step control.  Replaces
  *   OrbitSolver(dfx.Dopri8(), stepsize_controller=dfx.PIDController(rtol, atol)).solve(lstrat.VMap, field, ...)
  * and the per-particle solves of Integrator/evaluate_orbit (dynamics/_src/legacy/integrator.py:179-245,449-527;

@@ -1,0 +1,98 @@
+"""CPU: the run-length form of diffrax's ConstantStepSize time grid (gx_fixed_time_grid, host only -- no CUDA call).
+
+The fixed-step kernel of the three named Milky-Way models consumes the grid as runs of equal, exactly representable
+steps; these tests check the runs against a plain walk of the recurrence t_{n+1} = fl(t_n + dt0) with diffrax's
+``_clip_to_end`` (tolerance 1e-10), the same recurrence the oracle integrates on (oracle/galax_oracle.c)."""
+import ctypes as C
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from galax_b200 import _lib
+
+
+def walk(t0, t1, dt0, max_steps=None):
+    """The grid times in tau = dir * t, as a list starting at dir * t0."""
+    d = 1.0 if t1 >= t0 else -1.0
+    T0, T1, h0 = t0 * d, t1 * d, dt0 * d
+    clip = lambda tn: T1 if tn > T1 - 1e-10 else tn
+    ts, tprev, tnext = [T0], T0, clip(T0 + h0)
+    while tprev < T1:
+        if max_steps is not None and len(ts) - 1 >= max_steps:
+            return ts, True
+        ts.append(tnext)
+        tprev, tnext = tnext, clip(tnext + h0)
+    return ts, False
+
+
+def runs(t0, t1, dt0, max_steps=-1, cap=128):
+    L = _lib.lib()
+    n, hit, nr = C.c_int64(), C.c_int32(), C.c_int32()
+    cnt, h = (C.c_int64 * cap)(), (C.c_double * cap)()
+    rc = L.gx_fixed_time_grid(t0, t1, dt0, max_steps, C.byref(n), C.byref(hit), C.byref(nr), cnt, h, cap)
+    assert rc == 0
+    k = max(nr.value, 0)
+    return n.value, bool(hit.value), nr.value, list(cnt[:k]), list(h[:k])
+
+
+CASES = [
+    (0.0, 1000.0, 0.1),        # C1 / the bench
+    (0.0, 100.0, 0.1), (0.0, 37.3, 0.25), (-40.0, 55.5, 0.07), (30.0, -20.0, -0.13), (1000.0, 1003.0, 1e-3),
+    (0.0, 10.0, 3.0), (5.0, 5.0, 0.1), (0.0, 1.0, 2.0), (0.0, 200.0, 0.001), (-3000.0, 0.0, 0.5), (1e-3, 2e-3, 1e-7),
+    (0.0, 1.0, 1.0 / 3.0), (123.456, 789.0123, 0.0317),
+]
+
+
+@pytest.mark.parametrize("t0,t1,dt0", CASES)
+def test_runs_reproduce_the_grid_exactly(t0, t1, dt0):
+    ts, _ = walk(t0, t1, dt0)
+    n, hit, nr, cnt, h = runs(t0, t1, dt0)
+    assert n == len(ts) - 1 and not hit
+    assert nr >= 0 and sum(cnt) == n and all(c > 0 for c in cnt)
+    # inside a run the grid times are t_s + j h exactly (what the kernel's save-time search relies on), and the runs
+    # chain: the end of one is the start of the next
+    t, i = ts[0], 0
+    for c, hh in zip(cnt, h):
+        j = np.arange(1, c + 1, dtype=np.float64)
+        # fma(j, h, t_s) on the device: one rounding of the exact t_s + j h (here through Fraction)
+        got = np.array([float(Fraction(t) + int(jj) * Fraction(hh)) for jj in j[: min(c, 2000)]])  # = fma(j, h, t_s)
+        assert np.array_equal(got, np.array(ts[i + 1 : i + 1 + len(got)])), (t0, t1, dt0)
+        assert ts[i + c] - ts[i + c - 1] == hh
+        t, i = ts[i + c], i + c
+    assert i == n
+
+
+def test_c1_grid_is_a_few_dozen_runs_and_counts_follow_max_steps():
+    n, hit, nr, cnt, h = runs(0.0, 1000.0, 0.1)
+    assert n == 10_000 and 10 <= nr <= 60
+    assert abs(sum(c * hh for c, hh in zip(cnt, h)) - 1000.0) < 1e-9
+    n, hit, nr, cnt, h = runs(0.0, 1000.0, 0.1, max_steps=600)
+    assert n == 600 and hit and sum(cnt) == 600
+    n, hit, nr, cnt, h = runs(5.0, 5.0, 0.1)
+    assert n == 0 and nr == 0 and not hit
+
+
+def test_random_grids_and_fallback():
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        t0 = float(rng.uniform(-500, 500))
+        span = float(10 ** rng.uniform(-2, 3)) * (1 if rng.random() < 0.7 else -1)
+        dt0 = abs(span) / float(rng.integers(3, 4000)) * (1 if span > 0 else -1)
+        ts, _ = walk(t0, t0 + span, dt0)
+        n, hit, nr, cnt, h = runs(t0, t0 + span, dt0)
+        assert n == len(ts) - 1
+        if nr >= 0:
+            assert sum(cnt) == n
+            steps = np.diff(np.array(ts))
+            assert np.array_equal(np.repeat(np.array(h), np.array(cnt, dtype=np.int64)), steps)
+    # wrong direction of dt0 is an argument error; a grid needing more runs than the kernel takes reports -1
+    L = _lib.lib()
+    assert L.gx_fixed_time_grid(0.0, 1.0, -0.1, -1, None, None, None, None, None, 0) == -1  # GX_ERR_BADARG
+    # every sum a tie (dt0 an odd multiple of half an ulp of t): round-to-even settles on one step size after the first
+    # step, so even this grid is two runs
+    dt0 = (2.0**40 + 1) * 2.0**-53
+    ts, _ = walk(1.0, 1.1, dt0)
+    n, hit, nr, cnt, h = runs(1.0, 1.1, dt0)
+    assert n == len(ts) - 1 and 1 <= nr <= 3
+    assert np.array_equal(np.repeat(np.array(h), np.array(cnt, dtype=np.int64)), np.diff(np.array(ts)))

@@ -566,8 +566,8 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
 template <class C, bool FWD>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS)
 k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
-    static_assert(C::is_static, "run-length variant: static models only");
-    constexpr bool STAGED = C::kPLC > 0;
+    // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
+    constexpr bool STAGED = C::is_static && C::kPLC > 0;
     plc_stage<C>(P);
     const unsigned plc_base = plc_smem_base<C>();
     constexpr bool NFWT = nfw_tab_fixed_ok<C>();
@@ -616,12 +616,20 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qx = fma(px, hs, qx);
                     qy = fma(py, hs, qy);
                     qz = fma(pz, hs, qz);
-                    double fh, fv;
-                    gradient_factors<C, STAGED, NFWT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
-                    const double fhh = -fh * hs, fvh = -fv * hs;
-                    px = fma(fhh, qx, px);
-                    py = fma(fhh, qy, py);
-                    pz = fma(fvh, qz, pz);
+                    if constexpr (C::is_static) {
+                        double fh, fv;
+                        gradient_factors<C, STAGED, NFWT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
+                        const double fhh = -fh * hs, fvh = -fv * hs;
+                        px = fma(fhh, qx, px);
+                        py = fma(fhh, qy, py);
+                        pz = fma(fvh, qz, pz);
+                    } else {
+                        double g0, g1, g2;
+                        gradient<C, false, false>(P, qx, qy, qz, g0, g1, g2);
+                        px = fma(-g0, hs, px);
+                        py = fma(-g1, hs, py);
+                        pz = fma(-g2, hs, pz);
+                    }
                 }
             }
             tprev = fma((double)m, h, tprev);
@@ -629,10 +637,17 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
             if (cnt > 0) {  // the step that contains (at least) one save time
                 const double tnext = tprev + h;
                 const double nqx = fma(px, hs, qx), nqy = fma(py, hs, qy), nqz = fma(pz, hs, qz);
-                double fh, fv;
-                gradient_factors<C, STAGED, NFWT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
-                const double fhh = -fh * hs, fvh = -fv * hs;
-                const double npx = fma(fhh, nqx, px), npy = fma(fhh, nqy, py), npz = fma(fvh, nqz, pz);
+                double npx, npy, npz;
+                if constexpr (C::is_static) {
+                    double fh, fv;
+                    gradient_factors<C, STAGED, NFWT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
+                    const double fhh = -fh * hs, fvh = -fv * hs;
+                    npx = fma(fhh, nqx, px); npy = fma(fhh, nqy, py); npz = fma(fvh, nqz, pz);
+                } else {
+                    double g0, g1, g2;
+                    gradient<C, false, false>(P, nqx, nqy, nqz, g0, g1, g2);
+                    npx = fma(-g0, hs, px); npy = fma(-g1, hs, py); npz = fma(-g2, hs, pz);
+                }
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
                     const double th = (tsave - tprev) / (tnext - tprev);
                     qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
@@ -1340,7 +1355,8 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     if (N == 0) return 0;
     FixedArgs a;
     FixedSeg sg;
-    bool seg_ok = GX_FIXED_SEG && GX_FUSED_UPDATE && !general_kernel && scheme == GX_SCHEME_SEMI_IMPLICIT_EULER && model != MODEL_GENERIC;
+    bool seg_ok = GX_FIXED_SEG && GX_FUSED_UPDATE && !general_kernel && scheme == GX_SCHEME_SEMI_IMPLICIT_EULER &&
+                  (model != MODEL_GENERIC || D.td.n == 0);
     a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p; a.status = status;
     a.N = N; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
@@ -1360,9 +1376,13 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
             if (fwd) k_integrate_fixed_seg<CountsMW2022, true><<<grid, block, 0, s>>>(D, a, sg);
             else k_integrate_fixed_seg<CountsMW2022, false><<<grid, block, 0, s>>>(D, a, sg);
             break;
-        default:
+        case MODEL_BOVY:
             if (fwd) k_integrate_fixed_seg<CountsBovy, true><<<grid, block, 0, s>>>(D, a, sg);
             else k_integrate_fixed_seg<CountsBovy, false><<<grid, block, 0, s>>>(D, a, sg);
+            break;
+        default:  // runtime composite, no time-dependent parameter
+            if (fwd) k_integrate_fixed_seg<CountsRuntime, true><<<grid, block, 0, s>>>(D, a, sg);
+            else k_integrate_fixed_seg<CountsRuntime, false><<<grid, block, 0, s>>>(D, a, sg);
             break;
         }
     } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {

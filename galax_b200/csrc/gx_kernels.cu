@@ -211,6 +211,12 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
     default: { using C = CountsRuntime; CALL; } break;          \
     }
 
+// A runtime composite of the four basic kinds with constant parameters: the integrators run it through CountsBasic.
+static inline bool is_basic_composite(const DevPot &D, Model model) {
+    return model == MODEL_GENERIC && D.td.n == 0 &&
+           D.n_log + D.n_iso + D.n_satoh + D.n_rad + D.n_harm + D.n_henon == 0;
+}
+
 static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : GX_ERR_CUDA; }
 
 // ================================================================================================
@@ -767,7 +773,7 @@ __device__ __noinline__ void accel_call_timed(double t, double x, double y, doub
 }
 template <class C>
 __device__ __forceinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az, double t) {
-    if constexpr (C::is_static) accel_call_static<C>(x, y, z, ax, ay, az);
+    if constexpr (C::is_static || C::basic_only) accel_call_static<C>(x, y, z, ax, ay, az);
     else accel_call_timed<C>(t, x, y, z, ax, ay, az);
 }
 
@@ -1381,8 +1387,13 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
             else k_integrate_fixed_seg<CountsBovy, false><<<grid, block, 0, s>>>(D, a, sg);
             break;
         default:  // runtime composite, no time-dependent parameter
-            if (fwd) k_integrate_fixed_seg<CountsRuntime, true><<<grid, block, 0, s>>>(D, a, sg);
-            else k_integrate_fixed_seg<CountsRuntime, false><<<grid, block, 0, s>>>(D, a, sg);
+            if (is_basic_composite(D, model)) {
+                if (fwd) k_integrate_fixed_seg<CountsBasic, true><<<grid, block, 0, s>>>(D, a, sg);
+                else k_integrate_fixed_seg<CountsBasic, false><<<grid, block, 0, s>>>(D, a, sg);
+            } else {
+                if (fwd) k_integrate_fixed_seg<CountsRuntime, true><<<grid, block, 0, s>>>(D, a, sg);
+                else k_integrate_fixed_seg<CountsRuntime, false><<<grid, block, 0, s>>>(D, a, sg);
+            }
             break;
         }
     } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
@@ -1477,7 +1488,8 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
 #if GX_DP8_CONST_POT
     if ((rc = stage_const_pot(D, s)) != 0) return rc;
 #endif
-    GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
+    if (is_basic_composite(D, model)) GX_LAUNCH_DP8(CountsBasic);
+    else GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
 #undef GX_LAUNCH_DP8
     return cuda_rc(cudaGetLastError());
 }

@@ -255,23 +255,30 @@ __device__ __forceinline__ void rad_profile(const DevRad &c, double m2, double &
 
 // Static component counts let the compiler unroll and schedule the whole evaluation as one block of
 // straight-line code; Runtime (-1) is the generic fallback for arbitrary composites of the four kinds.
-template <int NMN, int NH, int NNFW, int NPLC, bool MN_SHARED_B = false>
+template <int NMN, int NH, int NNFW, int NPLC, bool MN_SHARED_B = false, bool BASIC = false>
 struct Counts {
     static constexpr bool is_static = (NMN >= 0);
+    // BASIC (runtime counts only): a composite of the four basic kinds with constant parameters -- the loops over the
+    // further kinds and the time-dependent branch are compiled out (the full runtime kernel is 85 KB of SASS against a
+    // 32 KB instruction cache).
+    static constexpr bool basic_only = BASIC;
     // all Miyamoto-Nagai terms have the same b (the three disks of an MN3 model, mn3.py:121-130): sqrt(z^2 + b^2)
     // is evaluated once.  Same bits as evaluating it per term; the host checks the equality before dispatching.
     static constexpr bool mn_shared_b = MN_SHARED_B;
     static constexpr int kMN = is_static ? NMN : MAX_MN, kH = is_static ? NH : MAX_HERN,
                          kNFW = is_static ? NNFW : MAX_NFW, kPLC = is_static ? NPLC : MAX_PLC;
     // the three specialised Milky-Way models contain none of the further kinds; the runtime path loops over them
-    static constexpr int kLOG = is_static ? 0 : MAX_LOG, kISO = is_static ? 0 : MAX_ISO, kSAT = is_static ? 0 : MAX_SATOH;
-    static constexpr int kRAD = is_static ? 0 : MAX_RAD, kHARM = is_static ? 0 : MAX_HARM, kHENON = is_static ? 0 : MAX_HENON;
+    static constexpr int kLOG = (is_static || BASIC) ? 0 : MAX_LOG, kISO = (is_static || BASIC) ? 0 : MAX_ISO,
+                         kSAT = (is_static || BASIC) ? 0 : MAX_SATOH;
+    static constexpr int kRAD = (is_static || BASIC) ? 0 : MAX_RAD, kHARM = (is_static || BASIC) ? 0 : MAX_HARM,
+                         kHENON = (is_static || BASIC) ? 0 : MAX_HENON;
     __device__ __forceinline__ static int mn(const DevPot &P) { return is_static ? NMN : P.n_mn; }
     __device__ __forceinline__ static int hern(const DevPot &P) { return is_static ? NH : P.n_hern; }
     __device__ __forceinline__ static int nfw(const DevPot &P) { return is_static ? NNFW : P.n_nfw; }
     __device__ __forceinline__ static int plc(const DevPot &P) { return is_static ? NPLC : P.n_plc; }
 };
 using CountsRuntime = Counts<-1, -1, -1, -1>;
+using CountsBasic = Counts<-1, -1, -1, -1, false, true>;  // runtime counts of MN / Hernquist / NFW / PowerLawCutoff only
 using CountsMW = Counts<1, 2, 1, 0>;      // MilkyWayPotential:      MN disk, NFW halo, 2 Hernquist
 using CountsMW2022 = Counts<3, 2, 1, 0, true>;  // MilkyWayPotential2022:  MN3 disk (one b), NFW halo, 2 Hernquist
 using CountsBovy = Counts<1, 0, 1, 1>;    // BovyMWPotential2014:    MN disk, PLC bulge, NFW halo
@@ -562,7 +569,7 @@ __device__ __noinline__ void gradient_td(const DevTD &R, double t, double x, dou
 template <class C, bool PLC_SMEM = false, bool NFW_TAB = false>
 __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
                                          double &gz_, double t = 0.0, unsigned nfw_base = 0) {
-    if (!C::is_static && P.td.n > 0) {  // time-dependent composite (runtime path only)
+    if (!C::is_static && !C::basic_only && P.td.n > 0) {  // time-dependent composite (runtime path only)
         gradient_td(P.td, t, x, y, z, gx_, gy_, gz_);
         return;
     }

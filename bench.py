@@ -109,7 +109,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "galax/JAX/diffrax are not installable offline; 'port' = oracle/galax_oracle.c (plain C, OpenMP)",
     }  # fmt: skip
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -173,9 +173,6 @@ def run_gpu(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set
-        # in the environment) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()  # fails loudly if libgalax_b200.so is missing
     pot = gp.MilkyWayPotential()
@@ -407,12 +404,32 @@ def run_gpu(args) -> None:
         "energy_drift": energy, "fp64_peak_tflops_measured": dfma_peak,
         "fp64_peak_tflops_measured_3reg_operands": dfma_peak_3reg,
     }  # fmt: skip
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line.  Libraries write banners there (NCCL prints "NCCL version ..." on the first
+    # communicator when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the
+    # duration of the run and the line goes to a saved copy of the original descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

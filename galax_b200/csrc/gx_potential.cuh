@@ -35,7 +35,7 @@ constexpr double TINY = 2.2250738585072014e-308;
 
 struct DevMN { double GM, a, b2, ab2; };             // ab2 = a*b^2 (Hessian)
 struct DevHern { double GM, c; };
-struct DevNFW { double GM, rs, inv_rs, GM_inv_rs, GM_rs3, pad_; };  // GM_rs3 = GM / rs^3 (force table)
+struct DevNFW { double GM, rs, inv_rs, GM_rs3, GM_inv_rs, pad_; };  // GM_rs3 = GM / rs^3 (force table); {inv_rs, GM_rs3} one 16-byte load
 // ga: a = 3/2 - alpha/2; ga2: a - 1/2; tail = Gamma(a2)/(rc Gamma(a)).
 // tab: optional device table of G(s) = P(a, s^2) / s^3, s = r/r_c, as degree-(PLC_DEG) polynomials on 2^PLC_SUB_BITS
 // intervals per octave of s in [2^PLC_E_LO, 2^PLC_E_HI) (built on the host in long double, see plc_table.h);
@@ -166,8 +166,9 @@ struct DevTD {
     double p[TD_MAX][TD_NP], dp[TD_MAX][TD_NP];
 };
 
-struct DevPot {
-    int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, n_rad, n_harm, n_henon;
+struct alignas(16) DevPot {
+    int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, n_rad, n_harm, n_henon, pad0_, pad1_;  // 48 B: the arrays below
+    // start 16-byte aligned, so {GM, a} of a disk or {GM, c} of a sphere are one 16-byte constant load
     DevMN mn[MAX_MN];
     DevHern hern[MAX_HERN];
     DevNFW nfw[MAX_NFW];

@@ -199,6 +199,8 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
             model = MODEL_MW2022;  // CountsMW2022 evaluates sqrt(z^2 + b^2) once: needs one b (an MN3 disk)
         if (D.n_mn == 1 && D.n_hern == 0 && D.n_nfw == 1 && D.n_plc == 1 && D.plc[0].tab != nullptr)
             model = MODEL_BOVY;  // (the integrators stage the bulge's force table in shared memory)
+        // ... and the NFW force table for MW / MW2022: without it (allocation failed) they run as runtime composites
+        if ((model == MODEL_MW || model == MODEL_MW2022) && use_device && D.nfw_tab == nullptr) model = MODEL_GENERIC;
     }
     return 0;
 }
@@ -754,27 +756,30 @@ __device__ __forceinline__ const DevPot &rhs_pot() {
     return *pot_smem<C>();
 #endif
 }
+// The callees return the acceleration BY VALUE (three doubles in registers): with reference parameters the results
+// went through the caller's local-memory frame (3 STL + 3 LDL + the generic-to-local address arithmetic per call).
+struct Acc3 { double x, y, z; };
 template <class C>
-__device__ __noinline__ void accel_call_static(double x, double y, double z, double &ax, double &ay, double &az) {
+__device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
     double g0, g1, g2;
-    unsigned nfw_base = 0;  // the kernel prologue staged the NFW force table (nfw_stage) iff the potential carries it
-    if constexpr (nfw_tab_ok<C>()) {
-        if (rhs_pot<C>().nfw_tab != nullptr) nfw_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
-    }
+    unsigned nfw_base = 0;  // the kernel prologue staged the NFW force table (nfw_stage)
+    if constexpr (nfw_tab_ok<C>()) nfw_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
     gradient<C, (C::is_static && C::kPLC > 0), nfw_tab_ok<C>()>(rhs_pot<C>(), x, y, z, g0, g1, g2, 0.0, nfw_base);
-    ax = -g0; ay = -g1; az = -g2;
+    return Acc3{-g0, -g1, -g2};
 }
 // runtime composites may be time dependent (LinearParameter): the callee also receives the physical time
 template <class C>
-__device__ __noinline__ void accel_call_timed(double t, double x, double y, double z, double &ax, double &ay, double &az) {
+__device__ __noinline__ Acc3 accel_call_timed(double t, double x, double y, double z) {
     double g0, g1, g2;
     gradient<C, false>(rhs_pot<C>(), x, y, z, g0, g1, g2, t);
-    ax = -g0; ay = -g1; az = -g2;
+    return Acc3{-g0, -g1, -g2};
 }
 template <class C>
 __device__ __forceinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az, double t) {
-    if constexpr (C::is_static || C::basic_only) accel_call_static<C>(x, y, z, ax, ay, az);
-    else accel_call_timed<C>(t, x, y, z, ax, ay, az);
+    Acc3 a;
+    if constexpr (C::is_static || C::basic_only) a = accel_call_static<C>(x, y, z);
+    else a = accel_call_timed<C>(t, x, y, z);
+    ax = a.x; ay = a.y; az = a.z;
 }
 
 // Hairer-Norsett-Wanner initial step as restated by diffrax (_select_initial_step); inv_order = 1 / error order.

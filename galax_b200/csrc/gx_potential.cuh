@@ -335,20 +335,18 @@ __device__ __forceinline__ double *nfw_smem() {
     __shared__ __align__(16) double t[NFW_NINT * PLC_STRIDE];
     return t;
 }
-// Call once per CTA, by all threads; returns the shared-window address of the table (0 = no table: closed form).
+// Call once per CTA, by all threads; returns the shared-window address of the table.
 template <class C, bool ON>
 __device__ __forceinline__ unsigned nfw_stage(const DevPot &P) {
     unsigned b = 0;
-    if constexpr (ON) {
-        if (P.nfw_tab != nullptr) {  // (uniform)
-            double *t = nfw_smem<C>();
-            const double2 *src2 = reinterpret_cast<const double2 *>(P.nfw_tab);
-            double2 *t2 = reinterpret_cast<double2 *>(t);
-            for (int idx = threadIdx.x; idx < NFW_NINT * PLC_STRIDE / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
-            __syncthreads();
-            b = (unsigned)__cvta_generic_to_shared(t);
-            asm volatile("" : "+r"(b));
-        }
+    if constexpr (ON) {  // (the host only picks a static model's integrator kernels when P.nfw_tab exists)
+        double *t = nfw_smem<C>();
+        const double2 *src2 = reinterpret_cast<const double2 *>(P.nfw_tab);
+        double2 *t2 = reinterpret_cast<double2 *>(t);
+        for (int idx = threadIdx.x; idx < NFW_NINT * PLC_STRIDE / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
+        __syncthreads();
+        b = (unsigned)__cvta_generic_to_shared(t);
+        asm volatile("" : "+r"(b));
     }
     return b;
 }
@@ -436,7 +434,7 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
             const double s = r * c.inv_rs;
             if constexpr (NFW_TAB) {
                 double F;
-                if (nfw_base != 0 && poly_table_eval<true, NFW_E_LO, NFW_NINT>(nullptr, s, F, nullptr, nfw_base)) {
+                if (poly_table_eval<true, NFW_E_LO, NFW_NINT>(nullptr, s, F, nullptr, nfw_base)) {
                     fs = fma(c.GM_rs3, F, fs);  // Phi'/r = (GM / rs^3) F(s)
                     continue;
                 }

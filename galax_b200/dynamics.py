@@ -257,7 +257,8 @@ def _pipeline_ok(torch, q0, p0, t0, ts, layout) -> bool:
     if isinstance(t0, torch.Tensor) and t0.is_cuda:
         return False
     n = q0.numel() // 3
-    if n * max(int(np.size(ts)), 1) * 48 > PIPELINE_MAX_OUTPUT_BYTES:  # (pinned host buffers for the whole result)
+    n_saves = int(ts.numel()) if isinstance(ts, torch.Tensor) else int(np.size(ts))
+    if n * max(n_saves, 1) * 48 > PIPELINE_MAX_OUTPUT_BYTES:  # (pinned host buffers for the whole result)
         return False
     return n >= PIPELINE_MIN_PARTICLES and q0.is_contiguous() and p0.is_contiguous()
 

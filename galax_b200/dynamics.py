@@ -239,7 +239,8 @@ def _period_order(q, p, t0v, t1, torch):
     return torch.argsort(cost, descending=True).to(torch.int32).contiguous()
 
 
-# Large batches that arrive in pinned host memory are processed in PIPELINE_CHUNKS slices on two side streams, so that
+# Large batches that arrive in host memory (pinned tensors or numpy arrays) are processed in PIPELINE_CHUNKS slices on two
+# side streams, so that
 # the host->device copy of slice k+1 and the device->host copy of slice k-1 overlap the kernel of slice k (particles
 # are independent; the kernels of neighbouring slices also fill each other's tail waves).  Same numbers as one launch.
 PIPELINE_MIN_PARTICLES = 1 << 19
@@ -248,19 +249,30 @@ PIPELINE_MAX_OUTPUT_BYTES = 8 << 30
 
 
 def _pipeline_ok(torch, q0, p0, t0, ts, layout) -> bool:
-    if layout != "NT3" or not (isinstance(q0, torch.Tensor) and isinstance(p0, torch.Tensor)):
+    if layout != "NT3":
         return False
-    if q0.is_cuda or p0.is_cuda or not (q0.is_pinned() and p0.is_pinned()):
-        return False
-    if q0.dtype != torch.float64 or p0.dtype != torch.float64 or q0.shape != p0.shape or q0.shape[-1] != 3:
-        return False
+    both_np = isinstance(q0, np.ndarray) and isinstance(p0, np.ndarray)
+    if both_np:
+        # numpy callers: pageable memory.  A pageable host->device copy blocks the host but not the kernels already
+        # queued, so slice k+1 is copied while slice k runs -- same pipeline, only the first slice's copy is exposed.
+        if q0.dtype != np.float64 or p0.dtype != np.float64 or q0.shape != p0.shape or q0.shape[-1] != 3:
+            return False
+        if not (q0.flags.c_contiguous and p0.flags.c_contiguous):
+            return False
+    else:
+        if not (isinstance(q0, torch.Tensor) and isinstance(p0, torch.Tensor)) or q0.is_cuda or p0.is_cuda:
+            return False
+        if q0.dtype != torch.float64 or p0.dtype != torch.float64 or q0.shape != p0.shape or q0.shape[-1] != 3:
+            return False
+        if not (q0.is_contiguous() and p0.is_contiguous()):
+            return False
     if isinstance(t0, torch.Tensor) and t0.is_cuda:
         return False
-    n = q0.numel() // 3
+    n = int(np.prod(q0.shape[:-1]))
     n_saves = int(ts.numel()) if isinstance(ts, torch.Tensor) else int(np.size(ts))
     if n * max(n_saves, 1) * 48 > PIPELINE_MAX_OUTPUT_BYTES:  # (pinned host buffers for the whole result)
         return False
-    return n >= PIPELINE_MIN_PARTICLES and q0.is_contiguous() and p0.is_contiguous()
+    return n >= PIPELINE_MIN_PARTICLES
 
 
 _PIPELINE_STREAMS: dict[int, list] = {}
@@ -278,6 +290,9 @@ def _pipeline_streams(torch, dev):
 def _integrate_pipelined(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort, throw, general_kernel):
     import torch
 
+    from_numpy = isinstance(q0, np.ndarray)
+    if from_numpy:
+        q0, p0 = torch.from_numpy(q0), torch.from_numpy(p0)  # (views, no copy)
     batch = tuple(q0.shape[:-1])
     qh, ph = q0.reshape(-1, 3), p0.reshape(-1, 3)
     N = qh.shape[0]
@@ -324,8 +339,10 @@ def _integrate_pipelined(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, ma
             code = int(status[i])
             why = {1: "max_steps reached", 2: "non-finite state"}.get(code, f"status {code}")
             raise RuntimeError(f"integration failed for particle {i} of {N}: {why} ({bad.shape[0]} failed in total)")
-    return (q_out.reshape(batch + (T, 3)), p_out.reshape(batch + (T, 3)), status.reshape(batch),
-            {k: v.reshape(batch) for k, v in stat_out.items()})
+    q_out, p_out = q_out.reshape(batch + (T, 3)), p_out.reshape(batch + (T, 3))
+    if from_numpy:  # numpy in -> numpy out, as the single-launch path does
+        q_out, p_out = q_out.numpy(), p_out.numpy()
+    return q_out, p_out, status.reshape(batch), {k: v.reshape(batch) for k, v in stat_out.items()}
 
 
 def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",

@@ -568,6 +568,8 @@ def test_pipelined_host_path_equals_single_launch():
     b = gd._integrate(pot, qd, pd, 0.0, 20.0, ts, **kw)
     assert not a[0].is_cuda and a[0].shape == (N, 2, 3)
     assert torch.equal(a[0], b[0].cpu()) and torch.equal(a[1], b[1].cpu()) and torch.equal(a[2], b[2].cpu())
+    c = gd._integrate(pot, q0, p0, 0.0, 20.0, ts, **kw)  # numpy (pageable) in -> numpy out, same pipeline
+    assert isinstance(c[0], np.ndarray) and np.array_equal(c[0], b[0].cpu().numpy()) and np.array_equal(c[1], b[1].cpu().numpy())
     kw = dict(solver=gd.Dopri8(), controller=gd.PIDController(1e-8, 1e-8), dt0=None, max_steps=4096)
     t0 = np.linspace(0.0, 5.0, N)  # per-particle start times are sliced with the particles
     a = gd._integrate(pot, qp, pp, t0, 20.0, ts, **kw)

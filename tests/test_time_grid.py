@@ -98,9 +98,9 @@ def test_random_grids_and_fallback():
     assert np.array_equal(np.repeat(np.array(h), np.array(cnt, dtype=np.int64)), np.diff(np.array(ts)))
 
 
-def test_pipeline_gate_is_off_for_host_arrays_that_are_not_pinned_tensors():
-    """dynamics._pipeline_ok: only pinned float64 torch tensors above the size threshold take the chunked
-    copy/compute pipeline; everything else is one launch (decided without touching a device)."""
+def test_pipeline_gate():
+    """dynamics._pipeline_ok: large contiguous float64 host batches (numpy or torch) take the chunked copy/compute
+    pipeline; everything else is one launch (decided without touching a device)."""
     import torch
 
     import galax_b200.dynamics as gd
@@ -108,8 +108,11 @@ def test_pipeline_gate_is_off_for_host_arrays_that_are_not_pinned_tensors():
     n = gd.PIPELINE_MIN_PARTICLES
     q = torch.zeros((n, 3), dtype=torch.float64)
     ts = np.array([1.0])
-    assert not gd._pipeline_ok(torch, q.numpy(), q.numpy(), 0.0, ts, "NT3")      # numpy
-    assert not gd._pipeline_ok(torch, q, q, 0.0, ts, "NT3")                      # pageable tensor
+    assert gd._pipeline_ok(torch, q.numpy(), q.numpy(), 0.0, ts, "NT3")          # large numpy batch: pipelined
+    assert gd._pipeline_ok(torch, q, q, 0.0, ts, "NT3")                          # ... and host tensors, pinned or not
+    assert not gd._pipeline_ok(torch, q.numpy(), q.numpy()[::-1], 0.0, ts, "NT3")  # not contiguous
+    assert not gd._pipeline_ok(torch, q.numpy(), q, 0.0, ts, "NT3")              # mixed kinds
+    assert not gd._pipeline_ok(torch, q, q, 0.0, np.zeros(40_000), "NT3")        # result too large for pinned buffers
     assert not gd._pipeline_ok(torch, q[:10], q[:10], 0.0, ts, "NT3")            # small
     assert not gd._pipeline_ok(torch, q, q, 0.0, ts, "T3N")                      # layout that cannot be sliced by particle
     assert not gd._pipeline_ok(torch, q.float(), q.float(), 0.0, ts, "NT3")      # dtype

@@ -121,7 +121,9 @@ int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int6
  *       .solve(HamiltonianField(pot), (q0, p0), t0, t1, dt0=dt0, max_steps=..., saveat=ts)
  * (dynamics/_src/orbit/field_hamiltonian.py:256-301, dynamics/_src/orbit/solver.py:774-803 -> diffrax.diffeqsolve).
  * q0,p0: [N,3]; ts: [T] device array of save times inside [t0,t1] (ascending in the direction of integration);
- * q,p: saved states in `layout`; status: [N] int32 (may be NULL); max_steps < 0 = unbounded. */
+ * q,p: saved states in `layout`; status: [N] int32 (may be NULL); max_steps < 0 = unbounded.
+ * SemiImplicitEuler with constant parameters runs on the run-length form of the time grid (gx_fixed_time_grid below):
+ * same results bit for bit as the step-by-step kernel, which GX_SCHEME_GENERAL_KERNEL selects. */
 int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0, double t1,
                        double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
                        double *q, double *p, int32_t *status, void *stream);

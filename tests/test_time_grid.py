@@ -116,3 +116,22 @@ def test_pipeline_gate():
     assert not gd._pipeline_ok(torch, q[:10], q[:10], 0.0, ts, "NT3")            # small
     assert not gd._pipeline_ok(torch, q, q, 0.0, ts, "T3N")                      # layout that cannot be sliced by particle
     assert not gd._pipeline_ok(torch, q.float(), q.float(), 0.0, ts, "NT3")      # dtype
+
+
+def test_trip_count_agrees_with_the_oracle_integrator():
+    """The library's host walk and the C oracle's integrator (oracle/galax_oracle.c) take the same number of steps on
+    the same grids, max_steps included."""
+    from oracle import cref
+    from oracle import potentials as op
+
+    pot = op.milky_way_potential()
+    q0, p0 = np.array([[8.0, 0.0, 0.5]]), np.array([[0.0, 0.2, 0.01]])
+    for t0, t1, dt0 in CASES:
+        if t0 == t1 or abs((t1 - t0) / dt0) > 30_000:
+            continue
+        _, _, st, n = cref.integrate_fixed(pot, q0, p0, t0, t1, dt0, [t1])
+        n_lib, hit, *_ = runs(t0, t1, dt0)
+        assert int(n[0]) == n_lib and not hit and st[0] == 0, (t0, t1, dt0)
+    _, _, st, n = cref.integrate_fixed(pot, q0, p0, 0.0, 100.0, 0.1, [100.0], max_steps=77)
+    n_lib, hit, *_ = runs(0.0, 100.0, 0.1, max_steps=77)
+    assert int(n[0]) == n_lib == 77 and hit and st[0] == 1

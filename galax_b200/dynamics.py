@@ -196,9 +196,19 @@ class HamiltonianField:
             raise TypeError("HamiltonianField needs a galax_b200 potential")
         self.potential = potential
 
-    def __call__(self, t, q, p, args=None):
-        if args is not None:
-            raise NotImplementedError("field args are not supported")
+    def __call__(self, t, *xv):
+        """The reference's array-level call forms (field_hamiltonian.py:108-175): ``field(t, q, p[, None])``,
+        ``field(t, (q, p)[, None])`` and ``field(t, qp[, None])`` with ``qp`` of shape ``(*batch, 6)``."""
+        if xv and xv[-1] is None and len(xv) > 1:
+            xv = xv[:-1]  # args=None
+        if len(xv) == 2:
+            q, p = xv
+        elif len(xv) == 1 and isinstance(xv[0], (tuple, list)) and len(xv[0]) == 2:
+            q, p = xv[0]
+        elif len(xv) == 1 and hasattr(xv[0], "shape") and xv[0].shape[-1] == 6:
+            q, p = xv[0][..., :3], xv[0][..., 3:]
+        else:
+            raise NotImplementedError("HamiltonianField: expected (t, q, p), (t, (q, p)) or (t, qp[..., 6]); field args are not supported")
         return p, self.potential.acceleration(q, t)
 
 

@@ -579,3 +579,15 @@ def test_pipelined_host_path_equals_single_launch():
     with pytest.raises(RuntimeError, match="max_steps"):
         gd._integrate(pot, qp, pp, 0.0, 20.0, ts, solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(),
                       dt0=0.1, max_steps=5)
+
+
+def test_hamiltonian_field_call_forms_reference_doctest():
+    """HamiltonianField.__call__ (a-10): the reference's doctest values (orbit/field_hamiltonian.py:108-133) through its
+    three array-level call forms."""
+    field = gd.HamiltonianField(gp.KeplerPotential(m_tot=1e11))
+    x, v = np.array([8.0, 0, 0]), np.array([0, 0.22499668, 0])
+    forms = [field(0, x, v, None), field(0, x, v), field(0, (x, v)), field(0, (x, v), None), field(0, np.concatenate([x, v]))]
+    for dq, dp in forms:
+        assert np.array_equal(dq, v) and np.allclose(dp, [-0.00702891, 0.0, 0.0], rtol=0, atol=5e-9)
+    with pytest.raises(NotImplementedError):
+        field(0, x, v, {"extra": 1})

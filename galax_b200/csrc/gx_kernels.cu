@@ -1708,6 +1708,32 @@ int gx_fixed_time_grid(double t0, double t1, double dt0, int64_t max_steps, int6
     return 0;
 }
 
+int gx_force_table(int32_t which, double a, double *coef, int64_t capacity, int32_t *n_intervals, int32_t *degree,
+                   int32_t *e_lo, int32_t *sub_bits, double *max_rel_err) {
+    // host only: the same long-double Chebyshev fits nfw_table() / plc_table_for(a) upload to the device
+    if (which != 0 && which != 1) return GX_ERR_BADARG;
+    if (which == 1 && !(a > 0.0)) return GX_ERR_BADARG;
+    const int nint = which == 0 ? NFW_NINT : PLC_NINT, lo = which == 0 ? NFW_E_LO : PLC_E_LO;
+    if (n_intervals) *n_intervals = nint;
+    if (degree) *degree = PLC_DEG;
+    if (e_lo) *e_lo = lo;
+    if (sub_bits) *sub_bits = PLC_SUB_BITS;
+    if (!coef && !max_rel_err) return 0;
+    if (coef && capacity < (int64_t)nint * (PLC_DEG + 1)) return GX_ERR_BADARG;
+    std::vector<double> row(PLC_DEG + 1);
+    double worst = 0.0;
+    for (int j = 0; j < nint; ++j) {
+        const int e = lo + j / PLC_SUB, sub = j % PLC_SUB;
+        const long double base = ldexpl(1.0L, e);
+        const long double s0 = base * (1.0L + sub / (long double)PLC_SUB), s1 = base * (1.0L + (sub + 1) / (long double)PLC_SUB);
+        if (which == 0) fit_interval(nfw_F_ld, s0, s1, row.data(), &worst);
+        else plc_fit_interval((long double)a, s0, s1, row.data(), &worst);
+        if (coef) memcpy(coef + (size_t)j * (PLC_DEG + 1), row.data(), sizeof(double) * (PLC_DEG + 1));
+    }
+    if (max_rel_err) *max_rel_err = worst;
+    return 0;
+}
+
 int gx_debug_math(int32_t op, double a, const double *x, int64_t N, double *out, void *stream) {
     if (N < 0 || (N > 0 && (!x || !out))) return GX_ERR_BADARG;
     if (N == 0) return 0;

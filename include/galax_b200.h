@@ -228,6 +228,13 @@ int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void
  * normals `jr.normal(k_j, ())` on `jr.split(subkey, 4)`.  The key chain is inherently sequential and runs on the host
  * (integer arithmetic, ~50 ns per link); the 4 M normals are computed on the device.  draws: device [4][M]. */
 int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *stream);
+/* Host only (no CUDA call): the piecewise-polynomial force tables the integrators stage in shared memory, as fitted on
+ * the host -- which = 0: NFW F(s) = (ln(1+s) - s/(1+s)) / s^3; which = 1: PowerLawCutoff G(s) = P(a, s^2) / s^3 for
+ * the exponent a = 3/2 - alpha/2.  Rows of (degree + 1) monomial coefficients in t in [-1, 1) per interval,
+ * 2^sub_bits intervals per octave of s starting at 2^e_lo; max_rel_err is the fit's own check against the long-double
+ * function.  coef may be NULL (only the layout / the error are wanted). */
+int gx_force_table(int32_t which, double a, double *coef, int64_t capacity, int32_t *n_intervals, int32_t *degree,
+                   int32_t *e_lo, int32_t *sub_bits, double *max_rel_err);
 /* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x), 4 NFW shape ln(1+s) - s/(1+s),
  * 5 NFW force table F(s) = shape / s^3, 6 / 7 PowerLawCutoff table G(s) = P(a, s^2) / s^3 and dG/ds (NaN outside the
  * tabulated range) */

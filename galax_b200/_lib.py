@@ -12,16 +12,17 @@ import os
 import shutil
 import subprocess
 from pathlib import Path
+from typing import Sequence
 
 _PKG = Path(__file__).resolve().parent
 _SRC = _PKG / "csrc"
 LIB_PATH = Path(os.environ.get("GALAX_B200_LIB", _PKG / "libgalax_b200.so"))  # override: A/B builds only
 HEADER = _PKG.parent / "include" / "galax_b200.h"
 
-NVCC_FLAGS = [
+NVCC_COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "20091",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]  # fmt: skip
 
 GX_MAX_COMPONENTS = 14
@@ -32,6 +33,7 @@ PHI, GRAD, ACC, HESS = 1, 2, 4, 8
 OK, MAX_STEPS_REACHED, NONFINITE = 0, 1, 2
 SCHEME_SIE, SCHEME_LEAPFROG_MIDPOINT = 0, 1
 SCHEME_GENERAL_KERNEL = 0x100
+SCHEME_STRICT = 0x200
 LAYOUT_NT3, LAYOUT_T3N = 0, 1
 DF_FARDAL15, DF_CHEN24 = 0, 1
 DENSE_RECORD_DOUBLES = 51
@@ -61,37 +63,53 @@ class GalaxB200Error(RuntimeError):
     pass
 
 
-def sources() -> list[Path]:
-    return [_SRC / "gx_kernels.cu"]
+def sources() -> list[tuple[Path, list[str]]]:
+    """Translation units and their extra flags.  ``gx_strict.cu`` (the reference-order kernels) is compiled without
+    floating-point contraction: its arithmetic must be reproducible bit for bit by a plain C program."""
+    return [(_SRC / "gx_kernels.cu", []), (_SRC / "gx_strict.cu", ["-fmad=false"])]
 
 
 def _stale() -> bool:
     if not LIB_PATH.exists():
         return True
     m = LIB_PATH.stat().st_mtime
-    deps = list(_SRC.glob("*.cu")) + list(_SRC.glob("*.cuh")) + list(_SRC.glob("*.h")) + [HEADER]
+    deps = list(_SRC.glob("*.cu")) + list(_SRC.glob("*.cuh")) + list(_SRC.glob("*.h")) + list(HEADER.parent.glob("*.h"))
     return any(d.stat().st_mtime > m for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines: Sequence[str] = (), out: Path | None = None) -> Path:
     """Compile ``libgalax_b200.so`` for sm_100a if it is missing or older than its sources."""
-    if not force and not _stale():
+    target = Path(out) if out is not None else LIB_PATH
+    if out is None and not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(nvcc).exists():
         raise GalaxB200Error("nvcc not found: cannot build libgalax_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(s) for s in sources()]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
     env.pop("CC", None)  # the image's $CC points at a gcc nvcc cannot drive
     env.pop("CXX", None)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    objdir = _PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    jobs = []
+    for src, extra in sources():
+        obj = objdir / (target.stem + "_" + src.stem + ".o")
+        cmd = [nvcc, *NVCC_COMPILE_FLAGS, *extra, *defines, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        jobs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)))
+    objs = []
+    for obj, proc in jobs:
+        out_, err_ = proc.communicate()
+        if proc.returncode != 0:
+            raise GalaxB200Error(f"nvcc failed:\n{out_}\n{err_}")
+        if verbose:
+            print(err_)
+        objs.append(str(obj))
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(target), *objs],
+                         capture_output=True, text=True, env=env)
     if res.returncode != 0:
-        raise GalaxB200Error(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
-    return LIB_PATH
+        raise GalaxB200Error(f"nvcc link failed:\n{res.stdout}\n{res.stderr}")
+    return target
 
 
 _lib = None

@@ -1285,6 +1285,11 @@ __global__ void k_debug_math(int op, const GammaTab *gt, const double *tab, cons
 // ================================================================================================
 using namespace gx;
 
+// gx_strict.cu (compiled with -fmad=false): the reference-order kernels behind GX_SCHEME_STRICT
+int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
+                              double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
+                              int32_t layout, double *q, double *p, int32_t *status, void *stream);
+
 extern "C" {
 
 int gx_version(void) { return GX_VERSION; }
@@ -1358,12 +1363,16 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     if (rc) return rc;
     if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
     const bool general_kernel = (scheme & GX_SCHEME_GENERAL_KERNEL) != 0;
-    scheme &= ~GX_SCHEME_GENERAL_KERNEL;
+    const bool strict = (scheme & GX_SCHEME_STRICT) != 0;
+    scheme &= ~(GX_SCHEME_GENERAL_KERNEL | GX_SCHEME_STRICT);
     if (scheme != GX_SCHEME_SEMI_IMPLICIT_EULER && scheme != GX_SCHEME_LEAPFROG_MIDPOINT) return GX_ERR_BADARG;
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
     if (t1 != t0 && !(dt0 * dir > 0.0)) return GX_ERR_BADARG;  // ConstantStepSize needs dt0 in the direction of t1
     if (N == 0) return 0;
+    if (strict)
+        return gx_strict_integrate_fixed(pot, q0, p0, N, t0, t1, dt0, ts, T, scheme, max_steps, layout, q, p, status,
+                                         stream);
     FixedArgs a;
     FixedSeg sg;
     bool seg_ok = GX_FIXED_SEG && GX_FUSED_UPDATE && !general_kernel && scheme == GX_SCHEME_SEMI_IMPLICIT_EULER &&

@@ -41,12 +41,20 @@ from .potential import AbstractPotential, _to_device, _to_host_many
 
 @dataclasses.dataclass(frozen=True)
 class SemiImplicitEuler:
-    """diffrax.SemiImplicitEuler: q1 = q0 + p0 h ; p1 = p0 - grad Phi(q1) h.  The reference's "leapfrog"."""
+    """diffrax.SemiImplicitEuler: q1 = q0 + p0 h ; p1 = p0 - grad Phi(q1) h.  The reference's "leapfrog".
+
+    ``strict=True`` (not a diffrax field) selects the reference-order kernel (``GX_SCHEME_STRICT``): the reference's
+    arithmetic operation by operation -- components summed in composite order, IEEE division / square root, no FMA
+    contraction, portable log1p -- reproducible bit for bit on a CPU, several times slower."""
+
+    strict: bool = False
 
 
 @dataclasses.dataclass(frozen=True)
 class LeapfrogMidpoint:
-    """diffrax.LeapfrogMidpoint: y_{n+1} = y_{n-1} + f(y_n) (t_{n+1} - t_{n-1})."""
+    """diffrax.LeapfrogMidpoint: y_{n+1} = y_{n-1} + f(y_n) (t_{n+1} - t_{n-1}).  ``strict``: see SemiImplicitEuler."""
+
+    strict: bool = False
 
 
 @dataclasses.dataclass(frozen=True)
@@ -410,6 +418,8 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             scheme = _lib.SCHEME_SIE if isinstance(solver, SemiImplicitEuler) else _lib.SCHEME_LEAPFROG_MIDPOINT
             if general_kernel:  # testing aid: the per-step time arithmetic kernel instead of the run-length one
                 scheme |= _lib.SCHEME_GENERAL_KERNEL
+            if solver.strict:
+                scheme |= _lib.SCHEME_STRICT
             rc = L.gx_integrate_fixed(C.byref(P), dq.data_ptr(), dp.data_ptr(), N, t0s, t1, float(dt0),
                                       dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
                                       status.data_ptr(), stream)  # fmt: skip

@@ -107,12 +107,20 @@ class AbstractPotential:
         P = _lib.GxPotential()
         P.n = len(comps)
         P.G = float(self.G)
+        groups = self._flat_groups()
         for i, (kind, params) in enumerate(comps):
             P.c[i].kind = kind
+            P.c[i].reserved = groups[i]
             for j, v in enumerate(params):
                 P.c[i].p[j] = float(v)
                 P.c[i].dp[j] = float(getattr(v, "rate", 0.0))
         return P
+
+    def _flat_groups(self) -> list[int]:
+        """Summation group of every flat component (``gx_component.reserved``): components that were ONE reference
+        component (the three Miyamoto-Nagai terms of an MN3 disk, a nested composite) share a non-zero id and the
+        reference-order kernels (``GX_SCHEME_STRICT``) sum them first, as base_multi.py:48-55 does.  0 = its own."""
+        return [0] * len(self._flat_components())
 
     @property
     def is_time_dependent(self) -> bool:
@@ -619,6 +627,18 @@ class CompositePotential(AbstractPotential):
         out = []
         for v in self._data.values():
             out.extend(v._flat_components())
+        return out
+
+    def _flat_groups(self):
+        out: list[int] = []
+        for gid, v in enumerate(self._data.values(), start=1):
+            n = len(v._flat_components())
+            if n > 1 and isinstance(v, CompositePotential) and len(v) > 1 and any(
+                len(c._flat_components()) > 1 for c in v.values()
+            ):
+                out.extend([-1] * n)  # groups inside a group: one level is all gx_component.reserved can express
+            else:
+                out.extend([gid if n > 1 else 0] * n)
         return out
 
 

@@ -53,7 +53,9 @@ extern "C" {
  * gx_energy_angmom return GX_ERR_UNSUPPORTED for them. */
 typedef struct {
     int32_t kind;
-    int32_t reserved;
+    int32_t reserved; /* summation group: consecutive components with the same non-zero value were ONE reference
+                         component (the three Miyamoto-Nagai terms of an MN3 disk) and GX_SCHEME_STRICT sums them first,
+                         as the reference does; 0 = a component of its own.  Ignored by the default kernels. */
     double p[8];
     double dp[8];
 } gx_component;
@@ -89,6 +91,13 @@ typedef struct {
 /* or-ed into `scheme`: use the general fixed-step kernel (time arithmetic every step) where the run-length kernel
  * would be chosen.  Results are bit-identical; for tests and A/B timing. */
 #define GX_SCHEME_GENERAL_KERNEL 0x100
+/* or-ed into `scheme`: reference-order arithmetic (galax_b200/csrc/gx_strict.cu) -- every component evaluated and
+ * summed in composite order as potential/_src/base_multi.py:48-55 does (gx_component.reserved = summation group, see
+ * below), IEEE division / square root, no FMA contraction, portable fdlibm log1p / exp / log
+ * (include/gx_portable_math.h), the update as a multiply and an add.  Bit for bit what a plain C program computes on
+ * an IEEE-754 CPU; several times slower than the default kernels.  Static composites of MIYAMOTO_NAGAI, HERNQUIST,
+ * NFW and POWERLAWCUTOFF components only (GX_ERR_UNSUPPORTED otherwise). */
+#define GX_SCHEME_STRICT 0x200
 
 /* output layout of saved states, element (particle n, save k, component c) */
 #define GX_LAYOUT_NT3 0 /* [N,T,3]  the reference's (*batch, T, 3), orbit/register_dfx.py:80-82 */

@@ -52,7 +52,8 @@ class _Pid(C.Structure):
 def build(force: bool = False) -> Path:
     so = _HERE / "libgalax_oracle.so"
     src = _HERE / "galax_oracle.c"
-    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+    hdr = _HERE.parent / "include" / "gx_portable_math.h"
+    if force or not so.exists() or so.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return so
 

@@ -49,6 +49,16 @@
 
 #define OC_TINY 2.2250738585072014e-308
 
+/* log, exp and log1p on the gradient path are the portable fdlibm forms of include/gx_portable_math.h (a public
+ * header of the library, not product kernels): glibc's and CUDA's own functions are each < 1 ulp but round
+ * differently, and the strict-parity test (tests/test_gpu_strict.py) compares the reference-order GPU kernel with this
+ * file BIT FOR BIT.  Accuracy of the portable forms against 50-digit mpmath: tests/test_portable_math.py. */
+#include "../include/gx_portable_math.h"
+void oc_pm_eval(int op, int64_t n, const double *x, double *out) {
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = (op == 0) ? gx_pm_log(x[i]) : (op == 1) ? gx_pm_exp(x[i]) : gx_pm_log1p(x[i]);
+}
+
 typedef struct {
     int kind;
     int group; /* components with equal group id are summed first (MN3 disk) */
@@ -76,7 +86,7 @@ static double oc_gammainc_P(double a, double x) {
             sum += del;
             if (fabs(del) < fabs(sum) * 1e-17) break;
         }
-        return sum * exp(-x + a * log(x) - lg);
+        return sum * gx_pm_exp(-x + a * gx_pm_log(x) - lg);
     } else {
         const double FPMIN = 1e-300;
         double b = x + 1.0 - a, c = 1.0 / FPMIN, d = 1.0 / b, h = d;
@@ -92,7 +102,7 @@ static double oc_gammainc_P(double a, double x) {
             h *= del;
             if (fabs(del - 1.0) < 1e-17) break;
         }
-        return 1.0 - exp(-x + a * log(x) - lg) * h;
+        return 1.0 - gx_pm_exp(-x + a * gx_pm_log(x) - lg) * h;
     }
 }
 
@@ -110,7 +120,7 @@ static double nfw_menc_shape(double s) {
         }
         return ser * s * s;
     }
-    return log1p(s) - s / (1.0 + s);
+    return gx_pm_log1p(s) - s / (1.0 + s);
 }
 
 static double comp_potential(double G, const oc_component *c, const double q[3]) {

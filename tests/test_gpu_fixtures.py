@@ -6,6 +6,7 @@ import pytest
 
 import galax_b200.dynamics as gd
 import galax_b200.potential as gp
+from conftest import one_ulp_sensitivity, rel_dev
 
 pytestmark = pytest.mark.gpu
 FX = np.load(Path(__file__).parent / "golden" / "oracle_fixtures.npz")
@@ -26,14 +27,19 @@ def test_potential_against_fixture(name):
 
 @pytest.mark.parametrize("name", list(MODELS))
 def test_fixed_step_against_fixture(name):
-    """64 orbits with pericentre-safe ICs (r0 >= 6 kpc), 10^4 SemiImplicitEuler steps, saves at 0 / 333.3 / 1000 Myr."""
+    """64 orbits, 10^4 SemiImplicitEuler steps, saves at 0 / 333.3 / 1000 Myr.  The reference-order kernel reproduces
+    the committed oracle output BIT FOR BIT; the fast kernel is within 1e-12, or 100 x the orbit's own one-ulp
+    sensitivity where that is larger (tests/test_gpu_strict.py explains the bound)."""
     pot = MODELS[name]()
+    q0, p0, ts = FX[f"sie_{name}_q0"], FX[f"sie_{name}_p0"], FX[f"sie_{name}_ts"]
+    ref = (FX[f"sie_{name}_q"], FX[f"sie_{name}_p"])
+    sens, strict = one_ulp_sensitivity(pot, q0, p0, 0.0, 1000.0, 0.1, saveat=ts)
+    assert np.array_equal(strict.ys[0], ref[0]) and np.array_equal(strict.ys[1], ref[1])
     solver = gd.OrbitSolver(solver=gd.SemiImplicitEuler(), stepsize_controller=gd.ConstantStepSize(), max_steps=None)
-    sol = solver.solve(pot, (FX[f"sie_{name}_q0"], FX[f"sie_{name}_p0"]), 0.0, 1000.0, saveat=FX[f"sie_{name}_ts"], dt0=0.1)
-    for got, ref in ((sol.ys[0], FX[f"sie_{name}_q"]), (sol.ys[1], FX[f"sie_{name}_p"])):
-        e = np.linalg.norm(got - ref, axis=-1) / np.linalg.norm(ref, axis=-1)
-        assert np.median(e[:, -1]) <= 1e-13 and np.mean(e[:, -1] <= 1e-12) >= 0.95 and e.max() <= 1e-9
-        assert np.array_equal(got[:, 0], ref[:, 0])
+    sol = solver.solve(pot, (q0, p0), 0.0, 1000.0, saveat=ts, dt0=0.1)
+    e = rel_dev(sol.ys, ref)
+    assert (e <= np.maximum(1e-12, 100.0 * sens)).all() and np.median(e) <= 1e-13
+    assert np.array_equal(sol.ys[0][:, 0], ref[0][:, 0])
 
 
 def test_dopri8_against_fixture():

@@ -10,7 +10,7 @@ import galax_b200.potential as gp
 from oracle import cref
 from oracle import potentials as op
 
-from conftest import synthetic_ics
+from conftest import one_ulp_sensitivity, rel_dev, synthetic_ics
 
 pytestmark = pytest.mark.gpu
 
@@ -39,28 +39,22 @@ def relerr_vec(a, b):
 
 @pytest.mark.parametrize("name", list(PAIRS))
 def test_sie_c1_parity(name):
-    """C1 shape: dt = 0.1 Myr over 1 Gyr = 10 000 steps; north_star tolerance 1e-12 relative on final q, p."""
+    """C1 shape: dt = 0.1 Myr over 1 Gyr = 10 000 steps; north_star tolerance 1e-12 relative on final q, p.
+
+    No orbit is excluded by hand.  The bar is 1e-12 for every particle except where the ORACLE's own arithmetic
+    (the reference-order kernel, bit-identical to it: tests/test_gpu_strict.py runs all 10^4 C1 particles) moves by more
+    than 1e-14 under a one-ulp change of that particle's initial condition; there the bar is 100 x that movement."""
     cls, ofun = PAIRS[name]
     pot, opot = cls(), ofun()
     q0, p0 = synthetic_ics(opot, 384, seed=1)
     sol = SIE.solve(pot, (q0, p0), 0.0, 1000.0, dt0=0.1)
     qr, pr, st, n = cref.integrate_fixed(opot, q0, p0, 0.0, 1000.0, 0.1, [1000.0])
     assert (n == 10000).all()
-    eq = np.linalg.norm(sol.ys[0][:, 0] - qr[:, 0], axis=1) / np.linalg.norm(qr[:, 0], axis=1)
-    ep = np.linalg.norm(sol.ys[1][:, 0] - pr[:, 0], axis=1) / np.linalg.norm(pr[:, 0], axis=1)
-    e = np.maximum(eq, ep)
-    # The state update is bit-identical to the oracle's (un-fused multiply-add); the only difference is the
-    # acceleration (~1e-15 relative: MUFU-seeded rsqrt/rcp vs libm).  How much that is amplified over 10^4
-    # steps depends on the orbit: measured on B200, median 3.5e-14, p99 7e-13, and every orbit whose
-    # pericentre stays outside 4 kpc is <= 1e-12 (99.6% of all orbits are); orbits that plunge through the 70 pc nucleus are scattered
-    # and can differ at 1e-8 in ANY two implementations (SURVEY.md section 7 "hard parts").
-    dense = SIE.solve(pot, (q0, p0), 0.0, 1000.0, saveat=np.linspace(0.0, 1000.0, 2001), dt0=0.1)
-    rmin = np.linalg.norm(dense.ys[0], axis=2).min(axis=1)
-    regular = rmin > 4.0
-    assert regular.mean() > 0.5
-    assert e[regular].max() <= 1e-12, e[regular].max()  # north_star bar, fixed step
-    assert np.mean(e <= 1e-12) >= 0.97 and np.median(e) <= 1e-13
-    assert e[rmin > 0.25].max() <= 1e-11 and e.max() <= 1e-5
+    sens, strict = one_ulp_sensitivity(pot, q0, p0, 0.0, 1000.0, 0.1)
+    assert np.array_equal(strict.ys[0], qr) and np.array_equal(strict.ys[1], pr)
+    e = rel_dev(sol.ys, (qr, pr))
+    assert (e <= np.maximum(1e-12, 100.0 * sens)).all(), (e / np.maximum(sens, 1e-17)).max()
+    assert np.median(e) <= min(1e-13, np.median(sens)) and np.mean(e <= 1e-12) >= np.mean(sens <= 1e-12) - 0.02
 
 
 def test_sie_saves_layouts_and_interpolation():

@@ -4,23 +4,31 @@
 One bench "step" = one pass of the hot path over one batch: every particle of the batch is integrated
 from t = 0 to 1 Gyr with dt = 0.1 Myr (10 000 SemiImplicitEuler steps, the reference's "leapfrog",
 SURVEY.md 8a-11) in MilkyWayPotential, final state saved.  The batch is C1's synthetic initial-condition
-distribution scaled up to fill one B200 (C1's own 10^4 particles occupy 2 warps per SM; its number is
-reported beside the headline as ``c1_exact``).  Weak scaling: every rank owns N_PER_GPU particles; the
-only collective is the all-gather of the final states.
+distribution scaled up to fill one B200 (C1's own 10^4 particles occupy 2 warps per SM; its numbers are
+reported beside the headline under ``extra.C1_exact``).  Weak scaling: every rank owns N_PER_GPU particles; the
+only collective is ONE all-gather of the packed (q, p) result per step, issued asynchronously so that it runs under
+the next step's kernel (galax_b200.distributed.ResultGather).
 
   python bench.py --gpus 1 --steps 5 --warmup 3
   python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 --steps 5 --warmup 3
-  python bench.py --impl reference     # the CPU restatement (oracle port) on the host cores
+  python bench.py --impl reference     # the reference's CPU path: galax on JAX-CPU if importable, else the C port
 
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  Nothing in the line is quoted from an earlier profile: the FP64 instruction counts,
+the FP64-pipe utilisation and the DRAM traffic of the headline kernel are measured in this run by an ``ncu``
+sub-invocation of one launch of the very library the bench loaded (``roofline.source``); where ncu cannot run, the
+counts fall back to a static count of the kernel's hot loop in the library's SASS and the line says so.
+``extra`` carries BASELINE.json's other configurations (C2, C3, C5 on rank 0; C4 strong-scaled over all ranks).
 """
 
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
+import re
+import shutil
 import subprocess
 import sys
 import threading
@@ -37,13 +45,16 @@ UNIT = "particle-steps/s"
 N_PER_GPU = 148 * 8192  # 1 212 416 particles: 64 CTAs of 128 threads per SM
 N_STEPS = 10_000  # dt0 = 0.1 Myr over 1 Gyr
 T1, DT0 = 1000.0, 0.1
-FLOP_PER_STEP = 280.0  # canonical weighted fp64 flop per MilkyWayPotential fixed step
-# FP64 thread-instructions the kernel really executes per particle-step, counted by ncu on this very launch
-# (profiles/ncu_k_integrate_fixed_r1f.txt: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on / (N x steps))
-NCU_FP64_INSTR_PER_STEP = {"dfma": 39.07, "dmul": 23.03, "dadd": 7.01}
-NCU_FP64_PIPE_ACTIVE_PCT = 82.9
+CANONICAL_FLOP_PER_STEP = 280.0  # SURVEY.md 8d weighted op count (div = sqrt = 18, log1p = 56): informational only
 CPU_SAMPLE_PER_CORE = 8192  # cpu_baseline leg: ~10 s of CPU work at ~9e6 particle-steps/s/core
 REF_ARM_SAMPLE_PER_CORE = 2048  # --impl reference: ~2.5 s per bench step
+HOT_KERNEL_SYMBOL = "k_integrate_fixed_segINS_6CountsILi1ELi2ELi1ELi0ELb0ELb0EEELb1E"  # <MilkyWayPotential, forward>
+NCU_METRICS = (
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__inst_executed.sum",
+    "smsp__inst_executed_pipe_fp64.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum",
+)  # fmt: skip
 
 
 def workload_config(n_gpus: int, n: int = N_PER_GPU) -> dict:
@@ -52,7 +63,7 @@ def workload_config(n_gpus: int, n: int = N_PER_GPU) -> dict:
         f"{n} particles per GPU, C1 synthetic ICs (r~U(4,20) kpc, |v|=v_c*U(0.6,1)), final state saved",
         "particles_per_gpu": n,
         "integrator_steps": N_STEPS,
-        "parallelism": f"particle-sharded x{n_gpus}, all-gather of final states",
+        "parallelism": f"particle-sharded x{n_gpus}, one asynchronous all-gather of the packed (q, p) result per step",
         "l2": "L2 flushed between timed iterations (256 MiB write)",
     }
 
@@ -73,9 +84,41 @@ def host_ics(n: int, seed: int):
 # --------------------------------------------------------------------------------------------- reference arm
 
 
+def _galax_reference_step(q: np.ndarray, p: np.ndarray):
+    """The reference itself (plan 1): galax on JAX-CPU, the call of
+    dynamics/_src/orbit/field_hamiltonian.py:282-290.  Returns a callable running one bench step, or raises
+    ImportError / any set-up error (the caller then falls back to the C port and says so)."""
+    ref = ROOT / "baseline" / "_ref"
+    if ref.is_dir() and str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    os.environ.setdefault("JAX_PLATFORMS", "cpu")
+    os.environ.setdefault("JAX_ENABLE_X64", "1")
+    import jax  # noqa: F401  (ImportError here = the reference cannot run on this box)
+
+    jax.config.update("jax_enable_x64", True)
+    import diffrax as dfx
+    import galax.dynamics as gd
+    import galax.potential as gp
+    import jax.numpy as jnp
+
+    pot = gp.MilkyWayPotential()
+    field = gd.fields.HamiltonianField(pot)
+    solver = gd.OrbitSolver(dfx.SemiImplicitEuler(), stepsize_controller=dfx.ConstantStepSize())
+    qj, pj = jnp.asarray(q), jnp.asarray(p)
+
+    def step():
+        sol = solver.solve(field, (qj, pj), 0.0, T1, dt0=DT0, max_steps=None)
+        jax.block_until_ready(sol.ys)
+        return sol
+
+    step()  # compile
+    return step
+
+
 def run_reference(args) -> None:
-    """The reference's CPU path for this metric.  galax (JAX/diffrax) cannot be installed in this image, so this
-    times the repo's C restatement of the same algorithm (oracle/, OpenMP over particles) on all host cores."""
+    """The reference's CPU path for this metric, on all host cores: galax (JAX-CPU) when it can be imported -- from
+    baseline/_ref or the environment -- otherwise the repo's C restatement of the same algorithm (oracle/, OpenMP over
+    particles).  ``cpu_baseline.kind`` says which one ran; ``note`` carries the import error when it was the port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -88,10 +131,18 @@ def run_reference(args) -> None:
     n = REF_ARM_SAMPLE_PER_CORE * cores
     q, r, vdir, f = host_ics(n, seed=1)
     p = vdir * (op.circular_velocity(opot, r) * f)[:, None]
+    kind, note = "port", None
+    try:
+        step = _galax_reference_step(q, p)
+        kind = "reference"
+        impl_desc = "galax (JAX-CPU, diffrax SemiImplicitEuler + ConstantStepSize, OrbitSolver.solve)"
+    except Exception as exc:  # ImportError offline; anything else: say what
+        note = f"galax/JAX/diffrax not runnable here ({type(exc).__name__}: {str(exc)[:120]}); timed the C port instead"
 
-    def step():
-        cref.integrate_fixed(opot, q, p, 0.0, T1, DT0, [T1])
+        def step():
+            cref.integrate_fixed(opot, q, p, 0.0, T1, DT0, [T1])
 
+        impl_desc = "oracle/galax_oracle.c (plain C restatement, OpenMP over particles)"
     for _ in range(min(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -99,20 +150,20 @@ def run_reference(args) -> None:
         step()
     dt = (time.perf_counter() - t0) / args.steps
     value = n * N_STEPS / dt
-    sample = f"{n} particles x {N_STEPS} steps per bench step (same ICs/potential/dt as the GPU arm)"
+    sample = f"{n} particles x {N_STEPS} steps per bench step (same ICs/potential/dt as the GPU arm); {impl_desc}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "galax/JAX/diffrax are not installable offline; 'port' = oracle/galax_oracle.c (plain C, OpenMP)",
+        "note": note,
     }  # fmt: skip
     emit(line)
 
 
-# --------------------------------------------------------------------------------------------- GPU arm
+# --------------------------------------------------------------------------------------------- measurement helpers
 
 
 class ClockSampler:
@@ -155,11 +206,149 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}  # fmt: skip
 
 
+def lib_sha16(path: Path) -> str:
+    return hashlib.sha256(path.read_bytes()).hexdigest()[:16]
+
+
+def ncu_counts(n: int, lib_path: Path) -> dict | None:
+    """One launch of the headline kernel (this library, the bench's own inputs) under ``ncu --metrics``: FP64
+    thread-instruction counts, FP64-pipe utilisation, DRAM bytes.  None when ncu is missing or the capture fails."""
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not Path(ncu).exists():
+        return None
+    cmd = [ncu, "--metrics", ",".join(NCU_METRICS), "--clock-control", "none", "-k", "regex:k_integrate_fixed",
+           "-c", "1", "--csv", sys.executable, str(ROOT / "bench.py"), "--one-launch", str(n)]  # fmt: skip
+    env = dict(os.environ, GX_BENCH_CHILD="1", GALAX_B200_LIB=str(lib_path))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    vals: dict[str, float] = {}
+    kernel = None
+    for line in res.stdout.splitlines():
+        cells = [c.strip('"') for c in line.split('","')]
+        if len(cells) < 4:
+            continue
+        for m in NCU_METRICS:
+            if m in cells:
+                try:
+                    vals[m] = float(cells[-1].replace(",", ""))
+                    kernel = next((c for c in cells if "k_integrate_fixed" in c), kernel)
+                except ValueError:
+                    pass
+    need = NCU_METRICS[:3]
+    if not all(m in vals for m in need):
+        return None
+    units = float(n) * N_STEPS
+    return {
+        "dfma": vals[need[0]] / units, "dmul": vals[need[1]] / units, "dadd": vals[need[2]] / units,
+        "warp_instr_per_warp_step": vals.get("smsp__inst_executed.sum", 0.0) / (units / 32.0) or None,
+        "fp64_warp_instr_per_warp_step": vals.get("smsp__inst_executed_pipe_fp64.sum", 0.0) / (units / 32.0) or None,
+        "fp64_pipe_active_pct": vals.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+        "dram_bytes": (vals.get("dram__bytes_read.sum", 0.0) + vals.get("dram__bytes_write.sum", 0.0)) or None,
+        "dram_read": vals.get("dram__bytes_read.sum"), "dram_write": vals.get("dram__bytes_write.sum"),
+        "kernel": kernel, "kernel_ms_under_ncu": vals.get("gpu__time_duration.sum", 0.0) * 1e-6 or None,
+    }  # fmt: skip
+
+
+def static_sass_counts(lib_path: Path) -> dict | None:
+    """Fallback: FP64 instructions in the hot loop of the headline kernel, counted in the library's SASS (the
+    smallest backward-branch span with >= 25 DFMA).  An UPPER bound: both sides of the NFW small-s switch are inside."""
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", str(lib_path)], capture_output=True, text=True, timeout=300).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    ins, on = [], False
+    for line in out.splitlines():
+        if "Function :" in line:
+            on = HOT_KERNEL_SYMBOL in line
+            continue
+        if on:
+            m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/\s+(.*?);", line)
+            if m:
+                ins.append((int(m.group(1), 16), m.group(2).strip()))
+    best = None
+    for a, t in ins:
+        m = re.search(r"BRA\s+(?:\w+,\s*)?0x([0-9a-f]+)", t)
+        if m and int(m.group(1), 16) < a:
+            lo = int(m.group(1), 16)
+            body = [x for b, x in ins if lo <= b <= a]
+            if sum("DFMA" in x for x in body) >= 25 and (best is None or len(body) < len(best)):
+                best = body
+    if not best:
+        return None
+    cnt = lambda k: float(sum(re.search(r"(^|\s)" + k + r"(\.|\s)", x) is not None for x in best))  # noqa: E731
+    return {"dfma": cnt("DFMA"), "dmul": cnt("DMUL"), "dadd": cnt("DADD"), "loop_instructions": len(best)}
+
+
+def one_launch(n: int) -> None:
+    """Child of ncu_counts(): exactly one launch of the headline kernel on the bench's inputs."""
+    import torch
+
+    import galax_b200.potential as gp
+    from galax_b200 import _lib
+
+    L = _lib.lib()
+    pot = gp.MilkyWayPotential()
+    P = pot.c_struct()
+    q_h, r_h, vdir, f = host_ics(n, seed=1)
+    xr = np.stack([r_h, np.zeros_like(r_h), np.zeros_like(r_h)], axis=1)
+    vc = np.sqrt(r_h * pot.gradient(xr)[:, 0])
+    dev = torch.device("cuda", 0)
+    q_d = torch.from_numpy(q_h).to(dev)
+    p_d = torch.from_numpy(vdir * (vc * f)[:, None]).to(dev)
+    ts_d = torch.tensor([T1], dtype=torch.float64, device=dev)
+    out = torch.empty((2, n, 1, 3), dtype=torch.float64, device=dev)
+    st = torch.empty((n,), dtype=torch.int32, device=dev)
+    rc = L.gx_integrate_fixed(C.byref(P), q_d.data_ptr(), p_d.data_ptr(), n, 0.0, T1, DT0, ts_d.data_ptr(), 1,
+                              _lib.SCHEME_SIE, -1, _lib.LAYOUT_NT3, out[0].data_ptr(), out[1].data_ptr(),
+                              st.data_ptr(), torch.cuda.current_stream().cuda_stream)  # fmt: skip
+    _lib.check(rc, "gx_integrate_fixed")
+    torch.cuda.synchronize()
+
+
+def ev_timed(torch, fn, reps: int = 2, warm: int = 1):
+    """Device time of ``fn`` (CUDA events on the current stream, synchronised both sides), best of ``reps``."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best, last = None, None
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = a.elapsed_time(b) * 1e-3
+        best = t if best is None else min(best, t)
+    return best, last
+
+
+def device_ics(torch, pot, n: int, seed: int, dev):
+    """C1-C4 synthetic initial conditions generated on the device (extra legs; same distribution as host_ics)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    r = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 16 + 4
+    d = torch.randn(n, 3, generator=g, device=dev, dtype=torch.float64)
+    d = d / d.norm(dim=1, keepdim=True)
+    q = d * r[:, None]
+    xr = torch.stack([r, torch.zeros_like(r), torch.zeros_like(r)], 1)
+    vc = (r * pot.gradient(xr)[:, 0]).sqrt()
+    d2 = torch.randn(n, 3, generator=g, device=dev, dtype=torch.float64)
+    d2 = d2 / d2.norm(dim=1, keepdim=True)
+    p = d2 * (vc * (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 0.4 + 0.6))[:, None]
+    return q.contiguous(), p.contiguous()
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+
+
 def run_gpu(args) -> None:
     import torch
     import torch.distributed as dist
 
-    import galax_b200
+    import galax_b200  # noqa: F401
     import galax_b200.dynamics as gd
     import galax_b200.potential as gp
     from galax_b200 import _lib
@@ -188,19 +377,20 @@ def run_gpu(args) -> None:
     p_pin = torch.from_numpy(p_h).pin_memory()
     q_d, p_d = q_pin.to(dev), p_pin.to(dev)
     ts_d = torch.tensor([T1], dtype=torch.float64, device=dev)
-    q_out = torch.empty((n, 1, 3), dtype=torch.float64, device=dev)
-    p_out = torch.empty_like(q_out)
     status = torch.empty((n,), dtype=torch.int32, device=dev)
-    gathered_q = torch.empty((world * n, 1, 3), dtype=torch.float64, device=dev) if world > 1 else None
-    gathered_p = torch.empty_like(gathered_q) if world > 1 else None
+    gather = gdist.ResultGather(world * n, 1, device=dev, depth=2)  # packed (q, p) result, one async all-gather per step
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     launches = 0
-    kernel_ms: list[float] = []
+    step_no = 0
 
     def device_step(record: bool):
-        nonlocal launches
+        nonlocal launches, step_no
+        k = step_no
+        step_no += 1
         flush.zero_()  # evict L2 between iterations
+        gather.wait(k)  # (the gather that used this buffer two steps ago)
+        q_out, p_out = gather.views(k)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = L.gx_integrate_fixed(C.byref(P), q_d.data_ptr(), p_d.data_ptr(), n, 0.0, T1, DT0, ts_d.data_ptr(), 1,
@@ -209,14 +399,11 @@ def run_gpu(args) -> None:
         e1.record()
         _lib.check(rc, "gx_integrate_fixed")
         launches += 1
-        if world > 1:  # the job's only collective: gather the result shards
-            dist.all_gather_into_tensor(gathered_q, q_out)
-            dist.all_gather_into_tensor(gathered_p, p_out)
-        if record:
-            return e0, e1
-        return None
+        gather.start(k)  # the job's only collective; runs under the next step's kernel
+        return (e0, e1) if record else None
 
     def barrier():
+        gather.wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -237,6 +424,12 @@ def run_gpu(args) -> None:
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
     assert int((status != 0).sum()) == 0, "integration reported failures"
     gpu_launches = launches
+    q_fin, p_fin = gather.views(step_no - 1)
+    q_fin, p_fin = q_fin.clone(), p_fin.clone()
+    if world > 1:  # every rank holds the whole job's result
+        qa, pa = gather.result(step_no - 1)
+        assert qa.shape == (world * n, 1, 3) and torch.equal(qa[rank * n : (rank + 1) * n], q_fin)
+        del qa, pa
     el = torch.tensor([elapsed], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -255,76 +448,90 @@ def run_gpu(args) -> None:
         qf, pf = e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_ms = []
     for _ in range(args.steps):
-        ts0 = time.perf_counter()
         qf, pf = e2e_step()
-        e2e_ms.append((time.perf_counter() - ts0) * 1e3)
     barrier()
     e2e_elapsed = time.perf_counter() - t0
-    if rank == 0 and os.environ.get("GX_BENCH_DEBUG"):
-        print("e2e per-step ms:", [round(v, 2) for v in e2e_ms], file=sys.stderr)
     el = torch.tensor([e2e_elapsed], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     e2e_value = world * n * N_STEPS * args.steps / float(el)
     assert not qf.is_cuda and qf.shape == (n, 1, 3)
 
+    # ---- C4 (BASELINE.json configs[3]): 1e8 particles, BovyMWPotential2014, strong-scaled over the ranks, gather included
+    extra: dict = {}
+    if not args.no_extras:
+        extra["C4_strong"] = leg_c4(torch, dist, gd, gp, gdist, L, _lib, dev, world, rank, args)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- rank 0 extras: FP64 peak (live), C1 exact, energy drift, CPU baseline
+    # ---- rank 0: FP64 peak (live), executed instruction mix (ncu, live), HBM leg, other configs, CPU baseline
     sink = torch.zeros(8, dtype=torch.float64, device=dev)
     nf = C.c_int64()
-    best = None
-    for _ in range(3):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        L.gx_bench_dfma(148 * 8, 256, 20000, sink.data_ptr(), C.byref(nf), stream)
-        b.record()
-        torch.cuda.synchronize()
-        t = a.elapsed_time(b) * 1e-3
-        best = t if best is None else min(best, t)
-    dfma_peak = 2.0 * nf.value * 148 * 8 * 256 / best / 1e12
-    best3 = None
-    for _ in range(3):  # same chains with three distinct register operands per DFMA: the register-file-fed rate
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        L.gx_bench_dfma(-148 * 8, 256, 20000, sink.data_ptr(), C.byref(nf), stream)
-        b.record()
-        torch.cuda.synchronize()
-        t = a.elapsed_time(b) * 1e-3
-        best3 = t if best3 is None else min(best3, t)
-    dfma_peak_3reg = 2.0 * nf.value * 148 * 8 * 256 / best3 / 1e12
 
+    def dfma_peak(blocks):
+        best = None
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            L.gx_bench_dfma(blocks, 256, 20000, sink.data_ptr(), C.byref(nf), stream)
+            b.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b) * 1e-3
+            best = t if best is None else min(best, t)
+        return 2.0 * nf.value * abs(blocks) * 256 / best / 1e12
+
+    peak = dfma_peak(148 * 8)
+    peak_3reg = dfma_peak(-148 * 8)  # same chains, three distinct register operands per DFMA
+
+    lib_path = Path(_lib.LIB_PATH)
+    counts, source = None, None
+    if not args.no_ncu:
+        del flush
+        torch.cuda.empty_cache()
+        counts = ncu_counts(n, lib_path)
+        flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+        if counts:
+            source = f"ncu --metrics sub-invocation in this run: one launch of {counts['kernel']} on the bench inputs, library sha256 {lib_sha16(lib_path)}"
+    if counts is None:
+        counts = static_sass_counts(lib_path)
+        if counts:
+            source = (f"static count of the kernel's hot loop in the loaded library's SASS (cuobjdump, library sha256 "
+                      f"{lib_sha16(lib_path)}): an upper bound, ncu was not available")  # fmt: skip
     k_ms = float(np.mean(kernel_ms))
     per_gpu_rate = n * N_STEPS / (k_ms * 1e-3)
-    achieved = per_gpu_rate * FLOP_PER_STEP / 1e12
-    roofline = {
-        "bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved / dfma_peak,
-        "traffic": 78.8e6 if n == N_PER_GPU else None,
-        "traffic_source": "ncu --set full, profiles/ncu_k_integrate_fixed_r1f.txt: dram read 59.8 MB + write 19.0 MB per "
-                          "launch (algorithmic: 58.2 MB in + 58.2 MB out + 4.8 MB status; L2 absorbs part of the writes)",
+    if counts:
+        flop_exec = 2.0 * counts["dfma"] + counts["dmul"] + counts["dadd"]
+        n_instr = counts["dfma"] + counts["dmul"] + counts["dadd"]
+        achieved = per_gpu_rate * flop_exec / 1e12
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": counts.get("dram_bytes"),
+            "flop_per_particle_step": flop_exec,
+            "fp64_instr_per_particle_step": {k: counts[k] for k in ("dfma", "dmul", "dadd")},
+            "fp64_issue_slot_frac": per_gpu_rate * n_instr / (peak * 1e12 / 2.0),
+            "fp64_pipe_active_pct": counts.get("fp64_pipe_active_pct"),
+            "warp_instr_per_warp_step": counts.get("warp_instr_per_warp_step"),
+            "source": source,
+        }  # fmt: skip
+    else:
+        roofline = {"bound": "fp64", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                    "source": "neither ncu nor cuobjdump available: executed instruction mix not measured"}  # fmt: skip
+    roofline.update({
         "kernel": "k_integrate_fixed_seg<MW> (SemiImplicitEuler, run-length time grid)", "kernel_ms": k_ms,
-        "algorithmic_flop_per_particle_step": FLOP_PER_STEP,
-        "peak_three_register_operands": dfma_peak_3reg,
+        "algorithmic_bytes_per_launch": n * (48 + 48 + 4),
+        "peak_three_register_operands": peak_3reg,
         "peak_source": "measured live: gx_bench_dfma (8 independent DFMA chains/thread), best of 3; "
                        "MEASURED_PEAKS.json has no FP64 entry",
-        "note": "canonical weighted flop (div/sqrt=18, log1p=56) per SURVEY.md 8d; the kernel issues fewer real "
-                "instructions than that (MUFU-seeded rcp/rsqrt): see 'executed' for the ncu-counted rate",
-    }  # fmt: skip
-    n_instr = sum(NCU_FP64_INSTR_PER_STEP.values())
-    n_flop = 2.0 * NCU_FP64_INSTR_PER_STEP["dfma"] + NCU_FP64_INSTR_PER_STEP["dmul"] + NCU_FP64_INSTR_PER_STEP["dadd"]
-    roofline["executed"] = {
-        "fp64_instr_per_particle_step": NCU_FP64_INSTR_PER_STEP,
-        "tflops": per_gpu_rate * n_flop / 1e12,                         # dfma x 2 + dmul + dadd, as ncu counts flop
-        "frac_of_dfma_peak": per_gpu_rate * n_flop / 1e12 / dfma_peak,
-        "fp64_issue_frac": per_gpu_rate * n_instr / (dfma_peak * 1e12 / 2.0),  # FP64 instructions / FP64 issue slots
-        "ncu_fp64_pipe_active_pct": NCU_FP64_PIPE_ACTIVE_PCT,
-        "source": "profiles/ncu_k_integrate_fixed_r1f.txt (same kernel, same launch shape)",
-    }
+        "canonical": {"flop_per_particle_step": CANONICAL_FLOP_PER_STEP,
+                      "tflops": per_gpu_rate * CANONICAL_FLOP_PER_STEP / 1e12,
+                      "note": "SURVEY.md 8d weighted op count (div = sqrt = 18, log1p = 56 flop); the kernel does that "
+                              "work in fewer real instructions (MUFU-seeded rcp/rsqrt, table log), so this is NOT a "
+                              "fraction of peak -- informational"},
+    })  # fmt: skip
 
     # The HBM-bound leg of the path (C5): acceleration + Hessian on 2e7 points, against the measured copy peak
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -353,25 +560,18 @@ def run_gpu(args) -> None:
                    "algorithmic_bytes_per_point": 120, "points": npts, "peak_source": hbm_src}  # fmt: skip
     del xs, acc_o, hes_o
 
-    # C1 exactly as stated: 10^4 particles
-    qc, pc = q_d[:10_000].contiguous(), p_d[:10_000].contiguous()
-    qo, po = torch.empty((10_000, 1, 3), dtype=torch.float64, device=dev), torch.empty((10_000, 1, 3), dtype=torch.float64, device=dev)
-    c1 = []
-    for i in range(4):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        L.gx_integrate_fixed(C.byref(P), qc.data_ptr(), pc.data_ptr(), 10_000, 0.0, T1, DT0, ts_d.data_ptr(), 1,
-                             _lib.SCHEME_SIE, -1, _lib.LAYOUT_NT3, qo.data_ptr(), po.data_ptr(), None, stream)
-        b.record()
-        torch.cuda.synchronize()
-        if i:
-            c1.append(a.elapsed_time(b) * 1e-3)
-    c1_rate = 10_000 * N_STEPS / min(c1)
-
     E0 = gd._energy(pot, q_d, p_d)
-    E1 = gd._energy(pot, q_out[:, 0], p_out[:, 0])
+    E1 = gd._energy(pot, q_fin[:, 0], p_fin[:, 0])
     drift = (E1 / E0 - 1).abs()
-    energy = {"median": float(drift.median()), "p99": float(drift.quantile(0.99)), "max": float(drift.max())}
+    rmin_note = int((drift > 1e-2).sum())
+    energy = {"median": float(drift.median()), "p99": float(drift.quantile(0.99)), "max": float(drift.max()),
+              "particles_above_1e-2": rmin_note,
+              "note": "SemiImplicitEuler at dt = 0.1 Myr; the few large values are orbits through the 70 pc nucleus"}  # fmt: skip
+
+    if not args.no_extras:
+        del flush
+        torch.cuda.empty_cache()
+        extra.update(legs_rank0(torch, gd, gp, L, _lib, dev, pot, P, q_d, p_d, q_h, p_h, peak, hbm_peak))
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -385,11 +585,16 @@ def run_gpu(args) -> None:
         t0 = time.perf_counter()
         qr, pr, st, _ = cref.integrate_fixed(opot, q_h[:ns], p_h[:ns], 0.0, T1, DT0, [T1])
         dt = time.perf_counter() - t0
-        e = np.linalg.norm(q_out[:ns, 0].cpu().numpy() - qr[:, 0], axis=1) / np.linalg.norm(qr[:, 0], axis=1)
+        e = np.linalg.norm(q_fin[:ns, 0].cpu().numpy() - qr[:, 0], axis=1) / np.linalg.norm(qr[:, 0], axis=1)
+        # the reference-order kernel on the same sample must be the C oracle bit for bit
+        strict = gd.OrbitSolver(solver=gd.SemiImplicitEuler(strict=True), stepsize_controller=gd.ConstantStepSize(),
+                                max_steps=None).solve(pot, (q_h[:ns], p_h[:ns]), 0.0, T1, dt0=DT0)  # fmt: skip
         cpu = {"value": ns * N_STEPS / dt, "unit": UNIT, "cores": cref.num_threads(), "kind": "port",
                "sample": f"first {ns} particles of rank 0's batch x {N_STEPS} steps, oracle/galax_oracle.c (OpenMP)",
                "parity_vs_gpu": {"median_rel": float(np.median(e)), "p99_rel": float(np.quantile(e, 0.99)),
-                                 "frac_le_1e-12": float(np.mean(e <= 1e-12))}}  # fmt: skip
+                                 "frac_le_1e-12": float(np.mean(e <= 1e-12)),
+                                 "strict_kernel_bit_identical": bool(np.array_equal(strict.ys[0], qr)
+                                                                     and np.array_equal(strict.ys[1], pr))}}  # fmt: skip
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -400,13 +605,146 @@ def run_gpu(args) -> None:
                 "api": "galax_b200.dynamics.OrbitSolver(SemiImplicitEuler, ConstantStepSize).solve(pot, (q, p), 0, 1000, dt0=0.1) "
                        "with pinned host tensors"},
         "gpu_launches": gpu_launches, "roofline": roofline, "roofline_hbm_leg": roofline_k1, "cpu_baseline": cpu,
-        "c1_exact": {"particles": 10_000, "value": c1_rate, "unit": UNIT, "ms": min(c1) * 1e3},
-        "energy_drift": energy, "fp64_peak_tflops_measured": dfma_peak,
-        "fp64_peak_tflops_measured_3reg_operands": dfma_peak_3reg,
+        "extra": extra, "energy_drift": energy, "fp64_peak_tflops_measured": peak,
+        "fp64_peak_tflops_measured_3reg_operands": peak_3reg,
     }  # fmt: skip
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def leg_c4(torch, dist, gd, gp, gdist, L, _lib, dev, world, rank, args) -> dict:
+    """C4: 1e8 particles, BovyMWPotential2014, fixed step over 1 Gyr, STRONG-scaled: the job's particles are split over
+    the ranks (shard_bounds), every rank integrates its block, one all-gather of the packed final states.  Timed on the
+    device, max over ranks.  Executed by ALL ranks (it contains the collective)."""
+    n_total = args.c4_particles
+    pot = gp.BovyMWPotential2014()
+    P = pot.c_struct()
+    g = gdist.ResultGather(n_total, 1, device=dev, depth=1)
+    nl = g.n_local
+    q0, p0 = device_ics(torch, pot, nl, seed=400 + rank, dev=dev)
+    ts_d = torch.tensor([T1], dtype=torch.float64, device=dev)
+    status = torch.empty((nl,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(t_end, dt0):
+        qv, pv = g.views(0)
+        rc = L.gx_integrate_fixed(C.byref(P), q0.data_ptr(), p0.data_ptr(), nl, 0.0, t_end, dt0, ts_d.data_ptr(), 1,
+                                  _lib.SCHEME_SIE, -1, _lib.LAYOUT_NT3, qv.data_ptr(), pv.data_ptr(), status.data_ptr(),
+                                  stream)  # fmt: skip
+        _lib.check(rc, "gx_integrate_fixed")
+        g.start(0)
+        g.wait(0)
+
+    ts_d.fill_(10.0)
+    run(10.0, DT0)  # warm-up: 100 steps (table upload, NCCL buffers)
+    ts_d.fill_(T1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run(T1, DT0)
+    b.record()
+    torch.cuda.synchronize()
+    el = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    t = float(el)
+    ok = int((status != 0).sum()) == 0
+    del g, q0, p0
+    torch.cuda.empty_cache()
+    return {"config": f"{n_total} particles, BovyMWPotential2014, SemiImplicitEuler dt=0.1 Myr x {N_STEPS} steps, "
+                      f"particle-sharded over {world} GPU(s), all-gather of the final states included",
+            "particles": n_total, "n_gpus": world, "s": t, "value": n_total * N_STEPS / t, "unit": UNIT,
+            "scaling": "strong", "gather_bytes_per_rank": nl * 48, "all_ok": ok}  # fmt: skip
+
+
+def legs_rank0(torch, gd, gp, L, _lib, dev, pot, P, q_d, p_d, q_h, p_h, peak, hbm_peak) -> dict:
+    """BASELINE.json's other configurations at full single-GPU size, device-timed (CUDA events), rank 0."""
+    out: dict = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    SIE = dict(solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(), dt0=DT0, max_steps=None)
+
+    # C1 exactly: 10^4 particles.  Device-resident, then end to end (numpy in -> numpy out through OrbitSolver.solve)
+    qc, pc = q_d[:10_000].contiguous(), p_d[:10_000].contiguous()
+    t_dev, _ = ev_timed(torch, lambda: gd._integrate(pot, qc, pc, 0.0, T1, np.array([T1]), **SIE), reps=3)
+    t_101, _ = ev_timed(torch, lambda: gd._integrate(pot, qc, pc, 0.0, T1, np.linspace(0.0, T1, 101), **SIE), reps=3)
+    solver = gd.OrbitSolver(solver=gd.SemiImplicitEuler(), stepsize_controller=gd.ConstantStepSize(), max_steps=None)
+    qn, pn = q_h[:10_000].copy(), p_h[:10_000].copy()
+    solver.solve(pot, (qn, pn), 0.0, T1, dt0=DT0)
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sol = solver.solve(pot, (qn, pn), 0.0, T1, dt0=DT0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert isinstance(sol.ys[0], np.ndarray)
+    out["C1_exact"] = {"config": "10^4 particles, MilkyWayPotential, SemiImplicitEuler dt=0.1 Myr x 10^4 steps",
+                       "device_s": t_dev, "value": 1e8 / t_dev, "unit": UNIT, "device_s_101_saves": t_101,
+                       "e2e_s": best, "e2e_value": 1e8 / best, "h2d_bytes": 480_000, "d2h_bytes": 520_000,
+                       "note": "2 warps per SM: bound by the dependent chain of one step, not by issue slots"}  # fmt: skip
+
+    # C2: 1e6 particles, MilkyWayPotential2022, Dopri8 rtol = atol = 1e-10, 1000 saves over 5 Gyr (48 GB of output)
+    pot2 = gp.MilkyWayPotential2022()
+    N2 = 1_000_000
+    q2, p2 = device_ics(torch, pot2, N2, seed=2, dev=dev)
+    ts = np.linspace(0.0, 5000.0, 1000)
+    kw = dict(solver=gd.Dopri8(), controller=gd.PIDController(1e-10, 1e-10), dt0=None, max_steps=2**16, throw=False)
+    gd._integrate(pot2, q2[:4096], p2[:4096], 0.0, 5000.0, ts, **kw)
+    t2, res = ev_timed(torch, lambda: gd._integrate(pot2, q2, p2, 0.0, 5000.0, ts, **kw), reps=1, warm=1)
+    qq, pp, st, stats = res
+    na, nt = int(stats["num_accepted_steps"].sum()), int(stats["num_steps"].sum())
+    dE = (gd._energy(pot2, qq[:, -1], pp[:, -1]) / gd._energy(pot2, q2, p2) - 1).abs()
+    out["C2"] = {"config": "1e6 particles, MilkyWayPotential2022, Dopri8 + PID rtol=atol=1e-10, 1000 saves over 5 Gyr, "
+                           "[N,T,3] output (48 GB) resident in HBM",
+                 "s": t2, "accepted_steps": na, "attempted_steps": nt, "accepted_steps_per_s": na / t2,
+                 "rhs_per_s": 13 * nt / t2, "output_GB": 48.0, "failed": int((st != 0).sum()),
+                 "energy_drift_median": float(dE.median())}  # fmt: skip
+    del qq, pp, res, q2, p2
+    torch.cuda.empty_cache()
+
+    # C3: Pal-5-like mock stream, Fardal DF, 5e5 stripping times -> 1e6 particles over 3 Gyr
+    M = 500_000
+    ts3 = np.linspace(0.0, 3000.0, M)
+    w0 = gd.PhaseSpaceCoordinate(np.array([30.0, 10, 20]), np.array([10.0, -150, -20]) * gp.KMS, 0.0)
+    draws = np.random.default_rng(3).standard_normal((4, M))
+    gen = gd.MockStreamGenerator(gd.FardalStreamDF(), pot)
+    gen.run(draws[:, :1000], ts3[:1000], w0, 1e4)
+    best = None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stream_, prog = gen.run(draws, ts3, w0, 1e4)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out["C3"] = {"config": "MockStreamGenerator(FardalStreamDF, MilkyWayPotential).run: 5e5 stripping times, 1e6 particles, "
+                           "3 Gyr, Dopri8 rtol=atol=1e-7; host draws in, host arrays out (wall clock, end to end)",
+                 "s": best, "released_particles_per_s": 2 * M / best, "finite": bool(np.isfinite(stream_.q).all())}  # fmt: skip
+
+    # C5 shard: acceleration + Hessian at 1.25e8 points (1e9 / 8 GPUs), MilkyWayPotential
+    N5 = 125_000_000
+    g = torch.Generator(device=dev).manual_seed(5)
+    r = 10 ** (torch.rand(N5, generator=g, device=dev, dtype=torch.float64) * 3 - 1)
+    d = torch.randn(N5, 3, generator=g, device=dev, dtype=torch.float64)
+    d /= d.norm(dim=1, keepdim=True)
+    x = (d * r[:, None]).contiguous()
+    del d, r
+    acc_o = torch.empty((N5, 3), dtype=torch.float64, device=dev)
+    hes_o = torch.empty((N5, 9), dtype=torch.float64, device=dev)
+
+    def k1():
+        rc = L.gx_potential_eval(C.byref(P), x.data_ptr(), 0.0, N5, _lib.ACC | _lib.HESS, None, None, acc_o.data_ptr(),
+                                 hes_o.data_ptr(), stream)
+        _lib.check(rc, "gx_potential_eval")
+
+    t5, _ = ev_timed(torch, k1, reps=3)
+    out["C5_shard"] = {"config": "acceleration + Hessian at 1.25e8 points (the per-GPU shard of 1e9 on 8), MilkyWayPotential",
+                       "s": t5, "points_per_s": N5 / t5, "GB_per_s": N5 * 120 / t5 / 1e9,
+                       "frac_of_hbm_peak": N5 * 120 / t5 / 1e9 / hbm_peak}  # fmt: skip
+    return out
 
 
 _JSON_FD = None
@@ -427,17 +765,24 @@ def main():
     # communicator when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the
     # duration of the run and the line goes to a saved copy of the original descriptor.
     global _JSON_FD
-    sys.stdout.flush()
-    _JSON_FD = os.dup(1)
-    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="galax_b200", choices=["galax_b200", "reference"])
     ap.add_argument("--particles-per-gpu", type=int, default=N_PER_GPU)
+    ap.add_argument("--c4-particles", type=int, default=100_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1-exact / C2 / C3 / C4 / C5 legs")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the ncu sub-invocation (static SASS count instead)")
+    ap.add_argument("--one-launch", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.one_launch:
+        one_launch(args.one_launch)
+        return
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

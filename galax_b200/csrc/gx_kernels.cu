@@ -381,6 +381,95 @@ __global__ void __launch_bounds__(TILE) k_potential_eval(const __grid_constant__
 // K2 fixed-step integrator
 // ================================================================================================
 
+// ---- saved states in the reference layout [N,T,3] (dynamics/_src/orbit/register_dfx.py:78-82) ----
+// A thread owns a particle.  Its saves k, k+1, ... are 24 bytes apart in q[N,T,3] (and in p) and the next particle's
+// row is 24 T bytes away, so a store instruction of the warp touches 32 different 32-byte sectors with 8 bytes each;
+// and when the saves of one particle are far apart in time, a partially written sector leaves L2 before its
+// neighbours arrive (ncu, round 1, Dopri8 with 10 saves: 3.75x the algorithmic DRAM write traffic, plus the
+// read-modify-write reads).  So each lane stages up to four saves in shared memory ([slot][6][lane]: conflict-free,
+// private to the lane, no barrier) and writes them out when the run ENDS ON A SECTOR BOUNDARY of the output:
+// 24 (T i + k + 1) = 0 (mod 32)  <=>  (T i + k + 1) mod 4 == 0.  Every flush but a row's first and last is then
+// exactly three whole sectors of q and three of p, written by back-to-back stores of one lane (L2 sees whole sectors).
+// Used when the caller asks for GX_LAYOUT_NT3 with T >= SAVE_STAGE_MIN_T; GX_LAYOUT_T3N and short rows store directly.
+constexpr int SAVE_SLOTS = 4;  // saves per run (the last one of a run is written straight from registers)
+constexpr int SAVE_STAGE_MIN_T = 4;
+// Nothing but the save index k is carried between saves: the sector phase of save k is (T i + k) mod 4, the number of
+// staged saves is that phase (or k itself inside the row's first, shorter run).
+__device__ __forceinline__ double *save_buf() {
+    extern __shared__ __align__(16) double gx_save_buf[];
+    return gx_save_buf;
+}
+template <class A>
+__device__ __forceinline__ int save_staged(const A &a, long long i, int k) {  // saves staged before save k
+    const int ph = (int)(((unsigned)a.T * (unsigned)i + (unsigned)k) & 3u);
+    return ph < k ? ph : k;
+}
+// (a rolled loop: the integrators' register allocation should not pay for this cold path)
+__device__ __forceinline__ void save_flush_n(double *qd, double *pd, int n) {
+    const int bd = blockDim.x;
+    const double *b = save_buf() + threadIdx.x;
+#pragma unroll 1
+    for (int s = 0; s < n; ++s, b += 6 * bd, qd += 3, pd += 3) {
+        qd[0] = b[0]; qd[1] = b[bd]; qd[2] = b[2 * bd];
+        pd[0] = b[3 * bd]; pd[1] = b[4 * bd]; pd[2] = b[5 * bd];
+    }
+}
+template <class A>
+__device__ __forceinline__ void save_flush(const A &a, long long i, int kend) {  // write out what is staged before kend
+    if (!a.stage) return;
+    const int n = save_staged(a, i, kend);
+    if (n > 0) save_flush_n(a.q + i * a.sn + 3LL * (kend - n), a.p + i * a.sn + 3LL * (kend - n), n);
+}
+// Where save k of particle i goes: component c of q at q[c * st], of p at p[c * st] -- the output itself (direct
+// stores, or the save that closes a run) or the lane's staging column.  The caller stores the six values as it
+// computes them (nothing extra is live across the dense-output evaluation) and then calls save_commit().
+struct SaveDst {
+    double *q, *p;
+    long long st;
+};
+template <class A>
+__device__ __forceinline__ SaveDst save_dst(const A &a, long long i, int k) {
+    SaveDst d;
+    if (!a.stage) {
+        d.q = a.q + i * a.sn + k * a.sk; d.p = a.p + i * a.sn + k * a.sk; d.st = a.sc;
+    } else if ((((unsigned)a.T * (unsigned)i + (unsigned)k + 1u) & 3u) != 0u) {  // not at a sector boundary: stage
+        const int bd = blockDim.x;
+        d.q = save_buf() + threadIdx.x + (6 * save_staged(a, i, k)) * bd; d.p = d.q + 3 * bd; d.st = bd;
+    } else {  // save k ends on a sector boundary: it goes straight out, behind the staged ones (save_commit)
+        d.q = a.q + i * a.sn + 3LL * k; d.p = a.p + i * a.sn + 3LL * k; d.st = 1;
+    }
+    return d;
+}
+template <class A>
+__device__ __forceinline__ void save_commit(const A &a, long long i, int k) {
+    if (a.stage && (((unsigned)a.T * (unsigned)i + (unsigned)k + 1u) & 3u) == 0u) save_flush(a, i, k);
+}
+template <class A>
+__device__ __forceinline__ void save_put(const A &a, long long i, int k, double qx, double qy, double qz, double px,
+                                         double py, double pz) {
+    const SaveDst d = save_dst(a, i, k);
+    d.q[0] = qx; d.q[d.st] = qy; d.q[2 * d.st] = qz;
+    d.p[0] = px; d.p[d.st] = py; d.p[2 * d.st] = pz;
+    save_commit(a, i, k);
+}
+// the saves a failed particle never reached: NaN, like an unfilled diffrax buffer
+template <class A>
+__device__ __forceinline__ void save_fill_nan(const A &a, long long i, int k) {
+    save_flush(a, i, k);
+    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+    double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
+    for (; k < a.T; ++k) {
+        qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
+        po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
+    }
+}
+#ifndef GX_SAVE_STAGE
+#define GX_SAVE_STAGE 1
+#endif
+static inline size_t save_stage_bytes(int layout, int T, int block) {
+    return (GX_SAVE_STAGE && layout == GX_LAYOUT_NT3 && T >= SAVE_STAGE_MIN_T) ? (size_t)block * (SAVE_SLOTS - 1) * 6 * sizeof(double) : 0;
+}
+
 struct FixedArgs {
     const double *q0, *p0, *ts;
     double *q, *p;
@@ -389,6 +478,7 @@ struct FixedArgs {
     long long sn, sk, sc;  // output strides (elements): particle, save, component
     double t0, t1, dt0;
     int T, hit_max_steps;
+    int stage;  // saves go through the per-lane staging buffer (save_put)
 };
 
 // Run-length form of the shared time grid (k_integrate_fixed_seg).  diffrax's grid t_{n+1} = fl(t_n + dt0) has a step
@@ -447,6 +537,16 @@ __device__ __forceinline__ double clip_to_end(double tprev, double tnext, double
 __device__ __forceinline__ bool finite3(double a, double b, double c) {
     return isfinite(a) && isfinite(b) && isfinite(c);
 }
+// six at once, branch-free on the integer pipe: the largest exponent field is not all ones.  (A chain of isfinite()
+// compiles to one branch per component, and every branch target of the Dopri kernel's accept block then gets its own
+// copy of the block's register moves: 145 moves per step in the round-2 profile.)
+__device__ __forceinline__ bool finite6(double a, double b, double c, double d, double e, double f) {
+    const unsigned M = 0x7ff00000u;
+    const unsigned m = max(max(max((unsigned)__double2hiint(a) & M, (unsigned)__double2hiint(b) & M),
+                               max((unsigned)__double2hiint(c) & M, (unsigned)__double2hiint(d) & M)),
+                           max((unsigned)__double2hiint(e) & M, (unsigned)__double2hiint(f) & M));
+    return m != M;
+}
 
 // SemiImplicitEuler state update y1 = y0 + f*dt as one FMA per component (GX_FUSED_UPDATE=1, default): six FP64
 // instructions fewer per step (+4 % measured).  diffrax writes a multiply and an add; whether XLA contracts them is
@@ -481,14 +581,12 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
     double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
     double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
     double mqx = qx, mqy = qy, mqz = qz, mpx = px, mpy = py, mpz = pz, tm = T0;  // LeapfrogMidpoint memory
-    double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int k = 0;
     auto load_ts = [&](int kk) { return (kk < a.T) ? (FWD ? __ldg(a.ts + kk) : -__ldg(a.ts + kk)) : INF; };
     double tsave = load_ts(k);
     while (tsave <= T0) {  // save times equal to t0 return y0
-        qo[k * a.sk] = qx; qo[k * a.sk + a.sc] = qy; qo[k * a.sk + 2 * a.sc] = qz;
-        po[k * a.sk] = px; po[k * a.sk + a.sc] = py; po[k * a.sk + 2 * a.sc] = pz;
+        save_put(a, i, k, qx, qy, qz, px, py, pz);
         ++k;
         tsave = load_ts(k);
     }
@@ -541,12 +639,10 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         if (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
             do {
                 const double th = (tsave - tprev) / (tnext - tprev);
-                qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
-                qo[k * a.sk + a.sc] = __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy)));
-                qo[k * a.sk + 2 * a.sc] = __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz)));
-                po[k * a.sk] = __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px)));
-                po[k * a.sk + a.sc] = __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py)));
-                po[k * a.sk + 2 * a.sc] = __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz)));
+                save_put(a, i, k, __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx))),
+                         __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy))), __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz))),
+                         __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px))), __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py))),
+                         __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz))));
                 ++k;
                 tsave = load_ts(k);
             } while (tsave <= tnext);
@@ -557,11 +653,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
     }
     int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
     if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
-    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
-    for (; k < a.T; ++k) {
-        qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
-        po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
-    }
+    save_fill_nan(a, i, k);
     if (a.status) a.status[i] = st;
 }
 
@@ -585,14 +677,12 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     const double T0 = FWD ? a.t0 : -a.t0;
     double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
     double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
-    double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int k = 0;
     auto load_ts = [&](int kk) { return (kk < a.T) ? (FWD ? __ldg(a.ts + kk) : -__ldg(a.ts + kk)) : INF; };
     double tsave = load_ts(k);
     while (tsave <= T0) {  // save times equal to t0 return y0
-        qo[k * a.sk] = qx; qo[k * a.sk + a.sc] = qy; qo[k * a.sk + 2 * a.sc] = qz;
-        po[k * a.sk] = px; po[k * a.sk + a.sc] = py; po[k * a.sk + 2 * a.sc] = pz;
+        save_put(a, i, k, qx, qy, qz, px, py, pz);
         ++k;
         tsave = load_ts(k);
     }
@@ -658,12 +748,10 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 }
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
                     const double th = (tsave - tprev) / (tnext - tprev);
-                    qo[k * a.sk] = __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx)));
-                    qo[k * a.sk + a.sc] = __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy)));
-                    qo[k * a.sk + 2 * a.sc] = __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz)));
-                    po[k * a.sk] = __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px)));
-                    po[k * a.sk + a.sc] = __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py)));
-                    po[k * a.sk + 2 * a.sc] = __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz)));
+                    save_put(a, i, k, __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx))),
+                             __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy))), __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz))),
+                             __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px))), __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py))),
+                             __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz))));
                     ++k;
                     tsave = load_ts(k);
                 }
@@ -675,11 +763,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     }
     int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
     if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
-    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
-    for (; k < a.T; ++k) {
-        qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
-        po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
-    }
+    save_fill_nan(a, i, k);
     if (a.status) a.status[i] = st;
 }
 
@@ -701,6 +785,7 @@ struct Dp8Args {
     double t0s, t1;
     double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax, dtmin, dtmax, dt0;
     int T;
+    int stage;  // saves go through the per-lane staging buffer (save_put)
 };
 
 template <class TB>
@@ -761,6 +846,8 @@ __device__ __forceinline__ const DevPot &rhs_pot() {
 struct Acc3 { double x, y, z; };
 template <class C>
 __device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
+    // (handing the table's shared-window address down in a register instead of re-deriving it here -- S2R + LEA + ISETP
+    // + MOV per call -- was measured: the extra live register costs the Dopri8 kernel 40 bytes of spills)
     double g0, g1, g2;
     unsigned nfw_base = 0;  // the kernel prologue staged the NFW force table (nfw_stage)
     if constexpr (nfw_tab_ok<C>()) nfw_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
@@ -839,13 +926,11 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     (void)nfw_stage<C, nfw_tab_ok<C>()>(P);  // (MW, MW2022) the NFW force table, likewise
     const unsigned FULL = 0xffffffffu;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
-
     const bool simple_i = (TB::ORDER == 8) && (a.pcoeff == 0.0 && a.dcoeff == 0.0 && a.icoeff == 1.0);
     bool have = false, exhausted = false;
     long long idx = 0;
     double q0x = 0, q0y = 0, q0z = 0, p0x = 0, p0y = 0, p0z = 0;  // state at tprev
-    double rx[NS], ry[NS], rz_[NS];  // stage accelerations; [0] is the FSAL value
+    double fsx = 0.0, fsy = 0.0, fsz = 0.0;  // acceleration at (tprev, q0): the FSAL value, the only stage carried over
 #define AX(l) rx[l]
 #define AY(l) ry[l]
 #define AZ(l) rz_[l]
@@ -853,9 +938,27 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     double prev_inv = 1.0, prev_prev_inv = 1.0;
     bool at_dtmin = false;
     int k = 0, nacc = 0, ntot = 0, st = GX_OK;
-    AX(0) = 0.0; AY(0) = 0.0; AZ(0) = 0.0;
 
+    // Every lane passes the same points of the loop in every iteration (no `continue`): the warp votes below need it.
+    //   1. a lane whose particle is finished (or failed) writes its tail and frees itself;
+    //   2. free lanes pull the next particle from the global ticket;
+    //   3. lanes with a particle attempt one step and run the controller (a rejected lane simply retries next time);
+    //   4. SaveAt: all lanes whose accepted step contains a save time evaluate the dense output TOGETHER, once per
+    //      round of a warp-uniform loop (__any_sync) -- left to the compiler's reconvergence, the same code ran
+    //      with 6 of 32 lanes active and the dense output was a quarter of C2 (ncu, round 2);
+    //   5. accepted lanes advance.
     for (;;) {
+        // ---------------- finished (or failed) particle: write remaining saves, counters, free the lane
+        if (have && (!(tprev < T1) || st != GX_OK || (a.max_steps >= 0 && ntot >= a.max_steps))) {
+            if (tprev < T1 && st == GX_OK) st = GX_MAX_STEPS_REACHED;
+            save_fill_nan(a, idx, k);  // (writes out what is still staged; NaN for saves never reached)
+            k = a.T;
+            if (a.status) a.status[idx] = st;
+            if (a.n_acc) a.n_acc[idx] = nacc;
+            if (a.n_tot) a.n_tot[idx] = ntot;
+            if (a.rec && a.n_rec) *a.n_rec = nacc < a.rec_cap ? nacc : a.rec_cap;
+            have = false;
+        }
         // ---------------- refill idle lanes from the global ticket counter
         if (!have && !exhausted) {
             unsigned long long tk = atomicAdd(a.ticket, 1ULL);
@@ -872,15 +975,13 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                 k = 0; nacc = 0; ntot = 0; st = GX_OK;
                 prev_inv = prev_prev_inv = 1.0;
                 at_dtmin = false;
-                double *qo = a.q + idx * a.sn, *po = a.p + idx * a.sn;
                 tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 while (tsave <= T0) {
-                    qo[k * a.sk] = q0x; qo[k * a.sk + a.sc] = q0y; qo[k * a.sk + 2 * a.sc] = q0z;
-                    po[k * a.sk] = p0x; po[k * a.sk + a.sc] = p0y; po[k * a.sk + 2 * a.sc] = p0z;
+                    save_put(a, idx, k, q0x, q0y, q0z, p0x, p0y, p0z);
                     ++k;
                     tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 }
-                { double t0_, t1_, t2_; accel_call<C>(q0x, q0y, q0z, t0_, t1_, t2_, dir * T0); AX(0) = t0_; AY(0) = t1_; AZ(0) = t2_; }
+                accel_call<C>(q0x, q0y, q0z, fsx, fsy, fsz, dir * T0);
                 // PIDController.init: heuristic when dt0 is None (exponent 1/(error_order + 1), Hairer II.4 -- the
                 // choice that reproduces the reference's 8-digit OrbitSolver doctests), then clamp to [dtmin, dtmax]
                 double h;
@@ -888,7 +989,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     h = a.dt0;
                 } else {
                     const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
-                    const double a0[3] = {AX(0), AY(0), AZ(0)};
+                    const double a0[3] = {fsx, fsy, fsz};
                     h = select_initial_step<C>(P, dir, T0, y, a0, a.rtol, a.atol, 1.0 / (TB::ORDER + 1));
                 }
                 if (a.dtmax > 0.0) h = fmin(h, a.dtmax);
@@ -899,28 +1000,18 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
             }
         }
         if (__all_sync(FULL, !have)) break;
-        if (!have) continue;
-
-        // ---------------- finished (or failed) particle: write remaining saves, counters, free the lane
-        if (!(tprev < T1) || st != GX_OK || (a.max_steps >= 0 && ntot >= a.max_steps && tprev < T1)) {
-            if (tprev < T1 && st == GX_OK) st = GX_MAX_STEPS_REACHED;
-            double *qo = a.q + idx * a.sn, *po = a.p + idx * a.sn;
-            for (; k < a.T; ++k) {
-                qo[k * a.sk] = NANV; qo[k * a.sk + a.sc] = NANV; qo[k * a.sk + 2 * a.sc] = NANV;
-                po[k * a.sk] = NANV; po[k * a.sk + a.sc] = NANV; po[k * a.sk + 2 * a.sc] = NANV;
-            }
-            if (a.status) a.status[idx] = st;
-            if (a.n_acc) a.n_acc[idx] = nacc;
-            if (a.n_tot) a.n_tot[idx] = ntot;
-            if (a.rec && a.n_rec) *a.n_rec = nacc < a.rec_cap ? nacc : a.rec_cap;
-            have = false;
-            continue;
-        }
-
-        // ---------------- one attempted step of size h from (tprev, y0)
+        const bool run = have && (tprev < T1) && st == GX_OK && !(a.max_steps >= 0 && ntot >= a.max_steps);
         const double h = tnext - tprev;
         const double hd = h * dir;  // signed step in physical time
         const double hd2 = hd * hd;
+        bool keep = false;
+        double dt = 0.0, inv = 1.0, q1x = 0, q1y = 0, q1z = 0, p1x = 0, p1y = 0, p1z = 0;
+        // stage accelerations of THIS attempt (dead at the end of the iteration: declared here so that nothing but the
+        // FSAL value is loop-carried and the register allocator need not keep 42 doubles in place across the back edge)
+        double rx[NS], ry[NS], rz_[NS];
+        AX(0) = fsx; AY(0) = fsy; AZ(0) = fsz;
+        if (run) {
+        // ---------------- one attempted step of size h from (tprev, y0)
         double sx = 0, sy = 0, sz = 0;
 #pragma unroll
         for (int i = 1; i < NS; ++i) {
@@ -941,7 +1032,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
             { double t0_, t1_, t2_; accel_call<C>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
             if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1
         }
-        const double q1x = sx, q1y = sy, q1z = sz;
+        q1x = sx; q1y = sy; q1z = sz;
         double bx = 0, by = 0, bz = 0, epx = 0, epy = 0, epz = 0, eqx = 0, eqy = 0, eqz = 0;
 #pragma unroll
         for (int l = 0; l < NS; ++l) {
@@ -949,7 +1040,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
             if (TB::E_NZ(l)) { epx = fma(TB::E(l), AX(l), epx); epy = fma(TB::E(l), AY(l), epy); epz = fma(TB::E(l), AZ(l), epz); }
             if (TB::EA_NZ(l)) { eqx = fma(TB::EA(l), AX(l), eqx); eqy = fma(TB::EA(l), AY(l), eqy); eqz = fma(TB::EA(l), AZ(l), eqz); }
         }
-        const double p1x = fma(hd, bx, p0x), p1y = fma(hd, by, p0y), p1z = fma(hd, bz, p0z);
+        p1x = fma(hd, bx, p0x); p1y = fma(hd, by, p0y); p1z = fma(hd, bz, p0z);
         ++ntot;
 
         // ---------------- PID controller (diffrax PIDController.adapt_step_size)
@@ -965,9 +1056,9 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         ms = fma(e1, e1, ms); ms = fma(e2, e2, ms); ms = fma(e3, e3, ms); ms = fma(e4, e4, ms); ms = fma(e5, e5, ms);
         ms *= (1.0 / 6.0);
         const bool bad = !(ms <= 1.7976931348623157e308);  // NaN or inf error estimate -> reject, shrink
-        bool keep = !bad && ms < 1.0;
+        keep = !bad && ms < 1.0;
         if (a.dtmin > 0.0) keep = keep || at_dtmin;
-        double factor, inv = 1.0;
+        double factor;
         if (simple_i) {
             // I-controller (diffrax default pcoeff = dcoeff = 0, icoeff = 1):
             // factor = safety * serr^(-1/8) = safety * ms^(-1/16), by one rsqrt and three square roots
@@ -989,7 +1080,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         }
         const double fmin_ = keep ? 1.0 : a.factormin;
         factor = fmin(fmax(factor, fmin_), a.factormax);
-        double dt = h * factor;
+        dt = h * factor;
         if (inv == 0.0 || isinf(inv)) { inv = 1.0; prev_inv = 1.0; }
         if (a.dtmax > 0.0) dt = fmin(dt, a.dtmax);
         if (a.dtmin > 0.0) { at_dtmin = dt <= a.dtmin; dt = fmax(dt, a.dtmin); }
@@ -1006,50 +1097,59 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     st = GX_MAX_STEPS_REACHED;  // record buffer exhausted
                 }
             }
-            // ------------ SaveAt(ts): degree-6 continuous extension on the accepted step
-            if (tsave <= tnext) {
-                double *qo = a.q + idx * a.sn, *po = a.p + idx * a.sn;
-                while (tsave <= tnext) {
-                    const double th = (tsave - tprev) / (tnext - tprev);
-                    double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
+        }
+        }  // if (run)
+
+        // ---------------- SaveAt(ts): degree-6 continuous extension on the accepted step, warp-converged
+        bool want = keep && (tsave <= tnext);
+        while (__any_sync(FULL, want)) {
+            if (want) {
+                const double th = (tsave - tprev) / (tnext - tprev);
+                double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
 #pragma unroll
-                    for (int l = 0; l < NS; ++l) {
-                        if (dq_row_nz<TB>(l)) {
-                            double w = TB::DQ(l, 5);
+                for (int l = 0; l < NS; ++l) {
+                    if (dq_row_nz<TB>(l)) {
+                        double w = TB::DQ(l, 5);
 #pragma unroll
-                            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DQ(l, m));
-                            w *= th;
-                            wqx = fma(w, AX(l), wqx); wqy = fma(w, AY(l), wqy); wqz = fma(w, AZ(l), wqz);
-                        }
-                        if (db_row_nz<TB>(l)) {
-                            double w = TB::DB(l, 5);
-#pragma unroll
-                            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DB(l, m));
-                            w *= th;
-                            wpx = fma(w, AX(l), wpx); wpy = fma(w, AY(l), wpy); wpz = fma(w, AZ(l), wpz);
-                        }
+                        for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DQ(l, m));
+                        w *= th;
+                        wqx = fma(w, AX(l), wqx); wqy = fma(w, AY(l), wqy); wqz = fma(w, AZ(l), wqz);
                     }
-                    const double thh = th * hd;
-                    qo[k * a.sk] = fma(hd2, wqx, fma(thh, p0x, q0x));
-                    qo[k * a.sk + a.sc] = fma(hd2, wqy, fma(thh, p0y, q0y));
-                    qo[k * a.sk + 2 * a.sc] = fma(hd2, wqz, fma(thh, p0z, q0z));
-                    po[k * a.sk] = fma(hd, wpx, p0x);
-                    po[k * a.sk + a.sc] = fma(hd, wpy, p0y);
-                    po[k * a.sk + 2 * a.sc] = fma(hd, wpz, p0z);
-                    ++k;
-                    tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+                    if (db_row_nz<TB>(l)) {
+                        double w = TB::DB(l, 5);
+#pragma unroll
+                        for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DB(l, m));
+                        w *= th;
+                        wpx = fma(w, AX(l), wpx); wpy = fma(w, AY(l), wpy); wpz = fma(w, AZ(l), wpz);
+                    }
                 }
+                const double thh = th * hd;
+                const SaveDst d = save_dst(a, idx, k);
+                d.q[0] = fma(hd2, wqx, fma(thh, p0x, q0x));
+                d.q[d.st] = fma(hd2, wqy, fma(thh, p0y, q0y));
+                d.q[2 * d.st] = fma(hd2, wqz, fma(thh, p0z, q0z));
+                d.p[0] = fma(hd, wpx, p0x);
+                d.p[d.st] = fma(hd, wpy, p0y);
+                d.p[2 * d.st] = fma(hd, wpz, p0z);
+                save_commit(a, idx, k);
+                ++k;
+                tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+                want = tsave <= tnext;
             }
+        }
+        if (keep) {
             q0x = q1x; q0y = q1y; q0z = q1z; p0x = p1x; p0y = p1y; p0z = p1z;
-            AX(0) = AX(NS - 1); AY(0) = AY(NS - 1); AZ(0) = AZ(NS - 1);
+            fsx = AX(NS - 1); fsy = AY(NS - 1); fsz = AZ(NS - 1);
             prev_prev_inv = prev_inv;
             prev_inv = inv;
             tprev = tnext;
             ++nacc;
-            if (!(finite3(q0x, q0y, q0z) && finite3(p0x, p0y, p0z))) st = GX_NONFINITE;
+            if (!finite6(q0x, q0y, q0z, p0x, p0y, p0z)) st = GX_NONFINITE;
         }
-        if (tprev > T1) tprev = T1;
-        tnext = clip_to_end(tprev, tprev + dt, T1, keep);
+        if (run) {
+            if (tprev > T1) tprev = T1;
+            tnext = clip_to_end(tprev, tprev + dt, T1, keep);
+        }
     }
 #undef AX
 #undef AY
@@ -1285,6 +1385,14 @@ __global__ void k_debug_math(int op, const GammaTab *gt, const double *tab, cons
 // ================================================================================================
 using namespace gx;
 
+// launch with `dyn` bytes of dynamic shared memory on top of the kernel's static tables (together they may exceed the
+// 48 KB a kernel gets without opting in; the attribute is per device, so it is set on every such launch)
+template <auto Kern, class... Args>
+static inline void launch_dyn(int grid, int block, size_t dyn, cudaStream_t s, const Args &...args) {
+    if (dyn) cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    Kern<<<grid, block, dyn, s>>>(args...);
+}
+
 // gx_strict.cu (compiled with -fmad=false): the reference-order kernels behind GX_SCHEME_STRICT
 int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
                               double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
@@ -1307,6 +1415,7 @@ const char *gx_strerror(int code) {
 int64_t gx_workspace_bytes(void) { return 256; }
 
 static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
 
 static void out_strides(int layout, long long N, int T, long long &sn, long long &sk, long long &sc) {
     if (layout == GX_LAYOUT_T3N) { sn = 1; sk = 3 * N; sc = N; }
@@ -1386,36 +1495,38 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
     const bool fwd = dir > 0;
+    const size_t dyn = save_stage_bytes(layout, T, block);  // per-lane staging of the saves (0: direct stores)
+    a.stage = dyn != 0;
     if (seg_ok) {
         switch (model) {
         case MODEL_MW:
-            if (fwd) k_integrate_fixed_seg<CountsMW, true><<<grid, block, 0, s>>>(D, a, sg);
-            else k_integrate_fixed_seg<CountsMW, false><<<grid, block, 0, s>>>(D, a, sg);
+            if (fwd) launch_dyn<k_integrate_fixed_seg<CountsMW, true>>(grid, block, dyn, s, D, a, sg);
+            else launch_dyn<k_integrate_fixed_seg<CountsMW, false>>(grid, block, dyn, s, D, a, sg);
             break;
         case MODEL_MW2022:
-            if (fwd) k_integrate_fixed_seg<CountsMW2022, true><<<grid, block, 0, s>>>(D, a, sg);
-            else k_integrate_fixed_seg<CountsMW2022, false><<<grid, block, 0, s>>>(D, a, sg);
+            if (fwd) launch_dyn<k_integrate_fixed_seg<CountsMW2022, true>>(grid, block, dyn, s, D, a, sg);
+            else launch_dyn<k_integrate_fixed_seg<CountsMW2022, false>>(grid, block, dyn, s, D, a, sg);
             break;
         case MODEL_BOVY:
-            if (fwd) k_integrate_fixed_seg<CountsBovy, true><<<grid, block, 0, s>>>(D, a, sg);
-            else k_integrate_fixed_seg<CountsBovy, false><<<grid, block, 0, s>>>(D, a, sg);
+            if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBovy, true>>(grid, block, dyn, s, D, a, sg);
+            else launch_dyn<k_integrate_fixed_seg<CountsBovy, false>>(grid, block, dyn, s, D, a, sg);
             break;
         default:  // runtime composite, no time-dependent parameter
             if (is_basic_composite(D, model)) {
-                if (fwd) k_integrate_fixed_seg<CountsBasic, true><<<grid, block, 0, s>>>(D, a, sg);
-                else k_integrate_fixed_seg<CountsBasic, false><<<grid, block, 0, s>>>(D, a, sg);
+                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasic, true>>(grid, block, dyn, s, D, a, sg);
+                else launch_dyn<k_integrate_fixed_seg<CountsBasic, false>>(grid, block, dyn, s, D, a, sg);
             } else {
-                if (fwd) k_integrate_fixed_seg<CountsRuntime, true><<<grid, block, 0, s>>>(D, a, sg);
-                else k_integrate_fixed_seg<CountsRuntime, false><<<grid, block, 0, s>>>(D, a, sg);
+                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsRuntime, true>>(grid, block, dyn, s, D, a, sg);
+                else launch_dyn<k_integrate_fixed_seg<CountsRuntime, false>>(grid, block, dyn, s, D, a, sg);
             }
             break;
         }
     } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
-        if (fwd) { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, true><<<grid, block, 0, s>>>(D, a))); }
-        else { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, false><<<grid, block, 0, s>>>(D, a))); }
+        if (fwd) { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, true>>(grid, block, dyn, s, D, a))); }
+        else { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, false>>(grid, block, dyn, s, D, a))); }
     } else {
-        if (fwd) { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, true><<<grid, block, 0, s>>>(D, a))); }
-        else { GX_DISPATCH_MODEL(model, (k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, false><<<grid, block, 0, s>>>(D, a))); }
+        if (fwd) { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, true>>(grid, block, dyn, s, D, a))); }
+        else { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, false>>(grid, block, dyn, s, D, a))); }
     }
     return cuda_rc(cudaGetLastError());
 }
@@ -1486,6 +1597,8 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     // persistent launch: resident CTAs only (occupancy query), never more lanes than particles; small batches
     // use narrow CTAs so that the few particles spread over all SMs.
     const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
+    const size_t dyn = save_stage_bytes(layout, T, block);  // per-lane staging of the saves (0: direct stores)
+    a.stage = dyn != 0;
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1493,11 +1606,12 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     do {                                                                                                      \
         auto kern = (solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5>                             \
                                                  : k_integrate_dopri8<C_, TabDp8>;                            \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);                               \
+        if (dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);           \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, dyn);                             \
         if (per_sm < 1) per_sm = 1;                                                                           \
         long long want = (N + block - 1) / block, resident = (long long)per_sm * sms;                         \
         int grid = (int)(want < resident ? want : resident);                                                  \
-        kern<<<grid, block, 0, s>>>(D, a);                                                                    \
+        kern<<<grid, block, dyn, s>>>(D, a);                                                                  \
     } while (0)
 #if GX_DP8_CONST_POT
     if ((rc = stage_const_pot(D, s)) != 0) return rc;

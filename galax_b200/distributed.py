@@ -87,4 +87,71 @@ def integrate_sharded(integrate_fn: Callable, q0, p0, *, group=None, gather: boo
     q, p = integrate_fn(local_shard(q0, rank, world), local_shard(p0, rank, world))
     if not gather or world == 1:
         return q, p
-    return all_gather_ragged(q, n, group), all_gather_ragged(p, n, group)
+    import torch
+
+    qp = all_gather_ragged(torch.stack([q, p], dim=0), n, group, dim=1)  # ONE collective for both halves
+    return qp[0], qp[1]
+
+
+class ResultGather:
+    """The job's only collective, once per step and off the critical path.
+
+    A rank's result shard -- q and p, each ``(n_local, T, 3)`` -- lives in ONE buffer ``[2, n_max, T, 3]`` whose two
+    halves the integrator kernels write directly (``views(k)``), so a step needs a single ``all_gather_into_tensor``
+    instead of one per half.  ``start(k)`` issues it asynchronously (NCCL: on the communicator's own stream, ordered
+    after the kernels already queued on the current stream), so the gather of step k runs under the kernel of step
+    k + 1; ``depth`` buffers alternate so that a running gather is never overwritten.  Shards may be ragged
+    (``shard_bounds``): every rank's slot is ``n_max`` rows, ``result(k)`` drops the padding.
+
+    Works on any backend (``gloo`` with CPU tensors in the tests)."""
+
+    def __init__(self, n_total: int, T: int, *, device, dtype=None, group=None, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bounds = shard_bounds(n_total, self.world)
+        self.n_local = self.bounds[self.rank][1] - self.bounds[self.rank][0]
+        self.n_max = max(hi - lo for lo, hi in self.bounds)
+        dtype = dtype or torch.float64
+        self.local = [torch.zeros((2, self.n_max, T, 3), dtype=dtype, device=device) for _ in range(depth)]
+        self.full = [torch.empty((self.world * 2, self.n_max, T, 3), dtype=dtype, device=device) if self.world > 1
+                     else None for _ in range(depth)]  # fmt: skip
+        self.work = [None] * depth
+        self.depth = depth
+
+    def views(self, k: int):
+        """(q, p) views of buffer k for this rank's kernels to write: each ``(n_local, T, 3)``, contiguous."""
+        buf = self.local[k % self.depth]
+        return buf[0, : self.n_local], buf[1, : self.n_local]
+
+    def start(self, k: int):
+        """Issue the gather of step k (asynchronously).  Waits first for the gather that last used this buffer."""
+        import torch.distributed as dist
+
+        i = k % self.depth
+        if self.world == 1:
+            return None
+        self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
+        return self.work[i]
+
+    def wait(self, k: int | None = None):
+        for i in range(self.depth) if k is None else [k % self.depth]:
+            if self.work[i] is not None:
+                self.work[i].wait()
+                self.work[i] = None
+
+    def result(self, k: int):
+        """Full ``(N, T, 3)`` q and p of step k on every rank (waits for its gather)."""
+        import torch
+
+        i = k % self.depth
+        self.wait(k)
+        if self.world == 1:
+            return self.views(k)
+        full = self.full[i].view(self.world, 2, self.n_max, *self.full[i].shape[2:])
+        parts = [full[r, :, : hi - lo] for r, (lo, hi) in enumerate(self.bounds)]
+        qp = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        return qp[0], qp[1]

@@ -51,6 +51,21 @@ def _worker(rank, world, port, n, tmp):
         qs, ps = gdist.integrate_sharded(fn, torch.from_numpy(q0), torch.from_numpy(p0), gather=False)
         lo, hi = gdist.shard_bounds(n, world)[rank]
         assert qs.shape[0] == hi - lo and torch.equal(q[lo:hi], qs)
+        # the packed, asynchronous form of the same gather (what bench.py uses): two steps in flight
+        g = gdist.ResultGather(n, len(ts), device="cpu", depth=2)
+        assert g.n_local == hi - lo
+        for k in range(3):
+            qv, pv = g.views(k)
+            qv.copy_(qs + k)
+            pv.copy_(ps - k)
+            if k >= 2:
+                g.wait(k)  # buffer reuse: the gather of step k - 2 must be complete (it was consumed below)
+            g.start(k)
+            if k >= 1:
+                qa, pa = g.result(k - 1)
+                assert torch.equal(qa, q + (k - 1)) and torch.equal(pa, p - (k - 1))
+        qa, pa = g.result(2)
+        assert torch.equal(qa, q + 2) and torch.equal(pa, p - 2)
         torch.save((q, p), f"{tmp}/out{rank}.pt")
         dist.barrier()
     finally:

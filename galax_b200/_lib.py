@@ -157,7 +157,8 @@ _SIGNATURES = {
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gx_bench_dfma": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "gx_jax_normal": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
-    "gx_jax_fardal_chain": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "gx_jax_fardal_chain": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_jax_fardal_chain_workspace_bytes": (C.c_int64, [C.c_int64]),
     "gx_debug_math": (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "gx_force_table": (C.c_int, [C.c_int32, C.c_double, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),

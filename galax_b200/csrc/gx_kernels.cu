@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/galax_b200.h"
 #include "gx_potential.cuh"
@@ -86,6 +87,10 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
             m.a = c.p[1];
             m.b2 = c.p[2] * c.p[2];
             m.ab2 = c.p[1] * m.b2;
+            // b = 0 (KuzminPotential): zeta = sqrt(z^2 + b^2) vanishes in the disk plane and 0 * (1/0) would be NaN.
+            // With the smallest normal number under the root the in-plane z-force is exactly 0, as the reference's
+            // |z| form gives (builtin/kuzmin.py:82-84); for b > 0 nothing changes (b^2 + tiny == b^2).
+            if (m.b2 == 0.0) m.b2 = 2.2250738585072014e-308;
             break;
         }
         case GX_KIND_HERNQUIST: {
@@ -150,6 +155,7 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
             m.a = c.p[1];
             m.b2 = c.p[2] * c.p[2];
             m.ab2 = c.p[1] * m.b2;
+            if (m.b2 == 0.0) m.b2 = 2.2250738585072014e-308;  // (as for Miyamoto-Nagai above)
             break;
         }
         case GX_KIND_TRIAXIAL_HERNQUIST:
@@ -230,6 +236,7 @@ struct EvalArgs {
     double *phi, *grad, *acc, *hess;
     long long N;
     unsigned what;
+    int tma_ok;  // every tile address is 16-byte aligned: full tiles may move by cp.async.bulk (else plain loads/stores)
 };
 
 // Light outputs (Phi / grad / acc only): one thread per point, direct loads and stores; the 24-byte stride
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(TILE) k_potential_eval(const __grid_constant__
     const int tid = threadIdx.x;
     const long long n_tiles = (a.N + TILE - 1) / TILE;
     auto tile_cnt = [&](long long t) { long long r = a.N - t * TILE; return (int)(r < TILE ? r : TILE); };
+    auto tile_full = [&](long long t) { return a.tma_ok && tile_cnt(t) == TILE; };  // moved by the TMA engine
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(TILE) k_potential_eval(const __grid_constant__
     }
     __syncthreads();
     long long tile = blockIdx.x;
-    if (tid == 0 && tile < n_tiles && tile_cnt(tile) == TILE) {
+    if (tid == 0 && tile < n_tiles && tile_full(tile)) {
         mbar_expect_tx(&bar[0], TILE * 24);
         tma_load_1d(s_in, a.xyz + tile * TILE * 3, TILE * 24, &bar[0]);
     }
@@ -322,11 +330,11 @@ __global__ void __launch_bounds__(TILE) k_potential_eval(const __grid_constant__
         const int stage = it & 1;
         const long long base = tile * TILE;
         const int cnt = tile_cnt(tile);
-        const bool full = (cnt == TILE);
+        const bool full = tile_full(tile);
         const long long next = tile + gridDim.x;
         double *in = s_in + stage * TILE * 3, *out = s_out + stage * per_stage;
         if (tid == 0) {
-            if (next < n_tiles && tile_cnt(next) == TILE) {  // prefetch the next tile's positions
+            if (next < n_tiles && tile_full(next)) {  // prefetch the next tile's positions
                 mbar_expect_tx(&bar[stage ^ 1], TILE * 24);
                 tma_load_1d(s_in + (stage ^ 1) * TILE * 3, a.xyz + next * TILE * 3, TILE * 24, &bar[stage ^ 1]);
             }
@@ -818,60 +826,56 @@ __device__ __forceinline__ void accel(const DevPot &P, double x, double y, doubl
 // Out-of-line right-hand side for the Dopri8 kernel: 13 inlined copies of the gradient make the step body
 // ~100 KB of SASS, far beyond the 32 KB instruction cache (ncu: "no_instruction" was the top stall), so the callee
 // takes no pointer argument and finds the potential parameters itself (constant or shared memory, next paragraph).
-// Parameters of the out-of-line RHS live in __constant__ memory (GX_DP8_CONST_POT=1, default): inside the callee they
-// are constant-bank operands of the FP64 instructions instead of ~30 shared-memory loads per call (measured: -6.5 %
-// on the Dopri8 step).  One image per device, managed by stage_const_pot() below; GX_DP8_CONST_POT=0 stages the
-// parameters in shared memory once per CTA instead.
-#ifndef GX_DP8_CONST_POT
-#define GX_DP8_CONST_POT 1
-#endif
-#if GX_DP8_CONST_POT
+// Where the out-of-line RHS finds the potential: template parameter IMG.
+//   IMG = true   a __constant__ image (c_pot_dp8): inside the callee the parameters are constant-bank operands of the
+//                FP64 instructions instead of ~30 shared-memory loads per call (measured: -6.5 % on the Dopri8 step).
+//                One image per device, shared by every launch: use_const_image() below decides, without ever blocking,
+//                whether a launch may use it.
+//   IMG = false  the kernel copies its own __grid_constant__ parameter into shared memory once per CTA: no state
+//                outside the launch.  Used whenever the image is busy with another potential on another stream, and
+//                always under CUDA-graph capture.
 __constant__ DevPot c_pot_dp8;
-#endif
 template <class C>
 __device__ __forceinline__ DevPot *pot_smem() {
     __shared__ DevPot sP;
     return &sP;
 }
-template <class C>
+template <class C, bool IMG>
 __device__ __forceinline__ const DevPot &rhs_pot() {
-#if GX_DP8_CONST_POT
-    return c_pot_dp8;
-#else
-    return *pot_smem<C>();
-#endif
+    if constexpr (IMG) return c_pot_dp8;
+    else return *pot_smem<C>();
 }
 // The callees return the acceleration BY VALUE (three doubles in registers): with reference parameters the results
 // went through the caller's local-memory frame (3 STL + 3 LDL + the generic-to-local address arithmetic per call).
 struct Acc3 { double x, y, z; };
-template <class C>
+template <class C, bool IMG>
 __device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
     // (handing the table's shared-window address down in a register instead of re-deriving it here -- S2R + LEA + ISETP
     // + MOV per call -- was measured: the extra live register costs the Dopri8 kernel 40 bytes of spills)
     double g0, g1, g2;
     unsigned nfw_base = 0;  // the kernel prologue staged the NFW force table (nfw_stage)
     if constexpr (nfw_tab_ok<C>()) nfw_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
-    gradient<C, (C::is_static && C::kPLC > 0), nfw_tab_ok<C>()>(rhs_pot<C>(), x, y, z, g0, g1, g2, 0.0, nfw_base);
+    gradient<C, (C::is_static && C::kPLC > 0), nfw_tab_ok<C>()>(rhs_pot<C, IMG>(), x, y, z, g0, g1, g2, 0.0, nfw_base);
     return Acc3{-g0, -g1, -g2};
 }
 // runtime composites may be time dependent (LinearParameter): the callee also receives the physical time
-template <class C>
+template <class C, bool IMG>
 __device__ __noinline__ Acc3 accel_call_timed(double t, double x, double y, double z) {
     double g0, g1, g2;
-    gradient<C, false>(rhs_pot<C>(), x, y, z, g0, g1, g2, t);
+    gradient<C, false>(rhs_pot<C, IMG>(), x, y, z, g0, g1, g2, t);
     return Acc3{-g0, -g1, -g2};
 }
-template <class C>
+template <class C, bool IMG>
 __device__ __forceinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az, double t) {
     Acc3 a;
-    if constexpr (C::is_static || C::basic_only) a = accel_call_static<C>(x, y, z);
-    else a = accel_call_timed<C>(t, x, y, z);
+    if constexpr (C::is_static || C::basic_only) a = accel_call_static<C, IMG>(x, y, z);
+    else a = accel_call_timed<C, IMG>(t, x, y, z);
     ax = a.x; ay = a.y; az = a.z;
 }
 
 // Hairer-Norsett-Wanner initial step as restated by diffrax (_select_initial_step); inv_order = 1 / error order.
 // Works in tau = dir*t: f = dir * (p, a).
-template <class C>
+template <class C, bool IMG>
 __device__ double select_initial_step(const DevPot &P, double dir, double tau0, const double y[6], const double a0[3],
                                       double rtol, double atol, double inv_order) {
     double f0[6] = {y[3] * dir, y[4] * dir, y[5] * dir, a0[0] * dir, a0[1] * dir, a0[2] * dir};
@@ -890,7 +894,7 @@ __device__ double select_initial_step(const DevPot &P, double dir, double tau0, 
 #pragma unroll
     for (int i = 0; i < 6; ++i) y1[i] = y[i] + h0 * f0[i];
     double a1x, a1y, a1z;
-    accel_call<C>(y1[0], y1[1], y1[2], a1x, a1y, a1z, dir * (tau0 + h0));
+    accel_call<C, IMG>(y1[0], y1[1], y1[2], a1x, a1y, a1z, dir * (tau0 + h0));
     double f1[6] = {y1[3] * dir, y1[4] * dir, y1[5] * dir, a1x * dir, a1y * dir, a1z * dir};
 #pragma unroll
     for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
@@ -910,18 +914,16 @@ constexpr int REC_DOUBLES = GX_DENSE_RECORD_DOUBLES;  // tprev, tnext, hd, q0[3]
 // alternatives on B200 (MW2022, rtol = atol = 1e-10, 3e5 particles): everything inlined with the stages in
 // registers 161 ms (I-cache bound: 105 KB of SASS); stages in shared memory 151-205 ms; this version 121 ms.
 // TB = TabDp8 (diffrax.Dopri8) or TabDp5 (diffrax.Dopri5): same kernel, tableau resolved at compile time.
-template <class C, class TB>
+template <class C, class TB, bool IMG>
 __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
 k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     constexpr int NS = TB::NS;
-#if !GX_DP8_CONST_POT
-    {   // stage the potential parameters in shared memory for accel_call()
+    if constexpr (!IMG) {  // stage the potential parameters in shared memory for accel_call()
         const double *src = reinterpret_cast<const double *>(&P);
         double *dst = reinterpret_cast<double *>(pot_smem<C>());
         for (int w = threadIdx.x; w < (int)(sizeof(DevPot) / sizeof(double)); w += blockDim.x) dst[w] = src[w];
         __syncthreads();
     }
-#endif
     plc_stage<C>(P);  // (Bovy) the PowerLawCutoff table, read by accel_call()
     (void)nfw_stage<C, nfw_tab_ok<C>()>(P);  // (MW, MW2022) the NFW force table, likewise
     const unsigned FULL = 0xffffffffu;
@@ -981,7 +983,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     ++k;
                     tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 }
-                accel_call<C>(q0x, q0y, q0z, fsx, fsy, fsz, dir * T0);
+                accel_call<C, IMG>(q0x, q0y, q0z, fsx, fsy, fsz, dir * T0);
                 // PIDController.init: heuristic when dt0 is None (exponent 1/(error_order + 1), Hairer II.4 -- the
                 // choice that reproduces the reference's 8-digit OrbitSolver doctests), then clamp to [dtmin, dtmax]
                 double h;
@@ -990,7 +992,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                 } else {
                     const double y[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
                     const double a0[3] = {fsx, fsy, fsz};
-                    h = select_initial_step<C>(P, dir, T0, y, a0, a.rtol, a.atol, 1.0 / (TB::ORDER + 1));
+                    h = select_initial_step<C, IMG>(P, dir, T0, y, a0, a.rtol, a.atol, 1.0 / (TB::ORDER + 1));
                 }
                 if (a.dtmax > 0.0) h = fmin(h, a.dtmax);
                 if (a.dtmin > 0.0) { at_dtmin = h <= a.dtmin; h = fmax(h, a.dtmin); }
@@ -1029,7 +1031,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
             const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
             const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
             const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
-            { double t0_, t1_, t2_; accel_call<C>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
+            { double t0_, t1_, t2_; accel_call<C, IMG>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
             if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1
         }
         q1x = sx; q1y = sy; q1z = sz;
@@ -1433,7 +1435,12 @@ int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int6
     if (((what & GX_PHI) && !phi) || ((what & GX_GRAD) && !grad) || ((what & GX_ACC) && !acc) ||
         ((what & GX_HESS) && !hess))
         return GX_ERR_BADARG;
-    EvalArgs a{xyz, phi, grad, acc, hess, (long long)N, what};
+    // cp.async.bulk needs 16-byte aligned global addresses; a tile starts 256 * 24 (or 72) bytes after the previous one,
+    // so the bases decide.  Odd-row views of an [N,3] array (xyz[1:]) are only 8-byte aligned: plain path for those.
+    const uintptr_t al = (uintptr_t)xyz | ((what & GX_GRAD) ? (uintptr_t)grad : 0) | ((what & GX_ACC) ? (uintptr_t)acc : 0) |
+                         ((what & GX_HESS) ? (uintptr_t)hess : 0);
+    if (al & 7) return GX_ERR_BADARG;
+    EvalArgs a{xyz, phi, grad, acc, hess, (long long)N, what, (al & 15) == 0};
     const int block = EVAL_TILE;
     long long want = (N + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1535,34 +1542,74 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
 
 // Shared implementation of every adaptive entry point: `solver` picks the tableau, `rec` (optional) switches the
 // kernel from saving to recording accepted steps.
-#if GX_DP8_CONST_POT
-// The __constant__ image of the potential is shared by every launch on a device.  Launches with the image's current
-// content only wait (on their own stream) for the copy that wrote it; a launch with different content first waits for
-// the whole device to drain (kernels on any stream may still be reading the old image), then copies.  Changing the
-// potential between adaptive launches is the rare case, and callers read results back (= synchronise) anyway.
-static int stage_const_pot(const DevPot &D, cudaStream_t s) {
-    constexpr int MAXDEV = 64;
-    static std::mutex mtx;
-    static bool valid[MAXDEV];
-    static DevPot content[MAXDEV];
-    static cudaEvent_t copied[MAXDEV];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return GX_ERR_CUDA;
-    std::lock_guard<std::mutex> lock(mtx);
-    if (!copied[dev] && cudaEventCreateWithFlags(&copied[dev], cudaEventDisableTiming) != cudaSuccess) return GX_ERR_CUDA;
-    if (!valid[dev] || memcmp(&content[dev], &D, sizeof D) != 0) {
-        if (valid[dev] && cudaDeviceSynchronize() != cudaSuccess) return GX_ERR_CUDA;
-        valid[dev] = false;
-        if (cudaMemcpyToSymbolAsync(c_pot_dp8, &D, sizeof D, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return GX_ERR_CUDA;
-        if (cudaEventRecord(copied[dev], s) != cudaSuccess) return GX_ERR_CUDA;
-        memcpy(&content[dev], &D, sizeof D);
-        valid[dev] = true;
-    } else if (cudaStreamWaitEvent(s, copied[dev], 0) != cudaSuccess) {
-        return GX_ERR_CUDA;
+// The __constant__ image of the potential (c_pot_dp8) is shared by every launch on a device, so a launch may only read
+// it when nothing can change it underneath, and may only change it when nobody else can still be reading it.  All of
+// that is decided here WITHOUT blocking the host and without making any stream wait for work it did not depend on:
+//   * the image already holds this potential: the launch's stream waits for the copy that wrote it (an event; a no-op
+//     on the stream that issued the copy) and the kernel reads the image;
+//   * it holds another potential and every launch that read it is finished, or was issued on this very stream (the new
+//     copy is then ordered behind it): the image is rewritten in stream order, the kernel reads it;
+//   * it holds another potential that a launch on ANOTHER stream may still be reading (cudaEventQuery: not ready):
+//     the image is left alone and this launch runs the IMG = false kernel, which carries the potential in its own
+//     kernel parameter (shared-memory copy per CTA; ~6 % slower, no state outside the launch);
+//   * the stream is being captured into a CUDA graph: always the IMG = false kernel (a graph may be replayed at any
+//     time, concurrently with anything).
+// The mutex is held from the decision until the launch's last-use event is recorded, so two host threads cannot
+// interleave "decide" and "launch".
+namespace {
+struct ImgUser { cudaStream_t stream; cudaEvent_t ev; };
+struct ImgState {
+    bool valid = false;
+    DevPot content;
+    cudaEvent_t staged = nullptr;
+    cudaStream_t staged_on = nullptr;
+    std::vector<ImgUser> users;
+};
+constexpr int IMG_MAXDEV = 64;
+std::mutex g_img_mtx;
+ImgState g_img[IMG_MAXDEV];
+}  // namespace
+
+// 1: launch the IMG = true kernel; 0: launch the IMG = false kernel; < 0: error.  Caller holds g_img_mtx.
+static int use_const_image(const DevPot &D, cudaStream_t s, int dev) {
+    if (dev < 0 || dev >= IMG_MAXDEV) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) return GX_ERR_CUDA;
+    if (cap != cudaStreamCaptureStatusNone) return 0;
+    ImgState &I = g_img[dev];
+    if (!I.staged && cudaEventCreateWithFlags(&I.staged, cudaEventDisableTiming) != cudaSuccess) return GX_ERR_CUDA;
+    if (I.valid && memcmp(&I.content, &D, sizeof D) == 0) {
+        if (I.staged_on != s && cudaStreamWaitEvent(s, I.staged, 0) != cudaSuccess) return GX_ERR_CUDA;
+        return 1;
     }
-    return 0;
+    bool busy = false;
+    if (I.valid && I.staged_on != s && cudaEventQuery(I.staged) != cudaSuccess) busy = true;
+    for (const ImgUser &u : I.users)
+        if (u.stream != s && cudaEventQuery(u.ev) != cudaSuccess) busy = true;
+    (void)cudaGetLastError();  // cudaErrorNotReady from the queries is an answer, not an error
+    if (busy) return 0;
+    memcpy(&I.content, &D, sizeof D);
+    I.valid = false;
+    if (cudaMemcpyToSymbolAsync(c_pot_dp8, &I.content, sizeof D, 0, cudaMemcpyHostToDevice, s) != cudaSuccess) return GX_ERR_CUDA;
+    if (cudaEventRecord(I.staged, s) != cudaSuccess) return GX_ERR_CUDA;
+    I.staged_on = s;
+    I.valid = true;
+    for (size_t k = 0; k < I.users.size();) {  // everything on other streams has finished (checked above): retire it
+        if (I.users[k].stream != s) { cudaEventDestroy(I.users[k].ev); I.users[k] = I.users.back(); I.users.pop_back(); }
+        else ++k;
+    }
+    return 1;
 }
-#endif
+// after the launch of an IMG = true kernel on `s`: remember that the image is in use there.  Caller holds g_img_mtx.
+static int const_image_used(cudaStream_t s, int dev) {
+    ImgState &I = g_img[dev];
+    for (ImgUser &u : I.users)
+        if (u.stream == s) return cuda_rc(cudaEventRecord(u.ev, s));
+    ImgUser u{s, nullptr};
+    if (cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming) != cudaSuccess) return GX_ERR_CUDA;
+    I.users.push_back(u);
+    return cuda_rc(cudaEventRecord(u.ev, s));
+}
 
 static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const gx_potential *pot, const gx_pid *pid,
                          const double *q0, const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
@@ -1602,10 +1649,10 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define GX_LAUNCH_DP8(C_)                                                                                     \
+#define GX_LAUNCH_DP8_(C_, IMG_)                                                                              \
     do {                                                                                                      \
-        auto kern = (solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5>                             \
-                                                 : k_integrate_dopri8<C_, TabDp8>;                            \
+        auto kern = (solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5, IMG_>                       \
+                                                 : k_integrate_dopri8<C_, TabDp8, IMG_>;                      \
         if (dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);           \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, dyn);                             \
         if (per_sm < 1) per_sm = 1;                                                                           \
@@ -1613,13 +1660,21 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
         int grid = (int)(want < resident ? want : resident);                                                  \
         kern<<<grid, block, dyn, s>>>(D, a);                                                                  \
     } while (0)
-#if GX_DP8_CONST_POT
-    if ((rc = stage_const_pot(D, s)) != 0) return rc;
-#endif
+#define GX_LAUNCH_DP8(C_)                                                                                     \
+    do {                                                                                                      \
+        if (img) GX_LAUNCH_DP8_(C_, true);                                                                    \
+        else GX_LAUNCH_DP8_(C_, false);                                                                       \
+    } while (0)
+    std::lock_guard<std::mutex> img_lock(g_img_mtx);
+    const int img = use_const_image(D, s, dev);
+    if (img < 0) return img;
     if (is_basic_composite(D, model)) GX_LAUNCH_DP8(CountsBasic);
     else GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
+    rc = cuda_rc(cudaGetLastError());
+    if (rc == 0 && img) rc = const_image_used(s, dev);
+    return rc;
+#undef GX_LAUNCH_DP8_
 #undef GX_LAUNCH_DP8
-    return cuda_rc(cudaGetLastError());
 }
 
 extern "C" {
@@ -1784,32 +1839,33 @@ __global__ void __launch_bounds__(256) k_jax_fardal_per_key(const uint2 *subkeys
     }
 }
 
-int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *stream) {
-    if (M < 0 || (M > 0 && !draws)) return GX_ERR_BADARG;
-    if (M == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    uint2 *h = (uint2 *)malloc((size_t)M * sizeof(uint2));
-    if (!h) return GX_ERR_CUDA;
-    uint32_t a = key_hi, b = key_lo;
-    for (int64_t i = 0; i < M; ++i) {  // key, subkey = split(key): split(key)[c] = threefry(key, counter c)
-        uint32_t n0, n1;
-        threefry2x32(a, b, 0u, 1u, h[i].x, h[i].y);
+// the key chain itself: key, subkey = split(key) -- split(key)[c] = threefry(key, counter c) -- M times in a row.  A hash
+// chain has no parallelism, so ONE device thread walks it (two independent threefry evaluations per link, ~0.15 us a
+// link): slower than a host core, but the entry stays enqueue-only (no host buffer that must outlive an asynchronous
+// copy, no allocation, no synchronisation) and can be captured into a graph.
+__global__ void k_jax_key_chain(uint32_t k0, uint32_t k1, long long M, uint2 *subkeys) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t a = k0, b = k1;
+    for (long long i = 0; i < M; ++i) {
+        uint32_t s0, s1, n0, n1;
+        threefry2x32(a, b, 0u, 1u, s0, s1);
         threefry2x32(a, b, 0u, 0u, n0, n1);
+        subkeys[i] = make_uint2(s0, s1);
         a = n0;
         b = n1;
     }
-    uint2 *d = nullptr;
-    int rc = 0;
-    if (cudaMallocAsync((void **)&d, (size_t)M * sizeof(uint2), s) != cudaSuccess) { free(h); return GX_ERR_CUDA; }
-    if (cudaMemcpyAsync(d, h, (size_t)M * sizeof(uint2), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = GX_ERR_CUDA;
-    if (!rc) {
-        k_jax_fardal_per_key<<<grid_for(M, 256), 256, 0, s>>>(d, (long long)M, draws);
-        rc = cuda_rc(cudaGetLastError());
-    }
-    cudaStreamSynchronize(s);  // the pageable staging buffer must outlive the copy
-    cudaFreeAsync(d, s);
-    free(h);
-    return rc;
+}
+
+int64_t gx_jax_fardal_chain_workspace_bytes(int64_t M) { return M > 0 ? M * (int64_t)sizeof(uint2) : 0; }
+
+int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *workspace, void *stream) {
+    if (M < 0 || (M > 0 && (!draws || !workspace))) return GX_ERR_BADARG;
+    if (M == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint2 *d = (uint2 *)workspace;
+    k_jax_key_chain<<<1, 32, 0, s>>>(key_hi, key_lo, (long long)M, d);
+    k_jax_fardal_per_key<<<grid_for(M, 256), 256, 0, s>>>(d, (long long)M, draws);
+    return cuda_rc(cudaGetLastError());
 }
 
 int gx_fixed_time_grid(double t0, double t1, double dt0, int64_t max_steps, int64_t *n_steps, int32_t *hit_max_steps,

@@ -517,7 +517,7 @@ __device__ __noinline__ void gradient_td(const DevTD &R, double t, double x, dou
         const double GM = R.G * p0;
         switch (R.kind[i]) {
         case 0: {  // Miyamoto-Nagai (m, a, b)
-            const double zeta2 = fma(p2, p2, z2), rz = rsqrt_fast(zeta2), apz = fma(zeta2, rz, p1);
+            const double zeta2 = fma(p2, p2, z2 + TINY), rz = rsqrt_fast(zeta2), apz = fma(zeta2, rz, p1);  // (+tiny: b = 0, z = 0)
             const double rD = rsqrt_fast(fma(apz, apz, R2)), f = (GM * rD) * (rD * rD);
             fxy += f;
             fz = fma(f, apz * rz, fz);
@@ -539,7 +539,7 @@ __device__ __noinline__ void gradient_td(const DevTD &R, double t, double x, dou
             break;
         }
         case 6: {  // Satoh (m, a, b)
-            const double b2 = p2 * p2, zs2 = z2 + b2, rzs = rsqrt_fast(zs2), apz = fma(zs2, rzs, p1);
+            const double b2 = p2 * p2, zs2 = (z2 + TINY) + b2, rzs = rsqrt_fast(zs2), apz = fma(zs2, rzs, p1);
             const double rD = rsqrt_fast(fma(apz, apz, R2 - b2)), f = (GM * rD) * (rD * rD);
             fxy += f;
             fz = fma(f, apz * rzs, fz);

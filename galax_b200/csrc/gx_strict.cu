@@ -85,7 +85,9 @@ __device__ double nfw_menc_shape(double s) {
 __device__ void comp_gradient(double G, const StrictComp &c, double x, double y, double z, double g[3]) {
     const double *p = c.p;
     if (c.kind == GX_KIND_MIYAMOTO_NAGAI) {
-        double zeta = sqrt(z * z + p[2] * p[2]);
+        double b2 = p[2] * p[2];
+        if (b2 == 0.0) b2 = TINY;  // Kuzmin (b = 0): zero z-force in the disk plane, as in oracle/galax_oracle.c
+        double zeta = sqrt(z * z + b2);
         double D2 = x * x + y * y + (p[1] + zeta) * (p[1] + zeta);
         double f = G * p[0] / (D2 * sqrt(D2));
         g[0] = f * x;

@@ -159,11 +159,13 @@ def _fardal_normals(key, M: int):
 
 def _fardal_chain_normals(key_data, M: int):
     """(4, M) normals of the ``StreamSimulator.init`` scan (``key, subkey = jr.split(key)`` per release time, then four
-    scalar normals on ``jr.split(subkey, 4)``): ``gx_jax_fardal_chain`` -- key chain on the host, draws on the device."""
+    scalar normals on ``jr.split(subkey, 4)``): ``gx_jax_fardal_chain`` -- key chain and draws on the device."""
     torch = _lib.require_cuda()
+    L = _lib.lib()
     out = torch.empty((4, M), dtype=torch.float64, device="cuda")
-    rc = _lib.lib().gx_jax_fardal_chain(int(key_data[0]), int(key_data[1]), M, out.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream)
+    ws = torch.empty((max(int(L.gx_jax_fardal_chain_workspace_bytes(M)), 8) // 8,), dtype=torch.int64, device="cuda")
+    rc = L.gx_jax_fardal_chain(int(key_data[0]), int(key_data[1]), M, out.data_ptr(), ws.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "gx_jax_fardal_chain")
     return out
 

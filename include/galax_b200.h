@@ -13,9 +13,16 @@
  *   - return value: 0 on success, <0 on an argument / CUDA error (gx_strerror); per-particle
  *     outcomes (max_steps reached, non-finite state) are reported in the `status` array;
  *   - units: whatever unit system the potential parameters are expressed in (galax: kpc, Myr, Msun);
- *   - re-entrant: the potential is passed by value into each launch (kernel-parameter constant bank); the only
- *     process-wide state is an append-only, mutex-guarded cache of immutable PowerLawCutoff force tables
- *     (12.5 KB of device memory per device and exponent, allocated on first use).
+ *   - re-entrant and safe to call from several host threads / on several streams: the potential is passed by value
+ *     into each launch (kernel-parameter constant bank).  Process-wide state: (1) an append-only, mutex-guarded cache
+ *     of immutable force tables (NFW 30 KB, PowerLawCutoff 35 KB per exponent; device memory, allocated on FIRST use --
+ *     the one allocation an enqueue-only entry can make, so warm an entry up once before capturing it into a graph);
+ *     (2) for the adaptive integrators, a per-device __constant__ copy of the potential that a launch reads only when
+ *     no launch on another stream can still be reading a different one -- otherwise, and always under stream capture,
+ *     the launch carries the potential itself (same results, a few per cent slower).  No entry ever blocks the host
+ *     or synchronises a stream with work it does not depend on;
+ *   - alignment: every pointer must be aligned to its element type (8 bytes for fp64); gx_potential_eval is fastest
+ *     when xyz / grad / acc / hess are 16-byte aligned (TMA bulk copies) and takes a plain load/store path otherwise.
  */
 #ifndef GALAX_B200_H
 #define GALAX_B200_H
@@ -120,8 +127,8 @@ int gx_version(void);
 
 /* Bulk evaluation.  Replaces pot.potential/gradient/acceleration/hessian on (N,3) arrays:
  * potential/_src/register_funcs.py:33-98,276-288,327-340 -> AbstractCompositePotential._gradient/_hessian
- * (base_multi.py:48-82).  Unrequested outputs may be NULL.  `t` is accepted for signature parity; the
- * supported parameters are time-independent (ConstantParameter). */
+ * (base_multi.py:48-82).  Unrequested outputs may be NULL.  Parameters with a rate (LinearParameter, gx_component.dp)
+ * are evaluated at `t`; constant parameters ignore it. */
 int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what, double *phi,
                       double *grad, double *acc, double *hess, void *stream);
 
@@ -234,9 +241,11 @@ int gx_bench_dfma(int32_t blocks, int32_t threads, int64_t iters, double *sink, 
 int gx_jax_normal(uint32_t key_hi, uint32_t key_lo, int64_t n, double *out, void *stream);
 /* The draws of the experimental StreamSimulator.init scan (experimental/stream.py:212-226, experimental/df.py:146-163):
  * `for i in range(M): key, subkey = jr.split(key); Fardal2015DF.sample(subkey, ...)`, each sample being four scalar
- * normals `jr.normal(k_j, ())` on `jr.split(subkey, 4)`.  The key chain is inherently sequential and runs on the host
- * (integer arithmetic, ~50 ns per link); the 4 M normals are computed on the device.  draws: device [4][M]. */
-int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *stream);
+ * normals `jr.normal(k_j, ())` on `jr.split(subkey, 4)`.  The key chain is inherently sequential: one device thread
+ * walks it (~0.15 us per link) into `workspace`, then the 4 M normals are computed in parallel.  Enqueue-only like every
+ * gx_* entry.  draws: device [4][M]; workspace: device buffer of gx_jax_fardal_chain_workspace_bytes(M) bytes. */
+int64_t gx_jax_fardal_chain_workspace_bytes(int64_t M);
+int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *draws, void *workspace, void *stream);
 /* Host only (no CUDA call): the piecewise-polynomial force tables the integrators stage in shared memory, as fitted on
  * the host -- which = 0: NFW F(s) = (ln(1+s) - s/(1+s)) / s^3; which = 1: PowerLawCutoff G(s) = P(a, s^2) / s^3 for
  * the exponent a = 3/2 - alpha/2.  Rows of (degree + 1) monomial coefficients in t in [-1, 1) per interval,

@@ -110,6 +110,15 @@ double oc_gammainc(double a, double x) { return oc_gammainc_P(a, x); }
 
 /* ---------------------------------------------------------------- single components */
 
+/* b^2 under the root of zeta = sqrt(z^2 + b^2) in the DERIVATIVES of Miyamoto-Nagai / Satoh terms: for b = 0
+ * (KuzminPotential, builtin/kuzmin.py:82-84, Phi = -GM / sqrt(R^2 + (|z| + a)^2)) the closed forms divide by zeta, which
+ * vanishes in the disk plane; the reference's autodiff gives d|z|/dz = 0 there, i.e. a zero z-force and no delta
+ * function in the Hessian.  The smallest normal number under the root reproduces exactly that; b > 0 is unchanged. */
+static inline double oc_b2(double b) {
+    double b2 = b * b;
+    return b2 == 0.0 ? OC_TINY : b2;
+}
+
 static double nfw_menc_shape(double s) {
     /* ln(1+s) - s/(1+s); alternating series below s = 2^-4 where the difference cancels */
     if (s < 0.0625) {
@@ -300,7 +309,7 @@ static void comp_gradient(double G, const oc_component *c, const double q[3], do
     }
     if (c->kind == OC_KIND_SATOH) {
         const double *p = c->p;
-        double zeta = sqrt(z * z + p[2] * p[2]);
+        double zeta = sqrt(z * z + oc_b2(p[2]));
         double S = x * x + y * y + z * z + p[1] * (p[1] + 2.0 * zeta);
         double f = G * p[0] / (S * sqrt(S));
         g[0] = f * x;
@@ -310,7 +319,7 @@ static void comp_gradient(double G, const oc_component *c, const double q[3], do
     }
     if (c->kind == OC_KIND_MN) {
         const double *p = c->p;
-        double zeta = sqrt(z * z + p[2] * p[2]);
+        double zeta = sqrt(z * z + oc_b2(p[2]));
         double D2 = x * x + y * y + (p[1] + zeta) * (p[1] + zeta);
         double f = G * p[0] / (D2 * sqrt(D2));
         g[0] = f * x;
@@ -359,11 +368,11 @@ static void comp_hessian(double G, const oc_component *c, const double q[3], dou
     if (c->kind == OC_KIND_SATOH) {
         const double *p = c->p;
         double a = p[1], b = p[2];
-        double zeta = sqrt(z * z + b * b);
+        double zeta = sqrt(z * z + oc_b2(b));
         double S = x * x + y * y + z * z + a * (a + 2.0 * zeta);
         double f3 = G * p[0] / (S * sqrt(S)), f5 = 3.0 * f3 / S;
         double u[3] = {x, y, z * (1.0 + a / zeta)};
-        double duz = 1.0 + a * b * b / (zeta * zeta * zeta);
+        double duz = 1.0 + (b != 0.0 ? a * b * b / (zeta * zeta * zeta) : 0.0);
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) H[3 * i + j] = -f5 * (u[i] * u[j]);
         H[0] += f3;
@@ -374,13 +383,13 @@ static void comp_hessian(double G, const oc_component *c, const double q[3], dou
     if (c->kind == OC_KIND_MN) {
         const double *p = c->p;
         double a = p[1], b = p[2];
-        double zeta = sqrt(z * z + b * b);
+        double zeta = sqrt(z * z + oc_b2(b));
         double D2 = x * x + y * y + (a + zeta) * (a + zeta);
         double D = sqrt(D2);
         double f3 = G * p[0] / (D2 * D);
         double f5 = 3.0 * G * p[0] / (D2 * D2 * D);
         double u[3] = {x, y, z * (a + zeta) / zeta};
-        double duz = 1.0 + a * b * b / (zeta * zeta * zeta);
+        double duz = 1.0 + (b != 0.0 ? a * b * b / (zeta * zeta * zeta) : 0.0);
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) H[3 * i + j] = -f5 * (u[i] * u[j]);
         H[0] += f3;

@@ -3,8 +3,9 @@
 Every ``potential_*`` below follows the reference's closed form line by line; the
 ``gradient_*`` / ``hessian_*`` functions are the hand-derived derivatives of those closed
 forms (the reference obtains them with ``jax.grad`` / ``jax.hessian``,
-``/root/reference/src/galax/potential/_src/base.py:170-179,230-239``).  ``oracle/highprec.py``
-checks the hand derivations against mpmath differentiation of the *potential* itself.
+``/root/reference/src/galax/potential/_src/base.py:170-179,230-239``).
+``tests/test_oracle_potentials.py::test_hand_derivatives_vs_mpmath_differentiation`` checks the hand derivations
+against 40-digit mpmath differentiation of the *potential* itself.
 
 Unit system: galactic (kpc, Myr, Msun, rad).  All arrays are fp64; ``xyz`` has shape
 ``(..., 3)``.
@@ -110,9 +111,15 @@ def potential_mn(G, m, a, b, xyz):
     return -G * m / np.sqrt(R2 + zp2)
 
 
+def _b2(b):
+    """b^2 under the root of zeta in the derivatives; for b = 0 (Kuzmin, builtin/kuzmin.py:82-84: |z| in place of
+    zeta) the smallest normal number, which gives the zero in-plane z-force the reference's autodiff of |z| gives."""
+    return b * b if b * b != 0.0 else TINY
+
+
 def gradient_mn(G, m, a, b, xyz):
     x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
-    zeta = np.sqrt(z**2 + b**2)
+    zeta = np.sqrt(z**2 + _b2(b))
     D2 = x**2 + y**2 + (a + zeta) ** 2
     f = G * m / (D2 * np.sqrt(D2))
     return np.stack([f * x, f * y, f * z * (a + zeta) / zeta], axis=-1)
@@ -120,13 +127,13 @@ def gradient_mn(G, m, a, b, xyz):
 
 def hessian_mn(G, m, a, b, xyz):
     x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
-    zeta = np.sqrt(z**2 + b**2)
+    zeta = np.sqrt(z**2 + _b2(b))
     D2 = x**2 + y**2 + (a + zeta) ** 2
     D = np.sqrt(D2)
     f3 = G * m / (D2 * D)
     f5 = 3.0 * G * m / (D2 * D2 * D)
     uz = z * (a + zeta) / zeta
-    duz = 1.0 + a * b**2 / zeta**3  # d(uz)/dz
+    duz = 1.0 + (a * b**2 / zeta**3 if b != 0.0 else 0.0)  # d(uz)/dz
     u = np.stack([x, y, uz], axis=-1)
     H = -f5[..., None, None] * (u[..., :, None] * u[..., None, :])
     H[..., 0, 0] += f3
@@ -298,7 +305,7 @@ def potential_satoh(G, m, a, b, xyz):
 
 def gradient_satoh(G, m, a, b, xyz):
     x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
-    zeta = np.sqrt(z**2 + b**2)
+    zeta = np.sqrt(z**2 + _b2(b))
     S = x**2 + y**2 + z**2 + a * (a + 2 * zeta)
     f = G * m / (S * np.sqrt(S))
     return np.stack([f * x, f * y, f * z * (1 + a / zeta)], axis=-1)
@@ -306,12 +313,12 @@ def gradient_satoh(G, m, a, b, xyz):
 
 def hessian_satoh(G, m, a, b, xyz):
     x, y, z = xyz[..., 0], xyz[..., 1], xyz[..., 2]
-    zeta = np.sqrt(z**2 + b**2)
+    zeta = np.sqrt(z**2 + _b2(b))
     S = x**2 + y**2 + z**2 + a * (a + 2 * zeta)
     f3 = G * m / (S * np.sqrt(S))
     f5 = 3.0 * f3 / S
     u = np.stack([x, y, z * (1 + a / zeta)], axis=-1)
-    duz = 1.0 + a * b**2 / zeta**3
+    duz = 1.0 + (a * b**2 / zeta**3 if b != 0.0 else 0.0)
     H = -f5[..., None, None] * (u[..., :, None] * u[..., None, :])
     H[..., 0, 0] += f3
     H[..., 1, 1] += f3

@@ -38,6 +38,7 @@ LAYOUT_NT3, LAYOUT_T3N = 0, 1
 DF_FARDAL15, DF_CHEN24 = 0, 1
 DENSE_RECORD_DOUBLES = 51
 SOLVER_DOPRI8, SOLVER_DOPRI5 = 8, 5
+SOLVER_STRICT = 0x200
 
 
 class GxComponent(C.Structure):

@@ -1400,6 +1400,11 @@ int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const d
                               double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
                               int32_t layout, double *q, double *p, int32_t *status, void *stream);
 
+int gx_strict_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                 const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
+                                 const double *ts, int32_t T, int64_t max_steps, int32_t layout, double *q, double *p,
+                                 int32_t *status, int32_t *n_accepted, int32_t *n_attempted, void *stream);
+
 extern "C" {
 
 int gx_version(void) { return GX_VERSION; }
@@ -1616,15 +1621,22 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
                          const double *ts, int32_t T, int64_t max_steps, const int32_t *order, int32_t layout,
                          double *q, double *p, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
                          void *workspace, void *stream) {
+    const bool strict = (solver & GX_SOLVER_STRICT) != 0;
+    solver &= ~GX_SOLVER_STRICT;
     if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE);
+    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE);
     if (rc) return rc;
     if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
         return GX_ERR_BADARG;
     if (!(pid->rtol >= 0.0) || !(pid->atol >= 0.0) || (pid->rtol == 0.0 && pid->atol == 0.0)) return GX_ERR_BADARG;
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
     if (N == 0) return 0;
+    if (strict) {
+        if (rec) return GX_ERR_UNSUPPORTED;
+        return gx_strict_integrate_adaptive(solver, pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, layout, q, p,
+                                            status, n_accepted, n_attempted, stream);
+    }
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
     if (e != cudaSuccess) return GX_ERR_CUDA;
@@ -1699,7 +1711,7 @@ int gx_integrate_adaptive_record(int32_t solver, const gx_potential *pot, const 
                                  const double *p0, double t0, double t1, int64_t max_steps, double *rec,
                                  int32_t rec_capacity, int32_t *n_rec, int32_t *status, int32_t *n_accepted,
                                  int32_t *n_attempted, void *workspace, void *stream) {
-    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
+    if ((solver & ~GX_SOLVER_STRICT) != GX_SOLVER_DOPRI8 && (solver & ~GX_SOLVER_STRICT) != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     if (!rec || !n_rec || rec_capacity <= 0) return GX_ERR_BADARG;
     if (cudaMemsetAsync(n_rec, 0, sizeof(int32_t), (cudaStream_t)stream) != cudaSuccess) return GX_ERR_CUDA;
     return adaptive_impl(solver, rec, n_rec, rec_capacity, pot, pid, q0, p0, 1, nullptr, t0, t1, nullptr, 0, max_steps,

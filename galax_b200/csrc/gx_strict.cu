@@ -23,6 +23,11 @@
 
 #include "../../include/galax_b200.h"
 #include "../../include/gx_portable_math.h"
+// the Runge-Kutta tables (generic form: A, b_err, c, dense-output weights); a second copy of the constants, under
+// another namespace so that the two translation units of the library do not define the same symbols
+#define gx gxs_tab
+#include "gx_tables.h"
+#undef gx
 
 namespace gxs {
 
@@ -202,16 +207,198 @@ __global__ void __launch_bounds__(64) k_integrate_fixed_strict(const __grid_cons
     if (a.status) a.status[i] = st;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Dopri8 / Dopri5 + PID controller in the reference's own (generic, 6-component) form: k_i = f(y0 + sum_j a_ij k_j) h,
+// error = sum_j e_j k_j, SaveAt from y0 + sum_j b_j(theta) k_j, factor = safety * (1/err)^(1/order) through the
+// portable pow.  Operation for operation the loop of oracle/galax_oracle.c::oc_integrate_dopri8 (a restatement of
+// diffrax's diffeqsolve + PIDController.adapt_step_size as galax drives them: dynamics/_src/legacy/integrator.py:161-245,
+// dynamics/_src/orbit/solver.py:121-141): same results, same accept / reject sequence, bit for bit.
+struct StrictDpArgs {
+    const double *q0, *p0, *t0v, *ts;
+    double *q, *p;
+    int *status, *n_acc, *n_tot;
+    long long N, max_steps;
+    long long sn, sk, sc;
+    double t0s, t1;
+    double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax, dtmin, dtmax, dt0;
+    int T;
+};
+
+__device__ __forceinline__ double rms6(const double v[6]) {
+    double s = 0;
+    for (int i = 0; i < 6; ++i) s += v[i] * v[i];
+    return sqrt(s / 6.0);
+}
+
+__device__ void field_dir(const StrictPot &P, double dir, const double y[6], double f[6]) {
+    double g[3];
+    gradient(P, y[0], y[1], y[2], g);
+    for (int c = 0; c < 3; ++c) { f[c] = y[3 + c] * dir; f[3 + c] = -g[c] * dir; }
+}
+
+__device__ double select_initial_step(const StrictPot &P, double dir, const double y0[6], const double f0[6], double rtol,
+                                      double atol, double order) {
+    double sc[6], v[6];
+    for (int i = 0; i < 6; ++i) sc[i] = atol + fabs(y0[i]) * rtol;
+    for (int i = 0; i < 6; ++i) v[i] = y0[i] / sc[i];
+    double d0 = rms6(v);
+    for (int i = 0; i < 6; ++i) v[i] = f0[i] / sc[i];
+    double d1 = rms6(v);
+    int cond = (d0 < 1e-5) || (d1 < 1e-5);
+    double h0 = cond ? 1e-6 : 0.01 * (d0 / d1);
+    double y1[6], f1[6];
+    for (int i = 0; i < 6; ++i) y1[i] = y0[i] + h0 * f0[i];
+    field_dir(P, dir, y1, f1);
+    for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
+    double d2 = rms6(v) / h0;
+    double maxd = fmax(d1, d2);
+    double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : gx_pm_pow(0.01 / maxd, 1.0 / order);
+    return fmin(100.0 * h0, h1);
+}
+
+__device__ __forceinline__ double clip_to_end_keep(double tprev, double tnext, double t1, int keep) {
+    if (tnext > t1 - 1e-10) return keep ? t1 : tprev + 0.5 * (t1 - tprev);
+    return tnext;
+}
+
+template <class TB>
+__global__ void __launch_bounds__(64) k_integrate_adaptive_strict(const __grid_constant__ StrictPot P, const StrictDpArgs a) {
+    constexpr int ns = TB::NS;
+    const double order = TB::ORDER;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const double t0 = a.t0v ? a.t0v[i] : a.t0s;
+    const double dir = (a.t1 >= t0) ? 1.0 : -1.0;
+    const double T0 = t0 * dir, T1 = a.t1 * dir;
+    double y[6] = {a.q0[3 * i], a.q0[3 * i + 1], a.q0[3 * i + 2], a.p0[3 * i], a.p0[3 * i + 1], a.p0[3 * i + 2]};
+    double *qo = a.q + i * a.sn, *po = a.p + i * a.sn;
+    int k = 0, st = GX_OK;
+    int nacc = 0, ntot = 0;
+    while (k < a.T && a.ts[k] * dir <= T0) {
+        for (int c = 0; c < 3; ++c) { qo[k * a.sk + c * a.sc] = y[c]; po[k * a.sk + c * a.sc] = y[3 + c]; }
+        ++k;
+    }
+    double f0[6];
+    field_dir(P, dir, y, f0);
+    double tprev = T0, tnext;
+    double prev_inv = 1.0, prev_prev_inv = 1.0;
+    int at_dtmin = 0;
+    {
+        double h = (a.dt0 > 0.0) ? a.dt0 : select_initial_step(P, dir, y, f0, a.rtol, a.atol, order + 1.0);
+        if (a.dtmax > 0.0 && isfinite(a.dtmax)) h = fmin(h, a.dtmax);
+        if (a.dtmin > 0.0) { at_dtmin = h <= a.dtmin; h = fmax(h, a.dtmin); }
+        tnext = clip_to_end_keep(T0, T0 + h, T1, 1);
+    }
+    double K[ns][6], flast[6];
+    while (tprev < T1) {
+        if (a.max_steps >= 0 && ntot >= a.max_steps) { st = GX_MAX_STEPS_REACHED; break; }
+        double h = tnext - tprev;
+        for (int c = 0; c < 6; ++c) K[0][c] = f0[c] * h;
+        double ys[6];
+        for (int s = 1; s < ns; ++s) {
+            for (int c = 0; c < 6; ++c) {
+                double inc = 0.0;
+                for (int j = 0; j < s; ++j) inc += TB::A(s, j) * K[j][c];
+                ys[c] = y[c] + inc;
+            }
+            field_dir(P, dir, ys, flast);
+            for (int c = 0; c < 6; ++c) K[s][c] = flast[c] * h;
+        }
+        double y1[6], err[6], sc[6];
+        for (int c = 0; c < 6; ++c) {
+            y1[c] = ys[c];
+            double e = 0.0;
+            for (int j = 0; j < ns; ++j) e += TB::E(j) * K[j][c];
+            err[c] = e;
+        }
+        ++ntot;
+        int nan1 = 0;
+        for (int c = 0; c < 6; ++c) nan1 |= isnan(y1[c]);
+        for (int c = 0; c < 6; ++c) {
+            double yc = nan1 ? y[c] : y1[c];
+            sc[c] = err[c] / (a.atol + fmax(fabs(y[c]), fabs(yc)) * a.rtol);
+            if (isnan(sc[c])) sc[c] = __longlong_as_double(0x7ff0000000000000LL);
+        }
+        double serr = rms6(sc);
+        int keep = serr < 1.0;
+        if (a.dtmin > 0.0) keep = keep || at_dtmin;
+        double inv = 1.0 / serr;
+        double c1 = (a.icoeff + a.pcoeff + a.dcoeff) / order;
+        double c2 = -(a.pcoeff + 2.0 * a.dcoeff) / order;
+        double c3 = a.dcoeff / order;
+        double fac1 = (c1 == 0.0) ? 1.0 : gx_pm_pow(inv, c1);
+        double fac2 = (c2 == 0.0) ? 1.0 : gx_pm_pow(prev_inv, c2);
+        double fac3 = (c3 == 0.0) ? 1.0 : gx_pm_pow(prev_prev_inv, c3);
+        double fmin_ = keep ? 1.0 : a.factormin;
+        double factor = a.safety * fac1 * fac2 * fac3;
+        if (factor < fmin_) factor = fmin_;
+        if (factor > a.factormax) factor = a.factormax;
+        double dt = h * factor;
+        if (inv == 0.0 || isinf(inv)) { inv = 1.0; prev_inv = 1.0; }
+        if (a.dtmax > 0.0 && isfinite(a.dtmax)) dt = fmin(dt, a.dtmax);
+        if (a.dtmin > 0.0) {
+            at_dtmin = dt <= a.dtmin;
+            dt = fmax(dt, a.dtmin);
+        }
+        if (keep) {
+            while (k < a.T && a.ts[k] * dir <= tnext) {
+                double th = (a.ts[k] * dir - tprev) / (tnext - tprev);
+                double bw[ns];
+                for (int j = 0; j < ns; ++j) {
+                    double pv = TB::DB(j, 5);
+                    for (int m = 4; m >= 0; --m) pv = pv * th + TB::DB(j, m);
+                    bw[j] = pv * th;
+                }
+                for (int c = 0; c < 6; ++c) {
+                    double inc = 0.0;
+                    for (int j = 0; j < ns; ++j) inc += bw[j] * K[j][c];
+                    double v = y[c] + inc;
+                    if (c < 3) qo[k * a.sk + c * a.sc] = v; else po[k * a.sk + (c - 3) * a.sc] = v;
+                }
+                ++k;
+            }
+            for (int c = 0; c < 6; ++c) { y[c] = y1[c]; f0[c] = flast[c]; }
+            prev_prev_inv = prev_inv;
+            prev_inv = inv;
+            tprev = tnext;
+            ++nacc;
+            int fin = 1;
+            for (int c = 0; c < 6; ++c) fin &= isfinite(y[c]) ? 1 : 0;
+            if (!fin) { st = GX_NONFINITE; break; }
+        }
+        if (tprev > T1) tprev = T1;
+        tnext = clip_to_end_keep(tprev, tprev + dt, T1, keep);
+    }
+    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+    for (; k < a.T; ++k)
+        for (int c = 0; c < 3; ++c) { qo[k * a.sk + c * a.sc] = NANV; po[k * a.sk + c * a.sc] = NANV; }
+    if (a.status) a.status[i] = st;
+    if (a.n_acc) a.n_acc[i] = nacc;
+    if (a.n_tot) a.n_tot[i] = ntot;
+}
+
+// tableau views for the strict kernels (generic A, not the Nystrom products the fast kernels use)
+struct STabDp8 {
+    static constexpr int NS = 14;
+    static constexpr int ORDER = 8;
+    __device__ __forceinline__ static double A(int i, int j) { return gxs_tab::dp8::A[i][j]; }
+    __device__ __forceinline__ static double E(int j) { return gxs_tab::dp8::E[j]; }
+    __device__ __forceinline__ static double DB(int j, int m) { return gxs_tab::dp8::DB[j][m]; }
+};
+struct STabDp5 {
+    static constexpr int NS = 7;
+    static constexpr int ORDER = 5;
+    __device__ __forceinline__ static double A(int i, int j) { return gxs_tab::dp5::A[i][j]; }
+    __device__ __forceinline__ static double E(int j) { return gxs_tab::dp5::E[j]; }
+    __device__ __forceinline__ static double DB(int j, int m) { return gxs_tab::dp5::DB[j][m]; }
+};
+
 }  // namespace gxs
 
-// Called by gx_integrate_fixed (gx_kernels.cu) when GX_SCHEME_STRICT is set; arguments already validated there.
 // gx_component.reserved carries the summation group: consecutive components with the same non-zero value are one
 // reference component (an MN3 disk) and are summed first; 0 = a component of its own.
-int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
-                              double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
-                              int32_t layout, double *q, double *p, int32_t *status, void *stream) {
-    using namespace gxs;
-    StrictPot P;
+static int strict_pot(const gx_potential *pot, gxs::StrictPot &P) {
     P.n = pot->n;
     P.G = pot->G;
     int next_group = 1 << 20;
@@ -228,6 +415,16 @@ int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const d
         P.c[i].p[0] = c.p[0]; P.c[i].p[1] = c.p[1]; P.c[i].p[2] = c.p[2];
         P.c[i].lg = (c.kind == GX_KIND_POWERLAWCUTOFF) ? lgamma(1.5 - c.p[1] / 2) : 0.0;
     }
+    return 0;
+}
+
+// Called by gx_integrate_fixed (gx_kernels.cu) when GX_SCHEME_STRICT is set; arguments already validated there.
+int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
+                              double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
+                              int32_t layout, double *q, double *p, int32_t *status, void *stream) {
+    using namespace gxs;
+    StrictPot P;
+    if (int rc = strict_pot(pot, P)) return rc;
     StrictArgs a;
     a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p; a.status = status;
     a.N = N; a.max_steps = max_steps; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T; a.scheme = scheme;
@@ -235,5 +432,32 @@ int gx_strict_integrate_fixed(const gx_potential *pot, const double *q0, const d
     else { a.sn = 3LL * T; a.sk = 3; a.sc = 1; }
     const int block = (N >= 148LL * 64 * 4) ? 64 : 32;
     gxs::k_integrate_fixed_strict<<<(int)((N + block - 1) / block), block, 0, (cudaStream_t)stream>>>(P, a);
+    return cudaGetLastError() == cudaSuccess ? 0 : GX_ERR_CUDA;
+}
+
+// Called by the adaptive entries (gx_kernels.cu) when GX_SOLVER_STRICT is or-ed into `solver`; arguments validated there.
+int gx_strict_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                 const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
+                                 const double *ts, int32_t T, int64_t max_steps, int32_t layout, double *q, double *p,
+                                 int32_t *status, int32_t *n_accepted, int32_t *n_attempted, void *stream) {
+    using namespace gxs;
+    StrictPot P;
+    if (int rc = strict_pot(pot, P)) return rc;
+    StrictDpArgs a;
+    a.q0 = q0; a.p0 = p0; a.t0v = t0; a.ts = ts; a.q = q; a.p = p;
+    a.status = status; a.n_acc = n_accepted; a.n_tot = n_attempted;
+    a.N = N; a.max_steps = max_steps; a.t0s = t0_scalar; a.t1 = t1;
+    a.rtol = pid->rtol; a.atol = pid->atol;
+    a.pcoeff = pid->pcoeff; a.icoeff = pid->icoeff; a.dcoeff = pid->dcoeff;
+    a.safety = pid->safety; a.factormin = pid->factormin; a.factormax = pid->factormax;
+    a.dtmin = pid->dtmin; a.dtmax = pid->dtmax;
+    a.dt0 = (pid->dt0 > 0.0) ? pid->dt0 : -1.0;
+    a.T = T;
+    if (layout == GX_LAYOUT_T3N) { a.sn = 1; a.sk = 3 * N; a.sc = N; }
+    else { a.sn = 3LL * T; a.sk = 3; a.sc = 1; }
+    const int block = (N >= 148LL * 64 * 4) ? 64 : 32;
+    const int grid = (int)((N + block - 1) / block);
+    if (solver == GX_SOLVER_DOPRI5) k_integrate_adaptive_strict<STabDp5><<<grid, block, 0, (cudaStream_t)stream>>>(P, a);
+    else k_integrate_adaptive_strict<STabDp8><<<grid, block, 0, (cudaStream_t)stream>>>(P, a);
     return cudaGetLastError() == cudaSuccess ? 0 : GX_ERR_CUDA;
 }

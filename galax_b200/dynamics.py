@@ -59,16 +59,23 @@ class LeapfrogMidpoint:
 
 @dataclasses.dataclass(frozen=True)
 class Dopri8:
-    """diffrax.Dopri8 (Prince-Dormand 8(7)13M + FSAL); ``scan_kind`` has no numerical effect."""
+    """diffrax.Dopri8 (Prince-Dormand 8(7)13M + FSAL); ``scan_kind`` has no numerical effect.
+
+    ``strict=True`` (not a diffrax field): the reference-order kernel (``GX_SOLVER_STRICT``) -- generic Runge-Kutta form,
+    IEEE division / square root, no FMA contraction, portable transcendental functions: results and accept / reject
+    sequence reproducible bit for bit on a CPU; roughly an order of magnitude slower than the default kernel."""
 
     scan_kind: str | None = None
+    strict: bool = False
 
 
 @dataclasses.dataclass(frozen=True)
 class Dopri5:
-    """diffrax.Dopri5 (Dormand-Prince 5(4) + FSAL): default of the reference's experimental StreamSimulator."""
+    """diffrax.Dopri5 (Dormand-Prince 5(4) + FSAL): default of the reference's experimental StreamSimulator.
+    ``strict``: see Dopri8."""
 
     scan_kind: str | None = None
+    strict: bool = False
 
 
 @dataclasses.dataclass(frozen=True)
@@ -428,12 +435,14 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             if not isinstance(controller, PIDController):
                 raise NotImplementedError("Dopri8 / Dopri5 require a PIDController")
             code = _lib.SOLVER_DOPRI8 if isinstance(solver, Dopri8) else _lib.SOLVER_DOPRI5
+            if solver.strict:
+                code |= _lib.SOLVER_STRICT
             pid = controller.c_struct(dt0)
             nacc = torch.empty((N,), dtype=torch.int32, device=dev)
             ntot = torch.empty((N,), dtype=torch.int32, device=dev)
             ws = torch.empty((int(L.gx_workspace_bytes()) // 8,), dtype=torch.int64, device=dev)
             order = _period_order(dq, dp, t0_arr, t1, torch) if (sort and N > 64) else None
-            if N == 1 and T >= 64 and t0_arr is None and t0s != t1 and layout == "NT3":
+            if N == 1 and T >= 64 and t0_arr is None and t0s != t1 and layout == "NT3" and not solver.strict:
                 # single orbit, many saves (mock-stream progenitor): record the steps, evaluate the dense output
                 # for all save times in parallel (gx_integrate_dopri8_record + gx_dense_eval)
                 cap = int(min(ms, 1 << 16)) if ms > 0 else (1 << 16)

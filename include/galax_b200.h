@@ -187,6 +187,13 @@ int gx_dense_eval(const double *rec, const int32_t *n_rec, double t0, double t1,
  * (dynamics/_src/experimental/stream.py:32-41).  gx_integrate_dopri8* are these with solver = GX_SOLVER_DOPRI8. */
 #define GX_SOLVER_DOPRI8 8
 #define GX_SOLVER_DOPRI5 5
+/* or-ed into `solver` of gx_integrate_adaptive: reference-order arithmetic, the adaptive counterpart of GX_SCHEME_STRICT
+ * (galax_b200/csrc/gx_strict.cu) -- the generic six-component Runge-Kutta form with k_i = f(.) h, components summed in
+ * composite order, IEEE division / square root, no FMA contraction, portable log1p / exp / log / pow, one thread per
+ * particle.  Results AND the accept / reject sequence are bit for bit what a plain C program computes on an IEEE-754
+ * CPU (tests/test_gpu_strict.py: every particle of a 4096-particle C2-shaped run equals oracle/galax_oracle.c at
+ * all 1000 saves).  Same component kinds as GX_SCHEME_STRICT; `order`, `workspace` are ignored; not for *_record. */
+#define GX_SOLVER_STRICT 0x200
 int gx_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
                           const double *p0, int64_t N, const double *t0, double t0_scalar, double t1, const double *ts,
                           int32_t T, int64_t max_steps, const int32_t *order, int32_t layout, double *q, double *p,

@@ -203,4 +203,9 @@ GX_PM_FN double gx_pm_exp(double x) {
     return y * 9.33263618503218878990e-302; /* 2^-1000 */
 }
 
+/* x^y for x >= 0 as exp(y log x): a few ulp for |y log x| < 10, which is all its users need (the step-size controller's
+ * factor = safety * (1/err)^(1/order), the initial-step heuristic's (0.01/d)^(1/(order+1))).  pow(inf, y > 0) = inf,
+ * pow(0, y > 0) = 0, nan propagates. */
+GX_PM_FN double gx_pm_pow(double x, double y) { return gx_pm_exp(y * gx_pm_log(x)); }
+
 #endif /* GX_PORTABLE_MATH_H */

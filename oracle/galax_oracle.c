@@ -56,7 +56,7 @@
 #include "../include/gx_portable_math.h"
 void oc_pm_eval(int op, int64_t n, const double *x, double *out) {
     for (int64_t i = 0; i < n; ++i)
-        out[i] = (op == 0) ? gx_pm_log(x[i]) : (op == 1) ? gx_pm_exp(x[i]) : gx_pm_log1p(x[i]);
+        out[i] = (op == 0) ? gx_pm_log(x[i]) : (op == 1) ? gx_pm_exp(x[i]) : (op == 2) ? gx_pm_log1p(x[i]) : gx_pm_pow(x[i], 0.125);
 }
 
 typedef struct {
@@ -662,7 +662,7 @@ static double select_initial_step(const oc_potential *P, int td, double dir, dou
     for (int i = 0; i < 6; ++i) v[i] = (f1[i] - f0[i]) / sc[i];
     double d2 = rms6(v) / h0;
     double maxd = fmax(d1, d2);
-    double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / maxd, 1.0 / order);
+    double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : gx_pm_pow(0.01 / maxd, 1.0 / order);
     return fmin(100.0 * h0, h1);
 }
 
@@ -741,9 +741,11 @@ int oc_integrate_dopri8(const oc_potential *P, const oc_tableau *tab, const oc_p
             double c1 = (pid->icoeff + pid->pcoeff + pid->dcoeff) / order;
             double c2 = -(pid->pcoeff + 2.0 * pid->dcoeff) / order;
             double c3 = pid->dcoeff / order;
-            double fac1 = (c1 == 0.0) ? 1.0 : pow(inv, c1);
-            double fac2 = (c2 == 0.0) ? 1.0 : pow(prev_inv, c2);
-            double fac3 = (c3 == 0.0) ? 1.0 : pow(prev_prev_inv, c3);
+            /* x^c through the portable exp / log (include/gx_portable_math.h): libm's pow differs between platforms in
+             * the last bit, and the last bit of the factor decides accept / reject sequences (tests/test_gpu_strict.py) */
+            double fac1 = (c1 == 0.0) ? 1.0 : gx_pm_pow(inv, c1);
+            double fac2 = (c2 == 0.0) ? 1.0 : gx_pm_pow(prev_inv, c2);
+            double fac3 = (c3 == 0.0) ? 1.0 : gx_pm_pow(prev_prev_inv, c3);
             double fmin_ = keep ? 1.0 : pid->factormin;
             double factor = pid->safety * fac1 * fac2 * fac3;
             if (factor < fmin_) factor = fmin_;

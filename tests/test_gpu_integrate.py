@@ -213,7 +213,20 @@ def test_dopri8_parity_with_oracle(name, tol):
     dp = (np.abs(sol.ys[1] - pr) / (tol + tol * np.abs(pr))).max(axis=(1, 2))
     d = np.maximum(dq, dp)
     assert np.median(d) <= 10.0, np.median(d)
-    assert np.mean(d <= 10.0) >= 0.6, np.mean(d <= 10.0)
+    # The reference-order kernel takes the oracle's step sequence exactly (bit-identical saves and step counts); the
+    # share of particles the FAST kernel keeps inside the bar is held against what the oracle's own arithmetic keeps
+    # inside it when started one ulp away (tests/test_gpu_strict.py has the full-size C2 version and the reasoning).
+    strict = gd.OrbitSolver(solver=gd.Dopri8(strict=True), stepsize_controller=gd.PIDController(rtol=tol, atol=tol),
+                            max_steps=2**16)  # fmt: skip
+    s0 = strict.solve(pot, (q0, p0), 0.0, 1000.0, saveat=ts)
+    assert np.array_equal(s0.ys[0], qr) and np.array_equal(s0.ys[1], pr)
+    assert np.array_equal(np.asarray(s0.stats["num_steps"]), nt) and np.array_equal(np.asarray(s0.stats["num_accepted_steps"]), na)
+    rng = np.random.default_rng(5)
+    nudge = lambda x: np.where(rng.integers(0, 2, size=x.shape) > 0, np.nextafter(x, np.inf), np.nextafter(x, -np.inf))  # noqa: E731
+    s1 = strict.solve(pot, (nudge(q0), nudge(p0)), 0.0, 1000.0, saveat=ts)
+    dt_ = np.maximum((np.abs(s1.ys[0] - qr) / (tol + tol * np.abs(qr))).max(axis=(1, 2)),
+                     (np.abs(s1.ys[1] - pr) / (tol + tol * np.abs(pr))).max(axis=(1, 2)))
+    assert np.mean(d <= 10.0) >= np.mean(dt_ <= 10.0) - 0.3 and np.median(d) <= 4.0 * np.median(dt_) + 0.5
     qt, pt, stt, _, _ = cref.integrate_dopri8(opot, q0, p0, 0.0, 1000.0, ts, rtol=1e-13, atol=1e-13)
     err_gpu = np.abs(sol.ys[0] - qt).max(axis=(1, 2))
     err_orc = np.abs(qr - qt).max(axis=(1, 2))

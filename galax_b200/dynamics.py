@@ -691,7 +691,11 @@ class AbstractStreamDF:
         else:
             mass = np.full((M,), float(getattr(prog_mass, "value", prog_mass)))
         dm = torch.from_numpy(np.ascontiguousarray(mass)).to(dq.device)
-        draws = rng if isinstance(rng, (np.ndarray, torch.Tensor)) else self._draws(rng, M)
+        is_key = isinstance(rng, np.ndarray) and rng.dtype == np.uint32 and rng.shape == (2,)  # raw jax key data
+        draws = rng if (isinstance(rng, (np.ndarray, torch.Tensor)) and not is_key) else self._draws(rng, M)
+        want = (4, M) if self.df_kind == _lib.DF_FARDAL15 else (M, 6)
+        if tuple(draws.shape) != want:
+            raise ValueError(f"random draws must have shape {want} for {type(self).__name__}, got {tuple(draws.shape)}")
         dd, _ = _to_device(draws)
         dd = dd.contiguous()
         outs = [torch.empty((M, 3), dtype=torch.float64, device=dq.device) for _ in range(4)]

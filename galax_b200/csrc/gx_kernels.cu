@@ -207,6 +207,19 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
             model = MODEL_BOVY;  // (the integrators stage the bulge's force table in shared memory)
         // ... and the NFW force table for MW / MW2022: without it (allocation failed) they run as runtime composites
         if ((model == MODEL_MW || model == MODEL_MW2022) && use_device && D.nfw_tab == nullptr) model = MODEL_GENERIC;
+#if GX_SPH_TABLE
+        // the composite's combined spherical table S(r^2) (fitted and uploaded on first use of these parameters)
+        if (model != MODEL_GENERIC && use_device) {
+            std::vector<SphComp> cs;
+            for (int i = 0; i < pot->n; ++i) {
+                const gx_component &c = pot->c[i];
+                if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, G * c.p[0], c.p[1], 0.0});
+                if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
+            }
+            D.sph_tab = sph_table_for(cs);
+            if (D.sph_tab == nullptr) model = MODEL_GENERIC;
+        }
+#endif
     }
     return 0;
 }
@@ -577,11 +590,15 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #endif
 template <class C, int SCHEME, bool FWD>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
-    constexpr bool STAGED = C::is_static && C::kPLC > 0;  // PowerLawCutoff table in shared memory (Bovy)
-    plc_stage<C>(P);
-    const unsigned plc_base = plc_smem_base<C>();
-    constexpr bool NFWT = nfw_tab_fixed_ok<C>();
-    const unsigned nfw_base = nfw_stage<C, NFWT>(P);
+    // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
+    // tables of round 1 (GX_SPH_TABLE=0 builds)
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 1 : 0;
+    constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
+    constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
+    unsigned plc_base = 0, nfw_base = 0;
+    if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
+    if constexpr (SPHT != 0) nfw_base = sph_stage<C, SPHT != 0>(P);
+    else nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     // integrate in tau = dir * t (diffrax flips the sign of time the same way for t1 < t0)
@@ -610,14 +627,14 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                gradient_factors<C, STAGED, NFWT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
+                gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
                 npy = fma(fhh, nqy, py);
                 npz = fma(fvh, nqz, pz);
                 gx_ = gy_ = gz_ = 0.0;
             } else {
-                gradient<C, STAGED, NFWT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
+                gradient<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
                 npx = fma(-gx_, hs, px);
                 npy = fma(-gy_, hs, py);
                 npz = fma(-gz_, hs, pz);
@@ -626,7 +643,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqx = __dadd_rn(qx, __dmul_rn(px, hs));
             nqy = __dadd_rn(qy, __dmul_rn(py, hs));
             nqz = __dadd_rn(qz, __dmul_rn(pz, hs));
-            gradient<C, STAGED, NFWT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
+            gradient<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
             npx = __dadd_rn(px, __dmul_rn(-gx_, hs));
             npy = __dadd_rn(py, __dmul_rn(-gy_, hs));
             npz = __dadd_rn(pz, __dmul_rn(-gz_, hs));
@@ -634,7 +651,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         } else {
             const double hm = tnext - tm;
             const double hh = FWD ? hm : -hm;
-            gradient<C, STAGED, NFWT>(P, qx, qy, qz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
+            gradient<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
             nqx = __dadd_rn(mqx, __dmul_rn(px, hh));
             nqy = __dadd_rn(mqy, __dmul_rn(py, hh));
             nqz = __dadd_rn(mqz, __dmul_rn(pz, hh));
@@ -675,11 +692,15 @@ template <class C, bool FWD>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS)
 k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
-    constexpr bool STAGED = C::is_static && C::kPLC > 0;
-    plc_stage<C>(P);
-    const unsigned plc_base = plc_smem_base<C>();
-    constexpr bool NFWT = nfw_tab_fixed_ok<C>();
-    const unsigned nfw_base = nfw_stage<C, NFWT>(P);
+    // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
+    // tables of round 1 (GX_SPH_TABLE=0 builds)
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 1 : 0;
+    constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
+    constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
+    unsigned plc_base = 0, nfw_base = 0;
+    if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
+    if constexpr (SPHT != 0) nfw_base = sph_stage<C, SPHT != 0>(P);
+    else nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     const double T0 = FWD ? a.t0 : -a.t0;
@@ -724,7 +745,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qz = fma(pz, hs, qz);
                     if constexpr (C::is_static) {
                         double fh, fv;
-                        gradient_factors<C, STAGED, NFWT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
+                        gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
                         const double fhh = -fh * hs, fvh = -fv * hs;
                         px = fma(fhh, qx, px);
                         py = fma(fhh, qy, py);
@@ -746,7 +767,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 double npx, npy, npz;
                 if constexpr (C::is_static) {
                     double fh, fv;
-                    gradient_factors<C, STAGED, NFWT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
+                    gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                     const double fhh = -fh * hs, fvh = -fv * hs;
                     npx = fma(fhh, nqx, px); npy = fma(fhh, nqy, py); npz = fma(fvh, nqz, pz);
                 } else {
@@ -853,9 +874,12 @@ __device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
     // (handing the table's shared-window address down in a register instead of re-deriving it here -- S2R + LEA + ISETP
     // + MOV per call -- was measured: the extra live register costs the Dopri8 kernel 40 bytes of spills)
     double g0, g1, g2;
-    unsigned nfw_base = 0;  // the kernel prologue staged the NFW force table (nfw_stage)
-    if constexpr (nfw_tab_ok<C>()) nfw_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
-    gradient<C, (C::is_static && C::kPLC > 0), nfw_tab_ok<C>()>(rhs_pot<C, IMG>(), x, y, z, g0, g1, g2, 0.0, nfw_base);
+    unsigned tab_base = 0;  // the kernel prologue staged the force table (sph_stage / nfw_stage)
+    constexpr int SPHM = sph_tab_ok<C>() ? 2 : 0;  // Estrin form: the call ends on this polynomial
+    if constexpr (SPHM != 0) tab_base = (unsigned)__cvta_generic_to_shared(sph_smem<C>());
+    else if constexpr (nfw_tab_ok<C>()) tab_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
+    gradient<C, (!SPHM && C::is_static && C::kPLC > 0), (!SPHM && nfw_tab_ok<C>()), SPHM>(rhs_pot<C, IMG>(), x, y, z, g0, g1,
+                                                                                          g2, 0.0, tab_base);
     return Acc3{-g0, -g1, -g2};
 }
 // runtime composites may be time dependent (LinearParameter): the callee also receives the physical time
@@ -924,8 +948,12 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         for (int w = threadIdx.x; w < (int)(sizeof(DevPot) / sizeof(double)); w += blockDim.x) dst[w] = src[w];
         __syncthreads();
     }
-    plc_stage<C>(P);  // (Bovy) the PowerLawCutoff table, read by accel_call()
-    (void)nfw_stage<C, nfw_tab_ok<C>()>(P);  // (MW, MW2022) the NFW force table, likewise
+    if constexpr (sph_tab_ok<C>()) {
+        (void)sph_stage<C, sph_tab_ok<C>()>(P);  // (MW, MW2022, Bovy) the combined spherical table, read by accel_call()
+    } else {
+        plc_stage<C>(P);  // (GX_SPH_TABLE=0) the PowerLawCutoff table
+        (void)nfw_stage<C, nfw_tab_ok<C>()>(P);  // ... and the NFW force table
+    }
     const unsigned FULL = 0xffffffffu;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const bool simple_i = (TB::ORDER == 8) && (a.pcoeff == 0.0 && a.dcoeff == 0.0 && a.icoeff == 1.0);
@@ -1921,6 +1949,29 @@ int gx_force_table(int32_t which, double a, double *coef, int64_t capacity, int3
         else plc_fit_interval((long double)a, s0, s1, row.data(), &worst);
         if (coef) memcpy(coef + (size_t)j * (PLC_DEG + 1), row.data(), sizeof(double) * (PLC_DEG + 1));
     }
+    if (max_rel_err) *max_rel_err = worst;
+    return 0;
+}
+
+int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
+                             int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err) {
+    if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
+    std::vector<SphComp> cs;
+    for (int i = 0; i < pot->n; ++i) {
+        const gx_component &c = pot->c[i];
+        if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, pot->G * c.p[0], c.p[1], 0.0});
+        if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, pot->G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
+    }
+    if (cs.empty()) return GX_ERR_UNSUPPORTED;
+    if (n_intervals) *n_intervals = SPH_NINT;
+    if (degree) *degree = PLC_DEG;
+    if (e_lo) *e_lo = SPH_E_LO;
+    if (sub_bits) *sub_bits = SPH_SUB_BITS;
+    if (!coef && !max_rel_err) return 0;
+    if (coef && capacity < (int64_t)SPH_NINT * (PLC_DEG + 1)) return GX_ERR_BADARG;
+    std::vector<double> tmp;
+    if (!coef) { tmp.resize((size_t)SPH_NINT * (PLC_DEG + 1)); coef = tmp.data(); }
+    const double worst = sph_table_fit(cs, coef);
     if (max_rel_err) *max_rel_err = worst;
     return 0;
 }

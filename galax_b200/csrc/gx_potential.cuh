@@ -61,14 +61,13 @@ __device__ __forceinline__ double2 lds_v2f64(unsigned addr) {
 // Piecewise-polynomial table lookup: value and (optionally) derivative with respect to s of a function tabulated on
 // 2^PLC_SUB_BITS intervals per octave of s in [2^E_LO, 2^E_LO + NINT / 2^PLC_SUB_BITS octaves); returns false when s is
 // outside the tabulated range.  Shared by the PowerLawCutoff and the NFW force tables.
-template <bool SMEM, int E_LO, int NINT>
+template <bool SMEM, int E_LO, int NINT, int B = PLC_SUB_BITS, bool ESTRIN = false>
 __device__ __forceinline__ bool poly_table_eval(const double *tab, double s, double &G, double *dG,
                                                 unsigned smem_base = 0) {
     if (!SMEM && tab == nullptr) return false;
     const int hi = __double2hiint(s);
     // interval index from the bits of s > 0: (hi >> (20 - B)) = exponent field * 2^B + top B mantissa bits
-    constexpr int B = PLC_SUB_BITS;
-    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + E_LO) * PLC_SUB);
+    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + E_LO) << B);
     if (j >= (unsigned)NINT) return false;  // s outside the table (also NaN / negative)
     // interval [2^e (1 + sub/2^B), 2^e (1 + (sub+1)/2^B)), t in [-1, 1):  t = 2^(B+1) m - (2^(B+1) + 2 sub + 1) with
     // m = s / 2^e in [1, 2).  Both operands come straight from the bits of s (exact).
@@ -77,7 +76,19 @@ __device__ __forceinline__ bool poly_table_eval(const double *tab, double s, dou
     const double cB = __hiloint2double((hi & TOP) | HALF | EXPC, 0);  // 2^(B+1) (1 + sub/2^B + 2^-(B+1))
     const double t = fma(m, (double)(2 << B), -cB);
     double v, d = 0.0;
-    if (SMEM) {
+    if (SMEM && ESTRIN) {
+        // Estrin's scheme: 12 FP64 instructions, 4 deep (Horner: 9, 9 deep) -- for the latency-bound Dopri kernels,
+        // whose right-hand side ends on this polynomial.  Value only.
+        static_assert(PLC_DEG == 9, "Estrin form written for degree 9");
+        const unsigned a0 = (smem_base ? smem_base : (unsigned)__cvta_generic_to_shared(tab)) + j * (unsigned)(PLC_STRIDE * 8);
+        const double2 c01 = lds_v2f64(a0), c23 = lds_v2f64(a0 + 16), c45 = lds_v2f64(a0 + 32), c67 = lds_v2f64(a0 + 48),
+                      c89 = lds_v2f64(a0 + 64);
+        const double t2 = t * t, t4 = t2 * t2, t8 = t4 * t4;
+        const double p01 = fma(c01.y, t, c01.x), p23 = fma(c23.y, t, c23.x), p45 = fma(c45.y, t, c45.x),
+                     p67 = fma(c67.y, t, c67.x), p89 = fma(c89.y, t, c89.x);
+        const double q0 = fma(p23, t2, p01), q1 = fma(p67, t2, p45);
+        v = fma(p89, t8, fma(q1, t4, q0));
+    } else if (SMEM) {
         // 32-bit shared-window address; the fixed-step kernels pass the table's base (plc_smem_base) so that the window
         // base (S2R SR_CgaCtaId + LEA) is not re-derived in every step
         const unsigned a0 = (smem_base ? smem_base : (unsigned)__cvta_generic_to_shared(tab)) + j * (unsigned)(PLC_STRIDE * 8);
@@ -132,6 +143,19 @@ constexpr int NFW_NINT = (NFW_E_HI - NFW_E_LO) * PLC_SUB;
 #ifndef GX_NFW_TABLE
 #define GX_NFW_TABLE 1
 #endif
+// Combined spherical force table of one composite: S(u) = sum over its spherical components of Phi_i'(r)/r as a
+// function of u = r^2 (Hernquist GM/(r (r+c)^2), NFW (GM/r_s^3) F(r/r_s), PowerLawCutoff (GM/r_c^3) G(r/r_c)), fitted
+// per potential on the host in long double (plc_table.h: sph_table_for).  Indexed by the bits of r^2, it removes from a
+// right-hand side of the static models everything spherical: the rsqrt of r^2, the Hernquist reciprocals, the NFW /
+// PowerLawCutoff lookups in s = r/r_s (MilkyWayPotential2022: 75 -> 55 FP64 instructions, 3 -> 1 MUFU chains), and the
+// lookup no longer waits for sqrt(r^2).  2^SPH_SUB_BITS = 16 intervals per octave of u (= 32 per octave of r: u^(-3/2)
+// converges like 66^-n), degree 9, u in [2^-14, 2^18) (r from 7.8 pc to 512 kpc): 512 rows x 80 B = 40 KB of shared
+// memory.  Outside the range: the closed forms (spherical_fallback, out of line).
+constexpr int SPH_E_LO = -14, SPH_E_HI = 18, SPH_SUB_BITS = 4;
+constexpr int SPH_NINT = (SPH_E_HI - SPH_E_LO) << SPH_SUB_BITS;
+#ifndef GX_SPH_TABLE
+#define GX_SPH_TABLE 1
+#endif
 __device__ __forceinline__ bool plc_table_eval(const DevPLC &c, double s, double &G, double *dG) {
     return plc_table_eval_at<false>(c.tab, s, G, dG);
 }
@@ -180,6 +204,7 @@ struct alignas(16) DevPot {
     DevHarm harm[MAX_HARM];
     DevHenon henon[MAX_HENON];
     const double *nfw_tab;  // universal NFW force table (nfw_table(), plc_table.h) or nullptr
+    const double *sph_tab;  // this composite's spherical force table S(r^2) (sph_table_for(), plc_table.h) or nullptr
     DevTD td;
 };
 
@@ -351,18 +376,131 @@ __device__ __forceinline__ unsigned nfw_stage(const DevPot &P) {
     return b;
 }
 
+// The combined spherical table S(r^2) of a static model (MW, MW2022, Bovy): which kernels use it, and its staging.
+//   mode 0: not used; 1: Horner (issue-bound fixed-step kernels); 2: Estrin (latency-bound Dopri kernels).
+template <class C>
+__host__ __device__ constexpr bool sph_tab_ok() { return GX_SPH_TABLE && C::is_static && (C::kH + C::kNFW + C::kPLC > 0); }
+// Fixed step: the lookup moves 80 B per lane from scattered rows through the SM's one shared-memory port (~60 port
+// cycles per warp with the bank conflicts); MilkyWayPotential's single-disk step is short enough to saturate it (the
+// NFW table alone cost it 14 %), so the fixed-step kernels take the table from GX_SPH_TABLE_FIXED_MIN_MN disks up or
+// when the model has a PowerLawCutoff bulge (whose own table went through the same port anyway).
+#ifndef GX_SPH_TABLE_FIXED_MIN_MN
+#define GX_SPH_TABLE_FIXED_MIN_MN 3
+#endif
+template <class C>
+__host__ __device__ constexpr bool sph_tab_fixed_ok() {
+    return sph_tab_ok<C>() && (C::kMN >= GX_SPH_TABLE_FIXED_MIN_MN || C::kPLC > 0);
+}
+template <class C>
+__device__ __forceinline__ double *sph_smem() {
+    __shared__ __align__(16) double t[SPH_NINT * PLC_STRIDE];
+    return t;
+}
+// Call once per CTA, by all threads; returns the shared-window address of the table.
+template <class C, bool ON>
+__device__ __forceinline__ unsigned sph_stage(const DevPot &P) {
+    unsigned b = 0;
+    if constexpr (ON) {  // (the host only picks a static model's integrator kernels when P.sph_tab exists)
+        double *t = sph_smem<C>();
+        const double2 *src2 = reinterpret_cast<const double2 *>(P.sph_tab);
+        double2 *t2 = reinterpret_cast<double2 *>(t);
+        for (int idx = threadIdx.x; idx < SPH_NINT * PLC_STRIDE / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
+        __syncthreads();
+        b = (unsigned)__cvta_generic_to_shared(t);
+        asm volatile("" : "+r"(b));
+    }
+    return b;
+}
+
 // ---------------------------------------------------------------------------------------------
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
 // The flattened + spherical part is returned as two scalars: grad = (fh x, fh y, fv z); the kinds that are neither
 // (triaxial logarithmic / ellipsoidal profiles / polynomials) are added to (ex, ey, ez) by gradient<C>() below.
 // Terms of the form GM_i w_i / r (Hernquist, NFW) are summed before the common factor 1/r is applied.
-template <class C, bool PLC_SMEM = false, bool NFW_TAB = false>
+// Sum over the spherical components of Phi'(r)/r at r^2 = r2 (> 0), closed forms / per-kind tables.
+template <class C, bool PLC_SMEM, bool NFW_TAB>
+__device__ __forceinline__ double spherical_factor(const DevPot &P, double r2, unsigned plc_base, unsigned nfw_base) {
+    double fs = 0.0, fr = 0.0;  // fs: terms Phi'/r as they are; fr: terms still to be divided by r
+    const double rinv = rsqrt_fast(r2);
+    const double r = r2 * rinv;
+    const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
+#if GX_HERN_PAIR
+    if constexpr (C::is_static && C::kH == 2) {
+        // bulge + nucleus over one reciprocal: GM1/u1^2 + GM2/u2^2 = (GM1 u2^2 + GM2 u1^2) / (u1 u2)^2
+        // (one MUFU seed + refinement instead of two: -1 FP64 and -3 other instructions per evaluation)
+        const double u1 = r + P.hern[0].c, u2 = r + P.hern[1].c;
+        const double w1 = u1 * u1, w2 = u2 * u2;
+        const double num = fma(P.hern[1].GM, w1, P.hern[0].GM * w2);
+        fr = num * rcp_fast(w1 * w2);
+    } else
+#endif
+    {
+#pragma unroll
+        for (int i = 0; i < C::kH; ++i) {
+            if (!C::is_static && i >= P.n_hern) break;
+            const DevHern &c = P.hern[i];
+            double u = r + c.c;
+            double w = rcp_fast(u * u);  // Phi'/r = GM / ((r+c)^2 r)
+            if (C::is_static && i == 0) fr = c.GM * w; else fr = fma(c.GM, w, fr);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < C::kISO; ++i) {
+        if (i >= P.n_iso) break;
+        const DevIso &c = P.iso[i];
+        double ia = rsqrt_fast(r2 + c.b2);            // 1/a, a = sqrt(r^2 + b^2)
+        double ibpa = rcp_fast(fma(r2 + c.b2, ia, c.b));  // 1/(b + a)
+        fs = fma(c.GM * ia, ibpa * ibpa, fs);         // Phi'/r = GM / (a (b+a)^2)
+    }
+#pragma unroll
+    for (int i = 0; i < C::kNFW; ++i) {
+        if (!C::is_static && i >= P.n_nfw) break;
+        const DevNFW &c = P.nfw[i];
+        const double s = r * c.inv_rs;
+        if constexpr (NFW_TAB) {
+            double F;
+            if (poly_table_eval<true, NFW_E_LO, NFW_NINT>(nullptr, s, F, nullptr, nfw_base)) {
+                fs = fma(c.GM_rs3, F, fs);  // Phi'/r = (GM / rs^3) F(s)
+                continue;
+            }
+        }
+        double m = nfw_menc_shape(s);
+        // Phi'/r = GM m(s) / r^3 = (GM m / r^2) / r
+        if (C::is_static && C::kH == 0 && i == 0) fr = (c.GM * m) * rinv2; else fr = fma(c.GM * m, rinv2, fr);
+    }
+#pragma unroll
+    for (int i = 0; i < C::kPLC; ++i) {
+        if (!C::is_static && i >= P.n_plc) break;
+        const DevPLC &c = P.plc[i];
+        const double s = r * c.inv_rc;
+        double Gs;
+        if (s >= PLC_S_ONE) {
+            fr = fma(c.GM, rinv2, fr);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
+        } else if (PLC_SMEM ? plc_table_eval_at<true>(plc_smem<C>(), s, Gs, nullptr, plc_base)
+                            : plc_table_eval(c, s, Gs, nullptr)) {
+            fs = fma(c.GM_rc3, Gs, fs);  // GM P(a, s^2) / r^3 = (GM / rc^3) G(s)
+        } else {
+            const double Pg = gammainc_P(c.ga, s * s, nullptr);
+            fr = fma(c.GM * Pg, rinv2, fr);
+        }
+    }
+    if (C::is_static && C::kPLC == 0 && !NFW_TAB) fs = fr * rinv; else fs = fma(fr, rinv, fs);
+    return fs;
+}
+// the combined table's out-of-range path (r < 7.8 pc or r > 512 kpc): the closed forms, out of line
+template <class C>
+__device__ __noinline__ double spherical_fallback(const DevPot *P, double r2) {
+    return spherical_factor<C, false, false>(*P, r2, 0u, 0u);
+}
+
+template <class C, bool PLC_SMEM = false, bool NFW_TAB = false, int SPH = 0>
 __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, double y, double z, double &fh, double &fv,
                                                  unsigned plc_base = 0, unsigned nfw_base = 0) {
+    // (SPH != 0: nfw_base is the shared-window address of the combined spherical table)
     const double z2 = z * z;
     const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
-    double fxy = 0.0, fz = 0.0, fs = 0.0, fr = 0.0;  // fs: terms Phi'/r as they are; fr: terms still to be divided by r
+    double fxy = 0.0, fz = 0.0, fs = 0.0;
     double zeta2 = 0.0, rz = 0.0;
 #pragma unroll
     for (int i = 0; i < C::kMN; ++i) {
@@ -376,10 +514,17 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
         double D2 = fma(apz, apz, R2);
         double rD = rsqrt_fast(D2);
         double f = (c.GM * rD) * (rD * rD);  // GM / D^3
-        double g = f * (apz * rz);           // GM/D^3 * (a+zeta)/zeta
-        if (C::is_static && i == 0) { fxy = f; fz = g; }
-        else { fxy += f; fz += g; }
+        if constexpr (C::is_static && C::mn_shared_b) {
+            // one zeta for all disks: sum_i f_i (a_i + zeta) first, the common 1/zeta once after the loop
+            if (i == 0) { fxy = f; fz = f * apz; }
+            else { fxy += f; fz = fma(f, apz, fz); }
+        } else {
+            double g = f * (apz * rz);           // GM/D^3 * (a+zeta)/zeta
+            if (C::is_static && i == 0) { fxy = f; fz = g; }
+            else { fxy += f; fz += g; }
+        }
     }
+    if constexpr (C::is_static && C::mn_shared_b && C::kMN > 0) fz *= rz;
 #pragma unroll
     for (int i = 0; i < C::kSAT; ++i) {
         if (i >= P.n_satoh) break;
@@ -396,70 +541,12 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
                                       : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
     if (any_sph) {
         const double r2 = R2 + z2;  // (R2 carries the TINY that keeps r > 0)
-        const double rinv = rsqrt_fast(r2);
-        const double r = r2 * rinv;
-        const double rinv2 = rinv * rinv;  // (kept apart from the third factor: rinv^3 overflows at r -> 0)
-#if GX_HERN_PAIR
-        if constexpr (C::is_static && C::kH == 2) {
-            // bulge + nucleus over one reciprocal: GM1/u1^2 + GM2/u2^2 = (GM1 u2^2 + GM2 u1^2) / (u1 u2)^2
-            // (one MUFU seed + refinement instead of two: -1 FP64 and -3 other instructions per evaluation)
-            const double u1 = r + P.hern[0].c, u2 = r + P.hern[1].c;
-            const double w1 = u1 * u1, w2 = u2 * u2;
-            const double num = fma(P.hern[1].GM, w1, P.hern[0].GM * w2);
-            fr = num * rcp_fast(w1 * w2);
-        } else
-#endif
-        {
-#pragma unroll
-            for (int i = 0; i < C::kH; ++i) {
-                if (!C::is_static && i >= P.n_hern) break;
-                const DevHern &c = P.hern[i];
-                double u = r + c.c;
-                double w = rcp_fast(u * u);  // Phi'/r = GM / ((r+c)^2 r)
-                if (C::is_static && i == 0) fr = c.GM * w; else fr = fma(c.GM, w, fr);
-            }
+        if constexpr (SPH != 0) {
+            if (!poly_table_eval<true, SPH_E_LO, SPH_NINT, SPH_SUB_BITS, SPH == 2>(nullptr, r2, fs, nullptr, nfw_base))
+                fs = spherical_fallback<C>(&P, r2);
+        } else {
+            fs = spherical_factor<C, PLC_SMEM, NFW_TAB>(P, r2, plc_base, nfw_base);
         }
-#pragma unroll
-        for (int i = 0; i < C::kISO; ++i) {
-            if (i >= P.n_iso) break;
-            const DevIso &c = P.iso[i];
-            double ia = rsqrt_fast(r2 + c.b2);            // 1/a, a = sqrt(r^2 + b^2)
-            double ibpa = rcp_fast(fma(r2 + c.b2, ia, c.b));  // 1/(b + a)
-            fs = fma(c.GM * ia, ibpa * ibpa, fs);         // Phi'/r = GM / (a (b+a)^2)
-        }
-#pragma unroll
-        for (int i = 0; i < C::kNFW; ++i) {
-            if (!C::is_static && i >= P.n_nfw) break;
-            const DevNFW &c = P.nfw[i];
-            const double s = r * c.inv_rs;
-            if constexpr (NFW_TAB) {
-                double F;
-                if (poly_table_eval<true, NFW_E_LO, NFW_NINT>(nullptr, s, F, nullptr, nfw_base)) {
-                    fs = fma(c.GM_rs3, F, fs);  // Phi'/r = (GM / rs^3) F(s)
-                    continue;
-                }
-            }
-            double m = nfw_menc_shape(s);
-            // Phi'/r = GM m(s) / r^3 = (GM m / r^2) / r
-            if (C::is_static && C::kH == 0 && i == 0) fr = (c.GM * m) * rinv2; else fr = fma(c.GM * m, rinv2, fr);
-        }
-#pragma unroll
-        for (int i = 0; i < C::kPLC; ++i) {
-            if (!C::is_static && i >= P.n_plc) break;
-            const DevPLC &c = P.plc[i];
-            const double s = r * c.inv_rc;
-            double Gs;
-            if (s >= PLC_S_ONE) {
-                fr = fma(c.GM, rinv2, fr);  // beyond the table P(a, s^2) == 1 in fp64: Kepler
-            } else if (PLC_SMEM ? plc_table_eval_at<true>(plc_smem<C>(), s, Gs, nullptr, plc_base)
-                                : plc_table_eval(c, s, Gs, nullptr)) {
-                fs = fma(c.GM_rc3, Gs, fs);  // GM P(a, s^2) / r^3 = (GM / rc^3) G(s)
-            } else {
-                const double Pg = gammainc_P(c.ga, s * s, nullptr);
-                fr = fma(c.GM * Pg, rinv2, fr);
-            }
-        }
-        if (C::is_static && C::kPLC == 0 && !NFW_TAB) fs = fr * rinv; else fs = fma(fr, rinv, fs);
     }
     fh = fxy + fs;
     fv = fz + fs;
@@ -565,7 +652,7 @@ __device__ __noinline__ void gradient_td(const DevTD &R, double t, double x, dou
 
 // gradient (hot path of the integrators): g = grad Phi(q).  ~1-2 ulp per term, branch-free except the
 // small-s NFW series and the incomplete-gamma routine.
-template <class C, bool PLC_SMEM = false, bool NFW_TAB = false>
+template <class C, bool PLC_SMEM = false, bool NFW_TAB = false, int SPH = 0>
 __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, double z, double &gx_, double &gy_,
                                          double &gz_, double t = 0.0, unsigned nfw_base = 0) {
     if (!C::is_static && !C::basic_only && P.td.n > 0) {  // time-dependent composite (runtime path only)
@@ -573,7 +660,7 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
         return;
     }
     double fh, fv;
-    gradient_factors<C, PLC_SMEM, NFW_TAB>(P, x, y, z, fh, fv, 0, nfw_base);
+    gradient_factors<C, PLC_SMEM, NFW_TAB, SPH>(P, x, y, z, fh, fv, 0, nfw_base);
     gx_ = fh * x;
     gy_ = fh * y;
     gz_ = fv * z;

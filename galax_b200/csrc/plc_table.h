@@ -18,6 +18,9 @@
 #include <mutex>
 #include <vector>
 
+#include <string.h>
+
+#include "../../include/galax_b200.h"
 #include "gx_potential.cuh"
 
 namespace gx {
@@ -167,6 +170,89 @@ static const double *plc_table_for(double a, double *max_rel_err_out = nullptr) 
         }
     }
     cache.push_back({dev, a, d, worst});
+    if (max_rel_err_out) *max_rel_err_out = worst;
+    return d;
+}
+
+// ---- combined spherical force table of one composite (SPH_* in gx_potential.cuh) --------------------------------
+// S(u) = sum_i Phi_i'(r)/r at r = sqrt(u) over the composite's spherical components, in long double from the same fp64
+// parameters (G m as the kernels form it) the closed forms use.
+struct SphComp { int kind; double GM, p1, p2; };  // Hernquist (GM, c) / NFW (GM, r_s) / PowerLawCutoff (GM, r_c, a)
+static long double sph_S_ld(const std::vector<SphComp> &cs, long double u) {
+    const long double r = sqrtl(u);
+    long double sum = 0.0L;
+    for (const SphComp &c : cs) {
+        if (c.kind == GX_KIND_HERNQUIST) {
+            const long double w = r + (long double)c.p1;
+            sum += (long double)c.GM / (r * w * w);
+        } else if (c.kind == GX_KIND_NFW) {
+            const long double rs = c.p1;
+            sum += (long double)c.GM / (rs * rs * rs) * nfw_F_ld(r / rs);
+        } else {  // PowerLawCutoff: P(a, s^2) == 1 to long-double precision beyond s^2 = 64 (a <= 3/2)
+            const long double rc = c.p1, s = r / rc;
+            const long double g = (s * s < 64.0L) ? plc_G_ld(c.p2, s) : 1.0L / (s * s * s);
+            sum += (long double)c.GM / (rc * rc * rc) * g;
+        }
+    }
+    return sum;
+}
+
+// Fit of the table (host only; also used by gx_force_table): coef[SPH_NINT][PLC_DEG + 1], returns the worst relative
+// error of the fp64 Horner evaluation against the long-double function on a 41-point grid per interval.
+static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
+    double worst = 0.0;
+    for (int j = 0; j < SPH_NINT; ++j) {
+        const int e = SPH_E_LO + (j >> SPH_SUB_BITS), sub = j & ((1 << SPH_SUB_BITS) - 1);
+        const long double base = ldexpl(1.0L, e), nsub = (long double)(1 << SPH_SUB_BITS);
+        fit_interval([&cs](long double u) { return sph_S_ld(cs, u); }, base * (1.0L + sub / nsub),
+                     base * (1.0L + (sub + 1) / nsub), coef + (size_t)j * (PLC_DEG + 1), &worst);
+    }
+    return worst;
+}
+
+// The device table of this set of spherical components on the current device: built (a few ms of host time) and
+// uploaded on FIRST use of a potential, immutable afterwards and kept for the life of the process -- at most
+// SPH_CACHE_MAX distinct (device, parameter set) entries; beyond that, or if the fit misses 1e-14, nullptr (the caller
+// then runs the composite through the runtime-count kernels).
+constexpr size_t SPH_CACHE_MAX = 256;
+static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr) {
+    struct Entry { int device; std::vector<SphComp> cs; double *dev_ptr; double max_rel_err; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    int dev = 0;
+    if (cs.empty() || cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::vector<double> *fitted = nullptr;
+    static std::vector<std::vector<double>> fits;  // host copies, index-aligned with `cache` (another device re-uses the fit)
+    for (size_t k = 0; k < cache.size(); ++k) {
+        const Entry &e = cache[k];
+        if (e.cs.size() == cs.size() && memcmp(e.cs.data(), cs.data(), cs.size() * sizeof(SphComp)) == 0) {
+            if (e.device == dev) {
+                if (max_rel_err_out) *max_rel_err_out = e.max_rel_err;
+                return e.dev_ptr;
+            }
+            fitted = &fits[k];
+        }
+    }
+    if (cache.size() >= SPH_CACHE_MAX) return nullptr;
+    std::vector<double> host;
+    double worst = 0.0;
+    if (fitted) {
+        host = *fitted;
+    } else {
+        host.resize((size_t)SPH_NINT * (PLC_DEG + 1));
+        worst = sph_table_fit(cs, host.data());
+    }
+    double *d = nullptr;
+    if (worst < 1e-14) {
+        if (cudaMalloc(&d, host.size() * sizeof(double)) != cudaSuccess) return nullptr;  // (not cached: may succeed later)
+        if (cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(d);
+            return nullptr;
+        }
+    }
+    cache.push_back({dev, cs, d, worst});
+    fits.push_back(std::move(host));
     if (max_rel_err_out) *max_rel_err_out = worst;
     return d;
 }

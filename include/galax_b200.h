@@ -15,8 +15,10 @@
  *   - units: whatever unit system the potential parameters are expressed in (galax: kpc, Myr, Msun);
  *   - re-entrant and safe to call from several host threads / on several streams: the potential is passed by value
  *     into each launch (kernel-parameter constant bank).  Process-wide state: (1) an append-only, mutex-guarded cache
- *     of immutable force tables (NFW 30 KB, PowerLawCutoff 35 KB per exponent; device memory, allocated on FIRST use --
- *     the one allocation an enqueue-only entry can make, so warm an entry up once before capturing it into a graph);
+ *     of immutable force tables (NFW 30 KB, PowerLawCutoff 35 KB per exponent, and for the three named Milky-Way
+ *     models 40 KB per distinct set of spherical-component parameters, at most 256 sets; device memory, fitted,
+ *     allocated and uploaded on FIRST use -- the one allocation an enqueue-only entry can make, so warm an entry up
+ *     once with a potential before capturing it into a graph);
  *     (2) for the adaptive integrators, a per-device __constant__ copy of the potential that a launch reads only when
  *     no launch on another stream can still be reading a different one -- otherwise, and always under stream capture,
  *     the launch carries the potential itself (same results, a few per cent slower).  No entry ever blocks the host
@@ -260,6 +262,13 @@ int gx_jax_fardal_chain(uint32_t key_hi, uint32_t key_lo, int64_t M, double *dra
  * function.  coef may be NULL (only the layout / the error are wanted). */
 int gx_force_table(int32_t which, double a, double *coef, int64_t capacity, int32_t *n_intervals, int32_t *degree,
                    int32_t *e_lo, int32_t *sub_bits, double *max_rel_err);
+/* Host only (no CUDA call): the COMBINED spherical force table of a composite, S(u) = sum over its Hernquist / NFW /
+ * PowerLawCutoff components of Phi_i'(r)/r as a function of u = r^2 -- what the integrators of the three named
+ * Milky-Way models look up instead of evaluating the spherical components (fitted per potential on first use, cached
+ * per device; same row layout as gx_force_table, intervals per octave of u).  GX_ERR_UNSUPPORTED if the potential has
+ * no spherical component of these kinds. */
+int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
+                             int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err);
 /* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x), 4 NFW shape ln(1+s) - s/(1+s),
  * 5 NFW force table F(s) = shape / s^3, 6 / 7 PowerLawCutoff table G(s) = P(a, s^2) / s^3 and dG/ds (NaN outside the
  * tabulated range) */

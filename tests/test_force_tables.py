@@ -66,3 +66,80 @@ def test_bad_arguments():
     assert L.gx_force_table(1, -1.0, None, 0, None, None, None, None, None) == -1
     buf = np.empty(10)
     assert L.gx_force_table(0, 0.0, buf.ctypes.data, 10, None, None, None, None, None) == -1  # capacity too small
+
+
+# ---- the combined spherical table S(r^2) of a composite (gx_spherical_force_table) ------------------------------
+def sph_table(pot):
+    L = _lib.lib()
+    cs = pot.c_struct()
+    n, deg, lo, sb, err = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+    assert L.gx_spherical_force_table(C.byref(cs), None, 0, C.byref(n), C.byref(deg), C.byref(lo), C.byref(sb), None) == 0
+    coef = np.empty((n.value, deg.value + 1))
+    assert L.gx_spherical_force_table(C.byref(cs), coef.ctypes.data, coef.size, None, None, None, None, C.byref(err)) == 0
+    return coef, lo.value, sb.value, err.value
+
+
+def evaluate_estrin(coef, e_lo, sub_bits, s):
+    """The Estrin form the Dopri kernels use (poly_table_eval<..., ESTRIN = true>), in numpy."""
+    s = np.asarray(s, dtype=np.float64)
+    hi = (s.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    j = (hi >> (20 - sub_bits)) - (1023 + e_lo) * (1 << sub_bits)
+    m = 2.0 * np.frexp(s)[0]
+    sub = (hi >> (20 - sub_bits)) & ((1 << sub_bits) - 1)
+    t = m * float(2 << sub_bits) - (float(2 << sub_bits) + 2.0 * sub + 1.0)
+    c = coef[j]
+    t2 = t * t; t4 = t2 * t2; t8 = t4 * t4
+    p = [c[:, 2 * k + 1] * t + c[:, 2 * k] for k in range(5)]
+    return p[4] * t8 + ((p[3] * t2 + p[2]) * t4 + (p[1] * t2 + p[0]))
+
+
+def sph_reference(pot, r):
+    """sum of Phi'(r)/r over the spherical components, 30 digits (closed forms of the reference's potentials:
+    hernquist.py:60-66, nfw/base.py:326-338, powerlawcutoff.py:88-117)."""
+    import galax_b200._lib as L_
+    mp.mp.dps = 30
+    cs = pot.c_struct()
+    out = []
+    for x in r:
+        x = mp.mpf(float(x)); tot = mp.mpf(0)
+        for i in range(cs.n):
+            c = cs.c[i]
+            GM = mp.mpf(float(np.float64(cs.G) * np.float64(c.p[0])))  # G m as the kernels form it (one fp64 product)
+            if c.kind == L_.KIND_HERNQUIST:
+                tot += GM / (x * (x + mp.mpf(c.p[1])) ** 2)
+            elif c.kind == L_.KIND_NFW:
+                s = x / mp.mpf(c.p[1])
+                tot += GM * (mp.log1p(s) - s / (1 + s)) / x ** 3
+            elif c.kind == L_.KIND_PLC:
+                a = mp.mpf(1.5) - mp.mpf(c.p[1]) / 2
+                tot += GM * mp.gammainc(a, 0, (x / mp.mpf(c.p[2])) ** 2, regularized=True) / x ** 3
+        out.append(float(tot))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("name", ["MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014"])
+def test_combined_spherical_table_on_the_host(name):
+    import galax_b200.potential as gp
+
+    pot = getattr(gp, name)()
+    coef, e_lo, sb, err = sph_table(pot)
+    assert coef.shape == (512, 10) and e_lo == -14 and sb == 4 and err < 4e-16
+    rng = np.random.default_rng(5)
+    edges = np.ldexp(1.0 + np.arange(16) / 16.0, rng.integers(-14, 18, 16))
+    below = np.nextafter(edges, 0)
+    u = np.concatenate([2.0 ** rng.uniform(-14, 18, 300), edges, below[below >= 2.0**-14], [2.0**-14, np.nextafter(2.0**18, 0)]])
+    ref = sph_reference(pot, np.sqrt(u) if False else [mp.sqrt(mp.mpf(float(x))) for x in u])
+    for ev in (evaluate, evaluate_estrin):
+        S = ev(coef, e_lo, sb, u)
+        assert np.abs(S / ref - 1).max() < 8e-16, ev.__name__
+
+
+def test_combined_spherical_table_bad_arguments():
+    import galax_b200.potential as gp
+
+    L = _lib.lib()
+    cs = gp.MiyamotoNagaiPotential(m_tot=1e10, a=3.0, b=0.3).c_struct()
+    assert L.gx_spherical_force_table(C.byref(cs), None, 0, None, None, None, None, None) == -2  # GX_ERR_UNSUPPORTED: no spherical component
+    cs = gp.MilkyWayPotential().c_struct()
+    buf = np.empty(10)
+    assert L.gx_spherical_force_table(C.byref(cs), buf.ctypes.data, 10, None, None, None, None, None) == -1

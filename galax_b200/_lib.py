@@ -60,6 +60,10 @@ class GxPid(C.Structure):
     ]  # fmt: skip
 
 
+class GxOrbitEpilogue(C.Structure):
+    _fields_ = [("energy", C.c_void_p), ("angmom", C.c_void_p), ("tidal", C.c_void_p)]
+
+
 class GalaxB200Error(RuntimeError):
     pass
 
@@ -125,6 +129,15 @@ _SIGNATURES = {
     "gx_integrate_fixed": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                      C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_integrate_fixed_epilogue": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                              C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                                              C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GxOrbitEpilogue),
+                                              C.c_void_p]),
+    "gx_integrate_adaptive_epilogue": (C.c_int, [C.c_int32, C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p,
+                                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                                 C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.POINTER(GxOrbitEpilogue), C.c_void_p]),
     "gx_integrate_dopri8": (C.c_int, [C.POINTER(GxPotential), C.POINTER(GxPid), C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_int64,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

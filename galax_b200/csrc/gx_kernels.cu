@@ -48,8 +48,10 @@ static void fill_gamma_tab(GammaTab &g, double a) {
 // carry the raw parameters to the device for per-stage evaluation (integrators), or refuse.
 enum TdMode { TD_REJECT = 0, TD_FREEZE = 1, TD_INTEGRATE = 2 };
 
+// may_upload = false (the caller's stream is being captured into a graph): a combined spherical table that is not in the
+// cache yet is not fitted and uploaded now -- the composite then runs through the runtime-count kernels.
 static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, bool use_device = true,
-                        TdMode td_mode = TD_REJECT, double t_freeze = 0.0) {
+                        TdMode td_mode = TD_REJECT, double t_freeze = 0.0, bool may_upload = true) {
     if (!pot_in || pot_in->n < 0 || pot_in->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
     memset(&D, 0, sizeof D);
     gx_potential frozen = *pot_in;
@@ -216,7 +218,7 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
                 if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, G * c.p[0], c.p[1], 0.0});
                 if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
             }
-            D.sph_tab = sph_table_for(cs);
+            D.sph_tab = sph_table_for(cs, nullptr, may_upload);
             if (D.sph_tab == nullptr) model = MODEL_GENERIC;
         }
 #endif
@@ -239,6 +241,11 @@ static inline bool is_basic_composite(const DevPot &D, Model model) {
 }
 
 static inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : GX_ERR_CUDA; }
+static inline bool stream_is_capturing(void *stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return cap != cudaStreamCaptureStatusNone;
+}
 
 // ================================================================================================
 // K1 bulk evaluation
@@ -426,11 +433,11 @@ __device__ __forceinline__ int save_staged(const A &a, long long i, int k) {  //
     return ph < k ? ph : k;
 }
 // (a rolled loop: the integrators' register allocation should not pay for this cold path)
-__device__ __forceinline__ void save_flush_n(double *qd, double *pd, int n) {
+__device__ __forceinline__ void save_flush_n(double *qd, double *pd, int n, int nv) {
     const int bd = blockDim.x;
     const double *b = save_buf() + threadIdx.x;
 #pragma unroll 1
-    for (int s = 0; s < n; ++s, b += 6 * bd, qd += 3, pd += 3) {
+    for (int s = 0; s < n; ++s, b += nv * bd, qd += 3, pd += 3) {
         qd[0] = b[0]; qd[1] = b[bd]; qd[2] = b[2 * bd];
         pd[0] = b[3 * bd]; pd[1] = b[4 * bd]; pd[2] = b[5 * bd];
     }
@@ -439,7 +446,7 @@ template <class A>
 __device__ __forceinline__ void save_flush(const A &a, long long i, int kend) {  // write out what is staged before kend
     if (!a.stage) return;
     const int n = save_staged(a, i, kend);
-    if (n > 0) save_flush_n(a.q + i * a.sn + 3LL * (kend - n), a.p + i * a.sn + 3LL * (kend - n), n);
+    if (n > 0) save_flush_n(a.q + i * a.sn + 3LL * (kend - n), a.p + i * a.sn + 3LL * (kend - n), n, a.epi.nv);
 }
 // Where save k of particle i goes: component c of q at q[c * st], of p at p[c * st] -- the output itself (direct
 // stores, or the save that closes a run) or the lane's staging column.  The caller stores the six values as it
@@ -455,7 +462,7 @@ __device__ __forceinline__ SaveDst save_dst(const A &a, long long i, int k) {
         d.q = a.q + i * a.sn + k * a.sk; d.p = a.p + i * a.sn + k * a.sk; d.st = a.sc;
     } else if ((((unsigned)a.T * (unsigned)i + (unsigned)k + 1u) & 3u) != 0u) {  // not at a sector boundary: stage
         const int bd = blockDim.x;
-        d.q = save_buf() + threadIdx.x + (6 * save_staged(a, i, k)) * bd; d.p = d.q + 3 * bd; d.st = bd;
+        d.q = save_buf() + threadIdx.x + (a.epi.nv * save_staged(a, i, k)) * bd; d.p = d.q + 3 * bd; d.st = bd;
     } else {  // save k ends on a sector boundary: it goes straight out, behind the staged ones (save_commit)
         d.q = a.q + i * a.sn + 3LL * k; d.p = a.p + i * a.sn + 3LL * k; d.st = 1;
     }
@@ -487,8 +494,120 @@ __device__ __forceinline__ void save_fill_nan(const A &a, long long i, int k) {
 #ifndef GX_SAVE_STAGE
 #define GX_SAVE_STAGE 1
 #endif
-static inline size_t save_stage_bytes(int layout, int T, int block) {
-    return (GX_SAVE_STAGE && layout == GX_LAYOUT_NT3 && T >= SAVE_STAGE_MIN_T) ? (size_t)block * (SAVE_SLOTS - 1) * 6 * sizeof(double) : 0;
+static inline size_t save_stage_bytes(int layout, int T, int block, int nv = 6) {
+    return (GX_SAVE_STAGE && layout == GX_LAYOUT_NT3 && T >= SAVE_STAGE_MIN_T) ? (size_t)block * (SAVE_SLOTS - 1) * nv * sizeof(double) : 0;
+}
+
+// ---- Orbit post-processing fused into the save path --------------------------------------------------
+// Orbit.total_energy / angular_momentum (coordinates/_src/pscs/base.py:182-330) and tidal_tensor along the orbit
+// (potential/_src/register_funcs.py:347-377) are functions of the saved (q, p) alone; evaluated on the values while they
+// are still in registers they cost one potential (and Hessian) evaluation per save and no second pass over the saved
+// states (C2: 48 GB).  They travel through the same per-lane staging as q and p -- a staged save is nv doubles: q, p,
+// then L (3) and E (1), then the nine tidal-tensor entries -- and leave with the same flush: 4 saves of E are exactly
+// one 32-byte sector, of L three, of the tensor nine.  Kernels are instantiated with EPI = true only for these calls;
+// the default kernels do not contain any of this.
+struct EpiOut {
+    double *E, *L, *TT;  // [N,T], [N,T,3], [N,T,3,3] (GX_LAYOUT_NT3) / [T,N], [T,3,N], [T,9,N] (GX_LAYOUT_T3N); any may be null
+    int t3n;
+    int nv;  // doubles per staged save: 6, 10 (L, E) or 19 (L, E, tidal tensor)
+};
+// (explicit FMA forms: the fused epilogue and the stand-alone pass gx_energy_angmom give the same bits)
+__device__ __forceinline__ double kinetic_plus(double phi, double vx, double vy, double vz) {
+    return fma(0.5, fma(vx, vx, fma(vy, vy, vz * vz)), phi);
+}
+__device__ __forceinline__ void cross3(double x, double y, double z, double vx, double vy, double vz, double &lx,
+                                       double &ly, double &lz) {
+    lx = fma(y, vz, -(z * vy)); ly = fma(z, vx, -(x * vz)); lz = fma(x, vy, -(y * vx));
+}
+template <class A>
+__device__ __forceinline__ void epilogue_flush(const A &a, long long i, int kend) {  // staged extras before save kend
+    if (!a.stage) return;
+    const int n = save_staged(a, i, kend);
+    const EpiOut &e = a.epi;
+    const int bd = blockDim.x;
+    const double *b = save_buf() + threadIdx.x + 6 * bd;
+    long long r = i * a.T + (kend - n);
+#pragma unroll 1
+    for (int s = 0; s < n; ++s, b += e.nv * bd, ++r) {
+        if (e.L) { e.L[3 * r] = b[0]; e.L[3 * r + 1] = b[bd]; e.L[3 * r + 2] = b[2 * bd]; }
+        if (e.E) e.E[r] = b[3 * bd];
+        if (e.TT) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) e.TT[9 * r + c] = b[(4 + c) * bd];
+        }
+    }
+}
+// E, L and the tidal tensor of save k of particle i, given the saved state (out of line: cold beside the step loop)
+template <class C, class A>
+__device__ __noinline__ void epilogue_put(const DevPot *Pp, const A *ap, long long i, int k, double qx, double qy,
+                                          double qz, double px, double py, double pz) {
+    const A &a = *ap;
+    const EpiOut &e = a.epi;
+    double v[13];
+    cross3(qx, qy, qz, px, py, pz, v[0], v[1], v[2]);
+    v[3] = e.E ? kinetic_plus(potential_value<C>(*Pp, qx, qy, qz), px, py, pz) : 0.0;
+    if (e.TT) {
+        double g[3], H[6];
+        grad_hess<C>(*Pp, qx, qy, qz, g, H);
+        const double tr3 = (H[0] + H[3] + H[5]) * (1.0 / 3.0);  // J - tr(J)/3 I
+        v[4] = H[0] - tr3; v[5] = H[1]; v[6] = H[2];
+        v[7] = H[1]; v[8] = H[3] - tr3; v[9] = H[4];
+        v[10] = H[2]; v[11] = H[4]; v[12] = H[5] - tr3;
+    }
+    if (e.t3n) {
+        const long long N = a.N;
+        if (e.E) e.E[(long long)k * N + i] = v[3];
+        if (e.L) { e.L[(3LL * k) * N + i] = v[0]; e.L[(3LL * k + 1) * N + i] = v[1]; e.L[(3LL * k + 2) * N + i] = v[2]; }
+        if (e.TT) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) e.TT[(9LL * k + c) * N + i] = v[4 + c];
+        }
+        return;
+    }
+    if (a.stage && (((unsigned)a.T * (unsigned)i + (unsigned)k + 1u) & 3u) != 0u) {  // inside a run: stage
+        const int bd = blockDim.x;
+        double *b = save_buf() + threadIdx.x + (e.nv * save_staged(a, i, k) + 6) * bd;
+        b[0] = v[0]; b[bd] = v[1]; b[2 * bd] = v[2]; b[3 * bd] = v[3];
+        if (e.TT) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) b[(4 + c) * bd] = v[4 + c];
+        }
+        return;
+    }
+    epilogue_flush(a, i, k);  // the save that closes a run (or direct stores): behind the staged ones
+    const long long r = i * a.T + k;
+    if (e.L) { e.L[3 * r] = v[0]; e.L[3 * r + 1] = v[1]; e.L[3 * r + 2] = v[2]; }
+    if (e.E) e.E[r] = v[3];
+    if (e.TT) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) e.TT[9 * r + c] = v[4 + c];
+    }
+}
+// end of a particle: what is still staged, then NaN for the saves it never reached (as save_fill_nan does for q, p)
+template <class A>
+__device__ __noinline__ void epilogue_finish(const A *ap, long long i, int k) {
+    const A &a = *ap;
+    const EpiOut &e = a.epi;
+    epilogue_flush(a, i, k);
+    const double NANV = __longlong_as_double(0x7ff8000000000000LL);
+    for (; k < a.T; ++k) {
+        const long long r = i * a.T + k, N = a.N;
+        if (e.E) e.E[e.t3n ? (long long)k * N + i : r] = NANV;
+        if (e.L) for (int c = 0; c < 3; ++c) e.L[e.t3n ? (3LL * k + c) * N + i : 3 * r + c] = NANV;
+        if (e.TT) for (int c = 0; c < 9; ++c) e.TT[e.t3n ? (9LL * k + c) * N + i : 9 * r + c] = NANV;
+    }
+}
+
+template <bool EPI, class C, class A>
+__device__ __forceinline__ void save_put_epi(const DevPot &P, const A &a, long long i, int k, double qx, double qy,
+                                             double qz, double px, double py, double pz) {
+    save_put(a, i, k, qx, qy, qz, px, py, pz);
+    if constexpr (EPI) epilogue_put<C>(&P, &a, i, k, qx, qy, qz, px, py, pz);
+}
+template <bool EPI, class A>
+__device__ __forceinline__ void save_finish(const A &a, long long i, int k) {
+    if constexpr (EPI) epilogue_finish(&a, i, k);
+    save_fill_nan(a, i, k);
 }
 
 struct FixedArgs {
@@ -500,6 +619,7 @@ struct FixedArgs {
     double t0, t1, dt0;
     int T, hit_max_steps;
     int stage;  // saves go through the per-lane staging buffer (save_put)
+    EpiOut epi;  // fused E / L / tidal-tensor outputs (EPI kernels); epi.nv = 6 otherwise
 };
 
 // Run-length form of the shared time grid (k_integrate_fixed_seg).  diffrax's grid t_{n+1} = fl(t_n + dt0) has a step
@@ -588,11 +708,14 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #ifndef GX_FIXED_SEG
 #define GX_FIXED_SEG 1
 #endif
-template <class C, int SCHEME, bool FWD>
+#ifndef GX_FIXED_SMALL
+#define GX_FIXED_SMALL 1
+#endif
+template <class C, int SCHEME, bool FWD, bool EPI = false, bool SMALL = false>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
-    // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
-    // tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 1 : 0;
+    // tables in shared memory: the composite's combined spherical table (MW2022, Bovy; every static model in small
+    // batches, see k_integrate_fixed_seg), else the PowerLawCutoff / NFW tables of round 1 (GX_SPH_TABLE=0 builds)
+    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? 1 : 0);
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     unsigned plc_base = 0, nfw_base = 0;
@@ -611,7 +734,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
     auto load_ts = [&](int kk) { return (kk < a.T) ? (FWD ? __ldg(a.ts + kk) : -__ldg(a.ts + kk)) : INF; };
     double tsave = load_ts(k);
     while (tsave <= T0) {  // save times equal to t0 return y0
-        save_put(a, i, k, qx, qy, qz, px, py, pz);
+        save_put_epi<EPI, C>(P, a, i, k, qx, qy, qz, px, py, pz);
         ++k;
         tsave = load_ts(k);
     }
@@ -664,7 +787,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
         if (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
             do {
                 const double th = (tsave - tprev) / (tnext - tprev);
-                save_put(a, i, k, __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx))),
+                save_put_epi<EPI, C>(P, a, i, k, __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx))),
                          __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy))), __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz))),
                          __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px))), __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py))),
                          __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz))));
@@ -678,7 +801,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
     }
     int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
     if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
-    save_fill_nan(a, i, k);
+    save_finish<EPI>(a, i, k);
     if (a.status) a.status[i] = st;
 }
 
@@ -688,13 +811,17 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
 // (fma(j, h, t_s) is the grid time itself) instead of a DADD + 2 DSETP + FSEL per step, the step is a uniform
 // constant-bank operand, and the state is updated in place.  Saves are interpolated exactly as in k_integrate_fixed
 // (same theta, same operations): results are bit-identical to it.
-template <class C, bool FWD>
+// SMALL: a batch too small to fill the machine (C1's 10^4 particles are one warp on half of the schedulers) is bound by
+// the dependent chain of ONE step, not by issue slots or the shared-memory port: such launches take the combined
+// spherical table for every static model, in its 4-deep Estrin form -- q -> r^2 -> lookup -> p instead of
+// q -> r^2 -> rsqrt -> r -> s -> 1 + s -> rcp -> table log -> shape -> 1/r^3 -> p.
+template <class C, bool FWD, bool SMALL = false, bool EPI = false>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS)
 k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
     // tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 1 : 0;
+    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? 1 : 0);
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     unsigned plc_base = 0, nfw_base = 0;
@@ -711,7 +838,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     auto load_ts = [&](int kk) { return (kk < a.T) ? (FWD ? __ldg(a.ts + kk) : -__ldg(a.ts + kk)) : INF; };
     double tsave = load_ts(k);
     while (tsave <= T0) {  // save times equal to t0 return y0
-        save_put(a, i, k, qx, qy, qz, px, py, pz);
+        save_put_epi<EPI, C>(P, a, i, k, qx, qy, qz, px, py, pz);
         ++k;
         tsave = load_ts(k);
     }
@@ -777,7 +904,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 }
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
                     const double th = (tsave - tprev) / (tnext - tprev);
-                    save_put(a, i, k, __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx))),
+                    save_put_epi<EPI, C>(P, a, i, k, __dadd_rn(qx, __dmul_rn(th, __dsub_rn(nqx, qx))),
                              __dadd_rn(qy, __dmul_rn(th, __dsub_rn(nqy, qy))), __dadd_rn(qz, __dmul_rn(th, __dsub_rn(nqz, qz))),
                              __dadd_rn(px, __dmul_rn(th, __dsub_rn(npx, px))), __dadd_rn(py, __dmul_rn(th, __dsub_rn(npy, py))),
                              __dadd_rn(pz, __dmul_rn(th, __dsub_rn(npz, pz))));
@@ -792,7 +919,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     }
     int st = a.hit_max_steps ? GX_MAX_STEPS_REACHED : GX_OK;
     if (!(finite3(qx, qy, qz) && finite3(px, py, pz))) st = (st == GX_OK) ? GX_NONFINITE : st;
-    save_fill_nan(a, i, k);
+    save_finish<EPI>(a, i, k);
     if (a.status) a.status[i] = st;
 }
 
@@ -815,6 +942,7 @@ struct Dp8Args {
     double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax, dtmin, dtmax, dt0;
     int T;
     int stage;  // saves go through the per-lane staging buffer (save_put)
+    EpiOut epi;  // fused E / L / tidal-tensor outputs (EPI kernels); epi.nv = 6 otherwise
 };
 
 template <class TB>
@@ -938,7 +1066,7 @@ constexpr int REC_DOUBLES = GX_DENSE_RECORD_DOUBLES;  // tprev, tnext, hd, q0[3]
 // alternatives on B200 (MW2022, rtol = atol = 1e-10, 3e5 particles): everything inlined with the stages in
 // registers 161 ms (I-cache bound: 105 KB of SASS); stages in shared memory 151-205 ms; this version 121 ms.
 // TB = TabDp8 (diffrax.Dopri8) or TabDp5 (diffrax.Dopri5): same kernel, tableau resolved at compile time.
-template <class C, class TB, bool IMG>
+template <class C, class TB, bool IMG, bool EPI = false>
 __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
 k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     constexpr int NS = TB::NS;
@@ -981,7 +1109,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         // ---------------- finished (or failed) particle: write remaining saves, counters, free the lane
         if (have && (!(tprev < T1) || st != GX_OK || (a.max_steps >= 0 && ntot >= a.max_steps))) {
             if (tprev < T1 && st == GX_OK) st = GX_MAX_STEPS_REACHED;
-            save_fill_nan(a, idx, k);  // (writes out what is still staged; NaN for saves never reached)
+            save_finish<EPI>(a, idx, k);  // (writes out what is still staged; NaN for saves never reached)
             k = a.T;
             if (a.status) a.status[idx] = st;
             if (a.n_acc) a.n_acc[idx] = nacc;
@@ -1007,7 +1135,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                 at_dtmin = false;
                 tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 while (tsave <= T0) {
-                    save_put(a, idx, k, q0x, q0y, q0z, p0x, p0y, p0z);
+                    save_put_epi<EPI, C>(P, a, idx, k, q0x, q0y, q0z, p0x, p0y, p0z);
                     ++k;
                     tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 }
@@ -1154,14 +1282,20 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                     }
                 }
                 const double thh = th * hd;
-                const SaveDst d = save_dst(a, idx, k);
-                d.q[0] = fma(hd2, wqx, fma(thh, p0x, q0x));
-                d.q[d.st] = fma(hd2, wqy, fma(thh, p0y, q0y));
-                d.q[2 * d.st] = fma(hd2, wqz, fma(thh, p0z, q0z));
-                d.p[0] = fma(hd, wpx, p0x);
-                d.p[d.st] = fma(hd, wpy, p0y);
-                d.p[2 * d.st] = fma(hd, wpz, p0z);
-                save_commit(a, idx, k);
+                if constexpr (EPI) {
+                    save_put_epi<EPI, C>(P, a, idx, k, fma(hd2, wqx, fma(thh, p0x, q0x)), fma(hd2, wqy, fma(thh, p0y, q0y)),
+                                         fma(hd2, wqz, fma(thh, p0z, q0z)), fma(hd, wpx, p0x), fma(hd, wpy, p0y),
+                                         fma(hd, wpz, p0z));
+                } else {
+                    const SaveDst d = save_dst(a, idx, k);
+                    d.q[0] = fma(hd2, wqx, fma(thh, p0x, q0x));
+                    d.q[d.st] = fma(hd2, wqy, fma(thh, p0y, q0y));
+                    d.q[2 * d.st] = fma(hd2, wqz, fma(thh, p0z, q0z));
+                    d.p[0] = fma(hd, wpx, p0x);
+                    d.p[d.st] = fma(hd, wpy, p0y);
+                    d.p[2 * d.st] = fma(hd, wpz, p0z);
+                    save_commit(a, idx, k);
+                }
                 ++k;
                 tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
                 want = tsave <= tnext;
@@ -1337,12 +1471,8 @@ __global__ void __launch_bounds__(256) k_energy_angmom(const __grid_constant__ D
     if (i >= N) return;
     const double x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
     const double vx = p[3 * i], vy = p[3 * i + 1], vz = p[3 * i + 2];
-    if (E) E[i] = 0.5 * (vx * vx + vy * vy + vz * vz) + potential_value<C>(P, x, y, z);
-    if (L) {
-        L[3 * i] = y * vz - z * vy;
-        L[3 * i + 1] = z * vx - x * vz;
-        L[3 * i + 2] = x * vy - y * vx;
-    }
+    if (E) E[i] = kinetic_plus(potential_value<C>(P, x, y, z), vx, vy, vz);
+    if (L) cross3(x, y, z, vx, vy, vz, L[3 * i], L[3 * i + 1], L[3 * i + 2]);
 }
 
 __global__ void k_bench_dfma(long long iters, double *sink) {
@@ -1504,11 +1634,83 @@ int gx_potential_eval(const gx_potential *pot, const double *xyz, double t, int6
     return cuda_rc(cudaGetLastError());
 }
 
-int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0, double t1,
-                       double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
-                       double *q, double *p, int32_t *status, void *stream) {
+}  // extern "C" (reopened below)
+
+static int epi_setup(const gx_orbit_epilogue *epi, int layout, EpiOut &e) {
+    e = EpiOut{nullptr, nullptr, nullptr, layout == GX_LAYOUT_T3N, 6};
+    if (!epi) return 0;
+    e.E = epi->energy; e.L = epi->angmom; e.TT = epi->tidal;
+    if (!e.E && !e.L && !e.TT) return 0;
+    e.nv = e.TT ? 19 : 10;
+    return 1;
+}
+
+template <bool EPI>
+static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, int scheme, bool fwd, int grid, int block,
+                         size_t dyn, cudaStream_t s, const FixedArgs &a, const FixedSeg &sg) {
+    if (seg_ok) {
+        switch (model) {
+#define GX_SEG_STATIC(C_)                                                                                     \
+    do {                                                                                                      \
+        if (small) {                                                                                          \
+            if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, true, EPI>>(grid, block, dyn, s, D, a, sg);   \
+            else launch_dyn<k_integrate_fixed_seg<C_, false, true, EPI>>(grid, block, dyn, s, D, a, sg);      \
+        } else {                                                                                              \
+            if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, false, EPI>>(grid, block, dyn, s, D, a, sg);  \
+            else launch_dyn<k_integrate_fixed_seg<C_, false, false, EPI>>(grid, block, dyn, s, D, a, sg);     \
+        }                                                                                                     \
+    } while (0)
+        case MODEL_MW: GX_SEG_STATIC(CountsMW); break;
+        case MODEL_MW2022: GX_SEG_STATIC(CountsMW2022); break;
+        case MODEL_BOVY: GX_SEG_STATIC(CountsBovy); break;
+#undef GX_SEG_STATIC
+        default:  // runtime composite, no time-dependent parameter
+            if (is_basic_composite(D, model)) {
+                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasic, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                else launch_dyn<k_integrate_fixed_seg<CountsBasic, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
+            } else {
+                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsRuntime, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                else launch_dyn<k_integrate_fixed_seg<CountsRuntime, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
+            }
+            break;
+        }
+        return;
+    }
+    // the step-by-step kernel (LeapfrogMidpoint, time-dependent parameters, > 120 runs, GX_SCHEME_GENERAL_KERNEL); the
+    // static models take the same small-batch variant as above, so both kernels keep giving the same bits
+#define GX_GEN(C_, SCHEME_, SMALL_)                                                                                \
+    do {                                                                                                           \
+        if (fwd) launch_dyn<k_integrate_fixed<C_, SCHEME_, true, EPI, SMALL_>>(grid, block, dyn, s, D, a);         \
+        else launch_dyn<k_integrate_fixed<C_, SCHEME_, false, EPI, SMALL_>>(grid, block, dyn, s, D, a);            \
+    } while (0)
+#define GX_GEN_STATIC(C_)                                                                                          \
+    do {                                                                                                           \
+        if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {                                                             \
+            if (small) GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, true);                                            \
+            else GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, false);                                                 \
+        } else {                                                                                                   \
+            if (small) GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, true);                                              \
+            else GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, false);                                                   \
+        }                                                                                                          \
+    } while (0)
+    switch (model) {
+    case MODEL_MW: GX_GEN_STATIC(CountsMW); break;
+    case MODEL_MW2022: GX_GEN_STATIC(CountsMW2022); break;
+    case MODEL_BOVY: GX_GEN_STATIC(CountsBovy); break;
+    default:
+        if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) GX_GEN(CountsRuntime, GX_SCHEME_SEMI_IMPLICIT_EULER, false);
+        else GX_GEN(CountsRuntime, GX_SCHEME_LEAPFROG_MIDPOINT, false);
+        break;
+    }
+#undef GX_GEN_STATIC
+#undef GX_GEN
+}
+
+static int fixed_impl(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0, double t1,
+                      double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
+                      double *q, double *p, int32_t *status, const gx_orbit_epilogue *epi, void *stream) {
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE);
+    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE, 0.0, !stream_is_capturing(stream));
     if (rc) return rc;
     if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
     const bool general_kernel = (scheme & GX_SCHEME_GENERAL_KERNEL) != 0;
@@ -1518,11 +1720,13 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
     const double dir = (t1 >= t0) ? 1.0 : -1.0;
     if (t1 != t0 && !(dt0 * dir > 0.0)) return GX_ERR_BADARG;  // ConstantStepSize needs dt0 in the direction of t1
+    FixedArgs a;
+    const bool with_epi = epi_setup(epi, layout, a.epi) != 0;
+    if (with_epi && (strict || D.td.n > 0)) return GX_ERR_UNSUPPORTED;  // (E needs Phi(q, t): static potentials only)
     if (N == 0) return 0;
     if (strict)
         return gx_strict_integrate_fixed(pot, q0, p0, N, t0, t1, dt0, ts, T, scheme, max_steps, layout, q, p, status,
                                          stream);
-    FixedArgs a;
     FixedSeg sg;
     bool seg_ok = GX_FIXED_SEG && GX_FUSED_UPDATE && !general_kernel && scheme == GX_SCHEME_SEMI_IMPLICIT_EULER &&
                   (model != MODEL_GENERIC || D.td.n == 0);
@@ -1535,40 +1739,28 @@ int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
     const bool fwd = dir > 0;
-    const size_t dyn = save_stage_bytes(layout, T, block);  // per-lane staging of the saves (0: direct stores)
+    const size_t dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
     a.stage = dyn != 0;
-    if (seg_ok) {
-        switch (model) {
-        case MODEL_MW:
-            if (fwd) launch_dyn<k_integrate_fixed_seg<CountsMW, true>>(grid, block, dyn, s, D, a, sg);
-            else launch_dyn<k_integrate_fixed_seg<CountsMW, false>>(grid, block, dyn, s, D, a, sg);
-            break;
-        case MODEL_MW2022:
-            if (fwd) launch_dyn<k_integrate_fixed_seg<CountsMW2022, true>>(grid, block, dyn, s, D, a, sg);
-            else launch_dyn<k_integrate_fixed_seg<CountsMW2022, false>>(grid, block, dyn, s, D, a, sg);
-            break;
-        case MODEL_BOVY:
-            if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBovy, true>>(grid, block, dyn, s, D, a, sg);
-            else launch_dyn<k_integrate_fixed_seg<CountsBovy, false>>(grid, block, dyn, s, D, a, sg);
-            break;
-        default:  // runtime composite, no time-dependent parameter
-            if (is_basic_composite(D, model)) {
-                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasic, true>>(grid, block, dyn, s, D, a, sg);
-                else launch_dyn<k_integrate_fixed_seg<CountsBasic, false>>(grid, block, dyn, s, D, a, sg);
-            } else {
-                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsRuntime, true>>(grid, block, dyn, s, D, a, sg);
-                else launch_dyn<k_integrate_fixed_seg<CountsRuntime, false>>(grid, block, dyn, s, D, a, sg);
-            }
-            break;
-        }
-    } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {
-        if (fwd) { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, true>>(grid, block, dyn, s, D, a))); }
-        else { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_SEMI_IMPLICIT_EULER, false>>(grid, block, dyn, s, D, a))); }
-    } else {
-        if (fwd) { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, true>>(grid, block, dyn, s, D, a))); }
-        else { GX_DISPATCH_MODEL(model, (launch_dyn<k_integrate_fixed<C, GX_SCHEME_LEAPFROG_MIDPOINT, false>>(grid, block, dyn, s, D, a))); }
-    }
+    // latency-bound launches (fewer than 4 warps per scheduler): the table / Estrin variant of the static models
+    const bool small = GX_SPH_TABLE && GX_FIXED_SMALL && block < 128;
+    if (with_epi) launch_fixed<true>(model, D, seg_ok, small, scheme, fwd, grid, block, dyn, s, a, sg);
+    else launch_fixed<false>(model, D, seg_ok, small, scheme, fwd, grid, block, dyn, s, a, sg);
     return cuda_rc(cudaGetLastError());
+}
+
+extern "C" {
+
+int gx_integrate_fixed(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0, double t1,
+                       double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
+                       double *q, double *p, int32_t *status, void *stream) {
+    return fixed_impl(pot, q0, p0, N, t0, t1, dt0, ts, T, scheme, max_steps, layout, q, p, status, nullptr, stream);
+}
+
+int gx_integrate_fixed_epilogue(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
+                                double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
+                                int32_t layout, double *q, double *p, int32_t *status, const gx_orbit_epilogue *epi,
+                                void *stream) {
+    return fixed_impl(pot, q0, p0, N, t0, t1, dt0, ts, T, scheme, max_steps, layout, q, p, status, epi, stream);
 }
 
 }  // extern "C"
@@ -1648,17 +1840,20 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
                          const double *q0, const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
                          const double *ts, int32_t T, int64_t max_steps, const int32_t *order, int32_t layout,
                          double *q, double *p, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
-                         void *workspace, void *stream) {
+                         void *workspace, void *stream, const gx_orbit_epilogue *epi = nullptr) {
     const bool strict = (solver & GX_SOLVER_STRICT) != 0;
     solver &= ~GX_SOLVER_STRICT;
     if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE);
+    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE, 0.0, !stream_is_capturing(stream));
     if (rc) return rc;
     if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
         return GX_ERR_BADARG;
     if (!(pid->rtol >= 0.0) || !(pid->atol >= 0.0) || (pid->rtol == 0.0 && pid->atol == 0.0)) return GX_ERR_BADARG;
     if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
+    Dp8Args a;
+    const bool with_epi = epi_setup(epi, layout, a.epi) != 0;
+    if (with_epi && (strict || rec || D.td.n > 0)) return GX_ERR_UNSUPPORTED;  // (E needs Phi(q, t): static potentials)
     if (N == 0) return 0;
     if (strict) {
         if (rec) return GX_ERR_UNSUPPORTED;
@@ -1668,7 +1863,6 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(workspace, 0, 256, s);
     if (e != cudaSuccess) return GX_ERR_CUDA;
-    Dp8Args a;
     a.q0 = q0; a.p0 = p0; a.t0v = t0; a.ts = ts; a.order = order; a.q = q; a.p = p;
     a.status = status; a.n_acc = n_accepted; a.n_tot = n_attempted;
     a.ticket = (unsigned long long *)workspace;
@@ -1684,15 +1878,17 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     // persistent launch: resident CTAs only (occupancy query), never more lanes than particles; small batches
     // use narrow CTAs so that the few particles spread over all SMs.
     const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
-    const size_t dyn = save_stage_bytes(layout, T, block);  // per-lane staging of the saves (0: direct stores)
+    const size_t dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
     a.stage = dyn != 0;
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define GX_LAUNCH_DP8_(C_, IMG_)                                                                              \
     do {                                                                                                      \
-        auto kern = (solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5, IMG_>                       \
-                                                 : k_integrate_dopri8<C_, TabDp8, IMG_>;                      \
+        auto kern = with_epi ? ((solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5, IMG_, true>     \
+                                                             : k_integrate_dopri8<C_, TabDp8, IMG_, true>)    \
+                             : ((solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5, IMG_>           \
+                                                             : k_integrate_dopri8<C_, TabDp8, IMG_>);         \
         if (dyn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);           \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, dyn);                             \
         if (per_sm < 1) per_sm = 1;                                                                           \
@@ -1725,6 +1921,15 @@ int gx_integrate_adaptive(int32_t solver, const gx_potential *pot, const gx_pid 
                           int32_t *status, int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
     return adaptive_impl(solver, nullptr, nullptr, 0, pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, order,
                          layout, q, p, status, n_accepted, n_attempted, workspace, stream);
+}
+
+int gx_integrate_adaptive_epilogue(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                   const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
+                                   const double *ts, int32_t T, int64_t max_steps, const int32_t *order, int32_t layout,
+                                   double *q, double *p, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
+                                   void *workspace, const gx_orbit_epilogue *epi, void *stream) {
+    return adaptive_impl(solver, nullptr, nullptr, 0, pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, order,
+                         layout, q, p, status, n_accepted, n_attempted, workspace, stream, epi);
 }
 
 int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,

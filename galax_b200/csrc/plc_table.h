@@ -214,8 +214,14 @@ static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
 // uploaded on FIRST use of a potential, immutable afterwards and kept for the life of the process -- at most
 // SPH_CACHE_MAX distinct (device, parameter set) entries; beyond that, or if the fit misses 1e-14, nullptr (the caller
 // then runs the composite through the runtime-count kernels).
+static bool sph_same(const std::vector<SphComp> &a, const std::vector<SphComp> &b) {  // (field by field: the struct has padding)
+    if (a.size() != b.size()) return false;
+    for (size_t k = 0; k < a.size(); ++k)
+        if (a[k].kind != b[k].kind || a[k].GM != b[k].GM || a[k].p1 != b[k].p1 || a[k].p2 != b[k].p2) return false;
+    return true;
+}
 constexpr size_t SPH_CACHE_MAX = 256;
-static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr) {
+static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr, bool may_upload = true) {
     struct Entry { int device; std::vector<SphComp> cs; double *dev_ptr; double max_rel_err; };
     static std::mutex mu;
     static std::vector<Entry> cache;
@@ -226,7 +232,7 @@ static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_r
     static std::vector<std::vector<double>> fits;  // host copies, index-aligned with `cache` (another device re-uses the fit)
     for (size_t k = 0; k < cache.size(); ++k) {
         const Entry &e = cache[k];
-        if (e.cs.size() == cs.size() && memcmp(e.cs.data(), cs.data(), cs.size() * sizeof(SphComp)) == 0) {
+        if (sph_same(e.cs, cs)) {
             if (e.device == dev) {
                 if (max_rel_err_out) *max_rel_err_out = e.max_rel_err;
                 return e.dev_ptr;
@@ -234,7 +240,7 @@ static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_r
             fitted = &fits[k];
         }
     }
-    if (cache.size() >= SPH_CACHE_MAX) return nullptr;
+    if (cache.size() >= SPH_CACHE_MAX || !may_upload) return nullptr;  // (!may_upload: the caller's stream is being captured)
     std::vector<double> host;
     double worst = 0.0;
     if (fitted) {

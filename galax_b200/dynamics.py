@@ -130,14 +130,34 @@ class _PhaseSpaceDiagnostics:
         pot = _as_potential(potential if potential is not None else getattr(self, "potential", None))
         return pot.potential(self.q, 0.0)
 
+    def _fused(self, name, potential=None):
+        """A diagnostic the integrator kernel already evaluated at every save (``diagnostics=`` of evaluate_orbit /
+        compute_orbit / OrbitSolver.solve), if it is the one asked for."""
+        d = getattr(self, "diagnostics", None) or {}
+        if name in d and (potential is None or potential is getattr(self, "potential", None)):
+            return d[name]
+        return None
+
     def total_energy(self, potential=None):
         """|p|^2/2 + Phi(q) (pscs/base.py:231-283)."""
+        fused = self._fused("energy", potential)
+        if fused is not None:
+            return fused
         pot = _as_potential(potential if potential is not None else getattr(self, "potential", None))
         return _energy(pot, self.q, self.p)
 
     def angular_momentum(self):
         """q x p (pscs/base.py:285-322, ``specific_angular_momentum``)."""
-        return _energy(None, self.q, self.p, want="L")
+        fused = self._fused("angular_momentum")
+        return fused if fused is not None else _energy(None, self.q, self.p, want="L")
+
+    def tidal_tensor(self, potential=None):
+        """J - tr(J)/3 I of the potential's Hessian along the states (potential/_src/register_funcs.py:347-377)."""
+        fused = self._fused("tidal_tensor", potential)
+        if fused is not None:
+            return fused
+        pot = _as_potential(potential if potential is not None else getattr(self, "potential", None))
+        return pot.tidal_tensor(self.q, 0.0)
 
     def w(self):
         return _cat(self.q, self.p)
@@ -166,6 +186,7 @@ class Orbit(_PhaseSpaceDiagnostics):
     potential: AbstractPotential | None = None
     status: Any = None
     n_steps: Any = None
+    diagnostics: dict | None = None  # fused kernel epilogue: {"energy": (*batch, T), "angular_momentum": ..., "tidal_tensor": ...}
 
     @property
     def shape(self):
@@ -370,11 +391,22 @@ def _integrate_pipelined(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, ma
     return q_out, p_out, status.reshape(batch), {k: v.reshape(batch) for k, v in stat_out.items()}
 
 
+DIAGNOSTICS = ("energy", "angular_momentum", "tidal_tensor")
+
+
 def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",
-               throw=True, general_kernel=False):  # fmt: skip
-    """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,)."""
+               throw=True, general_kernel=False, diagnostics=()):  # fmt: skip
+    """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,).
+
+    ``diagnostics``: any of ``"energy"``, ``"angular_momentum"``, ``"tidal_tensor"`` -- evaluated inside the integrator
+    kernel at every saved state (``gx_integrate_*_epilogue``) and returned in the stats dict under those names with
+    shapes (*batch, T), (*batch, T, 3), (*batch, T, 3, 3) (layout "T3N": (T, N), (T, 3, N), (T, 9, N))."""
     torch = _lib.require_cuda()
-    if _pipeline_ok(torch, q0, p0, t0, ts, layout):
+    diagnostics = tuple(diagnostics or ())
+    for d in diagnostics:
+        if d not in DIAGNOSTICS:
+            raise ValueError(f"unknown diagnostic {d!r}; choose from {DIAGNOSTICS}")
+    if not diagnostics and _pipeline_ok(torch, q0, p0, t0, ts, layout):
         return _integrate_pipelined(pot, q0, p0, t0, t1, ts, solver=solver, controller=controller, dt0=dt0,
                                     max_steps=max_steps, sort=sort, throw=throw, general_kernel=general_kernel)
     dq, restore = _to_device(q0)
@@ -413,6 +445,16 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
     ms = -1 if max_steps is None else int(max_steps)
     stats: dict[str, Any] = {}
     L = _lib.lib()
+    epi = None
+    diag: dict[str, Any] = {}
+    if diagnostics:
+        nt3 = layout == "NT3"
+        shapes = {"energy": (N, T) if nt3 else (T, N), "angular_momentum": (N, T, 3) if nt3 else (T, 3, N),
+                  "tidal_tensor": (N, T, 3, 3) if nt3 else (T, 9, N)}
+        for d in diagnostics:
+            diag[d] = torch.empty(shapes[d], dtype=torch.float64, device=dev)
+        ptr = lambda d: diag[d].data_ptr() if d in diag else None  # noqa: E731
+        epi = _lib.GxOrbitEpilogue(ptr("energy"), ptr("angular_momentum"), ptr("tidal_tensor"))
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         if isinstance(solver, (SemiImplicitEuler, LeapfrogMidpoint)):
@@ -427,9 +469,14 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
                 scheme |= _lib.SCHEME_GENERAL_KERNEL
             if solver.strict:
                 scheme |= _lib.SCHEME_STRICT
-            rc = L.gx_integrate_fixed(C.byref(P), dq.data_ptr(), dp.data_ptr(), N, t0s, t1, float(dt0),
-                                      dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
-                                      status.data_ptr(), stream)  # fmt: skip
+            if epi is not None:
+                rc = L.gx_integrate_fixed_epilogue(C.byref(P), dq.data_ptr(), dp.data_ptr(), N, t0s, t1, float(dt0),
+                                                   dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
+                                                   status.data_ptr(), C.byref(epi), stream)  # fmt: skip
+            else:
+                rc = L.gx_integrate_fixed(C.byref(P), dq.data_ptr(), dp.data_ptr(), N, t0s, t1, float(dt0),
+                                          dts.data_ptr(), T, scheme, ms, lay, q.data_ptr(), p.data_ptr(),
+                                          status.data_ptr(), stream)  # fmt: skip
             _lib.check(rc, "gx_integrate_fixed")
         elif isinstance(solver, (Dopri8, Dopri5)):
             if not isinstance(controller, PIDController):
@@ -442,7 +489,14 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             ntot = torch.empty((N,), dtype=torch.int32, device=dev)
             ws = torch.empty((int(L.gx_workspace_bytes()) // 8,), dtype=torch.int64, device=dev)
             order = _period_order(dq, dp, t0_arr, t1, torch) if (sort and N > 64) else None
-            if N == 1 and T >= 64 and t0_arr is None and t0s != t1 and layout == "NT3" and not solver.strict:
+            if epi is not None:
+                rc = L.gx_integrate_adaptive_epilogue(
+                    code, C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
+                    None if t0_arr is None else t0_arr.data_ptr(), t0s, t1, dts.data_ptr(), T, ms,
+                    None if order is None else order.data_ptr(), lay, q.data_ptr(), p.data_ptr(), status.data_ptr(),
+                    nacc.data_ptr(), ntot.data_ptr(), ws.data_ptr(), C.byref(epi), stream)  # fmt: skip
+                _lib.check(rc, "gx_integrate_adaptive_epilogue")
+            elif N == 1 and T >= 64 and t0_arr is None and t0s != t1 and layout == "NT3" and not solver.strict:
                 # single orbit, many saves (mock-stream progenitor): record the steps, evaluate the dense output
                 # for all save times in parallel (gx_integrate_dopri8_record + gx_dense_eval)
                 cap = int(min(ms, 1 << 16)) if ms > 0 else (1 << 16)
@@ -471,6 +525,10 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
     if layout == "NT3":
         q = q.reshape(batch + (T, 3))
         p = p.reshape(batch + (T, 3))
+        for d, tail in (("energy", (T,)), ("angular_momentum", (T, 3)), ("tidal_tensor", (T, 3, 3))):
+            if d in diag:
+                diag[d] = diag[d].reshape(batch + tail)
+    stats.update(diag)
     host_caller = not (hasattr(q0, "is_cuda") and q0.is_cuda)
     if host_caller:
         # Host callers get host results and host bookkeeping (int32 torch tensors on the CPU: np.asarray(...) /
@@ -480,6 +538,8 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
         stats = dict(zip(stats.keys(), rest))
         if isinstance(q0, np.ndarray) or not isinstance(q0, torch.Tensor):
             q, p = q.numpy(), p.numpy()
+            for d in diag:
+                stats[d] = stats[d].numpy()
     if throw:
         bad = torch.nonzero(status != _lib.OK)
         if bad.numel():
@@ -532,7 +592,7 @@ class OrbitSolver:
     event: Any = None
 
     def solve(self, field, w0, t0, t1=None, /, *, saveat=None, dt0=None, max_steps="default", args=None,
-              dense=False, unbatch_time=False, throw=True, sort=True):  # fmt: skip
+              dense=False, unbatch_time=False, throw=True, sort=True, diagnostics=()):  # fmt: skip
         """``OrbitSolver.solve(field, (q0, p0), t0, t1, saveat=ts, dt0=..., max_steps=...)``.
 
         Like orbit/solver.py:774-803; when ``w0`` carries a time, the 3-argument form
@@ -551,7 +611,7 @@ class OrbitSolver:
         ms = self.max_steps if max_steps == "default" else max_steps
         q, p, status, stats = _integrate(pot, q0, p0, t0, t1f, ts, solver=self.solver,
                                          controller=self.stepsize_controller, dt0=dt0, max_steps=ms, throw=throw,
-                                         sort=sort)  # fmt: skip
+                                         sort=sort, diagnostics=diagnostics)  # fmt: skip
         if unbatch_time and ts.shape[0] == 1:
             q, p = q[..., 0, :], p[..., 0, :]
         return Solution(t0=t0, t1=t1f, ts=ts, ys=(q, p), stats=stats, result=status)
@@ -569,24 +629,33 @@ class Integrator:
     dynamics_solver: OrbitSolver = dataclasses.field(default_factory=_default_integrator_solver)
     diffeq_kw: dict = dataclasses.field(default_factory=lambda: {"max_steps": None})
 
-    def __call__(self, field, w0, t0, t1, /, *, saveat=None, dense=False, throw=True):
+    def __call__(self, field, w0, t0, t1, /, *, saveat=None, dense=False, throw=True, diagnostics=()):
         if dense:
             raise NotImplementedError("dense=True (interpolated orbits) is not supported by the CUDA path")
         kw = dict(self.diffeq_kw)
         q0, p0, _ = _split_w0(w0)
         sol = self.dynamics_solver.solve(field, (q0, p0), t0, t1, saveat=saveat, dt0=kw.get("dt0"),
-                                         max_steps=kw.get("max_steps", "default"), throw=throw)  # fmt: skip
+                                         max_steps=kw.get("max_steps", "default"), throw=throw,
+                                         diagnostics=diagnostics)  # fmt: skip
         q, p = sol.ys
         if saveat is None:
             return PhaseSpaceCoordinate(q[..., 0, :], p[..., 0, :], sol.t1)
-        return PhaseSpaceCoordinate(q, p, sol.ts)
+        w = PhaseSpaceCoordinate(q, p, sol.ts)
+        if diagnostics:
+            w.diagnostics = {d: sol.stats[d] for d in diagnostics}
+        return w
 
 
 default_integrator = Integrator()
 
 
-def evaluate_orbit(pot, w0, t, /, *, integrator: Integrator | None = None, dense: bool = False, throw=True) -> Orbit:
-    """``gd.evaluate_orbit`` (legacy/funcs.py:42-213): integrate w0 to t[0], then t[0] -> t[-1] saving at t."""
+def evaluate_orbit(pot, w0, t, /, *, integrator: Integrator | None = None, dense: bool = False, throw=True,
+                   diagnostics=()) -> Orbit:  # fmt: skip
+    """``gd.evaluate_orbit`` (legacy/funcs.py:42-213): integrate w0 to t[0], then t[0] -> t[-1] saving at t.
+
+    ``diagnostics`` (an extension): any of "energy", "angular_momentum", "tidal_tensor" -- evaluated by the integrator
+    kernel at every saved state; ``Orbit.total_energy()`` / ``.angular_momentum()`` / ``.tidal_tensor()`` then return
+    them without a second pass over the orbit."""
     if dense:
         raise NotImplementedError("dense=True is not supported by the CUDA path")
     pot = _as_potential(pot)
@@ -603,12 +672,13 @@ def evaluate_orbit(pot, w0, t, /, *, integrator: Integrator | None = None, dense
             w = integrator(field, (q0, p0), tw0 if tw0f.ndim else float(tw0f), float(t_host[0]), throw=throw)
             q0, p0 = w.q, w.p
     # integration B: t[0] -> t[-1], saveat = t (legacy/funcs.py:210)
-    w = integrator(field, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw)
-    return Orbit(q=w.q, p=w.p, t=t_host, potential=pot)
+    w = integrator(field, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw,
+                   diagnostics=diagnostics)
+    return Orbit(q=w.q, p=w.p, t=t_host, potential=pot, diagnostics=getattr(w, "diagnostics", None))
 
 
 def compute_orbit(pot_or_field, w0, ts, /, *, solver: OrbitSolver | None = None, dense: bool = False,
-                  throw=True) -> Orbit:  # fmt: skip
+                  throw=True, diagnostics=()) -> Orbit:  # fmt: skip
     """``gd.compute_orbit`` (orbit/compute.py:28-98): same two-phase solve with an ``OrbitSolver``."""
     if dense:
         raise NotImplementedError("dense=True is not supported by the CUDA path")
@@ -619,8 +689,10 @@ def compute_orbit(pot_or_field, w0, ts, /, *, solver: OrbitSolver | None = None,
     if tw0 is not None and float(np.asarray(tw0)) != float(t_host[0]):
         s0 = solver.solve(pot, (q0, p0), float(np.asarray(tw0)), float(t_host[0]), throw=throw)
         q0, p0 = s0.ys[0][..., 0, :], s0.ys[1][..., 0, :]
-    sol = solver.solve(pot, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw)
-    return Orbit(q=sol.ys[0], p=sol.ys[1], t=t_host, potential=pot, status=sol.result, n_steps=sol.stats)
+    sol = solver.solve(pot, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw,
+                       diagnostics=diagnostics)
+    return Orbit(q=sol.ys[0], p=sol.ys[1], t=t_host, potential=pot, status=sol.result, n_steps=sol.stats,
+                 diagnostics={d: sol.stats[d] for d in diagnostics} if diagnostics else None)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -224,6 +224,29 @@ int gx_stream_release(const gx_potential *pot, int32_t df, const double *prog_q,
 int gx_energy_angmom(const gx_potential *pot, const double *q, const double *p, int64_t N, double *energy,
                      double *angmom, void *stream);
 
+/* Orbit post-processing fused into the integrators: the specific total energy E = |p|^2/2 + Phi(q)
+ * (coordinates/_src/pscs/base.py:231-283 total_energy = kinetic + potential_energy), the angular momentum L = q x p
+ * (:285-330) and the tidal tensor J - tr(J)/3 I of the potential's Hessian J (potential/_src/register_funcs.py:347-377)
+ * AT EVERY SAVED STATE, computed while the state is in registers and written with the same sector-aligned staging as q
+ * and p -- no second pass over the saved orbit.  Each pointer may be NULL (not wanted).  Shapes follow `layout`:
+ * GX_LAYOUT_NT3: energy [N,T], angmom [N,T,3], tidal [N,T,3,3]; GX_LAYOUT_T3N: [T,N], [T,3,N], [T,9,N].  Saves a
+ * particle never reached are NaN, as in q and p.  Static potentials only (GX_ERR_UNSUPPORTED for LinearParameter
+ * composites and for the reference-order GX_SCHEME_STRICT / GX_SOLVER_STRICT kernels). */
+typedef struct {
+    double *energy;
+    double *angmom;
+    double *tidal;
+} gx_orbit_epilogue;
+int gx_integrate_fixed_epilogue(const gx_potential *pot, const double *q0, const double *p0, int64_t N, double t0,
+                                double t1, double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps,
+                                int32_t layout, double *q, double *p, int32_t *status, const gx_orbit_epilogue *epi,
+                                void *stream);
+int gx_integrate_adaptive_epilogue(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                   const double *p0, int64_t N, const double *t0, double t0_scalar, double t1,
+                                   const double *ts, int32_t T, int64_t max_steps, const int32_t *order, int32_t layout,
+                                   double *q, double *p, int32_t *status, int32_t *n_accepted, int32_t *n_attempted,
+                                   void *workspace, const gx_orbit_epilogue *epi, void *stream);
+
 /* ---- host-buffer convenience entries (allocate, copy in, run, copy out, synchronise) ---- */
 int gx_host_potential_eval(const gx_potential *pot, const double *xyz, double t, int64_t N, uint32_t what,
                            double *phi, double *grad, double *acc, double *hess);

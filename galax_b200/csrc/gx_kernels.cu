@@ -8,6 +8,7 @@
 //   K4  k_stream_release     Fardal+15 / Chen+24 release conditions (then K3 with per-particle t0)
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo (no fast-math).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <mutex>
@@ -1320,6 +1321,281 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
 #undef AZ
 }
 
+// ================================================================================================
+// K3j: the reference's JOINT batch semantics -- one shared adaptive step for the whole batch
+// ================================================================================================
+// evaluate_orbit(pot, w0[N,6], t) / OrbitSolver.solve(field, (q[N,3], p[N,3]), t0, t1) with scalar times hand the whole
+// batch to ONE diffeqsolve (dynamics/_src/orbit/solver.py:774-803, legacy/integrator.py:288-298): a single 6N-dimensional
+// ODE, one step size, the error norm an RMS over all 6N numbers, one accept / reject decision per attempt.  K3 controls
+// the step per particle (what the reference does under vmap); this kernel restates the joint form for callers that need
+// the reference's numbers for that call form: a persistent cooperative grid, every thread walks its share of the
+// particles through the 13 stages of the attempt (state in a global ping-pong buffer, stage loop rolled -- this is the
+// semantic mode, not the fast one), the squared scaled errors are reduced in a FIXED order (per thread, per CTA tree,
+// then the CTA partials by every CTA the same way: run-to-run reproducible), one grid barrier per attempt, and every
+// thread then takes the same controller decision from the same number.  SaveAt values are evaluated speculatively
+// while the stages are in registers (a rejected attempt's saves are overwritten by the step that finally contains them).
+namespace cgx = cooperative_groups;
+
+struct JointArgs {
+    const double *q0, *p0, *ts;
+    double *q, *p;
+    int *status, *n_acc, *n_tot;
+    double *ws;  // state[2][9][N] (q, p, FSAL acceleration; SoA), then 2 x JOINT_PART x gridDim partial sums
+    long long N, max_steps;
+    long long sn, sk, sc;
+    double t0, t1;
+    double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax, dtmin, dtmax, dt0;
+    int T;
+};
+constexpr int JOINT_PART = 3;       // values per reduction (sums of squares / non-finite count)
+constexpr int JOINT_MAX_GRID = 2048;
+
+// Sum over the grid of JOINT_PART per-thread values, identical in every thread, in a fixed order.  `slot` alternates so
+// that a CTA still reading the partials of one reduction cannot see the next one's.
+__device__ __forceinline__ void joint_reduce(cgx::grid_group &grid, double *part, int slot, double v[JOINT_PART]) {
+    __shared__ double sh[JOINT_PART][128];
+    __shared__ double tot[JOINT_PART];
+    const int tid = threadIdx.x, bd = blockDim.x;
+#pragma unroll
+    for (int c = 0; c < JOINT_PART; ++c) sh[c][tid] = v[c];
+    __syncthreads();
+    for (int w = bd >> 1; w > 0; w >>= 1) {
+        if (tid < w) {
+#pragma unroll
+            for (int c = 0; c < JOINT_PART; ++c) sh[c][tid] += sh[c][tid + w];
+        }
+        __syncthreads();
+    }
+    double *mine = part + (size_t)slot * JOINT_PART * JOINT_MAX_GRID;
+    if (tid < JOINT_PART) mine[tid * JOINT_MAX_GRID + blockIdx.x] = sh[tid][0];
+    __threadfence();
+    grid.sync();
+    // every CTA adds the partials the same way: thread t takes blocks t, t + bd, ... then the same tree as above
+#pragma unroll
+    for (int c = 0; c < JOINT_PART; ++c) {
+        double acc = 0.0;
+        for (int b = tid; b < (int)gridDim.x; b += bd) acc += __ldcg(mine + c * JOINT_MAX_GRID + b);
+        sh[c][tid] = acc;
+    }
+    __syncthreads();
+    for (int w = bd >> 1; w > 0; w >>= 1) {
+        if (tid < w) {
+#pragma unroll
+            for (int c = 0; c < JOINT_PART; ++c) sh[c][tid] += sh[c][tid + w];
+        }
+        __syncthreads();
+    }
+    if (tid < JOINT_PART) tot[tid] = sh[tid][0];
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < JOINT_PART; ++c) v[c] = tot[c];
+    __syncthreads();
+}
+
+template <class C, class TB>
+__global__ void __launch_bounds__(128) k_integrate_joint(const __grid_constant__ DevPot P, const JointArgs a) {
+    constexpr int NS = TB::NS;
+    cgx::grid_group grid = cgx::this_grid();
+    const long long N = a.N, gt = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    double *S[2] = {a.ws, a.ws + 9 * N};
+    double *part = a.ws + 18 * N;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL), NANV = __longlong_as_double(0x7ff8000000000000LL);
+    const double dir = (a.t1 >= a.t0) ? 1.0 : -1.0, T0 = a.t0 * dir, T1 = a.t1 * dir;
+    const double n6 = 6.0 * (double)N;
+    int slot = 0, cur = 0, k = 0;
+    auto acc_at = [&](double x, double y, double z, double t, double &ax, double &ay, double &az) {
+        double g0, g1, g2;
+        gradient<C>(P, x, y, z, g0, g1, g2, t);
+        ax = -g0; ay = -g1; az = -g2;
+    };
+    auto out_q = [&](long long i, int kk, int c) -> double & { return a.q[i * a.sn + kk * a.sk + c * a.sc]; };
+    auto out_p = [&](long long i, int kk, int c) -> double & { return a.p[i * a.sn + kk * a.sk + c * a.sc]; };
+    auto ts_at = [&](int kk) { return (kk < a.T) ? __ldg(a.ts + kk) * dir : INF; };
+
+    // ---- t0: FSAL acceleration, saves at t0, and the initial step (PIDController.init / _select_initial_step on the
+    //      joint state: the norms are RMS over all 6N numbers)
+    int k0 = 0;
+    while (ts_at(k0) <= T0) ++k0;
+    double v[JOINT_PART] = {0.0, 0.0, 0.0};
+    for (long long i = gt; i < N; i += stride) {
+        double y[6] = {a.q0[3 * i], a.q0[3 * i + 1], a.q0[3 * i + 2], a.p0[3 * i], a.p0[3 * i + 1], a.p0[3 * i + 2]};
+        double f[3];
+        acc_at(y[0], y[1], y[2], dir * T0, f[0], f[1], f[2]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) S[0][c * N + i] = y[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S[0][(6 + c) * N + i] = f[c];
+        for (int kk = 0; kk < k0; ++kk)
+            for (int c = 0; c < 3; ++c) { out_q(i, kk, c) = y[c]; out_p(i, kk, c) = y[3 + c]; }
+        const double f0[6] = {y[3] * dir, y[4] * dir, y[5] * dir, f[0] * dir, f[1] * dir, f[2] * dir};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const double sc = a.atol + fabs(y[c]) * a.rtol;
+            const double u = y[c] / sc, w = f0[c] / sc;
+            v[0] = fma(u, u, v[0]);
+            v[1] = fma(w, w, v[1]);
+        }
+    }
+    k = k0;
+    double h;
+    if (a.dt0 > 0.0) {
+        h = a.dt0;
+    } else {
+        joint_reduce(grid, part, slot, v); slot ^= 1;
+        const double d0 = sqrt(v[0] / n6), d1 = sqrt(v[1] / n6);
+        const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+        v[0] = v[1] = v[2] = 0.0;
+        for (long long i = gt; i < N; i += stride) {
+            double y[6], f[3], f1[3];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) y[c] = S[0][c * N + i];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[c] = S[0][(6 + c) * N + i];
+            const double f0[6] = {y[3] * dir, y[4] * dir, y[5] * dir, f[0] * dir, f[1] * dir, f[2] * dir};
+            double y1[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) y1[c] = y[c] + h0 * f0[c];
+            acc_at(y1[0], y1[1], y1[2], dir * (T0 + h0), f1[0], f1[1], f1[2]);
+            const double g1[6] = {y1[3] * dir, y1[4] * dir, y1[5] * dir, f1[0] * dir, f1[1] * dir, f1[2] * dir};
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double w = (g1[c] - f0[c]) / (a.atol + fabs(y[c]) * a.rtol);
+                v[0] = fma(w, w, v[0]);
+            }
+        }
+        joint_reduce(grid, part, slot, v); slot ^= 1;
+        const double d2 = sqrt(v[0] / n6) / h0;
+        const double maxd = fmax(d1, d2);
+        const double h1 = (maxd <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / maxd, 1.0 / (TB::ORDER + 1));
+        h = fmin(100.0 * h0, h1);
+    }
+    bool at_dtmin = false;
+    if (a.dtmax > 0.0) h = fmin(h, a.dtmax);
+    if (a.dtmin > 0.0) { at_dtmin = h <= a.dtmin; h = fmax(h, a.dtmin); }
+    double tprev = T0, tnext = clip_to_end(T0, T0 + h, T1, true);
+    double prev_inv = 1.0, prev_prev_inv = 1.0;
+    long long nacc = 0, ntot = 0;
+    int st = GX_OK;
+    grid.sync();  // (dt0 given: the state written above must be visible before the first attempt reads it -- own
+                  //  particles only, but keep the phases aligned)
+
+    while (tprev < T1 && st == GX_OK) {
+        if (a.max_steps >= 0 && ntot >= a.max_steps) { st = GX_MAX_STEPS_REACHED; break; }
+        h = tnext - tprev;
+        const double hd = h * dir, hd2 = hd * hd;
+        int kend = k;  // saves k .. kend-1 lie in (tprev, tnext]
+        while (ts_at(kend) <= tnext) ++kend;
+        v[0] = v[1] = v[2] = 0.0;
+        const double *Sc = S[cur];
+        double *Sn = S[cur ^ 1];
+        for (long long i = gt; i < N; i += stride) {
+            const double q0x = Sc[i], q0y = Sc[N + i], q0z = Sc[2 * N + i];
+            const double p0x = Sc[3 * N + i], p0y = Sc[4 * N + i], p0z = Sc[5 * N + i];
+            double ax[NS], ay[NS], az[NS];
+            ax[0] = Sc[6 * N + i]; ay[0] = Sc[7 * N + i]; az[0] = Sc[8 * N + i];
+            double xi = q0x, yi = q0y, zi = q0z;
+#pragma unroll 1
+            for (int s = 1; s < NS; ++s) {
+                double sx = 0, sy = 0, sz = 0;
+                for (int l = 0; l < s; ++l) {
+                    const double c = TB::AA(s, l);
+                    sx = fma(c, ax[l], sx); sy = fma(c, ay[l], sy); sz = fma(c, az[l], sz);
+                }
+                const double ch = TB::CN(s) * hd;
+                xi = fma(hd2, sx, fma(ch, p0x, q0x));
+                yi = fma(hd2, sy, fma(ch, p0y, q0y));
+                zi = fma(hd2, sz, fma(ch, p0z, q0z));
+                acc_at(xi, yi, zi, fma(TB::CN(s), hd, dir * tprev), ax[s], ay[s], az[s]);
+            }
+            double bx = 0, by = 0, bz = 0, epx = 0, epy = 0, epz = 0, eqx = 0, eqy = 0, eqz = 0;
+            for (int l = 0; l < NS; ++l) {
+                bx = fma(TB::B(l), ax[l], bx); by = fma(TB::B(l), ay[l], by); bz = fma(TB::B(l), az[l], bz);
+                epx = fma(TB::E(l), ax[l], epx); epy = fma(TB::E(l), ay[l], epy); epz = fma(TB::E(l), az[l], epz);
+                eqx = fma(TB::EA(l), ax[l], eqx); eqy = fma(TB::EA(l), ay[l], eqy); eqz = fma(TB::EA(l), az[l], eqz);
+            }
+            const double y0[6] = {q0x, q0y, q0z, p0x, p0y, p0z};
+            const double y1[6] = {xi, yi, zi, fma(hd, bx, p0x), fma(hd, by, p0y), fma(hd, bz, p0z)};
+            const double er[6] = {hd2 * eqx, hd2 * eqy, hd2 * eqz, hd * epx, hd * epy, hd * epz};
+            bool fin = true;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double e = er[c] / (a.atol + fmax(fabs(y0[c]), fabs(y1[c])) * a.rtol);
+                v[0] = fma(e, e, v[0]);
+                fin = fin && isfinite(y1[c]);
+                Sn[c * N + i] = y1[c];
+            }
+            if (!fin) v[1] += 1.0;
+            Sn[6 * N + i] = ax[NS - 1]; Sn[7 * N + i] = ay[NS - 1]; Sn[8 * N + i] = az[NS - 1];
+            // SaveAt(ts) on this attempt (dense output; a save time equal to tnext gets theta = 1 like the rest)
+            for (int kk = k; kk < kend; ++kk) {
+                const double th = (ts_at(kk) - tprev) / (tnext - tprev);
+                double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
+                for (int l = 0; l < NS; ++l) {
+                    double wq = TB::DQ(l, 5), wp = TB::DB(l, 5);
+                    for (int m = 4; m >= 0; --m) { wq = fma(wq, th, TB::DQ(l, m)); wp = fma(wp, th, TB::DB(l, m)); }
+                    wq *= th; wp *= th;
+                    wqx = fma(wq, ax[l], wqx); wqy = fma(wq, ay[l], wqy); wqz = fma(wq, az[l], wqz);
+                    wpx = fma(wp, ax[l], wpx); wpy = fma(wp, ay[l], wpy); wpz = fma(wp, az[l], wpz);
+                }
+                const double thh = th * hd;
+                out_q(i, kk, 0) = fma(hd2, wqx, fma(thh, p0x, q0x));
+                out_q(i, kk, 1) = fma(hd2, wqy, fma(thh, p0y, q0y));
+                out_q(i, kk, 2) = fma(hd2, wqz, fma(thh, p0z, q0z));
+                out_p(i, kk, 0) = fma(hd, wpx, p0x);
+                out_p(i, kk, 1) = fma(hd, wpy, p0y);
+                out_p(i, kk, 2) = fma(hd, wpz, p0z);
+            }
+        }
+        joint_reduce(grid, part, slot, v); slot ^= 1;
+        ++ntot;
+        // ---- PID controller on the joint error norm (diffrax PIDController.adapt_step_size), the same in every thread
+        const double ms = v[0] / n6;
+        const bool bad = !(ms <= 1.7976931348623157e308);
+        bool keep = !bad && ms < 1.0;
+        if (a.dtmin > 0.0) keep = keep || at_dtmin;
+        const double serr = bad ? INF : sqrt(ms);
+        double inv = 1.0 / serr;
+        const double c1 = (a.icoeff + a.pcoeff + a.dcoeff) * (1.0 / TB::ORDER);
+        const double c2 = -(a.pcoeff + 2.0 * a.dcoeff) * (1.0 / TB::ORDER);
+        const double c3 = a.dcoeff * (1.0 / TB::ORDER);
+        double factor = a.safety;
+        if (bad) {
+            factor = 0.0;
+        } else if (!(ms > 0.0)) {
+            factor = a.factormax;
+        } else {
+            if (c1 != 0.0) factor *= pow(inv, c1);
+            if (c2 != 0.0) factor *= pow(prev_inv, c2);
+            if (c3 != 0.0) factor *= pow(prev_prev_inv, c3);
+        }
+        factor = fmin(fmax(factor, keep ? 1.0 : a.factormin), a.factormax);
+        double dt = h * factor;
+        if (inv == 0.0 || isinf(inv)) { inv = 1.0; prev_inv = 1.0; }
+        if (a.dtmax > 0.0) dt = fmin(dt, a.dtmax);
+        if (a.dtmin > 0.0) { at_dtmin = dt <= a.dtmin; dt = fmax(dt, a.dtmin); }
+        if (keep) {
+            cur ^= 1;
+            prev_prev_inv = prev_inv;
+            prev_inv = inv;
+            tprev = tnext;
+            ++nacc;
+            k = kend;
+            if (v[1] > 0.0) st = GX_NONFINITE;
+        }
+        if (tprev > T1) tprev = T1;
+        tnext = clip_to_end(tprev, tprev + dt, T1, keep);
+    }
+    // saves never reached: NaN, like an unfilled diffrax buffer
+    for (long long i = gt; i < N; i += stride)
+        for (int kk = k; kk < a.T; ++kk)
+            for (int c = 0; c < 3; ++c) { out_q(i, kk, c) = NANV; out_p(i, kk, c) = NANV; }
+    if (gt == 0) {
+        if (a.status) *a.status = st;
+        if (a.n_acc) *a.n_acc = (int)nacc;
+        if (a.n_tot) *a.n_tot = (int)ntot;
+    }
+}
+
 // Dense output in parallel: one thread per save time, binary search over the recorded accepted steps, then the
 // same degree-6 continuous extension as the in-kernel SaveAt path.  Used for single orbits with many saves (the
 // progenitor orbit of a mock stream: 5e5 saves on ~10^3 steps), where a serial in-kernel evaluation would dominate.
@@ -1930,6 +2206,62 @@ int gx_integrate_adaptive_epilogue(int32_t solver, const gx_potential *pot, cons
                                    void *workspace, const gx_orbit_epilogue *epi, void *stream) {
     return adaptive_impl(solver, nullptr, nullptr, 0, pot, pid, q0, p0, N, t0, t0_scalar, t1, ts, T, max_steps, order,
                          layout, q, p, status, n_accepted, n_attempted, workspace, stream, epi);
+}
+
+int64_t gx_joint_workspace_bytes(int64_t N) {
+    return N < 0 ? 0 : (int64_t)sizeof(double) * (18 * N + 2 * JOINT_PART * JOINT_MAX_GRID);
+}
+
+int gx_integrate_adaptive_joint(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                const double *p0, int64_t N, double t0, double t1, const double *ts, int32_t T,
+                                int64_t max_steps, int32_t layout, double *q, double *p, int32_t *status,
+                                int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream) {
+    if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE, 0.0, !stream_is_capturing(stream));
+    if (rc) return rc;
+    if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
+        return GX_ERR_BADARG;
+    if (!(pid->rtol >= 0.0) || !(pid->atol >= 0.0) || (pid->rtol == 0.0 && pid->atol == 0.0)) return GX_ERR_BADARG;
+    if (layout != GX_LAYOUT_NT3 && layout != GX_LAYOUT_T3N) return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    int dev = 0, sms = 148, coop = 0, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return GX_ERR_UNSUPPORTED;
+    JointArgs a;
+    a.q0 = q0; a.p0 = p0; a.ts = ts; a.q = q; a.p = p;
+    a.status = status; a.n_acc = n_accepted; a.n_tot = n_attempted;
+    a.ws = (double *)workspace;
+    a.N = N; a.max_steps = max_steps; a.t0 = t0; a.t1 = t1;
+    a.rtol = pid->rtol; a.atol = pid->atol;
+    a.pcoeff = pid->pcoeff; a.icoeff = pid->icoeff; a.dcoeff = pid->dcoeff;
+    a.safety = pid->safety; a.factormin = pid->factormin; a.factormax = pid->factormax;
+    a.dtmin = pid->dtmin; a.dtmax = pid->dtmax;
+    a.dt0 = (pid->dt0 > 0.0) ? pid->dt0 : -1.0;
+    a.T = T;
+    out_strides(layout, N, T, a.sn, a.sk, a.sc);
+    const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t err = cudaSuccess;
+#define GX_LAUNCH_JOINT(C_)                                                                                   \
+    do {                                                                                                      \
+        void *kern = (solver == GX_SOLVER_DOPRI5) ? (void *)k_integrate_joint<C_, TabDp5>                     \
+                                                  : (void *)k_integrate_joint<C_, TabDp8>;                    \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0);                               \
+        if (per_sm < 1) per_sm = 1;                                                                           \
+        long long want = (N + block - 1) / block, resident = (long long)per_sm * sms;                         \
+        if (resident > JOINT_MAX_GRID) resident = JOINT_MAX_GRID;                                             \
+        int grid = (int)(want < resident ? want : resident);                                                  \
+        void *params[2] = {(void *)&D, (void *)&a};                                                           \
+        err = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(block), params, 0, s);                       \
+    } while (0)
+    if (is_basic_composite(D, model)) GX_LAUNCH_JOINT(CountsBasic);
+    else GX_DISPATCH_MODEL(model, GX_LAUNCH_JOINT(C));
+#undef GX_LAUNCH_JOINT
+    if (err != cudaSuccess) return GX_ERR_CUDA;
+    return cuda_rc(cudaGetLastError());
 }
 
 int gx_integrate_dopri8(const gx_potential *pot, const gx_pid *pid, const double *q0, const double *p0, int64_t N,

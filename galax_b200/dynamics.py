@@ -395,8 +395,12 @@ DIAGNOSTICS = ("energy", "angular_momentum", "tidal_tensor")
 
 
 def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",
-               throw=True, general_kernel=False, diagnostics=()):  # fmt: skip
+               throw=True, general_kernel=False, diagnostics=(), joint=False):  # fmt: skip
     """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,).
+
+    ``joint=True`` (adaptive solvers, scalar t0): the whole batch is ONE ODE with one shared step and an error norm over
+    all 6N components -- what the reference's scalar-time call forms do (orbit/solver.py:774-803); the default controls
+    the step per particle (the reference under ``vmap``).  status and step counts are then the same for every particle.
 
     ``diagnostics``: any of ``"energy"``, ``"angular_momentum"``, ``"tidal_tensor"`` -- evaluated inside the integrator
     kernel at every saved state (``gx_integrate_*_epilogue``) and returned in the stats dict under those names with
@@ -406,7 +410,9 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
     for d in diagnostics:
         if d not in DIAGNOSTICS:
             raise ValueError(f"unknown diagnostic {d!r}; choose from {DIAGNOSTICS}")
-    if not diagnostics and _pipeline_ok(torch, q0, p0, t0, ts, layout):
+    if joint and diagnostics:
+        raise NotImplementedError("diagnostics= is not available with joint=True")
+    if not diagnostics and not joint and _pipeline_ok(torch, q0, p0, t0, ts, layout):
         return _integrate_pipelined(pot, q0, p0, t0, t1, ts, solver=solver, controller=controller, dt0=dt0,
                                     max_steps=max_steps, sort=sort, throw=throw, general_kernel=general_kernel)
     dq, restore = _to_device(q0)
@@ -460,6 +466,7 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
         if isinstance(solver, (SemiImplicitEuler, LeapfrogMidpoint)):
             if not isinstance(controller, ConstantStepSize):
                 raise NotImplementedError(f"{type(solver).__name__} requires ConstantStepSize()")
+            joint = False  # (a constant step is shared by construction: both call forms are the same computation)
             if dt0 is None:
                 raise ValueError("ConstantStepSize requires dt0")
             if t0_arr is not None:
@@ -485,11 +492,28 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             if solver.strict:
                 code |= _lib.SOLVER_STRICT
             pid = controller.c_struct(dt0)
-            nacc = torch.empty((N,), dtype=torch.int32, device=dev)
-            ntot = torch.empty((N,), dtype=torch.int32, device=dev)
-            ws = torch.empty((int(L.gx_workspace_bytes()) // 8,), dtype=torch.int64, device=dev)
-            order = _period_order(dq, dp, t0_arr, t1, torch) if (sort and N > 64) else None
-            if epi is not None:
+            if joint:
+                if t0_arr is not None or solver.strict:
+                    raise NotImplementedError("joint=True needs a scalar t0 (batched start times are per-particle "
+                                              "solves in the reference too) and is not available in strict mode")
+                one = torch.empty((3,), dtype=torch.int32, device=dev)
+                ws = torch.empty((int(L.gx_joint_workspace_bytes(N)) // 8,), dtype=torch.float64, device=dev)
+                rc = L.gx_integrate_adaptive_joint(code, C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N, t0s, t1,
+                                                   dts.data_ptr(), T, ms, lay, q.data_ptr(), p.data_ptr(),
+                                                   one[0:].data_ptr(), one[1:].data_ptr(), one[2:].data_ptr(),
+                                                   ws.data_ptr(), stream)  # fmt: skip
+                _lib.check(rc, "gx_integrate_adaptive_joint")
+                status = one[0:1].expand(N).contiguous()
+                nacc, ntot = one[1:2].expand(N).contiguous(), one[2:3].expand(N).contiguous()
+                order = None
+            else:
+                nacc = torch.empty((N,), dtype=torch.int32, device=dev)
+                ntot = torch.empty((N,), dtype=torch.int32, device=dev)
+                ws = torch.empty((int(L.gx_workspace_bytes()) // 8,), dtype=torch.int64, device=dev)
+                order = _period_order(dq, dp, t0_arr, t1, torch) if (sort and N > 64) else None
+            if joint:
+                pass
+            elif epi is not None:
                 rc = L.gx_integrate_adaptive_epilogue(
                     code, C.byref(P), C.byref(pid), dq.data_ptr(), dp.data_ptr(), N,
                     None if t0_arr is None else t0_arr.data_ptr(), t0s, t1, dts.data_ptr(), T, ms,
@@ -592,11 +616,16 @@ class OrbitSolver:
     event: Any = None
 
     def solve(self, field, w0, t0, t1=None, /, *, saveat=None, dt0=None, max_steps="default", args=None,
-              dense=False, unbatch_time=False, throw=True, sort=True, diagnostics=()):  # fmt: skip
+              dense=False, unbatch_time=False, throw=True, sort=True, diagnostics=(), joint=False):  # fmt: skip
         """``OrbitSolver.solve(field, (q0, p0), t0, t1, saveat=ts, dt0=..., max_steps=...)``.
 
         Like orbit/solver.py:774-803; when ``w0`` carries a time, the 3-argument form
         ``solve(field, w0, t1)`` is accepted (orbit/solver.py:431-442).
+
+        Batch semantics.  The reference solves a batch ``(q0[N,3], p0[N,3])`` with scalar times as ONE ODE with a shared
+        adaptive step (and per particle under ``lstrat.VMap`` / batched times).  Here the default is per particle for
+        every call form (north_star: per-particle step control); ``joint=True`` selects the reference's shared-step
+        form for scalar times.  The two agree to the tolerance, not to rounding.
         """
         if args is not None or dense or self.event is not None:
             raise NotImplementedError("args / dense=True / events are not supported by the CUDA path")
@@ -611,7 +640,7 @@ class OrbitSolver:
         ms = self.max_steps if max_steps == "default" else max_steps
         q, p, status, stats = _integrate(pot, q0, p0, t0, t1f, ts, solver=self.solver,
                                          controller=self.stepsize_controller, dt0=dt0, max_steps=ms, throw=throw,
-                                         sort=sort, diagnostics=diagnostics)  # fmt: skip
+                                         sort=sort, diagnostics=diagnostics, joint=joint)  # fmt: skip
         if unbatch_time and ts.shape[0] == 1:
             q, p = q[..., 0, :], p[..., 0, :]
         return Solution(t0=t0, t1=t1f, ts=ts, ys=(q, p), stats=stats, result=status)
@@ -629,14 +658,14 @@ class Integrator:
     dynamics_solver: OrbitSolver = dataclasses.field(default_factory=_default_integrator_solver)
     diffeq_kw: dict = dataclasses.field(default_factory=lambda: {"max_steps": None})
 
-    def __call__(self, field, w0, t0, t1, /, *, saveat=None, dense=False, throw=True, diagnostics=()):
+    def __call__(self, field, w0, t0, t1, /, *, saveat=None, dense=False, throw=True, diagnostics=(), joint=False):
         if dense:
             raise NotImplementedError("dense=True (interpolated orbits) is not supported by the CUDA path")
         kw = dict(self.diffeq_kw)
         q0, p0, _ = _split_w0(w0)
         sol = self.dynamics_solver.solve(field, (q0, p0), t0, t1, saveat=saveat, dt0=kw.get("dt0"),
                                          max_steps=kw.get("max_steps", "default"), throw=throw,
-                                         diagnostics=diagnostics)  # fmt: skip
+                                         diagnostics=diagnostics, joint=joint)  # fmt: skip
         q, p = sol.ys
         if saveat is None:
             return PhaseSpaceCoordinate(q[..., 0, :], p[..., 0, :], sol.t1)
@@ -650,12 +679,15 @@ default_integrator = Integrator()
 
 
 def evaluate_orbit(pot, w0, t, /, *, integrator: Integrator | None = None, dense: bool = False, throw=True,
-                   diagnostics=()) -> Orbit:  # fmt: skip
+                   diagnostics=(), joint=False) -> Orbit:  # fmt: skip
     """``gd.evaluate_orbit`` (legacy/funcs.py:42-213): integrate w0 to t[0], then t[0] -> t[-1] saving at t.
 
     ``diagnostics`` (an extension): any of "energy", "angular_momentum", "tidal_tensor" -- evaluated by the integrator
     kernel at every saved state; ``Orbit.total_energy()`` / ``.angular_momentum()`` / ``.tidal_tensor()`` then return
-    them without a second pass over the orbit."""
+    them without a second pass over the orbit.
+
+    ``joint=True``: the reference's batch semantics for this call form -- the batch is one ODE with a shared adaptive
+    step (legacy/integrator.py:288-298); the default controls the step per particle (see ``OrbitSolver.solve``)."""
     if dense:
         raise NotImplementedError("dense=True is not supported by the CUDA path")
     pot = _as_potential(pot)
@@ -669,16 +701,17 @@ def evaluate_orbit(pot, w0, t, /, *, integrator: Integrator | None = None, dense
         if tw0f.ndim == 0 and float(tw0f) == float(t_host[0]):
             pass
         else:
-            w = integrator(field, (q0, p0), tw0 if tw0f.ndim else float(tw0f), float(t_host[0]), throw=throw)
+            w = integrator(field, (q0, p0), tw0 if tw0f.ndim else float(tw0f), float(t_host[0]), throw=throw,
+                           joint=joint and not tw0f.ndim)
             q0, p0 = w.q, w.p
     # integration B: t[0] -> t[-1], saveat = t (legacy/funcs.py:210)
     w = integrator(field, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw,
-                   diagnostics=diagnostics)
+                   diagnostics=diagnostics, joint=joint)
     return Orbit(q=w.q, p=w.p, t=t_host, potential=pot, diagnostics=getattr(w, "diagnostics", None))
 
 
 def compute_orbit(pot_or_field, w0, ts, /, *, solver: OrbitSolver | None = None, dense: bool = False,
-                  throw=True, diagnostics=()) -> Orbit:  # fmt: skip
+                  throw=True, diagnostics=(), joint=False) -> Orbit:  # fmt: skip
     """``gd.compute_orbit`` (orbit/compute.py:28-98): same two-phase solve with an ``OrbitSolver``."""
     if dense:
         raise NotImplementedError("dense=True is not supported by the CUDA path")
@@ -687,10 +720,10 @@ def compute_orbit(pot_or_field, w0, ts, /, *, solver: OrbitSolver | None = None,
     t_host = np.atleast_1d(np.asarray(ts.detach().cpu() if hasattr(ts, "detach") else ts, dtype=np.float64))
     q0, p0, tw0 = _split_w0(w0)
     if tw0 is not None and float(np.asarray(tw0)) != float(t_host[0]):
-        s0 = solver.solve(pot, (q0, p0), float(np.asarray(tw0)), float(t_host[0]), throw=throw)
+        s0 = solver.solve(pot, (q0, p0), float(np.asarray(tw0)), float(t_host[0]), throw=throw, joint=joint)
         q0, p0 = s0.ys[0][..., 0, :], s0.ys[1][..., 0, :]
     sol = solver.solve(pot, (q0, p0), float(t_host[0]), float(t_host[-1]), saveat=t_host, throw=throw,
-                       diagnostics=diagnostics)
+                       diagnostics=diagnostics, joint=joint)
     return Orbit(q=sol.ys[0], p=sol.ys[1], t=t_host, potential=pot, status=sol.result, n_steps=sol.stats,
                  diagnostics={d: sol.stats[d] for d in diagnostics} if diagnostics else None)
 

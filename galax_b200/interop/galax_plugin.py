@@ -29,6 +29,26 @@ Overloads registered (reference signature -> here):
                             under jax.vmap / lax.scan in the reference, which an eager binding cannot intercept
 """
 
+# Batch semantics of the adaptive solves (GALAX_B200_BATCH, or `galax_plugin.BATCH = ...` at run time):
+#   "per-particle" (default)  every orbit controls its own step -- what north_star asks of the kernels and what the
+#                             reference does under vmap / lstrat.VMap / batched start times;
+#   "reference"               a batch of initial conditions with scalar times is ONE ODE with a shared adaptive step and
+#                             an error norm over all 6N components, exactly as the reference's evaluate_orbit /
+#                             compute_orbit do for that call form (orbit/solver.py:774-803, legacy/integrator.py:288-298):
+#                             gx_integrate_adaptive_joint.  Use it when the reference's numbers for that call form are
+#                             wanted digit for digit (tests/test_gpu_joint.py reproduces its 8-digit doctests).
+# The two agree to the tolerance of the JOINT norm, which lets single orbits of a large batch err by more than rtol.
+import os
+
+BATCH = os.environ.get("GALAX_B200_BATCH", "per-particle")
+
+
+def _joint() -> bool:
+    if BATCH not in ("per-particle", "reference"):
+        raise ValueError(f"GALAX_B200_BATCH / galax_plugin.BATCH must be 'per-particle' or 'reference', not {BATCH!r}")
+    return BATCH == "reference"
+
+
 # NOTE: no `from __future__ import annotations` here.  The overloads below are annotated with types that only exist
 # inside register() (the `Supported` union of galax classes); plum resolves annotations when a method is registered,
 # and a postponed (string) annotation naming a local would be unresolvable.
@@ -346,7 +366,7 @@ def register() -> None:
         units = pot.units
         tt = np.atleast_1d(_np(u.ustrip(units["time"], t)))
         w, frame = _w0(w0, units)
-        orb = bd.evaluate_orbit(convert_potential(pot), w, tt, integrator=_integrator_spec(integrator))
+        orb = bd.evaluate_orbit(convert_potential(pot), w, tt, integrator=_integrator_spec(integrator), joint=_joint())
         return _wrap_orbit(orb, units, frame)
 
     @dispatch  # same mechanism as galax/interop/astropy/dynamics.py:21-93
@@ -358,9 +378,7 @@ def register() -> None:
         return _evaluate_orbit(pot, w0, t, integrator, dense)
 
     # ---- compute_orbit: dynamics/_src/orbit/compute.py:28-98 ----
-    # NOTE (semantics): with a batch of initial conditions and scalar times the reference integrates the whole batch as
-    # ONE ODE with a shared adaptive step (orbit/solver.py:774-803); the kernels control the step per particle, which
-    # is what the reference itself does under vmap / batched t0.  Results agree to the tolerance, not step for step.
+    # (batch semantics: see BATCH at the top of this module)
     @dispatch
     def compute_orbit(field: Supported | gd.fields.HamiltonianField, w0: gc.AbstractPhaseSpaceObject, ts: object, /, *,
                       solver: object = None, dense: bool = False):
@@ -372,7 +390,7 @@ def register() -> None:
         units = pot.units
         tt = np.atleast_1d(_np(u.ustrip(units["time"], ts)))
         w, frame = _w0(w0, units)
-        orb = bd.compute_orbit(convert_potential(pot), w, tt, solver=_solver_spec(solver))
+        orb = bd.compute_orbit(convert_potential(pot), w, tt, solver=_solver_spec(solver), joint=_joint())
         return _wrap_orbit(orb, units, frame)
 
 

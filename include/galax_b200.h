@@ -207,6 +207,21 @@ int gx_integrate_adaptive_record(int32_t solver, const gx_potential *pot, const 
 int gx_dense_eval_solver(int32_t solver, const double *rec, const int32_t *n_rec, double t0, double t1,
                          const double *ts, int64_t M, double *q, double *p, void *stream);
 
+/* The reference's JOINT batch semantics: ONE adaptive solve of the 6N-dimensional system with one shared step.  This is
+ * what evaluate_orbit(pot, w0[N,6], t) / OrbitSolver.solve(field, (q[N,3], p[N,3]), t0, t1) do for scalar times
+ * (dynamics/_src/orbit/solver.py:774-803, dynamics/_src/legacy/integrator.py:288-298 -> one diffrax.diffeqsolve on the
+ * (N,3) pytree: the error norm is the RMS over all 6N numbers, every particle takes the same steps), whereas
+ * gx_integrate_adaptive controls the step per particle (the reference under vmap / lstrat.VMap / batched t0).  The two
+ * agree to the tolerance, not to rounding; this entry gives the reference's numbers for that call form.  One
+ * cooperative launch (the grid must be resident: at most 2048 CTAs walk the batch), reductions in a fixed order, so
+ * results are reproducible run to run.  status / n_accepted / n_attempted: ONE int32 each (the solve is one ODE).
+ * workspace: gx_joint_workspace_bytes(N) bytes.  Any potential the per-particle entry accepts, LinearParameter included. */
+int64_t gx_joint_workspace_bytes(int64_t N);
+int gx_integrate_adaptive_joint(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,
+                                const double *p0, int64_t N, double t0, double t1, const double *ts, int32_t T,
+                                int64_t max_steps, int32_t layout, double *q, double *p, int32_t *status,
+                                int32_t *n_accepted, int32_t *n_attempted, void *workspace, void *stream);
+
 /* Stream release (distribution function).  Replaces FardalStreamDF._sample / ChenStreamDF._sample given the random
  * draws (dynamics/_src/legacy/mockstream/df/fardal15.py:49-94, df/chen24.py:61-137; tidal radius
  * dynamics/_src/cluster/radius.py:198-215; omega dynamics/_src/register_api.py:77-88).

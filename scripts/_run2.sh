@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_epilogue.py -m gpu -q -x -k "unreached or refuses" 2>&1 | tail -40
+timeout 600 python -m pytest tests/test_gpu_joint.py -m gpu -q -x 2>&1 | tail -15

@@ -181,6 +181,21 @@ def test_overloads_return_reference_containers_with_kernel_numbers(plugin):
     assert isinstance(orb4, gd.Orbit) and np.array_equal(orb4.q.value, ref4.q)
     assert np.array_equal(G["compute_orbit"](pot, w0, ts).q.value, ref4.q)
 
+    # the reference's own batch semantics for this call form (one ODE, shared step), on request
+    plugin.BATCH = "reference"
+    try:
+        orb5 = G["evaluate_orbit"](pot, w0, ts)
+        ref5 = bd.evaluate_orbit(nat, bd.PhaseSpaceCoordinate(q0, p0_kms * u.KMS, 0.0), np.linspace(0.0, 500.0, 6), joint=True)
+        assert np.array_equal(orb5.q.value, ref5.q) and not np.array_equal(orb5.q.value, ref.q)
+        assert np.abs(orb5.q.value - ref.q).max() < 1e-4
+        assert np.array_equal(G["compute_orbit"](pot, w0, ts).q.value,
+                              bd.compute_orbit(nat, bd.PhaseSpaceCoordinate(q0, p0_kms * u.KMS, 0.0), np.linspace(0.0, 500.0, 6), joint=True).q)
+        plugin.BATCH = "both"
+        with pytest.raises(ValueError):
+            G["evaluate_orbit"](pot, w0, ts)
+    finally:
+        plugin.BATCH = "per-particle"
+
     # MockStreamGenerator replacement: same call as tests/unit/dynamics/mockstream/test_mockstreamgenerator.py:48-98
     gen = plugin.MockStreamGenerator(gd.FardalStreamDF(), pot)
     prog = gc.PhaseSpaceCoordinate(q=u.Q([30.0, 10, 20], "kpc"), p=u.Q([10.0, -150, -20], "km / s"), t=u.Q(0.0, "Gyr"))

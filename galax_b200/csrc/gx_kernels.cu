@@ -1067,6 +1067,9 @@ constexpr int REC_DOUBLES = GX_DENSE_RECORD_DOUBLES;  // tprev, tnext, hd, q0[3]
 // alternatives on B200 (MW2022, rtol = atol = 1e-10, 3e5 particles): everything inlined with the stages in
 // registers 161 ms (I-cache bound: 105 KB of SASS); stages in shared memory 151-205 ms; this version 121 ms.
 // TB = TabDp8 (diffrax.Dopri8) or TabDp5 (diffrax.Dopri5): same kernel, tableau resolved at compile time.
+#ifndef GX_DENSE_COEF
+#define GX_DENSE_COEF 0
+#endif
 template <class C, class TB, bool IMG, bool EPI = false>
 __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
 k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
@@ -1261,6 +1264,88 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
 
         // ---------------- SaveAt(ts): degree-6 continuous extension on the accepted step, warp-converged
         bool want = keep && (tsave <= tnext);
+#if GX_DENSE_COEF
+        // Coefficient form.  A save evaluates q(theta) = q0 + theta hd p0 + hd^2 sum_l wq_l(theta) a_l (and p likewise)
+        // with 26 weight polynomials w_l(theta) = theta sum_m D(l, m) theta^m: 210 FP64 + ~100 constant loads per save,
+        // executed once per round of the warp-uniform loop below by the ~5 lanes that want a save -- and the warp runs
+        // 2.65 rounds per step at C2's 1000 saves (ncu, round 2: a third of the kernel's instructions).  Summing over
+        // the stages FIRST, c_m = sum_l D(l, m) a_l for the six powers, is done once per step and leaves 36 FP64 per
+        // save (six Horner chains).  The stage accelerations go through the thread's local memory and a ROLLED loop
+        // over the stages on this path: unrolled, the 36 coefficients beside the 42 accelerations spilled all over the
+        // step; as an out-of-line function, the second callee made ptxas save registers inside the right-hand side.
+        if (__any_sync(FULL, want)) {
+            double cq[3][6], cp[3][6];
+            double inv_h = 0.0;
+            // what the step still needs after the saves (the new state, the FSAL acceleration, the controller's output)
+            // waits in local memory meanwhile: explicit, so that the allocator does not spill the step's long-lived
+            // values all through the stage loop to make room for the coefficients here
+            double stash[NS + 8];
+            int zo;
+            asm volatile("mov.u32 %0, 0;" : "=r"(zo));  // (opaque index: keeps the array in local memory)
+            stash[zo + 0] = q1x; stash[zo + 1] = q1y; stash[zo + 2] = q1z; stash[zo + 3] = p1x; stash[zo + 4] = p1y;
+            stash[zo + 5] = p1z; stash[zo + 6] = dt; stash[zo + 7] = inv; stash[zo + 8] = prev_inv; stash[zo + 9] = prev_prev_inv;
+            stash[zo + 10] = AX(NS - 1); stash[zo + 11] = AY(NS - 1); stash[zo + 12] = AZ(NS - 1);
+            if (want) {
+                double al[NS][3];
+#pragma unroll
+                for (int l = 0; l < NS; ++l) { al[l][0] = AX(l); al[l][1] = AY(l); al[l][2] = AZ(l); }
+                inv_h = rcp_fast(tnext - tprev);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) { cq[c][m] = 0.0; cp[c][m] = 0.0; }
+#pragma unroll 1
+                for (int l = 0; l < NS; ++l) {
+                    const double a0 = al[l][0], a1 = al[l][1], a2 = al[l][2];
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        const double dq = TB::DQ(l, m), db = TB::DB(l, m);
+                        cq[0][m] = fma(dq, a0, cq[0][m]); cq[1][m] = fma(dq, a1, cq[1][m]); cq[2][m] = fma(dq, a2, cq[2][m]);
+                        cp[0][m] = fma(db, a0, cp[0][m]); cp[1][m] = fma(db, a1, cp[1][m]); cp[2][m] = fma(db, a2, cp[2][m]);
+                    }
+                }
+                // the step folded in: q = q0 + theta (hd p0 + hd^2 sum ...), p = p0 + theta hd sum ...
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    cq[0][m] *= hd2; cq[1][m] *= hd2; cq[2][m] *= hd2;
+                    cp[0][m] *= hd; cp[1][m] *= hd; cp[2][m] *= hd;
+                }
+                cq[0][0] = fma(hd, p0x, cq[0][0]); cq[1][0] = fma(hd, p0y, cq[1][0]); cq[2][0] = fma(hd, p0z, cq[2][0]);
+            }
+            while (__any_sync(FULL, want)) {
+                if (want) {
+                    const double th = (tsave - tprev) * inv_h;
+                    double vq[3], vp[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        double wq = cq[c][5], wp = cp[c][5];
+#pragma unroll
+                        for (int m = 4; m >= 0; --m) { wq = fma(wq, th, cq[c][m]); wp = fma(wp, th, cp[c][m]); }
+                        vq[c] = wq; vp[c] = wp;
+                    }
+                    if constexpr (EPI) {
+                        save_put_epi<EPI, C>(P, a, idx, k, fma(th, vq[0], q0x), fma(th, vq[1], q0y), fma(th, vq[2], q0z),
+                                             fma(th, vp[0], p0x), fma(th, vp[1], p0y), fma(th, vp[2], p0z));
+                    } else {
+                        const SaveDst d = save_dst(a, idx, k);
+                        d.q[0] = fma(th, vq[0], q0x);
+                        d.q[d.st] = fma(th, vq[1], q0y);
+                        d.q[2 * d.st] = fma(th, vq[2], q0z);
+                        d.p[0] = fma(th, vp[0], p0x);
+                        d.p[d.st] = fma(th, vp[1], p0y);
+                        d.p[2 * d.st] = fma(th, vp[2], p0z);
+                        save_commit(a, idx, k);
+                    }
+                    ++k;
+                    tsave = (k < a.T) ? __ldg(a.ts + k) * dir : INF;
+                    want = tsave <= tnext;
+                }
+            }
+            q1x = stash[zo + 0]; q1y = stash[zo + 1]; q1z = stash[zo + 2]; p1x = stash[zo + 3]; p1y = stash[zo + 4];
+            p1z = stash[zo + 5]; dt = stash[zo + 6]; inv = stash[zo + 7]; prev_inv = stash[zo + 8]; prev_prev_inv = stash[zo + 9];
+            AX(NS - 1) = stash[zo + 10]; AY(NS - 1) = stash[zo + 11]; AZ(NS - 1) = stash[zo + 12];
+        }
+#else
         while (__any_sync(FULL, want)) {
             if (want) {
                 const double th = (tsave - tprev) / (tnext - tprev);
@@ -1302,6 +1387,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
                 want = tsave <= tnext;
             }
         }
+#endif
         if (keep) {
             q0x = q1x; q0y = q1y; q0z = q1z; p0x = p1x; p0y = p1y; p0z = p1z;
             fsx = AX(NS - 1); fsy = AY(NS - 1); fsz = AZ(NS - 1);

@@ -684,7 +684,8 @@ def legs_rank0(torch, gd, gp, L, _lib, dev, pot, P, q_d, p_d, q_h, p_h, peak, hb
     out["C1_exact"] = {"config": "10^4 particles, MilkyWayPotential, SemiImplicitEuler dt=0.1 Myr x 10^4 steps",
                        "device_s": t_dev, "value": 1e8 / t_dev, "unit": UNIT, "device_s_101_saves": t_101,
                        "e2e_s": best, "e2e_value": 1e8 / best, "h2d_bytes": 480_000, "d2h_bytes": 520_000,
-                       "note": "2 warps per SM: bound by the dependent chain of one step, not by issue slots"}  # fmt: skip
+                       "note": "2 warps per SM: bound by the dependent chain of one step, not by issue slots; small batches run "
+                               "the combined spherical table in Estrin form (round 2: 2.40 -> 2.1 ms)"}  # fmt: skip
 
     # C2: 1e6 particles, MilkyWayPotential2022, Dopri8 rtol = atol = 1e-10, 1000 saves over 5 Gyr (48 GB of output)
     pot2 = gp.MilkyWayPotential2022()
@@ -702,8 +703,34 @@ def legs_rank0(torch, gd, gp, L, _lib, dev, pot, P, q_d, p_d, q_h, p_h, peak, hb
                  "s": t2, "accepted_steps": na, "attempted_steps": nt, "accepted_steps_per_s": na / t2,
                  "rhs_per_s": 13 * nt / t2, "output_GB": 48.0, "failed": int((st != 0).sum()),
                  "energy_drift_median": float(dE.median())}  # fmt: skip
-    del qq, pp, res, q2, p2
+    del qq, pp, res
+    # Orbit post-processing fused into the kernel against a second pass over the saved orbit: a quarter of
+    # C2 (303 104 particles x 1000 saves), total energy + angular momentum at every save
+    Nf = 148 * 2048
+    qf, pf = q2[:Nf].contiguous(), p2[:Nf].contiguous()
+    t_plain, res = ev_timed(torch, lambda: gd._integrate(pot2, qf, pf, 0.0, 5000.0, ts, **kw), reps=1, warm=1)
+    t_pass, _ = ev_timed(torch, lambda: (gd._energy(pot2, res[0], res[1]), gd._energy(None, res[0], res[1], want="L")), reps=1, warm=1)
+    del res
+    t_fused, resf = ev_timed(torch, lambda: gd._integrate(pot2, qf, pf, 0.0, 5000.0, ts, diagnostics=("energy", "angular_momentum"), **kw),
+                             reps=1, warm=1)
+    drift = (resf[3]["energy"][:, -1] / resf[3]["energy"][:, 0] - 1).abs()
+    out["C2_fused_diagnostics"] = {"config": "303 104 particles of C2 (1000 saves): E and L at every save, fused into the "
+                                             "Dopri8 kernel vs a second pass over the 14.5 GB of saved states",
+                                   "integrate_s": t_plain, "second_pass_s": t_pass, "fused_integrate_s": t_fused,
+                                   "energy_drift_median_from_fused": float(drift.median())}  # fmt: skip
+    del resf, q2, p2, qf, pf
     torch.cuda.empty_cache()
+
+    # the reference's joint batch semantics (one shared adaptive step: gx_integrate_adaptive_joint) beside the
+    # per-particle default, C1's particles, Dopri8 rtol = atol = 1e-8 over 1 Gyr
+    kwj = dict(solver=gd.Dopri8(), controller=gd.PIDController(1e-8, 1e-8), dt0=None, max_steps=2**16, throw=False)
+    t_per, rp = ev_timed(torch, lambda: gd._integrate(pot, qc, pc, 0.0, T1, np.array([T1]), **kwj), reps=2)
+    t_joint, rj = ev_timed(torch, lambda: gd._integrate(pot, qc, pc, 0.0, T1, np.array([T1]), joint=True, **kwj), reps=2)
+    out["joint_batch"] = {"config": "10^4 particles, MilkyWayPotential, Dopri8 rtol=atol=1e-8, 1 Gyr: per-particle step control "
+                                    "(default) vs ONE shared step for the batch (the reference's scalar-time call form)",
+                          "per_particle_s": t_per, "joint_s": t_joint, "joint_attempted_steps": int(rj[3]["num_steps"][0]),
+                          "per_particle_attempted_steps_median": float(rp[3]["num_steps"].double().median()),
+                          "per_particle_attempted_steps_max": int(rp[3]["num_steps"].max())}  # fmt: skip
 
     # C3: Pal-5-like mock stream, Fardal DF, 5e5 stripping times -> 1e6 particles over 3 Gyr
     M = 500_000

@@ -168,6 +168,10 @@ _SIGNATURES = {
     "gx_stream_release": (C.c_int, [C.POINTER(GxPotential), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
+    "gx_stream_release_t": (C.c_int, [C.POINTER(GxPotential), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gx_energy_angmom_t": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gx_energy_angmom": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "gx_host_potential_eval": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_double, C.c_int64, C.c_uint32,

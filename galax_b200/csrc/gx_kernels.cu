@@ -1757,6 +1757,7 @@ struct ReleaseArgs {
     long long M;
     double G;
     int df;
+    const double *t_rel;  // release times (time-dependent potentials: each particle sees the potential of its own time)
 };
 
 template <class C>
@@ -1773,7 +1774,16 @@ __global__ void __launch_bounds__(128) k_stream_release(const __grid_constant__ 
     // d2Phi/dr2 = rhat . H . rhat  (register_funcs.py:442-457); r_t = cbrt(G m / (omega^2 - d2Phi/dr2))
     double H[6];
     double gdummy[3];
-    grad_hess<C>(P, x[0], x[1], x[2], gdummy, H);
+    bool frozen = false;
+    if constexpr (!C::is_static && !C::basic_only) {
+        if (P.td.n > 0) {  // LinearParameter composite: the potential at this particle's release time
+            FrozenPot F;
+            freeze_td(P.td, a.t_rel[i], F);
+            grad_hess<C>(F, x[0], x[1], x[2], gdummy, H);
+            frozen = true;
+        }
+    }
+    if (!frozen) grad_hess<C>(P, x[0], x[1], x[2], gdummy, H);
     const double rh[3] = {x[0] / r, x[1] / r, x[2] / r};
     const double d2 = rh[0] * (H[0] * rh[0] + H[1] * rh[1] + H[2] * rh[2]) +
                       rh[1] * (H[1] * rh[0] + H[3] * rh[1] + H[4] * rh[2]) +
@@ -1828,12 +1838,26 @@ __global__ void __launch_bounds__(128) k_stream_release(const __grid_constant__ 
 
 template <class C>
 __global__ void __launch_bounds__(256) k_energy_angmom(const __grid_constant__ DevPot P, const double *q,
-                                                       const double *p, long long N, double *E, double *L) {
+                                                       const double *p, long long N, double *E, double *L,
+                                                       const double *tv, double ts, long long t_period) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const double x = q[3 * i], y = q[3 * i + 1], z = q[3 * i + 2];
     const double vx = p[3 * i], vy = p[3 * i + 1], vz = p[3 * i + 2];
-    if (E) E[i] = kinetic_plus(potential_value<C>(P, x, y, z), vx, vy, vz);
+    if (E) {
+        double phi;
+        bool frozen = false;
+        if constexpr (!C::is_static && !C::basic_only) {
+            if (P.td.n > 0) {  // LinearParameter composite: Phi(q, t) at the state's own time (tv[i mod t_period] or ts)
+                FrozenPot F;
+                freeze_td(P.td, tv ? tv[i % t_period] : ts, F);
+                phi = potential_value<C>(F, x, y, z);
+                frozen = true;
+            }
+        }
+        if (!frozen) phi = potential_value<C>(P, x, y, z);
+        E[i] = kinetic_plus(phi, vx, vy, vz);
+    }
     if (L) cross3(x, y, z, vx, vy, vz, L[3 * i], L[3 * i + 1], L[3 * i + 2]);
 }
 
@@ -2397,14 +2421,21 @@ int gx_dense_eval(const double *rec, const int32_t *n_rec, double t0, double t1,
 int gx_stream_release(const gx_potential *pot, int32_t df, const double *prog_q, const double *prog_p,
                       const double *prog_mass, const double *draws, int64_t M, double *q_lead, double *p_lead,
                       double *q_trail, double *p_trail, void *stream) {
+    return gx_stream_release_t(pot, df, prog_q, prog_p, prog_mass, nullptr, draws, M, q_lead, p_lead, q_trail, p_trail,
+                               stream);
+}
+
+int gx_stream_release_t(const gx_potential *pot, int32_t df, const double *prog_q, const double *prog_p,
+                        const double *prog_mass, const double *t_release, const double *draws, int64_t M,
+                        double *q_lead, double *p_lead, double *q_trail, double *p_trail, void *stream) {
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model);
+    int rc = build_devpot(pot, D, model, true, t_release ? TD_INTEGRATE : TD_REJECT);
     if (rc) return rc;
     if (df != GX_DF_FARDAL15 && df != GX_DF_CHEN24) return GX_ERR_BADARG;
     if (M < 0 || (M > 0 && (!prog_q || !prog_p || !prog_mass || !draws || !q_lead || !p_lead || !q_trail || !p_trail)))
         return GX_ERR_BADARG;
     if (M == 0) return 0;
-    ReleaseArgs a{prog_q, prog_p, prog_mass, draws, q_lead, p_lead, q_trail, p_trail, (long long)M, pot->G, df};
+    ReleaseArgs a{prog_q, prog_p, prog_mass, draws, q_lead, p_lead, q_trail, p_trail, (long long)M, pot->G, df, t_release};
     cudaStream_t s = (cudaStream_t)stream;
     GX_DISPATCH_MODEL(model, (k_stream_release<C><<<grid_for(M, 128), 128, 0, s>>>(D, a)));
     return cuda_rc(cudaGetLastError());
@@ -2418,7 +2449,21 @@ int gx_energy_angmom(const gx_potential *pot, const double *q, const double *p, 
     if (N < 0 || (N > 0 && (!q || !p))) return GX_ERR_BADARG;
     if (N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    GX_DISPATCH_MODEL(model, (k_energy_angmom<C><<<grid_for(N, 256), 256, 0, s>>>(D, q, p, (long long)N, energy, angmom)));
+    GX_DISPATCH_MODEL(model, (k_energy_angmom<C><<<grid_for(N, 256), 256, 0, s>>>(D, q, p, (long long)N, energy, angmom,
+                                                                                 nullptr, 0.0, 1LL)));
+    return cuda_rc(cudaGetLastError());
+}
+
+int gx_energy_angmom_t(const gx_potential *pot, const double *q, const double *p, int64_t N, const double *t,
+                       int64_t t_period, double t_scalar, double *energy, double *angmom, void *stream) {
+    DevPot D; Model model;
+    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE);
+    if (rc) return rc;
+    if (N < 0 || (N > 0 && (!q || !p)) || (t && t_period <= 0)) return GX_ERR_BADARG;
+    if (N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    GX_DISPATCH_MODEL(model, (k_energy_angmom<C><<<grid_for(N, 256), 256, 0, s>>>(D, q, p, (long long)N, energy, angmom, t,
+                                                                                 t_scalar, (long long)(t ? t_period : 1))));
     return cuda_rc(cudaGetLastError());
 }
 

@@ -298,10 +298,10 @@ struct Counts {
                          kSAT = (is_static || BASIC) ? 0 : MAX_SATOH;
     static constexpr int kRAD = (is_static || BASIC) ? 0 : MAX_RAD, kHARM = (is_static || BASIC) ? 0 : MAX_HARM,
                          kHENON = (is_static || BASIC) ? 0 : MAX_HENON;
-    __device__ __forceinline__ static int mn(const DevPot &P) { return is_static ? NMN : P.n_mn; }
-    __device__ __forceinline__ static int hern(const DevPot &P) { return is_static ? NH : P.n_hern; }
-    __device__ __forceinline__ static int nfw(const DevPot &P) { return is_static ? NNFW : P.n_nfw; }
-    __device__ __forceinline__ static int plc(const DevPot &P) { return is_static ? NPLC : P.n_plc; }
+    template <class PT> __device__ __forceinline__ static int mn(const PT &P) { return is_static ? NMN : P.n_mn; }
+    template <class PT> __device__ __forceinline__ static int hern(const PT &P) { return is_static ? NH : P.n_hern; }
+    template <class PT> __device__ __forceinline__ static int nfw(const PT &P) { return is_static ? NNFW : P.n_nfw; }
+    template <class PT> __device__ __forceinline__ static int plc(const PT &P) { return is_static ? NPLC : P.n_plc; }
 };
 using CountsRuntime = Counts<-1, -1, -1, -1>;
 using CountsBasic = Counts<-1, -1, -1, -1, false, true>;  // runtime counts of MN / Hernquist / NFW / PowerLawCutoff only
@@ -669,8 +669,8 @@ __device__ __forceinline__ void gradient(const DevPot &P, double x, double y, do
 
 // ---------------------------------------------------------------------------------------------
 // potential value and Hessian (bulk-evaluation kernel only; HBM-bound, so IEEE div/sqrt/log1p).
-template <class C>
-__device__ __forceinline__ double potential_value(const DevPot &P, double x, double y, double z) {
+template <class C, class PT = DevPot>
+__device__ __forceinline__ double potential_value(const PT &P, double x, double y, double z) {
     // the same MUFU-seeded primitives as the gradient (each within ~1 ulp); the PowerLawCutoff term keeps the series
     const double z2 = z * z, R2 = fma(y, y, x * x);
     double phi = 0.0;
@@ -736,8 +736,8 @@ __device__ __forceinline__ double potential_value(const DevPot &P, double x, dou
 // ---------------------------------------------------------------------------------------------
 // fused gradient + Hessian with the fast primitives (bulk kernel, C5 and the stream release).
 // g = grad Phi; H[0..5] = (xx, xy, xz, yy, yz, zz).
-template <class C>
-__device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, double z, double g[3], double H[6]) {
+template <class C, class PT = DevPot>
+__device__ __forceinline__ void grad_hess(const PT &P, double x, double y, double z, double g[3], double H[6]) {
     const double z2 = z * z, R2 = fma(y, y, x * x);
     double gxy = 0.0, gz = 0.0;  // g = (gxy x, gxy y, gz) for the flattened part
     double zeta2 = 0.0, rz = 0.0;
@@ -911,6 +911,77 @@ __device__ __forceinline__ void grad_hess(const DevPot &P, double x, double y, d
         H[1] += 2.0 * k * x * it2;
         H[3] += fma(-2.0 * k, y, 1.0) * it2;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A time-dependent composite (LinearParameter, DevTD) frozen at one time, per thread: the derived constants of its
+// components as build_devpot() forms them on the host for a static potential, so that potential_value / grad_hess
+// evaluate it through the same code (stream release at each particle's own release time, energies along an orbit).
+// Only the member names matter to those templates; the kinds a DevTD cannot hold have length-1 dummies (n = 0).
+struct FrozenPot {
+    int n_mn, n_hern, n_nfw, n_plc, n_log, n_iso, n_satoh, n_rad, n_harm, n_henon;
+    DevMN mn[MAX_MN];
+    DevHern hern[MAX_HERN];
+    DevNFW nfw[MAX_NFW];
+    DevIso iso[MAX_ISO];
+    DevSatoh satoh[MAX_SATOH];
+    DevRad rad[MAX_RAD];
+    DevPLC plc[1];
+    DevLog lg[1];
+    DevHarm harm[1];
+    DevHenon henon[1];
+};
+// false: more components of one kind than the static arrays hold (the host refuses such composites up front)
+__device__ __forceinline__ bool freeze_td(const DevTD &R, double t, FrozenPot &F) {
+    F.n_mn = F.n_hern = F.n_nfw = F.n_plc = F.n_log = F.n_iso = F.n_satoh = F.n_rad = F.n_harm = F.n_henon = 0;
+    for (int i = 0; i < R.n; ++i) {
+        const double p0 = fma(R.dp[i][0], t, R.p[i][0]), p1 = fma(R.dp[i][1], t, R.p[i][1]);
+        const double p2 = fma(R.dp[i][2], t, R.p[i][2]), p3 = fma(R.dp[i][3], t, R.p[i][3]);
+        const double GM = R.G * p0;
+        switch (R.kind[i]) {
+        case 0: {  // Miyamoto-Nagai (m, a, b)
+            if (F.n_mn >= MAX_MN) return false;
+            DevMN &m = F.mn[F.n_mn++];
+            m.GM = GM; m.a = p1; m.b2 = p2 * p2; m.ab2 = p1 * m.b2;
+            if (m.b2 == 0.0) m.b2 = TINY;
+            break;
+        }
+        case 1: {  // Hernquist (m, r_s)
+            if (F.n_hern >= MAX_HERN) return false;
+            DevHern &h = F.hern[F.n_hern++];
+            h.GM = GM; h.c = p1;
+            break;
+        }
+        case 2: {  // NFW (m, r_s)
+            if (F.n_nfw >= MAX_NFW) return false;
+            DevNFW &n = F.nfw[F.n_nfw++];
+            n.GM = GM; n.rs = p1; n.inv_rs = 1.0 / p1; n.GM_inv_rs = GM / p1; n.GM_rs3 = GM / (p1 * p1 * p1); n.pad_ = 0.0;
+            break;
+        }
+        case 5: {  // Isochrone (m, b)
+            if (F.n_iso >= MAX_ISO) return false;
+            DevIso &c = F.iso[F.n_iso++];
+            c.GM = GM; c.b = p1; c.b2 = p1 * p1;
+            break;
+        }
+        case 6: {  // Satoh (m, a, b)
+            if (F.n_satoh >= MAX_SATOH) return false;
+            DevSatoh &m = F.satoh[F.n_satoh++];
+            m.GM = GM; m.a = p1; m.b2 = p2 * p2; m.ab2 = p1 * m.b2;
+            if (m.b2 == 0.0) m.b2 = TINY;
+            break;
+        }
+        default: {  // 7: triaxial Hernquist (m, r_s, q1, q2); 8: Jaffe (m, r_s)
+            if (F.n_rad >= MAX_RAD) return false;
+            DevRad &r = F.rad[F.n_rad++];
+            r.pad_ = 0; r.K = GM; r.a = p1; r.b = 0.0; r.i1 = r.i2 = 1.0;
+            if (R.kind[i] == 7) { r.profile = RAD_HERNQUIST; r.i1 = 1.0 / (p2 * p2); r.i2 = 1.0 / (p3 * p3); }
+            else r.profile = RAD_JAFFE;
+            break;
+        }
+        }
+    }
+    return true;
 }
 
 }  // namespace gx

@@ -144,7 +144,7 @@ class _PhaseSpaceDiagnostics:
         if fused is not None:
             return fused
         pot = _as_potential(potential if potential is not None else getattr(self, "potential", None))
-        return _energy(pot, self.q, self.p)
+        return _energy(pot, self.q, self.p, t=getattr(self, "t", None) if pot.is_time_dependent else None)
 
     def angular_momentum(self):
         """q x p (pscs/base.py:285-322, ``specific_angular_momentum``)."""
@@ -574,8 +574,11 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
     return q, p, status.reshape(batch), stats
 
 
-def _energy(pot, q, p, want="E"):
-    """E = |p|^2/2 + Phi(q) (``pot`` None: kinetic energy only) or L = q x p, on the device."""
+def _energy(pot, q, p, want="E", t=None):
+    """E = |p|^2/2 + Phi(q) (``pot`` None: kinetic energy only) or L = q x p, on the device.
+
+    ``t``: the time(s) of the states, needed for potentials with LinearParameters -- a scalar, or the (T,) save times of
+    an orbit batch (*batch, T, 3)."""
     torch = _lib.require_cuda()
     dq, restore = _to_device(q)
     dp, _ = _to_device(p)
@@ -587,9 +590,21 @@ def _energy(pot, q, p, want="E"):
     L = torch.empty((n, 3), dtype=torch.float64, device=dq.device) if want == "L" else None
     P = pot.c_struct() if pot is not None else NullPotentialStruct()
     with torch.cuda.device(dq.device):
-        rc = _lib.lib().gx_energy_angmom(C.byref(P), dq.data_ptr(), dp.data_ptr(), n,
-                                         None if E is None else E.data_ptr(), None if L is None else L.data_ptr(),
-                                         torch.cuda.current_stream().cuda_stream)  # fmt: skip
+        if t is not None and pot is not None and want == "E":
+            tn = np.asarray(t.detach().cpu() if hasattr(t, "detach") else t, dtype=np.float64)
+            if tn.ndim == 0:
+                tv, period, tsc = None, 1, float(tn)
+            else:
+                if batch[-1:] != tn.shape:
+                    raise ValueError(f"times of shape {tn.shape} do not match states of shape {batch}")
+                tv, period, tsc = torch.from_numpy(np.ascontiguousarray(tn)).to(dq.device), int(tn.shape[0]), 0.0
+            rc = _lib.lib().gx_energy_angmom_t(C.byref(P), dq.data_ptr(), dp.data_ptr(), n,
+                                               None if tv is None else tv.data_ptr(), period, tsc, E.data_ptr(), None,
+                                               torch.cuda.current_stream().cuda_stream)  # fmt: skip
+        else:
+            rc = _lib.lib().gx_energy_angmom(C.byref(P), dq.data_ptr(), dp.data_ptr(), n,
+                                             None if E is None else E.data_ptr(), None if L is None else L.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)  # fmt: skip
     _lib.check(rc, "gx_energy_angmom")
     return restore(E.reshape(batch)) if want == "E" else restore(L.reshape(batch + (3,)))
 
@@ -805,11 +820,15 @@ class AbstractStreamDF:
         dd = dd.contiguous()
         outs = [torch.empty((M, 3), dtype=torch.float64, device=dq.device) for _ in range(4)]
         P = pot.c_struct()
+        # every stripping time sees the potential of its own time (fardal15.py:49-94: tidal_radius(..., t=t)); for a
+        # static potential the times are ignored
+        tt, _ = _to_device(np.broadcast_to(np.asarray(ts, dtype=np.float64), (M,)).copy() if not hasattr(ts, "is_cuda") else ts)
+        tt = tt.reshape(-1).contiguous()
         with torch.cuda.device(dq.device):
-            rc = _lib.lib().gx_stream_release(C.byref(P), self.df_kind, dq.data_ptr(), dp.data_ptr(), dm.data_ptr(),
-                                              dd.data_ptr(), M, *[o.data_ptr() for o in outs],
-                                              torch.cuda.current_stream().cuda_stream)  # fmt: skip
-        _lib.check(rc, "gx_stream_release")
+            rc = _lib.lib().gx_stream_release_t(C.byref(P), self.df_kind, dq.data_ptr(), dp.data_ptr(), dm.data_ptr(),
+                                                tt.data_ptr(), dd.data_ptr(), M, *[o.data_ptr() for o in outs],
+                                                torch.cuda.current_stream().cuda_stream)  # fmt: skip
+        _lib.check(rc, "gx_stream_release_t")
         ql, pl, qt, pt = (restore(o) for o in outs)
         return {"lead": MockStreamArm(ql, pl, ts, ts), "trail": MockStreamArm(qt, pt, ts, ts)}
 

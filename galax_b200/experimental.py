@@ -215,10 +215,11 @@ class Fardal2015DF:
 
         P = pot.c_struct()
         with torch.cuda.device(dq.device):
-            rc = _lib.lib().gx_stream_release(C.byref(P), _lib.DF_FARDAL15, dq.data_ptr(), dp.data_ptr(), dm.data_ptr(),
-                                              dd.data_ptr(), M, *[o.data_ptr() for o in outs],
-                                              torch.cuda.current_stream().cuda_stream)  # fmt: skip
-        _lib.check(rc, "gx_stream_release")
+            tt = torch.from_numpy(np.broadcast_to(np.asarray(t, dtype=np.float64), (M,)).copy()).to(dq.device)
+            rc = _lib.lib().gx_stream_release_t(C.byref(P), _lib.DF_FARDAL15, dq.data_ptr(), dp.data_ptr(), dm.data_ptr(),
+                                                tt.data_ptr(), dd.data_ptr(), M, *[o.data_ptr() for o in outs],
+                                                torch.cuda.current_stream().cuda_stream)  # fmt: skip
+        _lib.check(rc, "gx_stream_release_t")
         ql, pl, qt, pt = (restore(o[0] if scalar else o) for o in outs)
         return ql, pl, qt, pt
 

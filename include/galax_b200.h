@@ -58,8 +58,9 @@ extern "C" {
  * (potential/_src/params/core.py:25-110, slope * (t - point_time) + point_value with the offset folded into p[k]).
  * dp == 0 everywhere: a static potential.  Time-dependent composites are supported by gx_potential_eval (frozen at
  * its t) and by the integrators for the kinds MIYAMOTO_NAGAI, HERNQUIST, NFW, ISOCHRONE, SATOH, TRIAXIAL_HERNQUIST
- * and JAFFE (each right-hand side is evaluated with the parameters of its own stage time); gx_stream_release and
- * gx_energy_angmom return GX_ERR_UNSUPPORTED for them. */
+ * and JAFFE (each right-hand side is evaluated with the parameters of its own stage time), by gx_stream_release_t (each
+ * stripping time sees the potential of its own time) and gx_energy_angmom_t; the entries without a time argument,
+ * gx_stream_release and gx_energy_angmom, return GX_ERR_UNSUPPORTED for them. */
 typedef struct {
     int32_t kind;
     int32_t reserved; /* summation group: consecutive components with the same non-zero value were ONE reference
@@ -234,10 +235,23 @@ int gx_stream_release(const gx_potential *pot, int32_t df, const double *prog_q,
                       const double *prog_mass, const double *draws, int64_t M, double *q_lead, double *p_lead,
                       double *q_trail, double *p_trail, void *stream);
 
+/* The same with the release times: every stripping time sees the potential of ITS OWN time, as FardalStreamDF._sample /
+ * tidal_radius(pot, x, v, mass=..., t=t) do (df/fardal15.py:49-94, cluster/radius.py:198-215).  Needed for composites
+ * with LinearParameter rates (the kinds the integrators accept); t_release: device [M].  t_release = NULL is
+ * gx_stream_release (static potentials only). */
+int gx_stream_release_t(const gx_potential *pot, int32_t df, const double *prog_q, const double *prog_p,
+                        const double *prog_mass, const double *t_release, const double *draws, int64_t M,
+                        double *q_lead, double *p_lead, double *q_trail, double *p_trail, void *stream);
+
 /* Derived diagnostics on device: E = |p|^2/2 + Phi(q) and L = q x p for [N,3] states (used for the energy-drift
  * report; coordinates/_src/pscs/base.py total_energy / angular_momentum). */
 int gx_energy_angmom(const gx_potential *pot, const double *q, const double *p, int64_t N, double *energy,
                      double *angmom, void *stream);
+/* ... with the time of each state, for LinearParameter composites: E_i = |p_i|^2/2 + Phi(q_i, t[i mod t_period]) (an
+ * orbit batch [B,T,3] flattened to N = B T states passes its T save times and t_period = T), or Phi(., t_scalar) when
+ * t is NULL. */
+int gx_energy_angmom_t(const gx_potential *pot, const double *q, const double *p, int64_t N, const double *t,
+                       int64_t t_period, double t_scalar, double *energy, double *angmom, void *stream);
 
 /* Orbit post-processing fused into the integrators: the specific total energy E = |p|^2/2 + Phi(q)
  * (coordinates/_src/pscs/base.py:231-283 total_energy = kinetic + potential_energy), the angular momentum L = q x p

@@ -598,3 +598,56 @@ def test_hamiltonian_field_call_forms_reference_doctest():
         assert np.array_equal(dq, v) and np.allclose(dp, [-0.00702891, 0.0, 0.0], rtol=0, atol=5e-9)
     with pytest.raises(NotImplementedError):
         field(0, x, v, {"extra": 1})
+
+
+def test_time_dependent_potentials_in_stream_release_and_energies():
+    """LinearParameter composites beyond the integrators: every stripping time is released in the
+    potential of ITS OWN time (df/fardal15.py:49-94 passes t to tidal_radius), and Orbit.total_energy evaluates Phi(q, t)
+    at each state's time -- against the oracle frozen at each time."""
+    mix = gp.CompositePotential(
+        disk=gp.MiyamotoNagaiPotential(gp.LinearParameter(1e7, 0.0, 6.8e10), gp.LinearParameter(1e-4, 100.0, 3.01), 0.28),
+        halo=gp.NFWPotential(gp.LinearParameter(2e8, 0.0, 5.4e11), gp.LinearParameter(1e-3, 0.0, 15.62)),
+        bulge=gp.HernquistPotential(5e9, 1.0), nuc=gp.JaffePotential(gp.LinearParameter(-1e5, 0.0, 1e9), 0.3),
+        iso=gp.IsochronePotential(3e9, gp.LinearParameter(1e-4, 0.0, 2.0)), sat=gp.SatohPotential(2e9, 3.0, gp.LinearParameter(1e-5, 0.0, 0.4)),
+        tri=gp.TriaxialHernquistPotential(gp.LinearParameter(1e6, 0.0, 4e9), 0.8, 0.9, gp.LinearParameter(1e-5, 0.0, 0.7)))
+    omix = op.Potential((
+        op.Component(op.KIND_MN, (6.8e10, 3.0, 0.28), rates=(1e7, 1e-4, 0.0)), op.Component(op.KIND_NFW, (5.4e11, 15.62), rates=(2e8, 1e-3)),
+        op.Component(op.KIND_HERNQUIST, (5e9, 1.0)), op.Component(op.KIND_JAFFE, (1e9, 0.3), rates=(-1e5, 0.0)),
+        op.Component(op.KIND_ISOCHRONE, (3e9, 2.0), rates=(0.0, 1e-4)), op.Component(op.KIND_SATOH, (2e9, 3.0, 0.4), rates=(0.0, 0.0, 1e-5)),
+        op.Component(op.KIND_TRIAXIAL_HERNQUIST, (4e9, 0.8, 0.9, 0.7), rates=(1e6, 0.0, 0.0, 1e-5))))
+
+    def frozen(t):
+        return op.Potential(tuple(op.Component(c.kind, c.params_at(t), c.name) for c in omix.components), omix.G)
+
+    rng = np.random.default_rng(51)
+    M = 48
+    ts = np.linspace(0.0, 2000.0, M)
+    xq, xp = synthetic_ics(op.milky_way_potential(), M, seed=52)
+    normals = rng.standard_normal((4, M))
+    arms = gd.FardalStreamDF().sample(normals, mix, gd.Orbit(q=xq, p=xp, t=ts), 1e4)
+    at0 = gd.FardalStreamDF().sample(normals, mix, gd.Orbit(q=xq, p=xp, t=np.zeros(M)), 1e4)
+    for i in range(M):
+        ql, pl, qt, pt = cref.release_fardal(frozen(ts[i]), xq[i:i + 1], xp[i:i + 1], np.array([1e4]), normals[:, i:i + 1])
+        for got, ref in ((arms["lead"].q[i], ql[0]), (arms["lead"].p[i], pl[0]), (arms["trail"].q[i], qt[0]), (arms["trail"].p[i], pt[0])):
+            assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), i
+    assert np.array_equal(at0["lead"].q[0], arms["lead"].q[0])
+    assert np.abs(at0["lead"].q[-1] - arms["lead"].q[-1]).max() > 1e-6  # the halo has grown by 74 %: the tidal radius moved
+    chen = gd.ChenStreamDF().sample(rng.standard_normal((M, 6)) * 0.1 + np.array([1.6, -30, 0, 1, 20, 0]), mix, gd.Orbit(q=xq, p=xp, t=ts), 1e4)
+    assert np.isfinite(chen["lead"].q).all() and np.isfinite(chen["trail"].p).all()
+
+    # energies along an orbit batch: Phi at each save's own time
+    q0, p0 = synthetic_ics(op.milky_way_potential(), 32, seed=53)
+    tsv = np.linspace(0.0, 800.0, 9)
+    orbit = gd.evaluate_orbit(mix, (q0, p0), tsv)
+    E = orbit.total_energy()
+    ref = np.stack([0.5 * (orbit.p[:, k] ** 2).sum(-1) + op.potential(omix, orbit.q[:, k], tsv[k]) for k in range(9)], axis=1)
+    assert E.shape == (32, 9) and np.abs(E / ref - 1).max() < 5e-14
+    assert np.abs(gd._energy(mix, orbit.q[:, 3], orbit.p[:, 3], t=tsv[3]) / ref[:, 3] - 1).max() < 5e-14
+    assert np.abs(E[:, -1] / E[:, 0] - 1).max() > 1e-3  # not conserved: the potential deepens
+    with pytest.raises(NotImplementedError):  # without a time the entry refuses a time-dependent potential
+        gd._energy(mix, orbit.q, orbit.p)
+    # the whole generator runs in a time-dependent host
+    gen = gd.MockStreamGenerator(gd.FardalStreamDF(), mix)
+    w0 = gd.PhaseSpaceCoordinate(np.array([30.0, 10, 20]), np.array([10.0, -150, -20]) * KMS, 0.0)
+    stream, prog = gen.run(7, np.linspace(0.0, 1500.0, 64), w0, 1e4)
+    assert np.isfinite(stream.q).all() and stream.q.shape == (128, 3)

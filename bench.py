@@ -711,13 +711,23 @@ def legs_rank0(torch, gd, gp, L, _lib, dev, pot, P, q_d, p_d, q_h, p_h, peak, hb
     t_plain, res = ev_timed(torch, lambda: gd._integrate(pot2, qf, pf, 0.0, 5000.0, ts, **kw), reps=1, warm=1)
     t_pass, _ = ev_timed(torch, lambda: (gd._energy(pot2, res[0], res[1]), gd._energy(None, res[0], res[1], want="L")), reps=1, warm=1)
     del res
-    t_fused, resf = ev_timed(torch, lambda: gd._integrate(pot2, qf, pf, 0.0, 5000.0, ts, diagnostics=("energy", "angular_momentum"), **kw),
-                             reps=1, warm=1)
+    t_fused, resf = ev_timed(torch, lambda: gd._integrate(pot2, qf, pf, 0.0, 5000.0, ts, diagnostics=("energy", "angular_momentum"),
+                                                          fuse=True, **kw), reps=1, warm=1)
     drift = (resf[3]["energy"][:, -1] / resf[3]["energy"][:, 0] - 1).abs()
     out["C2_fused_diagnostics"] = {"config": "303 104 particles of C2 (1000 saves): E and L at every save, fused into the "
                                              "Dopri8 kernel vs a second pass over the 14.5 GB of saved states",
                                    "integrate_s": t_plain, "second_pass_s": t_pass, "fused_integrate_s": t_fused,
-                                   "energy_drift_median_from_fused": float(drift.median())}  # fmt: skip
+                                   "energy_drift_median_from_fused": float(drift.median()),
+                                   "note": "inside the adaptive kernel a save is evaluated by the ~5 lanes of a warp whose "
+                                           "step contains one; diagnostics= therefore fuses only up to 16 saves there "
+                                           "(always for the fixed-step kernels) and takes the second pass otherwise"}  # fmt: skip
+    # ... and where fusing is free: the fixed-step kernel, 101 saves (C1's second form at bench size)
+    SIEf = dict(solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(), dt0=DT0, max_steps=None)
+    ts101 = np.linspace(0.0, T1, 101)
+    t_k2, _ = ev_timed(torch, lambda: gd._integrate(pot, q_d[:Nf], p_d[:Nf], 0.0, T1, ts101, **SIEf), reps=1, warm=1)
+    t_k2f, _ = ev_timed(torch, lambda: gd._integrate(pot, q_d[:Nf], p_d[:Nf], 0.0, T1, ts101, diagnostics=("energy", "angular_momentum"),
+                                                     **SIEf), reps=1, warm=1)
+    out["C2_fused_diagnostics"]["fixed_step_101_saves"] = {"integrate_s": t_k2, "fused_integrate_s": t_k2f}
     del resf, q2, p2, qf, pf
     torch.cuda.empty_cache()
 

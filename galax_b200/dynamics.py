@@ -392,10 +392,11 @@ def _integrate_pipelined(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, ma
 
 
 DIAGNOSTICS = ("energy", "angular_momentum", "tidal_tensor")
+FUSE_MAX_SAVES_ADAPTIVE = 16
 
 
 def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, sort=True, layout="NT3",
-               throw=True, general_kernel=False, diagnostics=(), joint=False):  # fmt: skip
+               throw=True, general_kernel=False, diagnostics=(), joint=False, fuse="auto"):  # fmt: skip
     """One launch of the integrator kernels.  q0, p0: (*batch, 3); t0 scalar or (*batch,); ts: (T,).
 
     ``joint=True`` (adaptive solvers, scalar t0): the whole batch is ONE ODE with one shared step and an error norm over
@@ -404,7 +405,13 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
 
     ``diagnostics``: any of ``"energy"``, ``"angular_momentum"``, ``"tidal_tensor"`` -- evaluated inside the integrator
     kernel at every saved state (``gx_integrate_*_epilogue``) and returned in the stats dict under those names with
-    shapes (*batch, T), (*batch, T, 3), (*batch, T, 3, 3) (layout "T3N": (T, N), (T, 3, N), (T, 9, N))."""
+    shapes (*batch, T), (*batch, T, 3), (*batch, T, 3, 3) (layout "T3N": (T, N), (T, 3, N), (T, 9, N)).
+    ``fuse``: True = always in the kernel; False = a second pass over the saved states (same bits for E and L);
+    "auto" (default) = in the kernel for the fixed-step schemes and for adaptive solves with at most
+    ``FUSE_MAX_SAVES_ADAPTIVE`` saves.  Measured on a quarter of C2 (303 104 particles x 1000 saves, Dopri8): integration
+    0.110 s, second pass 0.006 s (HBM speed, every lane busy), fused 0.235 s -- inside the adaptive kernel a save is
+    evaluated by the ~5 lanes of a warp whose step contains one, so the potential evaluation is paid at a sixth of the
+    lanes; the fixed-step kernels save rarely relative to their steps and fuse for free."""
     torch = _lib.require_cuda()
     diagnostics = tuple(diagnostics or ())
     for d in diagnostics:
@@ -412,6 +419,15 @@ def _integrate(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, max_steps, s
             raise ValueError(f"unknown diagnostic {d!r}; choose from {DIAGNOSTICS}")
     if joint and diagnostics:
         raise NotImplementedError("diagnostics= is not available with joint=True")
+    if diagnostics and layout == "NT3" and (fuse is False or (fuse == "auto" and isinstance(solver, (Dopri8, Dopri5))
+                                                              and np.size(ts) > FUSE_MAX_SAVES_ADAPTIVE)):
+        q, p, status, stats = _integrate(pot, q0, p0, t0, t1, ts, solver=solver, controller=controller, dt0=dt0,
+                                         max_steps=max_steps, sort=sort, layout=layout, throw=throw,
+                                         general_kernel=general_kernel)
+        for d in diagnostics:  # the second pass: one HBM-bound kernel per quantity over the saved states
+            stats[d] = (_energy(pot, q, p) if d == "energy" else _energy(None, q, p, want="L") if d == "angular_momentum"
+                        else pot.tidal_tensor(q, 0.0))
+        return q, p, status, stats
     if not diagnostics and not joint and _pipeline_ok(torch, q0, p0, t0, ts, layout):
         return _integrate_pipelined(pot, q0, p0, t0, t1, ts, solver=solver, controller=controller, dt0=dt0,
                                     max_steps=max_steps, sort=sort, throw=throw, general_kernel=general_kernel)

@@ -94,9 +94,13 @@ def test_dopri8_epilogue(name, T):
     pot, opot = cls(), ofun()
     q0, p0 = synthetic_ics(opot, 301, seed=14)
     ts = np.linspace(0.0, 500.0, T)
-    q, p, status, st = gd._integrate(pot, q0, p0, 0.0, 500.0, ts, diagnostics=ALL, **DP8)
+    q, p, status, st = gd._integrate(pot, q0, p0, 0.0, 500.0, ts, diagnostics=ALL, fuse=True, **DP8)
     plain = gd._integrate(pot, q0, p0, 0.0, 500.0, ts, **DP8)
     check(pot, opot, q, p, st, plain)
+    # the default policy (fuse="auto": a second pass beyond 16 saves in the adaptive kernel) returns the same arrays
+    auto = gd._integrate(pot, q0, p0, 0.0, 500.0, ts, diagnostics=ALL, **DP8)[3]
+    assert np.array_equal(auto["energy"], st["energy"]) and np.array_equal(auto["angular_momentum"], st["angular_momentum"])
+    assert np.abs(auto["tidal_tensor"] - st["tidal_tensor"]).max() <= 1e-15 * np.abs(st["tidal_tensor"]).max()
     assert np.array_equal(st["num_steps"], plain[3]["num_steps"])
     # energy is conserved to the tolerance along every orbit, the z angular momentum exactly to rounding (axisymmetric)
     E = st["energy"]
@@ -110,7 +114,7 @@ def test_dopri8_epilogue_unreached_saves_are_nan_and_runtime_composites():
     q0, p0 = synthetic_ics(opot, 64, seed=15)
     ts = np.linspace(0.0, 3000.0, 40)
     kw = dict(DP8, max_steps=60)
-    q, p, status, st = gd._integrate(pot, q0, p0, 0.0, 3000.0, ts, diagnostics=ALL, throw=False, **kw)
+    q, p, status, st = gd._integrate(pot, q0, p0, 0.0, 3000.0, ts, diagnostics=ALL, throw=False, fuse=True, **kw)
     assert (np.asarray(status) == 1).any()
     nanq = np.isnan(q[..., 0])
     assert nanq.any() and np.array_equal(np.isnan(st["energy"]), nanq)

@@ -2632,13 +2632,13 @@ int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capa
     }
     if (cs.empty()) return GX_ERR_UNSUPPORTED;
     if (n_intervals) *n_intervals = SPH_NINT;
-    if (degree) *degree = PLC_DEG;
+    if (degree) *degree = SPH_DEG;
     if (e_lo) *e_lo = SPH_E_LO;
     if (sub_bits) *sub_bits = SPH_SUB_BITS;
     if (!coef && !max_rel_err) return 0;
-    if (coef && capacity < (int64_t)SPH_NINT * (PLC_DEG + 1)) return GX_ERR_BADARG;
+    if (coef && capacity < (int64_t)SPH_NINT * SPH_ROW) return GX_ERR_BADARG;
     std::vector<double> tmp;
-    if (!coef) { tmp.resize((size_t)SPH_NINT * (PLC_DEG + 1)); coef = tmp.data(); }
+    if (!coef) { tmp.resize((size_t)SPH_NINT * SPH_ROW); coef = tmp.data(); }
     const double worst = sph_table_fit(cs, coef);
     if (max_rel_err) *max_rel_err = worst;
     return 0;

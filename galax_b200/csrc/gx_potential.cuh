@@ -147,12 +147,19 @@ constexpr int NFW_NINT = (NFW_E_HI - NFW_E_LO) * PLC_SUB;
 // function of u = r^2 (Hernquist GM/(r (r+c)^2), NFW (GM/r_s^3) F(r/r_s), PowerLawCutoff (GM/r_c^3) G(r/r_c)), fitted
 // per potential on the host in long double (plc_table.h: sph_table_for).  Indexed by the bits of r^2, it removes from a
 // right-hand side of the static models everything spherical: the rsqrt of r^2, the Hernquist reciprocals, the NFW /
-// PowerLawCutoff lookups in s = r/r_s (MilkyWayPotential2022: 75 -> 55 FP64 instructions, 3 -> 1 MUFU chains), and the
-// lookup no longer waits for sqrt(r^2).  2^SPH_SUB_BITS = 16 intervals per octave of u (= 32 per octave of r: u^(-3/2)
-// converges like 66^-n), degree 9, u in [2^-14, 2^18) (r from 7.8 pc to 512 kpc): 512 rows x 80 B = 40 KB of shared
-// memory.  Outside the range: the closed forms (spherical_fallback, out of line).
-constexpr int SPH_E_LO = -14, SPH_E_HI = 18, SPH_SUB_BITS = 4;
+// PowerLawCutoff lookups in s = r/r_s (MilkyWayPotential2022: 77 -> 62 FP64 instructions, 6 -> 4 MUFU chains), and the
+// lookup no longer waits for sqrt(r^2).
+// Layout: 2^SPH_SUB_BITS = 32 intervals per octave of u (= 64 per octave of r: u^(-3/2) converges like 130^-n), degree
+// 7, u in [2^-8, 2^14) (r from 62 pc to 128 kpc): 704 rows of 8 doubles = 64 B = FOUR 16-byte loads per lookup, 44 KB
+// of shared memory.  (First version: degree 9 on 16 intervals, 80-byte rows, five loads.  The fixed-step kernels that
+// use the table are bound by the shared-memory port -- every lane reads another row -- so a row is as short as the
+// accuracy allows.)  A 64-byte row stride would put a chunk of every second row in the same bank group, so the four
+// 16-byte chunks of row j are stored XOR-swizzled: chunk c at position c ^ ((j >> 1) & 3); eight consecutive rows then
+// cover the eight bank groups for every c, as an odd stride would, without padding.
+// Outside the range: the closed forms (spherical_fallback, out of line).
+constexpr int SPH_E_LO = -8, SPH_E_HI = 14, SPH_SUB_BITS = 5, SPH_DEG = 7, SPH_ROW = SPH_DEG + 1;
 constexpr int SPH_NINT = (SPH_E_HI - SPH_E_LO) << SPH_SUB_BITS;
+static_assert(SPH_ROW == 8, "rows are four 16-byte chunks (swizzle, Estrin form)");
 #ifndef GX_SPH_TABLE
 #define GX_SPH_TABLE 1
 #endif
@@ -393,7 +400,7 @@ __host__ __device__ constexpr bool sph_tab_fixed_ok() {
 }
 template <class C>
 __device__ __forceinline__ double *sph_smem() {
-    __shared__ __align__(16) double t[SPH_NINT * PLC_STRIDE];
+    __shared__ __align__(64) double t[SPH_NINT * SPH_ROW];  // (64-byte aligned: the swizzle XORs address bits 4-5)
     return t;
 }
 // Call once per CTA, by all threads; returns the shared-window address of the table.
@@ -404,12 +411,42 @@ __device__ __forceinline__ unsigned sph_stage(const DevPot &P) {
         double *t = sph_smem<C>();
         const double2 *src2 = reinterpret_cast<const double2 *>(P.sph_tab);
         double2 *t2 = reinterpret_cast<double2 *>(t);
-        for (int idx = threadIdx.x; idx < SPH_NINT * PLC_STRIDE / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
+        for (int idx = threadIdx.x; idx < SPH_NINT * SPH_ROW / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
         __syncthreads();
         b = (unsigned)__cvta_generic_to_shared(t);
         asm volatile("" : "+r"(b));
     }
     return b;
+}
+
+// S(u) from the staged table (base = its shared-window address); false outside the tabulated range.
+// ESTRIN: 9 FP64 instructions, 3 deep (latency-bound callers: the Dopri kernels, small batches); else Horner, 7.
+template <bool ESTRIN>
+__device__ __forceinline__ bool sph_table_eval(double u, double &S, unsigned base) {
+    const int hi = __double2hiint(u);
+    constexpr int B = SPH_SUB_BITS;
+    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + SPH_E_LO) << B);
+    if (j >= (unsigned)SPH_NINT) return false;  // u outside the table (also NaN / negative)
+    // t in [-1, 1) on the interval, straight from the bits of u (see poly_table_eval)
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
+    constexpr int TOP = ((1 << B) - 1) << (20 - B), HALF = 1 << (19 - B), EXPC = (1023 + B + 1) << 20;
+    const double cB = __hiloint2double((hi & TOP) | HALF | EXPC, 0);
+    const double t = fma(m, (double)(2 << B), -cB);
+    const unsigned a0 = (base + j * (unsigned)(SPH_ROW * 8)) ^ ((j << 3) & 0x30u);  // chunk c lives at a0 ^ (16 c)
+    const double2 c01 = lds_v2f64(a0), c23 = lds_v2f64(a0 ^ 16u), c45 = lds_v2f64(a0 ^ 32u), c67 = lds_v2f64(a0 ^ 48u);
+    if (ESTRIN) {
+        const double t2 = t * t, t4 = t2 * t2;
+        const double p01 = fma(c01.y, t, c01.x), p23 = fma(c23.y, t, c23.x), p45 = fma(c45.y, t, c45.x),
+                     p67 = fma(c67.y, t, c67.x);
+        S = fma(fma(p67, t2, p45), t4, fma(p23, t2, p01));
+    } else {
+        double v = fma(c67.y, t, c67.x);
+        v = fma(v, t, c45.y); v = fma(v, t, c45.x);
+        v = fma(v, t, c23.y); v = fma(v, t, c23.x);
+        v = fma(v, t, c01.y); v = fma(v, t, c01.x);
+        S = v;
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -542,8 +579,7 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
     if (any_sph) {
         const double r2 = R2 + z2;  // (R2 carries the TINY that keeps r > 0)
         if constexpr (SPH != 0) {
-            if (!poly_table_eval<true, SPH_E_LO, SPH_NINT, SPH_SUB_BITS, SPH == 2>(nullptr, r2, fs, nullptr, nfw_base))
-                fs = spherical_fallback<C>(&P, r2);
+            if (!sph_table_eval<SPH == 2>(r2, fs, nfw_base)) fs = spherical_fallback<C>(&P, r2);
         } else {
             fs = spherical_factor<C, PLC_SMEM, NFW_TAB>(P, r2, plc_base, nfw_base);
         }

@@ -42,9 +42,8 @@ static long double plc_P_ld(long double a, long double x) {
 static long double plc_G_ld(long double a, long double s) { return plc_P_ld(a, s * s) / (s * s * s); }
 
 // Chebyshev interpolation on [-1, 1] at PLC_DEG+1 nodes, converted to monomial coefficients in long double.
-template <class F>
+template <int n = PLC_DEG + 1, class F>
 static void fit_interval(const F &fun, long double s0, long double s1, double *coef, double *max_rel_err) {
-    constexpr int n = PLC_DEG + 1;
     const long double PI = 3.141592653589793238462643383279502884L;
     long double f[n], c[n];
     for (int k = 0; k < n; ++k) {
@@ -197,15 +196,16 @@ static long double sph_S_ld(const std::vector<SphComp> &cs, long double u) {
     return sum;
 }
 
-// Fit of the table (host only; also used by gx_force_table): coef[SPH_NINT][PLC_DEG + 1], returns the worst relative
-// error of the fp64 Horner evaluation against the long-double function on a 41-point grid per interval.
+// Fit of the table (host only; also used by gx_spherical_force_table): coef[SPH_NINT][SPH_ROW] in natural order,
+// returns the worst relative error of the fp64 Horner evaluation against the long-double function on a 41-point grid
+// per interval.
 static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
     double worst = 0.0;
     for (int j = 0; j < SPH_NINT; ++j) {
         const int e = SPH_E_LO + (j >> SPH_SUB_BITS), sub = j & ((1 << SPH_SUB_BITS) - 1);
         const long double base = ldexpl(1.0L, e), nsub = (long double)(1 << SPH_SUB_BITS);
-        fit_interval([&cs](long double u) { return sph_S_ld(cs, u); }, base * (1.0L + sub / nsub),
-                     base * (1.0L + (sub + 1) / nsub), coef + (size_t)j * (PLC_DEG + 1), &worst);
+        fit_interval<SPH_ROW>([&cs](long double u) { return sph_S_ld(cs, u); }, base * (1.0L + sub / nsub),
+                              base * (1.0L + (sub + 1) / nsub), coef + (size_t)j * SPH_ROW, &worst);
     }
     return worst;
 }
@@ -246,13 +246,21 @@ static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_r
     if (fitted) {
         host = *fitted;
     } else {
-        host.resize((size_t)SPH_NINT * (PLC_DEG + 1));
+        host.resize((size_t)SPH_NINT * SPH_ROW);
         worst = sph_table_fit(cs, host.data());
     }
     double *d = nullptr;
     if (worst < 1e-14) {
-        if (cudaMalloc(&d, host.size() * sizeof(double)) != cudaSuccess) return nullptr;  // (not cached: may succeed later)
-        if (cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        // device layout: the four 16-byte chunks of row j XOR-swizzled by (j >> 1) & 3 (gx_potential.cuh)
+        std::vector<double> sw(host.size());
+        for (int j = 0; j < SPH_NINT; ++j)
+            for (int c = 0; c < 4; ++c) {
+                const int pos = c ^ ((j >> 1) & 3);
+                sw[(size_t)j * SPH_ROW + 2 * pos] = host[(size_t)j * SPH_ROW + 2 * c];
+                sw[(size_t)j * SPH_ROW + 2 * pos + 1] = host[(size_t)j * SPH_ROW + 2 * c + 1];
+            }
+        if (cudaMalloc(&d, sw.size() * sizeof(double)) != cudaSuccess) return nullptr;  // (not cached: may succeed later)
+        if (cudaMemcpy(d, sw.data(), sw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaFree(d);
             return nullptr;
         }

@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_integrate.py -m gpu -q -x -k "time_dependent" 2>&1 | tail -30
+python scripts/perf_r2.py 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5

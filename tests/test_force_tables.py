@@ -88,9 +88,10 @@ def evaluate_estrin(coef, e_lo, sub_bits, s):
     sub = (hi >> (20 - sub_bits)) & ((1 << sub_bits) - 1)
     t = m * float(2 << sub_bits) - (float(2 << sub_bits) + 2.0 * sub + 1.0)
     c = coef[j]
-    t2 = t * t; t4 = t2 * t2; t8 = t4 * t4
-    p = [c[:, 2 * k + 1] * t + c[:, 2 * k] for k in range(5)]
-    return p[4] * t8 + ((p[3] * t2 + p[2]) * t4 + (p[1] * t2 + p[0]))
+    assert c.shape[1] == 8
+    t2 = t * t; t4 = t2 * t2
+    p = [c[:, 2 * k + 1] * t + c[:, 2 * k] for k in range(4)]
+    return (p[3] * t2 + p[2]) * t4 + (p[1] * t2 + p[0])
 
 
 def sph_reference(pot, r):
@@ -123,11 +124,11 @@ def test_combined_spherical_table_on_the_host(name):
 
     pot = getattr(gp, name)()
     coef, e_lo, sb, err = sph_table(pot)
-    assert coef.shape == (512, 10) and e_lo == -14 and sb == 4 and err < 4e-16
+    assert coef.shape == (704, 8) and e_lo == -8 and sb == 5 and err < 4e-16
     rng = np.random.default_rng(5)
-    edges = np.ldexp(1.0 + np.arange(16) / 16.0, rng.integers(-14, 18, 16))
+    edges = np.ldexp(1.0 + np.arange(32) / 32.0, rng.integers(-8, 14, 32))
     below = np.nextafter(edges, 0)
-    u = np.concatenate([2.0 ** rng.uniform(-14, 18, 300), edges, below[below >= 2.0**-14], [2.0**-14, np.nextafter(2.0**18, 0)]])
+    u = np.concatenate([2.0 ** rng.uniform(-8, 14, 300), edges, below[below >= 2.0**-8], [2.0**-8, np.nextafter(2.0**14, 0)]])
     ref = sph_reference(pot, np.sqrt(u) if False else [mp.sqrt(mp.mpf(float(x))) for x in u])
     for ev in (evaluate, evaluate_estrin):
         S = ev(coef, e_lo, sb, u)

@@ -1,8 +1,10 @@
 // gx_xla_ffi.cc -- XLA FFI custom-call handlers wrapping the C ABI (include/galax_b200.h).
 //
 // NOT part of the default build: it needs the XLA FFI headers that ship inside jaxlib
-// (`python -c "import jax.ffi; print(jax.ffi.include_dir())"`), which are absent from the build container.
-// Where jaxlib is installed:
+// (`python -c "import jax.ffi; print(jax.ffi.include_dir())"`), which are absent from the build container.  What can be
+// checked here is checked: tests/test_abi.py compiles this file against tests/fake_xla/xla/ffi/api/ffi.h, a stand-in with
+// the same public names whose binder verifies -- as the real one does -- that every handler's parameter list is exactly
+// what its Ffi::Bind() chain declares.  Where jaxlib is installed:
 //
 //   nvcc -std=c++17 -shared -Xcompiler -fPIC -I$(python -c "import jax.ffi as f; print(f.include_dir())") \
 //        -I include -o galax_b200/libgalax_b200_ffi.so galax_b200/csrc/gx_xla_ffi.cc -Lgalax_b200 -lgalax_b200

@@ -122,3 +122,27 @@ def test_product_code_never_imports_oracle():
     for f in (ROOT / "galax_b200").rglob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_xla_ffi_shim_type_checks_against_a_stub_of_the_ffi_header():
+    """galax_b200/csrc/gx_xla_ffi.cc needs jaxlib's `xla/ffi/api/ffi.h`, which is not in this image.  tests/fake_xla holds
+    a stand-in with the same public names whose binder checks, like the real one, that every handler's parameter list
+    is exactly what its `Ffi::Bind()...` chain declares; the shim must compile against it (syntax + signatures), and a
+    deliberately wrong binding must not."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    gxx = shutil.which("g++")
+    cuda_inc = Path("/usr/local/cuda/include")
+    if gxx is None or not (cuda_inc / "cuda_runtime.h").exists():
+        pytest.skip("needs g++ and the CUDA headers")
+    src = root / "galax_b200" / "csrc" / "gx_xla_ffi.cc"
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-I", str(root / "tests" / "fake_xla"), "-I", str(cuda_inc)]
+    ok = subprocess.run(cmd + [str(src)], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr
+    bad = src.read_text().replace('.Attr<double>("t")', '.Attr<int32_t>("t")').replace(
+        '"../../include/galax_b200.h"', f'"{root / "include" / "galax_b200.h"}"')
+    res = subprocess.run(cmd + ["-x", "c++", "-"], input=bad, capture_output=True, text=True)
+    assert res.returncode != 0 and "parameter list its binding declares" in res.stderr

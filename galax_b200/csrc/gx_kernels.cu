@@ -719,9 +719,10 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
     constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? 1 : 0);
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
+    constexpr bool MIX = sph_mix_ok<C>() && !SMALL && SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER;  // (see k_integrate_fixed_seg)
     unsigned plc_base = 0, nfw_base = 0;
     if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
-    if constexpr (SPHT != 0) nfw_base = sph_stage<C, SPHT != 0>(P);
+    if constexpr (SPHT != 0 || MIX) nfw_base = sph_stage<C, (SPHT != 0 || MIX)>(P);
     else nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
@@ -751,7 +752,8 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
+                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, 1>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
                 npy = fma(fhh, nqy, py);
@@ -825,12 +827,19 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? 1 : 0);
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
+    // MIX (MilkyWayPotential in large batches): the closed forms cost issue slots (169 per warp-step, the kernel's whole
+    // budget) and leave the shared-memory port idle; the table lookup costs ~40 port cycles and 50 slots fewer.  Steps
+    // therefore ALTERNATE between the two evaluations of the same force, by the global index of the step (so the
+    // trajectory does not depend on where the save times fall, and the general kernel takes the same sequence): both
+    // resources work at the same time.
+    constexpr bool MIX = sph_mix_ok<C>() && !SMALL;
     unsigned plc_base = 0, nfw_base = 0;
     if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
-    if constexpr (SPHT != 0) nfw_base = sph_stage<C, SPHT != 0>(P);
+    if constexpr (SPHT != 0 || MIX) nfw_base = sph_stage<C, (SPHT != 0 || MIX)>(P);
     else nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
+    unsigned gstep = 0;  // index of the step in the whole grid (MIX)
     const double T0 = FWD ? a.t0 : -a.t0;
     double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
     double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
@@ -873,7 +882,9 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qz = fma(pz, hs, qz);
                     if constexpr (C::is_static) {
                         double fh, fv;
-                        gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
+                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 1>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
+                        else gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
+                        if constexpr (MIX) ++gstep;
                         const double fhh = -fh * hs, fvh = -fv * hs;
                         px = fma(fhh, qx, px);
                         py = fma(fhh, qy, py);
@@ -895,7 +906,9 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 double npx, npy, npz;
                 if constexpr (C::is_static) {
                     double fh, fv;
-                    gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
+                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 1>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                    else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
+                    if constexpr (MIX) ++gstep;
                     const double fhh = -fh * hs, fvh = -fv * hs;
                     npx = fma(fhh, nqx, px); npy = fma(fhh, nqy, py); npz = fma(fvh, nqz, pz);
                 } else {

@@ -398,6 +398,24 @@ template <class C>
 __host__ __device__ constexpr bool sph_tab_fixed_ok() {
     return sph_tab_ok<C>() && (C::kMN >= GX_SPH_TABLE_FIXED_MIN_MN || C::kPLC > 0);
 }
+// Fixed-step kernels of a static model that does NOT take the table on every step (MilkyWayPotential): out of every
+// GX_SPH_MIX_PERIOD steps, GX_SPH_MIX_TABLE use the table and the rest the closed forms (0: never mix).
+#ifndef GX_SPH_MIX_PERIOD
+#define GX_SPH_MIX_PERIOD 4
+#endif
+#ifndef GX_SPH_MIX_TABLE
+#define GX_SPH_MIX_TABLE 3
+#endif
+static_assert(GX_SPH_MIX_PERIOD == 0 || (GX_SPH_MIX_PERIOD & (GX_SPH_MIX_PERIOD - 1)) == 0, "a power of two (32-bit step counter)");
+template <class C>
+__host__ __device__ constexpr bool sph_mix_ok() {
+    return GX_SPH_MIX_PERIOD > 0 && sph_tab_ok<C>() && !sph_tab_fixed_ok<C>();
+}
+__device__ __forceinline__ bool sph_mix_table_step(unsigned long long step) {
+    // evenly spread (Bresenham): step * TABLE mod PERIOD < TABLE
+    return (unsigned)((step * (unsigned)GX_SPH_MIX_TABLE) % (unsigned)(GX_SPH_MIX_PERIOD > 0 ? GX_SPH_MIX_PERIOD : 1)) <
+           (unsigned)GX_SPH_MIX_TABLE;
+}
 template <class C>
 __device__ __forceinline__ double *sph_smem() {
     __shared__ __align__(64) double t[SPH_NINT * SPH_ROW];  // (64-byte aligned: the swizzle XORs address bits 4-5)

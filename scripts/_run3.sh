@@ -1,9 +1,12 @@
-bash scripts/ncu_capture.sh r2k > gpurun_out/ncu_capture_r2k.log 2>&1
-for k in fixed fixed_bovy dopri8 dopri8_1000; do
-  u=""; case $k in fixed*) u=1.212416e10;; esac
-  python scripts/ncu_summary.py gpurun_out/prof_${k}_r2k.ncu-rep $u > gpurun_out/ncu_summary_${k}_r2k.txt 2>&1
-  ncu -i gpurun_out/prof_${k}_r2k.ncu-rep --page source --csv --print-source sass > gpurun_out/sass_${k}_r2k.csv 2>/dev/null
-done
-rm -f gpurun_out/prof_fixed_r2k.ncu-rep gpurun_out/prof_fixed_bovy_r2k.ncu-rep gpurun_out/prof_dopri8_r2k.ncu-rep
-gzip -f gpurun_out/sass_*_r2k.csv
-ls -la gpurun_out | head -30
+mkdir -p gpurun_out
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r2l.json 2> gpurun_out/bench_r2l.err
+tail -3 gpurun_out/bench_r2l.err
+python - <<'PY'
+import json
+d=json.load(open("gpurun_out/bench_r2l.json"))
+print({k:d[k] for k in ("value","ms_per_step","e2e","clocks","energy_drift")})
+r=d["roofline"]; print({k:r[k] for k in r if k not in ("canonical","source","peak_source")})
+print(d["cpu_baseline"])
+for k,v in d.get("extra",{}).items(): print(k, {kk:vv for kk,vv in v.items() if kk not in ("config","note")})
+PY
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4

@@ -684,8 +684,8 @@ def legs_rank0(torch, gd, gp, L, _lib, dev, pot, P, q_d, p_d, q_h, p_h, peak, hb
     out["C1_exact"] = {"config": "10^4 particles, MilkyWayPotential, SemiImplicitEuler dt=0.1 Myr x 10^4 steps",
                        "device_s": t_dev, "value": 1e8 / t_dev, "unit": UNIT, "device_s_101_saves": t_101,
                        "e2e_s": best, "e2e_value": 1e8 / best, "h2d_bytes": 480_000, "d2h_bytes": 520_000,
-                       "note": "2 warps per SM: bound by the dependent chain of one step, not by issue slots; small batches run "
-                               "the combined spherical table in Estrin form (round 2: 2.40 -> 2.1 ms)"}  # fmt: skip
+                       "note": "2 warps per SM: bound by the dependent chain of one step, not by issue slots; same arithmetic as "
+                               "the large batches (a particle's bits do not depend on the batch size); round 1: 2.40 ms"}  # fmt: skip
 
     # C2: 1e6 particles, MilkyWayPotential2022, Dopri8 rtol = atol = 1e-10, 1000 saves over 5 Gyr (48 GB of output)
     pot2 = gp.MilkyWayPotential2022()

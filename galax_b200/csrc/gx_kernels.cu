@@ -710,13 +710,17 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #define GX_FIXED_SEG 1
 #endif
 #ifndef GX_FIXED_SMALL
-#define GX_FIXED_SMALL 1
+#define GX_FIXED_SMALL 0
+#endif
+// how a fixed-step table step evaluates its polynomial, for every batch size: 1 Horner (7 FP64, 7 deep), 2 Estrin (9, 3 deep)
+#ifndef GX_SPH_FIXED_FORM
+#define GX_SPH_FIXED_FORM 1
 #endif
 template <class C, int SCHEME, bool FWD, bool EPI = false, bool SMALL = false>
 __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy; every static model in small
     // batches, see k_integrate_fixed_seg), else the PowerLawCutoff / NFW tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? 1 : 0);
+    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? GX_SPH_FIXED_FORM : 0);
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     constexpr bool MIX = sph_mix_ok<C>() && !SMALL && SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER;  // (see k_integrate_fixed_seg)
@@ -752,7 +756,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, 1>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, GX_SPH_FIXED_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                 else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
@@ -814,7 +818,9 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
 // (fma(j, h, t_s) is the grid time itself) instead of a DADD + 2 DSETP + FSEL per step, the step is a uniform
 // constant-bank operand, and the state is updated in place.  Saves are interpolated exactly as in k_integrate_fixed
 // (same theta, same operations): results are bit-identical to it.
-// SMALL: a batch too small to fill the machine (C1's 10^4 particles are one warp on half of the schedulers) is bound by
+// SMALL (GX_FIXED_SMALL=1 builds only; measured and NOT shipped: it makes a particle's bits depend on the size of the
+// batch it travels in, and so on how a job is sharded -- the shipped kernels use one arithmetic for every batch size; C1
+// exactly 2.10 ms instead of 1.94): a batch too small to fill the machine (C1's 10^4 particles are one warp on half of the schedulers) is bound by
 // the dependent chain of ONE step, not by issue slots or the shared-memory port: such launches take the combined
 // spherical table for every static model, in its 4-deep Estrin form -- q -> r^2 -> lookup -> p instead of
 // q -> r^2 -> rsqrt -> r -> s -> 1 + s -> rcp -> table log -> shape -> 1/r^3 -> p.
@@ -824,7 +830,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
     // tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? 1 : 0);
+    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? GX_SPH_FIXED_FORM : 0);
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     // MIX (MilkyWayPotential in large batches): the closed forms cost issue slots (169 per warp-step, the kernel's whole
@@ -882,7 +888,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qz = fma(pz, hs, qz);
                     if constexpr (C::is_static) {
                         double fh, fv;
-                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 1>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
+                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_SPH_FIXED_FORM>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
                         else gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
                         if constexpr (MIX) ++gstep;
                         const double fhh = -fh * hs, fvh = -fv * hs;
@@ -906,7 +912,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 double npx, npy, npz;
                 if constexpr (C::is_static) {
                     double fh, fv;
-                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 1>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_SPH_FIXED_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                     else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                     if constexpr (MIX) ++gstep;
                     const double fhh = -fh * hs, fvh = -fv * hs;
@@ -2051,9 +2057,9 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
         switch (model) {
 #define GX_SEG_STATIC(C_)                                                                                     \
     do {                                                                                                      \
-        if (small) {                                                                                          \
-            if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, true, EPI>>(grid, block, dyn, s, D, a, sg);   \
-            else launch_dyn<k_integrate_fixed_seg<C_, false, true, EPI>>(grid, block, dyn, s, D, a, sg);      \
+        if (GX_FIXED_SMALL && small) {                                                                        \
+            if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, GX_FIXED_SMALL != 0, EPI>>(grid, block, dyn, s, D, a, sg);   \
+            else launch_dyn<k_integrate_fixed_seg<C_, false, GX_FIXED_SMALL != 0, EPI>>(grid, block, dyn, s, D, a, sg);      \
         } else {                                                                                              \
             if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, false, EPI>>(grid, block, dyn, s, D, a, sg);  \
             else launch_dyn<k_integrate_fixed_seg<C_, false, false, EPI>>(grid, block, dyn, s, D, a, sg);     \
@@ -2085,10 +2091,10 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
 #define GX_GEN_STATIC(C_)                                                                                          \
     do {                                                                                                           \
         if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {                                                             \
-            if (small) GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, true);                                            \
+            if (GX_FIXED_SMALL && small) GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, GX_FIXED_SMALL != 0);           \
             else GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, false);                                                 \
         } else {                                                                                                   \
-            if (small) GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, true);                                              \
+            if (GX_FIXED_SMALL && small) GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, GX_FIXED_SMALL != 0);             \
             else GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, false);                                                   \
         }                                                                                                          \
     } while (0)

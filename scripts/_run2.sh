@@ -1,3 +1,2 @@
-for v in mix34b mix58 mix1116 mix1316; do
-GALAX_B200_LIB=build_variants/libgx_$v.so python scripts/perf_r2.py k2 2>&1 | tail -1 | cut -c1-80
-done
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
+python scripts/perf_c1.py | tail -1

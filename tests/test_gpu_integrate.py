@@ -651,3 +651,26 @@ def test_time_dependent_potentials_in_stream_release_and_energies():
     w0 = gd.PhaseSpaceCoordinate(np.array([30.0, 10, 20]), np.array([10.0, -150, -20]) * KMS, 0.0)
     stream, prog = gen.run(7, np.linspace(0.0, 1500.0, 64), w0, 1e4)
     assert np.isfinite(stream.q).all() and stream.q.shape == (128, 3)
+
+
+@pytest.mark.parametrize("name", list(PAIRS))
+def test_a_particle_does_not_depend_on_the_batch_it_travels_in(name):
+    """One arithmetic for every batch size (narrow CTAs for small batches, the same instructions): a particle integrated
+    alone, in a batch of 10^3 or inside 10^5 others gives the same bits -- what makes a sharded multi-GPU run equal to
+    the unsharded one.  Fixed step (the run-length and the step-by-step kernel, MilkyWayPotential's
+    alternating table / closed-form steps included) and Dopri8."""
+    cls, ofun = PAIRS[name]
+    pot, opot = cls(), ofun()
+    q0, p0 = synthetic_ics(opot, 100_000, seed=61)
+    ts = np.linspace(0.0, 60.0, 4)
+    big = SIE.solve(pot, (q0, p0), 0.0, 60.0, dt0=0.1, saveat=ts)
+    for n in (1, 1000):
+        small = SIE.solve(pot, (q0[:n], p0[:n]), 0.0, 60.0, dt0=0.1, saveat=ts)
+        assert np.array_equal(small.ys[0], big.ys[0][:n]) and np.array_equal(small.ys[1], big.ys[1][:n]), n
+    gen = gd._integrate(pot, q0[:1000], p0[:1000], 0.0, 60.0, ts, solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(),
+                        dt0=0.1, max_steps=None, general_kernel=True)
+    assert np.array_equal(gen[0], big.ys[0][:1000])
+    ad = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=1e-9, atol=1e-9))
+    bigd = ad.solve(pot, (q0[:30_000], p0[:30_000]), 0.0, 200.0, saveat=np.linspace(0, 200.0, 5))
+    one = ad.solve(pot, (q0[:257], p0[:257]), 0.0, 200.0, saveat=np.linspace(0, 200.0, 5))
+    assert np.array_equal(one.ys[0], bigd.ys[0][:257]) and np.array_equal(one.stats["num_steps"], bigd.stats["num_steps"][:257])

@@ -118,6 +118,8 @@ def build(force: bool = False, verbose: bool = False, defines: Sequence[str] = (
                          capture_output=True, text=True, env=env)
     if res.returncode != 0:
         raise GalaxB200Error(f"nvcc link failed:\n{res.stdout}\n{res.stderr}")
+    for o in objs:  # (the objects are as large as the library and would travel with every snapshot of the tree)
+        Path(o).unlink(missing_ok=True)
     return target
 
 

@@ -978,6 +978,24 @@ __host__ __device__ constexpr bool db_row_nz(int l) {
     return false;
 }
 
+// Dense-output weight of stage l at theta: theta * sum_m D(l, m) theta^m.  For every row but the first the constant term
+// D(l, 0) vanishes (the interpolant's slope at theta = 0 is k_1 alone), so those rows are theta^2 * (degree-4 Horner):
+// one FP64 instruction and one constant load fewer per row, 20 rows per save.  Shared by the in-kernel SaveAt path and
+// k_dense_eval so that both give the same bits.
+template <class TB, bool Q>
+__device__ __forceinline__ double dense_weight(int l, double th, double th2) {
+    const bool c0 = Q ? TB::DQ_NZ(l, 0) : TB::DB_NZ(l, 0);
+    double w = Q ? TB::DQ(l, 5) : TB::DB(l, 5);
+    if (c0) {
+#pragma unroll
+        for (int m = 4; m >= 0; --m) w = fma(w, th, Q ? TB::DQ(l, m) : TB::DB(l, m));
+        return w * th;
+    }
+#pragma unroll
+    for (int m = 4; m >= 1; --m) w = fma(w, th, Q ? TB::DQ(l, m) : TB::DB(l, m));
+    return w * th2;
+}
+
 __device__ __forceinline__ double rms6(double a, double b, double c, double d, double e, double f) {
     double s = a * a;
     s = fma(b, b, s); s = fma(c, c, s); s = fma(d, d, s); s = fma(e, e, s); s = fma(f, f, s);
@@ -1367,22 +1385,16 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
 #else
         while (__any_sync(FULL, want)) {
             if (want) {
-                const double th = (tsave - tprev) / (tnext - tprev);
+                const double th = (tsave - tprev) / (tnext - tprev), th2 = th * th;
                 double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
 #pragma unroll
                 for (int l = 0; l < NS; ++l) {
                     if (dq_row_nz<TB>(l)) {
-                        double w = TB::DQ(l, 5);
-#pragma unroll
-                        for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DQ(l, m));
-                        w *= th;
+                        const double w = dense_weight<TB, true>(l, th, th2);
                         wqx = fma(w, AX(l), wqx); wqy = fma(w, AY(l), wqy); wqz = fma(w, AZ(l), wqz);
                     }
                     if (db_row_nz<TB>(l)) {
-                        double w = TB::DB(l, 5);
-#pragma unroll
-                        for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DB(l, m));
-                        w *= th;
+                        const double w = dense_weight<TB, false>(l, th, th2);
                         wpx = fma(w, AX(l), wpx); wpy = fma(w, AY(l), wpy); wpz = fma(w, AZ(l), wpz);
                     }
                 }
@@ -1737,23 +1749,17 @@ __global__ void __launch_bounds__(256) k_dense_eval(const double *__restrict__ r
     }
     const double *r = rec + (long long)lo * REC_DOUBLES;
     const double tprev = r[0], tnext = r[1], hd = r[2], hd2 = hd * hd;
-    const double th = (tau - tprev) / (tnext - tprev);
+    const double th = (tau - tprev) / (tnext - tprev), th2 = th * th;
     double wqx = 0, wqy = 0, wqz = 0, wpx = 0, wpy = 0, wpz = 0;
 #pragma unroll
     for (int l = 0; l < NS; ++l) {
         const double ax = r[9 + 3 * l], ay = r[10 + 3 * l], az = r[11 + 3 * l];
         if (dq_row_nz<TB>(l)) {
-            double w = TB::DQ(l, 5);
-#pragma unroll
-            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DQ(l, m));
-            w *= th;
+            const double w = dense_weight<TB, true>(l, th, th2);
             wqx = fma(w, ax, wqx); wqy = fma(w, ay, wqy); wqz = fma(w, az, wqz);
         }
         if (db_row_nz<TB>(l)) {
-            double w = TB::DB(l, 5);
-#pragma unroll
-            for (int m = 4; m >= 0; --m) w = fma(w, th, TB::DB(l, m));
-            w *= th;
+            const double w = dense_weight<TB, false>(l, th, th2);
             wpx = fma(w, ax, wpx); wpy = fma(w, ay, wpy); wpz = fma(w, az, wpz);
         }
     }

@@ -220,7 +220,7 @@ static bool sph_same(const std::vector<SphComp> &a, const std::vector<SphComp> &
         if (a[k].kind != b[k].kind || a[k].GM != b[k].GM || a[k].p1 != b[k].p1 || a[k].p2 != b[k].p2) return false;
     return true;
 }
-constexpr size_t SPH_CACHE_MAX = 256;
+constexpr size_t SPH_CACHE_MAX = 4096;  // x 44 KB = 180 MB of device memory at most (a parameter scan: 15-25 ms of host time per new set)
 static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr, bool may_upload = true) {
     struct Entry { int device; std::vector<SphComp> cs; double *dev_ptr; double max_rel_err; };
     static std::mutex mu;

@@ -16,7 +16,7 @@
  *   - re-entrant and safe to call from several host threads / on several streams: the potential is passed by value
  *     into each launch (kernel-parameter constant bank).  Process-wide state: (1) an append-only, mutex-guarded cache
  *     of immutable force tables (NFW 30 KB, PowerLawCutoff 35 KB per exponent, and for the three named Milky-Way
- *     models 44 KB per distinct set of spherical-component parameters, at most 256 sets; device memory, fitted,
+ *     models 44 KB per distinct set of spherical-component parameters, at most 4096 sets = 180 MB; device memory, fitted in 15-25 ms of host time,
  *     allocated and uploaded on FIRST use -- the one allocation an enqueue-only entry can make, so warm an entry up
  *     once with a potential before capturing it into a graph);
  *     (2) for the adaptive integrators, a per-device __constant__ copy of the potential that a launch reads only when

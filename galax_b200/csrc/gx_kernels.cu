@@ -2145,8 +2145,12 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
     a.N = N; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
     walk_time_grid(t0, t1, dt0, max_steps, sg, seg_ok, a.n_steps, a.hit_max_steps);
-    // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers
-    const int block = (N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32);
+    // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers.  The static models stage their
+    // 44 KB force table per CTA, so five CTAs are resident per SM whatever their width: the narrowest CTA that still
+    // puts the whole batch on the machine in one wave (a second wave of narrow CTAs cost 60 000 particles 50 %)
+    const bool tabled = GX_SPH_TABLE && model != MODEL_GENERIC;
+    const int block = tabled ? ((N > 148LL * 5 * 64) ? 128 : ((N > 148LL * 5 * 32) ? 64 : 32))
+                             : ((N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32));
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
     const bool fwd = dir > 0;

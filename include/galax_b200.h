@@ -215,7 +215,8 @@ int gx_dense_eval_solver(int32_t solver, const double *rec, const int32_t *n_rec
  * gx_integrate_adaptive controls the step per particle (the reference under vmap / lstrat.VMap / batched t0).  The two
  * agree to the tolerance, not to rounding; this entry gives the reference's numbers for that call form.  One
  * cooperative launch (the grid must be resident: at most 2048 CTAs walk the batch), reductions in a fixed order, so
- * results are reproducible run to run.  status / n_accepted / n_attempted: ONE int32 each (the solve is one ODE).
+ * results are reproducible run to run (a cooperative launch: enqueue-only like the other entries, but do not count on
+ * capturing it into a CUDA graph).  status / n_accepted / n_attempted: ONE int32 each (the solve is one ODE).
  * workspace: gx_joint_workspace_bytes(N) bytes.  Any potential the per-particle entry accepts, LinearParameter included. */
 int64_t gx_joint_workspace_bytes(int64_t N);
 int gx_integrate_adaptive_joint(int32_t solver, const gx_potential *pot, const gx_pid *pid, const double *q0,

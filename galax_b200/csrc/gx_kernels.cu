@@ -211,8 +211,10 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
         // ... and the NFW force table for MW / MW2022: without it (allocation failed) they run as runtime composites
         if ((model == MODEL_MW || model == MODEL_MW2022) && use_device && D.nfw_tab == nullptr) model = MODEL_GENERIC;
 #if GX_SPH_TABLE
-        // the composite's combined spherical table S(r^2) (fitted and uploaded on first use of these parameters)
-        if (model != MODEL_GENERIC && use_device) {
+        // the composite's combined spherical table S(r^2) (fitted and uploaded on first use of these parameters): the
+        // three named models need it (else they run as runtime composites); any other composite of the four basic
+        // kinds takes it when it has spherical components (CountsBasicTab), and runs without it otherwise
+        if (use_device && (model != MODEL_GENERIC || D.n_hern + D.n_nfw + D.n_plc > 0)) {
             std::vector<SphComp> cs;
             for (int i = 0; i < pot->n; ++i) {
                 const gx_component &c = pot->c[i];
@@ -220,6 +222,7 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
                 if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
             }
             D.sph_tab = sph_table_for(cs, nullptr, may_upload);
+            D.sph_j0 = (unsigned)((1023 + sph_e_lo(cs)) << SPH_SUB_BITS);
             if (D.sph_tab == nullptr) model = MODEL_GENERIC;
         }
 #endif
@@ -897,7 +900,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                         pz = fma(fvh, qz, pz);
                     } else {
                         double g0, g1, g2;
-                        gradient<C, false, false>(P, qx, qy, qz, g0, g1, g2);
+                        gradient<C, false, false, SPHT>(P, qx, qy, qz, g0, g1, g2, 0.0, nfw_base);
                         px = fma(-g0, hs, px);
                         py = fma(-g1, hs, py);
                         pz = fma(-g2, hs, pz);
@@ -919,7 +922,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     npx = fma(fhh, nqx, px); npy = fma(fhh, nqy, py); npz = fma(fvh, nqz, pz);
                 } else {
                     double g0, g1, g2;
-                    gradient<C, false, false>(P, nqx, nqy, nqz, g0, g1, g2);
+                    gradient<C, false, false, SPHT>(P, nqx, nqy, nqz, g0, g1, g2, 0.0, nfw_base);
                     npx = fma(-g0, hs, px); npy = fma(-g1, hs, py); npz = fma(-g2, hs, pz);
                 }
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)
@@ -2077,8 +2080,13 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
 #undef GX_SEG_STATIC
         default:  // runtime composite, no time-dependent parameter
             if (is_basic_composite(D, model)) {
-                if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasic, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
-                else launch_dyn<k_integrate_fixed_seg<CountsBasic, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                if (D.sph_tab) {  // spherical components in the combined table
+                    if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasicTab, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                    else launch_dyn<k_integrate_fixed_seg<CountsBasicTab, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                } else {
+                    if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasic, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                    else launch_dyn<k_integrate_fixed_seg<CountsBasic, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                }
             } else {
                 if (fwd) launch_dyn<k_integrate_fixed_seg<CountsRuntime, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
                 else launch_dyn<k_integrate_fixed_seg<CountsRuntime, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
@@ -2109,7 +2117,10 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
     case MODEL_MW2022: GX_GEN_STATIC(CountsMW2022); break;
     case MODEL_BOVY: GX_GEN_STATIC(CountsBovy); break;
     default:
-        if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) GX_GEN(CountsRuntime, GX_SCHEME_SEMI_IMPLICIT_EULER, false);
+        if (is_basic_composite(D, model) && D.sph_tab) {  // (the same arithmetic as the run-length kernel's)
+            if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) GX_GEN(CountsBasicTab, GX_SCHEME_SEMI_IMPLICIT_EULER, false);
+            else GX_GEN(CountsBasicTab, GX_SCHEME_LEAPFROG_MIDPOINT, false);
+        } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) GX_GEN(CountsRuntime, GX_SCHEME_SEMI_IMPLICIT_EULER, false);
         else GX_GEN(CountsRuntime, GX_SCHEME_LEAPFROG_MIDPOINT, false);
         break;
     }
@@ -2148,7 +2159,7 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
     // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers.  The static models stage their
     // 44 KB force table per CTA, so five CTAs are resident per SM whatever their width: the narrowest CTA that still
     // puts the whole batch on the machine in one wave (a second wave of narrow CTAs cost 60 000 particles 50 %)
-    const bool tabled = GX_SPH_TABLE && model != MODEL_GENERIC;
+    const bool tabled = GX_SPH_TABLE && (model != MODEL_GENERIC || (is_basic_composite(D, model) && D.sph_tab));
     const int block = tabled ? ((N > 148LL * 5 * 64) ? 128 : ((N > 148LL * 5 * 32) ? 64 : 32))
                              : ((N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32));
     const int grid = grid_for(N, block);
@@ -2319,8 +2330,10 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     std::lock_guard<std::mutex> img_lock(g_img_mtx);
     const int img = use_const_image(D, s, dev);
     if (img < 0) return img;
-    if (is_basic_composite(D, model)) GX_LAUNCH_DP8(CountsBasic);
-    else GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
+    if (is_basic_composite(D, model)) {
+        if (D.sph_tab) GX_LAUNCH_DP8(CountsBasicTab);
+        else GX_LAUNCH_DP8(CountsBasic);
+    } else GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
     rc = cuda_rc(cudaGetLastError());
     if (rc == 0 && img) rc = const_image_used(s, dev);
     return rc;
@@ -2662,7 +2675,7 @@ int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capa
     if (cs.empty()) return GX_ERR_UNSUPPORTED;
     if (n_intervals) *n_intervals = SPH_NINT;
     if (degree) *degree = SPH_DEG;
-    if (e_lo) *e_lo = SPH_E_LO;
+    if (e_lo) *e_lo = sph_e_lo(cs);
     if (sub_bits) *sub_bits = SPH_SUB_BITS;
     if (!coef && !max_rel_err) return 0;
     if (coef && capacity < (int64_t)SPH_NINT * SPH_ROW) return GX_ERR_BADARG;

@@ -150,15 +150,18 @@ constexpr int NFW_NINT = (NFW_E_HI - NFW_E_LO) * PLC_SUB;
 // PowerLawCutoff lookups in s = r/r_s (MilkyWayPotential2022: 77 -> 62 FP64 instructions, 6 -> 4 MUFU chains), and the
 // lookup no longer waits for sqrt(r^2).
 // Layout: 2^SPH_SUB_BITS = 32 intervals per octave of u (= 64 per octave of r: u^(-3/2) converges like 130^-n), degree
-// 7, u in [2^-8, 2^14) (r from 62 pc to 128 kpc): 704 rows of 8 doubles = 64 B = FOUR 16-byte loads per lookup, 44 KB
+// 7, 22 octaves of u (MW models: r from 62 pc to 128 kpc): 704 rows of 8 doubles = 64 B = FOUR 16-byte loads per lookup, 44 KB
 // of shared memory.  (First version: degree 9 on 16 intervals, 80-byte rows, five loads.  The fixed-step kernels that
 // use the table are bound by the shared-memory port -- every lane reads another row -- so a row is as short as the
 // accuracy allows.)  A 64-byte row stride would put a chunk of every second row in the same bank group, so the four
 // 16-byte chunks of row j are stored XOR-swizzled: chunk c at position c ^ ((j >> 1) & 3); eight consecutive rows then
 // cover the eight bank groups for every c, as an odd stride would, without padding.
 // Outside the range: the closed forms (spherical_fallback, out of line).
-constexpr int SPH_E_LO = -8, SPH_E_HI = 14, SPH_SUB_BITS = 5, SPH_DEG = 7, SPH_ROW = SPH_DEG + 1;
-constexpr int SPH_NINT = (SPH_E_HI - SPH_E_LO) << SPH_SUB_BITS;
+// The 22 octaves are placed per potential (sph_e_lo() in plc_table.h): up to 8 x the largest scale radius of the
+// spherical components, rounded up to a power of two -- [2^-8, 2^14) kpc^2 for the three Milky-Way models in galactic
+// units; the library does not know the unit system, the scale radii do.
+constexpr int SPH_E_LO = -8, SPH_OCTAVES = 22, SPH_SUB_BITS = 5, SPH_DEG = 7, SPH_ROW = SPH_DEG + 1;
+constexpr int SPH_NINT = SPH_OCTAVES << SPH_SUB_BITS;
 static_assert(SPH_ROW == 8, "rows are four 16-byte chunks (swizzle, Estrin form)");
 #ifndef GX_SPH_TABLE
 #define GX_SPH_TABLE 1
@@ -212,6 +215,8 @@ struct alignas(16) DevPot {
     DevHenon henon[MAX_HENON];
     const double *nfw_tab;  // universal NFW force table (nfw_table(), plc_table.h) or nullptr
     const double *sph_tab;  // this composite's spherical force table S(r^2) (sph_table_for(), plc_table.h) or nullptr
+    unsigned sph_j0;        // ... and where it starts: (1023 + e_lo) << SPH_SUB_BITS, the table covers u in [2^e_lo, 2^(e_lo + 22))
+    unsigned pad_sph_;
     DevTD td;
 };
 
@@ -288,9 +293,13 @@ __device__ __forceinline__ void rad_profile(const DevRad &c, double m2, double &
 
 // Static component counts let the compiler unroll and schedule the whole evaluation as one block of
 // straight-line code; Runtime (-1) is the generic fallback for arbitrary composites of the four kinds.
-template <int NMN, int NH, int NNFW, int NPLC, bool MN_SHARED_B = false, bool BASIC = false>
+template <int NMN, int NH, int NNFW, int NPLC, bool MN_SHARED_B = false, bool BASIC = false, bool BASIC_TAB = false>
 struct Counts {
     static constexpr bool is_static = (NMN >= 0);
+    // BASIC_TAB (with BASIC): the composite's spherical components -- however many Hernquist / NFW / PowerLawCutoff
+    // terms -- are ONE lookup in its combined force table S(r^2), as for the three named models; only the
+    // Miyamoto-Nagai terms are looped over at run time.  The host picks it when the table exists (P.sph_tab).
+    static constexpr bool basic_tab = BASIC && BASIC_TAB;
     // BASIC (runtime counts only): a composite of the four basic kinds with constant parameters -- the loops over the
     // further kinds and the time-dependent branch are compiled out (the full runtime kernel is 85 KB of SASS against a
     // 32 KB instruction cache).
@@ -312,6 +321,7 @@ struct Counts {
 };
 using CountsRuntime = Counts<-1, -1, -1, -1>;
 using CountsBasic = Counts<-1, -1, -1, -1, false, true>;  // runtime counts of MN / Hernquist / NFW / PowerLawCutoff only
+using CountsBasicTab = Counts<-1, -1, -1, -1, false, true, true>;  // ... with the spherical ones in the combined table
 using CountsMW = Counts<1, 2, 1, 0>;      // MilkyWayPotential:      MN disk, NFW halo, 2 Hernquist
 using CountsMW2022 = Counts<3, 2, 1, 0, true>;  // MilkyWayPotential2022:  MN3 disk (one b), NFW halo, 2 Hernquist
 using CountsBovy = Counts<1, 0, 1, 1>;    // BovyMWPotential2014:    MN disk, PLC bulge, NFW halo
@@ -386,7 +396,9 @@ __device__ __forceinline__ unsigned nfw_stage(const DevPot &P) {
 // The combined spherical table S(r^2) of a static model (MW, MW2022, Bovy): which kernels use it, and its staging.
 //   mode 0: not used; 1: Horner (issue-bound fixed-step kernels); 2: Estrin (latency-bound Dopri kernels).
 template <class C>
-__host__ __device__ constexpr bool sph_tab_ok() { return GX_SPH_TABLE && C::is_static && (C::kH + C::kNFW + C::kPLC > 0); }
+__host__ __device__ constexpr bool sph_tab_ok() {
+    return GX_SPH_TABLE && ((C::is_static && (C::kH + C::kNFW + C::kPLC > 0)) || C::basic_tab);
+}
 // Fixed step: the lookup moves 80 B per lane from scattered rows through the SM's one shared-memory port (~60 port
 // cycles per warp with the bank conflicts); MilkyWayPotential's single-disk step is short enough to saturate it (the
 // NFW table alone cost it 14 %), so the fixed-step kernels take the table from GX_SPH_TABLE_FIXED_MIN_MN disks up or
@@ -396,7 +408,7 @@ __host__ __device__ constexpr bool sph_tab_ok() { return GX_SPH_TABLE && C::is_s
 #endif
 template <class C>
 __host__ __device__ constexpr bool sph_tab_fixed_ok() {
-    return sph_tab_ok<C>() && (C::kMN >= GX_SPH_TABLE_FIXED_MIN_MN || C::kPLC > 0);
+    return sph_tab_ok<C>() && (C::basic_tab || C::kMN >= GX_SPH_TABLE_FIXED_MIN_MN || C::kPLC > 0);
 }
 // Fixed-step kernels of a static model that does NOT take the table on every step (MilkyWayPotential): out of every
 // GX_SPH_MIX_PERIOD steps, GX_SPH_MIX_TABLE use the table and the rest the closed forms (0: never mix).
@@ -440,10 +452,10 @@ __device__ __forceinline__ unsigned sph_stage(const DevPot &P) {
 // S(u) from the staged table (base = its shared-window address); false outside the tabulated range.
 // ESTRIN: 9 FP64 instructions, 3 deep (latency-bound callers: the Dopri kernels, small batches); else Horner, 7.
 template <bool ESTRIN>
-__device__ __forceinline__ bool sph_table_eval(double u, double &S, unsigned base) {
+__device__ __forceinline__ bool sph_table_eval(double u, double &S, unsigned base, unsigned j0) {
     const int hi = __double2hiint(u);
     constexpr int B = SPH_SUB_BITS;
-    const unsigned j = (unsigned)(hi >> (20 - B)) - (unsigned)((1023 + SPH_E_LO) << B);
+    const unsigned j = (unsigned)(hi >> (20 - B)) - j0;  // j0 = (1023 + e_lo) << B: the table's first octave (per potential)
     if (j >= (unsigned)SPH_NINT) return false;  // u outside the table (also NaN / negative)
     // t in [-1, 1) on the interval, straight from the bits of u (see poly_table_eval)
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
@@ -592,12 +604,12 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
         fxy += f;
         fz = fma(f, apz * rzs, fz);
     }
-    const bool any_sph = C::is_static ? (C::kH + C::kNFW + C::kPLC > 0)
-                                      : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
+    const bool any_sph = (C::is_static || SPH != 0) ? (SPH != 0 || C::kH + C::kNFW + C::kPLC > 0)
+                                                    : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
     if (any_sph) {
         const double r2 = R2 + z2;  // (R2 carries the TINY that keeps r > 0)
         if constexpr (SPH != 0) {
-            if (!sph_table_eval<SPH == 2>(r2, fs, nfw_base)) fs = spherical_fallback<C>(&P, r2);
+            if (!sph_table_eval<SPH == 2>(r2, fs, nfw_base, P.sph_j0)) fs = spherical_fallback<C>(&P, r2);
         } else {
             fs = spherical_factor<C, PLC_SMEM, NFW_TAB>(P, r2, plc_base, nfw_base);
         }

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cmath>
 
 #include <mutex>
 #include <vector>
@@ -196,13 +197,28 @@ static long double sph_S_ld(const std::vector<SphComp> &cs, long double u) {
     return sum;
 }
 
+// First octave (of u = r^2) of the table of these components: the 22 octaves end at (8 x the largest scale radius)^2
+// rounded up to a power of two; components without a scale (Kepler = Hernquist with c = 0) leave the default.
+static int sph_e_lo(const std::vector<SphComp> &cs) {
+    double smax = 0.0;
+    for (const SphComp &c : cs)
+        if (c.p1 > smax && std::isfinite(c.p1)) smax = c.p1;
+    if (!(smax > 0.0)) return SPH_E_LO;
+    const int e_hi_r = (int)ceil(log2(8.0 * smax));  // r up to 2^e_hi_r
+    int e_lo = 2 * e_hi_r - SPH_OCTAVES;
+    if (e_lo < -900) e_lo = -900;
+    if (e_lo > 900) e_lo = 900;
+    return e_lo;
+}
+
 // Fit of the table (host only; also used by gx_spherical_force_table): coef[SPH_NINT][SPH_ROW] in natural order,
 // returns the worst relative error of the fp64 Horner evaluation against the long-double function on a 41-point grid
 // per interval.
 static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
     double worst = 0.0;
+    const int e_lo = sph_e_lo(cs);
     for (int j = 0; j < SPH_NINT; ++j) {
-        const int e = SPH_E_LO + (j >> SPH_SUB_BITS), sub = j & ((1 << SPH_SUB_BITS) - 1);
+        const int e = e_lo + (j >> SPH_SUB_BITS), sub = j & ((1 << SPH_SUB_BITS) - 1);
         const long double base = ldexpl(1.0L, e), nsub = (long double)(1 << SPH_SUB_BITS);
         fit_interval<SPH_ROW>([&cs](long double u) { return sph_S_ld(cs, u); }, base * (1.0L + sub / nsub),
                               base * (1.0L + (sub + 1) / nsub), coef + (size_t)j * SPH_ROW, &worst);

@@ -135,6 +135,26 @@ def test_combined_spherical_table_on_the_host(name):
         assert np.abs(S / ref - 1).max() < 8e-16, ev.__name__
 
 
+def test_combined_spherical_table_follows_the_scale_radii():
+    """The 22 octaves end at (8 x the largest scale radius)^2 rounded up to a power of two: the library does not know the
+    unit system, the scale radii do.  Any composite of Hernquist / NFW / PowerLawCutoff terms gets one."""
+    import galax_b200.potential as gp
+
+    cases = [
+        (gp.CompositePotential(d=gp.MiyamotoNagaiPotential(5e10, 3.0, 0.3), b=gp.HernquistPotential(4e9, 0.5), h=gp.NFWPotential(8e11, 20.0)), -6),
+        (gp.CompositePotential(b=gp.HernquistPotential(1e6, 2e-3), h=gp.NFWPotential(1e8, 0.1)), -22),     # a dwarf, in kpc
+        (gp.CompositePotential(b=gp.HernquistPotential(4e9, 500.0), h=gp.NFWPotential(8e11, 2e4)), 14),      # the same galaxy in pc
+        (gp.KeplerPotential(1e12), -8),                                                                       # no scale: default
+    ]
+    rng = np.random.default_rng(6)
+    for pot, want in cases:
+        coef, e_lo, sb, err = sph_table(pot)
+        assert e_lo == want and coef.shape == (704, 8) and err < 4e-16, (want, e_lo, err)
+        u = 2.0 ** rng.uniform(e_lo, e_lo + 22, 120)
+        ref = sph_reference(pot, [mp.sqrt(mp.mpf(float(x))) for x in u])
+        assert np.abs(evaluate(coef, e_lo, sb, u) / ref - 1).max() < 8e-16
+
+
 def test_combined_spherical_table_bad_arguments():
     import galax_b200.potential as gp
 

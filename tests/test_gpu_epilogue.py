@@ -128,7 +128,9 @@ def test_dopri8_epilogue_unreached_saves_are_nan_and_runtime_composites():
     t0 = np.linspace(0.0, 100.0, 64)
     tsb = np.linspace(100.0, 400.0, 9)
     q, p, status, st = gd._integrate(comp, q0, p0, t0, 400.0, tsb, diagnostics=("energy", "angular_momentum"), **DP8)
-    assert np.array_equal(st["energy"], gd._energy(comp, q, p)) and np.isfinite(st["energy"]).all()
+    # (a runtime composite: the fused epilogue and the stand-alone pass are different instantiations of the evaluator,
+    #  so rounding-level, not bit-level, agreement)
+    assert np.abs(st["energy"] / gd._energy(comp, q, p) - 1).max() < 1e-15 and np.isfinite(st["energy"]).all()
 
 
 def test_epilogue_refuses_what_it_cannot_do():

@@ -715,6 +715,9 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #ifndef GX_FIXED_SMALL
 #define GX_FIXED_SMALL 0
 #endif
+#ifndef GX_BASIC_MIX
+#define GX_BASIC_MIX 0
+#endif
 // how a fixed-step table step evaluates its polynomial, for every batch size: 1 Horner (7 FP64, 7 deep), 2 Estrin (9, 3 deep)
 #ifndef GX_SPH_FIXED_FORM
 #define GX_SPH_FIXED_FORM 1
@@ -767,7 +770,9 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
                 npz = fma(fvh, nqz, pz);
                 gx_ = gy_ = gz_ = 0.0;
             } else {
-                gradient<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
+                if (GX_BASIC_MIX && C::basic_tab && GX_SPH_MIX_PERIOD > 0 && P.n_mn <= 1 && !sph_mix_table_step((unsigned long long)n))
+                    gradient<C, false, false, 0>(P, nqx, nqy, nqz, gx_, gy_, gz_);
+                else gradient<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, gx_, gy_, gz_, FWD ? tprev : -tprev, nfw_base);
                 npx = fma(-gx_, hs, px);
                 npy = fma(-gy_, hs, py);
                 npz = fma(-gz_, hs, pz);
@@ -849,6 +854,9 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
     unsigned gstep = 0;  // index of the step in the whole grid (MIX)
+    // (a runtime composite with one disk is MilkyWayPotential's case, but its closed forms are loops with runtime trip
+    //  counts: alternating measured 2.01e11 against 2.11e11 on the table alone -- GX_BASIC_MIX=1 builds only)
+    const bool mixb = GX_BASIC_MIX && C::basic_tab && GX_SPH_MIX_PERIOD > 0 && P.n_mn <= 1;
     const double T0 = FWD ? a.t0 : -a.t0;
     double qx = a.q0[3 * i], qy = a.q0[3 * i + 1], qz = a.q0[3 * i + 2];
     double px = a.p0[3 * i], py = a.p0[3 * i + 1], pz = a.p0[3 * i + 2];
@@ -900,7 +908,9 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                         pz = fma(fvh, qz, pz);
                     } else {
                         double g0, g1, g2;
-                        gradient<C, false, false, SPHT>(P, qx, qy, qz, g0, g1, g2, 0.0, nfw_base);
+                        if (mixb && !sph_mix_table_step(gstep)) gradient<C, false, false, 0>(P, qx, qy, qz, g0, g1, g2);
+                        else gradient<C, false, false, SPHT>(P, qx, qy, qz, g0, g1, g2, 0.0, nfw_base);
+                        if constexpr (C::basic_tab) ++gstep;
                         px = fma(-g0, hs, px);
                         py = fma(-g1, hs, py);
                         pz = fma(-g2, hs, pz);
@@ -922,7 +932,9 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     npx = fma(fhh, nqx, px); npy = fma(fhh, nqy, py); npz = fma(fvh, nqz, pz);
                 } else {
                     double g0, g1, g2;
-                    gradient<C, false, false, SPHT>(P, nqx, nqy, nqz, g0, g1, g2, 0.0, nfw_base);
+                    if (mixb && !sph_mix_table_step(gstep)) gradient<C, false, false, 0>(P, nqx, nqy, nqz, g0, g1, g2);
+                    else gradient<C, false, false, SPHT>(P, nqx, nqy, nqz, g0, g1, g2, 0.0, nfw_base);
+                    if constexpr (C::basic_tab) ++gstep;
                     npx = fma(-g0, hs, px); npy = fma(-g1, hs, py); npz = fma(-g2, hs, pz);
                 }
                 while (tsave <= tnext) {  // LocalLinearInterpolation between (tprev, y) and (tnext, yn)

@@ -10,7 +10,7 @@ SIE = dict(solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(), dt0=
 mw = gp.MilkyWayPotential()
 generic = gp.CompositePotential(dict(disk=gp.MiyamotoNagaiPotential(6.8e10, 3.0, 0.28), halo=gp.NFWPotential(5.4e11, 15.62),
                                      bulge=gp.HernquistPotential(5e9, 1.0), nucleus=gp.HernquistPotential(1.71e9, 0.07),
-                                     extra=gp.PlummerPotential(1e3, 1.0)))  # (a fifth component keeps it off the MW kernel)
+                                     extra=gp.KeplerPotential(1e3)))  # (a fifth component keeps it off the MW kernel; one disk)
 for name, pot in (("MW static", mw), ("MW + tiny Plummer, runtime kernel", generic), ("LM10", gp.LM10Potential())):
     N, steps = 148 * 8192, 2000
     q, p = ics(mw, N)

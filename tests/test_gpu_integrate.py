@@ -674,3 +674,32 @@ def test_a_particle_does_not_depend_on_the_batch_it_travels_in(name):
     bigd = ad.solve(pot, (q0[:30_000], p0[:30_000]), 0.0, 200.0, saveat=np.linspace(0, 200.0, 5))
     one = ad.solve(pot, (q0[:257], p0[:257]), 0.0, 200.0, saveat=np.linspace(0, 200.0, 5))
     assert np.array_equal(one.ys[0], bigd.ys[0][:257]) and np.array_equal(one.stats["num_steps"], bigd.stats["num_steps"][:257])
+
+
+def test_runtime_composites_on_the_combined_table():
+    """A composite of the four basic kinds that is none of the three named models (CountsBasicTab): spherical terms in the
+    potential's own force table, disks looped over at run time; with at most one disk the steps alternate between table and
+    closed forms as MilkyWayPotential's do.  Against the oracle, and run-length == step-by-step kernel bit for bit."""
+    one_disk = gp.CompositePotential(disk=gp.MiyamotoNagaiPotential(5e10, 3.0, 0.3), bulge=gp.HernquistPotential(4e9, 0.5),
+                                     halo=gp.NFWPotential(8e11, 20.0))
+    o_one = op.Potential((op.Component(op.KIND_MN, (5e10, 3.0, 0.3)), op.Component(op.KIND_HERNQUIST, (4e9, 0.5)),
+                          op.Component(op.KIND_NFW, (8e11, 20.0))))
+    two_disks = gp.CompositePotential(thin=gp.MiyamotoNagaiPotential(4e10, 3.0, 0.25), thick=gp.MiyamotoNagaiPotential(1e10, 2.5, 0.9),
+                                      bulge=gp.PowerLawCutoffPotential(5e9, 1.8, 1.9), halo=gp.NFWPotential(6e11, 18.0),
+                                      bh=gp.KeplerPotential(4e6))
+    o_two = op.Potential((op.Component(op.KIND_MN, (4e10, 3.0, 0.25)), op.Component(op.KIND_MN, (1e10, 2.5, 0.9)),
+                          op.Component(op.KIND_PLC, (5e9, 1.8, 1.9)), op.Component(op.KIND_NFW, (6e11, 18.0)),
+                          op.Component(op.KIND_HERNQUIST, (4e6, 0.0))))
+    for pot, opot in ((one_disk, o_one), (two_disks, o_two)):
+        q0, p0 = synthetic_ics(opot, 300, seed=71)
+        ts = np.linspace(0.0, 300.0, 4)
+        sol = SIE.solve(pot, (q0, p0), 0.0, 300.0, dt0=0.1, saveat=ts)
+        gen = gd._integrate(pot, q0, p0, 0.0, 300.0, ts, solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(),
+                            dt0=0.1, max_steps=None, general_kernel=True)
+        assert np.array_equal(gen[0], sol.ys[0]) and np.array_equal(gen[1], sol.ys[1])
+        qr, pr, st, n = cref.integrate_fixed(opot, q0, p0, 0.0, 300.0, 0.1, ts)
+        e = rel_dev(sol.ys, (qr, pr))
+        assert np.median(e) < 1e-13 and np.mean(e <= 1e-12) > 0.97, (np.median(e), np.mean(e <= 1e-12))
+        ad = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=1e-10, atol=1e-10)).solve(pot, (q0, p0), 0.0, 300.0, saveat=ts)
+        qd, pd, *_ = cref.integrate_dopri8(opot, q0, p0, 0.0, 300.0, ts, rtol=1e-10, atol=1e-10)
+        assert np.median(np.abs(ad.ys[0] - qd).max(axis=(1, 2))) < 1e-9

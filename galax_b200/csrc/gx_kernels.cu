@@ -1037,6 +1037,9 @@ __device__ __forceinline__ void accel(const DevPot &P, double x, double y, doubl
 //                outside the launch.  Used whenever the image is busy with another potential on another stream, and
 //                always under CUDA-graph capture.
 __constant__ DevPot c_pot_dp8;
+// (IMG = false kernels hold the potential AND the force table in static shared memory, which stops at 48 KB)
+static_assert(sizeof(DevPot) + sizeof(double) * SPH_NINT * SPH_ROW <= 48 * 1024,
+              "DevPot + the combined spherical table no longer fit the 48 KB of static shared memory");
 template <class C>
 __device__ __forceinline__ DevPot *pot_smem() {
     __shared__ DevPot sP;

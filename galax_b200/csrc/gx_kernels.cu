@@ -1125,6 +1125,9 @@ constexpr int REC_DOUBLES = GX_DENSE_RECORD_DOUBLES;  // tprev, tnext, hd, q0[3]
 #ifndef GX_DENSE_COEF
 #define GX_DENSE_COEF 0
 #endif
+#ifndef GX_DP8_PIPELINE
+#define GX_DP8_PIPELINE 1
+#endif
 template <class C, class TB, bool IMG, bool EPI = false>
 __global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
 k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
@@ -1230,6 +1233,38 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         if (run) {
         // ---------------- one attempted step of size h from (tprev, y0)
         double sx = 0, sy = 0, sz = 0;
+#if GX_DP8_PIPELINE
+        // Software-pipelined across the out-of-line call: the part of stage i+1's sum that does not need a_i is formed
+        // BEFORE the call that computes a_i (ptxas does not move work across a call), so it runs in the shadow of the
+        // callee's first instructions and only one FMA per component is left between two calls.
+        double nx = 0, ny = 0, nz = 0;  // sum_{l < i-1} AA(i, l) a_l for the coming stage i
+#pragma unroll
+        for (int i = 1; i < NS; ++i) {
+            sx = nx; sy = ny; sz = nz;
+            if (i >= 1 && TB::AA_NZ(i, i - 1)) {
+                sx = fma(TB::AA(i, i - 1), AX(i - 1), sx);
+                sy = fma(TB::AA(i, i - 1), AY(i - 1), sy);
+                sz = fma(TB::AA(i, i - 1), AZ(i - 1), sz);
+            }
+            const double ch = TB::CN(i) * hd;
+            const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
+            const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
+            const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
+            nx = 0; ny = 0; nz = 0;
+            if (i + 1 < NS) {
+#pragma unroll
+                for (int l = 0; l < i; ++l) {
+                    if (TB::AA_NZ(i + 1, l)) {
+                        nx = fma(TB::AA(i + 1, l), AX(l), nx);
+                        ny = fma(TB::AA(i + 1, l), AY(l), ny);
+                        nz = fma(TB::AA(i + 1, l), AZ(l), nz);
+                    }
+                }
+            }
+            { double t0_, t1_, t2_; accel_call<C, IMG>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
+            if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1
+        }
+#else
 #pragma unroll
         for (int i = 1; i < NS; ++i) {
             // q_i = q0 + CN[i] hd p0 + hd^2 sum_{l<i} TB::AA(i, l) a_l
@@ -1249,6 +1284,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
             { double t0_, t1_, t2_; accel_call<C, IMG>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
             if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1
         }
+#endif
         q1x = sx; q1y = sy; q1z = sz;
         double bx = 0, by = 0, bz = 0, epx = 0, epy = 0, epz = 0, eqx = 0, eqy = 0, eqz = 0;
 #pragma unroll

@@ -1237,29 +1237,31 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         // Software-pipelined across the out-of-line call: the part of stage i+1's sum that does not need a_i is formed
         // BEFORE the call that computes a_i (ptxas does not move work across a call), so it runs in the shadow of the
         // callee's first instructions and only one FMA per component is left between two calls.
-        double nx = 0, ny = 0, nz = 0;  // sum_{l < i-1} AA(i, l) a_l for the coming stage i
+        // (n = q0 + CN[i] hd p0 + hd^2 sum_{l < i-1} AA(i, l) a_l: everything of the coming stage point but a_{i-1}'s term)
+        double nx = fma(TB::CN(1) * hd, p0x, q0x), ny = fma(TB::CN(1) * hd, p0y, q0y), nz = fma(TB::CN(1) * hd, p0z, q0z);
 #pragma unroll
         for (int i = 1; i < NS; ++i) {
-            sx = nx; sy = ny; sz = nz;
-            if (i >= 1 && TB::AA_NZ(i, i - 1)) {
-                sx = fma(TB::AA(i, i - 1), AX(i - 1), sx);
-                sy = fma(TB::AA(i, i - 1), AY(i - 1), sy);
-                sz = fma(TB::AA(i, i - 1), AZ(i - 1), sz);
+            double xi = nx, yi = ny, zi = nz;
+            if (TB::AA_NZ(i, i - 1)) {
+                const double c = hd2 * TB::AA(i, i - 1);
+                xi = fma(c, AX(i - 1), xi);
+                yi = fma(c, AY(i - 1), yi);
+                zi = fma(c, AZ(i - 1), zi);
             }
-            const double ch = TB::CN(i) * hd;
-            const double xi = fma(hd2, sx, fma(ch, p0x, q0x));
-            const double yi = fma(hd2, sy, fma(ch, p0y, q0y));
-            const double zi = fma(hd2, sz, fma(ch, p0z, q0z));
-            nx = 0; ny = 0; nz = 0;
             if (i + 1 < NS) {
+                double tx = 0, ty = 0, tz = 0;
 #pragma unroll
                 for (int l = 0; l < i; ++l) {
                     if (TB::AA_NZ(i + 1, l)) {
-                        nx = fma(TB::AA(i + 1, l), AX(l), nx);
-                        ny = fma(TB::AA(i + 1, l), AY(l), ny);
-                        nz = fma(TB::AA(i + 1, l), AZ(l), nz);
+                        tx = fma(TB::AA(i + 1, l), AX(l), tx);
+                        ty = fma(TB::AA(i + 1, l), AY(l), ty);
+                        tz = fma(TB::AA(i + 1, l), AZ(l), tz);
                     }
                 }
+                const double chn = TB::CN(i + 1) * hd;
+                nx = fma(hd2, tx, fma(chn, p0x, q0x));
+                ny = fma(hd2, ty, fma(chn, p0y, q0y));
+                nz = fma(hd2, tz, fma(chn, p0z, q0z));
             }
             { double t0_, t1_, t2_; accel_call<C, IMG>(xi, yi, zi, t0_, t1_, t2_, fma(TB::CN(i), hd, dir * tprev)); AX(i) = t0_; AY(i) = t1_; AZ(i) = t2_; }
             if (i == NS - 1) { sx = xi; sy = yi; sz = zi; }  // FSAL: the last stage sits at q1

@@ -78,6 +78,46 @@ static ffi::Error IntegrateDopri8Impl(cudaStream_t stream, ffi::Buffer<ffi::F64>
                                       workspace->typed_data(), stream));
 }
 
+// The reference's joint batch semantics (one shared adaptive step for the whole (N, 3) batch): what galax's
+// evaluate_orbit / OrbitSolver.solve compute for scalar times, hence the handler a jit-compiled galax would call.
+static ffi::Error IntegrateJointImpl(cudaStream_t stream, ffi::Buffer<ffi::F64> q0, ffi::Buffer<ffi::F64> p0,
+                                     ffi::Buffer<ffi::F64> ts, ffi::Span<const uint8_t> pot_b,
+                                     ffi::Span<const uint8_t> pid_b, double t0, double t1, int64_t max_steps,
+                                     ffi::ResultBuffer<ffi::F64> q, ffi::ResultBuffer<ffi::F64> p,
+                                     ffi::ResultBuffer<ffi::S32> status, ffi::ResultBuffer<ffi::S32> n_acc,
+                                     ffi::ResultBuffer<ffi::S32> n_att, ffi::ResultBuffer<ffi::F64> workspace) {
+    gx_potential pot;
+    if (auto e = PotFromBytes(pot_b, &pot); e.failure()) return e;
+    if (pid_b.size() != sizeof(gx_pid)) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "bad pid attribute");
+    gx_pid pid;
+    std::memcpy(&pid, pid_b.begin(), sizeof pid);
+    int64_t n = q0.element_count() / 3;
+    if ((int64_t)workspace->element_count() * 8 < gx_joint_workspace_bytes(n))
+        return ffi::Error(ffi::ErrorCode::kInvalidArgument, "workspace smaller than gx_joint_workspace_bytes(N)");
+    return FromRc(gx_integrate_adaptive_joint(GX_SOLVER_DOPRI8, &pot, &pid, q0.typed_data(), p0.typed_data(), n, t0, t1,
+                                              ts.typed_data(), (int32_t)ts.element_count(), max_steps, GX_LAYOUT_NT3,
+                                              q->typed_data(), p->typed_data(), status->typed_data(), n_acc->typed_data(),
+                                              n_att->typed_data(), workspace->typed_data(), stream));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(GxIntegrateJoint, IntegrateJointImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Attr<ffi::Span<const uint8_t>>("pot")
+                                  .Attr<ffi::Span<const uint8_t>>("pid")
+                                  .Attr<double>("t0")
+                                  .Attr<double>("t1")
+                                  .Attr<int64_t>("max_steps")
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>());
+
 XLA_FFI_DEFINE_HANDLER_SYMBOL(GxPotentialEval, PotentialEvalImpl,
                               ffi::Ffi::Bind()
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()

@@ -290,7 +290,9 @@ def _period_order(q, p, t0v, t1, torch):
 # the host->device copy of slice k+1 and the device->host copy of slice k-1 overlap the kernel of slice k (particles
 # are independent; the kernels of neighbouring slices also fill each other's tail waves).  Same numbers as one launch.
 PIPELINE_MIN_PARTICLES = 1 << 19
-PIPELINE_CHUNKS = 4
+PIPELINE_CHUNKS = 4  # at least; up to PIPELINE_MAX_CHUNKS slices of ~PIPELINE_CHUNK_PARTICLES (1.2e6 particles: 8 slices, +1.2 %)
+PIPELINE_MAX_CHUNKS = 8
+PIPELINE_CHUNK_PARTICLES = 150_000
 PIPELINE_MAX_OUTPUT_BYTES = 8 << 30
 
 
@@ -357,8 +359,9 @@ def _integrate_pipelined(pot, q0, p0, t0, t1, ts, *, solver, controller, dt0, ma
     dev = torch.device("cuda", torch.cuda.current_device())
     cur = torch.cuda.current_stream(dev)
     streams = _pipeline_streams(torch, dev)
-    bounds = [(N * k) // PIPELINE_CHUNKS for k in range(PIPELINE_CHUNKS + 1)]
-    for k in range(PIPELINE_CHUNKS):
+    chunks = max(PIPELINE_CHUNKS, min(PIPELINE_MAX_CHUNKS, N // PIPELINE_CHUNK_PARTICLES))
+    bounds = [(N * k) // chunks for k in range(chunks + 1)]
+    for k in range(chunks):
         a, b = bounds[k], bounds[k + 1]
         s = streams[k % 2]
         s.wait_stream(cur)

@@ -51,8 +51,11 @@ enum TdMode { TD_REJECT = 0, TD_FREEZE = 1, TD_INTEGRATE = 2 };
 
 // may_upload = false (the caller's stream is being captured into a graph): a combined spherical table that is not in the
 // cache yet is not fitted and uploaded now -- the composite then runs through the runtime-count kernels.
+// tabs: which formats of the combined spherical table the caller's kernels look up (TAB_NARROW: Dopri kernels, TAB_WIDE:
+// fixed-step kernels); each is fitted and uploaded on first use only by the entries that need it.
+enum { TAB_NONE = 0, TAB_NARROW = 1, TAB_WIDE = 2 };
 static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, bool use_device = true,
-                        TdMode td_mode = TD_REJECT, double t_freeze = 0.0, bool may_upload = true) {
+                        TdMode td_mode = TD_REJECT, double t_freeze = 0.0, bool may_upload = true, int tabs = TAB_NONE) {
     if (!pot_in || pot_in->n < 0 || pot_in->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
     memset(&D, 0, sizeof D);
     gx_potential frozen = *pot_in;
@@ -214,16 +217,19 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
         // the composite's combined spherical table S(r^2) (fitted and uploaded on first use of these parameters): the
         // three named models need it (else they run as runtime composites); any other composite of the four basic
         // kinds takes it when it has spherical components (CountsBasicTab), and runs without it otherwise
-        if (use_device && (model != MODEL_GENERIC || D.n_hern + D.n_nfw + D.n_plc > 0)) {
+        if (use_device && tabs != TAB_NONE && (model != MODEL_GENERIC || D.n_hern + D.n_nfw + D.n_plc > 0)) {
             std::vector<SphComp> cs;
             for (int i = 0; i < pot->n; ++i) {
                 const gx_component &c = pot->c[i];
                 if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, G * c.p[0], c.p[1], 0.0});
                 if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
             }
-            D.sph_tab = sph_table_for(cs, nullptr, may_upload);
-            D.sph_j0 = (unsigned)((1023 + sph_e_lo(cs)) << SPH_SUB_BITS);
-            if (D.sph_tab == nullptr) model = MODEL_GENERIC;
+            const int e_lo = sph_e_lo(cs);
+            D.sph_j0 = (unsigned)((1023 + e_lo) << SPH_SUB_BITS);
+            D.sph_j0w = (unsigned)((1023 + e_lo) << SPHW_SUB_BITS);
+            if (tabs & TAB_NARROW) D.sph_tab = sph_table_for(cs, nullptr, may_upload);
+            if (tabs & TAB_WIDE) D.sph_wide = sph_wide_table_for(cs, nullptr, may_upload);
+            if (((tabs & TAB_NARROW) && D.sph_tab == nullptr) || ((tabs & TAB_WIDE) && D.sph_wide == nullptr)) model = MODEL_GENERIC;
         }
 #endif
     }
@@ -427,19 +433,17 @@ constexpr int SAVE_SLOTS = 4;  // saves per run (the last one of a run is writte
 constexpr int SAVE_STAGE_MIN_T = 4;
 // Nothing but the save index k is carried between saves: the sector phase of save k is (T i + k) mod 4, the number of
 // staged saves is that phase (or k itself inside the row's first, shorter run).
-__device__ __forceinline__ double *save_buf() {
-    extern __shared__ __align__(16) double gx_save_buf[];
-    return gx_save_buf;
-}
+// (dynamic shared memory: the wide force table of the fixed-step kernels first, `off` doubles of it, then the staging)
+__device__ __forceinline__ double *save_buf(int off) { return dyn_smem() + off; }
 template <class A>
 __device__ __forceinline__ int save_staged(const A &a, long long i, int k) {  // saves staged before save k
     const int ph = (int)(((unsigned)a.T * (unsigned)i + (unsigned)k) & 3u);
     return ph < k ? ph : k;
 }
 // (a rolled loop: the integrators' register allocation should not pay for this cold path)
-__device__ __forceinline__ void save_flush_n(double *qd, double *pd, int n, int nv) {
+__device__ __forceinline__ void save_flush_n(double *qd, double *pd, int n, int nv, int off) {
     const int bd = blockDim.x;
-    const double *b = save_buf() + threadIdx.x;
+    const double *b = save_buf(off) + threadIdx.x;
 #pragma unroll 1
     for (int s = 0; s < n; ++s, b += nv * bd, qd += 3, pd += 3) {
         qd[0] = b[0]; qd[1] = b[bd]; qd[2] = b[2 * bd];
@@ -450,7 +454,7 @@ template <class A>
 __device__ __forceinline__ void save_flush(const A &a, long long i, int kend) {  // write out what is staged before kend
     if (!a.stage) return;
     const int n = save_staged(a, i, kend);
-    if (n > 0) save_flush_n(a.q + i * a.sn + 3LL * (kend - n), a.p + i * a.sn + 3LL * (kend - n), n, a.epi.nv);
+    if (n > 0) save_flush_n(a.q + i * a.sn + 3LL * (kend - n), a.p + i * a.sn + 3LL * (kend - n), n, a.epi.nv, a.stage_off);
 }
 // Where save k of particle i goes: component c of q at q[c * st], of p at p[c * st] -- the output itself (direct
 // stores, or the save that closes a run) or the lane's staging column.  The caller stores the six values as it
@@ -466,7 +470,7 @@ __device__ __forceinline__ SaveDst save_dst(const A &a, long long i, int k) {
         d.q = a.q + i * a.sn + k * a.sk; d.p = a.p + i * a.sn + k * a.sk; d.st = a.sc;
     } else if ((((unsigned)a.T * (unsigned)i + (unsigned)k + 1u) & 3u) != 0u) {  // not at a sector boundary: stage
         const int bd = blockDim.x;
-        d.q = save_buf() + threadIdx.x + (a.epi.nv * save_staged(a, i, k)) * bd; d.p = d.q + 3 * bd; d.st = bd;
+        d.q = save_buf(a.stage_off) + threadIdx.x + (a.epi.nv * save_staged(a, i, k)) * bd; d.p = d.q + 3 * bd; d.st = bd;
     } else {  // save k ends on a sector boundary: it goes straight out, behind the staged ones (save_commit)
         d.q = a.q + i * a.sn + 3LL * k; d.p = a.p + i * a.sn + 3LL * k; d.st = 1;
     }
@@ -529,7 +533,7 @@ __device__ __forceinline__ void epilogue_flush(const A &a, long long i, int kend
     const int n = save_staged(a, i, kend);
     const EpiOut &e = a.epi;
     const int bd = blockDim.x;
-    const double *b = save_buf() + threadIdx.x + 6 * bd;
+    const double *b = save_buf(a.stage_off) + threadIdx.x + 6 * bd;
     long long r = i * a.T + (kend - n);
 #pragma unroll 1
     for (int s = 0; s < n; ++s, b += e.nv * bd, ++r) {
@@ -570,7 +574,7 @@ __device__ __noinline__ void epilogue_put(const DevPot *Pp, const A *ap, long lo
     }
     if (a.stage && (((unsigned)a.T * (unsigned)i + (unsigned)k + 1u) & 3u) != 0u) {  // inside a run: stage
         const int bd = blockDim.x;
-        double *b = save_buf() + threadIdx.x + (e.nv * save_staged(a, i, k) + 6) * bd;
+        double *b = save_buf(a.stage_off) + threadIdx.x + (e.nv * save_staged(a, i, k) + 6) * bd;
         b[0] = v[0]; b[bd] = v[1]; b[2 * bd] = v[2]; b[3 * bd] = v[3];
         if (e.TT) {
 #pragma unroll
@@ -623,6 +627,7 @@ struct FixedArgs {
     double t0, t1, dt0;
     int T, hit_max_steps;
     int stage;  // saves go through the per-lane staging buffer (save_put)
+    int stage_off;  // ... which starts this many doubles into dynamic shared memory (behind the wide force table)
     EpiOut epi;  // fused E / L / tidal-tensor outputs (EPI kernels); epi.nv = 6 otherwise
 };
 
@@ -722,17 +727,21 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #ifndef GX_SPH_FIXED_FORM
 #define GX_SPH_FIXED_FORM 1
 #endif
+// CTAs of the kernels that hold the wide table (132 KB: one per SM) are as wide as the batch needs, up to 640 threads
+// (384 with the save epilogue: its staging needs the room, and its kernels the registers)
+template <class C, bool EPI = false>
+__host__ __device__ constexpr int fixed_max_block() { return (sph_tab_fixed_ok<C>() || sph_mix_ok<C>()) ? (EPI ? 384 : 640) : 128; }
 template <class C, int SCHEME, bool FWD, bool EPI = false, bool SMALL = false>
-__global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
+__global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy; every static model in small
     // batches, see k_integrate_fixed_seg), else the PowerLawCutoff / NFW tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? GX_SPH_FIXED_FORM : 0);
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 3 : 0;  // 3: the wide format, at the start of dynamic shared memory
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     constexpr bool MIX = sph_mix_ok<C>() && !SMALL && SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER;  // (see k_integrate_fixed_seg)
     unsigned plc_base = 0, nfw_base = 0;
     if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
-    if constexpr (SPHT != 0 || MIX) nfw_base = sph_stage<C, (SPHT != 0 || MIX)>(P);
+    if constexpr (SPHT != 0 || MIX) nfw_base = sph_wide_stage(P);
     else nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
@@ -762,7 +771,7 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, GX_SPH_FIXED_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, 3>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                 else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
@@ -833,12 +842,12 @@ __global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS) k_integrate_fixed(co
 // spherical table for every static model, in its 4-deep Estrin form -- q -> r^2 -> lookup -> p instead of
 // q -> r^2 -> rsqrt -> r -> s -> 1 + s -> rcp -> table log -> shape -> 1/r^3 -> p.
 template <class C, bool FWD, bool SMALL = false, bool EPI = false>
-__global__ void __launch_bounds__(128, GX_FIXED_MIN_BLOCKS)
+__global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS)
 k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
     // tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = (SMALL && sph_tab_ok<C>()) ? 2 : (sph_tab_fixed_ok<C>() ? GX_SPH_FIXED_FORM : 0);
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 3 : 0;  // 3: the wide format, at the start of dynamic shared memory
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     // MIX (MilkyWayPotential in large batches): the closed forms cost issue slots (169 per warp-step, the kernel's whole
@@ -849,7 +858,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     constexpr bool MIX = sph_mix_ok<C>() && !SMALL;
     unsigned plc_base = 0, nfw_base = 0;
     if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
-    if constexpr (SPHT != 0 || MIX) nfw_base = sph_stage<C, (SPHT != 0 || MIX)>(P);
+    if constexpr (SPHT != 0 || MIX) nfw_base = sph_wide_stage(P);
     else nfw_base = nfw_stage<C, NFWT>(P);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
@@ -899,7 +908,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qz = fma(pz, hs, qz);
                     if constexpr (C::is_static) {
                         double fh, fv;
-                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_SPH_FIXED_FORM>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
+                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 3>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
                         else gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
                         if constexpr (MIX) ++gstep;
                         const double fhh = -fh * hs, fvh = -fv * hs;
@@ -925,7 +934,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 double npx, npy, npz;
                 if constexpr (C::is_static) {
                     double fh, fv;
-                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_SPH_FIXED_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 3>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                     else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                     if constexpr (MIX) ++gstep;
                     const double fhh = -fh * hs, fvh = -fv * hs;
@@ -977,6 +986,7 @@ struct Dp8Args {
     double rtol, atol, pcoeff, icoeff, dcoeff, safety, factormin, factormax, dtmin, dtmax, dt0;
     int T;
     int stage;  // saves go through the per-lane staging buffer (save_put)
+    int stage_off;  // ... which starts this many doubles into dynamic shared memory (behind the wide force table)
     EpiOut epi;  // fused E / L / tidal-tensor outputs (EPI kernels); epi.nv = 6 otherwise
 };
 
@@ -2133,7 +2143,7 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
 #undef GX_SEG_STATIC
         default:  // runtime composite, no time-dependent parameter
             if (is_basic_composite(D, model)) {
-                if (D.sph_tab) {  // spherical components in the combined table
+                if (D.sph_wide) {  // spherical components in the combined table
                     if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasicTab, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
                     else launch_dyn<k_integrate_fixed_seg<CountsBasicTab, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
                 } else {
@@ -2170,7 +2180,7 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
     case MODEL_MW2022: GX_GEN_STATIC(CountsMW2022); break;
     case MODEL_BOVY: GX_GEN_STATIC(CountsBovy); break;
     default:
-        if (is_basic_composite(D, model) && D.sph_tab) {  // (the same arithmetic as the run-length kernel's)
+        if (is_basic_composite(D, model) && D.sph_wide) {  // (the same arithmetic as the run-length kernel's)
             if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) GX_GEN(CountsBasicTab, GX_SCHEME_SEMI_IMPLICIT_EULER, false);
             else GX_GEN(CountsBasicTab, GX_SCHEME_LEAPFROG_MIDPOINT, false);
         } else if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) GX_GEN(CountsRuntime, GX_SCHEME_SEMI_IMPLICIT_EULER, false);
@@ -2185,7 +2195,7 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
                       double dt0, const double *ts, int32_t T, int32_t scheme, int64_t max_steps, int32_t layout,
                       double *q, double *p, int32_t *status, const gx_orbit_epilogue *epi, void *stream) {
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE, 0.0, !stream_is_capturing(stream));
+    int rc = build_devpot(pot, D, model, true, TD_INTEGRATE, 0.0, !stream_is_capturing(stream), TAB_WIDE);
     if (rc) return rc;
     if (N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p))) return GX_ERR_BADARG;
     const bool general_kernel = (scheme & GX_SCHEME_GENERAL_KERNEL) != 0;
@@ -2209,17 +2219,37 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
     a.N = N; a.t0 = t0; a.t1 = t1; a.dt0 = dt0; a.T = T;
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
     walk_time_grid(t0, t1, dt0, max_steps, sg, seg_ok, a.n_steps, a.hit_max_steps);
-    // small batches: narrow CTAs so the particles spread over all 148 SMs x 4 schedulers.  The static models stage their
-    // 44 KB force table per CTA, so five CTAs are resident per SM whatever their width: the narrowest CTA that still
-    // puts the whole batch on the machine in one wave (a second wave of narrow CTAs cost 60 000 particles 50 %)
-    const bool tabled = GX_SPH_TABLE && (model != MODEL_GENERIC || (is_basic_composite(D, model) && D.sph_tab));
-    const int block = tabled ? ((N > 148LL * 5 * 64) ? 128 : ((N > 148LL * 5 * 32) ? 64 : 32))
-                             : ((N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32));
+    // CTA width.  Kernels without a table: narrow CTAs for small batches, so that the particles spread over all SMs and
+    // schedulers.  Kernels that hold the 132 KB wide table: ONE CTA per SM, as wide as the batch needs (a multiple of 32
+    // between 128 and what the staging of the saves leaves room for, at most 640) -- 10^4 particles are 79 CTAs of four
+    // warps, one per scheduler; 1.2e6 particles are 640-thread CTAs in waves of 148.
+    const bool tabled = GX_SPH_TABLE && (model != MODEL_GENERIC || (is_basic_composite(D, model) && D.sph_wide));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int block;
+    size_t dyn;
+    a.stage_off = 0;
+    if (tabled) {
+        const size_t per_thread = save_stage_bytes(layout, T, 1, a.epi.nv);  // staging bytes per lane (0: direct stores)
+        const size_t room = (size_t)226 * 1024 - SPHW_BYTES;
+        int maxb = per_thread ? (int)((room / per_thread) / 32 * 32) : 640;
+        if (maxb > (with_epi ? 384 : 640)) maxb = with_epi ? 384 : 640;
+        if (maxb < 32) return GX_ERR_UNSUPPORTED;
+        long long want = ((N + sms - 1) / sms + 31) / 32 * 32;
+        block = (int)(want < 128 ? 128 : (want > maxb ? maxb : want));
+        if (block > maxb) block = maxb;
+        dyn = SPHW_BYTES + (size_t)block * per_thread;
+        a.stage = per_thread != 0;
+        a.stage_off = SPHW_BYTES / 8;
+    } else {
+        block = (N >= 148LL * 128 * 4) ? 128 : ((N >= 148LL * 64 * 2) ? 64 : 32);
+        dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
+        a.stage = dyn != 0;
+    }
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
     const bool fwd = dir > 0;
-    const size_t dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
-    a.stage = dyn != 0;
     // latency-bound launches (fewer than 4 warps per scheduler): the table / Estrin variant of the static models
     const bool small = GX_SPH_TABLE && GX_FIXED_SMALL && block < 128;
     if (with_epi) launch_fixed<true>(model, D, seg_ok, small, scheme, fwd, grid, block, dyn, s, a, sg);
@@ -2324,7 +2354,7 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     solver &= ~GX_SOLVER_STRICT;
     if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE, 0.0, !stream_is_capturing(stream));
+    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE, 0.0, !stream_is_capturing(stream), TAB_NARROW);
     if (rc) return rc;
     if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
         return GX_ERR_BADARG;
@@ -2359,6 +2389,7 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
     const size_t dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
     a.stage = dyn != 0;
+    a.stage_off = 0;
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2735,6 +2766,29 @@ int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capa
     std::vector<double> tmp;
     if (!coef) { tmp.resize((size_t)SPH_NINT * SPH_ROW); coef = tmp.data(); }
     const double worst = sph_table_fit(cs, coef);
+    if (max_rel_err) *max_rel_err = worst;
+    return 0;
+}
+
+int gx_spherical_force_table_wide(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
+                                  int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err) {
+    if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
+    std::vector<SphComp> cs;
+    for (int i = 0; i < pot->n; ++i) {
+        const gx_component &c = pot->c[i];
+        if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, pot->G * c.p[0], c.p[1], 0.0});
+        if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, pot->G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
+    }
+    if (cs.empty()) return GX_ERR_UNSUPPORTED;
+    if (n_intervals) *n_intervals = SPHW_NINT;
+    if (degree) *degree = SPHW_DEG;
+    if (e_lo) *e_lo = sph_e_lo(cs);
+    if (sub_bits) *sub_bits = SPHW_SUB_BITS;
+    if (!coef && !max_rel_err) return 0;
+    if (coef && capacity < (int64_t)SPHW_NINT * SPHW_ROW) return GX_ERR_BADARG;
+    std::vector<double> tmp;
+    if (!coef) { tmp.resize((size_t)SPHW_NINT * SPHW_ROW); coef = tmp.data(); }
+    const double worst = sph_table_fit<SPHW_SUB_BITS, SPHW_ROW>(cs, coef);
     if (max_rel_err) *max_rel_err = worst;
     return 0;
 }

@@ -43,7 +43,7 @@ static long double plc_P_ld(long double a, long double x) {
 static long double plc_G_ld(long double a, long double s) { return plc_P_ld(a, s * s) / (s * s * s); }
 
 // Chebyshev interpolation on [-1, 1] at PLC_DEG+1 nodes, converted to monomial coefficients in long double.
-template <int n = PLC_DEG + 1, class F>
+template <int n = PLC_DEG + 1, int NCHECK = 40, class F>
 static void fit_interval(const F &fun, long double s0, long double s1, double *coef, double *max_rel_err) {
     const long double PI = 3.141592653589793238462643383279502884L;
     long double f[n], c[n];
@@ -72,8 +72,8 @@ static void fit_interval(const F &fun, long double s0, long double s1, double *c
     for (int i = 0; i < n; ++i) coef[i] = (double)mono[i];
     // verify in double Horner (what the device does) on a fine grid
     double worst = 0.0;
-    for (int k = 0; k <= 40; ++k) {
-        double t = -1.0 + 2.0 * k / 40.0;
+    for (int k = 0; k <= NCHECK; ++k) {
+        double t = -1.0 + 2.0 * k / (double)NCHECK;
         double v = coef[n - 1];
         for (int i = n - 2; i >= 0; --i) v = fma(v, t, coef[i]);
         long double s = 0.5L * (s0 + s1) + 0.5L * (s1 - s0) * (long double)t;
@@ -214,14 +214,17 @@ static int sph_e_lo(const std::vector<SphComp> &cs) {
 // Fit of the table (host only; also used by gx_spherical_force_table): coef[SPH_NINT][SPH_ROW] in natural order,
 // returns the worst relative error of the fp64 Horner evaluation against the long-double function on a 41-point grid
 // per interval.
+template <int SUB_BITS = SPH_SUB_BITS, int ROW = SPH_ROW>
 static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
     double worst = 0.0;
     const int e_lo = sph_e_lo(cs);
-    for (int j = 0; j < SPH_NINT; ++j) {
-        const int e = e_lo + (j >> SPH_SUB_BITS), sub = j & ((1 << SPH_SUB_BITS) - 1);
-        const long double base = ldexpl(1.0L, e), nsub = (long double)(1 << SPH_SUB_BITS);
-        fit_interval<SPH_ROW>([&cs](long double u) { return sph_S_ld(cs, u); }, base * (1.0L + sub / nsub),
-                              base * (1.0L + (sub + 1) / nsub), coef + (size_t)j * SPH_ROW, &worst);
+    const int nint = SPH_OCTAVES << SUB_BITS;
+    for (int j = 0; j < nint; ++j) {
+        const int e = e_lo + (j >> SUB_BITS), sub = j & ((1 << SUB_BITS) - 1);
+        const long double base = ldexpl(1.0L, e), nsub = (long double)(1 << SUB_BITS);
+        // (the narrow intervals of the wide format are checked on a coarser grid: 4x as many of them)
+        fit_interval<ROW, (SUB_BITS >= 7 ? 10 : 40)>([&cs](long double u) { return sph_S_ld(cs, u); }, base * (1.0L + sub / nsub),
+                          base * (1.0L + (sub + 1) / nsub), coef + (size_t)j * ROW, &worst);
     }
     return worst;
 }
@@ -277,6 +280,49 @@ static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_r
             }
         if (cudaMalloc(&d, sw.size() * sizeof(double)) != cudaSuccess) return nullptr;  // (not cached: may succeed later)
         if (cudaMemcpy(d, sw.data(), sw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(d);
+            return nullptr;
+        }
+    }
+    cache.push_back({dev, cs, d, worst});
+    fits.push_back(std::move(host));
+    if (max_rel_err_out) *max_rel_err_out = worst;
+    return d;
+}
+
+// The WIDE format of the same table (SPHW_*: fixed-step kernels), cached the same way; plain row order.
+static const double *sph_wide_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr, bool may_upload = true) {
+    struct Entry { int device; std::vector<SphComp> cs; double *dev_ptr; double max_rel_err; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    static std::vector<std::vector<double>> fits;
+    int dev = 0;
+    if (cs.empty() || cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    const std::vector<double> *fitted = nullptr;
+    for (size_t k = 0; k < cache.size(); ++k) {
+        const Entry &e = cache[k];
+        if (sph_same(e.cs, cs)) {
+            if (e.device == dev) {
+                if (max_rel_err_out) *max_rel_err_out = e.max_rel_err;
+                return e.dev_ptr;
+            }
+            fitted = &fits[k];
+        }
+    }
+    if (cache.size() >= SPH_CACHE_MAX || !may_upload) return nullptr;
+    std::vector<double> host;
+    double worst = 0.0;
+    if (fitted) {
+        host = *fitted;
+    } else {
+        host.resize((size_t)SPHW_NINT * SPHW_ROW);
+        worst = sph_table_fit<SPHW_SUB_BITS, SPHW_ROW>(cs, host.data());
+    }
+    double *d = nullptr;
+    if (worst < 1e-14) {
+        if (cudaMalloc(&d, host.size() * sizeof(double)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaFree(d);
             return nullptr;
         }

@@ -69,13 +69,14 @@ def test_bad_arguments():
 
 
 # ---- the combined spherical table S(r^2) of a composite (gx_spherical_force_table) ------------------------------
-def sph_table(pot):
+def sph_table(pot, wide=False):
     L = _lib.lib()
+    fn = L.gx_spherical_force_table_wide if wide else L.gx_spherical_force_table
     cs = pot.c_struct()
     n, deg, lo, sb, err = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
-    assert L.gx_spherical_force_table(C.byref(cs), None, 0, C.byref(n), C.byref(deg), C.byref(lo), C.byref(sb), None) == 0
+    assert fn(C.byref(cs), None, 0, C.byref(n), C.byref(deg), C.byref(lo), C.byref(sb), None) == 0
     coef = np.empty((n.value, deg.value + 1))
-    assert L.gx_spherical_force_table(C.byref(cs), coef.ctypes.data, coef.size, None, None, None, None, C.byref(err)) == 0
+    assert fn(C.byref(cs), coef.ctypes.data, coef.size, None, None, None, None, C.byref(err)) == 0
     return coef, lo.value, sb.value, err.value
 
 
@@ -133,6 +134,22 @@ def test_combined_spherical_table_on_the_host(name):
     for ev in (evaluate, evaluate_estrin):
         S = ev(coef, e_lo, sb, u)
         assert np.abs(S / ref - 1).max() < 8e-16, ev.__name__
+
+
+@pytest.mark.parametrize("name", ["MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014"])
+def test_wide_format_of_the_combined_table_on_the_host(name):
+    """What the fixed-step kernels look up: 128 intervals per octave, degree 5, 48-byte rows."""
+    import galax_b200.potential as gp
+
+    pot = getattr(gp, name)()
+    coef, e_lo, sb, err = sph_table(pot, wide=True)
+    assert coef.shape == (2816, 6) and e_lo == -8 and sb == 7 and err < 4e-16
+    rng = np.random.default_rng(7)
+    edges = np.ldexp(1.0 + np.arange(0, 128, 5) / 128.0, rng.integers(-8, 14, 26))
+    below = np.nextafter(edges, 0)
+    u = np.concatenate([2.0 ** rng.uniform(-8, 14, 300), edges, below[below >= 2.0**-8], [2.0**-8, np.nextafter(2.0**14, 0)]])
+    ref = sph_reference(pot, [mp.sqrt(mp.mpf(float(x))) for x in u])
+    assert np.abs(evaluate(coef, e_lo, sb, u) / ref - 1).max() < 8e-16
 
 
 def test_combined_spherical_table_follows_the_scale_radii():

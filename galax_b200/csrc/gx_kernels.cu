@@ -1047,9 +1047,7 @@ __device__ __forceinline__ void accel(const DevPot &P, double x, double y, doubl
 //                outside the launch.  Used whenever the image is busy with another potential on another stream, and
 //                always under CUDA-graph capture.
 __constant__ DevPot c_pot_dp8;
-// (IMG = false kernels hold the potential AND the force table in static shared memory, which stops at 48 KB)
-static_assert(sizeof(DevPot) + sizeof(double) * SPH_NINT * SPH_ROW <= 48 * 1024,
-              "DevPot + the combined spherical table no longer fit the 48 KB of static shared memory");
+// (IMG = false kernels keep their copy of the potential in static shared memory; the force table is in dynamic memory)
 template <class C>
 __device__ __forceinline__ DevPot *pot_smem() {
     __shared__ DevPot sP;
@@ -1069,8 +1067,8 @@ __device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
     // + MOV per call -- was measured: the extra live register costs the Dopri8 kernel 40 bytes of spills)
     double g0, g1, g2;
     unsigned tab_base = 0;  // the kernel prologue staged the force table (sph_stage / nfw_stage)
-    constexpr int SPHM = sph_tab_ok<C>() ? 2 : 0;  // Estrin form: the call ends on this polynomial
-    if constexpr (SPHM != 0) tab_base = (unsigned)__cvta_generic_to_shared(sph_smem<C>());
+    constexpr int SPHM = sph_tab_ok<C>() ? 4 : 0;  // the wide table at the start of dynamic shared memory, Estrin form
+    if constexpr (SPHM != 0) tab_base = (unsigned)__cvta_generic_to_shared(dyn_smem());
     else if constexpr (nfw_tab_ok<C>()) tab_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
     gradient<C, (!SPHM && C::is_static && C::kPLC > 0), (!SPHM && nfw_tab_ok<C>()), SPHM>(rhs_pot<C, IMG>(), x, y, z, g0, g1,
                                                                                           g2, 0.0, tab_base);
@@ -1139,7 +1137,7 @@ constexpr int REC_DOUBLES = GX_DENSE_RECORD_DOUBLES;  // tprev, tnext, hd, q0[3]
 #define GX_DP8_PIPELINE 1
 #endif
 template <class C, class TB, bool IMG, bool EPI = false>
-__global__ void __launch_bounds__(128, GX_DP8_MIN_BLOCKS)
+__global__ void __launch_bounds__((sph_tab_ok<C>() ? 384 : 128), (sph_tab_ok<C>() ? 1 : GX_DP8_MIN_BLOCKS))
 k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
     constexpr int NS = TB::NS;
     if constexpr (!IMG) {  // stage the potential parameters in shared memory for accel_call()
@@ -1149,7 +1147,7 @@ k_integrate_dopri8(const __grid_constant__ DevPot P, const Dp8Args a) {
         __syncthreads();
     }
     if constexpr (sph_tab_ok<C>()) {
-        (void)sph_stage<C, sph_tab_ok<C>()>(P);  // (MW, MW2022, Bovy) the combined spherical table, read by accel_call()
+        (void)sph_wide_stage(P);  // the combined spherical table (132 KB, one CTA of 384 threads per SM), read by accel_call()
     } else {
         plc_stage<C>(P);  // (GX_SPH_TABLE=0) the PowerLawCutoff table
         (void)nfw_stage<C, nfw_tab_ok<C>()>(P);  // ... and the NFW force table
@@ -2354,7 +2352,7 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     solver &= ~GX_SOLVER_STRICT;
     if (solver != GX_SOLVER_DOPRI8 && solver != GX_SOLVER_DOPRI5) return GX_ERR_UNSUPPORTED;
     DevPot D; Model model;
-    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE, 0.0, !stream_is_capturing(stream), TAB_NARROW);
+    int rc = build_devpot(pot, D, model, !strict, TD_INTEGRATE, 0.0, !stream_is_capturing(stream), TAB_WIDE);
     if (rc) return rc;
     if (!pid || N < 0 || T < 0 || (N > 0 && (!q0 || !p0)) || (N > 0 && T > 0 && (!ts || !q || !p)) || !workspace)
         return GX_ERR_BADARG;
@@ -2386,13 +2384,31 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     out_strides(layout, N, T, a.sn, a.sk, a.sc);
     // persistent launch: resident CTAs only (occupancy query), never more lanes than particles; small batches
     // use narrow CTAs so that the few particles spread over all SMs.
-    const int block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
-    const size_t dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
-    a.stage = dyn != 0;
-    a.stage_off = 0;
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // Kernels that hold the 132 KB wide table: ONE CTA per SM, up to 384 threads (168 registers each), as wide as the batch
+    // needs and the staging of the saves leaves room for; the others as before.
+    const bool tabled = GX_SPH_TABLE && (model != MODEL_GENERIC || (is_basic_composite(D, model) && D.sph_wide));
+    int block;
+    size_t dyn;
+    a.stage_off = 0;
+    if (tabled) {
+        const size_t per_thread = save_stage_bytes(layout, T, 1, a.epi.nv);
+        const size_t room = (size_t)226 * 1024 - SPHW_BYTES;
+        int maxb = per_thread ? (int)((room / per_thread) / 32 * 32) : 384;
+        if (maxb > 384) maxb = 384;
+        if (maxb < 32) return GX_ERR_UNSUPPORTED;
+        long long want_b = ((N + sms - 1) / sms + 31) / 32 * 32;
+        block = (int)(want_b < 32 ? 32 : (want_b > maxb ? maxb : want_b));
+        dyn = SPHW_BYTES + (size_t)block * per_thread;
+        a.stage = per_thread != 0;
+        a.stage_off = SPHW_BYTES / 8;
+    } else {
+        block = (N >= 148LL * 128) ? 128 : ((N >= 148LL * 64) ? 64 : 32);
+        dyn = save_stage_bytes(layout, T, block, a.epi.nv);  // per-lane staging of the saves (0: direct stores)
+        a.stage = dyn != 0;
+    }
 #define GX_LAUNCH_DP8_(C_, IMG_)                                                                              \
     do {                                                                                                      \
         auto kern = with_epi ? ((solver == GX_SOLVER_DOPRI5) ? k_integrate_dopri8<C_, TabDp5, IMG_, true>     \
@@ -2415,7 +2431,7 @@ static int adaptive_impl(int solver, double *rec, int *n_rec, int rec_cap, const
     const int img = use_const_image(D, s, dev);
     if (img < 0) return img;
     if (is_basic_composite(D, model)) {
-        if (D.sph_tab) GX_LAUNCH_DP8(CountsBasicTab);
+        if (D.sph_wide) GX_LAUNCH_DP8(CountsBasicTab);
         else GX_LAUNCH_DP8(CountsBasic);
     } else GX_DISPATCH_MODEL(model, GX_LAUNCH_DP8(C));
     rc = cuda_rc(cudaGetLastError());

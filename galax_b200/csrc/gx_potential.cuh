@@ -491,6 +491,7 @@ __device__ __forceinline__ bool sph_table_eval(double u, double &S, unsigned bas
 }
 
 // The wide format: S(u) from the table at the start of the CTA's dynamic shared memory (base = its shared-window address).
+template <bool ESTRIN = false>
 __device__ __forceinline__ bool sph_wide_eval(double u, double &S, unsigned base, unsigned j0w) {
     const int hi = __double2hiint(u);
     constexpr int B = SPHW_SUB_BITS;
@@ -502,10 +503,16 @@ __device__ __forceinline__ bool sph_wide_eval(double u, double &S, unsigned base
     const double t = fma(m, (double)(2 << B), -cB);
     const unsigned a0 = base + j * (unsigned)(SPHW_ROW * 8);
     const double2 c01 = lds_v2f64(a0), c23 = lds_v2f64(a0 + 16u), c45 = lds_v2f64(a0 + 32u);
-    double v = fma(c45.y, t, c45.x);
-    v = fma(v, t, c23.y); v = fma(v, t, c23.x);
-    v = fma(v, t, c01.y); v = fma(v, t, c01.x);
-    S = v;
+    if (ESTRIN) {  // 6 FP64, 3 deep (the latency-bound Dopri kernels, whose right-hand side ends on this polynomial)
+        const double t2 = t * t;
+        const double p01 = fma(c01.y, t, c01.x), p23 = fma(c23.y, t, c23.x), p45 = fma(c45.y, t, c45.x);
+        S = fma(fma(p45, t2, p23), t2, p01);
+    } else {       // Horner: 5 FP64 (the fixed-step kernels)
+        double v = fma(c45.y, t, c45.x);
+        v = fma(v, t, c23.y); v = fma(v, t, c23.x);
+        v = fma(v, t, c01.y); v = fma(v, t, c01.x);
+        S = v;
+    }
     return true;
 }
 __device__ __forceinline__ double *dyn_smem() {
@@ -657,8 +664,8 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
     if (any_sph) {
         const double r2 = fma(z, z, R2);  // (R2 carries the TINY that keeps r > 0)
         if constexpr (SPH != 0) {
-            if constexpr (SPH == 3) {  // the wide format (fixed-step kernels)
-                if (!sph_wide_eval(r2, fs, nfw_base, P.sph_j0w)) fs = spherical_fallback<C>(&P, r2);
+            if constexpr (SPH >= 3) {  // the wide format: 3 Horner (fixed-step kernels), 4 Estrin (Dopri kernels)
+                if (!sph_wide_eval<SPH == 4>(r2, fs, nfw_base, P.sph_j0w)) fs = spherical_fallback<C>(&P, r2);
             } else {
                 if (!sph_table_eval<SPH == 2>(r2, fs, nfw_base, P.sph_j0)) fs = spherical_fallback<C>(&P, r2);
             }

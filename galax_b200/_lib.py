@@ -194,9 +194,6 @@ _SIGNATURES = {
     "gx_spherical_force_table": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_int64, C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.POINTER(C.c_double)]),
-    "gx_spherical_force_table_wide": (C.c_int, [C.POINTER(GxPotential), C.c_void_p, C.c_int64, C.POINTER(C.c_int32),
-                                                C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
-                                                C.POINTER(C.c_double)]),
     "gx_fixed_time_grid": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_int32]),
 }  # fmt: skip

@@ -51,9 +51,9 @@ enum TdMode { TD_REJECT = 0, TD_FREEZE = 1, TD_INTEGRATE = 2 };
 
 // may_upload = false (the caller's stream is being captured into a graph): a combined spherical table that is not in the
 // cache yet is not fitted and uploaded now -- the composite then runs through the runtime-count kernels.
-// tabs: which formats of the combined spherical table the caller's kernels look up (TAB_NARROW: Dopri kernels, TAB_WIDE:
-// fixed-step kernels); each is fitted and uploaded on first use only by the entries that need it.
-enum { TAB_NONE = 0, TAB_NARROW = 1, TAB_WIDE = 2 };
+// tabs: TAB_WIDE when the caller's kernels look the spherical components up in the combined table (the integrators); it is
+// fitted and uploaded on first use only by the entries that need it.
+enum { TAB_NONE = 0, TAB_WIDE = 2 };
 static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, bool use_device = true,
                         TdMode td_mode = TD_REJECT, double t_freeze = 0.0, bool may_upload = true, int tabs = TAB_NONE) {
     if (!pot_in || pot_in->n < 0 || pot_in->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
@@ -224,12 +224,9 @@ static int build_devpot(const gx_potential *pot_in, DevPot &D, Model &model, boo
                 if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, G * c.p[0], c.p[1], 0.0});
                 if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
             }
-            const int e_lo = sph_e_lo(cs);
-            D.sph_j0 = (unsigned)((1023 + e_lo) << SPH_SUB_BITS);
-            D.sph_j0w = (unsigned)((1023 + e_lo) << SPHW_SUB_BITS);
-            if (tabs & TAB_NARROW) D.sph_tab = sph_table_for(cs, nullptr, may_upload);
-            if (tabs & TAB_WIDE) D.sph_wide = sph_wide_table_for(cs, nullptr, may_upload);
-            if (((tabs & TAB_NARROW) && D.sph_tab == nullptr) || ((tabs & TAB_WIDE) && D.sph_wide == nullptr)) model = MODEL_GENERIC;
+            D.sph_j0w = (unsigned)((1023 + sph_e_lo(cs)) << SPHW_SUB_BITS);
+            D.sph_wide = sph_table_for(cs, nullptr, may_upload);
+            if (D.sph_wide == nullptr) model = MODEL_GENERIC;
         }
 #endif
     }
@@ -2765,29 +2762,6 @@ int gx_force_table(int32_t which, double a, double *coef, int64_t capacity, int3
 
 int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
                              int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err) {
-    if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
-    std::vector<SphComp> cs;
-    for (int i = 0; i < pot->n; ++i) {
-        const gx_component &c = pot->c[i];
-        if (c.kind == GX_KIND_HERNQUIST || c.kind == GX_KIND_NFW) cs.push_back({c.kind, pot->G * c.p[0], c.p[1], 0.0});
-        if (c.kind == GX_KIND_POWERLAWCUTOFF) cs.push_back({c.kind, pot->G * c.p[0], c.p[2], 1.5 - c.p[1] / 2});
-    }
-    if (cs.empty()) return GX_ERR_UNSUPPORTED;
-    if (n_intervals) *n_intervals = SPH_NINT;
-    if (degree) *degree = SPH_DEG;
-    if (e_lo) *e_lo = sph_e_lo(cs);
-    if (sub_bits) *sub_bits = SPH_SUB_BITS;
-    if (!coef && !max_rel_err) return 0;
-    if (coef && capacity < (int64_t)SPH_NINT * SPH_ROW) return GX_ERR_BADARG;
-    std::vector<double> tmp;
-    if (!coef) { tmp.resize((size_t)SPH_NINT * SPH_ROW); coef = tmp.data(); }
-    const double worst = sph_table_fit(cs, coef);
-    if (max_rel_err) *max_rel_err = worst;
-    return 0;
-}
-
-int gx_spherical_force_table_wide(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
-                                  int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err) {
     if (!pot || pot->n < 0 || pot->n > GX_MAX_COMPONENTS) return GX_ERR_BADARG;
     std::vector<SphComp> cs;
     for (int i = 0; i < pot->n; ++i) {

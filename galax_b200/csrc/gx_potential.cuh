@@ -146,28 +146,20 @@ constexpr int NFW_NINT = (NFW_E_HI - NFW_E_LO) * PLC_SUB;
 // Combined spherical force table of one composite: S(u) = sum over its spherical components of Phi_i'(r)/r as a
 // function of u = r^2 (Hernquist GM/(r (r+c)^2), NFW (GM/r_s^3) F(r/r_s), PowerLawCutoff (GM/r_c^3) G(r/r_c)), fitted
 // per potential on the host in long double (plc_table.h: sph_table_for).  Indexed by the bits of r^2, it removes from a
-// right-hand side of the static models everything spherical: the rsqrt of r^2, the Hernquist reciprocals, the NFW /
-// PowerLawCutoff lookups in s = r/r_s (MilkyWayPotential2022: 77 -> 62 FP64 instructions, 6 -> 4 MUFU chains), and the
-// lookup no longer waits for sqrt(r^2).
-// Layout: 2^SPH_SUB_BITS = 32 intervals per octave of u (= 64 per octave of r: u^(-3/2) converges like 130^-n), degree
-// 7, 22 octaves of u (MW models: r from 62 pc to 128 kpc): 704 rows of 8 doubles = 64 B = FOUR 16-byte loads per lookup, 44 KB
-// of shared memory.  (First version: degree 9 on 16 intervals, 80-byte rows, five loads.  The fixed-step kernels that
-// use the table are bound by the shared-memory port -- every lane reads another row -- so a row is as short as the
-// accuracy allows.)  A 64-byte row stride would put a chunk of every second row in the same bank group, so the four
-// 16-byte chunks of row j are stored XOR-swizzled: chunk c at position c ^ ((j >> 1) & 3); eight consecutive rows then
-// cover the eight bank groups for every c, as an odd stride would, without padding.
-// Outside the range: the closed forms (spherical_fallback, out of line).
+// right-hand side everything spherical: the rsqrt of r^2, the Hernquist reciprocals, the NFW / PowerLawCutoff lookups
+// in s = r/r_s (MilkyWayPotential2022: 77 -> 60 FP64 instructions, 6 -> 4 MUFU chains), and the lookup no longer waits
+// for sqrt(r^2).
+// Layout: 2^7 = 128 intervals per octave of u, degree 5, rows of 6 doubles = 48 bytes = THREE 16-byte loads per lookup
+// (an odd number of chunks: consecutive rows cover the eight bank groups without padding or swizzle), 22 octaves: 2816
+// rows = 132 KB, held in dynamic shared memory by ONE CTA per SM.  The kernels that use it are bound by the
+// shared-memory port (every lane reads another row), so a row is as short as the accuracy allows -- history: degree 9
+// on 16 intervals, 80-byte rows, five loads (40 KB); degree 7 on 32 intervals, 64-byte swizzled rows, four loads
+// (44 KB, +17..21 % on the port-bound fixed-step kernels); this one (+13..29 % again).
 // The 22 octaves are placed per potential (sph_e_lo() in plc_table.h): up to 8 x the largest scale radius of the
-// spherical components, rounded up to a power of two -- [2^-8, 2^14) kpc^2 for the three Milky-Way models in galactic
-// units; the library does not know the unit system, the scale radii do.
-constexpr int SPH_E_LO = -8, SPH_OCTAVES = 22, SPH_SUB_BITS = 5, SPH_DEG = 7, SPH_ROW = SPH_DEG + 1;
-constexpr int SPH_NINT = SPH_OCTAVES << SPH_SUB_BITS;
-static_assert(SPH_ROW == 8, "rows are four 16-byte chunks (swizzle, Estrin form)");
-// The WIDE format of the same table, for the fixed-step kernels (which the shared-memory port bounds): 128 intervals per
-// octave, degree 5, rows of 6 doubles = 48 bytes = THREE 16-byte loads per lookup (an odd number of chunks: consecutive
-// rows cover the bank groups without a swizzle), 22 x 128 x 48 B = 132 KB -- one CTA per SM, in dynamic shared memory.
-// Measured with a timing probe before it was built: three loads instead of four are worth +10 % on MilkyWayPotential's
-// mixed steps and +34 % on BovyMWPotential2014.
+// spherical components, rounded up to a power of two -- [2^-8, 2^14) kpc^2, i.e. 62 pc to 128 kpc, for the three
+// Milky-Way models in galactic units; the library does not know the unit system, the scale radii do.
+// Outside the range: the closed forms (spherical_fallback, out of line).
+constexpr int SPH_E_LO = -8, SPH_OCTAVES = 22;
 constexpr int SPHW_SUB_BITS = 7, SPHW_DEG = 5, SPHW_ROW = SPHW_DEG + 1;
 constexpr int SPHW_NINT = SPH_OCTAVES << SPHW_SUB_BITS;
 constexpr int SPHW_BYTES = SPHW_NINT * SPHW_ROW * 8;
@@ -223,10 +215,9 @@ struct alignas(16) DevPot {
     DevHarm harm[MAX_HARM];
     DevHenon henon[MAX_HENON];
     const double *nfw_tab;  // universal NFW force table (nfw_table(), plc_table.h) or nullptr
-    const double *sph_tab;  // this composite's spherical force table S(r^2) (sph_table_for(), plc_table.h) or nullptr
-    unsigned sph_j0;        // ... and where it starts: (1023 + e_lo) << SPH_SUB_BITS, the table covers u in [2^e_lo, 2^(e_lo + 22))
-    unsigned sph_j0w;       // the same for the wide format: (1023 + e_lo) << SPHW_SUB_BITS
-    const double *sph_wide; // the wide format of the table (fixed-step kernels) or nullptr
+    const double *sph_wide; // this composite's spherical force table S(r^2) (sph_table_for(), plc_table.h) or nullptr
+    unsigned sph_j0w;       // ... and where it starts: (1023 + e_lo) << SPHW_SUB_BITS, the table covers u in [2^e_lo, 2^(e_lo + 22))
+    unsigned pad_sph_;
     DevTD td;
 };
 
@@ -308,7 +299,7 @@ struct Counts {
     static constexpr bool is_static = (NMN >= 0);
     // BASIC_TAB (with BASIC): the composite's spherical components -- however many Hernquist / NFW / PowerLawCutoff
     // terms -- are ONE lookup in its combined force table S(r^2), as for the three named models; only the
-    // Miyamoto-Nagai terms are looped over at run time.  The host picks it when the table exists (P.sph_tab).
+    // Miyamoto-Nagai terms are looped over at run time.  The host picks it when the table exists (P.sph_wide).
     static constexpr bool basic_tab = BASIC && BASIC_TAB;
     // BASIC (runtime counts only): a composite of the four basic kinds with constant parameters -- the loops over the
     // further kinds and the time-dependent branch are compiled out (the full runtime kernel is 85 KB of SASS against a
@@ -403,8 +394,8 @@ __device__ __forceinline__ unsigned nfw_stage(const DevPot &P) {
     return b;
 }
 
-// The combined spherical table S(r^2) of a static model (MW, MW2022, Bovy): which kernels use it, and its staging.
-//   mode 0: not used; 1: Horner (issue-bound fixed-step kernels); 2: Estrin (latency-bound Dopri kernels).
+// The combined spherical table S(r^2): which kernels use it.
+//   mode 0: not used; 3: Horner (fixed-step kernels); 4: Estrin (latency-bound Dopri kernels).
 template <class C>
 __host__ __device__ constexpr bool sph_tab_ok() {
     return GX_SPH_TABLE && ((C::is_static && (C::kH + C::kNFW + C::kPLC > 0)) || C::basic_tab);
@@ -439,58 +430,8 @@ __device__ __forceinline__ bool sph_mix_table_step(unsigned long long step) {
     return (unsigned)((step * (unsigned)GX_SPH_MIX_TABLE) % (unsigned)(GX_SPH_MIX_PERIOD > 0 ? GX_SPH_MIX_PERIOD : 1)) <
            (unsigned)GX_SPH_MIX_TABLE;
 }
-template <class C>
-__device__ __forceinline__ double *sph_smem() {
-    __shared__ __align__(64) double t[SPH_NINT * SPH_ROW];  // (64-byte aligned: the swizzle XORs address bits 4-5)
-    return t;
-}
-// Call once per CTA, by all threads; returns the shared-window address of the table.
-template <class C, bool ON>
-__device__ __forceinline__ unsigned sph_stage(const DevPot &P) {
-    unsigned b = 0;
-    if constexpr (ON) {  // (the host only picks a static model's integrator kernels when P.sph_tab exists)
-        double *t = sph_smem<C>();
-        const double2 *src2 = reinterpret_cast<const double2 *>(P.sph_tab);
-        double2 *t2 = reinterpret_cast<double2 *>(t);
-        for (int idx = threadIdx.x; idx < SPH_NINT * SPH_ROW / 2; idx += blockDim.x) t2[idx] = __ldg(src2 + idx);
-        __syncthreads();
-        b = (unsigned)__cvta_generic_to_shared(t);
-        asm volatile("" : "+r"(b));
-    }
-    return b;
-}
-
-// S(u) from the staged table (base = its shared-window address); false outside the tabulated range.
-// ESTRIN: 9 FP64 instructions, 3 deep (latency-bound callers: the Dopri kernels, small batches); else Horner, 7.
-template <bool ESTRIN>
-__device__ __forceinline__ bool sph_table_eval(double u, double &S, unsigned base, unsigned j0) {
-    const int hi = __double2hiint(u);
-    constexpr int B = SPH_SUB_BITS;
-    const unsigned j = (unsigned)(hi >> (20 - B)) - j0;  // j0 = (1023 + e_lo) << B: the table's first octave (per potential)
-    if (j >= (unsigned)SPH_NINT) return false;  // u outside the table (also NaN / negative)
-    // t in [-1, 1) on the interval, straight from the bits of u (see poly_table_eval)
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
-    constexpr int TOP = ((1 << B) - 1) << (20 - B), HALF = 1 << (19 - B), EXPC = (1023 + B + 1) << 20;
-    const double cB = __hiloint2double((hi & TOP) | HALF | EXPC, 0);
-    const double t = fma(m, (double)(2 << B), -cB);
-    const unsigned a0 = (base + j * (unsigned)(SPH_ROW * 8)) ^ ((j << 3) & 0x30u);  // chunk c lives at a0 ^ (16 c)
-    const double2 c01 = lds_v2f64(a0), c23 = lds_v2f64(a0 ^ 16u), c45 = lds_v2f64(a0 ^ 32u), c67 = lds_v2f64(a0 ^ 48u);
-    if (ESTRIN) {
-        const double t2 = t * t, t4 = t2 * t2;
-        const double p01 = fma(c01.y, t, c01.x), p23 = fma(c23.y, t, c23.x), p45 = fma(c45.y, t, c45.x),
-                     p67 = fma(c67.y, t, c67.x);
-        S = fma(fma(p67, t2, p45), t4, fma(p23, t2, p01));
-    } else {
-        double v = fma(c67.y, t, c67.x);
-        v = fma(v, t, c45.y); v = fma(v, t, c45.x);
-        v = fma(v, t, c23.y); v = fma(v, t, c23.x);
-        v = fma(v, t, c01.y); v = fma(v, t, c01.x);
-        S = v;
-    }
-    return true;
-}
-
-// The wide format: S(u) from the table at the start of the CTA's dynamic shared memory (base = its shared-window address).
+// S(u) from the table at the start of the CTA's dynamic shared memory (base = its shared-window address); false outside
+// the tabulated range.
 template <bool ESTRIN = false>
 __device__ __forceinline__ bool sph_wide_eval(double u, double &S, unsigned base, unsigned j0w) {
     const int hi = __double2hiint(u);
@@ -664,11 +605,8 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
     if (any_sph) {
         const double r2 = fma(z, z, R2);  // (R2 carries the TINY that keeps r > 0)
         if constexpr (SPH != 0) {
-            if constexpr (SPH >= 3) {  // the wide format: 3 Horner (fixed-step kernels), 4 Estrin (Dopri kernels)
-                if (!sph_wide_eval<SPH == 4>(r2, fs, nfw_base, P.sph_j0w)) fs = spherical_fallback<C>(&P, r2);
-            } else {
-                if (!sph_table_eval<SPH == 2>(r2, fs, nfw_base, P.sph_j0)) fs = spherical_fallback<C>(&P, r2);
-            }
+            // SPH: 3 Horner (fixed-step kernels), 4 Estrin (Dopri kernels)
+            if (!sph_wide_eval<SPH == 4>(r2, fs, nfw_base, P.sph_j0w)) fs = spherical_fallback<C>(&P, r2);
         } else {
             fs = spherical_factor<C, PLC_SMEM, NFW_TAB>(P, r2, plc_base, nfw_base);
         }

@@ -211,10 +211,10 @@ static int sph_e_lo(const std::vector<SphComp> &cs) {
     return e_lo;
 }
 
-// Fit of the table (host only; also used by gx_spherical_force_table): coef[SPH_NINT][SPH_ROW] in natural order,
+// Fit of the table (host only; also used by gx_spherical_force_table): coef[SPHW_NINT][SPHW_ROW],
 // returns the worst relative error of the fp64 Horner evaluation against the long-double function on a 41-point grid
 // per interval.
-template <int SUB_BITS = SPH_SUB_BITS, int ROW = SPH_ROW>
+template <int SUB_BITS = SPHW_SUB_BITS, int ROW = SPHW_ROW>
 static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
     double worst = 0.0;
     const int e_lo = sph_e_lo(cs);
@@ -229,10 +229,6 @@ static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
     return worst;
 }
 
-// The device table of this set of spherical components on the current device: built (a few ms of host time) and
-// uploaded on FIRST use of a potential, immutable afterwards and kept for the life of the process -- at most
-// SPH_CACHE_MAX distinct (device, parameter set) entries; beyond that, or if the fit misses 1e-14, nullptr (the caller
-// then runs the composite through the runtime-count kernels).
 static bool sph_same(const std::vector<SphComp> &a, const std::vector<SphComp> &b) {  // (field by field: the struct has padding)
     if (a.size() != b.size()) return false;
     for (size_t k = 0; k < a.size(); ++k)
@@ -240,58 +236,12 @@ static bool sph_same(const std::vector<SphComp> &a, const std::vector<SphComp> &
     return true;
 }
 constexpr size_t SPH_CACHE_MAX = 4096;  // x 44 KB = 180 MB of device memory at most (a parameter scan: 15-25 ms of host time per new set)
+// The device table of this set of spherical components on the current device: fitted (12-25 ms of host time) and
+// uploaded on FIRST use of a potential by an integrator, immutable afterwards and kept for the life of the process -- at
+// most SPH_CACHE_MAX distinct (device, parameter set) entries; beyond that, if the fit misses 1e-14, or when the
+// caller's stream is being captured and the table is not there yet: nullptr (the caller then runs the composite
+// through the runtime-count kernels).
 static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr, bool may_upload = true) {
-    struct Entry { int device; std::vector<SphComp> cs; double *dev_ptr; double max_rel_err; };
-    static std::mutex mu;
-    static std::vector<Entry> cache;
-    int dev = 0;
-    if (cs.empty() || cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    const std::vector<double> *fitted = nullptr;
-    static std::vector<std::vector<double>> fits;  // host copies, index-aligned with `cache` (another device re-uses the fit)
-    for (size_t k = 0; k < cache.size(); ++k) {
-        const Entry &e = cache[k];
-        if (sph_same(e.cs, cs)) {
-            if (e.device == dev) {
-                if (max_rel_err_out) *max_rel_err_out = e.max_rel_err;
-                return e.dev_ptr;
-            }
-            fitted = &fits[k];
-        }
-    }
-    if (cache.size() >= SPH_CACHE_MAX || !may_upload) return nullptr;  // (!may_upload: the caller's stream is being captured)
-    std::vector<double> host;
-    double worst = 0.0;
-    if (fitted) {
-        host = *fitted;
-    } else {
-        host.resize((size_t)SPH_NINT * SPH_ROW);
-        worst = sph_table_fit(cs, host.data());
-    }
-    double *d = nullptr;
-    if (worst < 1e-14) {
-        // device layout: the four 16-byte chunks of row j XOR-swizzled by (j >> 1) & 3 (gx_potential.cuh)
-        std::vector<double> sw(host.size());
-        for (int j = 0; j < SPH_NINT; ++j)
-            for (int c = 0; c < 4; ++c) {
-                const int pos = c ^ ((j >> 1) & 3);
-                sw[(size_t)j * SPH_ROW + 2 * pos] = host[(size_t)j * SPH_ROW + 2 * c];
-                sw[(size_t)j * SPH_ROW + 2 * pos + 1] = host[(size_t)j * SPH_ROW + 2 * c + 1];
-            }
-        if (cudaMalloc(&d, sw.size() * sizeof(double)) != cudaSuccess) return nullptr;  // (not cached: may succeed later)
-        if (cudaMemcpy(d, sw.data(), sw.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
-            cudaFree(d);
-            return nullptr;
-        }
-    }
-    cache.push_back({dev, cs, d, worst});
-    fits.push_back(std::move(host));
-    if (max_rel_err_out) *max_rel_err_out = worst;
-    return d;
-}
-
-// The WIDE format of the same table (SPHW_*: fixed-step kernels), cached the same way; plain row order.
-static const double *sph_wide_table_for(const std::vector<SphComp> &cs, double *max_rel_err_out = nullptr, bool may_upload = true) {
     struct Entry { int device; std::vector<SphComp> cs; double *dev_ptr; double max_rel_err; };
     static std::mutex mu;
     static std::vector<Entry> cache;

@@ -16,7 +16,7 @@
  *   - re-entrant and safe to call from several host threads / on several streams: the potential is passed by value
  *     into each launch (kernel-parameter constant bank).  Process-wide state: (1) an append-only, mutex-guarded cache
  *     of immutable force tables (NFW 30 KB, PowerLawCutoff 35 KB per exponent, and for the three named Milky-Way
- *     models 44 KB (adaptive kernels) and 132 KB (fixed-step kernels) per distinct set of spherical-component parameters, at most 4096 sets each; device memory, fitted in 15-60 ms of host time by the first call that needs it,
+ *     models and every composite of the four basic kinds 132 KB per distinct set of spherical-component parameters, at most 4096 sets; device memory, fitted in 12-25 ms of host time by the first integrator call that needs it,
  *     allocated and uploaded on FIRST use -- the one allocation an enqueue-only entry can make, so warm an entry up
  *     once with a potential before capturing it into a graph);
  *     (2) for the adaptive integrators, a per-device __constant__ copy of the potential that a launch reads only when
@@ -317,16 +317,13 @@ int gx_force_table(int32_t which, double a, double *coef, int64_t capacity, int3
                    int32_t *e_lo, int32_t *sub_bits, double *max_rel_err);
 /* Host only (no CUDA call): the COMBINED spherical force table of a composite, S(u) = sum over its Hernquist / NFW /
  * PowerLawCutoff components of Phi_i'(r)/r as a function of u = r^2 -- what the integrators of the three named
- * Milky-Way models look up instead of evaluating the spherical components (fitted per potential on first use, cached
- * per device; same row layout as gx_force_table, intervals per octave of u).  GX_ERR_UNSUPPORTED if the potential has
- * no spherical component of these kinds. */
+ * Milky-Way models -- and of any other composite of the four basic kinds -- look up instead of evaluating the spherical
+ * components: 128 intervals per octave of u over 22 octaves placed by the scale radii, degree 5, rows of 6 doubles
+ * (48 bytes = three 16-byte loads per lookup: those kernels are bound by the shared-memory port), 132 KB held in shared
+ * memory by one CTA per SM.  Fitted per potential by the first integrator call that needs it, cached per device.
+ * GX_ERR_UNSUPPORTED if the potential has no spherical component of these kinds. */
 int gx_spherical_force_table(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
                              int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err);
-/* ... and its WIDE format, which the fixed-step kernels hold in shared memory (one CTA per SM): 128 intervals per octave,
- * degree 5, 48-byte rows = three 16-byte loads per lookup instead of four -- those kernels are bound by the shared-memory
- * port.  132 KB per parameter set, fitted and uploaded on the first fixed-step call with a potential. */
-int gx_spherical_force_table_wide(const gx_potential *pot, double *coef, int64_t capacity, int32_t *n_intervals,
-                                  int32_t *degree, int32_t *e_lo, int32_t *sub_bits, double *max_rel_err);
 /* elementwise math probes for the tests: op 0 rcp, 1 rsqrt, 2 log1p, 3 gammainc_P(a, x), 4 NFW shape ln(1+s) - s/(1+s),
  * 5 NFW force table F(s) = shape / s^3, 6 / 7 PowerLawCutoff table G(s) = P(a, s^2) / s^3 and dG/ds (NaN outside the
  * tabulated range) */

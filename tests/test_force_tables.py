@@ -69,9 +69,9 @@ def test_bad_arguments():
 
 
 # ---- the combined spherical table S(r^2) of a composite (gx_spherical_force_table) ------------------------------
-def sph_table(pot, wide=False):
+def sph_table(pot):
     L = _lib.lib()
-    fn = L.gx_spherical_force_table_wide if wide else L.gx_spherical_force_table
+    fn = L.gx_spherical_force_table
     cs = pot.c_struct()
     n, deg, lo, sb, err = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
     assert fn(C.byref(cs), None, 0, C.byref(n), C.byref(deg), C.byref(lo), C.byref(sb), None) == 0
@@ -81,7 +81,7 @@ def sph_table(pot, wide=False):
 
 
 def evaluate_estrin(coef, e_lo, sub_bits, s):
-    """The Estrin form the Dopri kernels use (poly_table_eval<..., ESTRIN = true>), in numpy."""
+    """The Estrin form the Dopri kernels use (sph_wide_eval<ESTRIN = true>: degree 5), in numpy."""
     s = np.asarray(s, dtype=np.float64)
     hi = (s.view(np.uint64) >> np.uint64(32)).astype(np.int64)
     j = (hi >> (20 - sub_bits)) - (1023 + e_lo) * (1 << sub_bits)
@@ -89,10 +89,10 @@ def evaluate_estrin(coef, e_lo, sub_bits, s):
     sub = (hi >> (20 - sub_bits)) & ((1 << sub_bits) - 1)
     t = m * float(2 << sub_bits) - (float(2 << sub_bits) + 2.0 * sub + 1.0)
     c = coef[j]
-    assert c.shape[1] == 8
-    t2 = t * t; t4 = t2 * t2
-    p = [c[:, 2 * k + 1] * t + c[:, 2 * k] for k in range(4)]
-    return (p[3] * t2 + p[2]) * t4 + (p[1] * t2 + p[0])
+    assert c.shape[1] == 6
+    t2 = t * t
+    p = [c[:, 2 * k + 1] * t + c[:, 2 * k] for k in range(3)]
+    return (p[2] * t2 + p[1]) * t2 + p[0]
 
 
 def sph_reference(pot, r):
@@ -121,35 +121,20 @@ def sph_reference(pot, r):
 
 @pytest.mark.parametrize("name", ["MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014"])
 def test_combined_spherical_table_on_the_host(name):
+    """What the integrators look up: 128 intervals per octave of r^2, degree 5, 48-byte rows; Horner (fixed step) and
+    Estrin (Dopri) evaluation, against the 30-digit closed forms."""
     import galax_b200.potential as gp
 
     pot = getattr(gp, name)()
     coef, e_lo, sb, err = sph_table(pot)
-    assert coef.shape == (704, 8) and e_lo == -8 and sb == 5 and err < 4e-16
-    rng = np.random.default_rng(5)
-    edges = np.ldexp(1.0 + np.arange(32) / 32.0, rng.integers(-8, 14, 32))
-    below = np.nextafter(edges, 0)
-    u = np.concatenate([2.0 ** rng.uniform(-8, 14, 300), edges, below[below >= 2.0**-8], [2.0**-8, np.nextafter(2.0**14, 0)]])
-    ref = sph_reference(pot, np.sqrt(u) if False else [mp.sqrt(mp.mpf(float(x))) for x in u])
-    for ev in (evaluate, evaluate_estrin):
-        S = ev(coef, e_lo, sb, u)
-        assert np.abs(S / ref - 1).max() < 8e-16, ev.__name__
-
-
-@pytest.mark.parametrize("name", ["MilkyWayPotential", "MilkyWayPotential2022", "BovyMWPotential2014"])
-def test_wide_format_of_the_combined_table_on_the_host(name):
-    """What the fixed-step kernels look up: 128 intervals per octave, degree 5, 48-byte rows."""
-    import galax_b200.potential as gp
-
-    pot = getattr(gp, name)()
-    coef, e_lo, sb, err = sph_table(pot, wide=True)
     assert coef.shape == (2816, 6) and e_lo == -8 and sb == 7 and err < 4e-16
     rng = np.random.default_rng(7)
     edges = np.ldexp(1.0 + np.arange(0, 128, 5) / 128.0, rng.integers(-8, 14, 26))
     below = np.nextafter(edges, 0)
     u = np.concatenate([2.0 ** rng.uniform(-8, 14, 300), edges, below[below >= 2.0**-8], [2.0**-8, np.nextafter(2.0**14, 0)]])
     ref = sph_reference(pot, [mp.sqrt(mp.mpf(float(x))) for x in u])
-    assert np.abs(evaluate(coef, e_lo, sb, u) / ref - 1).max() < 8e-16
+    for ev in (evaluate, evaluate_estrin):
+        assert np.abs(ev(coef, e_lo, sb, u) / ref - 1).max() < 8e-16, ev.__name__
 
 
 def test_combined_spherical_table_follows_the_scale_radii():
@@ -166,7 +151,7 @@ def test_combined_spherical_table_follows_the_scale_radii():
     rng = np.random.default_rng(6)
     for pot, want in cases:
         coef, e_lo, sb, err = sph_table(pot)
-        assert e_lo == want and coef.shape == (704, 8) and err < 4e-16, (want, e_lo, err)
+        assert e_lo == want and coef.shape == (2816, 6) and err < 6e-16, (want, e_lo, err)
         u = 2.0 ** rng.uniform(e_lo, e_lo + 22, 120)
         ref = sph_reference(pot, [mp.sqrt(mp.mpf(float(x))) for x in u])
         assert np.abs(evaluate(coef, e_lo, sb, u) / ref - 1).max() < 8e-16

@@ -521,11 +521,11 @@ def run_gpu(args) -> None:
         roofline = {"bound": "fp64", "achieved": None, "peak": peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
                     "source": "neither ncu nor cuobjdump available: executed instruction mix not measured"}  # fmt: skip
     roofline.update({
-        "kernel": "k_integrate_fixed_seg<MW> (SemiImplicitEuler, run-length time grid; three steps in four look the "
-                  "spherical force up in shared memory, one evaluates the closed forms)", "kernel_ms": k_ms,
-        "second_resource": "shared-memory port (the table steps): ~30 of the ~34.5 cycles per warp-step and SM, in parallel "
-                           "with the FP64 pipe; closed forms only (GX_SPH_MIX_PERIOD=0): 108 flop per step, frac 0.64, "
-                           "2.18e11 particle-steps/s",
+        "kernel": "k_integrate_fixed_seg<MW> (SemiImplicitEuler, run-length time grid; 13 steps in 16 look the spherical "
+                  "force up in the 132 KB table in shared memory, three evaluate the closed forms)", "kernel_ms": k_ms,
+        "second_resource": "shared-memory port (the table steps: three 16-byte loads per lane from scattered 48-byte "
+                           "rows), in parallel with the FP64 pipe; closed forms only (GX_SPH_MIX_PERIOD=0): 108 flop per "
+                           "step, frac 0.64, 2.18e11 particle-steps/s; table only: 2.86e11",
         "algorithmic_bytes_per_launch": n * (48 + 48 + 4),
         "peak_three_register_operands": peak_3reg,
         "peak_source": "measured live: gx_bench_dfma (8 independent DFMA chains/thread), best of 3; "

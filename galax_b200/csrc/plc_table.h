@@ -235,7 +235,7 @@ static bool sph_same(const std::vector<SphComp> &a, const std::vector<SphComp> &
         if (a[k].kind != b[k].kind || a[k].GM != b[k].GM || a[k].p1 != b[k].p1 || a[k].p2 != b[k].p2) return false;
     return true;
 }
-constexpr size_t SPH_CACHE_MAX = 4096;  // x 44 KB = 180 MB of device memory at most (a parameter scan: 15-25 ms of host time per new set)
+constexpr size_t SPH_CACHE_MAX = 4096;  // x 132 KB = 540 MB of device memory at most (a parameter scan: 15-25 ms of host time per new set)
 // The device table of this set of spherical components on the current device: fitted (12-25 ms of host time) and
 // uploaded on FIRST use of a potential by an integrator, immutable afterwards and kept for the life of the process -- at
 // most SPH_CACHE_MAX distinct (device, parameter set) entries; beyond that, if the fit misses 1e-14, or when the

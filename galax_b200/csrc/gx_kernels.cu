@@ -708,6 +708,18 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #ifndef GX_FUSED_UPDATE
 #define GX_FUSED_UPDATE 1
 #endif
+// Widest CTA of the kernels that hold the 132 KB table (one CTA per SM).  The run-length kernel is bound by latency --
+// FP64 chains and scattered shared-memory loads in turn -- and gains from every warp it can get: 1024 threads at 64
+// registers (MilkyWayPotential: no spill; MW2022 / Bovy / runtime composites: 8-32 bytes outside the hot loop) run 6.5 %
+// / 1.2 % / 1.5 % faster than 640 threads at 76-90 registers; 768 and 832 threads measured no better than 640.  The
+// step-by-step kernel (LeapfrogMidpoint, time-dependent parameters) would spill 40-64 bytes at 64 registers and stays
+// at 640.
+#ifndef GX_FIXED_TAB_BLOCK
+#define GX_FIXED_TAB_BLOCK 640
+#endif
+#ifndef GX_FIXED_SEG_BLOCK
+#define GX_FIXED_SEG_BLOCK 1024
+#endif
 #ifndef GX_FIXED_CNT32
 #define GX_FIXED_CNT32 1
 #endif
@@ -726,8 +738,10 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #endif
 // CTAs of the kernels that hold the wide table (132 KB: one per SM) are as wide as the batch needs, up to 640 threads
 // (384 with the save epilogue: its staging needs the room, and its kernels the registers)
-template <class C, bool EPI = false>
-__host__ __device__ constexpr int fixed_max_block() { return (sph_tab_fixed_ok<C>() || sph_mix_ok<C>()) ? (EPI ? 384 : 640) : 128; }
+template <class C, bool EPI = false, bool SEG = false>
+__host__ __device__ constexpr int fixed_max_block() {
+    return (sph_tab_fixed_ok<C>() || sph_mix_ok<C>()) ? (EPI ? 384 : (SEG ? GX_FIXED_SEG_BLOCK : GX_FIXED_TAB_BLOCK)) : 128;
+}
 template <class C, int SCHEME, bool FWD, bool EPI = false, bool SMALL = false>
 __global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy; every static model in small
@@ -839,7 +853,7 @@ __global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS
 // spherical table for every static model, in its 4-deep Estrin form -- q -> r^2 -> lookup -> p instead of
 // q -> r^2 -> rsqrt -> r -> s -> 1 + s -> rcp -> table log -> shape -> 1/r^3 -> p.
 template <class C, bool FWD, bool SMALL = false, bool EPI = false>
-__global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS)
+__global__ void __launch_bounds__(fixed_max_block<C, EPI, true>(), GX_FIXED_MIN_BLOCKS)
 k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
@@ -2216,8 +2230,9 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
     walk_time_grid(t0, t1, dt0, max_steps, sg, seg_ok, a.n_steps, a.hit_max_steps);
     // CTA width.  Kernels without a table: narrow CTAs for small batches, so that the particles spread over all SMs and
     // schedulers.  Kernels that hold the 132 KB wide table: ONE CTA per SM, as wide as the batch needs (a multiple of 32
-    // between 128 and what the staging of the saves leaves room for, at most 640) -- 10^4 particles are 79 CTAs of four
-    // warps, one per scheduler; 1.2e6 particles are 640-thread CTAs in waves of 148.
+    // between 128 and what the staging of the saves leaves room for, at most 1024 / 640 / 384 threads for the run-length
+    // kernel / the step-by-step kernel / the kernels with the save epilogue) -- 10^4 particles are 79 CTAs of four warps,
+    // one per scheduler; 1.2e6 particles are 1024-thread CTAs in 8 full waves of 148.
     const bool tabled = GX_SPH_TABLE && (model != MODEL_GENERIC || (is_basic_composite(D, model) && D.sph_wide));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -2228,12 +2243,15 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
     if (tabled) {
         const size_t per_thread = save_stage_bytes(layout, T, 1, a.epi.nv);  // staging bytes per lane (0: direct stores)
         const size_t room = (size_t)226 * 1024 - SPHW_BYTES;
-        int maxb = per_thread ? (int)((room / per_thread) / 32 * 32) : 640;
-        if (maxb > (with_epi ? 384 : 640)) maxb = with_epi ? 384 : 640;
+        const int cap = with_epi ? 384 : (seg_ok ? GX_FIXED_SEG_BLOCK : GX_FIXED_TAB_BLOCK);
+        int maxb = per_thread ? (int)((room / per_thread) / 32 * 32) : cap;
+        if (maxb > cap) maxb = cap;
         if (maxb < 32) return GX_ERR_UNSUPPORTED;
-        long long want = ((N + sms - 1) / sms + 31) / 32 * 32;
+        // full waves: the fewest waves of `sms` CTAs that hold the batch, then the narrowest CTA that fills them
+        const long long per_sm = (N + sms - 1) / sms;
+        const long long waves = (per_sm + maxb - 1) / maxb;
+        const long long want = ((per_sm + waves - 1) / waves + 31) / 32 * 32;
         block = (int)(want < 128 ? 128 : (want > maxb ? maxb : want));
-        if (block > maxb) block = maxb;
         dyn = SPHW_BYTES + (size_t)block * per_thread;
         a.stage = per_thread != 0;
         a.stage_off = SPHW_BYTES / 8;

@@ -161,6 +161,9 @@ constexpr int NFW_NINT = (NFW_E_HI - NFW_E_LO) * PLC_SUB;
 // Outside the range: the closed forms (spherical_fallback, out of line).
 constexpr int SPH_E_LO = -8, SPH_OCTAVES = 22;
 constexpr int SPHW_SUB_BITS = 7, SPHW_DEG = 5, SPHW_ROW = SPHW_DEG + 1;
+#ifndef GX_SPH_ARG_DIFF
+#define GX_SPH_ARG_DIFF 1
+#endif
 constexpr int SPHW_NINT = SPH_OCTAVES << SPHW_SUB_BITS;
 constexpr int SPHW_BYTES = SPHW_NINT * SPHW_ROW * 8;
 static_assert(SPHW_ROW == 6 && SPHW_BYTES % 16 == 0, "rows are three 16-byte chunks");
@@ -438,10 +441,19 @@ __device__ __forceinline__ bool sph_wide_eval(double u, double &S, unsigned base
     constexpr int B = SPHW_SUB_BITS;
     const unsigned j = (unsigned)(hi >> (20 - B)) - j0w;
     if (j >= (unsigned)SPHW_NINT) return false;
+#if GX_SPH_ARG_DIFF
+    // polynomial argument = u - (centre of the interval), an exact difference; the device rows are the fitted monomial
+    // coefficients in t in [-1, 1) rescaled by powers of two (plc_table.h::sph_rows_for_device), so every intermediate
+    // of the evaluation is the power-of-two multiple of what the t form gives: the same bits, three integer
+    // instructions fewer per lookup
+    constexpr int BELOW = (1 << (20 - B)) - 1, HALF = 1 << (19 - B);
+    const double t = u - __hiloint2double((hi & ~BELOW) | HALF, 0);
+#else
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
     constexpr int TOP = ((1 << B) - 1) << (20 - B), HALF = 1 << (19 - B), EXPC = (1023 + B + 1) << 20;
     const double cB = __hiloint2double((hi & TOP) | HALF | EXPC, 0);
     const double t = fma(m, (double)(2 << B), -cB);
+#endif
     const unsigned a0 = base + j * (unsigned)(SPHW_ROW * 8);
     const double2 c01 = lds_v2f64(a0), c23 = lds_v2f64(a0 + 16u), c45 = lds_v2f64(a0 + 32u);
     if (ESTRIN) {  // 6 FP64, 3 deep (the latency-bound Dopri kernels, whose right-hand side ends on this polynomial)

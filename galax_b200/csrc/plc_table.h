@@ -229,6 +229,22 @@ static double sph_table_fit(const std::vector<SphComp> &cs, double *coef) {
     return worst;
 }
 
+// The rows as the kernels hold them (GX_SPH_ARG_DIFF): coefficient k of the interval [2^e (1 + sub/2^B), ...) times
+// 2^(-k (e - B - 1)), i.e. monomials in u - centre instead of in t = (u - centre) / half-width.  Exact scalings.
+template <int SUB_BITS, int ROW>
+static void sph_rows_for_device(const std::vector<SphComp> &cs, std::vector<double> &rows) {
+#if GX_SPH_ARG_DIFF
+    const int e_lo = sph_e_lo(cs);
+    const int nint = SPH_OCTAVES << SUB_BITS;
+    for (int j = 0; j < nint; ++j) {
+        const int sh = e_lo + (j >> SUB_BITS) - SUB_BITS - 1;
+        for (int k = 1; k < ROW; ++k) rows[(size_t)j * ROW + k] = ldexp(rows[(size_t)j * ROW + k], -k * sh);
+    }
+#else
+    (void)cs; (void)rows;
+#endif
+}
+
 static bool sph_same(const std::vector<SphComp> &a, const std::vector<SphComp> &b) {  // (field by field: the struct has padding)
     if (a.size() != b.size()) return false;
     for (size_t k = 0; k < a.size(); ++k)
@@ -250,6 +266,7 @@ static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_r
     if (cs.empty() || cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
     const std::vector<double> *fitted = nullptr;
+    double fitted_err = 0.0;
     for (size_t k = 0; k < cache.size(); ++k) {
         const Entry &e = cache[k];
         if (sph_same(e.cs, cs)) {
@@ -258,21 +275,25 @@ static const double *sph_table_for(const std::vector<SphComp> &cs, double *max_r
                 return e.dev_ptr;
             }
             fitted = &fits[k];
+            fitted_err = e.max_rel_err;
         }
     }
     if (cache.size() >= SPH_CACHE_MAX || !may_upload) return nullptr;
     std::vector<double> host;
     double worst = 0.0;
     if (fitted) {
-        host = *fitted;
+        host = *fitted;  // (fitted for another device of this process)
+        worst = fitted_err;
     } else {
         host.resize((size_t)SPHW_NINT * SPHW_ROW);
         worst = sph_table_fit<SPHW_SUB_BITS, SPHW_ROW>(cs, host.data());
     }
     double *d = nullptr;
     if (worst < 1e-14) {
-        if (cudaMalloc(&d, host.size() * sizeof(double)) != cudaSuccess) return nullptr;
-        if (cudaMemcpy(d, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        std::vector<double> img = host;
+        sph_rows_for_device<SPHW_SUB_BITS, SPHW_ROW>(cs, img);
+        if (cudaMalloc(&d, img.size() * sizeof(double)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(d, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaFree(d);
             return nullptr;
         }

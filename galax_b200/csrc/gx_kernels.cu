@@ -714,6 +714,13 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 // / 1.2 % / 1.5 % faster than 640 threads at 76-90 registers; 768 and 832 threads measured no better than 640.  The
 // step-by-step kernel (LeapfrogMidpoint, time-dependent parameters) would spill 40-64 bytes at 64 registers and stays
 // at 640.
+#ifndef GX_RHS_FACTORS
+#define GX_RHS_FACTORS 1
+#endif
+// 3: Horner, 4: Estrin form of the table row in the fixed-step kernels
+#ifndef GX_FIXED_SPH_FORM
+#define GX_FIXED_SPH_FORM 3
+#endif
 #ifndef GX_FIXED_TAB_BLOCK
 #define GX_FIXED_TAB_BLOCK 640
 #endif
@@ -746,7 +753,7 @@ template <class C, int SCHEME, bool FWD, bool EPI = false, bool SMALL = false>
 __global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS) k_integrate_fixed(const __grid_constant__ DevPot P, const FixedArgs a) {
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy; every static model in small
     // batches, see k_integrate_fixed_seg), else the PowerLawCutoff / NFW tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 3 : 0;  // 3: the wide format, at the start of dynamic shared memory
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? GX_FIXED_SPH_FORM : 0;  // 3: the wide format, at the start of dynamic shared memory
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     constexpr bool MIX = sph_mix_ok<C>() && !SMALL && SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER;  // (see k_integrate_fixed_seg)
@@ -782,7 +789,7 @@ __global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS
             nqz = fma(pz, hs, qz);
             if (C::is_static) {  // p1 = p0 - (fh h) x: the step is folded into the two scalar factors
                 double fh, fv;
-                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, 3>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                if (MIX && sph_mix_table_step((unsigned long long)n)) gradient_factors<C, false, false, GX_FIXED_SPH_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                 else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                 const double fhh = -fh * hs, fvh = -fv * hs;
                 npx = fma(fhh, nqx, px);
@@ -858,7 +865,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
     // tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = sph_tab_fixed_ok<C>() ? 3 : 0;  // 3: the wide format, at the start of dynamic shared memory
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? GX_FIXED_SPH_FORM : 0;  // 3: the wide format, at the start of dynamic shared memory
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     // MIX (MilkyWayPotential in large batches): the closed forms cost issue slots (169 per warp-step, the kernel's whole
@@ -919,7 +926,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qz = fma(pz, hs, qz);
                     if constexpr (C::is_static) {
                         double fh, fv;
-                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 3>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
+                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_FIXED_SPH_FORM>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
                         else gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
                         if constexpr (MIX) ++gstep;
                         const double fhh = -fh * hs, fvh = -fv * hs;
@@ -945,7 +952,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 double npx, npy, npz;
                 if constexpr (C::is_static) {
                     double fh, fv;
-                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, 3>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_FIXED_SPH_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                     else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                     if constexpr (MIX) ++gstep;
                     const double fhh = -fh * hs, fvh = -fv * hs;
@@ -1085,6 +1092,21 @@ __device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
                                                                                           g2, 0.0, tab_base);
     return Acc3{-g0, -g1, -g2};
 }
+// The same callee returning the two scalar force factors of an axisymmetric model, a = -(f_h x, f_h y, f_v z): it no
+// longer needs q at its end (no copies of the arguments out of the way of its table loads), and the caller forms the
+// products straight into the stage's registers instead of moving three returned doubles there.
+struct Fac2 { double h, v; };
+template <class C, bool IMG>
+__device__ __noinline__ Fac2 accel_fac_static(double x, double y, double z) {
+    unsigned tab_base = 0;
+    constexpr int SPHM = sph_tab_ok<C>() ? 4 : 0;
+    if constexpr (SPHM != 0) tab_base = (unsigned)__cvta_generic_to_shared(dyn_smem());
+    else if constexpr (nfw_tab_ok<C>()) tab_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
+    double fh, fv;
+    gradient_factors<C, (!SPHM && C::is_static && C::kPLC > 0), (!SPHM && nfw_tab_ok<C>()), SPHM>(rhs_pot<C, IMG>(), x, y, z, fh,
+                                                                                                  fv, 0, tab_base);
+    return Fac2{fh, fv};
+}
 // runtime composites may be time dependent (LinearParameter): the callee also receives the physical time
 template <class C, bool IMG>
 __device__ __noinline__ Acc3 accel_call_timed(double t, double x, double y, double z) {
@@ -1094,6 +1116,11 @@ __device__ __noinline__ Acc3 accel_call_timed(double t, double x, double y, doub
 }
 template <class C, bool IMG>
 __device__ __forceinline__ void accel_call(double x, double y, double z, double &ax, double &ay, double &az, double t) {
+    if constexpr (GX_RHS_FACTORS && (C::is_static || C::basic_only)) {
+        const Fac2 f = accel_fac_static<C, IMG>(x, y, z);
+        ax = -__dmul_rn(f.h, x); ay = -__dmul_rn(f.h, y); az = -__dmul_rn(f.v, z);  // (the products gradient<>() forms)
+        return;
+    }
     Acc3 a;
     if constexpr (C::is_static || C::basic_only) a = accel_call_static<C, IMG>(x, y, z);
     else a = accel_call_timed<C, IMG>(t, x, y, z);

@@ -2279,6 +2279,7 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
         const long long waves = (per_sm + maxb - 1) / maxb;
         const long long want = ((per_sm + waves - 1) / waves + 31) / 32 * 32;
         block = (int)(want < 128 ? 128 : (want > maxb ? maxb : want));
+        if (block > maxb) block = maxb;
         dyn = SPHW_BYTES + (size_t)block * per_thread;
         a.stage = per_thread != 0;
         a.stage_off = SPHW_BYTES / 8;

@@ -733,9 +733,6 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 #ifndef GX_FIXED_SEG
 #define GX_FIXED_SEG 1
 #endif
-#ifndef GX_FIXED_SMALL
-#define GX_FIXED_SMALL 0
-#endif
 #ifndef GX_BASIC_MIX
 #define GX_BASIC_MIX 0
 #endif
@@ -756,7 +753,7 @@ __global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS
     constexpr int SPHT = sph_tab_fixed_ok<C>() ? GX_FIXED_SPH_FORM : 0;  // 3: the wide format, at the start of dynamic shared memory
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
-    constexpr bool MIX = sph_mix_ok<C>() && !SMALL && SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER;  // (see k_integrate_fixed_seg)
+    constexpr bool MIX = sph_mix_ok<C>() && SCHEME == GX_SCHEME_SEMI_IMPLICIT_EULER;  // (see k_integrate_fixed_seg)
     unsigned plc_base = 0, nfw_base = 0;
     if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
     if constexpr (SPHT != 0 || MIX) nfw_base = sph_wide_stage(P);
@@ -853,19 +850,19 @@ __global__ void __launch_bounds__(fixed_max_block<C, EPI>(), GX_FIXED_MIN_BLOCKS
 // (fma(j, h, t_s) is the grid time itself) instead of a DADD + 2 DSETP + FSEL per step, the step is a uniform
 // constant-bank operand, and the state is updated in place.  Saves are interpolated exactly as in k_integrate_fixed
 // (same theta, same operations): results are bit-identical to it.
-// SMALL (GX_FIXED_SMALL=1 builds only; measured and NOT shipped: it makes a particle's bits depend on the size of the
-// batch it travels in, and so on how a job is sharded -- the shipped kernels use one arithmetic for every batch size; C1
-// exactly 2.10 ms instead of 1.94): a batch too small to fill the machine (C1's 10^4 particles are one warp on half of the schedulers) is bound by
-// the dependent chain of ONE step, not by issue slots or the shared-memory port: such launches take the combined
-// spherical table for every static model, in its 4-deep Estrin form -- q -> r^2 -> lookup -> p instead of
-// q -> r^2 -> rsqrt -> r -> s -> 1 + s -> rcp -> table log -> shape -> 1/r^3 -> p.
+// SMALL: the instantiation for launches of few warps per scheduler (CTAs of up to 512 threads: C1's 10^4 particles are
+// one warp on half of the schedulers), which are bound by the dependent chain of ONE step: it fetches the table row as
+// soon as r^2 is known, before the disk terms (gradient_factors<..., 5>).  The SAME arithmetic, bit for bit -- a
+// particle's result must not depend on the batch it travels in (an earlier variant that took the table on every step in
+// Estrin form for small batches was measured, 1.94 ms, and not shipped for that reason).
 template <class C, bool FWD, bool SMALL = false, bool EPI = false>
-__global__ void __launch_bounds__(fixed_max_block<C, EPI, true>(), GX_FIXED_MIN_BLOCKS)
+__global__ void __launch_bounds__((SMALL && fixed_max_block<C, EPI, true>() > 512) ? 512 : fixed_max_block<C, EPI, true>(), GX_FIXED_MIN_BLOCKS)
 k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const __grid_constant__ FixedSeg sg) {
     // (runtime composites come here too when none of their parameters depends on time: same loop, gradient<C>())
     // tables in shared memory: the composite's combined spherical table (MW2022, Bovy), else the PowerLawCutoff / NFW
     // tables of round 1 (GX_SPH_TABLE=0 builds)
-    constexpr int SPHT = sph_tab_fixed_ok<C>() ? GX_FIXED_SPH_FORM : 0;  // 3: the wide format, at the start of dynamic shared memory
+    constexpr int SPHF = SMALL ? 5 : GX_FIXED_SPH_FORM;  // Horner; SMALL: the row fetched early
+    constexpr int SPHT = sph_tab_fixed_ok<C>() ? SPHF : 0;  // 3: the wide format, at the start of dynamic shared memory
     constexpr bool STAGED = !SPHT && C::is_static && C::kPLC > 0;
     constexpr bool NFWT = !SPHT && nfw_tab_fixed_ok<C>();
     // MIX (MilkyWayPotential in large batches): the closed forms cost issue slots (169 per warp-step, the kernel's whole
@@ -873,7 +870,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
     // therefore ALTERNATE between the two evaluations of the same force, by the global index of the step (so the
     // trajectory does not depend on where the save times fall, and the general kernel takes the same sequence): both
     // resources work at the same time.
-    constexpr bool MIX = sph_mix_ok<C>() && !SMALL;
+    constexpr bool MIX = sph_mix_ok<C>();
     unsigned plc_base = 0, nfw_base = 0;
     if constexpr (STAGED) { plc_stage<C>(P); plc_base = plc_smem_base<C>(); }
     if constexpr (SPHT != 0 || MIX) nfw_base = sph_wide_stage(P);
@@ -926,7 +923,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                     qz = fma(pz, hs, qz);
                     if constexpr (C::is_static) {
                         double fh, fv;
-                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_FIXED_SPH_FORM>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
+                        if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, SPHF>(P, qx, qy, qz, fh, fv, 0u, nfw_base);
                         else gradient_factors<C, STAGED, NFWT, SPHT>(P, qx, qy, qz, fh, fv, plc_base, nfw_base);
                         if constexpr (MIX) ++gstep;
                         const double fhh = -fh * hs, fvh = -fv * hs;
@@ -952,7 +949,7 @@ k_integrate_fixed_seg(const __grid_constant__ DevPot P, const FixedArgs a, const
                 double npx, npy, npz;
                 if constexpr (C::is_static) {
                     double fh, fv;
-                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, GX_FIXED_SPH_FORM>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
+                    if (MIX && sph_mix_table_step(gstep)) gradient_factors<C, false, false, SPHF>(P, nqx, nqy, nqz, fh, fv, 0u, nfw_base);
                     else gradient_factors<C, STAGED, NFWT, SPHT>(P, nqx, nqy, nqz, fh, fv, plc_base, nfw_base);
                     if constexpr (MIX) ++gstep;
                     const double fhh = -fh * hs, fvh = -fv * hs;
@@ -2165,9 +2162,9 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
         switch (model) {
 #define GX_SEG_STATIC(C_)                                                                                     \
     do {                                                                                                      \
-        if (GX_FIXED_SMALL && small) {                                                                        \
-            if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, GX_FIXED_SMALL != 0, EPI>>(grid, block, dyn, s, D, a, sg);   \
-            else launch_dyn<k_integrate_fixed_seg<C_, false, GX_FIXED_SMALL != 0, EPI>>(grid, block, dyn, s, D, a, sg);      \
+        if (small) {                                                                                          \
+            if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, true, EPI>>(grid, block, dyn, s, D, a, sg);   \
+            else launch_dyn<k_integrate_fixed_seg<C_, false, true, EPI>>(grid, block, dyn, s, D, a, sg);      \
         } else {                                                                                              \
             if (fwd) launch_dyn<k_integrate_fixed_seg<C_, true, false, EPI>>(grid, block, dyn, s, D, a, sg);  \
             else launch_dyn<k_integrate_fixed_seg<C_, false, false, EPI>>(grid, block, dyn, s, D, a, sg);     \
@@ -2176,12 +2173,10 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
         case MODEL_MW: GX_SEG_STATIC(CountsMW); break;
         case MODEL_MW2022: GX_SEG_STATIC(CountsMW2022); break;
         case MODEL_BOVY: GX_SEG_STATIC(CountsBovy); break;
-#undef GX_SEG_STATIC
         default:  // runtime composite, no time-dependent parameter
             if (is_basic_composite(D, model)) {
                 if (D.sph_wide) {  // spherical components in the combined table
-                    if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasicTab, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
-                    else launch_dyn<k_integrate_fixed_seg<CountsBasicTab, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
+                    GX_SEG_STATIC(CountsBasicTab);
                 } else {
                     if (fwd) launch_dyn<k_integrate_fixed_seg<CountsBasic, true, false, EPI>>(grid, block, dyn, s, D, a, sg);
                     else launch_dyn<k_integrate_fixed_seg<CountsBasic, false, false, EPI>>(grid, block, dyn, s, D, a, sg);
@@ -2192,6 +2187,7 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
             }
             break;
         }
+#undef GX_SEG_STATIC
         return;
     }
     // the step-by-step kernel (LeapfrogMidpoint, time-dependent parameters, > 120 runs, GX_SCHEME_GENERAL_KERNEL); the
@@ -2204,11 +2200,9 @@ static void launch_fixed(Model model, const DevPot &D, bool seg_ok, bool small, 
 #define GX_GEN_STATIC(C_)                                                                                          \
     do {                                                                                                           \
         if (scheme == GX_SCHEME_SEMI_IMPLICIT_EULER) {                                                             \
-            if (GX_FIXED_SMALL && small) GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, GX_FIXED_SMALL != 0);           \
-            else GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, false);                                                 \
+            GX_GEN(C_, GX_SCHEME_SEMI_IMPLICIT_EULER, false);                                                      \
         } else {                                                                                                   \
-            if (GX_FIXED_SMALL && small) GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, GX_FIXED_SMALL != 0);             \
-            else GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, false);                                                   \
+            GX_GEN(C_, GX_SCHEME_LEAPFROG_MIDPOINT, false);                                                        \
         }                                                                                                          \
     } while (0)
     switch (model) {
@@ -2291,8 +2285,8 @@ static int fixed_impl(const gx_potential *pot, const double *q0, const double *p
     const int grid = grid_for(N, block);
     cudaStream_t s = (cudaStream_t)stream;
     const bool fwd = dir > 0;
-    // latency-bound launches (fewer than 4 warps per scheduler): the table / Estrin variant of the static models
-    const bool small = GX_SPH_TABLE && GX_FIXED_SMALL && block < 128;
+    // latency-bound launches (at most 4 warps per scheduler): the instantiation that fetches the table row early
+    const bool small = tabled && seg_ok && block <= 512;
     if (with_epi) launch_fixed<true>(model, D, seg_ok, small, scheme, fwd, grid, block, dyn, s, a, sg);
     else launch_fixed<false>(model, D, seg_ok, small, scheme, fwd, grid, block, dyn, s, a, sg);
     return cuda_rc(cudaGetLastError());

@@ -472,6 +472,32 @@ __device__ __forceinline__ double *dyn_smem() {
     extern __shared__ __align__(16) double gx_save_buf[];  // (the one dynamic shared array of the library: table, then save staging)
     return gx_save_buf;
 }
+// The same lookup in two halves (SPH = 5): the three loads, issued as soon as r^2 is known with the row index clamped
+// into the table (always a valid address), and the Horner evaluation after the disk terms, whose arithmetic hides the
+// loads' latency.  Same operations, same bits as sph_wide_eval<false>.  For launches that are bound by the dependent
+// chain of one step (few warps per scheduler): C1's 10^4 particles 1.96 -> 1.68 ms (MilkyWayPotential), 2.01 -> 1.50
+// (MW2022), 1.77 -> 1.31 (Bovy); full machines lose 2 % to the twelve registers the row occupies meanwhile, so the host
+// picks this instantiation for CTAs of up to 512 threads only (the crossover, measured) -- the bits do not depend on it.
+struct SphRow { double2 c01, c23, c45; double t; bool ok; };
+__device__ __forceinline__ SphRow sph_wide_fetch(double u, unsigned base, unsigned j0w) {
+    SphRow r;
+    const int hi = __double2hiint(u);
+    constexpr int B = SPHW_SUB_BITS;
+    const unsigned j = (unsigned)(hi >> (20 - B)) - j0w;
+    r.ok = j < (unsigned)SPHW_NINT;
+    const unsigned jc = min(j, (unsigned)(SPHW_NINT - 1));
+    constexpr int BELOW = (1 << (20 - B)) - 1, HALF = 1 << (19 - B);
+    r.t = u - __hiloint2double((hi & ~BELOW) | HALF, 0);
+    const unsigned a0 = base + jc * (unsigned)(SPHW_ROW * 8);
+    r.c01 = lds_v2f64(a0); r.c23 = lds_v2f64(a0 + 16u); r.c45 = lds_v2f64(a0 + 32u);
+    return r;
+}
+__device__ __forceinline__ double sph_wide_poly(const SphRow &r) {
+    double v = fma(r.c45.y, r.t, r.c45.x);
+    v = fma(v, r.t, r.c23.y); v = fma(v, r.t, r.c23.x);
+    v = fma(v, r.t, r.c01.y); v = fma(v, r.t, r.c01.x);
+    return v;
+}
 // Call once per CTA, by all threads: copies the wide table to the start of dynamic shared memory.
 __device__ __forceinline__ unsigned sph_wide_stage(const DevPot &P) {
     double2 *t2 = reinterpret_cast<double2 *>(dyn_smem());
@@ -573,6 +599,13 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
     const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
     double fxy = 0.0, fz = 0.0, fs = 0.0;
     double zeta2 = 0.0, rz = 0.0;
+    constexpr bool EARLY = GX_SPH_ARG_DIFF && SPH == 5;  // (5: Horner like 3, the row fetched before the disk terms)
+    SphRow row;
+    double r2e = 0.0;
+    if constexpr (EARLY) {
+        r2e = fma(z, z, R2);
+        row = sph_wide_fetch(r2e, nfw_base, P.sph_j0w);
+    }
 #pragma unroll
     for (int i = 0; i < C::kMN; ++i) {
         if (!C::is_static && i >= P.n_mn) break;
@@ -616,8 +649,11 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
                                                     : (P.n_hern + P.n_nfw + P.n_plc + P.n_iso > 0);
     if (any_sph) {
         const double r2 = fma(z, z, R2);  // (R2 carries the TINY that keeps r > 0)
-        if constexpr (SPH != 0) {
-            // SPH: 3 Horner (fixed-step kernels), 4 Estrin (Dopri kernels)
+        if constexpr (EARLY) {
+            fs = sph_wide_poly(row);
+            if (!row.ok) fs = spherical_fallback<C>(&P, r2e);
+        } else if constexpr (SPH != 0) {
+            // SPH: 3 Horner (fixed-step kernels), 4 Estrin (Dopri kernels); 5 (Horner, early loads) is handled above
             if (!sph_wide_eval<SPH == 4>(r2, fs, nfw_base, P.sph_j0w)) fs = spherical_fallback<C>(&P, r2);
         } else {
             fs = spherical_factor<C, PLC_SMEM, NFW_TAB>(P, r2, plc_base, nfw_base);

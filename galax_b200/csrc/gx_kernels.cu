@@ -714,6 +714,13 @@ __device__ __forceinline__ bool finite6(double a, double b, double c, double d, 
 // / 1.2 % / 1.5 % faster than 640 threads at 76-90 registers; 768 and 832 threads measured no better than 640.  The
 // step-by-step kernel (LeapfrogMidpoint, time-dependent parameters) would spill 40-64 bytes at 64 registers and stays
 // at 640.
+// 4: Estrin form of the table row in the Dopri right-hand side; 6: the same with the row fetched as soon as r^2 is known,
+// before the disk terms (the call used to END on the loads' latency): Dopri8 MW 57.1 -> 53.1 ms, MW2022 68.5 -> 66.2, Bovy
+// 58.7 -> 53.5, C2's shape 101.3 -> 98.9; no spill at the 168-register budget (Bovy: 48 bytes outside the stage loop);
+// the same operations, the same bits.
+#ifndef GX_DP_SPH_FORM
+#define GX_DP_SPH_FORM 6
+#endif
 #ifndef GX_RHS_FACTORS
 #define GX_RHS_FACTORS 1
 #endif
@@ -1082,7 +1089,7 @@ __device__ __noinline__ Acc3 accel_call_static(double x, double y, double z) {
     // + MOV per call -- was measured: the extra live register costs the Dopri8 kernel 40 bytes of spills)
     double g0, g1, g2;
     unsigned tab_base = 0;  // the kernel prologue staged the force table (sph_stage / nfw_stage)
-    constexpr int SPHM = sph_tab_ok<C>() ? 4 : 0;  // the wide table at the start of dynamic shared memory, Estrin form
+    constexpr int SPHM = sph_tab_ok<C>() ? GX_DP_SPH_FORM : 0;  // the wide table at the start of dynamic shared memory, Estrin form
     if constexpr (SPHM != 0) tab_base = (unsigned)__cvta_generic_to_shared(dyn_smem());
     else if constexpr (nfw_tab_ok<C>()) tab_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
     gradient<C, (!SPHM && C::is_static && C::kPLC > 0), (!SPHM && nfw_tab_ok<C>()), SPHM>(rhs_pot<C, IMG>(), x, y, z, g0, g1,
@@ -1096,7 +1103,7 @@ struct Fac2 { double h, v; };
 template <class C, bool IMG>
 __device__ __noinline__ Fac2 accel_fac_static(double x, double y, double z) {
     unsigned tab_base = 0;
-    constexpr int SPHM = sph_tab_ok<C>() ? 4 : 0;
+    constexpr int SPHM = sph_tab_ok<C>() ? GX_DP_SPH_FORM : 0;
     if constexpr (SPHM != 0) tab_base = (unsigned)__cvta_generic_to_shared(dyn_smem());
     else if constexpr (nfw_tab_ok<C>()) tab_base = (unsigned)__cvta_generic_to_shared(nfw_smem<C>());
     double fh, fv;

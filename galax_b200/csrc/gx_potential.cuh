@@ -492,7 +492,13 @@ __device__ __forceinline__ SphRow sph_wide_fetch(double u, unsigned base, unsign
     r.c01 = lds_v2f64(a0); r.c23 = lds_v2f64(a0 + 16u); r.c45 = lds_v2f64(a0 + 32u);
     return r;
 }
+template <bool ESTRIN = false>
 __device__ __forceinline__ double sph_wide_poly(const SphRow &r) {
+    if (ESTRIN) {
+        const double t2 = r.t * r.t;
+        const double p01 = fma(r.c01.y, r.t, r.c01.x), p23 = fma(r.c23.y, r.t, r.c23.x), p45 = fma(r.c45.y, r.t, r.c45.x);
+        return fma(fma(p45, t2, p23), t2, p01);
+    }
     double v = fma(r.c45.y, r.t, r.c45.x);
     v = fma(v, r.t, r.c23.y); v = fma(v, r.t, r.c23.x);
     v = fma(v, r.t, r.c01.y); v = fma(v, r.t, r.c01.x);
@@ -599,7 +605,7 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
     const double R2 = fma(y, y, fma(x, x, TINY));  // TINY (2^-1022) is below half an ulp of any normal x^2: same bits
     double fxy = 0.0, fz = 0.0, fs = 0.0;
     double zeta2 = 0.0, rz = 0.0;
-    constexpr bool EARLY = GX_SPH_ARG_DIFF && SPH == 5;  // (5: Horner like 3, the row fetched before the disk terms)
+    constexpr bool EARLY = GX_SPH_ARG_DIFF && (SPH == 5 || SPH == 6);  // (5: Horner like 3, 6: Estrin like 4, the row fetched before the disk terms)
     SphRow row;
     double r2e = 0.0;
     if constexpr (EARLY) {
@@ -650,7 +656,7 @@ __device__ __forceinline__ void gradient_factors(const DevPot &P, double x, doub
     if (any_sph) {
         const double r2 = fma(z, z, R2);  // (R2 carries the TINY that keeps r > 0)
         if constexpr (EARLY) {
-            fs = sph_wide_poly(row);
+            fs = sph_wide_poly<SPH == 6>(row);
             if (!row.ok) fs = spherical_fallback<C>(&P, r2e);
         } else if constexpr (SPH != 0) {
             // SPH: 3 Horner (fixed-step kernels), 4 Estrin (Dopri kernels); 5 (Horner, early loads) is handled above

@@ -703,3 +703,44 @@ def test_runtime_composites_on_the_combined_table():
         ad = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=1e-10, atol=1e-10)).solve(pot, (q0, p0), 0.0, 300.0, saveat=ts)
         qd, pd, *_ = cref.integrate_dopri8(opot, q0, p0, 0.0, 300.0, ts, rtol=1e-10, atol=1e-10)
         assert np.median(np.abs(ad.ys[0] - qd).max(axis=(1, 2))) < 1e-9
+
+
+@pytest.mark.parametrize("name", list(PAIRS))
+def test_orbits_that_leave_the_force_table(name):
+    """The combined spherical table covers r^2 in [2^-8, 2^14) kpc^2 (62 pc .. 128 kpc) for these models; outside it the
+    kernels take the closed forms (spherical_fallback).  Orbits that start inside 62 pc, beyond 128 kpc, and that CROSS
+    either edge, through every instantiation that looks the table up: the small-launch fixed-step kernel (row fetched
+    early with a clamped index), the full-machine one (late loads), the step-by-step kernel and the Dopri8 right-hand
+    side -- against the oracle, and bit for bit among themselves."""
+    cls, ofun = PAIRS[name]
+    pot, opot = cls(), ofun()
+    rng = np.random.default_rng(91)
+    radii = np.array([0.012, 0.03, 0.055, 0.061, 0.064, 0.08, 0.2, 90.0, 120.0, 127.5, 128.5, 140.0, 250.0, 600.0])
+    r = np.repeat(radii, 8)
+    u = rng.standard_normal((r.size, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    q0 = r[:, None] * u
+    vc = np.sqrt(np.abs(np.sum(q0 * op.gradient(opot, q0), axis=1)))  # circular speed from the oracle's own gradient
+    w = rng.standard_normal((r.size, 3)); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    p0 = (vc * rng.uniform(0.3, 1.2, r.size))[:, None] * w  # eccentric: most of them cross an edge of the table
+    dt, t1 = 0.002, 4.0
+    ts = np.array([1.0, 2.5, t1])
+    sol = SIE.solve(pot, (q0, p0), 0.0, t1, dt0=dt, saveat=ts)
+    qr, pr, st, n = cref.integrate_fixed(opot, q0, p0, 0.0, t1, dt, ts)
+    rr = np.linalg.norm(sol.ys[0], axis=-1)
+    assert (rr.min() < 0.0625 < rr.max()) and (rr[r > 100].min() < 128.0 < rr.max())  # both edges really are crossed
+    e = rel_dev(sol.ys, (qr, pr))
+    assert e.max() < 1e-9 and np.median(e) < 1e-12, (e.max(), np.median(e))
+    gen = gd._integrate(pot, q0, p0, 0.0, t1, ts, solver=gd.SemiImplicitEuler(), controller=gd.ConstantStepSize(),
+                        dt0=dt, max_steps=None, general_kernel=True)
+    assert np.array_equal(gen[0], sol.ys[0]) and np.array_equal(gen[1], sol.ys[1])
+    # the same particles inside a launch wide enough for the late-load instantiation (more than 512 threads per CTA)
+    reps = 90_000 // r.size + 1
+    big = SIE.solve(pot, (np.tile(q0, (reps, 1)), np.tile(p0, (reps, 1))), 0.0, t1, dt0=dt, saveat=ts)
+    assert np.array_equal(big.ys[0][: r.size], sol.ys[0]) and np.array_equal(big.ys[1][-r.size:], sol.ys[1])
+    tol = 1e-10
+    ad = gd.OrbitSolver(stepsize_controller=gd.PIDController(rtol=tol, atol=tol))
+    a = ad.solve(pot, (q0, p0), 0.0, t1, saveat=ts)
+    qd, pd, *_ = cref.integrate_dopri8(opot, q0, p0, 0.0, t1, ts, rtol=tol, atol=tol)
+    dq = np.abs(a.ys[0] - qd) / (tol + tol * np.abs(qd))
+    dp = np.abs(a.ys[1] - pd) / (tol + tol * np.abs(pd))
+    assert dq.max() <= 10.0 and dp.max() <= 10.0, (dq.max(), dp.max())
